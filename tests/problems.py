@@ -1,0 +1,72 @@
+"""Problem builders shared by the oracle tests and the GPU parity tests.
+
+Each builder returns plain NumPy data (coords, connectivity, masks, parameters) in the
+reference's conventions, so that the same inputs feed the oracle and the b200 backend.
+"""
+import numpy as np
+
+from oracle import mesher as omesh
+from oracle import quadrature as oquad
+from oracle import elements as oel
+
+
+def readme_source(x):
+    """Source term of examples/miscellaneous/short_example.py:23-33 and
+    tests/test_dicts_as_dofs_user_potential.py:31-34 (x: (..., 2))."""
+    x2 = x - np.array([1.0, 0.5])
+    return 20.0 * (np.sin(10.0 * np.sum(x * x, axis=-1)) - np.cos(10.0 * np.sum(x2 * x2, axis=-1)))
+
+
+def readme_poisson(n):
+    """README / G1 problem on an n x n quad mesh of the unit square.  Dirichlet mask = boundary
+    nodes minus the 4 corners (geometry.psdf_polygon is NaN at corners)."""
+    pts = [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]
+    coords, elems = omesh.structured_mesh((n, n), pts, "quad")
+    gp = oquad.gauss_legendre_nd(2, 2)
+    st = dict(kind="domain", etype="quad4", conn=elems, nf=1, gp=gp,
+              model=dict(name="poisson_potential"))
+    st["model"]["source"] = readme_source(oel.gauss_point_coordinates(st, coords))
+    tol = 1e-9
+    on_b = ((np.abs(coords[:, 0]) < tol) | (np.abs(coords[:, 0] - 1) < tol)
+            | (np.abs(coords[:, 1]) < tol) | (np.abs(coords[:, 1] - 1) < tol))
+    corner = ((np.abs(coords[:, 0]) < tol) | (np.abs(coords[:, 0] - 1) < tol)) & \
+             ((np.abs(coords[:, 1]) < tol) | (np.abs(coords[:, 1] - 1) < tol))
+    mask = (on_b & ~corner)[:, None]
+    return dict(sets=[st], coords=coords, mask=mask, values=np.zeros(mask.shape), nf=1)
+
+
+# --- G2: Cook's membrane, hard-coded mesh of
+# tests/test_user_elem_impl_diff_and_adaptive_load_step.py:31-55 (mesh DATA, not code) ---
+COOK_NODES = np.array([
+    [0., 0.], [48., 44.], [48., 60.], [0., 44.], [12., 11.], [24., 22.], [36., 33.], [6., 5.5], [18., 16.5],
+    [30., 27.5], [42., 38.5], [48., 52.], [48., 48.], [48., 56.], [36., 56.], [24., 52.], [12., 48.], [42., 58.],
+    [30., 54.], [18., 50.], [6., 46.], [0., 33.], [0., 22.], [0., 11.], [0., 38.5], [0., 27.5], [0., 16.5],
+    [0., 5.5], [22.78099159, 39.33936105], [10.25815892, 28.78971905], [40.00000145, 47.99999935],
+    [11.44621914, 36.55774821], [30.81792875, 42.11576444], [7.62152819, 16.21744291], [23.3904958, 30.66968052],
+    [17.11360537, 37.94855463], [10.85218903, 32.67373363], [17.12907946, 25.39485952], [17.12134241, 31.67170708],
+    [8.93984355, 22.50358098], [9.81076409, 13.60872146], [13.46992178, 19.50179049], [38.00000072, 51.99999968],
+    [44.00000072, 49.99999968], [43.00000036, 53.99999984], [33.40896438, 37.55788222], [26.79946017, 40.72756274],
+    [28.39973009, 34.11378137], [38.00000072, 40.49999968], [43.00000036, 44.24999984], [11.72310957, 42.2788741],
+    [23.3904958, 45.66968052], [17.55680268, 43.97427731], [5.72310957, 34.7788741], [5.86155479, 40.38943705],
+    [33.40896438, 49.05788222], [35.70448255, 44.77894095], [5.12907946, 25.39485952], [5.42609452, 30.08686681],
+    [28.39973009, 47.36378137], [3.81076409, 13.60872146], [4.46992178, 19.50179049], [4.90538205, 9.55436073]])
+COOK_ELEMS = np.array([
+    [5, 28, 31, 29, 34, 35, 36, 37, 38], [4, 5, 29, 33, 8, 37, 39, 40, 41], [2, 14, 30, 11, 17, 42, 43, 13, 44],
+    [5, 6, 32, 28, 9, 45, 46, 34, 47], [6, 1, 11, 30, 10, 12, 43, 48, 49], [15, 16, 31, 28, 19, 50, 35, 51, 52],
+    [16, 3, 21, 31, 20, 24, 53, 50, 54], [6, 30, 14, 32, 48, 42, 55, 45, 56], [22, 29, 31, 21, 57, 36, 53, 25, 58],
+    [14, 15, 28, 32, 18, 51, 46, 55, 59], [23, 33, 29, 22, 60, 39, 57, 26, 61], [33, 23, 0, 4, 60, 27, 7, 40, 62]])
+COOK_SURF = np.array([
+    [0, 4, 7], [4, 5, 8], [5, 6, 9], [6, 1, 10], [1, 11, 12], [11, 2, 13], [2, 14, 17],
+    [14, 15, 18], [15, 16, 19], [16, 3, 20], [3, 21, 24], [21, 22, 25], [22, 23, 26], [23, 0, 27]])
+
+
+def cook_g2(q0=20.0, Em=100.0, nu=0.3):
+    """G2 set-up: Q2 plain-strain neo-Hooke + line3 Neumann on x=48."""
+    coords = COOK_NODES
+    mask = np.repeat((np.abs(coords[:, 0]) < 1e-6)[:, None], 2, axis=1)
+    neumann = COOK_SURF[np.all(np.abs(coords[COOK_SURF][:, :, 0] - 48.0) < 1e-6, axis=1)]
+    dom = dict(kind="domain", etype="quad9", conn=COOK_ELEMS, nf=2, gp=oquad.gauss_legendre_nd(2, 4),
+               model=dict(name="neo_hooke", mode="plain strain", youngs_modulus=Em, poisson_ratio=nu))
+    sur = dict(kind="surface", etype="line3", conn=neumann, nf=2, gp=oquad.gauss_legendre_nd(1, 4),
+               model=dict(name="neumann", traction=np.array([0.0, q0])))
+    return dict(sets=[dom, sur], coords=coords, mask=mask, values=np.zeros(mask.shape), nf=2, q0=q0)
