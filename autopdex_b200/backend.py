@@ -1,0 +1,250 @@
+"""Thin object layer over the C ABI: device arrays and the assembly/solve plan.
+
+Everything numerical happens inside libapdx_b200.so; this module marshals NumPy arrays
+into the C structs of include/apdx_b200.h.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, spaces
+
+
+class DeviceArray:
+    """A caller-owned FP64 (or raw byte) buffer in HBM."""
+
+    def __init__(self, n, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
+        self.n = int(n)
+        self.ptr = C.c_void_p()
+        _lib.check(_lib.load().apdx_malloc(C.byref(self.ptr), max(self.n, 1) * self.dtype.itemsize))
+
+    @classmethod
+    def from_host(cls, arr, dtype=np.float64):
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        out = cls(arr.size, dtype)
+        out.upload(arr)
+        return out
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        if arr.size != self.n:
+            raise ValueError("size mismatch: buffer %d, array %d" % (self.n, arr.size))
+        _lib.check(_lib.load().apdx_memcpy_h2d(self.ptr, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.n, dtype=self.dtype)
+        _lib.check(_lib.load().apdx_memcpy_d2h(out.ctypes.data_as(C.c_void_p), self.ptr, self.n * self.dtype.itemsize))
+        return out
+
+    def zero(self):
+        _lib.check(_lib.load().apdx_memset(self.ptr, 0, self.n * self.dtype.itemsize))
+
+    def free(self):
+        if self.ptr:
+            _lib.load().apdx_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class SetSpec:
+    """One connectivity set with its recognised closed-form model.
+
+    kind    'domain' | 'surface' | 'intpoint'
+    model   key of _lib.APDX_MODEL
+    family  'quad_brick' | 'tri_tet'   (domain / surface)
+    conn    (n_rows, nen) integer array
+    gp      (xi, w) reference Gauss rule (domain / surface)
+    params  {name: array}  name in _lib.APDX_PARAM; shapes () | (ncomp,) const,
+            (n_gp,) | (n_gp, ncomp) per Gauss point, (n_rows, n_gp[, ncomp]) per element
+    tables  (N, dNdx, w) per integration point (intpoint)
+    """
+
+    def __init__(self, kind, model, conn, family=None, gp=None, mode=None, params=None, tables=None):
+        self.kind, self.model, self.mode, self.family = kind, model, mode, family
+        self.conn = np.ascontiguousarray(conn)
+        if self.conn.dtype not in (np.int32, np.int64):
+            self.conn = self.conn.astype(np.int64)
+        self.gp = gp
+        self.params = dict(params or {})
+        self.tables = tables
+
+
+class KrylovOptions:
+    def __init__(self, method="cg", rtol=1e-8, atol=0.0, maxiter=0, jacobi=True, check_every=0):
+        if method not in _lib.APDX_KRYLOV:
+            raise ValueError("'solver' must be 'cg' or 'bicgstab' for the b200 backend, got %r" % (method,))
+        self.c = _lib.KrylovOpts(_lib.APDX_KRYLOV[method], int(maxiter), float(rtol), float(atol),
+                                 1 if jacobi else 0, int(check_every))
+
+
+class Plan:
+    """Pattern + index maps + device work space for one mesh / model configuration."""
+
+    def __init__(self, dim, n_nodes, nf, sets, dirichlet_mask=None):
+        lib = _lib.load()
+        if _lib.device_count() < 1:
+            raise RuntimeError("autopdex_b200: no CUDA device visible; the b200 backend has no CPU path")
+        self.dim, self.n_nodes, self.nf = int(dim), int(n_nodes), int(nf)
+        self.sets = list(sets)
+        descs = (_lib.SetDesc * len(self.sets))()
+        keep = []
+        for i, st in enumerate(self.sets):
+            d = descs[i]
+            d.kind = _lib.APDX_KIND[st.kind]
+            d.model = _lib.APDX_MODEL[st.model]
+            d.mode = _lib.APDX_MODE[st.mode]
+            d.n_rows, d.nen = st.conn.shape
+            d.conn_itemsize = st.conn.dtype.itemsize
+            d.conn_h = st.conn.ctypes.data_as(C.c_void_p)
+            if st.kind == "intpoint":
+                d.n_gp, d.dim_ref = 1, dim
+            else:
+                xi, w = st.gp
+                dr = dim if st.kind == "domain" else dim - 1
+                xi = np.asarray(xi, dtype=np.float64).reshape(-1, dr)
+                N, dN = spaces.shape_tables(st.family, d.nen, dr, xi)
+                N, dN = np.ascontiguousarray(N), np.ascontiguousarray(dN)
+                w = np.ascontiguousarray(w, dtype=np.float64)
+                keep += [N, dN, w]
+                d.n_gp, d.dim_ref = xi.shape[0], dr
+                d.shape_n_h = N.ctypes.data_as(C.c_void_p)
+                d.shape_dn_h = dN.ctypes.data_as(C.c_void_p)
+                d.gp_w_h = w.ctypes.data_as(C.c_void_p)
+                st.n_gp = xi.shape[0]
+        mask_p = None
+        if dirichlet_mask is not None:
+            m = np.ascontiguousarray(np.asarray(dirichlet_mask).ravel(), dtype=np.uint8)
+            if m.size != self.n_nodes * self.nf:
+                raise ValueError("'dirichlet dofs' has %d entries, expected %d" % (m.size, self.n_nodes * self.nf))
+            keep.append(m)
+            mask_p = m.ctypes.data_as(C.c_void_p)
+        self.h = C.c_void_p()
+        _lib.check(lib.apdx_plan_create(C.byref(self.h), self.dim, self.n_nodes, self.nf, len(self.sets), descs, mask_p))
+        q = (C.c_int64 * 8)()
+        _lib.check(lib.apdx_plan_query(self.h, q))
+        (self.n_dofs, self.n_free, self.nnz, self.nnz_reduced, self.n_coo, self.f0, self.f1, self.device_bytes) = list(q)
+        for i, st in enumerate(self.sets):
+            for name, val in st.params.items():
+                self.set_param(i, name, val)
+            if st.kind == "intpoint" and st.tables is not None:
+                self.set_intpoint_tables(i, *st.tables)
+
+    # -- life cycle ---------------------------------------------------------------------
+    def destroy(self):
+        if getattr(self, "h", None):
+            _lib.load().apdx_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # -- pattern ------------------------------------------------------------------------
+    def csr(self, reduced=False):
+        n, nnz = (self.n_free, self.nnz_reduced) if reduced else (self.n_dofs, self.nnz)
+        indptr = np.empty(n + 1, dtype=np.int64)
+        indices = np.empty(max(nnz, 1), dtype=np.int64)
+        _lib.check(_lib.load().apdx_plan_get_csr(self.h, int(reduced), indptr.ctypes.data_as(C.c_void_p),
+                                                 indices.ctypes.data_as(C.c_void_p)))
+        return indptr, indices[:nnz]
+
+    def elem_map(self, offset=0, count=None):
+        count = self.n_coo - offset if count is None else count
+        pos = np.empty(count, dtype=np.int64)
+        _lib.check(_lib.load().apdx_plan_get_elem_map(self.h, offset, count, pos.ctypes.data_as(C.c_void_p)))
+        return pos
+
+    # -- run-time fields ------------------------------------------------------------------
+    def set_coords(self, coords):
+        c = np.ascontiguousarray(coords, dtype=np.float64)
+        if c.shape != (self.n_nodes, self.dim):
+            raise ValueError("'node coordinates' must have shape (%d, %d)" % (self.n_nodes, self.dim))
+        _lib.check(_lib.load().apdx_set_coords(self.h, c.ctypes.data_as(C.c_void_p)))
+
+    def set_param(self, iset, name, value):
+        st = self.sets[iset]
+        ncomp = self.nf if name in ("body_load", "traction") else 1
+        v = np.asarray(value, dtype=np.float64)
+        n_rows = st.conn.shape[0]
+        n_gp = 1 if st.kind == "intpoint" else st.n_gp
+        if v.size == ncomp and v.ndim <= 1:
+            layout = "const"
+        elif v.shape in ((n_gp,), (n_gp, ncomp)) and v.size == n_gp * ncomp:
+            layout = "per_gp"
+        elif v.size == n_rows * n_gp * ncomp:
+            layout = "per_row_gp"
+        else:
+            raise ValueError("parameter %r of set %d has shape %s; expected (%d,), (%d,[%d]) or (%d,%d,[%d])"
+                             % (name, iset, v.shape, ncomp, n_gp, ncomp, n_rows, n_gp, ncomp))
+        v = np.ascontiguousarray(v.ravel())
+        _lib.check(_lib.load().apdx_set_param(self.h, iset, _lib.APDX_PARAM[name], _lib.APDX_LAYOUT[layout], ncomp,
+                                              v.ctypes.data_as(C.c_void_p)))
+
+    def set_intpoint_tables(self, iset, N, dNdx, w):
+        N = np.ascontiguousarray(N, dtype=np.float64)
+        dNdx = np.ascontiguousarray(dNdx, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        _lib.check(_lib.load().apdx_set_intpoint_tables(self.h, iset, N.ctypes.data_as(C.c_void_p),
+                                                        dNdx.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p)))
+
+    def set_time_increment(self, dt):
+        _lib.check(_lib.load().apdx_set_time_increment(self.h, float(dt)))
+
+    def set_dofs_n(self, dofs_n):
+        v = np.ascontiguousarray(np.asarray(dofs_n, dtype=np.float64).ravel())
+        _lib.check(_lib.load().apdx_set_dofs_n(self.h, v.ctypes.data_as(C.c_void_p)))
+
+    # -- assembly / solve -----------------------------------------------------------------
+    def assemble(self, dofs_d, want_tangent=True, residual_d=None):
+        rp = residual_d.ptr if residual_d is not None else None
+        _lib.check(_lib.load().apdx_assemble(self.h, dofs_d.ptr, int(want_tangent), rp))
+
+    def values(self, reduced=False):
+        nnz = self.nnz_reduced if reduced else self.nnz
+        out = np.empty(max(nnz, 1), dtype=np.float64)
+        _lib.check(_lib.load().apdx_get_values(self.h, int(reduced), out.ctypes.data_as(C.c_void_p)))
+        return out[:nnz]
+
+    def spmv(self, x_d, y_d):
+        _lib.check(_lib.load().apdx_spmv(self.h, x_d.ptr, y_d.ptr))
+
+    def krylov(self, opts, rhs_d, x_d):
+        it, rr = C.c_int32(0), C.c_double(0.0)
+        _lib.check(_lib.load().apdx_krylov(self.h, C.byref(opts.c), rhs_d.ptr, x_d.ptr, C.byref(it), C.byref(rr)))
+        return it.value, rr.value
+
+    def linear_step(self, opts, dofs_d, dirichlet_values_d, delta_d):
+        it = C.c_int32(0)
+        dv = dirichlet_values_d.ptr if dirichlet_values_d is not None else None
+        _lib.check(_lib.load().apdx_linear_step(self.h, C.byref(opts.c), dofs_d.ptr, dv, delta_d.ptr, C.byref(it)))
+        return it.value
+
+    def newton(self, opts, dofs_d, dirichlet_values_d, newton_tol=1e-8, maxiter=30, damping=1.0):
+        it, rn, dv = C.c_int32(0), C.c_double(0.0), C.c_int32(0)
+        dvals = dirichlet_values_d.ptr if dirichlet_values_d is not None else None
+        _lib.check(_lib.load().apdx_newton(self.h, C.byref(opts.c), dofs_d.ptr, dvals, float(newton_tol), int(maxiter),
+                                           float(damping), C.byref(it), C.byref(rn), C.byref(dv)))
+        return it.value, rn.value, bool(dv.value)
+
+    def stats(self):
+        out = (C.c_double * 8)()
+        _lib.check(_lib.load().apdx_plan_stats(self.h, out))
+        keys = ("assembly_tangent_ms", "assembly_residual_ms", "krylov_ms", "krylov_iters", "spmv_launches",
+                "total_ms", "kernel_launches")
+        return dict(zip(keys, list(out)[:7]))
+
+    def set_partition(self, owned_dof_begin, owned_dof_end, rank_lo=-1, rank_hi=-1):
+        _lib.check(_lib.load().apdx_plan_set_partition(self.h, int(owned_dof_begin), int(owned_dof_end), int(rank_lo),
+                                                       int(rank_hi)))
+        q = (C.c_int64 * 8)()
+        _lib.check(_lib.load().apdx_plan_query(self.h, q))
+        self.f0, self.f1 = q[5], q[6]

@@ -1,0 +1,597 @@
+// C ABI of libapdx_b200.so: plan life cycle, run-time fields, assembly, the Newton hot loop.
+// See include/apdx_b200.h for the contract and the reference functions each entry replaces.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+namespace apdx {
+
+size_t g_plan_bytes = 0;
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- small kernels of the Newton loop (utility.mask_op semantics, utility.py:283-368) --------
+__global__ void k_impose(double *__restrict__ dofs, const uint8_t *__restrict__ mask,
+                         const double *__restrict__ vals, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && mask[i]) dofs[i] = vals[i];
+}
+__global__ void k_rhs_reduced(const double *__restrict__ residual, const int32_t *__restrict__ free_list,
+                              int64_t n_free, double *__restrict__ rhs, double *__restrict__ x0) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_free) return;
+  rhs[q] = -residual[free_list[q]];  // solver.py:611, :1514-1515
+  x0[q] = 0.0;
+}
+__global__ void k_newton_update(double *__restrict__ dofs, const int32_t *__restrict__ free_list,
+                                const double *__restrict__ x, double damping, int64_t n_free) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n_free) dofs[free_list[q]] += damping * x[q];  // solver.py:881-885
+}
+__global__ void k_mixed_vector(const double *__restrict__ dofs, const int32_t *__restrict__ free_id,
+                               const double *__restrict__ x, int64_t n, double *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t q = free_id[i];
+  out[i] = q >= 0 ? x[q] : dofs[i];  // solver.py:648-656
+}
+constexpr int NORM_GRID = 592;
+__global__ void __launch_bounds__(256) k_norm_partial(const double *__restrict__ residual,
+                                                      const int32_t *__restrict__ free_list, int64_t q0, int64_t q1,
+                                                      double *__restrict__ partial) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (int64_t q = q0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += (int64_t)gridDim.x * blockDim.x) {
+    double v = residual[free_list[q]];
+    acc += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sh[w];
+    partial[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(256) k_norm_final(const double *__restrict__ partial, int n, double *out) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sh[w];
+    *out = s;
+  }
+}
+__global__ void k_lower_bound(const int32_t *__restrict__ sorted, int64_t n, int64_t key, int64_t *out) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (sorted[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  *out = lo;
+}
+
+static inline unsigned g1(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+static int assemble_internal(apdx_plan *pl, const double *dofs_d, int tangent_flags, double *residual_d) {
+  APDX_CHECK(launch_element_kernels(pl, dofs_d, tangent_flags != 0));
+  APDX_CHECK(launch_gather_reduce(pl, tangent_flags, residual_d));
+  if (tangent_flags) pl->have_values = true;
+  return APDX_OK;
+}
+
+// squared 2-norm of residual[free] over the owned range (solver.py:899-903), all ranks
+static int residual_norm(apdx_plan *pl, const double *residual_d, double *out) {
+  cudaStream_t s = pl->stream;
+  double *scratch = pl->kw.partial.p;
+  k_norm_partial<<<NORM_GRID, 256, 0, s>>>(residual_d, pl->free_list.p, pl->f0, pl->f1, scratch);
+  k_norm_final<<<1, 256, 0, s>>>(scratch, NORM_GRID, scratch + NORM_GRID);
+  pl->stats.kernel_launches += 2;
+  if (comm_active()) APDX_CHECK(comm_allreduce_sum(scratch + NORM_GRID, 1, s));
+  APDX_CUDA(cudaMemcpyAsync(pl->pinned + 40, scratch + NORM_GRID, sizeof(double), cudaMemcpyDeviceToHost, s));
+  APDX_CUDA(cudaStreamSynchronize(s));
+  *out = pl->pinned[40];
+  return APDX_OK;
+}
+
+static int ensure_newton_buffers(apdx_plan *pl) {
+  if (!pl->residual.p) {
+    APDX_CHECK(pl->residual.alloc(pl->n_dofs));
+    APDX_CHECK(pl->rhs_red.alloc(pl->n_free));
+    APDX_CHECK(pl->x_red.alloc(pl->n_free));
+  }
+  return krylov_alloc(pl);
+}
+
+static float elapsed(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+// one linear step on dofs (already holding the imposed Dirichlet values): assemble, solve; x_red = delta
+static int linear_step_internal(apdx_plan *pl, const apdx_krylov_opts *opts, const double *dofs_d, int32_t *kiters) {
+  cudaStream_t s = pl->stream;
+  APDX_CUDA(cudaEventRecord(pl->ev[0], s));
+  APDX_CHECK(assemble_internal(pl, dofs_d, 2, pl->residual.p));
+  k_rhs_reduced<<<g1(pl->n_free), 256, 0, s>>>(pl->residual.p, pl->free_list.p, pl->n_free, pl->rhs_red.p, pl->x_red.p);
+  pl->stats.kernel_launches += 1;
+  APDX_CUDA(cudaEventRecord(pl->ev[1], s));
+  int32_t it = 0;
+  double rr = 0;
+  APDX_CHECK(krylov_solve(pl, opts, pl->rhs_red.p, pl->x_red.p, &it, &rr));
+  APDX_CUDA(cudaEventRecord(pl->ev[2], s));
+  APDX_CUDA(cudaEventSynchronize(pl->ev[2]));
+  pl->stats.asm_tangent_ms += elapsed(pl->ev[0], pl->ev[1]);
+  pl->stats.krylov_ms += elapsed(pl->ev[1], pl->ev[2]);
+  if (kiters) *kiters = it;
+  return APDX_OK;
+}
+
+}  // namespace apdx
+
+using namespace apdx;
+
+extern "C" {
+
+int apdx_abi_version(void) { return APDX_ABI_VERSION; }
+const char *apdx_last_error(void) { return g_err; }
+
+int apdx_device_count(int *count) {
+  APDX_CUDA(cudaGetDeviceCount(count));
+  return APDX_OK;
+}
+int apdx_set_device(int device) {
+  APDX_CUDA(cudaSetDevice(device));
+  return APDX_OK;
+}
+int apdx_malloc(void **ptr_d, size_t bytes) {
+  APDX_CUDA(cudaMalloc(ptr_d, bytes ? bytes : 8));
+  return APDX_OK;
+}
+int apdx_free(void *ptr_d) {
+  APDX_CUDA(cudaFree(ptr_d));
+  return APDX_OK;
+}
+int apdx_host_alloc(void **ptr_h, size_t bytes) {
+  APDX_CUDA(cudaMallocHost(ptr_h, bytes ? bytes : 8));
+  return APDX_OK;
+}
+int apdx_host_free(void *ptr_h) {
+  APDX_CUDA(cudaFreeHost(ptr_h));
+  return APDX_OK;
+}
+int apdx_memcpy_h2d(void *dst_d, const void *src_h, size_t bytes) {
+  APDX_CUDA(cudaMemcpy(dst_d, src_h, bytes, cudaMemcpyHostToDevice));
+  return APDX_OK;
+}
+int apdx_memcpy_d2h(void *dst_h, const void *src_d, size_t bytes) {
+  APDX_CUDA(cudaMemcpy(dst_h, src_d, bytes, cudaMemcpyDeviceToHost));
+  return APDX_OK;
+}
+int apdx_memset(void *dst_d, int value, size_t bytes) {
+  APDX_CUDA(cudaMemset(dst_d, value, bytes));
+  return APDX_OK;
+}
+int apdx_synchronize(void) {
+  APDX_CUDA(cudaDeviceSynchronize());
+  return APDX_OK;
+}
+int apdx_mem_info(size_t *free_bytes, size_t *total_bytes) {
+  APDX_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+  return APDX_OK;
+}
+
+// ---- plan ------------------------------------------------------------------------------------------
+static int validate_set(const apdx_set_desc &d, int dim, int nf, int idx) {
+  APDX_REQUIRE(d.kind >= APDX_SET_DOMAIN && d.kind <= APDX_SET_INTPOINT, APDX_ERR_INVALID, "set %d: bad kind %d", idx, d.kind);
+  APDX_REQUIRE(d.model >= APDX_MODEL_POISSON_POTENTIAL && d.model <= APDX_MODEL_CAPACITY, APDX_ERR_UNSUPPORTED,
+               "set %d: model id %d is not a supported closed-form model", idx, d.model);
+  APDX_REQUIRE(d.nen >= 2 && d.nen <= 27, APDX_ERR_UNSUPPORTED, "set %d: %d nodes per element not supported", idx, d.nen);
+  APDX_REQUIRE(d.n_rows >= 0, APDX_ERR_INVALID, "set %d: negative row count", idx);
+  APDX_REQUIRE(d.conn_itemsize == 4 || d.conn_itemsize == 8, APDX_ERR_INVALID, "set %d: connectivity itemsize must be 4 or 8", idx);
+  APDX_REQUIRE(d.conn_h || d.n_rows == 0, APDX_ERR_INVALID, "set %d: connectivity pointer is NULL", idx);
+  const bool scalar = d.model == APDX_MODEL_POISSON_POTENTIAL || d.model == APDX_MODEL_POISSON_WEAK || d.model == APDX_MODEL_CAPACITY;
+  const bool vector = d.model == APDX_MODEL_LINEAR_ELASTICITY || d.model == APDX_MODEL_NEO_HOOKE;
+  if (scalar) APDX_REQUIRE(nf == 1, APDX_ERR_UNSUPPORTED, "set %d: scalar model needs one dof per node, got %d", idx, nf);
+  if (vector) APDX_REQUIRE(nf == dim, APDX_ERR_UNSUPPORTED, "set %d: elasticity model needs nf == dim (%d), got %d", idx, dim, nf);
+  if (vector) {
+    bool ok = (dim == 3 && d.mode == APDX_MODE_3D) ||
+              (dim == 2 && (d.mode == APDX_MODE_PLAIN_STRAIN || (d.mode == APDX_MODE_PLAIN_STRESS && d.model == APDX_MODEL_LINEAR_ELASTICITY)));
+    APDX_REQUIRE(ok, APDX_ERR_UNSUPPORTED, "set %d: elasticity mode %d not available for dim %d / this model", idx, d.mode, dim);
+  }
+  if (d.kind == APDX_SET_INTPOINT) {
+    APDX_REQUIRE(d.n_gp == 1, APDX_ERR_INVALID, "set %d: integration-point sets have n_gp = 1", idx);
+  } else {
+    APDX_REQUIRE(d.n_gp >= 1 && d.n_gp <= 64, APDX_ERR_UNSUPPORTED, "set %d: %d Gauss points not supported", idx, d.n_gp);
+    APDX_REQUIRE(d.shape_n_h && d.shape_dn_h && d.gp_w_h, APDX_ERR_INVALID, "set %d: shape tables missing", idx);
+    int want = d.kind == APDX_SET_DOMAIN ? dim : dim - 1;
+    APDX_REQUIRE(d.dim_ref == want, APDX_ERR_INVALID, "set %d: reference dimension %d, expected %d", idx, d.dim_ref, want);
+    if (d.kind == APDX_SET_SURFACE)
+      APDX_REQUIRE(d.model == APDX_MODEL_NEUMANN, APDX_ERR_UNSUPPORTED, "set %d: surface elements support neumann_weak only", idx);
+    if (d.kind == APDX_SET_DOMAIN)
+      APDX_REQUIRE(d.model != APDX_MODEL_CAPACITY && d.model != APDX_MODEL_NEUMANN, APDX_ERR_UNSUPPORTED,
+                   "set %d: this weak form is only available in 'sparse' / surface sets", idx);
+  }
+  return APDX_OK;
+}
+
+int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf, int32_t n_sets,
+                     const apdx_set_desc *sets, const uint8_t *dirichlet_mask_h) {
+  APDX_REQUIRE(plan && sets, APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(dim == 2 || dim == 3, APDX_ERR_UNSUPPORTED, "dim %d not supported", dim);
+  APDX_REQUIRE(nf == 1 || nf == dim, APDX_ERR_UNSUPPORTED, "nf=%d with dim=%d not supported", nf, dim);
+  APDX_REQUIRE(n_nodes > 0 && n_sets > 0, APDX_ERR_INVALID, "empty problem");
+  APDX_REQUIRE(n_nodes * nf < (1ll << 31), APDX_ERR_UNSUPPORTED, "more than 2^31 dofs per plan: partition the mesh");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  APDX_REQUIRE(ce == cudaSuccess && ndev > 0, APDX_ERR_CUDA,
+               "no CUDA device available (%s): the b200 backend has no CPU path", cudaGetErrorString(ce));
+  for (int i = 0; i < n_sets; ++i) APDX_CHECK(validate_set(sets[i], dim, nf, i));
+
+  apdx_plan *pl = new (std::nothrow) apdx_plan();
+  APDX_REQUIRE(pl, APDX_ERR_NOMEM, "out of host memory");
+  int rc = APDX_OK;
+  auto fail = [&](int code) {
+    apdx_plan_destroy(pl);
+    return code;
+  };
+  pl->dim = dim; pl->nf = nf; pl->n_sets = n_sets; pl->n_nodes = n_nodes; pl->n_dofs = n_nodes * nf;
+  if (cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    return fail(APDX_ERR_CUDA);
+  }
+  for (auto &e : pl->ev) cudaEventCreate(&e);
+  if (cudaMallocHost((void **)&pl->pinned, 64 * sizeof(double)) != cudaSuccess) {
+    set_error("cudaMallocHost failed");
+    return fail(APDX_ERR_CUDA);
+  }
+  pl->sets.resize(n_sets);
+  int64_t coo = 0, res = 0;
+  for (int i = 0; i < n_sets; ++i) {
+    SetData &st = pl->sets[i];
+    st.d = sets[i];
+    st.ndof_e = st.d.nen * nf;
+    st.coo_offset = coo;
+    st.res_offset = res;
+    coo += st.d.n_rows * (int64_t)st.ndof_e * st.ndof_e;
+    res += st.d.n_rows * (int64_t)st.ndof_e;
+    const int64_t cn = st.d.n_rows * st.d.nen;
+    if (cn > 0) {
+      if ((rc = st.conn.alloc(cn)) != APDX_OK) return fail(rc);
+      std::vector<int32_t> tmp;
+      const int32_t *src32 = nullptr;
+      if (st.d.conn_itemsize == 8) {
+        tmp.resize(cn);
+        const int64_t *c64 = static_cast<const int64_t *>(st.d.conn_h);
+        for (int64_t k = 0; k < cn; ++k) tmp[k] = (int32_t)c64[k];
+        src32 = tmp.data();
+      } else {
+        src32 = static_cast<const int32_t *>(st.d.conn_h);
+      }
+      for (int64_t k = 0; k < cn; ++k)
+        if (src32[k] < 0 || src32[k] >= n_nodes) {
+          set_error("set %d: node id %d out of range [0,%lld)", i, src32[k], (long long)n_nodes);
+          return fail(APDX_ERR_INVALID);
+        }
+      if (cudaMemcpy(st.conn.p, src32, cn * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("connectivity upload failed");
+        return fail(APDX_ERR_CUDA);
+      }
+    }
+    if (st.d.kind != APDX_SET_INTPOINT) {
+      size_t a = (size_t)st.d.n_gp * st.d.nen, b = a * st.d.dim_ref, c = st.d.n_gp;
+      if ((rc = st.shape_n.alloc(a)) != APDX_OK || (rc = st.shape_dn.alloc(b)) != APDX_OK ||
+          (rc = st.gp_w.alloc(c)) != APDX_OK)
+        return fail(rc);
+      cudaMemcpy(st.shape_n.p, st.d.shape_n_h, a * 8, cudaMemcpyHostToDevice);
+      cudaMemcpy(st.shape_dn.p, st.d.shape_dn_h, b * 8, cudaMemcpyHostToDevice);
+      cudaMemcpy(st.gp_w.p, st.d.gp_w_h, c * 8, cudaMemcpyHostToDevice);
+    }
+    st.d.conn_h = nullptr; st.d.shape_n_h = st.d.shape_dn_h = st.d.gp_w_h = nullptr;
+  }
+  pl->n_coo = coo;
+  pl->n_res = res;
+  if (coo == 0) {
+    set_error("no element in any set");
+    return fail(APDX_ERR_INVALID);
+  }
+  if ((rc = build_pattern(pl, dirichlet_mask_h)) != APDX_OK) return fail(rc);
+  if ((rc = pl->ke.alloc(pl->n_coo)) != APDX_OK || (rc = pl->re.alloc(pl->n_res)) != APDX_OK ||
+      (rc = pl->vals.alloc(pl->nnz)) != APDX_OK || (rc = pl->red_vals.alloc(pl->nnz_red > 0 ? pl->nnz_red : 1)) != APDX_OK)
+    return fail(rc);
+  // surface sets never write their (all-zero) tangent block: zero the stream once
+  cudaMemsetAsync(pl->ke.p, 0, pl->ke.bytes(), pl->stream);
+  cudaMemsetAsync(pl->re.p, 0, pl->re.bytes(), pl->stream);
+  cudaStreamSynchronize(pl->stream);
+  pl->owned_begin = 0; pl->owned_end = pl->n_dofs; pl->f0 = 0; pl->f1 = pl->n_free;
+  if (cudaGetLastError() != cudaSuccess) {
+    set_error("CUDA error during plan creation");
+    return fail(APDX_ERR_CUDA);
+  }
+  *plan = pl;
+  return APDX_OK;
+}
+
+int apdx_plan_destroy(apdx_plan *pl) {
+  if (!pl) return APDX_OK;
+  if (pl->stream) cudaStreamSynchronize(pl->stream);
+  for (auto &st : pl->sets) {
+    st.conn.release(); st.shape_n.release(); st.shape_dn.release(); st.gp_w.release();
+    st.ip_n.release(); st.ip_dndx.release(); st.ip_w.release();
+    for (auto &p : st.params) p.release();
+  }
+  pl->coords.release(); pl->dofs_n.release(); pl->mask.release(); pl->free_id.release(); pl->free_list.release();
+  pl->row_ptr.release(); pl->col.release(); pl->elem_map.release(); pl->perm.release(); pl->seg_ptr.release();
+  pl->rperm.release(); pl->rseg_ptr.release(); pl->red_row_ptr.release(); pl->red_col.release();
+  pl->red2full.release(); pl->red_diag.release(); pl->ke.release(); pl->re.release(); pl->vals.release();
+  pl->red_vals.release(); pl->residual.release(); pl->rhs_red.release(); pl->x_red.release(); pl->dofs_trial.release();
+  KrylovWork &k = pl->kw;
+  k.r.release(); k.p.release(); k.q.release(); k.z.release(); k.s.release(); k.t.release(); k.phat.release();
+  k.shat.release(); k.r0.release(); k.minv.release(); k.partial.release(); k.scal.release(); k.ticket.release();
+  k.flags.release();
+  if (pl->pinned) cudaFreeHost(pl->pinned);
+  for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
+  if (pl->stream) cudaStreamDestroy(pl->stream);
+  delete pl;
+  return APDX_OK;
+}
+
+int apdx_plan_query(const apdx_plan *pl, int64_t out[8]) {
+  APDX_REQUIRE(pl && out, APDX_ERR_INVALID, "NULL argument");
+  out[0] = pl->n_dofs; out[1] = pl->n_free; out[2] = pl->nnz; out[3] = pl->nnz_red; out[4] = pl->n_coo;
+  out[5] = pl->f0; out[6] = pl->f1; out[7] = (int64_t)g_plan_bytes;
+  return APDX_OK;
+}
+
+static int copy_i32_as_i64(const int32_t *src_d, int64_t n, int64_t *dst_h) {
+  std::vector<int32_t> tmp((size_t)n);
+  APDX_CUDA(cudaMemcpy(tmp.data(), src_d, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) dst_h[i] = tmp[i];
+  return APDX_OK;
+}
+
+int apdx_plan_get_csr(const apdx_plan *pl, int reduced, int64_t *indptr_h, int64_t *indices_h) {
+  APDX_REQUIRE(pl && indptr_h && indices_h, APDX_ERR_INVALID, "NULL argument");
+  if (reduced) {
+    APDX_CHECK(copy_i32_as_i64(pl->red_row_ptr.p, pl->n_free + 1, indptr_h));
+    if (pl->nnz_red > 0) APDX_CHECK(copy_i32_as_i64(pl->red_col.p, pl->nnz_red, indices_h));
+  } else {
+    APDX_CHECK(copy_i32_as_i64(pl->row_ptr.p, pl->n_dofs + 1, indptr_h));
+    APDX_CHECK(copy_i32_as_i64(pl->col.p, pl->nnz, indices_h));
+  }
+  return APDX_OK;
+}
+
+int apdx_plan_get_elem_map(const apdx_plan *pl, int64_t offset, int64_t count, int64_t *pos_h) {
+  APDX_REQUIRE(pl && pos_h, APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(offset >= 0 && count >= 0 && offset + count <= pl->n_coo, APDX_ERR_INVALID, "range outside the COO stream");
+  return copy_i32_as_i64(pl->elem_map.p + offset, count, pos_h);
+}
+
+// ---- fields ------------------------------------------------------------------------------------------
+int apdx_set_coords(apdx_plan *pl, const double *coords_h) {
+  APDX_REQUIRE(pl && coords_h, APDX_ERR_INVALID, "NULL argument");
+  if (!pl->coords.p) APDX_CHECK(pl->coords.alloc(pl->n_nodes * pl->dim));
+  APDX_CUDA(cudaMemcpyAsync(pl->coords.p, coords_h, pl->coords.bytes(), cudaMemcpyHostToDevice, pl->stream));
+  APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  pl->have_coords = true;
+  return APDX_OK;
+}
+
+int apdx_set_param(apdx_plan *pl, int32_t set, int32_t param, int32_t layout, int32_t ncomp, const double *values_h) {
+  APDX_REQUIRE(pl && values_h, APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(set >= 0 && set < pl->n_sets, APDX_ERR_INVALID, "set index %d out of range", set);
+  APDX_REQUIRE(param >= 0 && param < APDX_PARAM_COUNT, APDX_ERR_INVALID, "parameter id %d out of range", param);
+  SetData &st = pl->sets[set];
+  const bool vec = (param == APDX_PARAM_BODY_LOAD || param == APDX_PARAM_TRACTION);
+  APDX_REQUIRE(ncomp == (vec ? pl->nf : 1), APDX_ERR_INVALID, "parameter %d expects %d components", param, vec ? pl->nf : 1);
+  size_t count;
+  ParamView v{};
+  v.ncomp = ncomp;
+  if (layout == APDX_LAYOUT_CONST) { count = ncomp; v.s_row = 0; v.s_gp = 0; }
+  else if (layout == APDX_LAYOUT_PER_GP) { count = (size_t)st.d.n_gp * ncomp; v.s_row = 0; v.s_gp = ncomp; }
+  else if (layout == APDX_LAYOUT_PER_ROW_GP) { count = (size_t)st.d.n_rows * st.d.n_gp * ncomp; v.s_row = (int64_t)st.d.n_gp * ncomp; v.s_gp = ncomp; }
+  else APDX_REQUIRE(false, APDX_ERR_INVALID, "bad layout %d", layout);
+  if (st.params[param].n != count) APDX_CHECK(st.params[param].alloc(count));
+  APDX_CUDA(cudaMemcpyAsync(st.params[param].p, values_h, count * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+  APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  v.p = st.params[param].p;
+  st.pview[param] = v;
+  return APDX_OK;
+}
+
+int apdx_set_intpoint_tables(apdx_plan *pl, int32_t set, const double *n_h, const double *dndx_h, const double *w_h) {
+  APDX_REQUIRE(pl && n_h && dndx_h && w_h, APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(set >= 0 && set < pl->n_sets, APDX_ERR_INVALID, "set index %d out of range", set);
+  SetData &st = pl->sets[set];
+  APDX_REQUIRE(st.d.kind == APDX_SET_INTPOINT, APDX_ERR_INVALID, "set %d is not an integration-point set", set);
+  size_t a = (size_t)st.d.n_rows * st.d.nen;
+  if (!st.ip_n.p) {
+    APDX_CHECK(st.ip_n.alloc(a));
+    APDX_CHECK(st.ip_dndx.alloc(a * pl->dim));
+    APDX_CHECK(st.ip_w.alloc(st.d.n_rows));
+  }
+  APDX_CUDA(cudaMemcpyAsync(st.ip_n.p, n_h, a * 8, cudaMemcpyHostToDevice, pl->stream));
+  APDX_CUDA(cudaMemcpyAsync(st.ip_dndx.p, dndx_h, a * pl->dim * 8, cudaMemcpyHostToDevice, pl->stream));
+  APDX_CUDA(cudaMemcpyAsync(st.ip_w.p, w_h, st.d.n_rows * 8, cudaMemcpyHostToDevice, pl->stream));
+  APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  return APDX_OK;
+}
+
+int apdx_set_time_increment(apdx_plan *pl, double dt) {
+  APDX_REQUIRE(pl && dt != 0.0, APDX_ERR_INVALID, "bad time increment");
+  pl->time_increment = dt;
+  return APDX_OK;
+}
+
+int apdx_set_dofs_n(apdx_plan *pl, const double *dofs_n_h) {
+  APDX_REQUIRE(pl && dofs_n_h, APDX_ERR_INVALID, "NULL argument");
+  if (!pl->dofs_n.p) APDX_CHECK(pl->dofs_n.alloc(pl->n_dofs));
+  APDX_CUDA(cudaMemcpyAsync(pl->dofs_n.p, dofs_n_h, pl->dofs_n.bytes(), cudaMemcpyHostToDevice, pl->stream));
+  APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  return APDX_OK;
+}
+
+// ---- assembly / linear algebra ---------------------------------------------------------------------------
+int apdx_assemble(apdx_plan *pl, const double *dofs_d, int want_tangent, double *residual_d) {
+  APDX_REQUIRE(pl && dofs_d, APDX_ERR_INVALID, "NULL argument");
+  APDX_CHECK(assemble_internal(pl, dofs_d, want_tangent ? 3 : 0, residual_d));
+  APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  return APDX_OK;
+}
+
+int apdx_get_values(const apdx_plan *pl, int reduced, double *values_h) {
+  APDX_REQUIRE(pl && values_h, APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
+  if (reduced) {
+    if (pl->nnz_red > 0) APDX_CUDA(cudaMemcpy(values_h, pl->red_vals.p, pl->nnz_red * 8, cudaMemcpyDeviceToHost));
+  } else {
+    APDX_CUDA(cudaMemcpy(values_h, pl->vals.p, pl->nnz * 8, cudaMemcpyDeviceToHost));
+  }
+  return APDX_OK;
+}
+
+int apdx_spmv(apdx_plan *pl, const double *x_d, double *y_d) {
+  APDX_REQUIRE(pl && x_d && y_d, APDX_ERR_INVALID, "NULL argument");
+  APDX_CHECK(spmv_reduced(pl, x_d, y_d));
+  APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  return APDX_OK;
+}
+
+int apdx_krylov(apdx_plan *pl, const apdx_krylov_opts *opts, const double *rhs_d, double *x_d, int32_t *iters,
+                double *relres) {
+  APDX_REQUIRE(pl && opts && rhs_d && x_d, APDX_ERR_INVALID, "NULL argument");
+  cudaStream_t s = pl->stream;
+  APDX_CHECK(krylov_alloc(pl));
+  APDX_CUDA(cudaEventRecord(pl->ev[1], s));
+  APDX_CHECK(krylov_solve(pl, opts, rhs_d, x_d, iters, relres));
+  APDX_CUDA(cudaEventRecord(pl->ev[2], s));
+  APDX_CUDA(cudaEventSynchronize(pl->ev[2]));
+  pl->stats.krylov_ms += elapsed(pl->ev[1], pl->ev[2]);
+  return APDX_OK;
+}
+
+// ---- Newton ---------------------------------------------------------------------------------------------------
+int apdx_linear_step(apdx_plan *pl, const apdx_krylov_opts *opts, const double *dofs_d, const double *dirichlet_values_d,
+                     double *delta_d, int32_t *krylov_iters) {
+  APDX_REQUIRE(pl && opts && dofs_d && delta_d, APDX_ERR_INVALID, "NULL argument");
+  APDX_CHECK(ensure_newton_buffers(pl));
+  if (!pl->dofs_trial.p) APDX_CHECK(pl->dofs_trial.alloc(pl->n_dofs));
+  cudaStream_t s = pl->stream;
+  pl->stats = Stats();
+  APDX_CUDA(cudaMemcpyAsync(pl->dofs_trial.p, dofs_d, pl->n_dofs * 8, cudaMemcpyDeviceToDevice, s));
+  if (dirichlet_values_d) {
+    k_impose<<<g1(pl->n_dofs), 256, 0, s>>>(pl->dofs_trial.p, pl->mask.p, dirichlet_values_d, pl->n_dofs);  // solver.py:586-604
+    pl->stats.kernel_launches += 1;
+  }
+  APDX_CHECK(linear_step_internal(pl, opts, pl->dofs_trial.p, krylov_iters));
+  k_mixed_vector<<<g1(pl->n_dofs), 256, 0, s>>>(pl->dofs_trial.p, pl->free_id.p, pl->x_red.p, pl->n_dofs, delta_d);
+  pl->stats.kernel_launches += 1;
+  APDX_CUDA(cudaStreamSynchronize(s));
+  pl->stats.total_ms = pl->stats.asm_tangent_ms + pl->stats.krylov_ms;
+  return APDX_OK;
+}
+
+int apdx_newton(apdx_plan *pl, const apdx_krylov_opts *opts, double *dofs_d, const double *dirichlet_values_d,
+                double newton_tol, int32_t maxiter, double damping, int32_t *iters, double *res_norm, int32_t *diverged) {
+  APDX_REQUIRE(pl && opts && dofs_d && iters && res_norm && diverged, APDX_ERR_INVALID, "NULL argument");
+  APDX_CHECK(ensure_newton_buffers(pl));
+  cudaStream_t s = pl->stream;
+  pl->stats = Stats();
+  cudaEvent_t t0 = pl->ev[3];
+  APDX_CUDA(cudaEventRecord(t0, s));
+  // carry of solver.damped_newton (solver.py:944-946): (dofs, itt=0, not_stop=True, res_norm=0.0, diverged=False)
+  int32_t itt = 0;
+  bool not_stop = true, div = false;
+  double rn = 0.0;
+  while (not_stop) {
+    const double rn_old = rn;
+    // --- lin_solve_fun: impose Dirichlet values, assemble, solve (solver.py:586-656) ---
+    if (dirichlet_values_d) {
+      k_impose<<<g1(pl->n_dofs), 256, 0, s>>>(dofs_d, pl->mask.p, dirichlet_values_d, pl->n_dofs);
+      pl->stats.kernel_launches += 1;
+    }
+    APDX_CHECK(linear_step_internal(pl, opts, dofs_d, nullptr));
+    // --- damped update of the free dofs; Dirichlet entries keep the imposed values (:879-892) ---
+    k_newton_update<<<g1(pl->n_free), 256, 0, s>>>(dofs_d, pl->free_list.p, pl->x_red.p, damping, pl->n_free);
+    pl->stats.kernel_launches += 1;
+    // --- residual at the updated state and its norm over the free dofs (:898-903) ---
+    APDX_CUDA(cudaEventRecord(pl->ev[0], s));
+    APDX_CHECK(assemble_internal(pl, dofs_d, 0, pl->residual.p));
+    APDX_CUDA(cudaEventRecord(pl->ev[1], s));
+    double rn2 = 0.0;
+    APDX_CHECK(residual_norm(pl, pl->residual.p, &rn2));
+    pl->stats.asm_residual_ms += elapsed(pl->ev[0], pl->ev[1]);
+    rn = sqrt(rn2);
+    not_stop = rn > newton_tol;  // :904 (NaN compares false, handled by the divergence flag below)
+    bool next_step;
+    if (itt < maxiter) {  // :930
+      bool d = (rn / rn_old > 10.0) && (itt > 1);  // :915-917
+      if (rn != rn || rn2 != rn2 || isinf(rn2)) d = true;  // :919-923
+      next_step = !d;
+      div = d;
+    } else {  // :926-928
+      next_step = false;
+      div = true;
+    }
+    itt += 1;
+    not_stop = not_stop && next_step;
+  }
+  APDX_CUDA(cudaEventRecord(pl->ev[2], s));
+  APDX_CUDA(cudaEventSynchronize(pl->ev[2]));
+  pl->stats.total_ms = elapsed(t0, pl->ev[2]);
+  *iters = itt;
+  *res_norm = rn;
+  *diverged = div ? 1 : 0;
+  return APDX_OK;
+}
+
+int apdx_plan_stats(const apdx_plan *pl, double out[8]) {
+  APDX_REQUIRE(pl && out, APDX_ERR_INVALID, "NULL argument");
+  out[0] = pl->stats.asm_tangent_ms; out[1] = pl->stats.asm_residual_ms; out[2] = pl->stats.krylov_ms;
+  out[3] = pl->stats.krylov_iters; out[4] = pl->stats.spmv_launches; out[5] = pl->stats.total_ms;
+  out[6] = pl->stats.kernel_launches; out[7] = 0.0;
+  return APDX_OK;
+}
+
+int apdx_plan_set_partition(apdx_plan *pl, int64_t owned_dof_begin, int64_t owned_dof_end, int32_t rank_lo,
+                            int32_t rank_hi) {
+  APDX_REQUIRE(pl, APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(0 <= owned_dof_begin && owned_dof_begin < owned_dof_end && owned_dof_end <= pl->n_dofs, APDX_ERR_INVALID,
+               "bad owned range");
+  int64_t *out = reinterpret_cast<int64_t *>(pl->pinned + 48);
+  int64_t *tmp_d = nullptr;
+  APDX_CUDA(cudaMalloc((void **)&tmp_d, 2 * sizeof(int64_t)));
+  k_lower_bound<<<1, 1, 0, pl->stream>>>(pl->free_list.p, pl->n_free, owned_dof_begin, tmp_d);
+  k_lower_bound<<<1, 1, 0, pl->stream>>>(pl->free_list.p, pl->n_free, owned_dof_end, tmp_d + 1);
+  APDX_CUDA(cudaMemcpyAsync(out, tmp_d, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, pl->stream));
+  APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  cudaFree(tmp_d);
+  pl->owned_begin = owned_dof_begin; pl->owned_end = owned_dof_end;
+  pl->f0 = out[0]; pl->f1 = out[1];
+  pl->rank_lo = rank_lo; pl->rank_hi = rank_hi;
+  pl->halo_lo = pl->f0; pl->halo_hi = pl->n_free - pl->f1;
+  APDX_REQUIRE(pl->f1 > pl->f0, APDX_ERR_INVALID, "rank owns no free dof");
+  if (rank_lo < 0) APDX_REQUIRE(pl->halo_lo == 0, APDX_ERR_INVALID, "ghost dofs below the owned range but no lower neighbour");
+  if (rank_hi < 0) APDX_REQUIRE(pl->halo_hi == 0, APDX_ERR_INVALID, "ghost dofs above the owned range but no upper neighbour");
+  if (comm_active()) APDX_CHECK(comm_halo_setup(pl));
+  return APDX_OK;
+}
+
+}  // extern "C"

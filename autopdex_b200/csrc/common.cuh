@@ -1,0 +1,176 @@
+// Internal declarations shared by the translation units of libapdx_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/apdx_b200.h"
+
+namespace apdx {
+
+void set_error(const char *fmt, ...);
+
+#define APDX_CUDA(call)                                                                    \
+  do {                                                                                     \
+    cudaError_t err__ = (call);                                                            \
+    if (err__ != cudaSuccess) {                                                            \
+      apdx::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                   \
+                      cudaGetErrorString(err__));                                          \
+      return APDX_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+#define APDX_CHECK(call)                                                                   \
+  do {                                                                                     \
+    int rc__ = (call);                                                                     \
+    if (rc__ != APDX_OK) return rc__;                                                      \
+  } while (0)
+
+#define APDX_REQUIRE(cond, code, ...)                                                      \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      apdx::set_error(__VA_ARGS__);                                                        \
+      return (code);                                                                       \
+    }                                                                                      \
+  } while (0)
+
+// Device buffer with size bookkeeping (all plan memory goes through this).
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count);
+  void release();
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+extern size_t g_plan_bytes;  // bytes currently held by DevBufs (diagnostics)
+
+template <typename T>
+int DevBuf<T>::alloc(size_t count) {
+  release();
+  if (count == 0) return APDX_OK;
+  cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    p = nullptr;
+    set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? APDX_ERR_NOMEM : APDX_ERR_CUDA;
+  }
+  n = count;
+  g_plan_bytes += bytes();
+  return APDX_OK;
+}
+template <typename T>
+void DevBuf<T>::release() {
+  if (p) {
+    cudaFree(p);
+    g_plan_bytes -= bytes();
+  }
+  p = nullptr;
+  n = 0;
+}
+
+// Run-time parameter of a set: value(row, gp, comp) = p[row*s_row + gp*s_gp + comp]
+struct ParamView {
+  const double *p;
+  int64_t s_row;
+  int32_t s_gp;
+  int32_t ncomp;
+};
+
+struct SetData {
+  apdx_set_desc d{};          // host copy of the descriptor (pointers invalid after create)
+  int32_t ndof_e = 0;         // nen * nf
+  int64_t coo_offset = 0;     // offset of this set's block in the COO / Ke stream
+  int64_t res_offset = 0;     // offset of this set's block in the Re stream
+  DevBuf<int32_t> conn;       // [n_rows][nen]
+  DevBuf<double> shape_n, shape_dn, gp_w;
+  DevBuf<double> ip_n, ip_dndx, ip_w;  // integration-point tables
+  DevBuf<double> params[APDX_PARAM_COUNT];
+  ParamView pview[APDX_PARAM_COUNT]{};
+};
+
+struct KrylovWork {
+  DevBuf<double> r, p, q, z, s, t, phat, shat, r0, minv;
+  DevBuf<double> partial;     // per-block partial sums of the fused dot products
+  DevBuf<double> scal;        // device scalars (see krylov.cu)
+  DevBuf<unsigned int> ticket;
+  DevBuf<int32_t> flags;      // [0]=done [1]=iterations [2]=breakdown
+};
+
+struct Stats {
+  double asm_tangent_ms = 0, asm_residual_ms = 0, krylov_ms = 0, total_ms = 0;
+  double krylov_iters = 0, spmv_launches = 0, kernel_launches = 0;
+};
+
+}  // namespace apdx
+
+struct apdx_plan {
+  int32_t dim = 0, nf = 0, n_sets = 0;
+  int64_t n_nodes = 0, n_dofs = 0, n_free = 0, nnz = 0, nnz_red = 0, n_coo = 0, n_res = 0;
+  std::vector<apdx::SetData> sets;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4]{};
+
+  // fields
+  apdx::DevBuf<double> coords, dofs_n;
+  double time_increment = 1.0;
+  bool have_coords = false;
+
+  // Dirichlet maps
+  apdx::DevBuf<uint8_t> mask;        // [n_dofs] 1 = Dirichlet
+  apdx::DevBuf<int32_t> free_id;     // [n_dofs] reduced index or -1
+  apdx::DevBuf<int32_t> free_list;   // [n_free] full dof id
+
+  // full CSR pattern + element map + gather lists of the deterministic scatter
+  apdx::DevBuf<int32_t> row_ptr, col;      // [n_dofs+1], [nnz]
+  apdx::DevBuf<int32_t> elem_map;          // [n_coo] -> position in full CSR data
+  apdx::DevBuf<uint32_t> perm;             // [n_coo] COO entries grouped by CSR entry
+  apdx::DevBuf<int32_t> seg_ptr;           // [nnz+1] hmm: n_coo < 2^31 required
+  apdx::DevBuf<uint32_t> rperm;            // [n_res] element-vector entries grouped by dof
+  apdx::DevBuf<int32_t> rseg_ptr;          // [n_dofs+1]
+
+  // reduced CSR pattern
+  apdx::DevBuf<int32_t> red_row_ptr, red_col;  // [n_free+1], [nnz_red]
+  apdx::DevBuf<int32_t> red2full;              // [nnz_red] -> full CSR entry
+  apdx::DevBuf<int32_t> red_diag;              // [n_free] position of the diagonal in reduced data
+
+  // values
+  apdx::DevBuf<double> ke, re;             // element matrices / vectors (streams in COO order)
+  apdx::DevBuf<double> vals, red_vals;     // summed CSR data
+  bool have_values = false;
+
+  // Newton / Krylov work
+  apdx::DevBuf<double> residual, rhs_red, x_red, dofs_trial;
+  apdx::KrylovWork kw;
+  double *pinned = nullptr;                // small pinned host staging
+  apdx::Stats stats;
+
+  // partition (multi-GPU)
+  int64_t owned_begin = 0, owned_end = 0;  // local dof range
+  int64_t f0 = 0, f1 = 0;                  // owned range in reduced numbering
+  int32_t rank_lo = -1, rank_hi = -1;
+  int64_t halo_lo = 0, halo_hi = 0;        // ghost free-dof counts below / above
+  int64_t send_lo = 0, send_hi = 0;        // owned free dofs the lower / upper neighbour ghosts
+};
+
+namespace apdx {
+// pattern.cu
+int build_pattern(apdx_plan *pl, const uint8_t *mask_h);
+// elements.cu
+int launch_element_kernels(apdx_plan *pl, const double *dofs_d, bool want_tangent);
+int launch_gather_reduce(apdx_plan *pl, int tangent_flags, double *residual_d);
+// krylov.cu
+int krylov_alloc(apdx_plan *pl);
+int spmv_reduced(apdx_plan *pl, const double *x, double *y);
+int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, double *x,
+                 int32_t *iters, double *relres);
+// dist.cu
+bool comm_active();
+int comm_size();
+int comm_allreduce_sum(double *buf_d, int count, cudaStream_t s);
+int comm_halo_exchange(apdx_plan *pl, double *x_d, cudaStream_t s);
+int comm_halo_setup(apdx_plan *pl);
+}  // namespace apdx

@@ -1,0 +1,455 @@
+// Jacobi-preconditioned CG / BiCGSTAB on the reduced CSR system, all scalars on device.
+//
+// Device analogue of solver.linear_solve_jax (solver.py:1093-1126: M = 1/diag,
+// jax.scipy.sparse.linalg.cg / bicgstab) operating on the assembled reduced matrix that the
+// reference hands to SciPy (solver.py:1207-1217).  The stopping rule is the one of
+// jax.scipy.sparse.linalg: ||r||_2^2 <= max(rtol^2 ||b||^2, atol^2).  No positivity checks:
+// the reference's tangents are negative definite on mesher quad meshes.
+//
+// SpMV: CSR with int32 columns, a sub-warp of TPR lanes per row, warp-shuffle row reduction,
+// the dot product(s) that follow the SpMV fused into the same kernel.  Vector updates are
+// fused axpy+dot kernels.  Dot products are reduced per block, then by the last block in a fixed
+// order (deterministic for a given grid), then -- multi-GPU -- by ncclAllReduce.
+#include "common.cuh"
+
+namespace apdx {
+
+// device scalar slots
+enum {
+  S_RZ = 0, S_PQ, S_ALPHA, S_BETA, S_RR, S_TOL2, S_BB, S_RHO, S_OMEGA, S_TS, S_TT, S_R0V, S_SS,
+  S_PEND = 16,  // pending (locally reduced) sums of the running stage, up to 4
+  S_COUNT = 24
+};
+enum { F_DONE = 0, F_ITERS = 1, F_BREAKDOWN = 2, F_MAXITER = 3, F_COUNT = 4 };
+// stages of the scalar recurrences
+enum { ST_CG_INIT = 0, ST_CG_PQ, ST_CG_UPDATE, ST_BI_INIT, ST_BI_R0V, ST_BI_S, ST_BI_T, ST_BI_X };
+
+constexpr int VEC_BLOCK = 256;
+constexpr int VEC_GRID = 148 * 8;
+
+__device__ __forceinline__ void apply_stage(int stage, double *sc, int32_t *fl) {
+  const double *pd = sc + S_PEND;
+  switch (stage) {
+    case ST_CG_INIT:  // pend = (r.z, r.r, b.b)
+      sc[S_RZ] = pd[0]; sc[S_RR] = pd[1]; sc[S_BB] = pd[2];
+      {
+        double t = sc[S_TOL2] /*rtol^2*/ * pd[2];
+        double a2 = sc[S_SS] /*atol^2 parked here by the host*/;
+        sc[S_TOL2] = t > a2 ? t : a2;
+      }
+      if (!(sc[S_RR] > sc[S_TOL2])) fl[F_DONE] = 1;
+      break;
+    case ST_CG_PQ:  // pend = (p.q)
+      sc[S_PQ] = pd[0];
+      sc[S_ALPHA] = sc[S_RZ] / pd[0];
+      break;
+    case ST_CG_UPDATE:  // pend = (r.z, r.r) after the update
+      sc[S_BETA] = pd[0] / sc[S_RZ];
+      sc[S_RZ] = pd[0];
+      sc[S_RR] = pd[1];
+      fl[F_ITERS] += 1;
+      if (!(pd[1] > sc[S_TOL2]) || fl[F_ITERS] >= fl[F_MAXITER]) fl[F_DONE] = 1;
+      if (pd[1] != pd[1]) { fl[F_DONE] = 1; fl[F_BREAKDOWN] = 1; }
+      break;
+    case ST_BI_INIT:  // pend = (r0.r, r.r, b.b)
+      sc[S_RHO] = pd[0]; sc[S_RR] = pd[1]; sc[S_BB] = pd[2];
+      {
+        double t = sc[S_TOL2] * pd[2];
+        double a2 = sc[S_SS];
+        sc[S_TOL2] = t > a2 ? t : a2;
+      }
+      sc[S_ALPHA] = 1.0; sc[S_OMEGA] = 1.0; sc[S_BETA] = 0.0;
+      if (!(sc[S_RR] > sc[S_TOL2])) fl[F_DONE] = 1;
+      break;
+    case ST_BI_R0V:  // pend = (r0.v)
+      sc[S_ALPHA] = sc[S_RHO] / pd[0];
+      break;
+    case ST_BI_S:  // pend = (s.s)
+      sc[S_SS] = pd[0];
+      break;
+    case ST_BI_T:  // pend = (t.s, t.t); early exit of jax's bicgstab: s already converged -> omega = 0
+      sc[S_OMEGA] = (sc[S_SS] > sc[S_TOL2]) ? pd[0] / pd[1] : 0.0;
+      break;
+    case ST_BI_X:  // pend = (r0.r, r.r) of the new residual
+      sc[S_BETA] = (pd[0] / sc[S_RHO]) * (sc[S_ALPHA] / sc[S_OMEGA]);
+      sc[S_RHO] = pd[0];
+      sc[S_RR] = pd[1];
+      fl[F_ITERS] += 1;
+      if (!(pd[1] > sc[S_TOL2]) || fl[F_ITERS] >= fl[F_MAXITER]) fl[F_DONE] = 1;
+      if (pd[1] != pd[1] || pd[0] == 0.0) { fl[F_DONE] = 1; fl[F_BREAKDOWN] = (pd[1] > sc[S_TOL2]) ? 1 : 0; }
+      break;
+  }
+}
+
+__global__ void k_apply_stage(int stage, double *sc, int32_t *fl) {
+  if (fl[F_DONE] && stage != ST_CG_INIT && stage != ST_BI_INIT) return;
+  apply_stage(stage, sc, fl);
+}
+
+// Block-level reduction of NV running sums, then cross-block reduction by the last block.
+// fused != 0: the last block also applies the scalar stage (single-GPU path).
+template <int NV>
+__device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial, unsigned int *ticket,
+                                                double *sc, int32_t *fl, int stage, int fused) {
+  __shared__ double sh[NV][VEC_BLOCK / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sh[i][wid] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double x = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += sh[i][w];
+      partial[(size_t)i * gridDim.x + blockIdx.x] = x;
+    }
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) x += __ldcg(&partial[(size_t)i * gridDim.x + b]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if (lane == 0) sh[i][wid] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double y = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) y += sh[i][w];
+      sc[S_PEND + i] = y;
+    }
+  }
+  if (threadIdx.x == 0) {
+    *ticket = 0u;
+    if (fused) apply_stage(stage, sc, fl);
+  }
+}
+
+// y[row] = sum_j val[j] x[col[j]] for rows [row0,row1); dots: d0 = sum w[row]*y[row], d1 = sum y[row]^2
+template <int TPR, int NDOT>
+__global__ void __launch_bounds__(VEC_BLOCK) k_spmv_csr(const int32_t *__restrict__ rp, const int32_t *__restrict__ col,
+                                                        const double *__restrict__ val, const double *__restrict__ x,
+                                                        double *__restrict__ y, const double *__restrict__ w,
+                                                        int64_t row0, int64_t row1, double *partial,
+                                                        unsigned int *ticket, double *sc, int32_t *fl, int stage,
+                                                        int fused, int check_done) {
+  if (check_done && fl[F_DONE]) return;
+  const int sub = threadIdx.x % TPR;
+  const int64_t rows_per_block = VEC_BLOCK / TPR;
+  double acc[NDOT > 0 ? NDOT : 1];
+#pragma unroll
+  for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
+  for (int64_t rb = row0 + (int64_t)blockIdx.x * rows_per_block; rb < row1; rb += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t r = rb + threadIdx.x / TPR;  // block-uniform trip count: every lane reaches the shuffles
+    const bool valid = r < row1;
+    double s = 0.0;
+    if (valid) {
+      const int32_t b = rp[r], e = rp[r + 1];
+      for (int32_t j = b + sub; j < e; j += TPR) s += val[j] * __ldg(&x[col[j]]);
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, TPR);
+    if (valid && sub == 0) {
+      y[r] = s;
+      if (NDOT >= 1) acc[0] += w[r] * s;
+      if (NDOT >= 2) acc[1] += s * s;
+    }
+  }
+  if constexpr (NDOT > 0) reduce_finalize<NDOT>(acc, partial, ticket, sc, fl, stage, fused);
+}
+
+// ---- CG vector kernels -----------------------------------------------------------------------
+// r = b - q ; z = minv r ; p = z ; sums (r.z, r.r, b.b)
+__global__ void __launch_bounds__(VEC_BLOCK) k_cg_init(const double *__restrict__ b, const double *__restrict__ q,
+                                                       const double *__restrict__ minv, double *__restrict__ r,
+                                                       double *__restrict__ p, int64_t i0, int64_t i1,
+                                                       double *partial, unsigned int *ticket, double *sc, int32_t *fl,
+                                                       int stage, int fused) {
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    double bi = b[i];
+    double ri = bi - q[i];
+    double zi = minv[i] * ri;
+    r[i] = ri;
+    p[i] = zi;
+    acc[0] += ri * zi; acc[1] += ri * ri; acc[2] += bi * bi;
+  }
+  reduce_finalize<3>(acc, partial, ticket, sc, fl, stage, fused);
+}
+// x += alpha p ; r -= alpha q ; sums (r.(minv r), r.r)
+__global__ void __launch_bounds__(VEC_BLOCK) k_cg_update(const double *__restrict__ p, const double *__restrict__ q,
+                                                         const double *__restrict__ minv, double *__restrict__ x,
+                                                         double *__restrict__ r, int64_t i0, int64_t i1,
+                                                         double *partial, unsigned int *ticket, double *sc,
+                                                         int32_t *fl, int fused) {
+  if (fl[F_DONE]) return;
+  const double alpha = sc[S_ALPHA];
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    double ri = r[i] - alpha * q[i];
+    r[i] = ri;
+    acc[0] += ri * (minv[i] * ri);
+    acc[1] += ri * ri;
+  }
+  reduce_finalize<2>(acc, partial, ticket, sc, fl, ST_CG_UPDATE, fused);
+}
+// p = minv r + beta p
+__global__ void __launch_bounds__(VEC_BLOCK) k_cg_p(const double *__restrict__ r, const double *__restrict__ minv,
+                                                    double *__restrict__ p, int64_t i0, int64_t i1, const double *sc,
+                                                    const int32_t *fl) {
+  if (fl[F_DONE]) return;
+  const double beta = sc[S_BETA];
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = minv[i] * r[i] + beta * p[i];
+}
+
+// ---- BiCGSTAB vector kernels --------------------------------------------------------------------
+// r = b - q ; r0 = r ; p = 0 ; v = 0 ; sums (r0.r, r.r, b.b)
+__global__ void __launch_bounds__(VEC_BLOCK) k_bi_init(const double *__restrict__ b, const double *__restrict__ q,
+                                                       double *__restrict__ r, double *__restrict__ r0,
+                                                       double *__restrict__ p, double *__restrict__ v, int64_t i0,
+                                                       int64_t i1, double *partial, unsigned int *ticket, double *sc,
+                                                       int32_t *fl, int fused) {
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    double bi = b[i];
+    double ri = bi - q[i];
+    r[i] = ri; r0[i] = ri; p[i] = 0.0; v[i] = 0.0;
+    acc[0] += ri * ri; acc[1] += ri * ri; acc[2] += bi * bi;
+  }
+  reduce_finalize<3>(acc, partial, ticket, sc, fl, ST_BI_INIT, fused);
+}
+// p = r + beta (p - omega v) ; phat = minv p
+__global__ void __launch_bounds__(VEC_BLOCK) k_bi_p(const double *__restrict__ r, const double *__restrict__ v,
+                                                    const double *__restrict__ minv, double *__restrict__ p,
+                                                    double *__restrict__ phat, int64_t i0, int64_t i1,
+                                                    const double *sc, const int32_t *fl) {
+  if (fl[F_DONE]) return;
+  const double beta = sc[S_BETA], omega = sc[S_OMEGA];
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    double pi = r[i] + beta * (p[i] - omega * v[i]);
+    p[i] = pi;
+    phat[i] = minv[i] * pi;
+  }
+}
+// s = r - alpha v ; shat = minv s ; sums (s.s)
+__global__ void __launch_bounds__(VEC_BLOCK) k_bi_s(const double *__restrict__ r, const double *__restrict__ v,
+                                                    const double *__restrict__ minv, double *__restrict__ s,
+                                                    double *__restrict__ shat, int64_t i0, int64_t i1,
+                                                    double *partial, unsigned int *ticket, double *sc, int32_t *fl,
+                                                    int fused) {
+  if (fl[F_DONE]) return;
+  const double alpha = sc[S_ALPHA];
+  double acc[1] = {0.0};
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    double si = r[i] - alpha * v[i];
+    s[i] = si;
+    shat[i] = minv[i] * si;
+    acc[0] += si * si;
+  }
+  reduce_finalize<1>(acc, partial, ticket, sc, fl, ST_BI_S, fused);
+}
+// x += alpha phat + omega shat ; r = s - omega t ; sums (r0.r, r.r)
+__global__ void __launch_bounds__(VEC_BLOCK) k_bi_x(const double *__restrict__ phat, const double *__restrict__ shat,
+                                                    const double *__restrict__ s, const double *__restrict__ t,
+                                                    const double *__restrict__ r0, double *__restrict__ x,
+                                                    double *__restrict__ r, int64_t i0, int64_t i1, double *partial,
+                                                    unsigned int *ticket, double *sc, int32_t *fl, int fused) {
+  if (fl[F_DONE]) return;
+  const double alpha = sc[S_ALPHA], omega = sc[S_OMEGA];
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * phat[i] + omega * shat[i];
+    double ri = s[i] - omega * t[i];
+    r[i] = ri;
+    acc[0] += r0[i] * ri;
+    acc[1] += ri * ri;
+  }
+  reduce_finalize<2>(acc, partial, ticket, sc, fl, ST_BI_X, fused);
+}
+
+__global__ void k_jacobi_inv(const double *__restrict__ vals, const int32_t *__restrict__ diag, int64_t n,
+                             int jacobi, double *__restrict__ minv) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  minv[i] = (jacobi && diag[i] >= 0) ? 1.0 / vals[diag[i]] : 1.0;  // solver.py:1095
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+int krylov_alloc(apdx_plan *pl) {
+  KrylovWork &k = pl->kw;
+  if (k.r.p) return APDX_OK;
+  const int64_t n = pl->n_free;
+  APDX_CHECK(k.r.alloc(n));
+  APDX_CHECK(k.p.alloc(n));
+  APDX_CHECK(k.q.alloc(n));
+  APDX_CHECK(k.minv.alloc(n));
+  APDX_CHECK(k.partial.alloc(4 * (size_t)(VEC_GRID > 148 * 32 ? VEC_GRID : 148 * 32)));
+  APDX_CHECK(k.scal.alloc(S_COUNT));
+  APDX_CHECK(k.ticket.alloc(1));
+  APDX_CHECK(k.flags.alloc(F_COUNT));
+  APDX_CUDA(cudaMemsetAsync(k.ticket.p, 0, sizeof(unsigned int), pl->stream));
+  // halo entries outside the owned range must read as finite numbers
+  APDX_CUDA(cudaMemsetAsync(k.p.p, 0, n * sizeof(double), pl->stream));
+  return APDX_OK;
+}
+static int krylov_alloc_bicgstab(apdx_plan *pl) {
+  KrylovWork &k = pl->kw;
+  if (k.s.p) return APDX_OK;
+  const int64_t n = pl->n_free;
+  APDX_CHECK(k.s.alloc(n));
+  APDX_CHECK(k.t.alloc(n));
+  APDX_CHECK(k.phat.alloc(n));
+  APDX_CHECK(k.shat.alloc(n));
+  APDX_CHECK(k.r0.alloc(n));
+  APDX_CUDA(cudaMemsetAsync(k.phat.p, 0, n * sizeof(double), pl->stream));
+  APDX_CUDA(cudaMemsetAsync(k.shat.p, 0, n * sizeof(double), pl->stream));
+  return APDX_OK;
+}
+
+template <int NDOT>
+static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *w, int stage, int check_done) {
+  KrylovWork &k = pl->kw;
+  const int64_t rows = pl->f1 - pl->f0;
+  const double avg = rows > 0 ? (double)pl->nnz_red / (double)pl->n_free : 1.0;
+  const int fused = comm_active() ? 0 : 1;
+  cudaStream_t s = pl->stream;
+#define APDX_SPMV(TPR)                                                                                   \
+  do {                                                                                                   \
+    int64_t rpb = VEC_BLOCK / TPR;                                                                       \
+    int64_t nb = (rows + rpb - 1) / rpb;                                                                 \
+    int64_t cap = 148ll * 32;                                                                            \
+    unsigned grid = (unsigned)(nb < cap ? (nb > 0 ? nb : 1) : cap);                                      \
+    k_spmv_csr<TPR, NDOT><<<grid, VEC_BLOCK, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red_vals.p, x, y, w, \
+                                                     pl->f0, pl->f1, k.partial.p, k.ticket.p, k.scal.p,  \
+                                                     k.flags.p, stage, fused, check_done);               \
+  } while (0)
+  if (avg <= 6.0) APDX_SPMV(4);
+  else if (avg <= 12.0) APDX_SPMV(8);
+  else if (avg <= 40.0) APDX_SPMV(16);
+  else APDX_SPMV(32);
+#undef APDX_SPMV
+  pl->stats.spmv_launches += 1;
+  pl->stats.kernel_launches += 1;
+  APDX_CUDA(cudaGetLastError());
+  return APDX_OK;
+}
+
+// after a dot-product kernel: multi-GPU all-reduce of the pending sums + scalar stage
+static int finish_stage(apdx_plan *pl, int stage, int nv) {
+  if (!comm_active()) return APDX_OK;
+  KrylovWork &k = pl->kw;
+  APDX_CHECK(comm_allreduce_sum(k.scal.p + S_PEND, nv, pl->stream));
+  k_apply_stage<<<1, 1, 0, pl->stream>>>(stage, k.scal.p, k.flags.p);
+  pl->stats.kernel_launches += 1;
+  return APDX_OK;
+}
+
+int spmv_reduced(apdx_plan *pl, const double *x, double *y) {
+  APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
+  APDX_CHECK(krylov_alloc(pl));
+  if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, const_cast<double *>(x), pl->stream));
+  return launch_spmv<0>(pl, x, y, nullptr, 0, 0);
+}
+
+int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, double *x, int32_t *iters,
+                 double *relres) {
+  APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
+  APDX_REQUIRE(o->method == APDX_KRYLOV_CG || o->method == APDX_KRYLOV_BICGSTAB, APDX_ERR_UNSUPPORTED,
+               "Krylov method %d not supported (cg, bicgstab)", o->method);
+  APDX_CHECK(krylov_alloc(pl));
+  const bool bi = o->method == APDX_KRYLOV_BICGSTAB;
+  if (bi) APDX_CHECK(krylov_alloc_bicgstab(pl));
+  KrylovWork &k = pl->kw;
+  cudaStream_t s = pl->stream;
+  const int64_t i0 = pl->f0, i1 = pl->f1, n = pl->n_free;
+  const int fused = comm_active() ? 0 : 1;
+  const int maxiter = o->maxiter > 0 ? o->maxiter : 10 * (int)(n < 100000 ? n : 100000);
+  const int chunk = o->check_every > 0 ? o->check_every : 32;
+
+  k_jacobi_inv<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pl->red_vals.p, pl->red_diag.p, n, o->jacobi, k.minv.p);
+  double sc_h[S_COUNT] = {0};
+  sc_h[S_TOL2] = o->rtol * o->rtol;
+  sc_h[S_SS] = o->atol * o->atol;
+  int32_t fl_h[F_COUNT] = {0, 0, 0, maxiter};
+  APDX_CUDA(cudaMemcpyAsync(k.scal.p, sc_h, sizeof(sc_h), cudaMemcpyHostToDevice, s));
+  APDX_CUDA(cudaMemcpyAsync(k.flags.p, fl_h, sizeof(fl_h), cudaMemcpyHostToDevice, s));
+  pl->stats.kernel_launches += 1;
+
+  // q = A x0
+  if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, x, s));
+  APDX_CHECK(launch_spmv<0>(pl, x, bi ? k.t.p : k.q.p, nullptr, 0, 0));
+  if (!bi) {
+    k_cg_init<<<VEC_GRID, VEC_BLOCK, 0, s>>>(rhs, k.q.p, k.minv.p, k.r.p, k.p.p, i0, i1, k.partial.p, k.ticket.p,
+                                             k.scal.p, k.flags.p, ST_CG_INIT, fused);
+    pl->stats.kernel_launches += 1;
+    APDX_CHECK(finish_stage(pl, ST_CG_INIT, 3));
+  } else {
+    k_bi_init<<<VEC_GRID, VEC_BLOCK, 0, s>>>(rhs, k.t.p, k.r.p, k.r0.p, k.p.p, k.q.p, i0, i1, k.partial.p,
+                                             k.ticket.p, k.scal.p, k.flags.p, fused);
+    pl->stats.kernel_launches += 1;
+    APDX_CHECK(finish_stage(pl, ST_BI_INIT, 3));
+  }
+
+  int32_t *fl_pin = reinterpret_cast<int32_t *>(pl->pinned);
+  double *sc_pin = pl->pinned + 8;
+  int launched = 0;
+  while (true) {
+    APDX_CUDA(cudaMemcpyAsync(fl_pin, k.flags.p, sizeof(int32_t) * F_COUNT, cudaMemcpyDeviceToHost, s));
+    APDX_CUDA(cudaMemcpyAsync(sc_pin, k.scal.p, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, s));
+    APDX_CUDA(cudaStreamSynchronize(s));
+    if (fl_pin[F_DONE] || launched >= maxiter) break;
+    int todo = maxiter - launched < chunk ? maxiter - launched : chunk;
+    for (int it = 0; it < todo; ++it) {
+      if (!bi) {
+        if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, k.p.p, s));
+        APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, ST_CG_PQ, 1));
+        APDX_CHECK(finish_stage(pl, ST_CG_PQ, 1));
+        k_cg_update<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.p.p, k.q.p, k.minv.p, x, k.r.p, i0, i1, k.partial.p,
+                                                   k.ticket.p, k.scal.p, k.flags.p, fused);
+        APDX_CHECK(finish_stage(pl, ST_CG_UPDATE, 2));
+        k_cg_p<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.minv.p, k.p.p, i0, i1, k.scal.p, k.flags.p);
+        pl->stats.kernel_launches += 2;
+      } else {
+        k_bi_p<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.q.p, k.minv.p, k.p.p, k.phat.p, i0, i1, k.scal.p, k.flags.p);
+        if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, k.phat.p, s));
+        APDX_CHECK(launch_spmv<1>(pl, k.phat.p, k.q.p, k.r0.p, ST_BI_R0V, 1));
+        APDX_CHECK(finish_stage(pl, ST_BI_R0V, 1));
+        k_bi_s<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.q.p, k.minv.p, k.s.p, k.shat.p, i0, i1, k.partial.p,
+                                              k.ticket.p, k.scal.p, k.flags.p, fused);
+        APDX_CHECK(finish_stage(pl, ST_BI_S, 1));
+        if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, k.shat.p, s));
+        APDX_CHECK(launch_spmv<2>(pl, k.shat.p, k.t.p, k.s.p, ST_BI_T, 1));
+        APDX_CHECK(finish_stage(pl, ST_BI_T, 2));
+        k_bi_x<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.phat.p, k.shat.p, k.s.p, k.t.p, k.r0.p, x, k.r.p, i0, i1,
+                                              k.partial.p, k.ticket.p, k.scal.p, k.flags.p, fused);
+        APDX_CHECK(finish_stage(pl, ST_BI_X, 2));
+        pl->stats.kernel_launches += 3;
+      }
+    }
+    launched += todo;
+  }
+  APDX_CUDA(cudaGetLastError());
+  if (iters) *iters = fl_pin[F_ITERS];
+  if (relres) *relres = sc_pin[S_BB] > 0 ? sqrt(sc_pin[S_RR] / sc_pin[S_BB]) : sqrt(sc_pin[S_RR]);
+  pl->stats.krylov_iters += fl_pin[F_ITERS];
+  if (fl_pin[F_BREAKDOWN]) {
+    set_error("Krylov breakdown (NaN or zero inner product) after %d iterations", fl_pin[F_ITERS]);
+  }
+  return APDX_OK;
+}
+
+}  // namespace apdx

@@ -1,0 +1,196 @@
+/* apdx_b200.h -- C ABI of libapdx_b200.so, the B200 (sm_100a) backend for the AutoPDEx
+ * hot path "sparse residual/tangent assembly -> Newton linear solve".
+ *
+ * This is the drop-in boundary: the entry points below are what a
+ * `'solver backend': 'b200'` branch inside AutoPDEx's solver.solver
+ * (autopdex/solver.py:41-137, backend read at solver.py:576) binds through jax.ffi /
+ * ctypes.  INTEGRATION.md shows the reference-side stub.  Each entry point cites the
+ * reference function it replaces (paths relative to the AutoPDEx v1.1.4 tree).
+ *
+ * Conventions
+ *   - every function returns APDX_OK (0) or a negative error code; the message of the
+ *     last error of the calling thread is available from apdx_last_error();
+ *   - pointers suffixed _h are HOST pointers, pointers suffixed _d are DEVICE pointers
+ *     owned by the caller (allocate them with apdx_malloc or any CUDA allocator);
+ *   - all reals are FP64, dof/flat vectors use the reference's global numbering
+ *     gid = node*nf + comp (assembler.py:130, utility.dict_flatten utility.py:104-128);
+ *   - a plan is not thread-safe; the library is re-entrant across plans;
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef APDX_B200_H
+#define APDX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APDX_ABI_VERSION 1
+
+enum {
+  APDX_OK = 0,
+  APDX_ERR_INVALID = -1,     /* bad argument / inconsistent description */
+  APDX_ERR_CUDA = -2,        /* CUDA runtime error (message has the detail) */
+  APDX_ERR_UNSUPPORTED = -3, /* model / element outside the supported table: rejected, never emulated */
+  APDX_ERR_NOMEM = -4,
+  APDX_ERR_NCCL = -5,
+  APDX_ERR_STATE = -6        /* call order violated (e.g. solve before assemble) */
+};
+
+/* kind of a connectivity set (static_settings['assembling mode'][set]) */
+enum {
+  APDX_SET_DOMAIN = 0,   /* isoparametric domain element: 'user element' / 'user potential'
+                            (models.py:1616-1720, 1188-1269) */
+  APDX_SET_SURFACE = 1,  /* isoparametric surface element (models.py:1723-1850) */
+  APDX_SET_INTPOINT = 2  /* 'sparse' mode: one row per integration point (assembler.py:874-1035) */
+};
+
+/* closed-form models */
+enum {
+  APDX_MODEL_POISSON_POTENTIAL = 0, /* Pi = 1/2 c |grad phi|^2 - f phi  (README integrand) */
+  APDX_MODEL_POISSON_WEAK = 1,      /* models.poisson_weak, models.py:96-134 */
+  APDX_MODEL_LINEAR_ELASTICITY = 2, /* models.linear_elasticity_weak, models.py:510-635 */
+  APDX_MODEL_NEO_HOOKE = 3,         /* hyperelastic_steady_state_weak + neo_hooke, models.py:917-1000,1122-1146 */
+  APDX_MODEL_NEUMANN = 4,           /* models.neumann_weak, models.py:744-779 */
+  APDX_MODEL_CAPACITY = 5           /* models.forward_backward_euler_weak, models.py:1946-2010 */
+};
+
+enum { APDX_MODE_NONE = 0, APDX_MODE_PLAIN_STRAIN = 1, APDX_MODE_PLAIN_STRESS = 2, APDX_MODE_3D = 3 };
+
+/* run-time parameters of a set (values of the Python coefficient callables, evaluated by the host) */
+enum {
+  APDX_PARAM_COEFFICIENT = 0, /* c        (1 comp)  */
+  APDX_PARAM_SOURCE = 1,      /* f        (1 comp)  */
+  APDX_PARAM_YOUNGS = 2,      /* E        (1 comp)  */
+  APDX_PARAM_POISSON_RATIO = 3, /* nu     (1 comp)  */
+  APDX_PARAM_BODY_LOAD = 4,   /* b        (nf comps) */
+  APDX_PARAM_TRACTION = 5,    /* t        (nf comps) */
+  APDX_PARAM_COUNT = 6
+};
+enum {
+  APDX_LAYOUT_CONST = 0,       /* [ncomp]                      */
+  APDX_LAYOUT_PER_GP = 1,      /* [n_gp][ncomp]   (same for every element) */
+  APDX_LAYOUT_PER_ROW_GP = 2   /* [n_rows][n_gp][ncomp]        */
+};
+
+enum { APDX_KRYLOV_CG = 0, APDX_KRYLOV_BICGSTAB = 1 };
+
+typedef struct apdx_plan apdx_plan;
+
+/* One entry of settings['connectivity'] together with the recognised model of
+ * static_settings['model'][set].  All pointers are host pointers, read during
+ * apdx_plan_create only. */
+typedef struct {
+  int32_t kind;          /* APDX_SET_* */
+  int32_t model;         /* APDX_MODEL_* */
+  int32_t mode;          /* APDX_MODE_* (elasticity / neo-Hooke) */
+  int32_t nen;           /* nodes per row of conn */
+  int32_t n_gp;          /* Gauss points per element (1 for APDX_SET_INTPOINT) */
+  int32_t dim_ref;       /* reference dimension of the element (dim, or dim-1 for surfaces) */
+  int32_t conn_itemsize; /* 4 (int32) or 8 (int64, the reference's index dtype) */
+  int32_t reserved;
+  int64_t n_rows;        /* elements, or integration points for APDX_SET_INTPOINT */
+  const void *conn_h;    /* [n_rows][nen] node ids */
+  const double *shape_n_h;  /* [n_gp][nen] shape values at the Gauss points (domain/surface) */
+  const double *shape_dn_h; /* [n_gp][nen][dim_ref] reference gradients (domain/surface) */
+  const double *gp_w_h;     /* [n_gp] reference weights (domain/surface) */
+} apdx_set_desc;
+
+typedef struct {
+  int32_t method;    /* APDX_KRYLOV_* (static_settings['solver']: 'cg' | 'bicgstab') */
+  int32_t maxiter;   /* kwargs maxiter of linear_solve_jax, solver.py:1116 */
+  double rtol;       /* ||r|| <= max(rtol*||b||, atol), as jax.scipy.sparse.linalg.cg */
+  double atol;
+  int32_t jacobi;    /* 1: 'type of preconditioner': 'jacobi' (solver.py:1093-1099) */
+  int32_t check_every; /* iterations between host convergence polls (0 = default) */
+} apdx_krylov_opts;
+
+/* ---- library / device ------------------------------------------------------------- */
+int apdx_abi_version(void);
+const char *apdx_last_error(void);
+int apdx_device_count(int *count);
+int apdx_set_device(int device);
+int apdx_malloc(void **ptr_d, size_t bytes);
+int apdx_free(void *ptr_d);
+int apdx_host_alloc(void **ptr_h, size_t bytes);   /* pinned */
+int apdx_host_free(void *ptr_h);
+int apdx_memcpy_h2d(void *dst_d, const void *src_h, size_t bytes);
+int apdx_memcpy_d2h(void *dst_h, const void *src_d, size_t bytes);
+int apdx_memset(void *dst_d, int value, size_t bytes);
+int apdx_synchronize(void);
+int apdx_mem_info(size_t *free_bytes, size_t *total_bytes);
+
+/* ---- plan: pattern, element->CSR map, Dirichlet maps -------------------------------- *
+ * Replaces assembler._get_indices (assembler.py:47-141) + solver.scipy_assembling
+ * (solver.py:1180-1222): the COO (row,col) stream of all sets is sorted/uniqued ON DEVICE
+ * once; the result is the full CSR pattern, the reduced pattern csr[:,free][free], the
+ * element-local -> CSR position map, and the gather lists of the deterministic scatter.
+ * dirichlet_mask_h: [n_nodes*nf] bytes (settings['dirichlet dofs'] flattened) or NULL.   */
+int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf, int32_t n_sets,
+                     const apdx_set_desc *sets, const uint8_t *dirichlet_mask_h);
+int apdx_plan_destroy(apdx_plan *plan);
+/* out[0]=n_dofs out[1]=n_free out[2]=nnz_full out[3]=nnz_reduced out[4]=n_coo (nse)
+ * out[5]=owned_free_begin out[6]=owned_free_end out[7]=device bytes held by the plan */
+int apdx_plan_query(const apdx_plan *plan, int64_t out[8]);
+/* CSR pattern as int64 (the reference index dtype): indptr [n+1], indices [nnz] */
+int apdx_plan_get_csr(const apdx_plan *plan, int reduced, int64_t *indptr_h, int64_t *indices_h);
+/* pos[k] = index in full-CSR data of COO entry k, k in [offset, offset+count) */
+int apdx_plan_get_elem_map(const apdx_plan *plan, int64_t offset, int64_t count, int64_t *pos_h);
+
+/* ---- run-time fields (everything that lives in the traced `settings` dict) ----------- */
+int apdx_set_coords(apdx_plan *plan, const double *coords_h);            /* [n_nodes][dim] */
+int apdx_set_param(apdx_plan *plan, int32_t set, int32_t param, int32_t layout, int32_t ncomp,
+                   const double *values_h);
+/* per-row tables of an APDX_SET_INTPOINT set: N [n_rows][nen], dNdx [n_rows][nen][dim], w [n_rows]
+ * (settings['compiled shape functions'][set], settings['integration weights'][set]) */
+int apdx_set_intpoint_tables(apdx_plan *plan, int32_t set, const double *n_h, const double *dndx_h,
+                             const double *w_h);
+int apdx_set_time_increment(apdx_plan *plan, double dt);                 /* settings['time increment'] */
+int apdx_set_dofs_n(apdx_plan *plan, const double *dofs_n_h);            /* settings['dofs n'] */
+
+/* ---- assembly ------------------------------------------------------------------------ *
+ * Replaces assembler.assemble_residual / assemble_tangent (assembler.py:587-637,682-777)
+ * followed by the duplicate summation of solver.scipy_assembling.  residual_d [n_dofs].
+ * With want_tangent the summed values are kept inside the plan (full and reduced CSR).    */
+int apdx_assemble(apdx_plan *plan, const double *dofs_d, int want_tangent, double *residual_d);
+int apdx_get_values(const apdx_plan *plan, int reduced, double *values_h); /* [nnz] after assemble */
+
+/* ---- linear algebra on the assembled reduced system ---------------------------------- */
+int apdx_spmv(apdx_plan *plan, const double *x_d, double *y_d);           /* [n_free] each */
+/* Jacobi-preconditioned CG / BiCGSTAB on the reduced system (device analogue of
+ * solver.linear_solve_jax, solver.py:1093-1126).  x_d is the initial guess and the result. */
+int apdx_krylov(apdx_plan *plan, const apdx_krylov_opts *opts, const double *rhs_d, double *x_d,
+                int32_t *iters, double *relres);
+
+/* ---- the Newton hot loop ------------------------------------------------------------- *
+ * apdx_linear_step = solver.solve_linear with nodal imposition (solver.py:586-656):
+ * delta_d gets the MIXED vector (free entries = Newton increment, Dirichlet entries = imposed
+ * values).  apdx_newton = solver.damped_newton (solver.py:837-948) with identical loop
+ * semantics; dirichlet_values_d [n_dofs] (only masked entries are read).                  */
+int apdx_linear_step(apdx_plan *plan, const apdx_krylov_opts *opts, const double *dofs_d,
+                     const double *dirichlet_values_d, double *delta_d, int32_t *krylov_iters);
+int apdx_newton(apdx_plan *plan, const apdx_krylov_opts *opts, double *dofs_d,
+                const double *dirichlet_values_d, double newton_tol, int32_t maxiter, double damping,
+                int32_t *iters, double *res_norm, int32_t *diverged);
+/* timings (ms, CUDA events) and counters of the last apdx_newton / apdx_linear_step:
+ * out[0]=assembly(tangent+residual) out[1]=assembly(residual only) out[2]=krylov
+ * out[3]=krylov iterations out[4]=spmv launches out[5]=total out[6]=kernel launches       */
+int apdx_plan_stats(const apdx_plan *plan, double out[8]);
+
+/* ---- multi-GPU (one process per GPU, slab partition) -------------------- *
+ * Each rank builds a plan of its LOCAL mesh (owned nodes plus one ghost plane per side,
+ * local ids in global order).  owned dofs are the contiguous range [begin,end) of local
+ * dof ids; rank_lo/rank_hi are the neighbour ranks (-1: none).  Halo planes travel with
+ * ncclSend/ncclRecv, dot products and the Newton norm with ncclAllReduce.                 */
+int apdx_comm_unique_id(uint8_t id_out[128]);
+int apdx_comm_init(const uint8_t id[128], int32_t rank, int32_t nranks);
+int apdx_comm_destroy(void);
+int apdx_plan_set_partition(apdx_plan *plan, int64_t owned_dof_begin, int64_t owned_dof_end,
+                            int32_t rank_lo, int32_t rank_hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APDX_B200_H */

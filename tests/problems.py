@@ -70,3 +70,67 @@ def cook_g2(q0=20.0, Em=100.0, nu=0.3):
     sur = dict(kind="surface", etype="line3", conn=neumann, nf=2, gp=oquad.gauss_legendre_nd(1, 4),
                model=dict(name="neumann", traction=np.array([0.0, q0])))
     return dict(sets=[dom, sur], coords=coords, mask=mask, values=np.zeros(mask.shape), nf=2, q0=q0)
+
+
+def _boundary_mask_box(coords, lo, hi, tol=1e-9):
+    on = np.zeros(coords.shape[0], dtype=bool)
+    for d in range(coords.shape[1]):
+        on |= (np.abs(coords[:, d] - lo[d]) < tol) | (np.abs(coords[:, d] - hi[d]) < tol)
+    return on
+
+
+UNIT_CUBE = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
+
+
+def poisson_hex(n, etype="hex8", distort=0.0, source=1.0):
+    """BASELINE config 4 family: 3-D Poisson (models.poisson_weak as 'user element'), n^3 bricks on the
+    unit cube, unit coefficient, constant source, homogeneous Dirichlet on all six faces."""
+    coords, elems = omesh.structured_mesh((n, n, n), UNIT_CUBE, "brick")
+    order = 2
+    if etype == "hex27":
+        coords, elems = omesh.elevate_bricks(coords, elems)
+        order = 4
+    if distort:
+        rng = np.random.default_rng(3)
+        inner = ~_boundary_mask_box(coords, [0, 0, 0], [1, 1, 1])
+        coords = coords + inner[:, None] * rng.uniform(-distort, distort, coords.shape) / n
+    st = dict(kind="domain", etype=etype, conn=elems, nf=1, gp=oquad.gauss_legendre_nd(3, order),
+              model=dict(name="poisson_weak", coefficient=1.0, source=source))
+    mask = _boundary_mask_box(coords, [0, 0, 0], [1, 1, 1])[:, None]
+    return dict(sets=[st], coords=coords, mask=mask, values=np.zeros(mask.shape), nf=1)
+
+
+def boundary_faces_x1(n, etype="quad4"):
+    """quad4 faces of the structured n^3 brick mesh on the plane x = 1 (i = n), nodes (j,k),(j+1,k),(j+1,k+1),(j,k+1)."""
+    sy, sx = n + 1, (n + 1) * (n + 1)
+    J, K = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    J, K = J.ravel(), K.ravel()
+    nid = lambda dj, dk: n * sx + (J + dj) * sy + (K + dk)
+    return np.stack([nid(0, 0), nid(1, 0), nid(1, 1), nid(0, 1)], axis=1).astype(np.int64)
+
+
+def neo_hooke_brick(n, traction=(0.0, 0.0, -2.0), Em=100.0, nu=0.3, model="neo_hooke"):
+    """BASELINE config 5 family: n^3 hex8 brick, clamped at x=0, traction on the face x=1."""
+    coords, elems = omesh.structured_mesh((n, n, n), UNIT_CUBE, "brick")
+    dom = dict(kind="domain", etype="hex8", conn=elems, nf=3, gp=oquad.gauss_legendre_nd(3, 2),
+               model=dict(name=model, mode="3d", youngs_modulus=Em, poisson_ratio=nu))
+    sur = dict(kind="surface", etype="quad4", conn=boundary_faces_x1(n), nf=3, gp=oquad.gauss_legendre_nd(2, 2),
+               model=dict(name="neumann", traction=np.asarray(traction, float)))
+    mask = np.repeat((np.abs(coords[:, 0]) < 1e-9)[:, None], 3, axis=1)
+    return dict(sets=[dom, sur], coords=coords, mask=mask, values=np.zeros(mask.shape), nf=3)
+
+
+def elasticity_quad(n, mode="plain strain", etype="quad4", Em=100.0, nu=0.3, body=(0.0, -1.0)):
+    """2-D linear elasticity (models.linear_elasticity_weak) on Cook's membrane geometry."""
+    pts = [[0., 0.], [48., 44.], [48., 60.], [0., 44.]]
+    coords, elems = omesh.structured_mesh((n, n), pts, "quad")
+    order = 2
+    if etype == "quad9":
+        coords, elems = omesh.elevate_quads(coords, elems)
+        order = 4
+    dom = dict(kind="domain", etype=etype, conn=elems, nf=2, gp=oquad.gauss_legendre_nd(2, order),
+               model=dict(name="linear_elasticity", mode=mode, youngs_modulus=Em, poisson_ratio=nu,
+                          body_load=np.asarray(body, float)))
+    mask = np.repeat((np.abs(coords[:, 0]) < 1e-9)[:, None], 2, axis=1)
+    values = np.zeros(mask.shape)
+    return dict(sets=[dom], coords=coords, mask=mask, values=values, nf=2)
