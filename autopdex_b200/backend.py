@@ -235,6 +235,11 @@ class Plan:
                                            float(damping), C.byref(it), C.byref(rn), C.byref(dv)))
         return it.value, rn.value, bool(dv.value)
 
+    def time_spmv(self, reps=20):
+        ms = C.c_double(0.0)
+        _lib.check(_lib.load().apdx_time_spmv(self.h, int(reps), C.byref(ms)))
+        return ms.value
+
     def stats(self):
         out = (C.c_double * 8)()
         _lib.check(_lib.load().apdx_plan_stats(self.h, out))
@@ -248,3 +253,29 @@ class Plan:
         q = (C.c_int64 * 8)()
         _lib.check(_lib.load().apdx_plan_query(self.h, q))
         self.f0, self.f1 = q[5], q[6]
+
+
+# ---- multi-GPU plumbing (one process per GPU) ---------------------------------------------------------
+def comm_unique_id():
+    buf = (C.c_uint8 * 128)()
+    _lib.check(_lib.load().apdx_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init(unique_id, rank, nranks):
+    buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+    _lib.check(_lib.load().apdx_comm_init(buf, int(rank), int(nranks)))
+
+
+def comm_destroy():
+    _lib.check(_lib.load().apdx_comm_destroy())
+
+
+def comm_allreduce_host(values, op="sum"):
+    v = np.ascontiguousarray(values, dtype=np.float64).copy()
+    _lib.check(_lib.load().apdx_comm_allreduce_host(v.ctypes.data_as(C.c_void_p), v.size, 1 if op == "max" else 0))
+    return v
+
+
+def set_device(index):
+    _lib.check(_lib.load().apdx_set_device(int(index)))

@@ -474,6 +474,11 @@ int apdx_spmv(apdx_plan *pl, const double *x_d, double *y_d) {
   return APDX_OK;
 }
 
+int apdx_time_spmv(apdx_plan *pl, int32_t reps, double *ms_avg) {
+  APDX_REQUIRE(pl && ms_avg && reps > 0, APDX_ERR_INVALID, "bad argument");
+  return time_spmv(pl, reps, ms_avg);
+}
+
 int apdx_krylov(apdx_plan *pl, const apdx_krylov_opts *opts, const double *rhs_d, double *x_d, int32_t *iters,
                 double *relres) {
   APDX_REQUIRE(pl && opts && rhs_d && x_d, APDX_ERR_INVALID, "NULL argument");
@@ -501,6 +506,7 @@ int apdx_linear_step(apdx_plan *pl, const apdx_krylov_opts *opts, const double *
     pl->stats.kernel_launches += 1;
   }
   APDX_CHECK(linear_step_internal(pl, opts, pl->dofs_trial.p, krylov_iters));
+  if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, pl->x_red.p, s));
   k_mixed_vector<<<g1(pl->n_dofs), 256, 0, s>>>(pl->dofs_trial.p, pl->free_id.p, pl->x_red.p, pl->n_dofs, delta_d);
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaStreamSynchronize(s));
@@ -529,6 +535,7 @@ int apdx_newton(apdx_plan *pl, const apdx_krylov_opts *opts, double *dofs_d, con
     }
     APDX_CHECK(linear_step_internal(pl, opts, dofs_d, nullptr));
     // --- damped update of the free dofs; Dirichlet entries keep the imposed values (:879-892) ---
+    if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, pl->x_red.p, s));  // ghost dofs follow their owners
     k_newton_update<<<g1(pl->n_free), 256, 0, s>>>(dofs_d, pl->free_list.p, pl->x_red.p, damping, pl->n_free);
     pl->stats.kernel_launches += 1;
     // --- residual at the updated state and its norm over the free dofs (:898-903) ---

@@ -167,6 +167,7 @@ int krylov_alloc(apdx_plan *pl);
 int spmv_reduced(apdx_plan *pl, const double *x, double *y);
 int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, double *x,
                  int32_t *iters, double *relres);
+int time_spmv(apdx_plan *pl, int reps, double *ms_avg);
 // dist.cu
 bool comm_active();
 int comm_size();

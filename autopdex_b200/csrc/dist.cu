@@ -15,7 +15,7 @@ typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclInt64 = 4, ncclFloat64 = 8 };
-enum { ncclSum = 0 };
+enum { ncclSum = 0, ncclMax = 2 };
 
 struct Nccl {
   void *lib = nullptr;
@@ -141,6 +141,19 @@ int apdx_comm_init(const uint8_t id_in[128], int32_t rank, int32_t nranks) {
   APDX_NCCL(g_nccl.CommInitRank(&g_nccl.comm, nranks, id, rank));
   g_nccl.rank = rank;
   g_nccl.nranks = nranks;
+  return APDX_OK;
+}
+
+int apdx_comm_allreduce_host(double *inout_h, int32_t count, int32_t op) {
+  APDX_REQUIRE(inout_h && count > 0, APDX_ERR_INVALID, "bad argument");
+  if (!comm_active()) return APDX_OK;
+  double *buf = nullptr;
+  APDX_CUDA(cudaMalloc((void **)&buf, count * sizeof(double)));
+  APDX_CUDA(cudaMemcpy(buf, inout_h, count * sizeof(double), cudaMemcpyHostToDevice));
+  APDX_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, op == 1 ? ncclMax : ncclSum, g_nccl.comm, 0));
+  APDX_CUDA(cudaStreamSynchronize(0));
+  APDX_CUDA(cudaMemcpy(inout_h, buf, count * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(buf);
   return APDX_OK;
 }
 

@@ -365,6 +365,25 @@ int spmv_reduced(apdx_plan *pl, const double *x, double *y) {
   return launch_spmv<0>(pl, x, y, nullptr, 0, 0);
 }
 
+int time_spmv(apdx_plan *pl, int reps, double *ms_avg) {
+  APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
+  APDX_CHECK(krylov_alloc(pl));
+  KrylovWork &k = pl->kw;
+  cudaStream_t s = pl->stream;
+  const int64_t n = pl->n_free;
+  // a smooth non-trivial input vector: p = minv-free copy of the diagonal positions
+  k_jacobi_inv<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pl->red_vals.p, pl->red_diag.p, n, 1, k.p.p);
+  for (int i = 0; i < 3; ++i) APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, -1, 0));
+  APDX_CUDA(cudaEventRecord(pl->ev[0], s));
+  for (int i = 0; i < reps; ++i) APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, -1, 0));
+  APDX_CUDA(cudaEventRecord(pl->ev[1], s));
+  APDX_CUDA(cudaEventSynchronize(pl->ev[1]));
+  float ms = 0.f;
+  APDX_CUDA(cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]));
+  *ms_avg = (double)ms / reps;
+  return APDX_OK;
+}
+
 int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, double *x, int32_t *iters,
                  double *relres) {
   APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");

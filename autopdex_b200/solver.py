@@ -1,0 +1,364 @@
+"""`'solver backend': 'b200'` behind the reference entry point
+solver.solver(dofs, settings, static_settings, **kwargs)  (autopdex/solver.py:41-137).
+
+Same call signature and return contract as the reference:
+  'newton' / 'damped newton'  -> (dofs_like, (n_steps, res_norm, diverged))        solver.py:948
+  'linear'                    -> (dofs_like, None), the MIXED vector of solve_linear  solver.py:648-659
+Assembly, nodal Dirichlet imposition, the Newton loop and the Krylov solve run on the device
+inside libapdx_b200.so; this module reads the two settings dicts, rejects what the backend does
+not support (ValueError, never a CPU path), evaluates the Python coefficient callables on the
+host once per call, and owns the plan cache (pattern + index maps are built once per mesh).
+
+Keyword arguments: newton_tol, maxiter (Newton, as solver.solve_newton solver.py:741-743),
+damping_coefficient ('damped newton'); tol / atol / krylov_maxiter (Krylov, as the **kwargs of
+jax.scipy.sparse.linalg.cg in linear_solve_jax, solver.py:1116).  The reference's solve_newton
+silently drops Krylov kwargs (solver.py:766-768); here they are honoured.
+"""
+from collections import OrderedDict
+from collections.abc import Mapping
+from inspect import signature
+
+import numpy as np
+
+from . import backend, models, spaces, utility
+
+_SUPPORTED_SOLVER_TYPES = ("newton", "damped newton", "linear")
+_PLAN_CACHE = OrderedDict()
+_PLAN_CACHE_SIZE = 4
+last_stats = {}
+
+
+# ---- reading static_settings ---------------------------------------------------------------------
+def _get(static_settings, key, default=None, required=False):
+    try:
+        return static_settings[key]
+    except KeyError:
+        if required:
+            raise ValueError("b200 backend: static_settings[%r] is required" % key)
+        return default
+
+
+def _per_set(value, n_sets, key):
+    if isinstance(value, (tuple, list)):
+        if len(value) != n_sets:
+            raise ValueError("b200 backend: static_settings[%r] must have one entry per domain" % key)
+        return list(value)
+    return [value] * n_sets
+
+
+class _Config:
+    """Validated view of static_settings for the b200 path (settings-read-time rejection)."""
+
+    def __init__(self, static_settings):
+        if _get(static_settings, "solver backend") != "b200":
+            raise ValueError("autopdex_b200.solver handles 'solver backend': 'b200' only, got %r"
+                             % (_get(static_settings, "solver backend"),))
+        self.solver_type = _get(static_settings, "solver type", required=True)
+        if self.solver_type not in _SUPPORTED_SOLVER_TYPES:
+            raise ValueError("b200 backend: 'solver type' %r not supported (supported: %s)"
+                             % (self.solver_type, ", ".join(_SUPPORTED_SOLVER_TYPES)))
+        self.krylov = _get(static_settings, "solver", "cg")
+        if self.krylov not in ("cg", "bicgstab"):
+            raise ValueError("b200 backend: 'solver' must be 'cg' or 'bicgstab' (Jacobi-preconditioned Krylov), got %r"
+                             % (self.krylov,))
+        pc = _get(static_settings, "type of preconditioner", None)
+        if pc not in (None, "jacobi", "none"):
+            raise ValueError("b200 backend: 'type of preconditioner' %r not supported (jacobi)" % (pc,))
+        self.jacobi = pc == "jacobi"
+        self.verbose = _get(static_settings, "verbose", 0)
+        modes = _get(static_settings, "assembling mode", required=True)
+        self.n_sets = len(modes)
+        structure = _per_set(_get(static_settings, "solution structure", "off"), self.n_sets, "solution structure")
+        for s in structure:
+            if s not in ("nodal imposition", "off"):
+                raise ValueError("b200 backend: 'solution structure' %r not supported (nodal imposition, off)" % (s,))
+        # solver.py:584: `"nodal imposition" in static_settings["solution structure"]`
+        self.nodal_imposition = "nodal imposition" in structure
+        model_list = _get(static_settings, "model", required=True)
+        if len(model_list) != self.n_sets:
+            raise ValueError("b200 backend: one model per domain expected")
+        if _get(static_settings, "known sparsity pattern", "none") != "none":
+            raise ValueError("b200 backend: 'known sparsity pattern' is not supported")
+        self.shape_mode = _get(static_settings, "shape function mode", None)
+        self.sets = []
+        for i, mode in enumerate(modes):
+            m = models.recognise(model_list[i])
+            if mode in ("user element", "user potential"):
+                if not isinstance(m, models.ElementModel):
+                    raise ValueError("b200 backend: domain %d: assembling mode %r needs an isoparametric element model" % (i, mode))
+                if (mode == "user potential") != (m.weak.name == "poisson_potential"):
+                    raise ValueError("b200 backend: domain %d: model %r does not match assembling mode %r" % (i, m.weak, mode))
+                self.sets.append(("element", m))
+            elif mode == "sparse":
+                if not isinstance(m, models.WeakForm):
+                    raise ValueError("b200 backend: domain %d: 'sparse' mode needs a weak form" % i)
+                scheme = _per_set(_get(static_settings, "variational scheme", required=True), self.n_sets, "variational scheme")[i]
+                space = _per_set(_get(static_settings, "solution space", required=True), self.n_sets, "solution space")[i]
+                if scheme != "weak form galerkin" or space != "fem simplex":
+                    raise ValueError("b200 backend: domain %d: 'sparse' mode supports 'weak form galerkin' on 'fem simplex' "
+                                     "only, got %r / %r" % (i, scheme, space))
+                if self.shape_mode not in ("direct", "compiled"):
+                    raise ValueError("b200 backend: 'shape function mode' must be 'direct' or 'compiled'")
+                self.sets.append(("sparse", m))
+            else:
+                raise ValueError("b200 backend: assembling mode %r of domain %d is not supported "
+                                 "(user element, user potential, sparse)" % (mode, i))
+        self.key = (self.solver_type, self.krylov, self.jacobi, self.nodal_imposition, self.shape_mode,
+                    tuple(id(model_list[i]) for i in range(self.n_sets)), tuple(modes))
+
+
+def validate(static_settings):
+    """Reject unsupported static_settings (raises ValueError); returns the parsed configuration."""
+    return _Config(static_settings)
+
+
+# ---- host evaluation of coefficient callables ---------------------------------------------------------
+def _call(fun, x, settings):
+    if len(signature(fun).parameters) == 1:
+        return fun(x)
+    return fun(x, settings)
+
+
+def _eval_points(fun, pts, settings, ncomp, vectorized=None):
+    """Values of `fun` at pts (n, dim) -> (n,) or (n, ncomp); constants stay constants."""
+    if fun is None:
+        return None
+    if not callable(fun):
+        return np.asarray(fun, dtype=np.float64)
+    n = pts.shape[0]
+    want = (n,) if ncomp == 1 else (n, ncomp)
+    if vectorized or (vectorized is None and n > 64):
+        try:
+            v = np.asarray(_call(fun, pts, settings), dtype=np.float64)
+        except Exception:
+            v = None
+        if v is not None:
+            if v.shape == (() if ncomp == 1 else (ncomp,)):
+                return v                                   # constant
+            if v.shape == want:
+                probe = [0, n // 2, n - 1]                 # guard against accidental broadcasting
+                ok = all(np.allclose(np.asarray(_call(fun, pts[i], settings), dtype=np.float64), v[i], rtol=1e-13,
+                                     atol=1e-300) for i in probe)
+                if ok:
+                    return v
+        if vectorized:
+            raise ValueError("b200 backend: %r was declared vectorized but did not map an (n, dim) array to %s" % (fun, want))
+        if n > 2_000_000:
+            raise ValueError("b200 backend: coefficient callable %r is not vectorisable over %d points" % (fun, n))
+    out = np.empty(want)
+    for i in range(n):
+        out[i] = np.asarray(_call(fun, pts[i], settings), dtype=np.float64)
+    return out
+
+
+_NCOMP_NF = ("body_load", "traction")
+
+
+class _State:
+    """Plan + device buffers for one (mesh, model configuration)."""
+
+    def __init__(self, cfg, dofs, settings):
+        self.cfg = cfg
+        self.dict_key = None
+        if isinstance(dofs, Mapping):
+            keys = list(dofs.keys())
+            if len(keys) != 1:
+                raise ValueError("b200 backend: dict dofs with %d fields are not supported (single field only)" % len(keys))
+            self.dict_key = keys[0]
+        d0 = self._unwrap(dofs)
+        coords = np.asarray(self._unwrap(settings["node coordinates"]), dtype=np.float64)
+        self.n_nodes, self.dim = coords.shape
+        self.nf = 1 if d0.ndim == 1 else d0.shape[-1]
+        if d0.size != self.n_nodes * self.nf:
+            raise ValueError("b200 backend: dofs and node coordinates disagree on the number of nodes")
+        self.conn_refs = [self._unwrap(c) for c in settings["connectivity"]]
+        specs = []
+        for i, (route, m) in enumerate(cfg.sets):
+            conn = np.asarray(self.conn_refs[i])
+            if route == "element":
+                specs.append(backend.SetSpec(m.kind, m.weak.name, conn, family=m.family, gp=m.gp, mode=m.weak.mode))
+            else:
+                specs.append(backend.SetSpec("intpoint", m.name, conn, mode=m.mode))
+        mask = None
+        if cfg.nodal_imposition:
+            mask = np.asarray(self._unwrap(settings["dirichlet dofs"])).astype(bool).ravel()
+        self.mask = mask
+        self.plan = backend.Plan(self.dim, self.n_nodes, self.nf, specs, mask)
+        # multi-GPU: this process holds one slab (owned nodes + ghost planes, local ids in global order)
+        self.partition = settings.get("b200 partition")
+        if self.partition:
+            pt = self.partition
+            self.plan.set_partition(pt["owned_node_begin"] * self.nf, pt["owned_node_end"] * self.nf,
+                                    pt.get("rank_lo", -1), pt.get("rank_hi", -1))
+        n = self.plan.n_dofs
+        self.dofs_d = backend.DeviceArray(n)
+        self.vals_d = backend.DeviceArray(n)
+        self.out_d = backend.DeviceArray(n)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _unwrap(self, x):
+        if isinstance(x, Mapping):
+            if self.dict_key is None or list(x.keys()) != [self.dict_key]:
+                raise ValueError("b200 backend: dict-valued settings must have exactly the field of the dofs dict")
+            return np.asarray(x[self.dict_key])
+        return np.asarray(x)
+
+    # -- per-call upload of everything that lives in `settings` --------------------------------------
+    def update_fields(self, settings):
+        cfg, plan = self.cfg, self.plan
+        self.h2d_bytes = 0
+        coords = np.ascontiguousarray(self._unwrap(settings["node coordinates"]), dtype=np.float64)
+        plan.set_coords(coords)
+        self.h2d_bytes += coords.nbytes
+        for i, (route, m) in enumerate(cfg.sets):
+            weak = m.weak if route == "element" else m
+            conn = np.asarray(self.conn_refs[i])
+            if route == "element":
+                xi = m.gp[0].reshape(len(m.gp[1]), -1)
+                if m.physical_x:
+                    N, _ = spaces.shape_tables(m.family, conn.shape[1], xi.shape[1], xi)
+                    pts = np.einsum("ga,nad->ngd", N, coords[conn]).reshape(-1, self.dim)
+                else:
+                    pts = xi                                        # reference coordinates (models.py:1671-1679)
+                n_gp = xi.shape[0]
+            else:
+                n_gp = 1
+                x_int = np.asarray(settings["integration coordinates"][i], dtype=np.float64)
+                if cfg.shape_mode == "compiled":
+                    pts = np.zeros((1, self.dim))                   # variational_schemes.py:214-215
+                else:
+                    pts = x_int
+                self._upload_intpoint_tables(i, settings, conn, coords, x_int)
+            for name, fun in weak.funs.items():
+                ncomp = self.nf if name in _NCOMP_NF else 1
+                v = _eval_points(fun, pts, settings, ncomp, getattr(weak, "vectorized", None))
+                if v is None:
+                    continue
+                if route == "element" and m.physical_x and v.ndim >= 1 and v.shape[0] == pts.shape[0]:
+                    v = v.reshape((conn.shape[0], n_gp) + v.shape[1:])
+                plan.set_param(i, name, v)
+                self.h2d_bytes += np.asarray(v).nbytes
+            if weak.name == "capacity":
+                plan.set_time_increment(float(settings["time increment"]))
+                dn = np.asarray(settings["dofs n"], dtype=np.float64)
+                plan.set_dofs_n(dn)
+                self.h2d_bytes += dn.nbytes
+
+    def _upload_intpoint_tables(self, i, settings, conn, coords, x_int):
+        w = np.asarray(settings["integration weights"][i], dtype=np.float64)
+        if self.cfg.shape_mode == "compiled":
+            f, df = settings["compiled shape functions"][i][:2]
+            N, dN = np.asarray(f, dtype=np.float64), np.asarray(df, dtype=np.float64)
+        else:
+            N, dN = spaces.simplex_physical_tables(x_int, coords[conn])
+        self.plan.set_intpoint_tables(i, N.reshape(conn.shape), dN.reshape(conn.shape + (self.dim,)), w)
+        self.h2d_bytes += N.nbytes + dN.nbytes + w.nbytes
+
+
+def _state_for(cfg, dofs, settings):
+    conns = settings["connectivity"]
+    ids = []
+    for c in conns:
+        arr = next(iter(c.values())) if isinstance(c, Mapping) else c
+        ids.append((id(arr), tuple(np.shape(arr))))
+    dd = settings.get("dirichlet dofs") if cfg.nodal_imposition else None
+    if isinstance(dd, Mapping):
+        dd = next(iter(dd.values()))
+    mask_key = None if dd is None else hash(np.asarray(dd).astype(bool).tobytes())
+    d0 = next(iter(dofs.values())) if isinstance(dofs, Mapping) else dofs
+    key = (cfg.key, tuple(ids), mask_key, tuple(np.shape(d0)))
+    st = _PLAN_CACHE.get(key)
+    if st is None:
+        st = _State(cfg, dofs, settings)
+        _PLAN_CACHE[key] = st
+        while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+            _, old = _PLAN_CACHE.popitem(last=False)
+            old.plan.destroy()
+    else:
+        _PLAN_CACHE.move_to_end(key)
+    return st
+
+
+def clear_plan_cache():
+    while _PLAN_CACHE:
+        _, old = _PLAN_CACHE.popitem()
+        old.plan.destroy()
+
+
+# ---- the entry point --------------------------------------------------------------------------------------
+def solver(dofs, settings, static_settings, newton_tol=1e-8, maxiter=30, damping_coefficient=None,
+           tol=1e-10, atol=0.0, krylov_maxiter=0, **kwargs):
+    """Drop-in for autopdex.solver.solver with 'solver backend': 'b200' (solver.py:41-137)."""
+    global last_stats
+    cfg = _Config(static_settings)
+    if kwargs:
+        raise ValueError("b200 backend: unknown keyword arguments %s" % sorted(kwargs))
+    st = _state_for(cfg, dofs, settings)
+    st.update_fields(settings)
+    plan = st.plan
+    d0 = np.ascontiguousarray(st._unwrap(dofs), dtype=np.float64)
+    st.dofs_d.upload(d0.ravel())
+    st.h2d_bytes += d0.nbytes
+    vals_d = None
+    if cfg.nodal_imposition:
+        dv = np.ascontiguousarray(st._unwrap(settings["dirichlet conditions"]), dtype=np.float64)
+        st.vals_d.upload(dv.ravel())
+        st.h2d_bytes += dv.nbytes
+        vals_d = st.vals_d
+    opts = backend.KrylovOptions(cfg.krylov, rtol=tol, atol=atol, maxiter=krylov_maxiter, jacobi=cfg.jacobi)
+
+    def wrap(flat):
+        arr = flat.reshape(d0.shape)
+        return {st.dict_key: arr} if st.dict_key is not None else arr
+
+    if cfg.solver_type == "linear":
+        plan.linear_step(opts, st.dofs_d, vals_d, st.out_d)
+        sol = st.out_d.download()
+        infos = None
+    else:
+        damping = 1.0 if cfg.solver_type == "newton" else (0.8 if damping_coefficient is None else damping_coefficient)
+        n_it, res, div = plan.newton(opts, st.dofs_d, vals_d, newton_tol, maxiter, damping)
+        sol = st.dofs_d.download()
+        infos = (n_it, res, div)
+        if cfg.verbose > 0:
+            print("Residual after Newton iteration %d: %s" % (n_it, res))
+        if div and n_it > maxiter:
+            print("Warning: Newton scheme could not converge!")
+    st.d2h_bytes = sol.nbytes
+    last_stats = dict(plan.stats(), h2d_bytes=st.h2d_bytes, d2h_bytes=st.d2h_bytes)
+    return wrap(sol), infos
+
+
+def adaptive_load_stepping(dofs, settings, static_settings,
+                           multiplier_settings=lambda settings, multiplier: (settings.update({"load multiplier": multiplier}), settings)[1],
+                           path_dependent=True, implicit_diff_mode=None, max_multiplier=1.0, min_increment=0.01,
+                           max_increment=1.0, init_increment=0.2, max_load_steps=1000, target_num_newton_iter=7,
+                           newton_tol=1e-10, **kwargs):
+    """autopdex.solver.adaptive_load_stepping (solver.py:155-457) around the b200 Newton solve.
+    Returns the reference's carry (dofs, multiplier, increment, load_step, settings, res_norm)."""
+    if implicit_diff_mode is not None:
+        raise ValueError("b200 backend: implicit differentiation is not supported (implicit_diff_mode must be None)")
+    cfg = _Config(static_settings)
+    if cfg.solver_type not in ("newton", "damped newton"):
+        raise ValueError("adaptive_load_stepping works only with solver types 'newton' and 'damped newton'")
+    settings = dict(settings)
+    multiplier, increment, res_norm, load_step = 0.0, init_increment, 0.0, 0.0
+    while multiplier < max_multiplier and increment > min_increment:      # solver.py:296-300
+        multiplier += increment                                           # :316
+        if cfg.verbose > -1:
+            print("Multiplier: %s" % multiplier)
+        settings = multiplier_settings(settings, multiplier)              # :323
+        new, (steps, res_norm, diverged) = solver(dofs, settings, static_settings, newton_tol=newton_tol, **kwargs)
+        if diverged:                                                      # :356-371
+            multiplier -= increment
+            increment *= 0.5
+        else:
+            increment *= 1 + 0.5 * (target_num_newton_iter - steps) / target_num_newton_iter
+            dofs = new
+        increment = min(increment, max_increment)                         # :363
+        if multiplier + increment > max_multiplier:                       # :374-378
+            increment = max_multiplier - multiplier
+    if multiplier < max_multiplier - min_increment and increment < min_increment:
+        print("Adaptive load stepping could not converge; increment size below min_increment!")
+    return dofs, multiplier, increment, load_step, settings, res_norm

@@ -95,3 +95,29 @@ def shape_tables(family, nen, dim_ref, xi):
             raise ValueError("element with %d nodes in %d-D is not a supported P1/P2 triangle/tetrahedron" % (nen, dim_ref))
         return _simplex_tables(dim_ref, nen, xi)
     raise ValueError("unknown element family %r" % family)
+
+
+def simplex_physical_tables(x_eval, x_nodes):
+    """P1/P2 shape values and PHYSICAL gradients of 'fem simplex' in integration-point mode.
+
+    spaces.fem_ini_simplex (spaces.py:15194-15296) fits a complete polynomial of order 1 or 2 in
+    coordinates shifted to the evaluation point through the nodal values; with as many nodes as
+    monomials the fit interpolates, so N = row of the inverse Vandermonde matrix belonging to the
+    constant monomial and dN/dx_d = row of the monomial x_d.  Batched over integration points.
+    x_eval (n, dim), x_nodes (n, nen, dim) -> N (n, nen), dNdx (n, nen, dim).
+    """
+    x_eval = np.asarray(x_eval, dtype=np.float64)
+    x_nodes = np.asarray(x_nodes, dtype=np.float64)
+    n, nen, dim = x_nodes.shape
+    order = {(2, 3): 1, (2, 6): 2, (3, 4): 1, (3, 10): 2}.get((dim, nen))
+    if order is None:
+        raise ValueError("'fem simplex' with %d nodes in %d-D is not supported (P1/P2 only)" % (nen, dim))
+    y = x_nodes - x_eval[:, None, :]
+    cols = [np.ones((n, nen))] + [y[:, :, d] for d in range(dim)]
+    if order == 2:
+        for d in range(dim):
+            for e in range(d, dim):
+                cols.append(y[:, :, d] * y[:, :, e])
+    V = np.stack(cols, axis=2)                      # (n, nen, n_monomials == nen)
+    Cinv = np.linalg.inv(V)                         # coefficients = Cinv @ nodal values
+    return Cinv[:, 0, :].copy(), np.stack([Cinv[:, 1 + d, :] for d in range(dim)], axis=2)

@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the b200 hot path on BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size M]
+
+A *step* is one pass of the hot path = one Newton step of the 3-D Q1-hex Poisson problem
+(BASELINE.json configs[3]: M^3 hex8, default M=256 -> 16 974 593 dofs): Dirichlet imposition,
+fused tangent+residual assembly, Jacobi-PCG to rtol 1e-8, update, residual assembly + norm.
+  value      elements / device time of the step (apdx_newton, inputs resident in HBM, CUDA events)
+  e2e        the same through the public API autopdex_b200.solver.solver(dofs, settings,
+             static_settings) with HOST NumPy buffers (H2D of coordinates / dofs / Dirichlet
+             values and D2H of the solution inside the timed region)
+  roofline   SpMV kernel: algorithmic bytes nnz*12 + n*16 + (n+1)*4 / CUDA-event time
+  cpu_baseline / --impl reference: the reference's CPU path (oracle assembly restating the JAX half +
+             the reference's own SciPy calls) on a bounded sample mesh, host cores of this box.
+N > 1 (torchrun): strong scaling, the M^3 mesh is split into slabs along i, one rank per GPU,
+NCCL halo exchange + all-reduce; timing is the max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UNIT_CUBE = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
+METRIC = "elements/s through one Newton step (sparse assembly + Jacobi-PCG to 1e-8)"
+UNIT = "elements/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- workload ------------------------------------------------------------------------------------------
+def local_poisson_mesh(m, rank, nranks):
+    """Slab [rank] of the m^3 brick mesh of the unit cube, nodes in global order (local id = global - node_lo)."""
+    from autopdex_b200 import mesher
+    part = mesher.slab_partition((m, m, m), rank, nranks)
+    g0, g1 = part["plane_lo"], part["plane_hi"]
+    lin = np.linspace(-1.0, 1.0, m + 1)
+    v = np.asarray(UNIT_CUBE)
+    S, T, U = np.meshgrid(lin[g0:g1], lin, lin, indexing="ij")
+    s, t, u = S.reshape(-1, 1), T.reshape(-1, 1), U.reshape(-1, 1)
+    coords = ((1 - s) * (1 - t) * (1 - u) * v[0] + (1 + s) * (1 - t) * (1 - u) * v[1] + (1 + s) * (1 + t) * (1 - u) * v[2]
+              + (1 - s) * (1 + t) * (1 - u) * v[3] + (1 - s) * (1 - t) * (1 + u) * v[4] + (1 + s) * (1 - t) * (1 + u) * v[5]
+              + (1 + s) * (1 + t) * (1 + u) * v[6] + (1 - s) * (1 + t) * (1 + u) * v[7]) / 8
+    del S, T, U, s, t, u
+    e0, e1 = part["elem_lo"], part["elem_hi"]
+    I, J, K = [a.ravel() for a in np.meshgrid(np.arange(e0, e1), np.arange(m), np.arange(m), indexing="ij")]
+    sy, sx = m + 1, (m + 1) * (m + 1)
+    n0 = (I - g0) * sx + J * sy + K
+    elems = np.stack([n0, n0 + sx, n0 + sx + sy, n0 + sy, n0 + 1, n0 + sx + 1, n0 + sx + sy + 1, n0 + sy + 1],
+                     axis=1).astype(np.int32)
+    tol = 1e-12
+    mask = np.zeros(coords.shape[0], dtype=bool)
+    for d in range(3):
+        mask |= (np.abs(coords[:, d]) < tol) | (np.abs(coords[:, d] - 1.0) < tol)
+    owned_elems = (min(part["owned_plane_hi"], m) - part["owned_plane_lo"]) * m * m  # elements attributed to this rank
+    return part, coords, elems, mask, owned_elems
+
+
+def build_problem(m, rank, nranks):
+    from autopdex_b200 import models, seeder, spaces
+    part, coords, elems, mask, owned_elems = local_poisson_mesh(m, rank, nranks)
+    weak = models.poisson_weak(lambda x, settings: 1.0, lambda x: 1.0)
+    elem = models.isoparametric_domain_element_galerkin(weak, spaces.fem_iso_line_quad_brick,
+                                                        *seeder.gauss_legendre_nd(dimension=3, order=2))
+    static_settings = {"assembling mode": ("user element",), "solution structure": ("nodal imposition",),
+                       "model": (elem,), "solver type": "newton", "solver backend": "b200", "solver": "cg",
+                       "type of preconditioner": "jacobi", "verbose": -1}
+    settings = {"connectivity": (elems,), "node coordinates": coords, "dirichlet dofs": mask[:, None],
+                "dirichlet conditions": np.zeros((coords.shape[0], 1))}
+    if nranks > 1:
+        settings["b200 partition"] = dict(owned_node_begin=part["owned_node_lo"] - part["node_lo"],
+                                          owned_node_end=part["owned_node_hi"] - part["node_lo"],
+                                          rank_lo=part["rank_lo"], rank_hi=part["rank_hi"])
+    return settings, static_settings, owned_elems
+
+
+# ---- CPU reference path (oracle + the reference's SciPy calls) --------------------------------------------------
+def cpu_reference_step(m, solver="lapack"):
+    """One Newton step of the same problem on an m^3 sample with the reference 'scipy' backend semantics.
+    Returns (seconds, elements, breakdown dict)."""
+    from oracle import assemble as oasm
+    from oracle import solve as osolve
+    from tests import problems
+    p = problems.poisson_hex(m)
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+    dofs = np.zeros(p["mask"].shape)
+    t0 = time.perf_counter()
+    dofs[p["mask"]] = p["values"][p["mask"]]
+    R, data = oasm.assemble(p["sets"], p["coords"], dofs, {})                  # B-asm (restated JAX half)
+    t1 = time.perf_counter()
+    rows, cols = prob.coo()
+    free = ~p["mask"].ravel()
+    csr = oasm.scipy_assembling(data, rows, cols, dofs.size, free)             # B-dup (reference's own SciPy calls)
+    t2 = time.perf_counter()
+    import scipy.sparse.linalg as spla
+    b = -R[free]
+    if solver == "lapack":
+        x = spla.spsolve(csr, b)                                               # B-direct (SuperLU, solver.py:1520)
+    else:
+        d = csr.diagonal()
+        x, _ = spla.cg(csr, b, M=spla.LinearOperator(csr.shape, matvec=lambda v: v / d), rtol=1e-8, atol=0.0)
+    t3 = time.perf_counter()
+    dofs.ravel()[free] += x
+    R2 = prob.residual(dofs)                                                   # 2nd residual assembly of the step
+    np.linalg.norm(R2[free])
+    t4 = time.perf_counter()
+    n_el = p["sets"][0]["conn"].shape[0]
+    return t4 - t0, n_el, {"assembly_s": t1 - t0, "dup_sum_s": t2 - t1, "solve_s": t3 - t2, "residual_s": t4 - t3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    m = args.ref_size
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, n_el, br = cpu_reference_step(m, "lapack")
+        if i >= args.warmup:
+            times.append(dt)
+    dt = float(np.mean(times))
+    cg_dt, _, cg_br = cpu_reference_step(m, "cg")
+    value = n_el / dt
+    sample = ("%d^3 hex8 Poisson sample of the %d^3 workload (%d elements), reference 'scipy'/'lapack' path: "
+              "NumPy restatement of the JAX assembly + scipy coo->csr->[:,free][free] + spsolve" % (m, args.size, n_el))
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D Poisson Q1 hex %d^3 Newton step (sample %d^3 on CPU)" % (args.size, m)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "breakdown_s": br, "threads_used": "NumPy/SciPy (BLAS threads only), SuperLU serial",
+                             "jacobi_pcg_variant": {"value": n_el / cg_dt, "unit": UNIT, "breakdown_s": cg_br}},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---- own arm -----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    from autopdex_b200 import backend, solver
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if _device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the b200 backend has no CPU path")
+    backend.set_device(local_rank)
+    if world > 1:
+        from torch.distributed import TCPStore  # plumbing only: ships the NCCL id between ranks
+        store = TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")) + 1,
+                         world, rank == 0)
+        if rank == 0:
+            store.set("apdx_nccl_id", backend.comm_unique_id())
+        backend.comm_init(bytes(store.get("apdx_nccl_id")), rank, world)
+
+    m = args.size
+    t_mesh = time.perf_counter()
+    settings, static_settings, owned_elems = build_problem(m, rank, world)
+    t_mesh = time.perf_counter() - t_mesh
+    n_local = settings["node coordinates"].shape[0]
+    dofs0 = np.zeros((n_local, 1))
+    total_elems = m ** 3
+
+    def barrier():
+        backend.comm_allreduce_host(np.zeros(1))
+
+    # ---- end-to-end through the public API (host buffers in, host solution out) ----
+    t_plan = time.perf_counter()
+    sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)       # builds + caches the plan
+    t_plan = time.perf_counter() - t_plan
+    for _ in range(max(args.warmup - 1, 0)):
+        sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    launches_e2e = 0
+    for _ in range(args.steps):
+        sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)
+        launches_e2e += solver.last_stats["kernel_launches"]
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_s = float(backend.comm_allreduce_host([e2e_s], "max")[0])
+    st_e2e = dict(solver.last_stats)
+
+    # ---- device-resident steps: apdx_newton on HBM-resident inputs, CUDA-event timing inside the plan ----
+    state = next(iter(solver._PLAN_CACHE.values()))
+    plan = state.plan
+    opts = backend.KrylovOptions("cg", rtol=args.rtol, jacobi=True)
+    step_ms, asm_ms, res_ms, kry_ms, iters, launches = [], [], [], [], [], 0
+    for i in range(args.warmup + args.steps):
+        state.dofs_d.zero()
+        if i == args.warmup:
+            barrier()
+        n_it, rn, div = plan.newton(opts, state.dofs_d, state.vals_d, 1e-8, 30, 1.0)
+        s = plan.stats()
+        if i >= args.warmup:
+            step_ms.append(s["total_ms"]); asm_ms.append(s["assembly_tangent_ms"]); res_ms.append(s["assembly_residual_ms"])
+            kry_ms.append(s["krylov_ms"]); iters.append(s["krylov_iters"]); launches += s["kernel_launches"]
+    barrier()
+    ms = float(backend.comm_allreduce_host([np.mean(step_ms)], "max")[0])
+    spmv_ms = plan.time_spmv(20)
+    spmv_ms = float(backend.comm_allreduce_host([spmv_ms], "max")[0])
+    clocks = sampler.stop()
+
+    # ---- parity guard on the full-size run: residual norm and a discrete maximum principle ----
+    owned = slice(settings.get("b200 partition", {}).get("owned_node_begin", 0),
+                  settings.get("b200 partition", {}).get("owned_node_end", n_local))
+    sol_sum = float(backend.comm_allreduce_host([np.asarray(sol)[owned].sum()])[0])
+    ok = (info[0] == 1) and (not info[2]) and info[1] < 1e-8
+
+    nnz, nfree = plan.nnz_reduced, plan.n_free
+    rows = plan.f1 - plan.f0
+    spmv_bytes = nnz * 12 + rows * 16 + (rows + 1) * 4            # per rank (local reduced system incl. ghost columns)
+    hbm, which = peaks()
+    spmv_gbs = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    cg_iter_bytes = spmv_bytes + 72 * rows
+    mean_iters = float(np.mean(iters))
+    cg_gbs = cg_iter_bytes * mean_iters / (np.mean(kry_ms) * 1e-3) / 1e9
+    asm_elems = state.plan.sets[0].conn.shape[0]
+    asm_gbs = asm_elems * 290.0 / (np.mean(asm_ms) * 1e-3) / 1e9
+
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": total_elems / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D Poisson Q1 hex %d^3 (%d dofs), Newton + Jacobi-PCG rtol %.0e, slab-partitioned over %d GPU(s)"
+                               % (m, (m + 1) ** 3, args.rtol, world),
+                   "l2": "inputs larger than L2 (reduced CSR %.2f GB per rank)" % (nnz * 12 / 1e9),
+                   "parity_guard": {"newton_steps": info[0], "res_norm": info[1], "diverged": bool(info[2]), "ok": bool(ok),
+                                    "solution_sum": sol_sum}},
+        "clocks": clocks,
+        "e2e": {"value": total_elems / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
+                "plan_build_s_first_call": t_plan, "mesh_generation_s": t_mesh},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_spmv_csr (reduced CSR SpMV + fused p.Ap)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm,
+                     "unit": "GB/s", "frac": spmv_gbs / hbm, "frac_of_nominal_8TBs": spmv_gbs / 8000.0, "peak_source": which,
+                     "traffic": None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms},
+        "newton_step_ms": ms,
+        "assembly": {"elements_per_s": asm_elems / (np.mean(asm_ms) * 1e-3), "ms": float(np.mean(asm_ms)),
+                     "residual_only_ms": float(np.mean(res_ms)), "algorithmic_gbs": asm_gbs,
+                     "frac_of_hbm": asm_gbs / hbm, "bytes_per_element": 290},
+        "cg": {"iterations": mean_iters, "ms_per_iteration": float(np.mean(kry_ms)) / max(mean_iters, 1),
+               "algorithmic_gbs": cg_gbs, "frac_of_hbm": cg_gbs / hbm, "krylov_ms": float(np.mean(kry_ms))},
+        "system": {"n_free": nfree, "nnz_reduced": nnz, "plan_device_gb": plan.device_bytes / 1e9},
+    }
+    if world == 1 and not args.no_cpu:
+        dt, n_el, br = cpu_reference_step(args.ref_size, "lapack")
+        line["cpu_baseline"] = {"value": n_el / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": "%d^3 hex8 Poisson Newton step, reference 'scipy'/'lapack' path restated "
+                                          "(NumPy assembly + SciPy duplicate summing + spsolve), %d elements, %.1f s"
+                                          % (args.ref_size, n_el, dt),
+                                "breakdown_s": br}
+    print(json.dumps(line))
+
+
+def _device_count():
+    from autopdex_b200 import _lib
+    return _lib.device_count()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=256, help="elements per direction (BASELINE: 256)")
+    ap.add_argument("--ref-size", type=int, default=32, help="elements per direction of the bounded CPU sample")
+    ap.add_argument("--rtol", type=float, default=1e-8)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -179,6 +179,10 @@ int apdx_newton(apdx_plan *plan, const apdx_krylov_opts *opts, double *dofs_d,
  * out[3]=krylov iterations out[4]=spmv launches out[5]=total out[6]=kernel launches       */
 int apdx_plan_stats(const apdx_plan *plan, double out[8]);
 
+/* average device time (ms, CUDA events on the plan's stream) of `reps` launches of the SpMV kernel
+ * exactly as the CG loop launches it (fused p.Ap dot product included) */
+int apdx_time_spmv(apdx_plan *plan, int32_t reps, double *ms_avg);
+
 /* ---- multi-GPU (one process per GPU, slab partition) -------------------- *
  * Each rank builds a plan of its LOCAL mesh (owned nodes plus one ghost plane per side,
  * local ids in global order).  owned dofs are the contiguous range [begin,end) of local
@@ -187,6 +191,8 @@ int apdx_plan_stats(const apdx_plan *plan, double out[8]);
 int apdx_comm_unique_id(uint8_t id_out[128]);
 int apdx_comm_init(const uint8_t id[128], int32_t rank, int32_t nranks);
 int apdx_comm_destroy(void);
+/* host-side collective for scalars (timings, counters): op 0 = sum, 1 = max; no-op without a communicator */
+int apdx_comm_allreduce_host(double *inout_h, int32_t count, int32_t op);
 int apdx_plan_set_partition(apdx_plan *plan, int64_t owned_dof_begin, int64_t owned_dof_end,
                             int32_t rank_lo, int32_t rank_hi);
 
