@@ -90,8 +90,16 @@ static inline unsigned g1(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 static int assemble_internal(apdx_plan *pl, const double *dofs_d, int tangent_flags, double *residual_d) {
   APDX_CHECK(launch_element_kernels(pl, dofs_d, tangent_flags != 0));
-  APDX_CHECK(launch_gather_reduce(pl, tangent_flags, residual_d));
-  if (tangent_flags) pl->have_values = true;
+  // tangent_flags: bit 0 full CSR values, bit 1 reduced CSR values (cold paths), bit 2 sliced-ELL values (solver)
+  APDX_CHECK(launch_gather_reduce(pl, tangent_flags & 3, residual_d));
+  if (tangent_flags & 4) {
+    APDX_CHECK(sell_gather_reduce(pl));
+    pl->have_sell_values = true;
+  }
+  if (tangent_flags) {
+    pl->have_values = (tangent_flags & 1) != 0;
+    pl->have_red_values = (tangent_flags & 2) != 0;
+  }
   return APDX_OK;
 }
 
@@ -128,7 +136,7 @@ static float elapsed(cudaEvent_t a, cudaEvent_t b) {
 static int linear_step_internal(apdx_plan *pl, const apdx_krylov_opts *opts, const double *dofs_d, int32_t *kiters) {
   cudaStream_t s = pl->stream;
   APDX_CUDA(cudaEventRecord(pl->ev[0], s));
-  APDX_CHECK(assemble_internal(pl, dofs_d, 2, pl->residual.p));
+  APDX_CHECK(assemble_internal(pl, dofs_d, 4, pl->residual.p));
   k_rhs_reduced<<<g1(pl->n_free), 256, 0, s>>>(pl->residual.p, pl->free_list.p, pl->n_free, pl->rhs_red.p, pl->x_red.p);
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaEventRecord(pl->ev[1], s));
@@ -340,6 +348,7 @@ int apdx_plan_destroy(apdx_plan *pl) {
   pl->row_ptr.release(); pl->col.release(); pl->elem_map.release(); pl->perm.release(); pl->seg_ptr.release();
   pl->rperm.release(); pl->rseg_ptr.release(); pl->red_row_ptr.release(); pl->red_col.release();
   pl->red2full.release(); pl->red_diag.release(); pl->ke.release(); pl->re.release(); pl->vals.release();
+  pl->sell.release();
   pl->red_vals.release(); pl->residual.release(); pl->rhs_red.release(); pl->x_red.release(); pl->dofs_trial.release();
   KrylovWork &k = pl->kw;
   k.r.release(); k.p.release(); k.q.release(); k.z.release(); k.s.release(); k.t.release(); k.phat.release();
@@ -451,17 +460,26 @@ int apdx_set_dofs_n(apdx_plan *pl, const double *dofs_n_h) {
 // ---- assembly / linear algebra ---------------------------------------------------------------------------
 int apdx_assemble(apdx_plan *pl, const double *dofs_d, int want_tangent, double *residual_d) {
   APDX_REQUIRE(pl && dofs_d, APDX_ERR_INVALID, "NULL argument");
-  APDX_CHECK(assemble_internal(pl, dofs_d, want_tangent ? 3 : 0, residual_d));
+  APDX_CHECK(assemble_internal(pl, dofs_d, want_tangent ? 5 : 0, residual_d));
   APDX_CUDA(cudaStreamSynchronize(pl->stream));
   return APDX_OK;
 }
 
 int apdx_get_values(const apdx_plan *pl, int reduced, double *values_h) {
   APDX_REQUIRE(pl && values_h, APDX_ERR_INVALID, "NULL argument");
-  APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
+  APDX_REQUIRE(pl->have_values || pl->have_sell_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
   if (reduced) {
+    // cold path: the solver keeps the reduced system in sliced-ELL form; the CSR-ordered copy is summed on demand
+    // from the element matrices of the last assembly
+    apdx_plan *mpl = const_cast<apdx_plan *>(pl);
+    if (!pl->have_red_values) {
+      APDX_CHECK(launch_gather_reduce(mpl, 2, nullptr));
+      APDX_CUDA(cudaStreamSynchronize(pl->stream));
+      mpl->have_red_values = true;
+    }
     if (pl->nnz_red > 0) APDX_CUDA(cudaMemcpy(values_h, pl->red_vals.p, pl->nnz_red * 8, cudaMemcpyDeviceToHost));
   } else {
+    APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "full CSR values not assembled: call apdx_assemble first");
     APDX_CUDA(cudaMemcpy(values_h, pl->vals.p, pl->nnz * 8, cudaMemcpyDeviceToHost));
   }
   return APDX_OK;
@@ -590,6 +608,8 @@ int apdx_plan_set_partition(apdx_plan *pl, int64_t owned_dof_begin, int64_t owne
   APDX_CUDA(cudaMemcpyAsync(out, tmp_d, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, pl->stream));
   APDX_CUDA(cudaStreamSynchronize(pl->stream));
   cudaFree(tmp_d);
+  pl->sell.release();
+  pl->have_sell_values = false;
   pl->owned_begin = owned_dof_begin; pl->owned_end = owned_dof_end;
   pl->f0 = out[0]; pl->f1 = out[1];
   pl->rank_lo = rank_lo; pl->rank_hi = rank_hi;

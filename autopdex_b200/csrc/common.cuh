@@ -100,6 +100,23 @@ struct KrylovWork {
   DevBuf<int32_t> flags;      // [0]=done [1]=iterations [2]=breakdown
 };
 
+// sliced-ELL copy of the owned rows of the reduced system (sell.cu)
+struct Sell {
+  bool built = false;
+  int64_t row0 = 0, n_rows = 0, n_slices = 0, n_val = 0, n_idx = 0;
+  DevBuf<int32_t> sl_w;       // [n_slices] width | (offset mode ? 1<<31 : 0)
+  DevBuf<int64_t> valptr;     // [n_slices+1] start of the slice's value block (doubles)
+  DevBuf<int64_t> idxptr;     // [n_slices+1] start of the slice's index block (int32)
+  DevBuf<double> val;         // [n_val] column-major per slice
+  DevBuf<int32_t> idx;        // [n_idx] offsets (offset mode) or columns (explicit mode)
+  DevBuf<int32_t> src;        // [n_val] full-CSR entry behind each position, -1 = padding
+  DevBuf<int32_t> diag;       // [n_rows] diagonal position relative to the slice's value block, -1 = none
+  void release() {
+    sl_w.release(); valptr.release(); idxptr.release(); val.release(); idx.release(); src.release(); diag.release();
+    built = false;
+  }
+};
+
 struct Stats {
   double asm_tangent_ms = 0, asm_residual_ms = 0, krylov_ms = 0, total_ms = 0;
   double krylov_iters = 0, spmv_launches = 0, kernel_launches = 0;
@@ -145,6 +162,8 @@ struct apdx_plan {
   // Newton / Krylov work
   apdx::DevBuf<double> residual, rhs_red, x_red, dofs_trial;
   apdx::KrylovWork kw;
+  apdx::Sell sell;
+  bool have_sell_values = false, have_red_values = false;
   double *pinned = nullptr;                // small pinned host staging
   apdx::Stats stats;
 
@@ -168,6 +187,9 @@ int spmv_reduced(apdx_plan *pl, const double *x, double *y);
 int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, double *x,
                  int32_t *iters, double *relres);
 int time_spmv(apdx_plan *pl, int reps, double *ms_avg);
+// sell.cu
+int sell_build(apdx_plan *pl);
+int sell_gather_reduce(apdx_plan *pl);
 // dist.cu
 bool comm_active();
 int comm_size();

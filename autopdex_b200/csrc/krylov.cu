@@ -6,8 +6,8 @@
 // jax.scipy.sparse.linalg: ||r||_2^2 <= max(rtol^2 ||b||^2, atol^2).  No positivity checks:
 // the reference's tangents are negative definite on mesher quad meshes.
 //
-// SpMV: CSR with int32 columns, a sub-warp of TPR lanes per row, warp-shuffle row reduction,
-// the dot product(s) that follow the SpMV fused into the same kernel.  Vector updates are
+// SpMV: sliced-ELL with per-slice compressed column indices (sell.cu), 128-bit value loads, the dot
+// product(s) that follow the SpMV fused into the same kernel (warp-shuffle + fixed-order block reduction).  Vector updates are
 // fused axpy+dot kernels.  Dot products are reduced per block, then by the last block in a fixed
 // order (deterministic for a given grid), then -- multi-GPU -- by ncclAllReduce.
 #include "common.cuh"
@@ -137,34 +137,62 @@ __device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial
   }
 }
 
-// y[row] = sum_j val[j] x[col[j]] for rows [row0,row1); dots: d0 = sum w[row]*y[row], d1 = sum y[row]^2
-template <int TPR, int NDOT>
-__global__ void __launch_bounds__(VEC_BLOCK) k_spmv_csr(const int32_t *__restrict__ rp, const int32_t *__restrict__ col,
-                                                        const double *__restrict__ val, const double *__restrict__ x,
-                                                        double *__restrict__ y, const double *__restrict__ w,
-                                                        int64_t row0, int64_t row1, double *partial,
-                                                        unsigned int *ticket, double *sc, int32_t *fl, int stage,
-                                                        int fused, int check_done) {
+// Sliced-ELL SpMV (layout: sell.cu).  One warp per slice of 64 rows, two rows per lane, values read as
+// 128-bit double2 (512 contiguous bytes per warp instruction).  Offset mode: column = row + off[j]
+// (one broadcast int per slice column, x gathers coalesced); explicit mode: int2 column pairs.
+// n_cols: length of x (clamp target of the padded offsets, whose values are exact zeros).
+template <int NDOT>
+__global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restrict__ sl_w, const int64_t *__restrict__ valptr,
+                                                         const int64_t *__restrict__ idxptr, const double *__restrict__ val,
+                                                         const int32_t *__restrict__ idx, const double *__restrict__ x,
+                                                         double *__restrict__ y, const double *__restrict__ w,
+                                                         int64_t row0, int64_t row1, int64_t n_slices, int32_t n_cols,
+                                                         double *partial, unsigned int *ticket, double *sc, int32_t *fl,
+                                                         int stage, int fused, int check_done) {
   if (check_done && fl[F_DONE]) return;
-  const int sub = threadIdx.x % TPR;
-  const int64_t rows_per_block = VEC_BLOCK / TPR;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   double acc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
   for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
-  for (int64_t rb = row0 + (int64_t)blockIdx.x * rows_per_block; rb < row1; rb += (int64_t)gridDim.x * rows_per_block) {
-    const int64_t r = rb + threadIdx.x / TPR;  // block-uniform trip count: every lane reaches the shuffles
-    const bool valid = r < row1;
-    double s = 0.0;
-    if (valid) {
-      const int32_t b = rp[r], e = rp[r + 1];
-      for (int32_t j = b + sub; j < e; j += TPR) s += val[j] * __ldg(&x[col[j]]);
+  for (int64_t s = warp0; s < n_slices; s += nwarps) {
+    const int32_t wenc = sl_w[s];
+    const int32_t W = wenc & 0x7fffffff;
+    const double2 *vp = reinterpret_cast<const double2 *>(val + valptr[s]) + lane;
+    const int64_t r0 = row0 + s * 64 + 2 * lane;
+    double a0 = 0.0, a1 = 0.0;
+    if (wenc < 0) {
+      const int32_t *op = idx + idxptr[s];
+      const int32_t rr = (int32_t)r0;
+#pragma unroll 4
+      for (int32_t j = 0; j < W; ++j) {
+        const int32_t off = __ldg(op + j);
+        const double2 v = __ldcs(vp + (size_t)j * 32);
+        int32_t c0 = min(max(rr + off, 0), n_cols - 1);
+        int32_t c1 = min(max(rr + 1 + off, 0), n_cols - 1);
+        a0 += v.x * __ldg(x + c0);
+        a1 += v.y * __ldg(x + c1);
+      }
+    } else {
+      const int2 *cp = reinterpret_cast<const int2 *>(idx + idxptr[s]) + lane;
+#pragma unroll 4
+      for (int32_t j = 0; j < W; ++j) {
+        const int2 c = __ldcs(cp + (size_t)j * 32);
+        const double2 v = __ldcs(vp + (size_t)j * 32);
+        a0 += v.x * __ldg(x + c.x);
+        a1 += v.y * __ldg(x + c.y);
+      }
     }
-#pragma unroll
-    for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, TPR);
-    if (valid && sub == 0) {
-      y[r] = s;
-      if (NDOT >= 1) acc[0] += w[r] * s;
-      if (NDOT >= 2) acc[1] += s * s;
+    if (r0 < row1) {
+      y[r0] = a0;
+      if (NDOT >= 1) acc[0] += w[r0] * a0;
+      if (NDOT >= 2) acc[1] += a0 * a0;
+    }
+    if (r0 + 1 < row1) {
+      y[r0 + 1] = a1;
+      if (NDOT >= 1) acc[0] += w[r0 + 1] * a1;
+      if (NDOT >= 2) acc[1] += a1 * a1;
     }
   }
   if constexpr (NDOT > 0) reduce_finalize<NDOT>(acc, partial, ticket, sc, fl, stage, fused);
@@ -281,11 +309,13 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_bi_x(const double *__restrict__ p
   reduce_finalize<2>(acc, partial, ticket, sc, fl, ST_BI_X, fused);
 }
 
-__global__ void k_jacobi_inv(const double *__restrict__ vals, const int32_t *__restrict__ diag, int64_t n,
-                             int jacobi, double *__restrict__ minv) {
+// minv over the owned rows [row0, row0+n): 1/diag read from the sliced-ELL values (solver.py:1095)
+__global__ void k_jacobi_inv(const double *__restrict__ sell_val, const int64_t *__restrict__ valptr,
+                             const int32_t *__restrict__ diag, int64_t row0, int64_t n, int jacobi,
+                             double *__restrict__ minv) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  minv[i] = (jacobi && diag[i] >= 0) ? 1.0 / vals[diag[i]] : 1.0;  // solver.py:1095
+  minv[row0 + i] = (jacobi && diag[i] >= 0) ? 1.0 / sell_val[valptr[i >> 6] + diag[i]] : 1.0;
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -323,25 +353,15 @@ static int krylov_alloc_bicgstab(apdx_plan *pl) {
 template <int NDOT>
 static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *w, int stage, int check_done) {
   KrylovWork &k = pl->kw;
-  const int64_t rows = pl->f1 - pl->f0;
-  const double avg = rows > 0 ? (double)pl->nnz_red / (double)pl->n_free : 1.0;
+  Sell &S = pl->sell;
   const int fused = comm_active() ? 0 : 1;
-  cudaStream_t s = pl->stream;
-#define APDX_SPMV(TPR)                                                                                   \
-  do {                                                                                                   \
-    int64_t rpb = VEC_BLOCK / TPR;                                                                       \
-    int64_t nb = (rows + rpb - 1) / rpb;                                                                 \
-    int64_t cap = 148ll * 32;                                                                            \
-    unsigned grid = (unsigned)(nb < cap ? (nb > 0 ? nb : 1) : cap);                                      \
-    k_spmv_csr<TPR, NDOT><<<grid, VEC_BLOCK, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red_vals.p, x, y, w, \
-                                                     pl->f0, pl->f1, k.partial.p, k.ticket.p, k.scal.p,  \
-                                                     k.flags.p, stage, fused, check_done);               \
-  } while (0)
-  if (avg <= 6.0) APDX_SPMV(4);
-  else if (avg <= 12.0) APDX_SPMV(8);
-  else if (avg <= 40.0) APDX_SPMV(16);
-  else APDX_SPMV(32);
-#undef APDX_SPMV
+  const int64_t warps_per_block = VEC_BLOCK / 32;
+  int64_t nb = (S.n_slices + warps_per_block - 1) / warps_per_block;
+  const int64_t cap = 148ll * 32;
+  unsigned grid = (unsigned)(nb < cap ? (nb > 0 ? nb : 1) : cap);
+  k_spmv_sell<NDOT><<<grid, VEC_BLOCK, 0, pl->stream>>>(S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w,
+                                                        pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, k.partial.p,
+                                                        k.ticket.p, k.scal.p, k.flags.p, stage, fused, check_done);
   pl->stats.spmv_launches += 1;
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaGetLastError());
@@ -359,20 +379,21 @@ static int finish_stage(apdx_plan *pl, int stage, int nv) {
 }
 
 int spmv_reduced(apdx_plan *pl, const double *x, double *y) {
-  APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
+  APDX_REQUIRE(pl->have_sell_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
   APDX_CHECK(krylov_alloc(pl));
   if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, const_cast<double *>(x), pl->stream));
   return launch_spmv<0>(pl, x, y, nullptr, 0, 0);
 }
 
 int time_spmv(apdx_plan *pl, int reps, double *ms_avg) {
-  APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
+  APDX_REQUIRE(pl->have_sell_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
   APDX_CHECK(krylov_alloc(pl));
   KrylovWork &k = pl->kw;
   cudaStream_t s = pl->stream;
   const int64_t n = pl->n_free;
   // a smooth non-trivial input vector: p = minv-free copy of the diagonal positions
-  k_jacobi_inv<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pl->red_vals.p, pl->red_diag.p, n, 1, k.p.p);
+  k_jacobi_inv<<<(unsigned)((pl->sell.n_rows + 255) / 256), 256, 0, s>>>(pl->sell.val.p, pl->sell.valptr.p, pl->sell.diag.p,
+                                                                      pl->f0, pl->sell.n_rows, 1, k.p.p);
   for (int i = 0; i < 3; ++i) APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, -1, 0));
   APDX_CUDA(cudaEventRecord(pl->ev[0], s));
   for (int i = 0; i < reps; ++i) APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, -1, 0));
@@ -386,7 +407,7 @@ int time_spmv(apdx_plan *pl, int reps, double *ms_avg) {
 
 int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, double *x, int32_t *iters,
                  double *relres) {
-  APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
+  APDX_REQUIRE(pl->have_sell_values, APDX_ERR_STATE, "no assembled tangent: call apdx_assemble first");
   APDX_REQUIRE(o->method == APDX_KRYLOV_CG || o->method == APDX_KRYLOV_BICGSTAB, APDX_ERR_UNSUPPORTED,
                "Krylov method %d not supported (cg, bicgstab)", o->method);
   APDX_CHECK(krylov_alloc(pl));
@@ -399,7 +420,8 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
   const int maxiter = o->maxiter > 0 ? o->maxiter : 10 * (int)(n < 100000 ? n : 100000);
   const int chunk = o->check_every > 0 ? o->check_every : 32;
 
-  k_jacobi_inv<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pl->red_vals.p, pl->red_diag.p, n, o->jacobi, k.minv.p);
+  k_jacobi_inv<<<(unsigned)((pl->sell.n_rows + 255) / 256), 256, 0, s>>>(pl->sell.val.p, pl->sell.valptr.p, pl->sell.diag.p,
+                                                                      pl->f0, pl->sell.n_rows, o->jacobi, k.minv.p);
   double sc_h[S_COUNT] = {0};
   sc_h[S_TOL2] = o->rtol * o->rtol;
   sc_h[S_SS] = o->atol * o->atol;
