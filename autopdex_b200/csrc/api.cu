@@ -307,6 +307,9 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
       if ((rc = st.shape_n.alloc(a)) != APDX_OK || (rc = st.shape_dn.alloc(b)) != APDX_OK ||
           (rc = st.gp_w.alloc(c)) != APDX_OK)
         return fail(rc);
+      st.h_shape_n.assign(st.d.shape_n_h, st.d.shape_n_h + a);
+      st.h_shape_dn.assign(st.d.shape_dn_h, st.d.shape_dn_h + b);
+      st.h_gp_w.assign(st.d.gp_w_h, st.d.gp_w_h + c);
       cudaMemcpy(st.shape_n.p, st.d.shape_n_h, a * 8, cudaMemcpyHostToDevice);
       cudaMemcpy(st.shape_dn.p, st.d.shape_dn_h, b * 8, cudaMemcpyHostToDevice);
       cudaMemcpy(st.gp_w.p, st.d.gp_w_h, c * 8, cudaMemcpyHostToDevice);

@@ -87,6 +87,7 @@ struct SetData {
   int64_t res_offset = 0;     // offset of this set's block in the Re stream
   DevBuf<int32_t> conn;       // [n_rows][nen]
   DevBuf<double> shape_n, shape_dn, gp_w;
+  std::vector<double> h_shape_n, h_shape_dn, h_gp_w;  // host copies (kernel-argument tables of the fast kernels)
   DevBuf<double> ip_n, ip_dndx, ip_w;  // integration-point tables
   DevBuf<double> params[APDX_PARAM_COUNT];
   ParamView pview[APDX_PARAM_COUNT]{};
