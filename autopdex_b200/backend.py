@@ -244,8 +244,8 @@ class Plan:
         out = (C.c_double * 8)()
         _lib.check(_lib.load().apdx_plan_stats(self.h, out))
         keys = ("assembly_tangent_ms", "assembly_residual_ms", "krylov_ms", "krylov_iters", "spmv_launches",
-                "total_ms", "kernel_launches")
-        return dict(zip(keys, list(out)[:7]))
+                "total_ms", "kernel_launches", "sell_bytes")
+        return dict(zip(keys, list(out)[:8]))
 
     def set_partition(self, owned_dof_begin, owned_dof_end, rank_lo=-1, rank_hi=-1):
         _lib.check(_lib.load().apdx_plan_set_partition(self.h, int(owned_dof_begin), int(owned_dof_end), int(rank_lo),

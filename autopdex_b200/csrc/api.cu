@@ -594,7 +594,8 @@ int apdx_plan_stats(const apdx_plan *pl, double out[8]) {
   APDX_REQUIRE(pl && out, APDX_ERR_INVALID, "NULL argument");
   out[0] = pl->stats.asm_tangent_ms; out[1] = pl->stats.asm_residual_ms; out[2] = pl->stats.krylov_ms;
   out[3] = pl->stats.krylov_iters; out[4] = pl->stats.spmv_launches; out[5] = pl->stats.total_ms;
-  out[6] = pl->stats.kernel_launches; out[7] = 0.0;
+  out[6] = pl->stats.kernel_launches;
+  out[7] = (double)(pl->sell.n_val * 8 + pl->sell.n_idx * 4 + pl->sell.n_slices * 20);  // bytes of the sliced-ELL matrix
   return APDX_OK;
 }
 

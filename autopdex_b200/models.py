@@ -167,22 +167,28 @@ def _cells(fn):
     return out
 
 
+def _made_by(qualname, factory):
+    """True if `qualname` is that of a closure created directly inside `factory`
+    (e.g. 'poisson_weak.<locals>.pde_fun', possibly with an enclosing prefix)."""
+    return qualname.split(".")[-3:-1] == [factory, "<locals>"]
+
+
 def recognise_weak_form(fn):
     if isinstance(fn, WeakForm):
         return fn
     qn = getattr(fn, "__qualname__", "")
     c = _cells(fn)
-    if qn.startswith("poisson_weak.<locals>"):
+    if _made_by(qn, "poisson_weak"):
         return poisson_weak(c.get("coefficient_fun"), c.get("source_fun"))
-    if qn.startswith("linear_elasticity_weak.<locals>"):
+    if _made_by(qn, "linear_elasticity_weak"):
         return linear_elasticity_weak(c.get("youngs_mod_fun"), c.get("poisson_ratio_fun"), c.get("mode"),
                                       c.get("volume_load_fun"))
-    if qn.startswith("hyperelastic_steady_state_weak.<locals>"):
+    if _made_by(qn, "hyperelastic_steady_state_weak"):
         return hyperelastic_steady_state_weak(c.get("strain_energy_fun"), c.get("youngs_mod_fun"),
                                               c.get("poisson_ratio_fun"), c.get("mode"), c.get("volume_load_fun"))
-    if qn.startswith("neumann_weak.<locals>"):
+    if _made_by(qn, "neumann_weak"):
         return neumann_weak(c.get("neumann_fun"))
-    if qn.startswith("forward_backward_euler_weak.<locals>"):
+    if _made_by(qn, "forward_backward_euler_weak"):
         return forward_backward_euler_weak(c.get("inertia_coeff_fun"))
     _unsupported("model %r" % (fn,))
 
@@ -193,14 +199,14 @@ def recognise(model):
         return model
     qn = getattr(model, "__qualname__", "")
     c = _cells(model)
-    if qn.startswith("isoparametric_domain_element_galerkin.<locals>"):
+    if _made_by(qn, "isoparametric_domain_element_galerkin"):
         return isoparametric_domain_element_galerkin(c.get("weak_form_fun"), c.get("ansatz_fun"), c.get("ref_int_coor"),
                                                      c.get("ref_int_weights"), c.get("initial_config", True))
-    if qn.startswith("isoparametric_surface_element_galerkin.<locals>"):
+    if _made_by(qn, "isoparametric_surface_element_galerkin"):
         return isoparametric_surface_element_galerkin(c.get("weak_form_fun"), c.get("ansatz_fun"), c.get("ref_int_coor"),
                                                       c.get("ref_int_weights"), c.get("tangent_contributions", False),
                                                       c.get("initial_config", True))
-    if qn.startswith("mixed_reference_domain_potential.<locals>"):
+    if _made_by(qn, "mixed_reference_domain_potential"):
         return mixed_reference_domain_potential(c.get("integrand_fun"), c.get("ansatz_fun"), c.get("ref_int_coor"),
                                                 c.get("ref_int_weights"), c.get("mapping_key"))
     return recognise_weak_form(model)

@@ -30,6 +30,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 UNIT_CUBE = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_spmv_sell<1> launch from `ncu --set full` (profiles/), by mesh size
+NCU_TRAFFIC = {}
 METRIC = "elements/s through one Newton step (sparse assembly + Jacobi-PCG to 1e-8)"
 UNIT = "elements/s"
 
@@ -269,6 +271,8 @@ def run_b200(args):
     spmv_bytes = nnz * 12 + rows * 16 + (rows + 1) * 4            # per rank (local reduced system incl. ghost columns)
     hbm, which = peaks()
     spmv_gbs = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    impl_bytes = plan.stats()["sell_bytes"] + rows * 24     # what the sliced-ELL kernel streams: matrix + x + y + w
+    impl_gbs = impl_bytes / (spmv_ms * 1e-3) / 1e9
     cg_iter_bytes = spmv_bytes + 72 * rows
     mean_iters = float(np.mean(iters))
     cg_gbs = cg_iter_bytes * mean_iters / (np.mean(kry_ms) * 1e-3) / 1e9
@@ -291,9 +295,13 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
                 "plan_build_s_first_call": t_plan, "mesh_generation_s": t_mesh},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_spmv_csr (reduced CSR SpMV + fused p.Ap)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm,
+        "roofline": {"kernel": "k_spmv_sell<1> (sliced-ELL SpMV, compressed column indices, fused p.Ap)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm,
                      "unit": "GB/s", "frac": spmv_gbs / hbm, "frac_of_nominal_8TBs": spmv_gbs / 8000.0, "peak_source": which,
-                     "traffic": None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms},
+                     "traffic": NCU_TRAFFIC.get(m) if world == 1 else None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
+                     "note": "achieved uses the ALGORITHMIC CSR bytes nnz*12+n*16+(n+1)*4 (SURVEY.md 8d); the kernel streams fewer "
+                             "bytes because column indices are stored once per 64-row slice",
+                     "implementation_bytes_per_launch": impl_bytes, "implementation_gbs": impl_gbs,
+                     "implementation_frac_of_peak": impl_gbs / hbm},
         "newton_step_ms": ms,
         "assembly": {"elements_per_s": asm_elems / (np.mean(asm_ms) * 1e-3), "ms": float(np.mean(asm_ms)),
                      "residual_only_ms": float(np.mean(res_ms)), "algorithmic_gbs": asm_gbs,

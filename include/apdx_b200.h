@@ -176,7 +176,8 @@ int apdx_newton(apdx_plan *plan, const apdx_krylov_opts *opts, double *dofs_d,
                 int32_t *iters, double *res_norm, int32_t *diverged);
 /* timings (ms, CUDA events) and counters of the last apdx_newton / apdx_linear_step:
  * out[0]=assembly(tangent+residual) out[1]=assembly(residual only) out[2]=krylov
- * out[3]=krylov iterations out[4]=spmv launches out[5]=total out[6]=kernel launches       */
+ * out[3]=krylov iterations out[4]=spmv launches out[5]=total out[6]=kernel launches
+ * out[7]=bytes of the sliced-ELL matrix the SpMV streams (values + compressed indices)    */
 int apdx_plan_stats(const apdx_plan *plan, double out[8]);
 
 /* average device time (ms, CUDA events on the plan's stream) of `reps` launches of the SpMV kernel

@@ -134,3 +134,75 @@ def elasticity_quad(n, mode="plain strain", etype="quad4", Em=100.0, nu=0.3, bod
     mask = np.repeat((np.abs(coords[:, 0]) < 1e-9)[:, None], 2, axis=1)
     values = np.zeros(mask.shape)
     return dict(sets=[dom], coords=coords, mask=mask, values=values, nf=2)
+
+
+# ---- 'sparse' (integration point) mode: transient heat conduction on simplices -----------------------
+def _simplex_intpoints(coords, elems, ref_pts, ref_w, nv):
+    """Oracle-side restatement of seeder.int_pts_in_{line,tri,tet}_mesh (seeder.py:3456-3619): affine map through
+    the first nv nodes, weight = |size ratio| * w_ref, one connectivity row per integration point (element-major)."""
+    X = coords[elems[:, :nv]]
+    x_int, w, conn = [], [], []
+    for e in range(elems.shape[0]):
+        d = X[e, 1:] - X[e, 0]
+        if nv == 2:
+            ratio = np.linalg.norm(d[0])
+        elif nv == 3:
+            ratio = abs(np.linalg.det(d)) if d.shape[1] == 2 else np.linalg.norm(np.cross(d[0], d[1]))
+        else:
+            ratio = abs(np.linalg.det(d))
+        for p, wr in zip(np.atleast_2d(ref_pts), ref_w):
+            x_int.append(X[e, 0] + p @ d)
+            w.append(ratio * wr)
+            conn.append(elems[e])
+    return np.asarray(x_int), np.asarray(w), np.asarray(conn)
+
+
+TRI_RULE = (np.array([[1 / 6, 1 / 6], [1 / 6, 2 / 3], [2 / 3, 1 / 6]]), np.full(3, 1 / 6))
+_A, _B = 0.1381966011250105, 0.5854101966249685
+TET_RULE = (np.array([[_A, _A, _A], [_B, _A, _A], [_A, _B, _A], [_A, _A, _B]]), np.full(4, 1 / 24))
+
+
+def heat_sparse(dim=2, n=4, order=1, dt=0.2, inflow=-3.0, capacity=0.1, conduct=1.5, seed=0):
+    """Transient heat conduction as in examples/heat_conduction/maze_backward_euler.py:308-351: three 'sparse'
+    sets (poisson_weak conduction, forward_backward_euler_weak capacity, neumann_weak inflow on the face x=1)
+    on P1/P2 triangles or tetrahedra from the structured mesher.  Dirichlet theta=0 on the face x=0."""
+    from oracle import shapes as oshapes
+    if dim == 2:
+        coords, elems = omesh.structured_mesh((n, n), [[0., 0.], [1., 0.], [1.2, 1.], [0., 1.]], "tri")
+        if order == 2:
+            coords, elems = omesh.elevate_triangles(coords, elems)
+        rule, nv = TRI_RULE, 3
+    else:
+        coords, elems = omesh.structured_mesh((n, n, n), UNIT_CUBE, "tet")
+        rule, nv = TET_RULE, 4
+    x_int, w_int, conn = _simplex_intpoints(coords, elems, rule[0], rule[1], nv)
+    N, dN = oshapes.simplex_physical_tables(x_int, coords[conn])
+    # boundary facets on x = max: sub-simplices of the elements whose nodes all lie on that face
+    xmax = coords[:, 0].max()
+    if dim == 2:
+        on = np.abs(coords[:, 0] - (1.0 + 0.2 * coords[:, 1])) < 1e-9      # right edge of the trapezoid
+        face_of = lambda el: [el[list(c)] for c in ([0, 1], [1, 2], [2, 0]) if on[el[list(c)]].all()]
+        frule, fnv = (np.array([[0.21132486540518713], [0.7886751345948129]]), np.array([0.5, 0.5])), 2
+    else:
+        on = np.abs(coords[:, 0] - xmax) < 1e-9
+        face_of = lambda el: [el[list(c)] for c in ([0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]) if on[el[list(c)]].all()]
+        frule, fnv = TRI_RULE, 3
+    faces = np.asarray([f for el in elems[:, :nv] for f in face_of(el)])
+    xs, ws, sconn = _simplex_intpoints(coords, faces, frule[0], frule[1], fnv)
+    # surface shape functions: P1 on the facet in its own affine coordinates (exact for straight facets)
+    Ns = np.zeros((xs.shape[0], fnv))
+    for q in range(xs.shape[0]):
+        Xf = coords[sconn[q]]
+        A = np.vstack([np.ones(fnv), (Xf - Xf[0]).T])
+        Ns[q] = np.linalg.lstsq(A, np.concatenate([[1.0], xs[q] - Xf[0]]), rcond=None)[0]
+    rng = np.random.default_rng(seed)
+    theta_n = rng.uniform(0.0, 1.0, (coords.shape[0], 1))
+    cond = dict(kind="intpoint", conn=conn, nf=1, N=N, dNdx=dN, w=w_int,
+                model=dict(name="poisson_weak", coefficient=conduct, source=0.0))
+    cap = dict(kind="intpoint", conn=conn, nf=1, N=N, dNdx=dN, w=w_int, model=dict(name="capacity", coefficient=capacity))
+    sur = dict(kind="intpoint", conn=sconn, nf=1, N=Ns, dNdx=np.zeros(Ns.shape + (dim,)), w=ws,
+               model=dict(name="neumann", traction=np.array([inflow])))
+    mask = (np.abs(coords[:, 0]) < 1e-9)[:, None]
+    settings = {"time increment": dt, "dofs n": theta_n}
+    return dict(sets=[cond, cap, sur], coords=coords, mask=mask, values=np.zeros(mask.shape), nf=1,
+                settings=settings, x_int=(x_int, x_int, xs), w_int=(w_int, w_int, ws))

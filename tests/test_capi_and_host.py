@@ -1,0 +1,187 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, host logic of the
+reference-facing layer (settings validation / rejection, model recognition, callable evaluation,
+mesher, quadrature, shape tables) and the loud failure without a GPU.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from autopdex_b200 import _lib, backend, mesher, models, seeder, solver, spaces, utility
+from oracle import mesher as omesh
+from oracle import quadrature as oquad
+from oracle import shapes as oshapes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    txt = open(os.path.join(ROOT, "include", "apdx_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(apdx_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _header_functions()
+    assert len(names) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libapdx_b200.so does not export %s" % n
+    assert sorted(_lib.SIGNATURES) == names          # the ctypes table mirrors the header one to one
+    assert _lib.load().apdx_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    conn = np.array([[0, 1, 2, 3]])
+    st = backend.SetSpec("domain", "poisson_weak", conn, family="quad_brick", gp=seeder.gauss_legendre_nd(2, 2))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        backend.Plan(2, 4, 1, [st], None)
+
+
+# ---- settings validation: reject at read time, never fall back ------------------------------------
+def _static(**over):
+    weak = models.poisson_weak()
+    elem = models.isoparametric_domain_element_galerkin(weak, spaces.fem_iso_line_quad_brick,
+                                                        *seeder.gauss_legendre_nd(2, 2))
+    s = {"assembling mode": ("user element",), "solution structure": ("nodal imposition",), "model": (elem,),
+         "solver type": "newton", "solver backend": "b200", "solver": "cg", "type of preconditioner": "jacobi",
+         "verbose": -1}
+    s.update(over)
+    return s
+
+
+def test_validate_accepts_builtin_configuration():
+    cfg = solver.validate(_static())
+    assert cfg.nodal_imposition and cfg.jacobi and cfg.krylov == "cg"
+
+
+@pytest.mark.parametrize("over,msg", [
+    ({"solver type": "minimize"}, "solver type"),
+    ({"solver type": "diagonal linear"}, "solver type"),
+    ({"solver": "gmres"}, "'solver'"),
+    ({"solver": "lapack"}, "'solver'"),
+    ({"type of preconditioner": "ilu"}, "preconditioner"),
+    ({"assembling mode": ("dense",)}, "assembling mode"),
+    ({"solution structure": ("first order set",)}, "solution structure"),
+    ({"known sparsity pattern": "diagonal"}, "sparsity"),
+    ({"solver backend": "scipy"}, "b200"),
+])
+def test_validate_rejects_unsupported(over, msg):
+    with pytest.raises(ValueError, match=msg):
+        solver.validate(_static(**over))
+
+
+def test_user_written_models_are_rejected():
+    def my_integrand(x_int, ansatz_fun, settings, static_settings, elem_number, set):
+        return 0.0
+    with pytest.raises(ValueError, match="user-written integrand"):
+        models.mixed_reference_domain_potential(my_integrand, {"phi": spaces.fem_iso_line_quad_brick},
+                                                *seeder.gauss_legendre_nd(2, 2), "phi")
+    with pytest.raises(ValueError, match="not supported"):
+        solver.validate(_static(model=(lambda *a: 0.0,)))
+    with pytest.raises(ValueError, match="strain energy"):
+        models.hyperelastic_steady_state_weak(lambda F, p: 0.0, lambda x: 1.0, lambda x: 0.3, "3d")
+    with pytest.raises(ValueError, match="sparse"):
+        solver.validate(_static(**{"assembling mode": ("sparse",), "model": (models.poisson_weak(),),
+                                   "variational scheme": ("least square pde loss",), "solution space": ("mls",),
+                                   "shape function mode": "direct"}))
+
+
+def test_reference_closures_are_recognised_by_qualname():
+    """The reference's models are anonymous closures (models.py); the backend identifies them by
+    __qualname__ and closure cells without calling them.  Mimic their shape here."""
+    def fem_iso_line_quad_brick(x, xI, fI, settings, overwrite_diff, n_dim):
+        raise AssertionError("must not be called")
+
+    def neo_hooke(F, param):
+        raise AssertionError("must not be called")
+
+    def hyperelastic_steady_state_weak(strain_energy_fun, youngs_mod_fun, poisson_ratio_fun, mode, volume_load_fun=None):
+        def pde_fun(x, ansatz, test_ansatz, settings, static_settings, int_point_number, set):
+            return strain_energy_fun, youngs_mod_fun, poisson_ratio_fun, mode, volume_load_fun
+        return pde_fun
+
+    def isoparametric_domain_element_galerkin(weak_form_fun, ansatz_fun, ref_int_coor, ref_int_weights, initial_config=True):
+        def user_element(fI, xI, elem_number, settings, static_settings, mode, set):
+            return weak_form_fun, ansatz_fun, ref_int_coor, ref_int_weights, initial_config
+        return user_element
+
+    E = lambda x, settings: settings["youngs modulus"]
+    nu = lambda x, settings: settings["poisson ratio"]
+    ref_elem = isoparametric_domain_element_galerkin(hyperelastic_steady_state_weak(neo_hooke, E, nu, "plain strain"),
+                                                     fem_iso_line_quad_brick, *seeder.gauss_legendre_nd(2, 4))
+    m = models.recognise(ref_elem)
+    assert isinstance(m, models.ElementModel) and m.kind == "domain" and m.family == "quad_brick"
+    assert m.weak.name == "neo_hooke" and m.weak.mode == "plain strain"
+    assert m.weak.funs["youngs_modulus"] is E and len(m.gp[1]) == 9
+    cfg = solver.validate(_static(model=(ref_elem,), solver="bicgstab"))
+    assert cfg.sets[0][1].weak.name == "neo_hooke"
+
+
+def test_callable_evaluation_reference_vs_physical_points():
+    pts = np.random.default_rng(0).uniform(size=(100, 2))
+    f = lambda x: 20 * (np.sin(10 * np.sum(x * x, axis=-1)))
+    v = solver._eval_points(f, pts, {}, 1)
+    assert v.shape == (100,) and np.allclose(v[7], f(pts[7]))
+    g = lambda x: 20 * np.sin(10 * x @ x)            # NOT vectorisable: falls back to the per-point loop
+    assert np.allclose(solver._eval_points(g, pts, {}, 1), [g(p) for p in pts])
+    t = lambda x, settings: np.asarray([0.0, settings["load multiplier"]])
+    assert np.array_equal(solver._eval_points(t, pts[:3], {"load multiplier": 4.0}, 2), [[0, 4.0]] * 3)
+    assert solver._eval_points(lambda x: 1.0, pts, {}, 1).shape == ()
+    with pytest.raises(ValueError, match="vectorized"):
+        solver._eval_points(g, pts, {}, 1, vectorized=True)
+
+
+# ---- host restatements agree with the oracle's independent ones -------------------------------------
+@pytest.mark.parametrize("family,dim,nen,name", [
+    ("quad_brick", 1, 2, "line2"), ("quad_brick", 1, 3, "line3"), ("quad_brick", 2, 4, "quad4"),
+    ("quad_brick", 2, 9, "quad9"), ("quad_brick", 3, 8, "hex8"), ("quad_brick", 3, 27, "hex27"),
+    ("tri_tet", 2, 3, "tri3"), ("tri_tet", 2, 6, "tri6"), ("tri_tet", 3, 4, "tet4"), ("tri_tet", 3, 10, "tet10")])
+def test_shape_tables_match_oracle(family, dim, nen, name):
+    xi = np.random.default_rng(1).uniform(0.0, 0.3, (9, dim))
+    N, dN = spaces.shape_tables(family, nen, dim, xi)
+    No, dNo = oshapes.shape_tables(name, xi)
+    assert np.abs(N - No).max() < 1e-14 and np.abs(dN - dNo).max() < 1e-13
+    assert np.allclose(N.sum(axis=1), 1.0) and np.abs(dN.sum(axis=1)).max() < 1e-13
+    nodes = np.asarray(oshapes.REF_NODES[name], dtype=float)
+    assert np.allclose(spaces.shape_tables(family, nen, dim, nodes)[0], np.eye(nen), atol=1e-14)
+
+
+def test_quadrature_and_mesher_match_oracle():
+    for d in (1, 2, 3):
+        for o in (1, 2, 3, 4, 6):
+            a, b = seeder.gauss_legendre_nd(d, o), oquad.gauss_legendre_nd(d, o)
+            assert np.abs(a[0] - b[0]).max() < 1e-15 and np.abs(a[1] - b[1]).max() < 1e-15
+            assert np.isclose(a[1].sum(), 2.0 ** d)
+    cube = [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1.2], [1, 1, 1], [0, 1, 1]]
+    quad = [[0, 0], [2, 0], [2.5, 1.5], [0, 1]]
+    for args in [((3, 4), quad, "quad"), ((3, 4), quad, "tri"), ((2, 3, 4), cube, "brick"), ((2, 3, 2), cube, "tet")]:
+        a, b = mesher.structured_mesh(*args), omesh.structured_mesh(*args)
+        assert np.array_equal(a[1], b[1]) and np.abs(a[0] - b[0]).max() < 1e-15
+    c, e = mesher.structured_mesh((2, 2, 2), cube, "brick")
+    a, b = mesher.elevate_mesh_order(c, e), omesh.elevate_bricks(c, e)
+    assert np.array_equal(a[1], b[1]) and np.allclose(a[0], b[0]) and a[1].shape[1] == 27
+    # reference quirk: mesher quads are clockwise w.r.t. quad4 -> det J < 0
+    c, e = mesher.structured_mesh((2, 2), [[0, 0], [1, 0], [1, 1], [0, 1]], "quad")
+    _, dN = spaces.shape_tables("quad_brick", 4, 2, np.zeros((1, 2)))
+    J = np.einsum("ad,ak->dk", c[e[0]], dN[0])
+    assert np.linalg.det(J) < 0
+
+
+def test_utility_and_slab_partition():
+    d = {"phi": np.arange(6.0).reshape(3, 2)}
+    flat = utility.dict_flatten(d)
+    assert np.array_equal(utility.reshape_as(flat, d)["phi"], d["phi"])
+    assert utility.dof_select(np.array([True, False]), np.array([True, True])).shape == (2, 2)
+    m, world = 9, 4
+    owned = []
+    for r in range(world):
+        p = mesher.slab_partition((m, m, m), r, world)
+        owned.append((p["owned_node_lo"], p["owned_node_hi"]))
+        assert p["node_lo"] <= p["owned_node_lo"] < p["owned_node_hi"] <= p["node_hi"]
+        assert (p["rank_lo"] == -1) == (r == 0) and (p["rank_hi"] == -1) == (r == world - 1)
+    assert owned[0][0] == 0 and owned[-1][1] == (m + 1) ** 3
+    assert all(owned[i][1] == owned[i + 1][0] for i in range(world - 1))

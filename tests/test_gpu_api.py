@@ -1,0 +1,168 @@
+"""GPU parity through the reference-facing API: autopdex_b200.solver.solver / adaptive_load_stepping /
+assembler.* with `'solver backend': 'b200'`.  These read like the reference's own tests
+(tests/test_dicts_as_dofs_user_potential.py, tests/test_user_elem_impl_diff_and_adaptive_load_step.py,
+tests/test_backward_euler.py) with the backend swapped."""
+import numpy as np
+import pytest
+
+from oracle import assemble as oasm
+from oracle import solve as osolve
+from tests import problems
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_dict_dofs_user_potential_golden():
+    from autopdex_b200 import mesher, models, seeder, solver, spaces, utility
+    pts = [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]
+    coords, elems = mesher.structured_mesh((5, 5), pts, "quad")
+    node_coordinates = {"phi": coords}
+    connectivity = {"phi": elems}
+    p = problems.readme_poisson(5)            # Dirichlet selection: boundary minus corners (geometry.psdf_polygon quirk)
+    dirichlet_dofs = {"phi": p["mask"][:, 0]}
+    dirichlet_conditions = utility.dict_zeros_like(dirichlet_dofs, dtype=np.float64)
+    integrand = models.poisson_potential("phi", source_fun=problems.readme_source)
+    user_potential = models.mixed_reference_domain_potential(integrand, {"phi": spaces.fem_iso_line_quad_brick},
+                                                             *seeder.gauss_legendre_nd(dimension=2, order=2), "phi")
+    static_settings = {"assembling mode": ("user potential",), "solution structure": ("nodal imposition",),
+                       "model": (user_potential,), "solver type": "newton", "solver backend": "b200", "solver": "cg",
+                       "type of preconditioner": "jacobi", "verbose": -1}
+    settings = {"connectivity": (connectivity,), "dirichlet dofs": dirichlet_dofs, "node coordinates": node_coordinates,
+                "dirichlet conditions": dirichlet_conditions}
+    initial_guess = utility.dict_zeros_like(dirichlet_dofs, dtype=np.float64)
+    sol, infos = solver.solver(initial_guess, settings, static_settings)
+    assert infos[0] == 1 and not infos[2]
+    assert np.isclose(sol["phi"].sum(), 1.9066412530282952, rtol=1e-9, atol=0)     # reference golden value G1
+
+
+def _cook_settings(krylov="bicgstab"):
+    from autopdex_b200 import models, seeder, spaces
+    p = problems.cook_g2()
+    weak1 = models.hyperelastic_steady_state_weak(models.neo_hooke, lambda x, settings: settings["youngs modulus"],
+                                                  lambda x, settings: settings["poisson ratio"], "plain strain")
+    elem1 = models.isoparametric_domain_element_galerkin(weak1, spaces.fem_iso_line_quad_brick,
+                                                         *seeder.gauss_legendre_nd(dimension=2, order=4))
+    weak2 = models.neumann_weak(lambda x, settings: np.asarray([0.0, settings["load multiplier"]]))
+    elem2 = models.isoparametric_surface_element_galerkin(weak2, spaces.fem_iso_line_quad_brick,
+                                                          *seeder.gauss_legendre_nd(dimension=1, order=4),
+                                                          tangent_contributions=False)
+    static_settings = {"number of fields": (2, 2), "assembling mode": ("user element", "user element"),
+                       "solution structure": ("nodal imposition", "nodal imposition"), "model": (elem1, elem2),
+                       "solver type": "newton", "solver backend": "b200", "solver": krylov,
+                       "type of preconditioner": "jacobi", "verbose": -1}
+    settings = {"dirichlet dofs": p["mask"], "connectivity": (p["sets"][0]["conn"], p["sets"][1]["conn"]),
+                "load multiplier": p["q0"], "node coordinates": p["coords"], "dirichlet conditions": p["values"],
+                "youngs modulus": 100.0, "poisson ratio": 0.3}
+    return p, settings, static_settings
+
+
+def test_cook_adaptive_load_stepping_golden():
+    from autopdex_b200 import solver
+    p, settings, static_settings = _cook_settings()
+    q0 = p["q0"]
+
+    def multiplier_settings(settings, multiplier):
+        settings["load multiplier"] = multiplier * q0
+        return settings
+
+    dofs0 = np.zeros(p["mask"].shape)
+    out = solver.adaptive_load_stepping(dofs0, settings, static_settings, multiplier_settings, False, None,
+                                        newton_tol=1e-8, tol=1e-13)
+    dofs, multiplier = out[0], out[1]
+    assert np.isclose(multiplier, 1.0)
+    assert np.isclose(dofs.ravel() @ dofs.ravel(), 19390.35027108, rtol=1e-8, atol=0)   # reference golden value G2
+
+
+def test_linear_solver_type_returns_mixed_vector():
+    from autopdex_b200 import solver
+    p, settings, static_settings = _cook_settings("bicgstab")
+    static_settings = dict(static_settings, **{"solver type": "linear"})
+    settings["dirichlet conditions"] = np.where(p["mask"], 0.25, 0.0)          # non-homogeneous Dirichlet values
+    dofs0 = np.random.default_rng(2).uniform(-0.01, 0.01, p["mask"].shape)
+    sol, infos = solver.solver(dofs0, settings, static_settings, tol=1e-13)
+    assert infos is None
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], settings["dirichlet conditions"])
+    ref = osolve.solve_linear(prob, dofs0)
+    assert np.allclose(sol[p["mask"]], 0.25)                                    # Dirichlet entries = imposed values
+    assert np.linalg.norm(sol - ref) / np.linalg.norm(ref) < 1e-8
+
+
+def test_damped_newton_iteration_count_matches_oracle():
+    from autopdex_b200 import solver
+    p, settings, static_settings = _cook_settings()
+    static_settings = dict(static_settings, **{"solver type": "damped newton"})
+    settings["load multiplier"] = 3.0
+    p["sets"][1]["model"]["traction"] = np.array([0.0, 3.0])
+    dofs0 = np.zeros(p["mask"].shape)
+    sol, (it, rn, div) = solver.solver(dofs0, settings, static_settings, newton_tol=1e-6, damping_coefficient=0.8,
+                                       maxiter=30, tol=1e-13)
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+    ref, (rit, rrn, rdiv) = osolve.damped_newton(prob, dofs0, newton_tol=1e-6, damping=0.8)
+    assert (it, div) == (rit, rdiv)
+    assert np.linalg.norm(sol - ref) / np.linalg.norm(ref) < 1e-8
+
+
+def test_newton_maxiter_flags_divergence_like_reference():
+    from autopdex_b200 import solver
+    p, settings, static_settings = _cook_settings()
+    dofs0 = np.zeros(p["mask"].shape)
+    sol, (it, rn, div) = solver.solver(dofs0, settings, static_settings, newton_tol=1e-30, maxiter=2, tol=1e-13)
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+    ref, (rit, rrn, rdiv) = osolve.damped_newton(prob, dofs0, newton_tol=1e-30, maxiter=2)
+    assert (it, div) == (rit, rdiv) == (3, True)
+
+
+@pytest.mark.parametrize("dim,order,mode", [(2, 1, "direct"), (2, 2, "direct"), (3, 1, "direct"), (2, 1, "compiled")])
+def test_sparse_mode_backward_euler_steps(dim, order, mode):
+    """Three 'sparse' sets (conduction, capacity, surface inflow), 'solver type': 'linear', three backward-Euler
+    steps with the plan (pattern) reused -- the structure of tests/test_backward_euler.py:281-373."""
+    from autopdex_b200 import models, solver
+    p = problems.heat_sparse(dim, 3, order)
+    cond, cap, sur = p["sets"]
+    static_settings = {"assembling mode": ("sparse",) * 3, "solution structure": ("nodal imposition",) * 3,
+                       "variational scheme": ("weak form galerkin",) * 3, "solution space": ("fem simplex",) * 3,
+                       "shape function mode": mode,
+                       "model": (models.poisson_weak(lambda x, settings: 1.5, lambda x: 0.0),
+                                 models.forward_backward_euler_weak(lambda x, settings: 0.1),
+                                 models.neumann_weak(lambda x: -3.0)),
+                       "solver type": "linear", "solver backend": "b200", "solver": "cg",
+                       "type of preconditioner": "jacobi", "verbose": -1}
+    settings = {"connectivity": tuple(s["conn"] for s in p["sets"]), "node coordinates": p["coords"],
+                "dirichlet dofs": p["mask"], "dirichlet conditions": p["values"],
+                "integration coordinates": p["x_int"], "integration weights": p["w_int"],
+                "time increment": 0.2, "dofs n": p["settings"]["dofs n"].copy()}
+    if mode == "compiled":
+        settings["compiled shape functions"] = tuple((s["N"], s["dNdx"]) for s in p["sets"])
+    else:
+        # the surface set's physical-space P1 fit needs dim+1 nodes; feed its facet tables as 'compiled' is the
+        # reference's route for lower-dimensional facets, so test the direct route on the two volume sets only
+        static_settings["assembling mode"] = ("sparse",) * 2
+        for k in ("solution structure", "variational scheme", "solution space", "model"):
+            static_settings[k] = static_settings[k][:2]
+        for k in ("connectivity", "integration coordinates", "integration weights"):
+            settings[k] = settings[k][:2]
+        p["sets"] = p["sets"][:2]
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"], dict(p["settings"]))
+    dofs = p["settings"]["dofs n"].copy()
+    ref = dofs.copy()
+    for step in range(3):
+        settings["dofs n"] = dofs
+        dofs = dofs + solver.solver(dofs, settings, static_settings, tol=1e-13)[0]          # maze_backward_euler.py:362
+        prob.settings["dofs n"] = ref
+        ref = ref + osolve.solve_linear(prob, ref)
+        assert np.linalg.norm(dofs - ref) / np.linalg.norm(ref) < 1e-8
+    assert len(solver._PLAN_CACHE) >= 1
+
+
+def test_assembler_module_matches_oracle():
+    from autopdex_b200 import assembler
+    p, settings, static_settings = _cook_settings()
+    dofs = np.random.default_rng(0).uniform(-0.05, 0.05, p["mask"].shape)
+    R = assembler.assemble_residual(dofs, settings, static_settings)
+    K = assembler.assemble_tangent(dofs, settings, static_settings)
+    Ro, data = oasm.assemble(p["sets"], p["coords"], dofs, {})
+    rows, cols = oasm.coo_indices(p["sets"])
+    full = oasm.scipy_assembling(data, rows, cols, dofs.size)
+    assert np.array_equal(K.indptr, full.indptr) and np.array_equal(K.indices, full.indices)
+    assert np.abs(K.data - full.data).max() / np.abs(full.data).max() < 1e-12
+    assert np.abs(R.ravel() - Ro).max() / np.abs(Ro).max() < 1e-12

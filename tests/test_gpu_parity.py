@@ -162,3 +162,32 @@ def test_newton_neo_hooke_brick_matches_oracle():
     it, rn, dv = plan.newton(backend.KrylovOptions("bicgstab", rtol=1e-12), d, v)
     assert (it, dv) == (steps, div)
     assert np.linalg.norm(d.download() - ref.ravel()) / np.linalg.norm(ref) < 1e-8
+
+
+@pytest.mark.parametrize("dim,order", [(2, 1), (2, 2), (3, 1)])
+def test_sparse_intpoint_sets_pattern_values(dim, order):
+    p = problems.heat_sparse(dim, 3, order)
+    dofs = np.random.default_rng(0).uniform(-1, 1, p["mask"].shape)
+    _check_assembly(p, dofs, p["settings"])
+
+
+def test_tet10_tri6_domain_elements_pattern_values():
+    """P2 simplices as isoparametric 'user element's (spaces.fem_iso_line_tri_tet)."""
+    from oracle import mesher as omesh, quadrature as oquad
+    coords, elems = omesh.structured_mesh((3, 3), [[0., 0.], [2., 0.], [2.3, 1.], [0., 1.]], "tri")
+    coords, elems = omesh.elevate_triangles(coords, elems)
+    gp = (np.array([[1 / 6, 1 / 6], [1 / 6, 2 / 3], [2 / 3, 1 / 6]]), np.full(3, 1 / 6))
+    st = dict(kind="domain", etype="tri6", conn=elems, nf=2, gp=gp,
+              model=dict(name="neo_hooke", mode="plain strain", youngs_modulus=50.0, poisson_ratio=0.25))
+    mask = np.repeat((np.abs(coords[:, 0]) < 1e-9)[:, None], 2, axis=1)
+    p = dict(sets=[st], coords=coords, mask=mask, values=np.zeros(mask.shape), nf=2)
+    _check_assembly(p, np.random.default_rng(0).uniform(-0.02, 0.02, mask.shape))
+    coords, elems = omesh.structured_mesh((2, 2, 2), problems.UNIT_CUBE, "tet")
+    a, b = 0.1381966011250105, 0.5854101966249685
+    gp = (np.array([[a, a, a], [b, a, a], [a, b, a], [a, a, b]]), np.full(4, 1 / 24))
+    st = dict(kind="domain", etype="tet4", conn=elems, nf=3, gp=gp,
+              model=dict(name="linear_elasticity", mode="3d", youngs_modulus=50.0, poisson_ratio=0.25,
+                         body_load=np.array([0.0, 0.0, -1.0])))
+    mask = np.repeat((np.abs(coords[:, 2]) < 1e-9)[:, None], 3, axis=1)
+    p = dict(sets=[st], coords=coords, mask=mask, values=np.zeros(mask.shape), nf=3)
+    _check_assembly(p, np.random.default_rng(0).uniform(-0.02, 0.02, mask.shape))
