@@ -351,6 +351,7 @@ int apdx_plan_destroy(apdx_plan *pl) {
   pl->row_ptr.release(); pl->col.release(); pl->elem_map.release(); pl->perm.release(); pl->seg_ptr.release();
   pl->rperm.release(); pl->rseg_ptr.release(); pl->red_row_ptr.release(); pl->red_col.release();
   pl->red2full.release(); pl->red_diag.release(); pl->ke.release(); pl->re.release(); pl->vals.release();
+  p2p_teardown(pl);
   pl->sell.release();
   pl->red_vals.release(); pl->residual.release(); pl->rhs_red.release(); pl->x_red.release(); pl->dofs_trial.release();
   KrylovWork &k = pl->kw;
@@ -621,7 +622,11 @@ int apdx_plan_set_partition(apdx_plan *pl, int64_t owned_dof_begin, int64_t owne
   APDX_REQUIRE(pl->f1 > pl->f0, APDX_ERR_INVALID, "rank owns no free dof");
   if (rank_lo < 0) APDX_REQUIRE(pl->halo_lo == 0, APDX_ERR_INVALID, "ghost dofs below the owned range but no lower neighbour");
   if (rank_hi < 0) APDX_REQUIRE(pl->halo_hi == 0, APDX_ERR_INVALID, "ghost dofs above the owned range but no upper neighbour");
-  if (comm_active()) APDX_CHECK(comm_halo_setup(pl));
+  if (comm_active()) {
+    APDX_CHECK(comm_halo_setup(pl));
+    APDX_REQUIRE(!pl->kw.r.p, APDX_ERR_STATE, "apdx_plan_set_partition must precede the first solve");
+    APDX_CHECK(p2p_setup(pl));
+  }
   return APDX_OK;
 }
 

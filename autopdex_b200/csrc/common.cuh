@@ -41,8 +41,15 @@ template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  bool owned = true;
   int alloc(size_t count);
   void release();
+  void adopt(T *ptr, size_t count) {  // non-owning alias (vectors living in the peer-to-peer heap)
+    release();
+    p = ptr;
+    n = count;
+    owned = false;
+  }
   size_t bytes() const { return n * sizeof(T); }
 };
 
@@ -64,12 +71,13 @@ int DevBuf<T>::alloc(size_t count) {
 }
 template <typename T>
 void DevBuf<T>::release() {
-  if (p) {
+  if (p && owned) {
     cudaFree(p);
     g_plan_bytes -= bytes();
   }
   p = nullptr;
   n = 0;
+  owned = true;
 }
 
 // Run-time parameter of a set: value(row, gp, comp) = p[row*s_row + gp*s_gp + comp]
@@ -99,6 +107,31 @@ struct KrylovWork {
   DevBuf<double> scal;        // device scalars (see krylov.cu)
   DevBuf<unsigned int> ticket;
   DevBuf<int32_t> flags;      // [0]=done [1]=iterations [2]=breakdown
+};
+
+// ---- peer-to-peer (NVLink) plumbing of the multi-GPU Krylov loop (dist.cu, krylov.cu) ------------------
+constexpr int P2P_MAX_RANKS = 16;
+// device-visible descriptor; every pointer is dereferenceable from this GPU (peer memory mapped through CUDA IPC)
+struct P2PDev {
+  int rank, nranks, has_lo, has_hi;
+  double *mbox[P2P_MAX_RANKS];   // rank r's mailboxes: double [2 slots][P2P_MAX_RANKS senders][4]
+  int *mflag[P2P_MAX_RANKS];     // rank r's mailbox flags: int [2 slots][P2P_MAX_RANKS senders]
+  int *hflag_self;               // my halo flags: [0] written by the lower neighbour, [1] by the upper one
+  int *err;                      // my time-out flag
+};
+struct P2P {
+  bool enabled = false;
+  char *heap = nullptr;          // symmetric heap: [mailboxes | flags | 3 Krylov vectors of `stride` doubles]
+  size_t heap_bytes = 0;
+  void *peer_base[P2P_MAX_RANKS]{};
+  P2PDev *dev = nullptr;
+  int *err_d = nullptr;
+  double *vec_base = nullptr;
+  int64_t stride = 0;
+  double *peer_vec[2]{};         // vec_base of the lower / upper neighbour
+  int *peer_hflag[2]{};          // lower neighbour's hflag[1], upper neighbour's hflag[0]
+  int64_t peer_lo_f1 = 0;        // lower neighbour's owned end = start of its upper ghost range
+  int red_epoch = 0, halo_epoch = 0;
 };
 
 // sliced-ELL copy of the owned rows of the reduced system (sell.cu)
@@ -164,6 +197,7 @@ struct apdx_plan {
   apdx::DevBuf<double> residual, rhs_red, x_red, dofs_trial;
   apdx::KrylovWork kw;
   apdx::Sell sell;
+  apdx::P2P p2p;
   bool have_sell_values = false, have_red_values = false;
   double *pinned = nullptr;                // small pinned host staging
   apdx::Stats stats;
@@ -197,4 +231,7 @@ int comm_size();
 int comm_allreduce_sum(double *buf_d, int count, cudaStream_t s);
 int comm_halo_exchange(apdx_plan *pl, double *x_d, cudaStream_t s);
 int comm_halo_setup(apdx_plan *pl);
+int p2p_setup(apdx_plan *pl);
+void p2p_teardown(apdx_plan *pl);
+bool p2p_is_heap_vector(const apdx_plan *pl, const double *v);
 }  // namespace apdx

@@ -4,7 +4,10 @@
 // ncclSend/ncclRecv before every SpMV, and ncclAllReduce for dot products / the Newton norm.
 // NCCL is loaded with dlopen so that the single-GPU library has no link-time dependency on it.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -27,6 +30,7 @@ struct Nccl {
   ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
@@ -62,6 +66,7 @@ static int load_nccl() {
   SYM(Recv, "ncclRecv");
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
+  SYM(AllGather, "ncclAllGather");
   SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
   return APDX_OK;
@@ -91,30 +96,145 @@ int comm_halo_exchange(apdx_plan *pl, double *x_d, cudaStream_t s) {
   return APDX_OK;
 }
 
-// neighbours tell each other how many owned entries the other side ghosts
+// neighbours tell each other how many owned entries the other side ghosts, and where their owned range ends
 int comm_halo_setup(apdx_plan *pl) {
   int64_t *buf = nullptr;
-  APDX_CUDA(cudaMalloc((void **)&buf, 4 * sizeof(int64_t)));
-  int64_t h[4] = {pl->halo_lo, pl->halo_hi, 0, 0};
+  APDX_CUDA(cudaMalloc((void **)&buf, 8 * sizeof(int64_t)));
+  // send block: [halo_lo, f1] to the lower neighbour, [halo_hi, f1] to the upper one
+  int64_t h[8] = {pl->halo_lo, pl->f1, pl->halo_hi, pl->f1, 0, 0, 0, 0};
   APDX_CUDA(cudaMemcpy(buf, h, sizeof(h), cudaMemcpyHostToDevice));
   cudaStream_t s = pl->stream;
   APDX_NCCL(g_nccl.GroupStart());
   if (pl->rank_lo >= 0) {
-    APDX_NCCL(g_nccl.Send(buf + 0, 1, ncclInt64, pl->rank_lo, g_nccl.comm, s));
-    APDX_NCCL(g_nccl.Recv(buf + 2, 1, ncclInt64, pl->rank_lo, g_nccl.comm, s));
+    APDX_NCCL(g_nccl.Send(buf + 0, 2, ncclInt64, pl->rank_lo, g_nccl.comm, s));
+    APDX_NCCL(g_nccl.Recv(buf + 4, 2, ncclInt64, pl->rank_lo, g_nccl.comm, s));
   }
   if (pl->rank_hi >= 0) {
-    APDX_NCCL(g_nccl.Send(buf + 1, 1, ncclInt64, pl->rank_hi, g_nccl.comm, s));
-    APDX_NCCL(g_nccl.Recv(buf + 3, 1, ncclInt64, pl->rank_hi, g_nccl.comm, s));
+    APDX_NCCL(g_nccl.Send(buf + 2, 2, ncclInt64, pl->rank_hi, g_nccl.comm, s));
+    APDX_NCCL(g_nccl.Recv(buf + 6, 2, ncclInt64, pl->rank_hi, g_nccl.comm, s));
   }
   APDX_NCCL(g_nccl.GroupEnd());
   APDX_CUDA(cudaStreamSynchronize(s));
   APDX_CUDA(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
   cudaFree(buf);
-  pl->send_lo = pl->rank_lo >= 0 ? h[2] : 0;  // lower neighbour's upper-ghost count
-  pl->send_hi = pl->rank_hi >= 0 ? h[3] : 0;  // upper neighbour's lower-ghost count
+  pl->send_lo = pl->rank_lo >= 0 ? h[4] : 0;  // lower neighbour's upper-ghost count
+  pl->send_hi = pl->rank_hi >= 0 ? h[6] : 0;  // upper neighbour's lower-ghost count
+  pl->p2p.peer_lo_f1 = pl->rank_lo >= 0 ? h[5] : 0;
   APDX_REQUIRE(pl->send_lo <= pl->f1 - pl->f0 && pl->send_hi <= pl->f1 - pl->f0, APDX_ERR_INVALID,
                "neighbour ghosts more dofs than this rank owns");
+  return APDX_OK;
+}
+
+// ---- peer-to-peer heap: CUDA IPC mapping of every rank's mailbox / flag / Krylov-vector block -----------------
+constexpr size_t P2P_HDR = 4096;
+static inline double *hdr_mbox(void *base) { return reinterpret_cast<double *>(base); }
+static inline int *hdr_mflag(void *base) { return reinterpret_cast<int *>(static_cast<char *>(base) + 2 * P2P_MAX_RANKS * 4 * sizeof(double)); }
+static inline int *hdr_hflag(void *base) { return hdr_mflag(base) + 2 * P2P_MAX_RANKS; }
+static inline int *hdr_err(void *base) { return hdr_hflag(base) + 2; }
+static inline double *hdr_vec(void *base) { return reinterpret_cast<double *>(static_cast<char *>(base) + P2P_HDR); }
+
+bool p2p_is_heap_vector(const apdx_plan *pl, const double *v) {
+  const P2P &P = pl->p2p;
+  return P.enabled && v >= P.vec_base && v < P.vec_base + 3 * P.stride;
+}
+
+// A heap may still be mapped by the peers when its plan dies, so it is only parked here; apdx_comm_destroy
+// (a collective call) frees the parked heaps after a barrier.
+static std::vector<P2P> g_parked;
+
+void p2p_teardown(apdx_plan *pl) {
+  P2P &P = pl->p2p;
+  if (!P.heap) return;
+  g_parked.push_back(P);
+  P = P2P();
+}
+
+static void p2p_free_parked() {
+  for (P2P &P : g_parked) {
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+      if (P.peer_base[r] && P.peer_base[r] != P.heap) cudaIpcCloseMemHandle(P.peer_base[r]);
+    if (P.dev) cudaFree(P.dev);
+    cudaFree(P.heap);
+  }
+  g_parked.clear();
+}
+
+int p2p_setup(apdx_plan *pl) {
+  P2P &P = pl->p2p;
+  const char *mode = getenv("APDX_COMM");
+  if (mode && strcmp(mode, "nccl") == 0) return APDX_OK;  // A/B switch: NCCL-only Krylov loop
+  if (g_nccl.nranks > P2P_MAX_RANKS) return APDX_OK;
+  p2p_teardown(pl);
+  cudaStream_t s = pl->stream;
+  const int me = g_nccl.rank, nr = g_nccl.nranks;
+  // common vector stride = max n_free over ranks (rounded up to 512 doubles)
+  double *dmax = nullptr;
+  APDX_CUDA(cudaMalloc((void **)&dmax, sizeof(double)));
+  double nf = (double)((pl->n_free + 511) / 512 * 512);
+  APDX_CUDA(cudaMemcpy(dmax, &nf, sizeof(double), cudaMemcpyHostToDevice));
+  APDX_NCCL(g_nccl.AllReduce(dmax, dmax, 1, ncclFloat64, ncclMax, g_nccl.comm, s));
+  APDX_CUDA(cudaStreamSynchronize(s));
+  APDX_CUDA(cudaMemcpy(&nf, dmax, sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dmax);
+  P.stride = (int64_t)nf;
+  P.heap_bytes = P2P_HDR + 3 * (size_t)P.stride * sizeof(double);
+  APDX_CUDA(cudaMalloc((void **)&P.heap, P.heap_bytes));
+  APDX_CUDA(cudaMemset(P.heap, 0, P.heap_bytes));
+  // exchange IPC handles
+  cudaIpcMemHandle_t mine;
+  cudaError_t ce = cudaIpcGetMemHandle(&mine, P.heap);
+  char *hd = nullptr;
+  APDX_CUDA(cudaMalloc((void **)&hd, (size_t)(nr + 1) * sizeof(cudaIpcMemHandle_t)));
+  int ok_local = (ce == cudaSuccess) ? 1 : 0;
+  if (!ok_local) memset(&mine, 0, sizeof(mine));
+  APDX_CUDA(cudaMemcpy(hd + (size_t)nr * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  APDX_NCCL(g_nccl.AllGather(hd + (size_t)nr * sizeof(mine), hd, sizeof(mine), 0 /*ncclInt8*/, g_nccl.comm, s));
+  APDX_CUDA(cudaStreamSynchronize(s));
+  std::vector<cudaIpcMemHandle_t> all(nr);
+  APDX_CUDA(cudaMemcpy(all.data(), hd, (size_t)nr * sizeof(mine), cudaMemcpyDeviceToHost));
+  cudaFree(hd);
+  for (int r = 0; r < nr && ok_local; ++r) {
+    if (r == me) { P.peer_base[r] = P.heap; continue; }
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok_local = 0;
+      break;
+    }
+    P.peer_base[r] = ptr;
+  }
+  // everybody must succeed, otherwise everybody stays on the NCCL path
+  double *dok = nullptr;
+  APDX_CUDA(cudaMalloc((void **)&dok, sizeof(double)));
+  double okv = ok_local ? 0.0 : 1.0;
+  APDX_CUDA(cudaMemcpy(dok, &okv, sizeof(double), cudaMemcpyHostToDevice));
+  APDX_NCCL(g_nccl.AllReduce(dok, dok, 1, ncclFloat64, ncclSum, g_nccl.comm, s));
+  APDX_CUDA(cudaStreamSynchronize(s));
+  APDX_CUDA(cudaMemcpy(&okv, dok, sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dok);
+  if (okv != 0.0) {
+    if (me == 0) fprintf(stderr, "[apdx_b200] CUDA IPC peer mapping unavailable (%s): Krylov loop stays on NCCL\n",
+                         cudaGetErrorString(ce));
+    for (int r = 0; r < nr; ++r)
+      if (P.peer_base[r] && P.peer_base[r] != P.heap) cudaIpcCloseMemHandle(P.peer_base[r]);
+    cudaFree(P.heap);
+    P = P2P();
+    return APDX_OK;
+  }
+  P.vec_base = hdr_vec(P.heap);
+  P.err_d = hdr_err(P.heap);
+  if (pl->rank_lo >= 0) { P.peer_vec[0] = hdr_vec(P.peer_base[pl->rank_lo]); P.peer_hflag[0] = hdr_hflag(P.peer_base[pl->rank_lo]) + 1; }
+  if (pl->rank_hi >= 0) { P.peer_vec[1] = hdr_vec(P.peer_base[pl->rank_hi]); P.peer_hflag[1] = hdr_hflag(P.peer_base[pl->rank_hi]) + 0; }
+  P2PDev d{};
+  d.rank = me; d.nranks = nr; d.has_lo = pl->rank_lo >= 0; d.has_hi = pl->rank_hi >= 0;
+  for (int r = 0; r < nr; ++r) { d.mbox[r] = hdr_mbox(P.peer_base[r]); d.mflag[r] = hdr_mflag(P.peer_base[r]); }
+  d.hflag_self = hdr_hflag(P.heap);
+  d.err = P.err_d;
+  APDX_CUDA(cudaMalloc((void **)&P.dev, sizeof(P2PDev)));
+  APDX_CUDA(cudaMemcpy(P.dev, &d, sizeof(P2PDev), cudaMemcpyHostToDevice));
+  P.red_epoch = 0;
+  P.halo_epoch = 0;
+  P.enabled = true;
   return APDX_OK;
 }
 
@@ -159,6 +279,15 @@ int apdx_comm_allreduce_host(double *inout_h, int32_t count, int32_t op) {
 
 int apdx_comm_destroy(void) {
   if (g_nccl.comm) {
+    if (!g_parked.empty()) {  // barrier: no rank may still be storing into a heap that is about to be freed
+      double *b = nullptr;
+      APDX_CUDA(cudaMalloc((void **)&b, sizeof(double)));
+      APDX_CUDA(cudaMemset(b, 0, sizeof(double)));
+      APDX_NCCL(g_nccl.AllReduce(b, b, 1, ncclFloat64, ncclSum, g_nccl.comm, 0));
+      APDX_CUDA(cudaStreamSynchronize(0));
+      cudaFree(b);
+      p2p_free_parked();
+    }
     APDX_NCCL(g_nccl.CommDestroy(g_nccl.comm));
     g_nccl.comm = nullptr;
     g_nccl.nranks = 1;

@@ -71,16 +71,20 @@ def solve_linear(prob, dofs, solver="lapack", krylov_tol=None, nodal_imposition=
 
 
 def damped_newton(prob, dofs0, newton_tol=1e-8, maxiter=30, damping=1.0, solver="lapack",
-                  krylov_tol=None, nodal_imposition=True, history=None):
-    """solver.py:872-948.  Returns (dofs, (n_steps, res_norm, diverged))."""
+                  krylov_tol=None, nodal_imposition=True, history=None, lin_solve_fun=None, residual_fun=None,
+                  free=None):
+    """solver.py:872-948.  Returns (dofs, (n_steps, res_norm, diverged)).
+    lin_solve_fun / residual_fun / free override the problem's own (used to pin the loop semantics)."""
     dofs = np.array(dofs0, dtype=np.float64)
-    free = ~prob.mask if nodal_imposition else np.ones(dofs.shape, dtype=bool)
+    if free is None:
+        free = ~prob.mask if nodal_imposition else np.ones(dofs.shape, dtype=bool)
     itt, not_stop, res_norm, diverged = 0, True, 0.0, False
     while not_stop:
         res_old = res_norm
-        delta = solve_linear(prob, dofs, solver, krylov_tol, nodal_imposition)
+        delta = (lin_solve_fun(dofs) if lin_solve_fun is not None
+                 else solve_linear(prob, dofs, solver, krylov_tol, nodal_imposition))
         dofs = np.where(free, dofs + damping * delta, delta)           # :879-892
-        R = prob.residual(dofs).reshape(dofs.shape)
+        R = (residual_fun(dofs) if residual_fun is not None else prob.residual(dofs)).reshape(dofs.shape)
         rf = np.where(free, R, 0.0).ravel()                             # :900 (mask_select zero-fills)
         res_norm = float(np.linalg.norm(rf))
         not_stop = res_norm > newton_tol                                # :904

@@ -1,0 +1,216 @@
+#!/usr/bin/env python
+"""Generate tests/golden/reference_fixtures.npz by EXECUTING the unmodified reference (AutoPDEx under
+/root/reference) on top of the NumPy stand-in for JAX in fakejax.py.  Runs only in the build container
+(the reference tree does not travel to the GPU box); the .npz it writes is committed.
+
+    python tests/golden/make_reference_fixtures.py [case ...]
+
+Every array saved here is an OUTPUT OF THE REFERENCE'S OWN CODE (assembler.assemble_residual /
+assemble_tangent / _get_indices, solver.solver, mesher, seeder, spaces, geometry selectors); see fakejax.py
+for what is substituted (the AD engine is numerical: tangents ~1e-9, everything else ~1e-14).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import fakejax  # noqa: E402
+
+jax = fakejax.install()
+import flax  # noqa: E402
+import jax.numpy as jnp  # noqa: E402
+from autopdex import assembler, geometry, mesher, models, seeder, solver, spaces, utility  # noqa: E402
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from tests import problems  # noqa: E402  (mesh DATA of the Cook test only)
+
+OUT = os.path.join(HERE, "reference_fixtures.npz")
+A = lambda x: np.asarray(x)
+
+
+def bcoo_arrays(mat):
+    return A(mat.data).astype(float), A(mat.indices)[:, 0].astype(np.int64), A(mat.indices)[:, 1].astype(np.int64)
+
+
+def case_tables(out):
+    for d in (1, 2, 3):
+        for o in (1, 2, 3, 4, 5, 6):
+            x, w = seeder.gauss_legendre_nd(dimension=d, order=o)
+            out["gauss_%d_%d_x" % (d, o)], out["gauss_%d_%d_w" % (d, o)] = A(x), A(w)
+    for o in (1, 2):
+        x, w = seeder.int_pts_ref_tri(o)
+        out["tri_rule_%d_x" % o], out["tri_rule_%d_w" % o] = A(x), A(w)
+        x, w = seeder.int_pts_ref_tet(o)
+        out["tet_rule_%d_x" % o], out["tet_rule_%d_w" % o] = A(x), A(w)
+    rng = np.random.default_rng(11)
+    for fam, fn, cases in (("quad_brick", spaces.fem_iso_line_quad_brick, [(1, 2), (1, 3), (2, 4), (2, 9), (3, 8), (3, 27)]),
+                           ("tri_tet", spaces.fem_iso_line_tri_tet, [(2, 3), (2, 6), (3, 4), (3, 10)])):
+        for dim, nen in cases:
+            xi = rng.uniform(-0.8, 0.8, (5, dim)) if fam == "quad_brick" else rng.uniform(0.05, 0.3, (5, dim))
+            N = np.stack([A(fn(jnp.asarray(p[0] if dim == 1 else p), jnp.zeros((nen, dim)), jnp.eye(nen), None, False, dim))
+                          for p in xi])   # 1-D elements take a scalar xi (vmap over gauss_legendre_nd(1, .))
+            out["shape_%s_%d_%d_xi" % (fam, dim, nen)], out["shape_%s_%d_%d_N" % (fam, dim, nen)] = xi, N
+    cube = [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1.2], [1, 1, 1], [0, 1, 1]]
+    quad = [[0, 0], [2, 0], [2.5, 1.5], [0, 1]]
+    for name, args in (("quad", ((3, 4), quad, "quad")), ("tri", ((3, 4), quad, "tri")),
+                       ("brick", ((2, 3, 4), cube, "brick")), ("tet", ((2, 3, 2), cube, "tet"))):
+        c, e = mesher.structured_mesh(*args)
+        out["mesh_%s_coords" % name], out["mesh_%s_elems" % name] = A(c), A(e).astype(np.int64)
+    c, e = mesher.structured_mesh((2, 2, 2), cube, "brick")
+    c2, e2 = mesher.elevate_mesh_order(c, e)
+    out["mesh_hex27_coords"], out["mesh_hex27_elems"] = A(c2), A(e2).astype(np.int64)
+    c, e = mesher.structured_mesh((3, 2), quad, "tri")
+    c2, e2 = mesher.elevate_mesh_order(c, e)
+    out["mesh_tri6_coords"], out["mesh_tri6_elems"] = A(c2), A(e2).astype(np.int64)
+    # integration points in a triangle mesh ('sparse' mode input, seeder.py:3555-3585)
+    x_int, w_int, n_int, conn = seeder.int_pts_in_tri_mesh(c, e, 2)
+    out["intpts_tri_x"], out["intpts_tri_w"], out["intpts_tri_conn"] = A(x_int), A(w_int), A(conn).astype(np.int64)
+    # array-dof COO index emission (assembler.py:123-141)
+    conn = np.array([[0, 3, 4, 1], [1, 4, 5, 2]])
+    out["indices_nf2"] = A(assembler._get_indices(jnp.asarray(conn), jnp.zeros((6, 2)))).astype(np.int64)
+
+
+def readme_case(n, out, tag):
+    pts = [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]
+    coords, elems = mesher.structured_mesh((n, n), pts, "quad")
+    node_coordinates, connectivity = {"phi": coords}, {"phi": elems}
+    dirichlet_nodes = geometry.in_sdfs(node_coordinates["phi"], lambda x: geometry.psdf_polygon(x, pts))
+    dirichlet_dofs = {"phi": dirichlet_nodes}
+    dirichlet_conditions = utility.dict_zeros_like(dirichlet_dofs, dtype=jnp.float64)
+
+    def integrand_fun(x_int, ansatz_fun, settings, static_settings, elem_number, set):   # short_example.py:23-33
+        x = ansatz_fun["physical coor"](x_int)
+        phi_fun = ansatz_fun["phi"]
+        phi = phi_fun(x_int)
+        dphi_dx = jax.jacrev(phi_fun)(x_int)
+        x_1 = x
+        x_2 = x - jnp.array([1., 0.5])
+        source_term = 20 * (jnp.sin(10 * x_1 @ x_1) - jnp.cos(10 * x_2 @ x_2))
+        return (1 / 2) * dphi_dx @ dphi_dx - source_term * phi
+
+    user_potential = models.mixed_reference_domain_potential(
+        integrand_fun, {"phi": spaces.fem_iso_line_quad_brick}, *seeder.gauss_legendre_nd(dimension=2, order=2), "phi")
+    static_settings = flax.core.FrozenDict({"assembling mode": ("user potential",), "solution structure": ("nodal imposition",),
+                                            "model": (user_potential,), "solver type": "newton", "solver backend": "scipy",
+                                            "solver": "lapack", "verbose": -1})
+    settings = {"connectivity": (connectivity,), "dirichlet dofs": dirichlet_dofs, "node coordinates": node_coordinates,
+                "dirichlet conditions": dirichlet_conditions}
+    rng = np.random.default_rng(5)
+    dofs = {"phi": jnp.asarray(rng.uniform(-1, 1, coords.shape[0]))}
+    R = assembler.assemble_residual(dofs, settings, static_settings)
+    K = assembler.assemble_tangent(dofs, settings, static_settings)
+    data, rows, cols = bcoo_arrays(K)
+    sol, infos = solver.solver(utility.dict_zeros_like(dirichlet_dofs, dtype=jnp.float64), settings, static_settings)
+    out.update({tag + "_mask": A(dirichlet_nodes), tag + "_dofs": A(dofs["phi"]), tag + "_R": A(R["phi"]),
+                tag + "_K_data": data, tag + "_K_rows": rows, tag + "_K_cols": cols, tag + "_sol": A(sol["phi"]),
+                tag + "_infos": np.array([float(infos[0]), float(infos[1]), float(infos[2])])})
+
+
+def element_case(out, tag, coords, elems, nf, weak, ansatz, gp, surf=None, settings_extra=None, dofs_scale=0.02,
+                 solve=False, dirichlet_dofs=None):
+    """'user element' sets: domain element (+ optional surface set) -> R, K (BCOO) at random dofs, optional solve."""
+    elem = models.isoparametric_domain_element_galerkin(weak, ansatz, *gp)
+    model_list, conn_list, modes = [elem], [jnp.asarray(elems)], ["user element"]
+    if surf is not None:
+        s_elems, s_weak, s_gp = surf
+        model_list.append(models.isoparametric_surface_element_galerkin(s_weak, ansatz, *s_gp, tangent_contributions=False))
+        conn_list.append(jnp.asarray(s_elems))
+        modes.append("user element")
+    n = len(model_list)
+    static_settings = flax.core.FrozenDict({"number of fields": (nf,) * n, "assembling mode": tuple(modes),
+                                            "solution structure": ("nodal imposition",) * n, "model": tuple(model_list),
+                                            "solver type": "newton", "solver backend": "scipy", "solver": "lapack",
+                                            "verbose": -1})
+    if dirichlet_dofs is None:
+        dirichlet_dofs = np.zeros((coords.shape[0], nf), dtype=bool)
+    settings = {"dirichlet dofs": jnp.asarray(dirichlet_dofs), "connectivity": tuple(conn_list),
+                "node coordinates": jnp.asarray(coords), "dirichlet conditions": jnp.zeros((coords.shape[0], nf))}
+    settings.update(settings_extra or {})
+    rng = np.random.default_rng(7)
+    dofs = jnp.asarray(rng.uniform(-dofs_scale, dofs_scale, (coords.shape[0], nf)))
+    t = time.time()
+    R = assembler.assemble_residual(dofs, settings, static_settings)
+    K = assembler.assemble_tangent(dofs, settings, static_settings)
+    data, rows, cols = bcoo_arrays(K)
+    out.update({tag + "_dofs": A(dofs), tag + "_R": A(R), tag + "_K_data": data, tag + "_K_rows": rows, tag + "_K_cols": cols})
+    if solve:
+        sol, infos = solver.solver(jnp.zeros((coords.shape[0], nf)), settings, static_settings)
+        out[tag + "_sol"] = A(sol)
+        out[tag + "_infos"] = np.array([float(infos[0]), float(infos[1]), float(infos[2])])
+    print("  %s: %d dofs, %.1f s" % (tag, dofs.size, time.time() - t), flush=True)
+
+
+def case_elements(out):
+    E = lambda x, settings: settings["youngs modulus"]
+    nu = lambda x, settings: settings["poisson ratio"]
+    mat = {"youngs modulus": 100.0, "poisson ratio": 0.3, "load multiplier": 4.0}
+    # Cook's membrane, first 2 of the 12 Q2 elements + the two line3 Neumann elements (G2 set-up)
+    coords, elems = problems.COOK_NODES, problems.COOK_ELEMS
+    neumann = problems.COOK_SURF[[4, 5]]
+    weak = models.hyperelastic_steady_state_weak(models.neo_hooke, E, nu, "plain strain")
+    trac = models.neumann_weak(lambda x, settings: jnp.asarray([0., settings["load multiplier"]]))
+    element_case(out, "cook_q9", coords, elems[[2, 4]], 2, weak, spaces.fem_iso_line_quad_brick,
+                 seeder.gauss_legendre_nd(dimension=2, order=4),
+                 surf=(neumann, trac, seeder.gauss_legendre_nd(dimension=1, order=4)), settings_extra=mat, dofs_scale=0.3)
+    # hex8 neo-Hooke 3-D + quad4 traction face
+    c, e = mesher.structured_mesh((1, 1, 2), [[0, 0, 0], [1, 0, 0], [1.1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1.2], [1, 1, 1], [0, 1, 1]], "brick")
+    weak3 = models.hyperelastic_steady_state_weak(models.neo_hooke, E, nu, "3d")
+    trac3 = models.neumann_weak(lambda x, settings: jnp.asarray([0., 0.5, -settings["load multiplier"]]))
+    top = np.array([[2, 8, 11, 5]])                     # nodes with k = 2 (z top), any order is a valid quad4 input
+    element_case(out, "hex8_neo", A(c), A(e), 3, weak3, spaces.fem_iso_line_quad_brick,
+                 seeder.gauss_legendre_nd(dimension=3, order=2),
+                 surf=(top, trac3, seeder.gauss_legendre_nd(dimension=2, order=2)), settings_extra=mat, dofs_scale=0.03)
+    # linear elasticity: the three modes (plain strain carries the reference's C33 quirk)
+    cq, eq = mesher.structured_mesh((2, 1), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "quad")
+    for mode in ("plain strain", "plain stress"):
+        w = models.linear_elasticity_weak(E, nu, mode, lambda x: jnp.asarray([0.3, -1.0]))
+        element_case(out, "linel_" + mode.replace(" ", "_"), A(cq), A(eq), 2, w, spaces.fem_iso_line_quad_brick,
+                     seeder.gauss_legendre_nd(dimension=2, order=2), settings_extra=mat, dofs_scale=0.05)
+    w = models.linear_elasticity_weak(E, nu, "3d", lambda x: jnp.asarray([0.3, -1.0, 0.2]))
+    element_case(out, "linel_3d", A(c), A(e)[:1], 3, w, spaces.fem_iso_line_quad_brick,
+                 seeder.gauss_legendre_nd(dimension=3, order=2), settings_extra=mat, dofs_scale=0.05)
+    # P2 triangles as isoparametric user elements (spaces.fem_iso_line_tri_tet), neo-Hooke plain strain
+    ct, et = mesher.structured_mesh((1, 1), [[0, 0], [2, 0], [2.3, 1.0], [0, 1]], "tri")
+    ct, et = mesher.elevate_mesh_order(ct, et)
+    element_case(out, "tri6_neo", A(ct), A(et), 2, weak, spaces.fem_iso_line_tri_tet, seeder.int_pts_ref_tri(2),
+                 settings_extra=mat, dofs_scale=0.05)
+
+
+def case_newton_semantics(out):
+    """solver.damped_newton (solver.py:837-948) driven by synthetic residual sequences."""
+    def run(norms, newton_tol=1e-8, maxiter=30):
+        state = {"k": 0}
+
+        def lin_solve(d):
+            return jnp.zeros(2)
+
+        def residual(d):
+            r = norms[min(state["k"], len(norms) - 1)]
+            state["k"] += 1
+            return jnp.asarray([r, 0.0])
+        sol, (it, rn, div) = solver.damped_newton(jnp.zeros(2), residual, lin_solve, jnp.asarray([True, True]), newton_tol,
+                                                  maxiter, 1.0, verbose=-1)
+        return [float(it), float(rn), float(div)]
+    out["newton_converge"] = np.array(run([1.0, 1e-3, 1e-9]))
+    out["newton_diverge"] = np.array(run([1.0, 0.5, 0.4, 8.0, 1e-9]))
+    out["newton_early_jump_ok"] = np.array(run([1.0, 50.0, 1e-9]))         # ratio > 10 at itt <= 1 is tolerated
+    out["newton_nan"] = np.array(run([1.0, float("nan"), 1e-9]))
+    out["newton_maxiter"] = np.array(run([1.0] * 10, maxiter=3))
+
+
+CASES = {"tables": case_tables, "readme3": lambda o: readme_case(3, o, "readme3"),
+         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements,
+         "newton": case_newton_semantics}
+
+if __name__ == "__main__":
+    out = dict(np.load(OUT)) if os.path.exists(OUT) else {}
+    for name in (sys.argv[1:] or list(CASES)):
+        t = time.time()
+        print("case", name, flush=True)
+        CASES[name](out)
+        print("  done in %.1f s" % (time.time() - t), flush=True)
+        np.savez_compressed(OUT, **out)
+    print("wrote", OUT, "with", len(out), "arrays")

@@ -1,0 +1,131 @@
+"""Oracle and host code against OUTPUTS OF THE REFERENCE ITSELF.
+
+tests/golden/reference_fixtures.npz was produced by tests/golden/make_reference_fixtures.py, which executes the
+unmodified AutoPDEx modules on a NumPy stand-in for JAX (tests/golden/fakejax.py; AD replaced by numerical
+differentiation: tangents ~1e-9, everything else ~1e-14).  The reference tree does not travel to the GPU box,
+the fixture file does.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from autopdex_b200 import mesher, seeder, spaces
+from oracle import assemble as oasm
+from oracle import mesher as omesh
+from oracle import quadrature as oquad
+from oracle import shapes as oshapes
+from oracle import solve as osolve
+from tests import problems
+
+FIX = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_fixtures.npz"))
+TANGENT_RTOL = 2e-7        # numerical AD in the generator
+EXACT_RTOL = 1e-12
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---- tables: quadrature, shape functions, meshes, COO index order ------------------------------------------
+def test_gauss_rules_match_reference_tables():
+    for d in (1, 2, 3):
+        for o in (1, 2, 3, 4, 5, 6):
+            for impl in (seeder.gauss_legendre_nd, oquad.gauss_legendre_nd):
+                x, w = impl(d, o)
+                assert np.abs(x - FIX["gauss_%d_%d_x" % (d, o)]).max() < 4e-15
+                assert np.abs(w - FIX["gauss_%d_%d_w" % (d, o)]).max() < 4e-15
+
+
+def test_simplex_rules_low_order_match_reference():
+    x, w = seeder.int_pts_ref_tri(1)
+    assert np.allclose(x, FIX["tri_rule_1_x"]) and np.allclose(w, FIX["tri_rule_1_w"])
+    x, w = seeder.int_pts_ref_tri(2)
+    # same rule, possibly another point order: compare as sets
+    assert np.allclose(sorted(map(tuple, np.round(x, 12))), sorted(map(tuple, np.round(FIX["tri_rule_2_x"], 12))))
+    assert np.allclose(w, FIX["tri_rule_2_w"], atol=1e-15)
+    x, w = seeder.int_pts_ref_tet(1)
+    assert np.allclose(x, FIX["tet_rule_1_x"][:, :3] if FIX["tet_rule_1_x"].shape[1] > 3 else FIX["tet_rule_1_x"])
+
+
+@pytest.mark.parametrize("fam,dim,nen,name", [
+    ("quad_brick", 1, 2, "line2"), ("quad_brick", 1, 3, "line3"), ("quad_brick", 2, 4, "quad4"),
+    ("quad_brick", 2, 9, "quad9"), ("quad_brick", 3, 8, "hex8"), ("quad_brick", 3, 27, "hex27"),
+    ("tri_tet", 2, 3, "tri3"), ("tri_tet", 2, 6, "tri6"), ("tri_tet", 3, 4, "tet4"), ("tri_tet", 3, 10, "tet10")])
+def test_shape_functions_match_reference_generated_code(fam, dim, nen, name):
+    xi, N = FIX["shape_%s_%d_%d_xi" % (fam, dim, nen)], FIX["shape_%s_%d_%d_N" % (fam, dim, nen)]
+    assert np.abs(spaces.shape_tables(fam, nen, dim, xi)[0] - N).max() < 1e-13      # product host tables
+    assert np.abs(oshapes.shape_tables(name, xi)[0] - N).max() < 1e-13              # oracle
+
+
+def test_meshes_match_reference_mesher():
+    cube = [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1.2], [1, 1, 1], [0, 1, 1]]
+    quad = [[0, 0], [2, 0], [2.5, 1.5], [0, 1]]
+    for name, args in (("quad", ((3, 4), quad, "quad")), ("tri", ((3, 4), quad, "tri")),
+                       ("brick", ((2, 3, 4), cube, "brick")), ("tet", ((2, 3, 2), cube, "tet"))):
+        for impl in (mesher.structured_mesh, omesh.structured_mesh):
+            c, e = impl(*args)
+            assert np.array_equal(e, FIX["mesh_%s_elems" % name]) and np.abs(c - FIX["mesh_%s_coords" % name]).max() < 1e-15
+    c, e = mesher.structured_mesh((2, 2, 2), cube, "brick")
+    for impl in (mesher.elevate_mesh_order, omesh.elevate_bricks):
+        c2, e2 = impl(c, e)
+        assert np.array_equal(e2, FIX["mesh_hex27_elems"]) and np.allclose(c2, FIX["mesh_hex27_coords"], atol=1e-15)
+    c, e = mesher.structured_mesh((3, 2), quad, "tri")
+    for impl in (mesher.elevate_mesh_order, omesh.elevate_triangles):
+        c2, e2 = impl(c, e)
+        assert np.array_equal(e2, FIX["mesh_tri6_elems"]) and np.allclose(c2, FIX["mesh_tri6_coords"], atol=1e-15)
+    x, w, n, conn = seeder.int_pts_in_tri_mesh(c, e, 2)
+    assert np.array_equal(conn, FIX["intpts_tri_conn"]) and np.allclose(w, FIX["intpts_tri_w"], rtol=1e-13)
+    # same points per element, the rule's internal point order may differ
+    assert np.allclose(np.sort(x.reshape(-1, 3, 2), axis=1), np.sort(FIX["intpts_tri_x"].reshape(-1, 3, 2), axis=1))
+
+
+def test_coo_index_order_matches_reference_get_indices():
+    conn = np.array([[0, 3, 4, 1], [1, 4, 5, 2]])
+    rows, cols = oasm.coo_indices([dict(conn=conn, nf=2)])
+    assert np.array_equal(np.stack([rows, cols], axis=1), FIX["indices_nf2"])
+
+
+# ---- assembled residuals / tangents / solutions produced by the reference's assembler and solver ---------------
+def _check_against_reference(p, tag, settings=None, check_sol=False):
+    dofs = FIX[tag + "_dofs"].reshape(p["mask"].shape)
+    R, data = oasm.assemble(p["sets"], p["coords"], dofs, settings or {})
+    rows, cols = oasm.coo_indices(p["sets"])
+    assert np.array_equal(rows, FIX[tag + "_K_rows"]) and np.array_equal(cols, FIX[tag + "_K_cols"])
+    assert rel(R, FIX[tag + "_R"].ravel()) < EXACT_RTOL
+    assert rel(data, FIX[tag + "_K_data"]) < TANGENT_RTOL
+    if check_sol:
+        prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+        sol, (it, rn, div) = osolve.damped_newton(prob, np.zeros(p["mask"].shape))
+        assert it == int(FIX[tag + "_infos"][0]) and div == bool(FIX[tag + "_infos"][2])
+        assert rel(sol.ravel(), FIX[tag + "_sol"].ravel()) < 1e-9
+
+
+@pytest.mark.parametrize("n", [3, 5])
+def test_readme_potential_against_reference_run(n):
+    p = problems.readme_poisson(n)
+    tag = "readme%d" % n
+    assert np.array_equal(p["mask"][:, 0], FIX[tag + "_mask"])        # geometry.psdf_polygon: corners are NOT Dirichlet
+    _check_against_reference(p, tag, check_sol=True)
+    if n == 5:
+        assert np.isclose(FIX[tag + "_sol"].sum(), 1.9066412530282952, rtol=1e-13)   # the run reproduces the reference's golden
+
+
+def test_newton_loop_semantics_against_reference_damped_newton():
+    def run(norms, newton_tol=1e-8, maxiter=30):
+        k = {"i": 0}
+
+        def residual(d):
+            r = norms[min(k["i"], len(norms) - 1)]
+            k["i"] += 1
+            return np.array([r, 0.0])
+        _, (it, rn, div) = osolve.damped_newton(None, np.zeros(2), newton_tol, maxiter, 1.0, lin_solve_fun=lambda d: np.zeros(2),
+                                                residual_fun=residual, free=np.array([True, True]))
+        return it, rn, div
+    for name, args in (("newton_converge", ([1.0, 1e-3, 1e-9],)), ("newton_diverge", ([1.0, 0.5, 0.4, 8.0, 1e-9],)),
+                       ("newton_early_jump_ok", ([1.0, 50.0, 1e-9],)), ("newton_nan", ([1.0, float("nan"), 1e-9],)),
+                       ("newton_maxiter", ([1.0] * 10, 1e-8, 3))):
+        it, rn, div = run(*args)
+        ref = FIX[name]
+        assert it == int(ref[0]) and div == bool(ref[2]), name
+        assert (np.isnan(rn) and np.isnan(ref[1])) or np.isclose(rn, ref[1]), name
