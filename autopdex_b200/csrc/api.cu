@@ -351,13 +351,14 @@ int apdx_plan_destroy(apdx_plan *pl) {
   pl->row_ptr.release(); pl->col.release(); pl->elem_map.release(); pl->perm.release(); pl->seg_ptr.release();
   pl->rperm.release(); pl->rseg_ptr.release(); pl->red_row_ptr.release(); pl->red_col.release();
   pl->red2full.release(); pl->red_diag.release(); pl->ke.release(); pl->re.release(); pl->vals.release();
+  for (auto &g : pl->kgraph) if (g.exec) cudaGraphExecDestroy(g.exec);
   p2p_teardown(pl);
   pl->sell.release();
   pl->red_vals.release(); pl->residual.release(); pl->rhs_red.release(); pl->x_red.release(); pl->dofs_trial.release();
   KrylovWork &k = pl->kw;
   k.r.release(); k.p.release(); k.q.release(); k.z.release(); k.s.release(); k.t.release(); k.phat.release();
   k.shat.release(); k.r0.release(); k.minv.release(); k.partial.release(); k.scal.release(); k.ticket.release();
-  k.flags.release();
+  k.flags.release(); k.st_sc.release(); k.st_fl.release(); k.scratch.release();
   if (pl->pinned) cudaFreeHost(pl->pinned);
   for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
   if (pl->stream) cudaStreamDestroy(pl->stream);
@@ -613,6 +614,7 @@ int apdx_plan_set_partition(apdx_plan *pl, int64_t owned_dof_begin, int64_t owne
   APDX_CUDA(cudaMemcpyAsync(out, tmp_d, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, pl->stream));
   APDX_CUDA(cudaStreamSynchronize(pl->stream));
   cudaFree(tmp_d);
+  for (auto &g : pl->kgraph) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
   pl->sell.release();
   pl->have_sell_values = false;
   pl->owned_begin = owned_dof_begin; pl->owned_end = owned_dof_end;

@@ -105,6 +105,8 @@ struct KrylovWork {
   DevBuf<double> r, p, q, z, s, t, phat, shat, r0, minv;
   DevBuf<double> partial;     // per-block partial sums of the fused dot products
   DevBuf<double> scal;        // device scalars (see krylov.cu)
+  DevBuf<double> st_sc, scratch;  // double-buffered scalar state of the p2p-fused CG, reduction scratch
+  DevBuf<int32_t> st_fl;
   DevBuf<unsigned int> ticket;
   DevBuf<int32_t> flags;      // [0]=done [1]=iterations [2]=breakdown
 };
@@ -132,6 +134,15 @@ struct P2P {
   int *peer_hflag[2]{};          // lower neighbour's hflag[1], upper neighbour's hflag[0]
   int64_t peer_lo_f1 = 0;        // lower neighbour's owned end = start of its upper ghost range
   int red_epoch = 0, halo_epoch = 0;
+};
+
+// instantiated CUDA graph of one chunk of Krylov iterations (krylov.cu)
+struct KrylovGraph {
+  cudaGraphExec_t exec = nullptr;
+  const void *rhs = nullptr, *x = nullptr;
+  int mode = -1, chunk = 0;
+  int64_t i0 = 0, i1 = 0;
+  double kernel_launches = 0, spmv_launches = 0;
 };
 
 // sliced-ELL copy of the owned rows of the reduced system (sell.cu)
@@ -198,6 +209,7 @@ struct apdx_plan {
   apdx::KrylovWork kw;
   apdx::Sell sell;
   apdx::P2P p2p;
+  apdx::KrylovGraph kgraph[2];   // [0] CG, [1] BiCGSTAB
   bool have_sell_values = false, have_red_values = false;
   double *pinned = nullptr;                // small pinned host staging
   apdx::Stats stats;

@@ -162,7 +162,8 @@ static void p2p_free_parked() {
 int p2p_setup(apdx_plan *pl) {
   P2P &P = pl->p2p;
   const char *mode = getenv("APDX_COMM");
-  if (mode && strcmp(mode, "nccl") == 0) return APDX_OK;  // A/B switch: NCCL-only Krylov loop
+  // opt-in A/B variants of the Krylov loop (APDX_COMM=p2p | fused); the default multi-GPU path is NCCL
+  if (!mode || (strcmp(mode, "p2p") != 0 && strcmp(mode, "fused") != 0)) return APDX_OK;
   if (g_nccl.nranks > P2P_MAX_RANKS) return APDX_OK;
   p2p_teardown(pl);
   cudaStream_t s = pl->stream;
@@ -235,6 +236,7 @@ int p2p_setup(apdx_plan *pl) {
   P.red_epoch = 0;
   P.halo_epoch = 0;
   P.enabled = true;
+  if (getenv("APDX_VERBOSE")) fprintf(stderr, "[apdx_b200] rank %d: peer-to-peer Krylov loop enabled (heap %.1f MB, stride %lld)\n", me, P.heap_bytes / 1e6, (long long)P.stride);
   return APDX_OK;
 }
 

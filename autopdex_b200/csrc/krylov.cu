@@ -10,6 +10,12 @@
 // product(s) that follow the SpMV fused into the same kernel (warp-shuffle + fixed-order block reduction).  Vector updates are
 // fused axpy+dot kernels.  Dot products are reduced per block, then by the last block in a fixed
 // order (deterministic for a given grid), then -- multi-GPU -- by ncclAllReduce.
+#include <stdlib.h>
+#include <string.h>
+
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace apdx {
@@ -22,7 +28,7 @@ enum {
 };
 enum { F_DONE = 0, F_ITERS = 1, F_BREAKDOWN = 2, F_MAXITER = 3, F_COUNT = 4 };
 // stages of the scalar recurrences
-enum { ST_CG_INIT = 0, ST_CG_PQ, ST_CG_UPDATE, ST_BI_INIT, ST_BI_R0V, ST_BI_S, ST_BI_T, ST_BI_X };
+enum { ST_CG_INIT = 0, ST_CG_PQ, ST_CG_UPDATE, ST_BI_INIT, ST_BI_R0V, ST_BI_S, ST_BI_T, ST_BI_X, ST_CG2_INIT, ST_CG2_ITER };
 
 constexpr int VEC_BLOCK = 256;
 constexpr int VEC_GRID = 148 * 8;
@@ -50,6 +56,29 @@ __device__ __forceinline__ void apply_stage(int stage, double *sc, int32_t *fl) 
       fl[F_ITERS] += 1;
       if (!(pd[1] > sc[S_TOL2]) || fl[F_ITERS] >= fl[F_MAXITER]) fl[F_DONE] = 1;
       if (pd[1] != pd[1]) { fl[F_DONE] = 1; fl[F_BREAKDOWN] = 1; }
+      break;
+    case ST_CG2_INIT:  // single-reduction CG (Chronopoulos-Gear): pend = (w.u, r.u, r.r, b.b)
+      sc[S_RZ] = pd[1]; sc[S_RR] = pd[2]; sc[S_BB] = pd[3];
+      {
+        double t = sc[S_TOL2] * pd[3];
+        double a2 = sc[S_SS];
+        sc[S_TOL2] = t > a2 ? t : a2;
+      }
+      sc[S_BETA] = 0.0;
+      sc[S_ALPHA] = pd[1] / pd[0];
+      if (!(sc[S_RR] > sc[S_TOL2])) fl[F_DONE] = 1;
+      break;
+    case ST_CG2_ITER:  // pend = (w.u, r.u, r.r) after one more update of x and r
+      {
+        const double beta = pd[1] / sc[S_RZ];
+        sc[S_ALPHA] = pd[1] / (pd[0] - beta * pd[1] / sc[S_ALPHA]);
+        sc[S_BETA] = beta;
+        sc[S_RZ] = pd[1];
+        sc[S_RR] = pd[2];
+        fl[F_ITERS] += 1;
+        if (!(pd[2] > sc[S_TOL2]) || fl[F_ITERS] >= fl[F_MAXITER]) fl[F_DONE] = 1;
+        if (pd[2] != pd[2]) { fl[F_DONE] = 1; fl[F_BREAKDOWN] = 1; }
+      }
       break;
     case ST_BI_INIT:  // pend = (r0.r, r.r, b.b)
       sc[S_RHO] = pd[0]; sc[S_RR] = pd[1]; sc[S_BB] = pd[2];
@@ -82,7 +111,7 @@ __device__ __forceinline__ void apply_stage(int stage, double *sc, int32_t *fl) 
 }
 
 __global__ void k_apply_stage(int stage, double *sc, int32_t *fl) {
-  if (fl[F_DONE] && stage != ST_CG_INIT && stage != ST_BI_INIT) return;
+  if (fl[F_DONE] && stage != ST_CG_INIT && stage != ST_BI_INIT && stage != ST_CG2_INIT) return;
   apply_stage(stage, sc, fl);
 }
 
@@ -146,7 +175,7 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_halo_push(const double *__restric
 template <int NV>
 __device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial, unsigned int *ticket,
                                                 double *sc, int32_t *fl, int stage, int fused, const P2PDev *pd,
-                                                int epoch) {
+                                                int epoch, int slot0 = 0) {
   __shared__ double sh[NV][VEC_BLOCK / 32];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -184,7 +213,7 @@ __device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial
     if (threadIdx.x == 0) {
       double y = 0.0;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) y += sh[i][w];
-      sc[S_PEND + i] = y;
+      sc[S_PEND + slot0 + i] = y;
     }
   }
   if (threadIdx.x == 0) {
@@ -321,6 +350,139 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_cg_p(const double *__restrict__ r
     p[i] = minv[i] * r[i] + beta * p[i];
 }
 
+// ---- single-reduction CG (Chronopoulos & Gear) for the multi-GPU path: one vector kernel + one SpMV and ONE
+// all-reduce of (w.u, r.u, r.r) per iteration instead of two.  Same Krylov space and, in exact arithmetic, the
+// same iterates as the three-kernel CG above.
+//   p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M^-1 r ; sums (r.u, r.r) -> slots 1,2
+__global__ void __launch_bounds__(VEC_BLOCK) k_cg2_vec(const double *__restrict__ w, const double *__restrict__ minv,
+                                                       double *__restrict__ u, double *__restrict__ p, double *__restrict__ s,
+                                                       double *__restrict__ x, double *__restrict__ r, int64_t i0, int64_t i1,
+                                                       double *partial, unsigned int *ticket, double *sc, int32_t *fl) {
+  if (fl[F_DONE]) return;
+  const double alpha = sc[S_ALPHA], beta = sc[S_BETA];
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    const double pi = u[i] + beta * p[i];
+    const double si = w[i] + beta * s[i];
+    p[i] = pi;
+    s[i] = si;
+    x[i] += alpha * pi;
+    const double ri = r[i] - alpha * si;
+    r[i] = ri;
+    const double ui = minv[i] * ri;
+    u[i] = ui;
+    acc[0] += ri * ui;
+    acc[1] += ri * ri;
+  }
+  reduce_finalize<2>(acc, partial, ticket, sc, fl, -1, 0, nullptr, 0, 1);
+}
+// r = b - q ; u = M^-1 r ; p = s = 0 ; sums (r.u, r.r, b.b) -> slots 1,2,3
+__global__ void __launch_bounds__(VEC_BLOCK) k_cg2_init(const double *__restrict__ b, const double *__restrict__ q,
+                                                        const double *__restrict__ minv, double *__restrict__ r,
+                                                        double *__restrict__ u, double *__restrict__ p, double *__restrict__ s,
+                                                        int64_t i0, int64_t i1, double *partial, unsigned int *ticket,
+                                                        double *sc, int32_t *fl) {
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    const double ri = bi - q[i];
+    const double ui = minv[i] * ri;
+    r[i] = ri; u[i] = ui; p[i] = 0.0; s[i] = 0.0;
+    acc[0] += ri * ui; acc[1] += ri * ri; acc[2] += bi * bi;
+  }
+  reduce_finalize<3>(acc, partial, ticket, sc, fl, -1, 0, nullptr, 0, 1);
+}
+
+// ---- CG vector kernels, multi-GPU "p2p-fused" variants ---------------------------------------------------------
+// The scalar stage that follows a distributed dot product is applied in the PROLOGUE of the next kernel by every
+// block redundantly (wait for all ranks' mailbox posts, sum them in rank order, run the recurrence on a private
+// copy of the scalar state); block 0 stores the new state into the other half of a double-buffered state array.
+// The halo push of p is fused into the epilogue of the p-update.  Per iteration the GPU runs the same three
+// kernels as on one GPU; NCCL is not involved.
+struct StageCtx {
+  const double *sc_in;
+  double *sc_out;
+  const int32_t *fl_in;
+  int32_t *fl_out;
+  const P2PDev *pd;
+  int epoch, stage, nv;
+};
+__device__ __forceinline__ void stage_prologue(const StageCtx &c, double *s_sc, int32_t *s_fl) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S_COUNT; ++i) s_sc[i] = c.sc_in[i];
+    for (int i = 0; i < F_COUNT; ++i) s_fl[i] = c.fl_in[i];
+    if (!s_fl[F_DONE]) {
+      const int slot = c.epoch & 1;
+      for (int r = 0; r < c.pd->nranks; ++r)
+        p2p_wait(c.pd->mflag[c.pd->rank] + slot * P2P_MAX_RANKS + r, c.epoch, c.pd->err);
+      const volatile double *mb = c.pd->mbox[c.pd->rank] + (size_t)slot * P2P_MAX_RANKS * 4;
+      for (int i = 0; i < c.nv; ++i) {
+        double s = 0.0;
+        for (int r = 0; r < c.pd->nranks; ++r) s += mb[r * 4 + i];
+        s_sc[S_PEND + i] = s;
+      }
+      apply_stage(c.stage, s_sc, s_fl);
+    }
+    if (blockIdx.x == 0) {
+      for (int i = 0; i < S_COUNT; ++i) c.sc_out[i] = s_sc[i];
+      for (int i = 0; i < F_COUNT; ++i) c.fl_out[i] = s_fl[i];
+    }
+  }
+  __syncthreads();
+}
+// prologue: alpha = rz / (p.q);  body as k_cg_update;  the (r.z, r.r) sums are posted with `epoch`
+__global__ void __launch_bounds__(VEC_BLOCK) k_cg_update_pf(StageCtx st, const double *__restrict__ p,
+                                                            const double *__restrict__ q, const double *__restrict__ minv,
+                                                            double *__restrict__ x, double *__restrict__ r, int64_t i0,
+                                                            int64_t i1, double *partial, unsigned int *ticket,
+                                                            double *scratch, int epoch) {
+  __shared__ double s_sc[S_COUNT];
+  __shared__ int32_t s_fl[F_COUNT];
+  stage_prologue(st, s_sc, s_fl);
+  if (s_fl[F_DONE]) return;
+  const double alpha = s_sc[S_ALPHA];
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    double ri = r[i] - alpha * q[i];
+    r[i] = ri;
+    acc[0] += ri * (minv[i] * ri);
+    acc[1] += ri * ri;
+  }
+  reduce_finalize<2>(acc, partial, ticket, scratch, nullptr, ST_CG_UPDATE, 0, st.pd, epoch);
+}
+// prologue: beta, iteration count, convergence test;  body as k_cg_p;  epilogue: push the owned boundary entries of
+// the new p into the neighbours' ghost ranges and raise their halo flags
+__global__ void __launch_bounds__(VEC_BLOCK) k_cg_p_pf(StageCtx st, const double *__restrict__ r,
+                                                       const double *__restrict__ minv, double *__restrict__ p, int64_t i0,
+                                                       int64_t i1, int64_t send_lo, int64_t send_hi, double *peer_lo_dst,
+                                                       double *peer_hi_dst, int *peer_lo_flag, int *peer_hi_flag,
+                                                       int halo_epoch, unsigned int *ticket) {
+  __shared__ double s_sc[S_COUNT];
+  __shared__ int32_t s_fl[F_COUNT];
+  __shared__ bool last;
+  stage_prologue(st, s_sc, s_fl);
+  if (s_fl[F_DONE]) return;
+  const double beta = s_sc[S_BETA];
+  bool pushed = false;
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+    const double pn = minv[i] * r[i] + beta * p[i];
+    p[i] = pn;
+    if (peer_lo_dst && i - i0 < send_lo) { peer_lo_dst[i - i0] = pn; pushed = true; }
+    if (peer_hi_dst && i >= i1 - send_hi) { peer_hi_dst[i - (i1 - send_hi)] = pn; pushed = true; }
+  }
+  if (pushed) __threadfence_system();   // only the few threads that stored into peer memory pay the system fence
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *ticket = 0u;
+    __threadfence_system();
+    if (peer_lo_flag) *(volatile int *)peer_lo_flag = halo_epoch;
+    if (peer_hi_flag) *(volatile int *)peer_hi_flag = halo_epoch;
+  }
+}
+
 // ---- BiCGSTAB vector kernels --------------------------------------------------------------------
 // r = b - q ; r0 = r ; p = 0 ; v = 0 ; sums (r0.r, r.r, b.b)
 __global__ void __launch_bounds__(VEC_BLOCK) k_bi_init(const double *__restrict__ b, const double *__restrict__ q,
@@ -403,10 +565,18 @@ int krylov_alloc(apdx_plan *pl) {
   if (pl->p2p.enabled) k.p.adopt(pl->p2p.vec_base + 0 * pl->p2p.stride, n); else APDX_CHECK(k.p.alloc(n));
   APDX_CHECK(k.q.alloc(n));
   APDX_CHECK(k.minv.alloc(n));
+  if (comm_active()) {  // single-reduction CG needs u and s = A p as well
+    APDX_CHECK(k.z.alloc(n));
+    APDX_CHECK(k.s.alloc(n));
+    APDX_CUDA(cudaMemsetAsync(k.z.p, 0, n * sizeof(double), pl->stream));
+  }
   APDX_CHECK(k.partial.alloc(4 * (size_t)(VEC_GRID > 148 * 32 ? VEC_GRID : 148 * 32)));
-  APDX_CHECK(k.scal.alloc(S_COUNT));
+  APDX_CHECK(k.st_sc.alloc(2 * S_COUNT));
+  APDX_CHECK(k.st_fl.alloc(2 * F_COUNT));
+  APDX_CHECK(k.scratch.alloc(S_COUNT));
+  k.scal.adopt(k.st_sc.p, S_COUNT);     // half 0 of the double-buffered scalar state
+  k.flags.adopt(k.st_fl.p, F_COUNT);
   APDX_CHECK(k.ticket.alloc(2));
-  APDX_CHECK(k.flags.alloc(F_COUNT));
   APDX_CUDA(cudaMemsetAsync(k.ticket.p, 0, 2 * sizeof(unsigned int), pl->stream));
   // halo entries outside the owned range must read as finite numbers
   APDX_CUDA(cudaMemsetAsync(k.p.p, 0, n * sizeof(double), pl->stream));
@@ -414,9 +584,9 @@ int krylov_alloc(apdx_plan *pl) {
 }
 static int krylov_alloc_bicgstab(apdx_plan *pl) {
   KrylovWork &k = pl->kw;
-  if (k.s.p) return APDX_OK;
+  if (k.t.p) return APDX_OK;
   const int64_t n = pl->n_free;
-  APDX_CHECK(k.s.alloc(n));
+  if (!k.s.p) APDX_CHECK(k.s.alloc(n));
   APDX_CHECK(k.t.alloc(n));
   if (pl->p2p.enabled) k.phat.adopt(pl->p2p.vec_base + 1 * pl->p2p.stride, n); else APDX_CHECK(k.phat.alloc(n));
   if (pl->p2p.enabled) k.shat.adopt(pl->p2p.vec_base + 2 * pl->p2p.stride, n); else APDX_CHECK(k.shat.alloc(n));
@@ -555,10 +725,23 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
   APDX_CUDA(cudaMemcpyAsync(k.flags.p, fl_h, sizeof(fl_h), cudaMemcpyHostToDevice, s));
   pl->stats.kernel_launches += 1;
 
+  const char *cm = getenv("APDX_COMM");
+  // multi-GPU CG default: the three-kernel CG with NCCL halo + all-reduces.  Measured alternatives, opt-in through
+  // APDX_COMM: cg2 = single-reduction CG; p2p / fused = CUDA-IPC peer stores instead of NCCL
+  const bool cg2 = !bi && c.multi && !c.p2p && cm && strcmp(cm, "cg2") == 0;
+
   // q = A x0 (x is the caller's buffer: its ghost entries travel with NCCL)
   if (c.multi) APDX_CHECK(comm_halo_exchange(pl, x, s));
   APDX_CHECK(launch_spmv<0>(pl, x, bi ? k.t.p : k.q.p, nullptr, 0, 0));
-  if (!bi) {
+  if (cg2) {
+    k_cg2_init<<<VEC_GRID, VEC_BLOCK, 0, s>>>(rhs, k.q.p, k.minv.p, k.r.p, k.z.p, k.p.p, k.s.p, i0, i1, k.partial.p,
+                                              k.ticket.p, k.scal.p, k.flags.p);
+    APDX_CHECK(comm_halo_exchange(pl, k.z.p, s));
+    APDX_CHECK(launch_spmv<1>(pl, k.z.p, k.q.p, k.z.p, -1, 0));
+    APDX_CHECK(comm_allreduce_sum(k.scal.p + S_PEND, 4, s));
+    k_apply_stage<<<1, 1, 0, s>>>(ST_CG2_INIT, k.scal.p, k.flags.p);
+    pl->stats.kernel_launches += 2;
+  } else if (!bi) {
     k_cg_init<<<VEC_GRID, VEC_BLOCK, 0, s>>>(rhs, k.q.p, k.minv.p, k.r.p, k.p.p, i0, i1, k.partial.p, k.ticket.p,
                                              k.scal.p, k.flags.p, ST_CG_INIT, fused, pd, next_red_epoch(pl));
     pl->stats.kernel_launches += 1;
@@ -572,22 +755,93 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
 
   int32_t *fl_pin = reinterpret_cast<int32_t *>(pl->pinned);
   double *sc_pin = pl->pinned + 8;
-  int launched = 0, he = 0;
+  int launched = 0, he = 0, par = 0;
+  const bool trace_on = getenv("APDX_TRACE") != nullptr;
+  const char *ge = getenv("APDX_GRAPH");
+  const bool graphs_on = !(ge && strcmp(ge, "0") == 0);
+  std::vector<std::pair<cudaEvent_t, int>> trace;
+  // p2p-fused CG keeps the scalar state double-buffered in st_sc / st_fl; half 0 aliases k.scal / k.flags
+  const bool pfused = !bi && c.p2p && p2p_is_heap_vector(pl, k.p.p) && !(cm && strcmp(cm, "p2p") == 0);
   while (true) {
-    APDX_CUDA(cudaMemcpyAsync(fl_pin, k.flags.p, sizeof(int32_t) * F_COUNT, cudaMemcpyDeviceToHost, s));
-    APDX_CUDA(cudaMemcpyAsync(sc_pin, k.scal.p, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, s));
+    APDX_CUDA(cudaMemcpyAsync(fl_pin, (pfused ? k.st_fl.p + par * F_COUNT : k.flags.p), sizeof(int32_t) * F_COUNT,
+                              cudaMemcpyDeviceToHost, s));
+    APDX_CUDA(cudaMemcpyAsync(sc_pin, (pfused ? k.st_sc.p + par * S_COUNT : k.scal.p), sizeof(double) * S_COUNT,
+                              cudaMemcpyDeviceToHost, s));
     APDX_CUDA(cudaStreamSynchronize(s));
     if (fl_pin[F_DONE] || launched >= maxiter) break;
     int todo = maxiter - launched < chunk ? maxiter - launched : chunk;
-    for (int it = 0; it < todo; ++it) {
-      if (!bi) {
+    const bool tracing = trace_on && launched == chunk;   // APDX_TRACE: time every kernel of the second chunk
+    auto TR = [&](int label) {
+      if (!tracing) return;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, s);
+      trace.push_back({e, label});
+    };
+    TR(-1);
+    auto one_iteration = [&]() -> int {
+      if (cg2) {
+        // ---- multi-GPU default: vector kernel, halo, SpMV, ONE all-reduce of (w.u, r.u, r.r), scalar stage ----
+        k_cg2_vec<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.q.p, k.minv.p, k.z.p, k.p.p, k.s.p, x, k.r.p, i0, i1, k.partial.p,
+                                                 k.ticket.p, k.scal.p, k.flags.p);
+        TR(3);
+        APDX_CHECK(comm_halo_exchange(pl, k.z.p, s));
+        TR(0);
+        APDX_CHECK(launch_spmv<1>(pl, k.z.p, k.q.p, k.z.p, -1, 1));
+        TR(1);
+        APDX_CHECK(comm_allreduce_sum(k.scal.p + S_PEND, 3, s));
+        k_apply_stage<<<1, 1, 0, s>>>(ST_CG2_ITER, k.scal.p, k.flags.p);
+        TR(2);
+        pl->stats.kernel_launches += 2;
+      } else if (!bi && pfused) {
+        // ---- multi-GPU CG, three kernels per iteration, stages in the prologues (see k_cg_update_pf) ----
+        P2P &P = pl->p2p;
+        if (he == 0) APDX_CHECK(exchange_halo(pl, k.p.p, &he));   // first iteration: standalone push of p
+        {
+          // SpMV posts (p.q) with epoch e1; it reads the done flag of the current state half
+          Sell &S = pl->sell;
+          const int64_t wpb = VEC_BLOCK / 32;
+          int64_t nb = (S.n_slices + wpb - 1) / wpb;
+          unsigned grid = (unsigned)(nb < 148ll * 32 ? (nb > 0 ? nb : 1) : 148ll * 32);
+          const int e1 = ++P.red_epoch;
+          k_spmv_sell<1><<<grid, VEC_BLOCK, 0, s>>>(S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p,
+                                                    pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, k.partial.p, k.ticket.p,
+                                                    k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he);
+          TR(1);
+          pl->stats.spmv_launches += 1;
+          StageCtx c1{k.st_sc.p + par * S_COUNT, k.st_sc.p + (par ^ 1) * S_COUNT, k.st_fl.p + par * F_COUNT,
+                      k.st_fl.p + (par ^ 1) * F_COUNT, pd, e1, ST_CG_PQ, 1};
+          const int e2 = ++P.red_epoch;
+          k_cg_update_pf<<<VEC_GRID, VEC_BLOCK, 0, s>>>(c1, k.p.p, k.q.p, k.minv.p, x, k.r.p, i0, i1, k.partial.p, k.ticket.p,
+                                                        k.scratch.p, e2);
+          TR(3);
+          par ^= 1;
+          StageCtx c2{k.st_sc.p + par * S_COUNT, k.st_sc.p + (par ^ 1) * S_COUNT, k.st_fl.p + par * F_COUNT,
+                      k.st_fl.p + (par ^ 1) * F_COUNT, pd, e2, ST_CG_UPDATE, 2};
+          he = ++P.halo_epoch;
+          const int64_t off = k.p.p - P.vec_base;
+          double *lo = pl->rank_lo >= 0 ? P.peer_vec[0] + off + P.peer_lo_f1 : nullptr;
+          double *hi = pl->rank_hi >= 0 ? P.peer_vec[1] + off : nullptr;
+          k_cg_p_pf<<<VEC_GRID, VEC_BLOCK, 0, s>>>(c2, k.r.p, k.minv.p, k.p.p, i0, i1, pl->send_lo, pl->send_hi, lo, hi,
+                                                   P.peer_hflag[0], P.peer_hflag[1], he, k.ticket.p + 1);
+          TR(5);
+          par ^= 1;
+          pl->stats.kernel_launches += 3;
+        }
+      } else if (!bi) {
         APDX_CHECK(exchange_halo(pl, k.p.p, &he));
+        TR(0);
         APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, ST_CG_PQ, 1, he));
+        TR(1);
         APDX_CHECK(finish_stage(pl, ST_CG_PQ, 1));
+        TR(2);
         k_cg_update<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.p.p, k.q.p, k.minv.p, x, k.r.p, i0, i1, k.partial.p,
                                                    k.ticket.p, k.scal.p, k.flags.p, fused, pd, next_red_epoch(pl));
+        TR(3);
         APDX_CHECK(finish_stage(pl, ST_CG_UPDATE, 2));
+        TR(4);
         k_cg_p<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.minv.p, k.p.p, i0, i1, k.scal.p, k.flags.p);
+        TR(5);
         pl->stats.kernel_launches += 2;
       } else {
         k_bi_p<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.q.p, k.minv.p, k.p.p, k.phat.p, i0, i1, k.scal.p, k.flags.p);
@@ -605,8 +859,53 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
         APDX_CHECK(finish_stage(pl, ST_BI_X, 2));
         pl->stats.kernel_launches += 3;
       }
+      return APDX_OK;
+    };
+    // CUDA graph of one chunk of iterations: the loop is launch-bound for small systems and at high GPU counts.
+    // Kernels turn into no-ops once the device-side done flag is set, so replaying a whole chunk is always safe.
+    const int mode_id = cg2 ? 1 : (c.multi ? 2 : 0);
+    const bool graph_ok = graphs_on && !tracing && !c.p2p && todo == chunk;
+    KrylovGraph &G = pl->kgraph[bi ? 1 : 0];
+    if (graph_ok && G.exec && G.rhs == rhs && G.x == x && G.mode == mode_id && G.chunk == chunk && G.i0 == i0 && G.i1 == i1) {
+      APDX_CUDA(cudaGraphLaunch(G.exec, s));
+      pl->stats.kernel_launches += G.kernel_launches;
+      pl->stats.spmv_launches += G.spmv_launches;
+    } else if (graph_ok) {
+      if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+      const double k0 = pl->stats.kernel_launches, s0 = pl->stats.spmv_launches;
+      APDX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int rc = APDX_OK;
+      for (int it = 0; it < todo && rc == APDX_OK; ++it) rc = one_iteration();
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc != APDX_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      APDX_REQUIRE(ce == cudaSuccess && graph, APDX_ERR_CUDA, "stream capture of the Krylov chunk failed: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&G.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      APDX_REQUIRE(ce == cudaSuccess, APDX_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+      G.rhs = rhs; G.x = x; G.mode = mode_id; G.chunk = chunk; G.i0 = i0; G.i1 = i1;
+      G.kernel_launches = pl->stats.kernel_launches - k0;
+      G.spmv_launches = pl->stats.spmv_launches - s0;
+      APDX_CUDA(cudaGraphLaunch(G.exec, s));
+    } else {
+      for (int it = 0; it < todo; ++it) APDX_CHECK(one_iteration());
     }
     launched += todo;
+    if (tracing) {
+      APDX_CUDA(cudaStreamSynchronize(s));
+      double sum[6] = {0, 0, 0, 0, 0, 0};
+      for (size_t t = 1; t < trace.size(); ++t) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, trace[t - 1].first, trace[t].first);
+        if (trace[t].second >= 0) sum[trace[t].second] += ms;
+      }
+      const char *nm[6] = {"halo", "spmv", "stage_pq", "update", "stage_upd", "p_update"};
+      fprintf(stderr, "[apdx trace] us/iteration over %d iterations:", todo);
+      for (int l = 0; l < 6; ++l) fprintf(stderr, " %s %.1f", nm[l], 1e3 * sum[l] / todo);
+      fprintf(stderr, "\n");
+      for (auto &t : trace) cudaEventDestroy(t.first);
+      trace.clear();
+    }
   }
   APDX_CUDA(cudaGetLastError());
   if (c.p2p) {

@@ -84,14 +84,19 @@ class ClockSampler:
 
 
 # ---- workload ------------------------------------------------------------------------------------------
+NX_OVERRIDE = [0]   # diagnostic: elements along i (slowest index) if different from m
+
+
 def local_poisson_mesh(m, rank, nranks):
     """Slab [rank] of the m^3 brick mesh of the unit cube, nodes in global order (local id = global - node_lo)."""
     from autopdex_b200 import mesher
-    part = mesher.slab_partition((m, m, m), rank, nranks)
+    mx = NX_OVERRIDE[0] or m
+    part = mesher.slab_partition((mx, m, m), rank, nranks)
     g0, g1 = part["plane_lo"], part["plane_hi"]
     lin = np.linspace(-1.0, 1.0, m + 1)
+    lin_x = np.linspace(-1.0, 1.0, mx + 1)
     v = np.asarray(UNIT_CUBE)
-    S, T, U = np.meshgrid(lin[g0:g1], lin, lin, indexing="ij")
+    S, T, U = np.meshgrid(lin_x[g0:g1], lin, lin, indexing="ij")
     s, t, u = S.reshape(-1, 1), T.reshape(-1, 1), U.reshape(-1, 1)
     coords = ((1 - s) * (1 - t) * (1 - u) * v[0] + (1 + s) * (1 - t) * (1 - u) * v[1] + (1 + s) * (1 + t) * (1 - u) * v[2]
               + (1 - s) * (1 + t) * (1 - u) * v[3] + (1 - s) * (1 - t) * (1 + u) * v[4] + (1 + s) * (1 - t) * (1 + u) * v[5]
@@ -107,7 +112,7 @@ def local_poisson_mesh(m, rank, nranks):
     mask = np.zeros(coords.shape[0], dtype=bool)
     for d in range(3):
         mask |= (np.abs(coords[:, d]) < tol) | (np.abs(coords[:, d] - 1.0) < tol)
-    owned_elems = (min(part["owned_plane_hi"], m) - part["owned_plane_lo"]) * m * m  # elements attributed to this rank
+    owned_elems = (min(part["owned_plane_hi"], mx) - part["owned_plane_lo"]) * m * m  # elements attributed to this rank
     return part, coords, elems, mask, owned_elems
 
 
@@ -216,7 +221,7 @@ def run_b200(args):
     t_mesh = time.perf_counter() - t_mesh
     n_local = settings["node coordinates"].shape[0]
     dofs0 = np.zeros((n_local, 1))
-    total_elems = m ** 3
+    total_elems = (NX_OVERRIDE[0] or m) * m * m
 
     def barrier():
         backend.comm_allreduce_host(np.zeros(1))
@@ -335,7 +340,9 @@ def main():
     ap.add_argument("--ref-size", type=int, default=32, help="elements per direction of the bounded CPU sample")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nx", type=int, default=0, help="diagnostic: elements along the slowest index (default: --size)")
     args = ap.parse_args()
+    NX_OVERRIDE[0] = args.nx
     if args.impl == "reference":
         run_reference(args)
     else:

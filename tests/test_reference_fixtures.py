@@ -129,3 +129,87 @@ def test_newton_loop_semantics_against_reference_damped_newton():
         ref = FIX[name]
         assert it == int(ref[0]) and div == bool(ref[2]), name
         assert (np.isnan(rn) and np.isnan(ref[1])) or np.isclose(rn, ref[1]), name
+
+
+# ---- 'user element' sets executed by the reference's assembler (numerical AD in the generator) -------------------
+def _element_problem(tag):
+    from oracle import mesher as om
+    from oracle import quadrature as oq
+    cube2 = [[0, 0, 0], [1, 0, 0], [1.1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1.2], [1, 1, 1], [0, 1, 1]]
+    mat = dict(youngs_modulus=100.0, poisson_ratio=0.3)
+    if tag == "cook_q9":
+        sets = [dict(kind="domain", etype="quad9", conn=problems.COOK_ELEMS[[2, 4]], nf=2, gp=oq.gauss_legendre_nd(2, 4),
+                     model=dict(name="neo_hooke", mode="plain strain", **mat)),
+                dict(kind="surface", etype="line3", conn=problems.COOK_SURF[[4, 5]], nf=2, gp=oq.gauss_legendre_nd(1, 4),
+                     model=dict(name="neumann", traction=np.array([0.0, 4.0])))]
+        return sets, problems.COOK_NODES, 2
+    if tag == "hex8_neo":
+        c, e = om.structured_mesh((1, 1, 2), cube2, "brick")
+        sets = [dict(kind="domain", etype="hex8", conn=e, nf=3, gp=oq.gauss_legendre_nd(3, 2),
+                     model=dict(name="neo_hooke", mode="3d", **mat)),
+                dict(kind="surface", etype="quad4", conn=np.array([[2, 8, 11, 5]]), nf=3, gp=oq.gauss_legendre_nd(2, 2),
+                     model=dict(name="neumann", traction=np.array([0.0, 0.5, -4.0])))]
+        return sets, c, 3
+    if tag in ("linel_plain_strain", "linel_plain_stress"):
+        c, e = om.structured_mesh((2, 1), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "quad")
+        mode = tag[6:].replace("_", " ")
+        return [dict(kind="domain", etype="quad4", conn=e, nf=2, gp=oq.gauss_legendre_nd(2, 2),
+                     model=dict(name="linear_elasticity", mode=mode, body_load=np.array([0.3, -1.0]), **mat))], c, 2
+    if tag == "linel_3d":
+        c, e = om.structured_mesh((1, 1, 2), cube2, "brick")
+        return [dict(kind="domain", etype="hex8", conn=e[:1], nf=3, gp=oq.gauss_legendre_nd(3, 2),
+                     model=dict(name="linear_elasticity", mode="3d", body_load=np.array([0.3, -1.0, 0.2]), **mat))], c, 3
+    if tag == "tri6_neo":
+        c, e = om.structured_mesh((1, 1), [[0, 0], [2, 0], [2.3, 1.0], [0, 1]], "tri")
+        c, e = om.elevate_triangles(c, e)
+        gp = (FIX["tri_rule_2_x"], FIX["tri_rule_2_w"])
+        return [dict(kind="domain", etype="tri6", conn=e, nf=2, gp=gp,
+                     model=dict(name="neo_hooke", mode="plain strain", **mat))], c, 2
+    raise KeyError(tag)
+
+
+ELEMENT_TAGS = ["cook_q9", "hex8_neo", "linel_plain_strain", "linel_plain_stress", "linel_3d", "tri6_neo"]
+
+
+@pytest.mark.parametrize("tag", ELEMENT_TAGS)
+def test_user_elements_against_reference_run(tag):
+    if tag + "_R" not in FIX:
+        pytest.skip("fixture %s not generated yet" % tag)
+    sets, coords, nf = _element_problem(tag)
+    dofs = FIX[tag + "_dofs"]
+    R, data = oasm.assemble(sets, coords, dofs, {})
+    rows, cols = oasm.coo_indices(sets)
+    assert np.array_equal(rows, FIX[tag + "_K_rows"]) and np.array_equal(cols, FIX[tag + "_K_cols"])
+    assert rel(R, FIX[tag + "_R"].ravel()) < 1e-11
+    assert rel(data, FIX[tag + "_K_data"]) < TANGENT_RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ELEMENT_TAGS + ["readme3", "readme5"])
+def test_gpu_against_reference_run(tag):
+    """The CUDA path against the reference's own outputs (no oracle in between)."""
+    if tag + "_R" not in FIX:
+        pytest.skip("fixture %s not generated yet" % tag)
+    from autopdex_b200 import backend
+    from tests import gpu_util
+    if tag.startswith("readme"):
+        p = problems.readme_poisson(int(tag[6:]))
+        sets, coords, nf, mask = p["sets"], p["coords"], 1, p["mask"]
+    else:
+        sets, coords, nf = _element_problem(tag)
+        mask = np.zeros((coords.shape[0], nf), dtype=bool)
+        mask[0] = True                       # any mask: the full-CSR values do not depend on it
+    p = dict(sets=sets, coords=coords, mask=mask, values=np.zeros(mask.shape), nf=nf)
+    plan = gpu_util.make_plan(p)
+    dofs = FIX[tag + "_dofs"].reshape(mask.shape)
+    d, r = backend.DeviceArray.from_host(dofs), backend.DeviceArray(mask.size)
+    plan.assemble(d, True, r)
+    n = mask.size
+    import scipy.sparse as sp
+    ref = sp.csr_matrix(sp.coo_matrix((FIX[tag + "_K_data"], (FIX[tag + "_K_rows"], FIX[tag + "_K_cols"])), shape=(n, n)))
+    ref.sort_indices()
+    indptr, indices = plan.csr(False)
+    assert np.array_equal(indptr, ref.indptr) and np.array_equal(indices, ref.indices)
+    assert rel(plan.values(False), ref.data) < TANGENT_RTOL
+    assert rel(r.download(), FIX[tag + "_R"].ravel()) < 1e-11
+    plan.destroy()
