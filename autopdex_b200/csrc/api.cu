@@ -233,8 +233,8 @@ static int validate_set(const apdx_set_desc &d, int dim, int nf, int idx) {
     if (d.kind == APDX_SET_SURFACE)
       APDX_REQUIRE(d.model == APDX_MODEL_NEUMANN, APDX_ERR_UNSUPPORTED, "set %d: surface elements support neumann_weak only", idx);
     if (d.kind == APDX_SET_DOMAIN)
-      APDX_REQUIRE(d.model != APDX_MODEL_CAPACITY && d.model != APDX_MODEL_NEUMANN, APDX_ERR_UNSUPPORTED,
-                   "set %d: this weak form is only available in 'sparse' / surface sets", idx);
+      APDX_REQUIRE(d.model != APDX_MODEL_NEUMANN, APDX_ERR_UNSUPPORTED,
+                   "set %d: neumann_weak is only available in 'sparse' / surface sets", idx);
   }
   return APDX_OK;
 }

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) k_sell_build(const int32_t *__restrict__ 
       int32_t w = offset_mode ? wu : wmax;
       sl_w[s] = w | (offset_mode ? (int32_t)0x80000000 : 0);
       sz_val[s] = w * SELL_C;
-      sz_idx[s] = offset_mode ? w : w * SELL_C;
+      sz_idx[s] = offset_mode ? ((w + 1) & ~1) : w * SELL_C;  // even: explicit slices read their columns as int2
     }
     return;
   }

@@ -125,8 +125,10 @@ def isoparametric_domain_element_galerkin(weak_form_fun, ansatz_fun, ref_int_coo
     if not initial_config:
         _unsupported("initial_config=False (updated-Lagrangian mapping)")
     weak = recognise_weak_form(weak_form_fun)
-    if weak.name in ("neumann", "capacity", "poisson_potential"):
+    if weak.name in ("neumann", "poisson_potential"):
         _unsupported("weak form %s inside a domain user element" % weak.name)
+    # 'capacity' (forward_backward_euler_weak) inside an isoparametric element is an extension of the b200 backend:
+    # the reference evaluates it through solution_structure, i.e. in 'sparse' mode only (models.py:1996-1998)
     return ElementModel("domain", weak, _family(ansatz_fun), (ref_int_coor, ref_int_weights))
 
 
