@@ -149,6 +149,7 @@ struct KrylovGraph {
 struct Sell {
   bool built = false;
   int64_t row0 = 0, n_rows = 0, n_slices = 0, n_val = 0, n_idx = 0;
+  int nf = 1;                 // slices interleave the nf dofs per node (sell.cu)
   DevBuf<int32_t> sl_w;       // [n_slices] width | (offset mode ? 1<<31 : 0)
   DevBuf<int64_t> valptr;     // [n_slices+1] start of the slice's value block (doubles)
   DevBuf<int64_t> idxptr;     // [n_slices+1] start of the slice's index block (int32)

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restri
                                                          const int64_t *__restrict__ idxptr, const double *__restrict__ val,
                                                          const int32_t *__restrict__ idx, const double *__restrict__ x,
                                                          double *__restrict__ y, const double *__restrict__ w,
-                                                         int64_t row0, int64_t row1, int64_t n_slices, int32_t n_cols,
+                                                         int64_t row0, int64_t row1, int64_t n_slices, int32_t n_cols, int nf,
                                                          double *partial, unsigned int *ticket, double *sc, int32_t *fl,
                                                          int stage, int fused, int check_done, const P2PDev *pd, int epoch,
                                                          int halo_epoch) {
@@ -267,17 +267,19 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restri
     const int32_t wenc = sl_w[s];
     const int32_t W = wenc & 0x7fffffff;
     const double2 *vp = reinterpret_cast<const double2 *>(val + valptr[s]) + lane;
-    const int64_t r0 = row0 + s * 64 + 2 * lane;
+    // rows of the slice: one field component of 64 consecutive nodes (sell.cu), two rows per lane
+    const int64_t r0 = row0 + (s / nf) * (int64_t)64 * nf + (s % nf) + (int64_t)nf * (2 * lane);
+    const int64_t r1 = r0 + nf;
     double a0 = 0.0, a1 = 0.0;
     if (wenc < 0) {
       const int32_t *op = idx + idxptr[s];
-      const int32_t rr = (int32_t)r0;
+      const int32_t rr0 = (int32_t)r0, rr1 = (int32_t)r1;
 #pragma unroll 4
       for (int32_t j = 0; j < W; ++j) {
-        const int32_t off = __ldg(op + j);
+        const int32_t off = __ldg(op + j);             // same address in every lane: one broadcast transaction
         const double2 v = __ldcs(vp + (size_t)j * 32);
-        int32_t c0 = min(max(rr + off, 0), n_cols - 1);
-        int32_t c1 = min(max(rr + 1 + off, 0), n_cols - 1);
+        const int32_t c0 = min(max(rr0 + off, 0), n_cols - 1);
+        const int32_t c1 = min(max(rr1 + off, 0), n_cols - 1);
         a0 += v.x * __ldg(x + c0);
         a1 += v.y * __ldg(x + c1);
       }
@@ -296,9 +298,9 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restri
       if (NDOT >= 1) acc[0] += w[r0] * a0;
       if (NDOT >= 2) acc[1] += a0 * a0;
     }
-    if (r0 + 1 < row1) {
-      y[r0 + 1] = a1;
-      if (NDOT >= 1) acc[0] += w[r0 + 1] * a1;
+    if (r1 < row1) {
+      y[r1] = a1;
+      if (NDOT >= 1) acc[0] += w[r1] * a1;
       if (NDOT >= 2) acc[1] += a1 * a1;
     }
   }
@@ -549,11 +551,12 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_bi_x(const double *__restrict__ p
 
 // minv over the owned rows [row0, row0+n): 1/diag read from the sliced-ELL values (solver.py:1095)
 __global__ void k_jacobi_inv(const double *__restrict__ sell_val, const int64_t *__restrict__ valptr,
-                             const int32_t *__restrict__ diag, int64_t row0, int64_t n, int jacobi,
+                             const int32_t *__restrict__ diag, int64_t row0, int64_t n, int nf, int jacobi,
                              double *__restrict__ minv) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  minv[row0 + i] = (jacobi && diag[i] >= 0) ? 1.0 / sell_val[valptr[i >> 6] + diag[i]] : 1.0;
+  const int64_t slice = (i / (64 * nf)) * nf + (i % nf);   // slices interleave the nf components (sell.cu)
+  minv[row0 + i] = (jacobi && diag[i] >= 0) ? 1.0 / sell_val[valptr[slice] + diag[i]] : 1.0;
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -625,7 +628,7 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
   unsigned grid = (unsigned)(nb < cap ? (nb > 0 ? nb : 1) : cap);
   const int epoch = (NDOT > 0 && c.p2p && stage >= 0) ? ++pl->p2p.red_epoch : 0;
   k_spmv_sell<NDOT><<<grid, VEC_BLOCK, 0, pl->stream>>>(S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w,
-                                                        pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, k.partial.p,
+                                                        pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, S.nf, k.partial.p,
                                                         k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,
                                                         (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr),
                                                         epoch, halo_epoch);
@@ -686,7 +689,7 @@ int time_spmv(apdx_plan *pl, int reps, double *ms_avg) {
   cudaStream_t s = pl->stream;
   // a smooth non-trivial input vector: p = 1/diag on the owned rows
   k_jacobi_inv<<<(unsigned)((pl->sell.n_rows + 255) / 256), 256, 0, s>>>(pl->sell.val.p, pl->sell.valptr.p, pl->sell.diag.p,
-                                                                      pl->f0, pl->sell.n_rows, 1, k.p.p);
+                                                                      pl->f0, pl->sell.n_rows, pl->sell.nf, 1, k.p.p);
   for (int i = 0; i < 3; ++i) APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, -1, 0));
   APDX_CUDA(cudaEventRecord(pl->ev[0], s));
   for (int i = 0; i < reps; ++i) APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, -1, 0));
@@ -716,7 +719,7 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
   const int chunk = o->check_every > 0 ? o->check_every : 32;
 
   k_jacobi_inv<<<(unsigned)((pl->sell.n_rows + 255) / 256), 256, 0, s>>>(pl->sell.val.p, pl->sell.valptr.p, pl->sell.diag.p,
-                                                                      pl->f0, pl->sell.n_rows, o->jacobi, k.minv.p);
+                                                                      pl->f0, pl->sell.n_rows, pl->sell.nf, o->jacobi, k.minv.p);
   double sc_h[S_COUNT] = {0};
   sc_h[S_TOL2] = o->rtol * o->rtol;
   sc_h[S_SS] = o->atol * o->atol;
@@ -805,7 +808,7 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
           unsigned grid = (unsigned)(nb < 148ll * 32 ? (nb > 0 ? nb : 1) : 148ll * 32);
           const int e1 = ++P.red_epoch;
           k_spmv_sell<1><<<grid, VEC_BLOCK, 0, s>>>(S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p,
-                                                    pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, k.partial.p, k.ticket.p,
+                                                    pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, S.nf, k.partial.p, k.ticket.p,
                                                     k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he);
           TR(1);
           pl->stats.spmv_launches += 1;

@@ -31,12 +31,15 @@ __device__ __forceinline__ int32_t warp_max(int32_t v) {
 }
 
 // One warp per slice.  pass 0: count (width, mode, sizes).  pass 1: fill indices / sources / diagonal.
-// Rows of the slice: row0 + 64*s + 2*lane + h, h in {0,1}.  A row's CSR columns ascend, hence so do
-// its offsets col - row: the union over the slice is produced by repeated warp-wide min extraction.
+// Slices interleave the nf dofs of a node: slice s = b*nf + c holds the 64 rows row0 + b*64*nf + c + nf*k,
+// k = 0..63 (k = 2*lane + h), i.e. rows of ONE field component -- for vector problems the offsets col - row
+// of such rows coincide (3 dn + (c' - c)), which keeps elasticity matrices in offset mode.  nf = 1 gives
+// 64 consecutive rows.  A row's CSR columns ascend, hence so do its offsets: the union over the slice is
+// produced by repeated warp-wide min extraction.
 template <int PASS>
 __global__ void __launch_bounds__(256) k_sell_build(const int32_t *__restrict__ rp, const int32_t *__restrict__ col,
                                                     const int32_t *__restrict__ red2full, int64_t row0, int64_t row1,
-                                                    int64_t n_slices, int32_t *__restrict__ sl_w,
+                                                    int64_t n_slices, int nf, int32_t *__restrict__ sl_w,
                                                     int32_t *__restrict__ sz_val, int32_t *__restrict__ sz_idx,
                                                     const int64_t *__restrict__ valptr, const int64_t *__restrict__ idxptr,
                                                     int32_t *__restrict__ sell_idx, int32_t *__restrict__ sell_src,
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(256) k_sell_build(const int32_t *__restrict__ 
   int32_t b[2], e[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    r[h] = row0 + s * SELL_C + 2 * lane + h;
+    r[h] = row0 + (s / nf) * (int64_t)SELL_C * nf + (s % nf) + (int64_t)nf * (2 * lane + h);
     if (r[h] < row1) { b[h] = rp[r[h]]; e[h] = rp[r[h] + 1]; } else { b[h] = e[h] = 0; }
   }
   const int32_t wmax = warp_max(max(e[0] - b[0], e[1] - b[1]));
@@ -148,7 +151,8 @@ int sell_build(apdx_plan *pl) {
   const int64_t rows = pl->f1 - pl->f0;
   S.row0 = pl->f0;
   S.n_rows = rows;
-  S.n_slices = (rows + SELL_C - 1) / SELL_C;
+  S.nf = pl->nf;
+  S.n_slices = ((rows + (int64_t)SELL_C * S.nf - 1) / ((int64_t)SELL_C * S.nf)) * S.nf;
   const int64_t ns = S.n_slices;
   APDX_CHECK(S.sl_w.alloc(ns));
   APDX_CHECK(S.valptr.alloc(ns + 1));
@@ -161,7 +165,7 @@ int sell_build(apdx_plan *pl) {
   APDX_CUDA(cudaMemsetAsync(szv.p, 0, (ns + 1) * sizeof(int32_t), s));
   APDX_CUDA(cudaMemsetAsync(szi.p, 0, (ns + 1) * sizeof(int32_t), s));
   const unsigned grid = (unsigned)((ns * 32 + 255) / 256);
-  k_sell_build<0><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, pl->f0, pl->f1, ns, S.sl_w.p,
+  k_sell_build<0><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, pl->f0, pl->f1, ns, S.nf, S.sl_w.p,
                                        szv.p, szi.p, nullptr, nullptr, nullptr, nullptr, nullptr);
   APDX_CHECK(scan64(szv.p, S.valptr.p, ns + 1, s));
   APDX_CHECK(scan64(szi.p, S.idxptr.p, ns + 1, s));
@@ -174,7 +178,7 @@ int sell_build(apdx_plan *pl) {
   APDX_CHECK(S.val.alloc(S.n_val > 0 ? S.n_val : 1));
   APDX_CHECK(S.src.alloc(S.n_val > 0 ? S.n_val : 1));
   APDX_CHECK(S.idx.alloc(S.n_idx > 0 ? S.n_idx : 1));
-  k_sell_build<1><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, pl->f0, pl->f1, ns, S.sl_w.p,
+  k_sell_build<1><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, pl->f0, pl->f1, ns, S.nf, S.sl_w.p,
                                        nullptr, nullptr, S.valptr.p, S.idxptr.p, S.idx.p, S.src.p, S.diag.p);
   APDX_CUDA(cudaStreamSynchronize(s));
   APDX_CUDA(cudaGetLastError());
