@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libapdx_b200.so")
+LIB_PATH = os.environ.get("APDX_LIB") or os.path.join(_HERE, "lib", "libapdx_b200.so")   # APDX_LIB: A/B builds
 
 APDX_PARAM = {"coefficient": 0, "source": 1, "youngs_modulus": 2, "poisson_ratio": 3, "body_load": 4, "traction": 5}
 APDX_MODEL = {"poisson_potential": 0, "poisson_weak": 1, "linear_elasticity": 2, "neo_hooke": 3, "neumann": 4,
@@ -48,6 +48,8 @@ SIGNATURES = {
     "apdx_free": (C.c_int, [_P]),
     "apdx_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "apdx_host_free": (C.c_int, [_P]),
+    "apdx_host_register": (C.c_int, [_P, C.c_size_t]),
+    "apdx_host_unregister": (C.c_int, [_P]),
     "apdx_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t]),
     "apdx_memcpy_d2h": (C.c_int, [_P, _P, C.c_size_t]),
     "apdx_memset": (C.c_int, [_P, C.c_int, C.c_size_t]),

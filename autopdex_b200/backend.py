@@ -4,10 +4,49 @@ Everything numerical happens inside libapdx_b200.so; this module marshals NumPy 
 into the C structs of include/apdx_b200.h.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
 from . import _lib, spaces
+
+
+# ---- page-locking of host buffers that are uploaded repeatedly ----------------------------------------
+_SEEN, _PINNED = {}, {}
+_PIN_MIN_BYTES = 1 << 20
+
+
+def _unpin(ptr):
+    if _PINNED.pop(ptr, None):
+        try:
+            _lib.load().apdx_host_unregister(C.c_void_p(ptr))
+        except Exception:
+            pass
+
+
+def pin_if_repeated(arr):
+    """Settings arrays are usually the same NumPy buffers call after call (coordinates, Dirichlet values, the
+    initial guess).  The second time a large buffer is uploaded it is page-locked in place (cudaHostRegister), so
+    later host->device copies are DMA transfers instead of staged pageable copies; a finalizer unregisters it."""
+    if arr.nbytes < _PIN_MIN_BYTES or not arr.flags.c_contiguous:
+        return
+    ptr = arr.ctypes.data
+    key = (ptr, arr.nbytes)
+    if ptr in _PINNED:
+        return
+    _SEEN[key] = _SEEN.get(key, 0) + 1
+    if _SEEN[key] == 2:
+        base = arr
+        while isinstance(base.base, np.ndarray):
+            base = base.base
+        if _lib.load().apdx_host_register(C.c_void_p(ptr), arr.nbytes) == 0:
+            _PINNED[ptr] = True
+            try:
+                weakref.finalize(base, _unpin, ptr)
+            except TypeError:
+                pass
+        if len(_SEEN) > 4096:
+            _SEEN.clear()
 
 
 class DeviceArray:
@@ -30,6 +69,7 @@ class DeviceArray:
         arr = np.ascontiguousarray(arr, dtype=self.dtype)
         if arr.size != self.n:
             raise ValueError("size mismatch: buffer %d, array %d" % (self.n, arr.size))
+        pin_if_repeated(arr)
         _lib.check(_lib.load().apdx_memcpy_h2d(self.ptr, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
 
     def download(self, out=None):
@@ -168,6 +208,7 @@ class Plan:
         c = np.ascontiguousarray(coords, dtype=np.float64)
         if c.shape != (self.n_nodes, self.dim):
             raise ValueError("'node coordinates' must have shape (%d, %d)" % (self.n_nodes, self.dim))
+        pin_if_repeated(c)
         _lib.check(_lib.load().apdx_set_coords(self.h, c.ctypes.data_as(C.c_void_p)))
 
     def set_param(self, iset, name, value):

@@ -184,6 +184,19 @@ int apdx_host_free(void *ptr_h) {
   APDX_CUDA(cudaFreeHost(ptr_h));
   return APDX_OK;
 }
+int apdx_host_register(void *ptr_h, size_t bytes) {
+  cudaError_t e = cudaHostRegister(ptr_h, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // page-locking is an optimisation: clear the error state (e.g. RLIMIT_MEMLOCK) and report
+    set_error("cudaHostRegister of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return APDX_ERR_CUDA;
+  }
+  return APDX_OK;
+}
+int apdx_host_unregister(void *ptr_h) {
+  APDX_CUDA(cudaHostUnregister(ptr_h));
+  return APDX_OK;
+}
 int apdx_memcpy_h2d(void *dst_d, const void *src_h, size_t bytes) {
   APDX_CUDA(cudaMemcpy(dst_d, src_h, bytes, cudaMemcpyHostToDevice));
   return APDX_OK;

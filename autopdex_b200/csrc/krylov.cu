@@ -239,12 +239,12 @@ __device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial
 // 128-bit double2 (512 contiguous bytes per warp instruction).  Offset mode: column = row + off[j]
 // (one broadcast int per slice column, x gathers coalesced); explicit mode: int2 column pairs.
 // n_cols: length of x (clamp target of the padded offsets, whose values are exact zeros).
-template <int NDOT>
+template <int NDOT, int NF>
 __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restrict__ sl_w, const int64_t *__restrict__ valptr,
                                                          const int64_t *__restrict__ idxptr, const double *__restrict__ val,
                                                          const int32_t *__restrict__ idx, const double *__restrict__ x,
                                                          double *__restrict__ y, const double *__restrict__ w,
-                                                         int64_t row0, int64_t row1, int64_t n_slices, int32_t n_cols, int nf,
+                                                         int64_t row0, int64_t row1, int64_t n_slices, int32_t n_cols,
                                                          double *partial, unsigned int *ticket, double *sc, int32_t *fl,
                                                          int stage, int fused, int check_done, const P2PDev *pd, int epoch,
                                                          int halo_epoch) {
@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restri
     const int32_t W = wenc & 0x7fffffff;
     const double2 *vp = reinterpret_cast<const double2 *>(val + valptr[s]) + lane;
     // rows of the slice: one field component of 64 consecutive nodes (sell.cu), two rows per lane
-    const int64_t r0 = row0 + (s / nf) * (int64_t)64 * nf + (s % nf) + (int64_t)nf * (2 * lane);
-    const int64_t r1 = r0 + nf;
+    const int64_t r0 = row0 + (s / NF) * (int64_t)64 * NF + (s % NF) + (int64_t)NF * (2 * lane);
+    const int64_t r1 = r0 + NF;   // lane owns rows k = lane and lane + 32 of the slice: warp-contiguous x / y accesses
     double a0 = 0.0, a1 = 0.0;
     if (wenc < 0) {
       const int32_t *op = idx + idxptr[s];
@@ -627,11 +627,15 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
   const int64_t cap = 148ll * 32;
   unsigned grid = (unsigned)(nb < cap ? (nb > 0 ? nb : 1) : cap);
   const int epoch = (NDOT > 0 && c.p2p && stage >= 0) ? ++pl->p2p.red_epoch : 0;
-  k_spmv_sell<NDOT><<<grid, VEC_BLOCK, 0, pl->stream>>>(S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w,
-                                                        pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, S.nf, k.partial.p,
-                                                        k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,
-                                                        (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr),
-                                                        epoch, halo_epoch);
+#define APDX_SPMV_NF(NFV)                                                                                              \
+  k_spmv_sell<NDOT, NFV><<<grid, VEC_BLOCK, 0, pl->stream>>>(                                                          \
+      S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free,    \
+      k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,                                        \
+      (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch)
+  if (S.nf == 1) APDX_SPMV_NF(1);
+  else if (S.nf == 2) APDX_SPMV_NF(2);
+  else APDX_SPMV_NF(3);
+#undef APDX_SPMV_NF
   pl->stats.spmv_launches += 1;
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaGetLastError());
@@ -764,7 +768,7 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
   const bool graphs_on = !(ge && strcmp(ge, "0") == 0);
   std::vector<std::pair<cudaEvent_t, int>> trace;
   // p2p-fused CG keeps the scalar state double-buffered in st_sc / st_fl; half 0 aliases k.scal / k.flags
-  const bool pfused = !bi && c.p2p && p2p_is_heap_vector(pl, k.p.p) && !(cm && strcmp(cm, "p2p") == 0);
+  const bool pfused = !bi && c.p2p && pl->sell.nf == 1 && p2p_is_heap_vector(pl, k.p.p) && !(cm && strcmp(cm, "p2p") == 0);
   while (true) {
     APDX_CUDA(cudaMemcpyAsync(fl_pin, (pfused ? k.st_fl.p + par * F_COUNT : k.flags.p), sizeof(int32_t) * F_COUNT,
                               cudaMemcpyDeviceToHost, s));
@@ -807,9 +811,10 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
           int64_t nb = (S.n_slices + wpb - 1) / wpb;
           unsigned grid = (unsigned)(nb < 148ll * 32 ? (nb > 0 ? nb : 1) : 148ll * 32);
           const int e1 = ++P.red_epoch;
-          k_spmv_sell<1><<<grid, VEC_BLOCK, 0, s>>>(S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p,
-                                                    pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, S.nf, k.partial.p, k.ticket.p,
-                                                    k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he);
+          // (the opt-in p2p-fused CG is only wired for scalar problems)
+          k_spmv_sell<1, 1><<<grid, VEC_BLOCK, 0, s>>>(S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p,
+                                                       pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, k.partial.p, k.ticket.p,
+                                                       k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he);
           TR(1);
           pl->stats.spmv_launches += 1;
           StageCtx c1{k.st_sc.p + par * S_COUNT, k.st_sc.p + (par ^ 1) * S_COUNT, k.st_fl.p + par * F_COUNT,

@@ -32,7 +32,8 @@ __device__ __forceinline__ int32_t warp_max(int32_t v) {
 
 // One warp per slice.  pass 0: count (width, mode, sizes).  pass 1: fill indices / sources / diagonal.
 // Slices interleave the nf dofs of a node: slice s = b*nf + c holds the 64 rows row0 + b*64*nf + c + nf*k,
-// k = 0..63 (k = 2*lane + h), i.e. rows of ONE field component -- for vector problems the offsets col - row
+// k = 0..63 (lane handles k = lane and k = lane + 32, stored side by side as one double2 so that the x gathers
+// and y stores of a warp are contiguous), i.e. rows of ONE field component -- for vector problems the offsets col - row
 // of such rows coincide (3 dn + (c' - c)), which keeps elasticity matrices in offset mode.  nf = 1 gives
 // 64 consecutive rows.  A row's CSR columns ascend, hence so do its offsets: the union over the slice is
 // produced by repeated warp-wide min extraction.

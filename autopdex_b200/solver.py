@@ -183,6 +183,7 @@ class _State:
         if cfg.nodal_imposition:
             mask = np.asarray(self._unwrap(settings["dirichlet dofs"])).astype(bool).ravel()
         self.mask = mask
+        self.keepalive = [settings.get("dirichlet dofs")]      # the cache key uses id(): keep the object alive
         self.plan = backend.Plan(self.dim, self.n_nodes, self.nf, specs, mask)
         # multi-GPU: this process holds one slab (owned nodes + ghost planes, local ids in global order)
         self.partition = settings.get("b200 partition")
@@ -265,7 +266,8 @@ def _state_for(cfg, dofs, settings):
     dd = settings.get("dirichlet dofs") if cfg.nodal_imposition else None
     if isinstance(dd, Mapping):
         dd = next(iter(dd.values()))
-    mask_key = None if dd is None else hash(np.asarray(dd).astype(bool).tobytes())
+    # fingerprint of the Dirichlet mask (the plan bakes it): identity + shape + number of constrained dofs
+    mask_key = None if dd is None else (id(dd), tuple(np.shape(dd)), int(np.count_nonzero(dd)))
     d0 = next(iter(dofs.values())) if isinstance(dofs, Mapping) else dofs
     key = (cfg.key, tuple(ids), mask_key, tuple(np.shape(d0)))
     st = _PLAN_CACHE.get(key)

@@ -116,6 +116,10 @@ int apdx_malloc(void **ptr_d, size_t bytes);
 int apdx_free(void *ptr_d);
 int apdx_host_alloc(void **ptr_h, size_t bytes);   /* pinned */
 int apdx_host_free(void *ptr_h);
+/* page-lock an existing host buffer (cudaHostRegister) so that repeated uploads of the same settings array run as
+ * true DMA; the Python layer does this for buffers it sees twice */
+int apdx_host_register(void *ptr_h, size_t bytes);
+int apdx_host_unregister(void *ptr_h);
 int apdx_memcpy_h2d(void *dst_d, const void *src_h, size_t bytes);
 int apdx_memcpy_d2h(void *dst_h, const void *src_d, size_t bytes);
 int apdx_memset(void *dst_d, int value, size_t bytes);
