@@ -258,6 +258,7 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
   APDX_REQUIRE(dim == 2 || dim == 3, APDX_ERR_UNSUPPORTED, "dim %d not supported", dim);
   APDX_REQUIRE(nf == 1 || nf == dim, APDX_ERR_UNSUPPORTED, "nf=%d with dim=%d not supported", nf, dim);
   APDX_REQUIRE(n_nodes > 0 && n_sets > 0, APDX_ERR_INVALID, "empty problem");
+  APDX_REQUIRE(n_sets <= 16, APDX_ERR_UNSUPPORTED, "more than 16 connectivity sets per plan");
   APDX_REQUIRE(n_nodes * nf < (1ll << 31), APDX_ERR_UNSUPPORTED, "more than 2^31 dofs per plan: partition the mesh");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -288,6 +289,7 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
     SetData &st = pl->sets[i];
     st.d = sets[i];
     st.ndof_e = st.d.nen * nf;
+    st.soa = fast_kernel_applies(dim, nf, st.d);
     st.coo_offset = coo;
     st.res_offset = res;
     coo += st.d.n_rows * (int64_t)st.ndof_e * st.ndof_e;
@@ -478,8 +480,12 @@ int apdx_set_dofs_n(apdx_plan *pl, const double *dofs_n_h) {
 // ---- assembly / linear algebra ---------------------------------------------------------------------------
 int apdx_assemble(apdx_plan *pl, const double *dofs_d, int want_tangent, double *residual_d) {
   APDX_REQUIRE(pl && dofs_d, APDX_ERR_INVALID, "NULL argument");
+  pl->stats = Stats();
+  APDX_CUDA(cudaEventRecord(pl->ev[0], pl->stream));
   APDX_CHECK(assemble_internal(pl, dofs_d, want_tangent ? 5 : 0, residual_d));
+  APDX_CUDA(cudaEventRecord(pl->ev[1], pl->stream));
   APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  (want_tangent ? pl->stats.asm_tangent_ms : pl->stats.asm_residual_ms) = elapsed(pl->ev[0], pl->ev[1]);
   return APDX_OK;
 }
 

@@ -93,6 +93,7 @@ struct SetData {
   int32_t ndof_e = 0;         // nen * nf
   int64_t coo_offset = 0;     // offset of this set's block in the COO / Ke stream
   int64_t res_offset = 0;     // offset of this set's block in the Re stream
+  bool soa = false;           // element streams stored entry-major (sets handled by the register kernels)
   DevBuf<int32_t> conn;       // [n_rows][nen]
   DevBuf<double> shape_n, shape_dn, gp_w;
   std::vector<double> h_shape_n, h_shape_dn, h_gp_w;  // host copies (kernel-argument tables of the fast kernels)
@@ -226,6 +227,8 @@ struct apdx_plan {
 namespace apdx {
 // pattern.cu
 int build_pattern(apdx_plan *pl, const uint8_t *mask_h);
+// elements_fast.cu
+bool fast_kernel_applies(int dim, int nf, const apdx_set_desc &d);
 // elements.cu
 int launch_element_kernels(apdx_plan *pl, const double *dofs_d, bool want_tangent);
 int launch_gather_reduce(apdx_plan *pl, int tangent_flags, double *residual_d);

@@ -5,8 +5,8 @@
 // gathered straight into registers, the shape tables live in the kernel-argument constant bank
 // (so dN/dxi and the weights are immediate operands of the DFMAs), the symmetric element tangent
 // (NEN(NEN+1)/2 accumulators) and the residual stay in registers over the fully unrolled Gauss
-// loop, and the results leave through a per-warp shared-memory transpose so that every global
-// store instruction writes 256 contiguous bytes.  Same closed forms as the generic kernel
+// loop, and the results are stored entry-major (ke[ij][element]) so that every global store
+// instruction of a warp writes 256 contiguous bytes.  Same closed forms as the generic kernel
 // (elements.cu), same reference citations: models.py:96-134 (poisson_weak), the README potential,
 // signed w*det J of models.py:1691-1694, 1257-1261.
 #include "elements.cuh"
@@ -36,11 +36,6 @@ constexpr int FAST_BLOCK = 128;
 template <int DIM, int NEN, int NGP, bool TANGENT>
 __global__ void __launch_bounds__(FAST_BLOCK) k_elem_scalar_reg(const __grid_constant__ FastArgs<DIM, NEN, NGP> A) {
   constexpr int NSYM = NEN * (NEN + 1) / 2;
-  constexpr int NOUT = TANGENT ? NEN * NEN : NEN;   // doubles per element leaving through the transpose
-  constexpr int STRIDE = NOUT + 1;                  // odd stride: conflict-free 8-byte shared accesses
-  extern __shared__ double sm[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double *buf = sm + (size_t)wid * 32 * STRIDE;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < A.n_rows;
   const int64_t ec = active ? e : A.n_rows - 1;
@@ -119,45 +114,19 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_elem_scalar_reg(const __grid_con
     }
   }
 
-  // ---- per-warp transpose: thread-major registers -> element-major, 256-byte coalesced stores ----
+  // ---- entry-major stores: ke[ij][e], re[i][e]: consecutive threads (elements) write consecutive addresses ----
+  if (!active) return;
   if constexpr (TANGENT) {
 #pragma unroll
     for (int a = 0; a < NEN; ++a)
 #pragma unroll
       for (int b = 0; b < NEN; ++b) {
         const int lo = a < b ? a : b, hi = a < b ? b : a;
-        buf[lane * STRIDE + a * NEN + b] = K[lo * NEN - lo * (lo - 1) / 2 + (hi - lo)];
+        A.ke[(int64_t)(a * NEN + b) * A.n_rows + e] = K[lo * NEN - lo * (lo - 1) / 2 + (hi - lo)];
       }
-  } else {
+  }
 #pragma unroll
-    for (int a = 0; a < NEN; ++a) buf[lane * STRIDE + a] = R[a];
-  }
-  __syncwarp();
-  const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + wid * 32;
-  const int nact = (int)min((int64_t)32, A.n_rows - e0);
-  if (nact > 0) {
-    double *out = (TANGENT ? A.ke : A.re) + e0 * NOUT;
-    const int total = nact * NOUT;
-    for (int i = lane; i < total; i += 32) {
-      const int r = i / NOUT, cidx = i - r * NOUT;
-      out[i] = buf[r * STRIDE + cidx];
-    }
-  }
-  if constexpr (TANGENT) {
-    // residual through the same buffer
-    __syncwarp();
-#pragma unroll
-    for (int a = 0; a < NEN; ++a) buf[lane * STRIDE + a] = R[a];
-    __syncwarp();
-    if (nact > 0) {
-      double *out = A.re + e0 * NEN;
-      const int total = nact * NEN;
-      for (int i = lane; i < total; i += 32) {
-        const int r = i / NEN, cidx = i - r * NEN;
-        out[i] = buf[r * STRIDE + cidx];
-      }
-    }
-  }
+  for (int a = 0; a < NEN; ++a) A.re[(int64_t)a * A.n_rows + e] = R[a];
 }
 
 template <int DIM, int NEN, int NGP>
@@ -171,23 +140,26 @@ static int launch_fast(apdx_plan *pl, SetData &st, const ElemArgs &a) {
   for (int i = 0; i < NGP * NEN * DIM; ++i) F.tab.dN[i] = st.h_shape_dn[i];
   for (int i = 0; i < NGP; ++i) F.tab.w[i] = st.h_gp_w[i];
   const unsigned grid = (unsigned)((a.n_rows + FAST_BLOCK - 1) / FAST_BLOCK);
-  if (a.want_tangent) {
-    const size_t smem = (size_t)(FAST_BLOCK / 32) * 32 * (NEN * NEN + 1) * sizeof(double);
-    APDX_CUDA(cudaFuncSetAttribute(k_elem_scalar_reg<DIM, NEN, NGP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_elem_scalar_reg<DIM, NEN, NGP, true><<<grid, FAST_BLOCK, smem, pl->stream>>>(F);
-  } else {
-    const size_t smem = (size_t)(FAST_BLOCK / 32) * 32 * (NEN + 1) * sizeof(double);
-    k_elem_scalar_reg<DIM, NEN, NGP, false><<<grid, FAST_BLOCK, smem, pl->stream>>>(F);
-  }
+  if (a.want_tangent) k_elem_scalar_reg<DIM, NEN, NGP, true><<<grid, FAST_BLOCK, 0, pl->stream>>>(F);
+  else k_elem_scalar_reg<DIM, NEN, NGP, false><<<grid, FAST_BLOCK, 0, pl->stream>>>(F);
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaGetLastError());
   return APDX_OK;
 }
 
+// sets served by the register kernels store their element streams entry-major (see pattern.cu: k_to_soa)
+bool fast_kernel_applies(int dim, int nf, const apdx_set_desc &d) {
+  if (d.kind != APDX_SET_DOMAIN || nf != 1) return false;
+  if (d.model != APDX_MODEL_POISSON_WEAK && d.model != APDX_MODEL_POISSON_POTENTIAL) return false;
+  const int t[7][3] = {{3, 8, 8}, {2, 4, 4}, {3, 4, 1}, {3, 4, 4}, {2, 3, 1}, {2, 3, 3}, {2, 9, 9}};
+  for (auto &c : t)
+    if (dim == c[0] && d.nen == c[1] && d.n_gp == c[2]) return true;
+  return false;
+}
+
 int launch_fast_elements(apdx_plan *pl, SetData &st, const ElemArgs &a, bool *handled) {
   *handled = false;
-  if (a.kind != APDX_SET_DOMAIN || pl->nf != 1) return APDX_OK;
-  if (a.model != APDX_MODEL_POISSON_WEAK && a.model != APDX_MODEL_POISSON_POTENTIAL) return APDX_OK;
+  if (!st.soa) return APDX_OK;
   const int dim = pl->dim, nen = a.nen, ngp = a.n_gp;
 #define APDX_FAST(D, N, G)                                   \
   if (dim == D && nen == N && ngp == G) {                    \

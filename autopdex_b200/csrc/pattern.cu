@@ -43,6 +43,30 @@ __global__ void k_res_keys(const int32_t *__restrict__ conn, int64_t n_entries, 
   vals[offset + m] = (uint32_t)(offset + m);
 }
 
+// The element kernels store element matrices / vectors entry-major ("SoA": ke[set][ij][element]) so that both their
+// stores and the gathers of the segmented reduction are coalesced across consecutive elements.  The sort works on
+// reference-order COO indices k = e*nd2 + ij (needed for the element->CSR map); afterwards the gather lists are
+// rewritten to SoA addresses off + ij*n_rows + e.
+struct SoaSet {
+  int64_t off, n_rows;
+  int32_t width;   // ndof^2 (matrix stream) or ndof (vector stream)
+};
+struct SoaTable {
+  int n;
+  SoaSet s[16];
+};
+__global__ void k_to_soa(uint32_t *__restrict__ list, int64_t n, SoaTable t) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t k = list[i];
+  int q = 0;
+  while (q + 1 < t.n && k >= t.s[q + 1].off) ++q;
+  if (t.s[q].n_rows == 0) return;   // this set keeps the reference (element-major) layout
+  const int64_t local = k - t.s[q].off;
+  const int64_t e = local / t.s[q].width, ij = local - e * t.s[q].width;
+  list[i] = (uint32_t)(t.s[q].off + ij * t.s[q].n_rows + e);
+}
+
 template <typename K>
 __global__ void k_head_flags(const K *__restrict__ sorted, int64_t n, int32_t *__restrict__ flag) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,6 +244,12 @@ int build_pattern(apdx_plan *pl, const uint8_t *mask_h) {
     APDX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kin.p, kout.p, vin.p, pl->rperm.p, m, 0, eb, s));
     APDX_CHECK(pl->rseg_ptr.alloc(n + 1));
     k_res_fill<<<grid_for(m, B), B, 0, s>>>(kout.p, m, n, pl->rseg_ptr.p);
+    SoaTable t{};
+    for (auto &st : pl->sets) {
+      if (st.d.n_rows == 0) continue;
+      t.s[t.n++] = SoaSet{st.res_offset, st.soa ? st.d.n_rows : 0, st.ndof_e};
+    }
+    k_to_soa<<<grid_for(m, B), B, 0, s>>>(pl->rperm.p, m, t);
     APDX_CUDA(cudaStreamSynchronize(s));
   }
 
@@ -268,6 +298,12 @@ int build_pattern(apdx_plan *pl, const uint8_t *mask_h) {
     APDX_CUDA(cudaMemcpyAsync(pl->seg_ptr.p + pl->nnz, &nc32, sizeof(int32_t), cudaMemcpyHostToDevice, s));
     APDX_CHECK(pl->row_ptr.alloc(n + 1));
     k_row_ptr<<<grid_for(pl->nnz, B), B, 0, s>>>(sorted.p, pl->seg_ptr.p, pl->nnz, bits, n, pl->row_ptr.p);
+    SoaTable t{};
+    for (auto &st : pl->sets) {
+      if (st.d.n_rows == 0) continue;
+      t.s[t.n++] = SoaSet{st.coo_offset, st.soa ? st.d.n_rows : 0, st.ndof_e * st.ndof_e};
+    }
+    k_to_soa<<<grid_for(nc, B), B, 0, s>>>(pl->perm.p, nc, t);   // after k_unique_fill, which needs reference-order indices
     APDX_CUDA(cudaStreamSynchronize(s));
   }
   sorted.release();
