@@ -74,6 +74,7 @@ SIGNATURES = {
                               C.POINTER(_I32)]),
     "apdx_plan_stats": (C.c_int, [_P, C.POINTER(_D)]),
     "apdx_time_spmv": (C.c_int, [_P, _I32, C.POINTER(_D)]),
+    "apdx_measure_fp64_peak": (C.c_int, [C.POINTER(_D)]),
     "apdx_comm_allreduce_host": (C.c_int, [_P, _I32, _I32]),
     "apdx_comm_unique_id": (C.c_int, [_P]),
     "apdx_comm_init": (C.c_int, [_P, _I32, _I32]),

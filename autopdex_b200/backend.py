@@ -318,5 +318,11 @@ def comm_allreduce_host(values, op="sum"):
     return v
 
 
+def measure_fp64_peak():
+    tf = C.c_double(0.0)
+    _lib.check(_lib.load().apdx_measure_fp64_peak(C.byref(tf)))
+    return tf.value
+
+
 def set_device(index):
     _lib.check(_lib.load().apdx_set_device(int(index)))

@@ -86,6 +86,22 @@ __global__ void k_lower_bound(const int32_t *__restrict__ sorted, int64_t n, int
   *out = lo;
 }
 
+// FP64 peak probe: 16 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  const double b = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fma(a[i], b, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456) out[0] = s;   // keeps the chains alive
+}
+
 static inline unsigned g1(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 static int assemble_internal(apdx_plan *pl, const double *dofs_d, int tangent_flags, double *residual_d) {
@@ -519,6 +535,33 @@ int apdx_spmv(apdx_plan *pl, const double *x_d, double *y_d) {
 int apdx_time_spmv(apdx_plan *pl, int32_t reps, double *ms_avg) {
   APDX_REQUIRE(pl && ms_avg && reps > 0, APDX_ERR_INVALID, "bad argument");
   return time_spmv(pl, reps, ms_avg);
+}
+
+int apdx_measure_fp64_peak(double *tflops) {
+  APDX_REQUIRE(tflops, APDX_ERR_INVALID, "NULL argument");
+  double *d = nullptr;
+  APDX_CUDA(cudaMalloc((void **)&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  APDX_CUDA(cudaEventCreate(&e0));
+  APDX_CUDA(cudaEventCreate(&e1));
+  const int blocks = 148 * 8, iters = 20000;
+  k_fp64_peak<<<blocks, 256>>>(d, 1000);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    APDX_CUDA(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, 256>>>(d, iters);
+    APDX_CUDA(cudaEventRecord(e1));
+    APDX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 16.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return APDX_OK;
 }
 
 int apdx_krylov(apdx_plan *pl, const apdx_krylov_opts *opts, const double *rhs_d, double *x_d, int32_t *iters,

@@ -31,7 +31,9 @@ sys.path.insert(0, ROOT)
 
 UNIT_CUBE = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_spmv_sell<1> launch from `ncu --set full` (profiles/), by mesh size
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {256: 3.8625e9}     # profiles/r01c_k_spmv_sell_p256_full.txt: 3.750 GB read + 0.112 GB written
+# SASS count of k_elem_scalar_reg<3,8,8,true>: 2592 DFMA + 368 DMUL + 316 DADD per element
+HEX8_POISSON_FLOP = 2 * 2592 + 368 + 316
 METRIC = "elements/s through one Newton step (sparse assembly + Jacobi-PCG to 1e-8)"
 UNIT = "elements/s"
 
@@ -261,7 +263,7 @@ def run_b200(args):
             kry_ms.append(s["krylov_ms"]); iters.append(s["krylov_iters"]); launches += s["kernel_launches"]
     barrier()
     ms = float(backend.comm_allreduce_host([np.mean(step_ms)], "max")[0])
-    spmv_ms = plan.time_spmv(20)
+    spmv_ms = plan.time_spmv(50)
     spmv_ms = float(backend.comm_allreduce_host([spmv_ms], "max")[0])
     clocks = sampler.stop()
 
@@ -283,6 +285,8 @@ def run_b200(args):
     cg_gbs = cg_iter_bytes * mean_iters / (np.mean(kry_ms) * 1e-3) / 1e9
     asm_elems = state.plan.sets[0].conn.shape[0]
     asm_gbs = asm_elems * 290.0 / (np.mean(asm_ms) * 1e-3) / 1e9
+    fp64_peak = backend.measure_fp64_peak()                        # TFLOP/s, measured here (not in MEASURED_PEAKS.json)
+    asm_tflops = asm_elems * HEX8_POISSON_FLOP / (np.mean(asm_ms) * 1e-3) / 1e12
 
     if rank != 0:
         return
@@ -310,7 +314,10 @@ def run_b200(args):
         "newton_step_ms": ms,
         "assembly": {"elements_per_s": asm_elems / (np.mean(asm_ms) * 1e-3), "ms": float(np.mean(asm_ms)),
                      "residual_only_ms": float(np.mean(res_ms)), "algorithmic_gbs": asm_gbs,
-                     "frac_of_hbm": asm_gbs / hbm, "bytes_per_element": 290},
+                     "frac_of_hbm": asm_gbs / hbm, "bytes_per_element": 290,
+                     "flop_per_element": HEX8_POISSON_FLOP, "tflops_fp64": asm_tflops, "fp64_peak_measured_tflops": fp64_peak,
+                     "frac_of_fp64_peak": asm_tflops / fp64_peak,
+                     "note": "fused pass = element kernel (FP64-FMA bound) + deterministic segmented-reduction scatter (HBM bound)"},
         "cg": {"iterations": mean_iters, "ms_per_iteration": float(np.mean(kry_ms)) / max(mean_iters, 1),
                "algorithmic_gbs": cg_gbs, "frac_of_hbm": cg_gbs / hbm, "krylov_ms": float(np.mean(kry_ms))},
         "system": {"n_free": nfree, "nnz_reduced": nnz, "plan_device_gb": plan.device_bytes / 1e9},

@@ -188,6 +188,10 @@ int apdx_plan_stats(const apdx_plan *plan, double out[8]);
  * exactly as the CG loop launches it (fused p.Ap dot product included) */
 int apdx_time_spmv(apdx_plan *plan, int32_t reps, double *ms_avg);
 
+/* FP64 FMA peak of the current device (TFLOP/s), measured with a register-resident DFMA kernel and CUDA events:
+ * the denominator of the assembly kernels' FP64 roofline (MEASURED_PEAKS.json only holds bf16 and HBM figures) */
+int apdx_measure_fp64_peak(double *tflops);
+
 /* ---- multi-GPU (one process per GPU, slab partition) -------------------- *
  * Each rank builds a plan of its LOCAL mesh (owned nodes plus one ghost plane per side,
  * local ids in global order).  owned dofs are the contiguous range [begin,end) of local
