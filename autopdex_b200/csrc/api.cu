@@ -11,6 +11,16 @@
 namespace apdx {
 
 size_t g_plan_bytes = 0;
+// live plans: apdx_comm_destroy must drop their captured CUDA graphs (they hold NCCL operations of the communicator)
+static std::vector<apdx_plan *> g_plans;
+void drop_all_krylov_graphs() {
+  for (apdx_plan *pl : g_plans) {
+    if (pl->stream) cudaStreamSynchronize(pl->stream);
+    if (pl->stream2) cudaStreamSynchronize(pl->stream2);
+    for (auto &g : pl->kgraph)
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+  }
+}
 static thread_local char g_err[1024] = "";
 
 void set_error(const char *fmt, ...) {
@@ -295,6 +305,9 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
     return fail(APDX_ERR_CUDA);
   }
   for (auto &e : pl->ev) cudaEventCreate(&e);
+  cudaStreamCreateWithFlags(&pl->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming);
   if (cudaMallocHost((void **)&pl->pinned, 64 * sizeof(double)) != cudaSuccess) {
     set_error("cudaMallocHost failed");
     return fail(APDX_ERR_CUDA);
@@ -366,13 +379,16 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
     set_error("CUDA error during plan creation");
     return fail(APDX_ERR_CUDA);
   }
+  g_plans.push_back(pl);
   *plan = pl;
   return APDX_OK;
 }
 
 int apdx_plan_destroy(apdx_plan *pl) {
   if (!pl) return APDX_OK;
+  g_plans.erase(std::remove(g_plans.begin(), g_plans.end(), pl), g_plans.end());
   if (pl->stream) cudaStreamSynchronize(pl->stream);
+  if (pl->stream2) cudaStreamSynchronize(pl->stream2);
   for (auto &st : pl->sets) {
     st.conn.release(); st.shape_n.release(); st.shape_dn.release(); st.gp_w.release();
     st.ip_n.release(); st.ip_dndx.release(); st.ip_w.release();
@@ -392,6 +408,9 @@ int apdx_plan_destroy(apdx_plan *pl) {
   k.flags.release(); k.st_sc.release(); k.st_fl.release(); k.scratch.release();
   if (pl->pinned) cudaFreeHost(pl->pinned);
   for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+  if (pl->stream2) cudaStreamDestroy(pl->stream2);
   if (pl->stream) cudaStreamDestroy(pl->stream);
   delete pl;
   return APDX_OK;

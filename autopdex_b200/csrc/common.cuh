@@ -151,6 +151,7 @@ struct Sell {
   bool built = false;
   int64_t row0 = 0, n_rows = 0, n_slices = 0, n_val = 0, n_idx = 0;
   int nf = 1;                 // slices interleave the nf dofs per node (sell.cu)
+  int64_t lo_end = 0, hi_begin = 0;  // slices [lo_end, hi_begin) reference no ghost column (multi-GPU overlap)
   DevBuf<int32_t> sl_w;       // [n_slices] width | (offset mode ? 1<<31 : 0)
   DevBuf<int64_t> valptr;     // [n_slices+1] start of the slice's value block (doubles)
   DevBuf<int64_t> idxptr;     // [n_slices+1] start of the slice's index block (int32)
@@ -176,7 +177,9 @@ struct apdx_plan {
   int64_t n_nodes = 0, n_dofs = 0, n_free = 0, nnz = 0, nnz_red = 0, n_coo = 0, n_res = 0;
   std::vector<apdx::SetData> sets;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // halo exchange overlapping the interior SpMV
   cudaEvent_t ev[4]{};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   // fields
   apdx::DevBuf<double> coords, dofs_n;
@@ -225,6 +228,8 @@ struct apdx_plan {
 };
 
 namespace apdx {
+// api.cu
+void drop_all_krylov_graphs();
 // pattern.cu
 int build_pattern(apdx_plan *pl, const uint8_t *mask_h);
 // elements_fast.cu

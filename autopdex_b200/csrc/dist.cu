@@ -281,6 +281,8 @@ int apdx_comm_allreduce_host(double *inout_h, int32_t count, int32_t op) {
 
 int apdx_comm_destroy(void) {
   if (g_nccl.comm) {
+    drop_all_krylov_graphs();   // captured graphs hold NCCL operations of this communicator
+    cudaDeviceSynchronize();
     if (!g_parked.empty()) {  // barrier: no rank may still be storing into a heap that is about to be freed
       double *b = nullptr;
       APDX_CUDA(cudaMalloc((void **)&b, sizeof(double)));

@@ -175,7 +175,11 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_halo_push(const double *__restric
 template <int NV>
 __device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial, unsigned int *ticket,
                                                 double *sc, int32_t *fl, int stage, int fused, const P2PDev *pd,
-                                                int epoch, int slot0 = 0) {
+                                                int epoch, int slot0 = 0, int blk0 = 0, int nblk_total = -1,
+                                                int finalize = 1) {
+  // blk0 / nblk_total / finalize: one reduction may be fed by two launches (interior and boundary SpMV): the first
+  // only deposits its block partials, the second sums the partials of both
+  const unsigned nblk = nblk_total < 0 ? gridDim.x : (unsigned)nblk_total;
   __shared__ double sh[NV][VEC_BLOCK / 32];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -192,11 +196,15 @@ __device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial
     for (int i = 0; i < NV; ++i) {
       double x = 0.0;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += sh[i][w];
-      partial[(size_t)i * gridDim.x + blockIdx.x] = x;
+      partial[(size_t)i * nblk + blk0 + blockIdx.x] = x;
     }
-    __threadfence();
-    unsigned int t = atomicAdd(ticket, 1u);
-    last = (t == gridDim.x - 1);
+    if (finalize) {
+      __threadfence();
+      unsigned int t = atomicAdd(ticket, 1u);
+      last = (t == gridDim.x - 1);
+    } else {
+      last = false;
+    }
   }
   __syncthreads();
   if (!last) return;
@@ -204,7 +212,7 @@ __device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     double x = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) x += __ldcg(&partial[(size_t)i * gridDim.x + b]);
+    for (unsigned b = threadIdx.x; b < nblk; b += blockDim.x) x += __ldcg(&partial[(size_t)i * nblk + b]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     __syncthreads();
@@ -239,6 +247,11 @@ __device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial
 // 128-bit double2 (512 contiguous bytes per warp instruction).  Offset mode: column = row + off[j]
 // (one broadcast int per slice column, x gathers coalesced); explicit mode: int2 column pairs.
 // n_cols: length of x (clamp target of the padded offsets, whose values are exact zeros).
+struct SliceRange {
+  int64_t a0, a1, b0, b1;
+  int blk0, nblk_total, finalize;
+};
+
 template <int NDOT, int NF>
 __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restrict__ sl_w, const int64_t *__restrict__ valptr,
                                                          const int64_t *__restrict__ idxptr, const double *__restrict__ val,
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restri
                                                          int64_t row0, int64_t row1, int64_t n_slices, int32_t n_cols,
                                                          double *partial, unsigned int *ticket, double *sc, int32_t *fl,
                                                          int stage, int fused, int check_done, const P2PDev *pd, int epoch,
-                                                         int halo_epoch) {
+                                                         int halo_epoch, SliceRange rg) {
   if (check_done && fl[F_DONE]) return;
   if (pd && halo_epoch > 0) {
     // ghost entries of x are written by the neighbours' k_halo_push over NVLink: wait for this epoch's flags
@@ -263,7 +276,10 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restri
   double acc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
   for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
-  for (int64_t s = warp0; s < n_slices; s += nwarps) {
+  // rg: this launch covers slices [a0,a1) and [b0,b1) (interior launch: one range; boundary launch: the two ends)
+  const int64_t n_mine = (rg.a1 - rg.a0) + (rg.b1 - rg.b0);
+  for (int64_t si = warp0; si < n_mine; si += nwarps) {
+    const int64_t s = si < rg.a1 - rg.a0 ? rg.a0 + si : rg.b0 + (si - (rg.a1 - rg.a0));
     const int32_t wenc = sl_w[s];
     const int32_t W = wenc & 0x7fffffff;
     const double2 *vp = reinterpret_cast<const double2 *>(val + valptr[s]) + lane;
@@ -304,7 +320,8 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restri
       if (NDOT >= 2) acc[1] += a1 * a1;
     }
   }
-  if constexpr (NDOT > 0) reduce_finalize<NDOT>(acc, partial, ticket, sc, fl, stage, fused, pd, epoch);
+  if constexpr (NDOT > 0)
+    reduce_finalize<NDOT>(acc, partial, ticket, sc, fl, stage, fused, pd, epoch, 0, rg.blk0, rg.nblk_total, rg.finalize);
 }
 
 // ---- CG vector kernels -----------------------------------------------------------------------
@@ -573,7 +590,7 @@ int krylov_alloc(apdx_plan *pl) {
     APDX_CHECK(k.s.alloc(n));
     APDX_CUDA(cudaMemsetAsync(k.z.p, 0, n * sizeof(double), pl->stream));
   }
-  APDX_CHECK(k.partial.alloc(4 * (size_t)(VEC_GRID > 148 * 32 ? VEC_GRID : 148 * 32)));
+  APDX_CHECK(k.partial.alloc(4 * 2 * (size_t)(VEC_GRID > 148 * 32 ? VEC_GRID : 148 * 32)));   // x2: interior + boundary launches
   APDX_CHECK(k.st_sc.alloc(2 * S_COUNT));
   APDX_CHECK(k.st_fl.alloc(2 * F_COUNT));
   APDX_CHECK(k.scratch.alloc(S_COUNT));
@@ -616,22 +633,34 @@ static Comm comm_of(apdx_plan *pl) {
   return c;
 }
 
+static unsigned spmv_grid(int64_t n_slices) {
+  const int64_t warps_per_block = VEC_BLOCK / 32;
+  int64_t nb = (n_slices + warps_per_block - 1) / warps_per_block;
+  const int64_t cap = 148ll * 32;
+  return (unsigned)(nb < cap ? (nb > 0 ? nb : 1) : cap);
+}
+
+// part: 0 = all slices in one launch; 1 = interior slices only (deposits its dot partials); 2 = the boundary slices
+// at both ends of the owned range (they read ghost columns) + the final reduction over both launches
 template <int NDOT>
 static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *w, int stage, int check_done,
-                       int halo_epoch = 0) {
+                       int halo_epoch = 0, int part = 0) {
   KrylovWork &k = pl->kw;
   Sell &S = pl->sell;
   const Comm c = comm_of(pl);
-  const int64_t warps_per_block = VEC_BLOCK / 32;
-  int64_t nb = (S.n_slices + warps_per_block - 1) / warps_per_block;
-  const int64_t cap = 148ll * 32;
-  unsigned grid = (unsigned)(nb < cap ? (nb > 0 ? nb : 1) : cap);
+  SliceRange rg{0, S.n_slices, 0, 0, 0, -1, 1};
+  unsigned grid = spmv_grid(S.n_slices);
+  if (part != 0) {
+    const unsigned g_int = spmv_grid(S.hi_begin - S.lo_end), g_bnd = spmv_grid(S.lo_end + (S.n_slices - S.hi_begin));
+    if (part == 1) { rg = SliceRange{S.lo_end, S.hi_begin, 0, 0, 0, (int)(g_int + g_bnd), 0}; grid = g_int; }
+    else { rg = SliceRange{0, S.lo_end, S.hi_begin, S.n_slices, (int)g_int, (int)(g_int + g_bnd), 1}; grid = g_bnd; }
+  }
   const int epoch = (NDOT > 0 && c.p2p && stage >= 0) ? ++pl->p2p.red_epoch : 0;
 #define APDX_SPMV_NF(NFV)                                                                                              \
   k_spmv_sell<NDOT, NFV><<<grid, VEC_BLOCK, 0, pl->stream>>>(                                                          \
       S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free,    \
       k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,                                        \
-      (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch)
+      (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch, rg)
   if (S.nf == 1) APDX_SPMV_NF(1);
   else if (S.nf == 2) APDX_SPMV_NF(2);
   else APDX_SPMV_NF(3);
@@ -676,6 +705,32 @@ static int finish_stage(apdx_plan *pl, int stage, int nv) {
   pl->stats.kernel_launches += 1;
   return APDX_OK;
 }
+// y = A v with the ghost entries of v refreshed first.  Multi-GPU over NCCL: the halo exchange runs on a second
+// stream while the interior slices are multiplied; the boundary slices follow once the ghosts have arrived.
+template <int NDOT>
+static int spmv_exchange(apdx_plan *pl, double *v, double *y, const double *w, int stage, int check_done) {
+  const Comm c = comm_of(pl);
+  if (!c.multi) return launch_spmv<NDOT>(pl, v, y, w, stage, check_done);
+  Sell &S = pl->sell;
+  const char *ov = getenv("APDX_OVERLAP");
+  // measured on 2 B200s: no gain over the in-order exchange, so opt-in (APDX_OVERLAP=1)
+  const bool overlap = !c.p2p && (ov && strcmp(ov, "1") == 0) && S.hi_begin > S.lo_end &&
+                       (S.lo_end + (S.n_slices - S.hi_begin)) > 0;
+  if (!overlap) {
+    int he = 0;
+    APDX_CHECK(exchange_halo(pl, v, &he));
+    return launch_spmv<NDOT>(pl, v, y, w, stage, check_done, he);
+  }
+  cudaStream_t s = pl->stream, s2 = pl->stream2;
+  APDX_CUDA(cudaEventRecord(pl->ev_fork, s));
+  APDX_CUDA(cudaStreamWaitEvent(s2, pl->ev_fork, 0));
+  APDX_CHECK(comm_halo_exchange(pl, v, s2));
+  APDX_CUDA(cudaEventRecord(pl->ev_join, s2));
+  APDX_CHECK(launch_spmv<NDOT>(pl, v, y, w, stage, check_done, 0, 1));   // interior
+  APDX_CUDA(cudaStreamWaitEvent(s, pl->ev_join, 0));
+  return launch_spmv<NDOT>(pl, v, y, w, stage, check_done, 0, 2);        // boundary + reduction
+}
+
 // epoch argument of a vector kernel that ends in a reduction
 static int next_red_epoch(apdx_plan *pl) { return comm_of(pl).p2p ? ++pl->p2p.red_epoch : 0; }
 
@@ -814,7 +869,8 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
           // (the opt-in p2p-fused CG is only wired for scalar problems)
           k_spmv_sell<1, 1><<<grid, VEC_BLOCK, 0, s>>>(S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p,
                                                        pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, k.partial.p, k.ticket.p,
-                                                       k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he);
+                                                       k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he,
+                                                       SliceRange{0, S.n_slices, 0, 0, 0, -1, 1});
           TR(1);
           pl->stats.spmv_launches += 1;
           StageCtx c1{k.st_sc.p + par * S_COUNT, k.st_sc.p + (par ^ 1) * S_COUNT, k.st_fl.p + par * F_COUNT,
@@ -837,9 +893,13 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
           pl->stats.kernel_launches += 3;
         }
       } else if (!bi) {
-        APDX_CHECK(exchange_halo(pl, k.p.p, &he));
-        TR(0);
-        APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, ST_CG_PQ, 1, he));
+        if (c.p2p) {
+          APDX_CHECK(exchange_halo(pl, k.p.p, &he));
+          TR(0);
+          APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, ST_CG_PQ, 1, he));
+        } else {
+          APDX_CHECK(spmv_exchange<1>(pl, k.p.p, k.q.p, k.p.p, ST_CG_PQ, 1));
+        }
         TR(1);
         APDX_CHECK(finish_stage(pl, ST_CG_PQ, 1));
         TR(2);
@@ -853,14 +913,22 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
         pl->stats.kernel_launches += 2;
       } else {
         k_bi_p<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.q.p, k.minv.p, k.p.p, k.phat.p, i0, i1, k.scal.p, k.flags.p);
-        APDX_CHECK(exchange_halo(pl, k.phat.p, &he));
-        APDX_CHECK(launch_spmv<1>(pl, k.phat.p, k.q.p, k.r0.p, ST_BI_R0V, 1, he));
+        if (c.p2p) {
+          APDX_CHECK(exchange_halo(pl, k.phat.p, &he));
+          APDX_CHECK(launch_spmv<1>(pl, k.phat.p, k.q.p, k.r0.p, ST_BI_R0V, 1, he));
+        } else {
+          APDX_CHECK(spmv_exchange<1>(pl, k.phat.p, k.q.p, k.r0.p, ST_BI_R0V, 1));
+        }
         APDX_CHECK(finish_stage(pl, ST_BI_R0V, 1));
         k_bi_s<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.q.p, k.minv.p, k.s.p, k.shat.p, i0, i1, k.partial.p,
                                               k.ticket.p, k.scal.p, k.flags.p, fused, pd, next_red_epoch(pl));
         APDX_CHECK(finish_stage(pl, ST_BI_S, 1));
-        APDX_CHECK(exchange_halo(pl, k.shat.p, &he));
-        APDX_CHECK(launch_spmv<2>(pl, k.shat.p, k.t.p, k.s.p, ST_BI_T, 1, he));
+        if (c.p2p) {
+          APDX_CHECK(exchange_halo(pl, k.shat.p, &he));
+          APDX_CHECK(launch_spmv<2>(pl, k.shat.p, k.t.p, k.s.p, ST_BI_T, 1, he));
+        } else {
+          APDX_CHECK(spmv_exchange<2>(pl, k.shat.p, k.t.p, k.s.p, ST_BI_T, 1));
+        }
         APDX_CHECK(finish_stage(pl, ST_BI_T, 2));
         k_bi_x<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.phat.p, k.shat.p, k.s.p, k.t.p, k.r0.p, x, k.r.p, i0, i1,
                                               k.partial.p, k.ticket.p, k.scal.p, k.flags.p, fused, pd, next_red_epoch(pl));

@@ -12,6 +12,8 @@
 // `north_star`'s "sliced-ELL ... with 128-bit loads and warp-shuffle row reductions".
 #include <cub/cub.cuh>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace apdx {
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(256) k_sell_build(const int32_t *__restrict__ 
                                                     int32_t *__restrict__ sz_val, int32_t *__restrict__ sz_idx,
                                                     const int64_t *__restrict__ valptr, const int64_t *__restrict__ idxptr,
                                                     int32_t *__restrict__ sell_idx, int32_t *__restrict__ sell_src,
-                                                    int32_t *__restrict__ sell_diag) {
+                                                    int32_t *__restrict__ sell_diag, uint8_t *__restrict__ ghost) {
   const int lane = threadIdx.x & 31;
   const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (s >= n_slices) return;
@@ -82,6 +84,14 @@ __global__ void __launch_bounds__(256) k_sell_build(const int32_t *__restrict__ 
     return;
   }
   // ---- PASS 1: fill ------------------------------------------------------------------------------
+  {  // does the slice reference a column outside the owned range [row0,row1) (a ghost entry of x)?
+    bool g = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      for (int32_t q = b[h]; q < e[h]; ++q) g |= (col[q] < row0 || col[q] >= row1);
+    g = __any_sync(0xffffffffu, g);
+    if (lane == 0) ghost[s] = g ? 1 : 0;
+  }
   const int32_t wenc = sl_w[s];
   offset_mode = wenc < 0;
   const int32_t w = wenc & 0x7fffffff;
@@ -161,13 +171,15 @@ int sell_build(apdx_plan *pl) {
   APDX_CHECK(S.diag.alloc(rows));
   APDX_CUDA(cudaMemsetAsync(S.diag.p, 0xff, rows * sizeof(int32_t), s));
   DevBuf<int32_t> szv, szi;
+  DevBuf<uint8_t> ghost;
+  APDX_CHECK(ghost.alloc(ns > 0 ? ns : 1));
   APDX_CHECK(szv.alloc(ns + 1));
   APDX_CHECK(szi.alloc(ns + 1));
   APDX_CUDA(cudaMemsetAsync(szv.p, 0, (ns + 1) * sizeof(int32_t), s));
   APDX_CUDA(cudaMemsetAsync(szi.p, 0, (ns + 1) * sizeof(int32_t), s));
   const unsigned grid = (unsigned)((ns * 32 + 255) / 256);
   k_sell_build<0><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, pl->f0, pl->f1, ns, S.nf, S.sl_w.p,
-                                       szv.p, szi.p, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                       szv.p, szi.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   APDX_CHECK(scan64(szv.p, S.valptr.p, ns + 1, s));
   APDX_CHECK(scan64(szi.p, S.idxptr.p, ns + 1, s));
   int64_t tot[2];
@@ -180,8 +192,30 @@ int sell_build(apdx_plan *pl) {
   APDX_CHECK(S.src.alloc(S.n_val > 0 ? S.n_val : 1));
   APDX_CHECK(S.idx.alloc(S.n_idx > 0 ? S.n_idx : 1));
   k_sell_build<1><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, pl->f0, pl->f1, ns, S.nf, S.sl_w.p,
-                                       nullptr, nullptr, S.valptr.p, S.idxptr.p, S.idx.p, S.src.p, S.diag.p);
+                                       nullptr, nullptr, S.valptr.p, S.idxptr.p, S.idx.p, S.src.p, S.diag.p, ghost.p);
   APDX_CUDA(cudaStreamSynchronize(s));
+  {  // leading / trailing runs of slices that touch ghost columns; everything in between is "interior"
+    std::vector<uint8_t> gh((size_t)ns);
+    APDX_CUDA(cudaMemcpy(gh.data(), ghost.p, (size_t)ns, cudaMemcpyDeviceToHost));
+    int64_t first_clean = 0, last_clean = ns;
+    while (first_clean < ns && gh[first_clean]) ++first_clean;
+    while (last_clean > first_clean && gh[last_clean - 1]) --last_clean;
+    bool clean = true;
+    for (int64_t q = first_clean; q < last_clean; ++q) clean = clean && !gh[q];
+    // pad the runs a little so that flagged slices scattered just behind the ghost planes stay in the boundary part
+    if (!clean) {
+      int64_t lo = first_clean, hi = last_clean;
+      for (int64_t q = first_clean; q < last_clean; ++q)
+        if (gh[q]) { if (q < ns / 2) lo = q + 1; else { hi = q; break; } }
+      first_clean = lo;
+      last_clean = hi > lo ? hi : lo;
+      clean = true;
+      for (int64_t q = first_clean; q < last_clean; ++q) clean = clean && !gh[q];
+      if (!clean) { first_clean = ns; last_clean = ns; }   // irregular partition: no overlap, one launch
+    }
+    S.lo_end = first_clean;
+    S.hi_begin = last_clean;
+  }
   APDX_CUDA(cudaGetLastError());
   S.built = true;
   return APDX_OK;

@@ -49,6 +49,7 @@ def main():
         ok = err < 1e-8 and steps == rsteps and div == rdiv
         print("multi-gpu parity: ranks=%d m=%d %s steps=%d/%d res=%.2e rel-L2=%.2e -> %s"
               % (world, m, krylov, steps, rsteps, res, err, "OK" if ok else "FAIL"))
+    solver.clear_plan_cache()
     backend.comm_destroy()
     sys.exit(0 if ok else 1)
 
