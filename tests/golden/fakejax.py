@@ -111,8 +111,28 @@ class XPoint(np.ndarray):
 
 
 class _JvpOut:
+    """tangent produced by a custom-JVP rule for a tagged evaluation point; supports the LINEAR operations the
+    reference applies to an ansatz before the derivative is taken (shps @ local_dofs, [0], scaling, sums)"""
+
     def __init__(self, tangent):
         self.tangent = tangent
+
+    def __matmul__(self, other):
+        return _JvpOut(J(np.asarray(self.tangent) @ np.asarray(other)))
+
+    def __rmatmul__(self, other):
+        return _JvpOut(J(np.asarray(other) @ np.asarray(self.tangent)))
+
+    def __getitem__(self, idx):
+        return _JvpOut(J(np.asarray(self.tangent)[idx]))
+
+    def __mul__(self, other):
+        return _JvpOut(J(np.asarray(self.tangent) * other))
+    __rmul__ = __mul__
+
+    def __add__(self, other):
+        return _JvpOut(J(np.asarray(self.tangent) + (np.asarray(other.tangent) if isinstance(other, _JvpOut) else 0.0)))
+    __radd__ = __add__
 
 
 _CSTEP = 1e-30
@@ -295,6 +315,8 @@ def vmap(fun, in_axes=0, out_axes=0, **_):
 
 def _stack(outs):
     o0 = outs[0]
+    if isinstance(o0, _JvpOut):
+        return _JvpOut(J(np.stack([np.asarray(o.tangent) for o in outs])))
     if isinstance(o0, tuple):
         return tuple(_stack([o[i] for o in outs]) for i in range(len(o0)))
     if isinstance(o0, dict):

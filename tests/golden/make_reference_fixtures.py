@@ -179,6 +179,35 @@ def case_elements(out):
                  settings_extra=mat, dofs_scale=0.05)
 
 
+def case_sparse_compiled(out):
+    """'sparse' assembling mode (assembler.py:874-1035 -> variational_schemes.weak_form_galerkin ->
+    solution_structures 'compiled' shape functions): conduction + Euler capacity + surface inflow on P1 triangles,
+    one linear (backward-Euler) step through solver.solver with 'solver type': 'linear'."""
+    p = problems.heat_sparse(2, 2, 1)
+    cond, cap, sur = p["sets"]
+    static_settings = flax.core.FrozenDict({
+        "assembling mode": ("sparse",) * 3, "solution structure": ("nodal imposition",) * 3,
+        "variational scheme": ("weak form galerkin",) * 3, "solution space": ("fem simplex",) * 3,
+        "shape function mode": "compiled", "number of fields": (1, 1, 1), "maximal number of neighbors": (3, 3, 2),
+        "model": (models.poisson_weak(lambda x, settings: 1.5, lambda x: 0.0),
+                  models.forward_backward_euler_weak(lambda x, settings: 0.1),
+                  models.neumann_weak(lambda x: -3.0)),
+        "solver type": "linear", "solver backend": "scipy", "solver": "lapack", "verbose": -1})
+    dofs_n = jnp.asarray(p["settings"]["dofs n"])
+    settings = {"connectivity": tuple(jnp.asarray(s["conn"]) for s in p["sets"]), "node coordinates": jnp.asarray(p["coords"]),
+                "dirichlet dofs": jnp.asarray(p["mask"]), "dirichlet conditions": jnp.asarray(p["values"]),
+                "integration coordinates": tuple(jnp.asarray(x) for x in p["x_int"]),
+                "integration weights": tuple(jnp.asarray(w) for w in p["w_int"]),
+                "compiled shape functions": tuple((jnp.asarray(s["N"]), jnp.asarray(s["dNdx"])) for s in p["sets"]),
+                "time increment": 0.2, "dofs n": dofs_n}
+    R = assembler.assemble_residual(dofs_n, settings, static_settings)
+    K = assembler.assemble_tangent(dofs_n, settings, static_settings)
+    data, rows, cols = bcoo_arrays(K)
+    delta, _ = solver.solver(dofs_n, settings, static_settings)
+    out.update({"sparse_R": A(R), "sparse_K_data": data, "sparse_K_rows": rows, "sparse_K_cols": cols,
+                "sparse_delta": A(delta), "sparse_dofs_n": A(dofs_n)})
+
+
 def case_newton_semantics(out):
     """solver.damped_newton (solver.py:837-948) driven by synthetic residual sequences."""
     def run(norms, newton_tol=1e-8, maxiter=30):
@@ -202,7 +231,7 @@ def case_newton_semantics(out):
 
 
 CASES = {"tables": case_tables, "readme3": lambda o: readme_case(3, o, "readme3"),
-         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements,
+         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "sparse": case_sparse_compiled,
          "newton": case_newton_semantics}
 
 if __name__ == "__main__":

@@ -213,3 +213,19 @@ def test_gpu_against_reference_run(tag):
     assert rel(plan.values(False), ref.data) < TANGENT_RTOL
     assert rel(r.download(), FIX[tag + "_R"].ravel()) < 1e-11
     plan.destroy()
+
+
+def test_sparse_mode_compiled_against_reference_run():
+    """'sparse' mode chain of the reference (assembler.py:874-1035, variational_schemes.py:185-252, solution_structures.py:
+    242-248) for conduction + Euler capacity + surface inflow, and one 'linear' solver step (mixed return vector)."""
+    p = problems.heat_sparse(2, 2, 1)
+    dofs_n = FIX["sparse_dofs_n"]
+    assert np.array_equal(dofs_n, p["settings"]["dofs n"])
+    R, data = oasm.assemble(p["sets"], p["coords"], dofs_n, p["settings"])
+    rows, cols = oasm.coo_indices(p["sets"])
+    assert np.array_equal(rows, FIX["sparse_K_rows"]) and np.array_equal(cols, FIX["sparse_K_cols"])
+    assert rel(R, FIX["sparse_R"].ravel()) < 1e-11
+    assert rel(data, FIX["sparse_K_data"]) < TANGENT_RTOL
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"], p["settings"])
+    delta = osolve.solve_linear(prob, dofs_n)
+    assert rel(delta, FIX["sparse_delta"]) < 1e-9
