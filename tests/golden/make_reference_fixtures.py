@@ -208,6 +208,27 @@ def case_sparse_compiled(out):
                 "sparse_delta": A(delta), "sparse_dofs_n": A(dofs_n)})
 
 
+def case_simplex_direct(out):
+    """spaces.fem_ini_simplex (spaces.py:15194-15296), the 'direct' shape functions of 'fem simplex': values exactly,
+    physical gradients by Richardson differences of the reference function."""
+    from oracle import shapes as oshapes
+    rng = np.random.default_rng(21)
+    st = flax.core.FrozenDict({"shape function mode": "compiled"})
+    for name in ("tri3", "tri6", "tet4"):
+        ref = np.asarray(oshapes.REF_NODES[name], dtype=float)
+        dim = ref.shape[1]
+        Amat = np.eye(dim) + 0.2 * rng.standard_normal((dim, dim))
+        xI = ref @ Amat.T + rng.uniform(-1, 1, dim)
+        x = xI.mean(axis=0) + 0.05 * rng.standard_normal(dim)
+        fun = lambda xx: spaces.fem_ini_simplex(xx, jnp.asarray(xI), jnp.zeros((xI.shape[0], 1)), st, 0)
+        fakejax.POINT_MODE = "fd"       # nested derivatives w.r.t. small vectors: differences, not complex steps
+        N = A(fun(jnp.asarray(x)))
+        dN = A(jax.jacfwd(fun)(jnp.asarray(x)))
+        fakejax.POINT_MODE = "complex"
+        out["simplex_%s_xI" % name], out["simplex_%s_x" % name] = xI, x
+        out["simplex_%s_N" % name], out["simplex_%s_dN" % name] = N, dN
+
+
 def case_newton_semantics(out):
     """solver.damped_newton (solver.py:837-948) driven by synthetic residual sequences."""
     def run(norms, newton_tol=1e-8, maxiter=30):
@@ -231,7 +252,7 @@ def case_newton_semantics(out):
 
 
 CASES = {"tables": case_tables, "readme3": lambda o: readme_case(3, o, "readme3"),
-         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "sparse": case_sparse_compiled,
+         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 
 if __name__ == "__main__":

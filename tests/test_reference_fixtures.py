@@ -229,3 +229,15 @@ def test_sparse_mode_compiled_against_reference_run():
     prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"], p["settings"])
     delta = osolve.solve_linear(prob, dofs_n)
     assert rel(delta, FIX["sparse_delta"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["tri3", "tri6", "tet4"])
+def test_fem_ini_simplex_direct_tables_against_reference(name):
+    """Physical-space P1/P2 shape values and gradients of spaces.fem_ini_simplex (the 'direct' shape function mode)."""
+    if "simplex_%s_N" % name not in FIX:
+        pytest.skip("fixture not generated")
+    xI, x = FIX["simplex_%s_xI" % name], FIX["simplex_%s_x" % name]
+    for impl in (spaces.simplex_physical_tables, oshapes.simplex_physical_tables):
+        N, dN = impl(x[None, :], xI[None, :, :])
+        assert np.abs(N[0] - FIX["simplex_%s_N" % name]).max() < 1e-10
+        assert np.abs(dN[0] - FIX["simplex_%s_dN" % name]).max() < 1e-6 * max(1.0, np.abs(dN).max())
