@@ -13,9 +13,9 @@ SURVEY.md section 8c).  Every function cites the reference file:line it follows
 Parity pins (tests/test_oracle_golden.py):
   * G1  tests/test_dicts_as_dofs_user_potential.py:62-63   sum(phi) = 1.9066412530282952
   * G2  tests/test_user_elem_impl_diff_and_adaptive_load_step.py:153   u.u = 19390.35027108
-  * the reference's own shape-function and quadrature tables, evaluated from the
-    reference source by tests/golden/make_reference_fixtures.py and committed as
-    tests/golden/reference_tables.json
+  * outputs of the UNMODIFIED reference modules executed on a NumPy stand-in for JAX
+    (tests/golden/fakejax.py, generator tests/golden/make_reference_fixtures.py), committed as
+    tests/golden/reference_fixtures.npz and checked in tests/test_reference_fixtures.py
 The SciPy half of the reference path (coo->csr duplicate summing, row/column
 deletion, spsolve) is executed as-is with the same SciPy calls.
 """
