@@ -288,6 +288,11 @@ class Plan:
                 "total_ms", "kernel_launches", "sell_bytes")
         return dict(zip(keys, list(out)[:8]))
 
+    def sell_info(self):
+        out = (C.c_int64 * 6)()
+        _lib.check(_lib.load().apdx_plan_sell_info(self.h, out))
+        return dict(zip(("slices", "stored_values", "index_ints", "mirrored_entries", "symmetric", "dofs_per_node"), list(out)))
+
     def set_partition(self, owned_dof_begin, owned_dof_end, rank_lo=-1, rank_hi=-1):
         _lib.check(_lib.load().apdx_plan_set_partition(self.h, int(owned_dof_begin), int(owned_dof_end), int(rank_lo),
                                                        int(rank_hi)))

@@ -673,12 +673,20 @@ int apdx_newton(apdx_plan *pl, const apdx_krylov_opts *opts, double *dofs_d, con
   return APDX_OK;
 }
 
+int apdx_plan_sell_info(const apdx_plan *pl, int64_t out[6]) {
+  APDX_REQUIRE(pl && out, APDX_ERR_INVALID, "null argument");
+  APDX_REQUIRE(pl->sell.built, APDX_ERR_STATE, "no sliced-ELL matrix yet: assemble a tangent for the solver first");
+  const apdx::Sell &S = pl->sell;
+  out[0] = S.n_slices; out[1] = S.n_val; out[2] = S.n_idx; out[3] = S.n_mirrored; out[4] = S.sym ? 1 : 0; out[5] = S.nf;
+  return APDX_OK;
+}
+
 int apdx_plan_stats(const apdx_plan *pl, double out[8]) {
   APDX_REQUIRE(pl && out, APDX_ERR_INVALID, "NULL argument");
   out[0] = pl->stats.asm_tangent_ms; out[1] = pl->stats.asm_residual_ms; out[2] = pl->stats.krylov_ms;
   out[3] = pl->stats.krylov_iters; out[4] = pl->stats.spmv_launches; out[5] = pl->stats.total_ms;
   out[6] = pl->stats.kernel_launches;
-  out[7] = (double)(pl->sell.n_val * 8 + pl->sell.n_idx * 4 + pl->sell.n_slices * 20);  // bytes of the sliced-ELL matrix
+  out[7] = (double)(pl->sell.n_val * 8 + pl->sell.n_idx * 4 + pl->sell.n_slices * 24);  // bytes of the sliced-ELL matrix
   return APDX_OK;
 }
 

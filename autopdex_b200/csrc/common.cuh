@@ -149,18 +149,20 @@ struct KrylovGraph {
 // sliced-ELL copy of the owned rows of the reduced system (sell.cu)
 struct Sell {
   bool built = false;
-  int64_t row0 = 0, n_rows = 0, n_slices = 0, n_val = 0, n_idx = 0;
+  bool sym = true;            // lower columns read from the transposed position where possible (sell.cu)
+  int64_t row0 = 0, n_rows = 0, n_slices = 0, n_val = 0, n_idx = 0, n_mirrored = 0;
   int nf = 1;                 // slices interleave the nf dofs per node (sell.cu)
   int64_t lo_end = 0, hi_begin = 0;  // slices [lo_end, hi_begin) reference no ghost column (multi-GPU overlap)
-  DevBuf<int32_t> sl_w;       // [n_slices] width | (offset mode ? 1<<31 : 0)
+  DevBuf<int32_t> sl_w;       // [n_slices] stored width | (offset mode ? 1<<31 : 0)
+  DevBuf<int32_t> sl_m;       // [n_slices] number of mirrored lower columns (table behind the slice's offsets)
   DevBuf<int64_t> valptr;     // [n_slices+1] start of the slice's value block (doubles)
   DevBuf<int64_t> idxptr;     // [n_slices+1] start of the slice's index block (int32)
-  DevBuf<double> val;         // [n_val] column-major per slice
-  DevBuf<int32_t> idx;        // [n_idx] offsets (offset mode) or columns (explicit mode)
+  DevBuf<double> val;         // [n_val + 64] column-major per slice, then 64 zeros
+  DevBuf<int32_t> idx;        // [n_idx] offsets + mirror table (offset mode) or columns (explicit mode)
   DevBuf<int32_t> src;        // [n_val] full-CSR entry behind each position, -1 = padding
   DevBuf<int32_t> diag;       // [n_rows] diagonal position relative to the slice's value block, -1 = none
   void release() {
-    sl_w.release(); valptr.release(); idxptr.release(); val.release(); idx.release(); src.release(); diag.release();
+    sl_w.release(); sl_m.release(); valptr.release(); idxptr.release(); val.release(); idx.release(); src.release(); diag.release();
     built = false;
   }
 };

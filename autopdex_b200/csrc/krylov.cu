@@ -253,18 +253,23 @@ struct SliceRange {
   int blk0, nblk_total, finalize;
 };
 
-// U = slice columns whose loads are issued back to back before the first FMA.  The warp issues in order, so a
-// loop that alternates load / FMA keeps only one 512-byte value row in flight per warp (measured: 62 % of the
-// DRAM peak, long-scoreboard bound); batching U rows multiplies the bytes in flight per warp by U.
-template <int NDOT, int NF, int U>
-__global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restrict__ sl_w, const int64_t *__restrict__ valptr,
-                                                         const int64_t *__restrict__ idxptr, const double *__restrict__ val,
-                                                         const int32_t *__restrict__ idx, const double *__restrict__ x,
-                                                         double *__restrict__ y, const double *__restrict__ w,
-                                                         int64_t row0, int64_t row1, int64_t n_slices, int32_t n_cols,
-                                                         double *partial, unsigned int *ticket, double *sc, int32_t *fl,
-                                                         int stage, int fused, int check_done, const P2PDev *pd, int epoch,
-                                                         int halo_epoch, SliceRange rg) {
+// Loads are issued in batches of up to SPMV_U slice columns before the first FMA.  The warp issues in order, so a
+// loop that alternates load / FMA keeps only one 512-byte value row in flight per warp (measured: 62 % of the DRAM
+// peak, long-scoreboard bound; batching: 96 % of the measured copy bandwidth).  A slice's columns are taken in chunks of
+// 32 (lane u holds the offset / mirror-table entry of column u of the chunk, handed out by shuffles: no dependent
+// broadcast load per column) and every chunk in equal batches of at most SPMV_U columns.
+// SYM: lower columns of offset-mode slices are read from their transposed position (sell.cu); the value stream then
+// uses the default L2 policy (the partner slices re-read it from the L2 a few MB later) instead of evict-first.
+constexpr int SPMV_U = 9;
+
+template <int NDOT, int NF, bool SYM>
+__global__ void __launch_bounds__(VEC_BLOCK, 2)
+    k_spmv_sell(const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_m, const int64_t *__restrict__ valptr,
+                const int64_t *__restrict__ idxptr, const double *__restrict__ val, const int32_t *__restrict__ idx,
+                const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, int64_t row0,
+                int64_t row1, int64_t n_slices, int32_t n_cols, double *partial, unsigned int *ticket, double *sc,
+                int32_t *fl, int stage, int fused, int check_done, const P2PDev *pd, int epoch, int halo_epoch,
+                SliceRange rg) {
   if (check_done && fl[F_DONE]) return;
   if (pd && halo_epoch > 0) {
     // ghost entries of x are written by the neighbours' k_halo_push over NVLink: wait for this epoch's flags
@@ -286,228 +291,91 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_spmv_sell(const int32_t *__restri
     const int64_t s = si < rg.a1 - rg.a0 ? rg.a0 + si : rg.b0 + (si - (rg.a1 - rg.a0));
     const int32_t wenc = sl_w[s];
     const int32_t W = wenc & 0x7fffffff;
+    const int32_t M = SYM ? sl_m[s] : 0;
     const double2 *vp = reinterpret_cast<const double2 *>(val + valptr[s]) + lane;
     // rows of the slice: one field component of 64 consecutive nodes (sell.cu), two rows per lane
     const int64_t r0 = row0 + (s / NF) * (int64_t)64 * NF + (s % NF) + (int64_t)NF * (2 * lane);
-    const int64_t r1 = r0 + NF;   // lane owns rows k = lane and lane + 32 of the slice: warp-contiguous x / y accesses
-    double a0 = 0.0, a1 = 0.0;
-    if (wenc < 0) {
-      const int32_t *op = idx + idxptr[s];
-      const int32_t rr0 = (int32_t)r0, rr1 = (int32_t)r1;
-      // lane u of `offn` holds the offset of column j + u of the next batch (one coalesced load per batch instead of
-      // a dependent broadcast load per column)
-      int32_t j = 0;
-      int32_t offn = W > 0 ? __ldg(op + min(lane, W - 1)) : 0;
-      for (; j + U <= W; j += U) {
-        const int32_t offc = offn;
-        offn = __ldg(op + min(j + U + lane, W - 1));
-        double2 v[U];
-        double xa[U], xb[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = __ldcs(vp + (size_t)(j + u) * 32);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int32_t off = __shfl_sync(0xffffffffu, offc, u);
-          xa[u] = __ldg(x + min(max(rr0 + off, 0), n_cols - 1));
-          xb[u] = __ldg(x + min(max(rr1 + off, 0), n_cols - 1));
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) { a0 += v[u].x * xa[u]; a1 += v[u].y * xb[u]; }
-      }
-      for (int32_t t = 0; j < W; ++j, ++t) {
-        const int32_t off = __shfl_sync(0xffffffffu, offn, t);
-        const double2 v = __ldcs(vp + (size_t)j * 32);
-        a0 += v.x * __ldg(x + min(max(rr0 + off, 0), n_cols - 1));
-        a1 += v.y * __ldg(x + min(max(rr1 + off, 0), n_cols - 1));
-      }
-    } else {
-      const int2 *cp = reinterpret_cast<const int2 *>(idx + idxptr[s]) + lane;
-      int32_t j = 0;
-      for (; j + U <= W; j += U) {
-        int2 c[U];
-        double2 v[U];
-        double xa[U], xb[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) c[u] = __ldcs(cp + (size_t)(j + u) * 32);
-#pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = __ldcs(vp + (size_t)(j + u) * 32);
-#pragma unroll
-        for (int u = 0; u < U; ++u) { xa[u] = __ldg(x + c[u].x); xb[u] = __ldg(x + c[u].y); }
-#pragma unroll
-        for (int u = 0; u < U; ++u) { a0 += v[u].x * xa[u]; a1 += v[u].y * xb[u]; }
-      }
-      for (; j < W; ++j) {
-        const int2 c = __ldcs(cp + (size_t)j * 32);
-        const double2 v = __ldcs(vp + (size_t)j * 32);
-        a0 += v.x * __ldg(x + c.x);
-        a1 += v.y * __ldg(x + c.y);
-      }
-    }
-    if (r0 < row1) {
-      y[r0] = a0;
-      if (NDOT >= 1) acc[0] += w[r0] * a0;
-      if (NDOT >= 2) acc[1] += a0 * a0;
-    }
-    if (r1 < row1) {
-      y[r1] = a1;
-      if (NDOT >= 1) acc[0] += w[r1] * a1;
-      if (NDOT >= 2) acc[1] += a1 * a1;
-    }
-  }
-  if constexpr (NDOT > 0)
-    reduce_finalize<NDOT>(acc, partial, ticket, sc, fl, stage, fused, pd, epoch, 0, rg.blk0, rg.nblk_total, rg.finalize);
-}
-
-// ---- bulk-copy (TMA) pipelined SpMV ---------------------------------------------------------------------------
-// Same storage, same arithmetic order per row as k_spmv_sell.  The value block of a slice is one contiguous run
-// (W x 512 B), so it is streamed HBM -> shared memory by 1-D bulk async copies (cp.async.bulk + mbarrier
-// complete_tx) in chunks of BK_CH slice columns.  Every warp is an independent pipeline with its own ring of STAGES
-// chunks: lane 0 keeps STAGES x 4 KB in flight for the warp without holding them in registers, the 32 lanes
-// meanwhile gather the x operands of the chunk they are about to consume (those do not depend on the values),
-// wait on the chunk's mbarrier and run the FMAs out of shared memory.  One CTA per SM (WARPS x STAGES x 4 KB of
-// dynamic shared memory), slices strided over all warps of the grid so that the slices in flight are contiguous in
-// memory (x stays L2-resident; the values are tagged evict-first).
-constexpr int BK_CH = 8;   // slice columns per chunk: 8 x 512 B = 4 KB
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
-      : "memory");
-}
-
-template <int NDOT, int NF, int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-    k_spmv_sell_bulk(const int32_t *__restrict__ sl_w, const int64_t *__restrict__ valptr,
-                     const int64_t *__restrict__ idxptr, const double *__restrict__ val, const int32_t *__restrict__ idx,
-                     const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, int64_t row0,
-                     int64_t row1, int64_t n_slices, int32_t n_cols, double *partial, unsigned int *ticket, double *sc,
-                     int32_t *fl, int stage, int fused, int check_done, const P2PDev *pd, int epoch, int halo_epoch,
-                     SliceRange rg) {
-  if (check_done && fl[F_DONE]) return;
-  if (pd && halo_epoch > 0) {
-    if (threadIdx.x == 0) {
-      if (pd->has_lo) p2p_wait(pd->hflag_self + 0, halo_epoch, pd->err);
-      if (pd->has_hi) p2p_wait(pd->hflag_self + 1, halo_epoch, pd->err);
-    }
-    __syncthreads();
-  }
-  extern __shared__ __align__(128) unsigned char bk_smem[];
-  __shared__ __align__(8) uint64_t bk_bar[WARPS][STAGES];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double *ring = reinterpret_cast<double *>(bk_smem) + (size_t)wid * STAGES * BK_CH * 64;
-  const uint32_t ring_u = smem_u32(ring), bar_u = smem_u32(&bk_bar[wid][0]);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < STAGES; ++i) mbar_init(bar_u + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncwarp();
-  const uint64_t pol = l2_evict_first_policy();
-
-  const int64_t warp0 = (int64_t)blockIdx.x * WARPS + wid;
-  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
-  const int64_t n_a = rg.a1 - rg.a0;
-  const int64_t n_mine = n_a + (rg.b1 - rg.b0);
-  auto slice_of = [&](int64_t si) { return si < n_a ? rg.a0 + si : rg.b0 + (si - n_a); };
-
-  // ---- producer cursor (warp-uniform; only lane 0 issues) -----------------------------------------------------
-  int64_t p_si = warp0, p_vp = 0, pn_vp = 0;
-  int32_t p_W = 0, p_c = 0, pn_W = 0;
-  uint32_t p_k = 0, c_k = 0;
-  if (p_si < n_mine) { const int64_t s = slice_of(p_si); p_W = sl_w[s] & 0x7fffffff; p_vp = valptr[s]; }
-  if (p_si + nwarps < n_mine) { const int64_t s = slice_of(p_si + nwarps); pn_W = sl_w[s] & 0x7fffffff; pn_vp = valptr[s]; }
-  auto produce = [&]() {
-    while (p_si < n_mine && p_c >= p_W) {   // next slice (its header was requested one slice ago)
-      p_si += nwarps;
-      p_W = pn_W; p_vp = pn_vp; p_c = 0;
-      pn_W = 0;
-      if (p_si + nwarps < n_mine) { const int64_t s = slice_of(p_si + nwarps); pn_W = sl_w[s] & 0x7fffffff; pn_vp = valptr[s]; }
-    }
-    if (p_si >= n_mine) return;
-    const int32_t cols = min(BK_CH, p_W - p_c);
-    if (lane == 0) {
-      const uint32_t st = p_k % STAGES;
-      mbar_expect_tx(bar_u + 8 * st, (uint32_t)cols * 512u);
-      bulk_g2s(ring_u + st * (BK_CH * 512), val + p_vp + (int64_t)p_c * 64, (uint32_t)cols * 512u, bar_u + 8 * st, pol);
-    }
-    p_c += cols;
-    ++p_k;
-  };
-#pragma unroll 1
-  for (int i = 0; i < STAGES; ++i) produce();
-
-  double acc[NDOT > 0 ? NDOT : 1];
-#pragma unroll
-  for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
-  for (int64_t si = warp0; si < n_mine; si += nwarps) {
-    const int64_t s = slice_of(si);
-    const int32_t wenc = sl_w[s];
-    const int32_t W = wenc & 0x7fffffff;
-    const int64_t r0 = row0 + (s / NF) * (int64_t)64 * NF + (s % NF) + (int64_t)NF * (2 * lane);
-    const int64_t r1 = r0 + NF;
+    const int64_t r1 = r0 + NF;   // lane owns rows k = 2 lane and 2 lane + 1 of the slice: warp-contiguous x / y accesses
     const int32_t rr0 = (int32_t)r0, rr1 = (int32_t)r1;
     const int32_t *ip = idx + idxptr[s];
     double a0 = 0.0, a1 = 0.0;
-    for (int32_t c = 0; c < W; c += BK_CH) {
-      const int32_t cols = min(BK_CH, W - c);
-      double xa[BK_CH], xb[BK_CH];
+    for (int32_t jc = 0; jc < W; jc += 32) {
+      const int32_t nb = min(32, W - jc);
+      const int32_t nbt = (nb + SPMV_U - 1) / SPMV_U, bs = (nb + nbt - 1) / nbt;   // equal batches of <= SPMV_U columns
       if (wenc < 0) {
-        int32_t off[BK_CH];
+        const int32_t offl = __ldg(ip + jc + min(lane, nb - 1));
+        for (int32_t jb = 0; jb < nb; jb += bs) {
+          double2 v[SPMV_U];
+          double xa[SPMV_U], xb[SPMV_U];
 #pragma unroll
-        for (int u = 0; u < BK_CH; ++u) off[u] = __ldg(ip + min(c + u, W - 1));   // broadcast loads, independent
+          for (int u = 0; u < SPMV_U; ++u) {
+            v[u] = make_double2(0.0, 0.0);
+            if (u < bs && jb + u < nb) v[u] = SYM ? __ldg(vp + (size_t)(jc + jb + u) * 32) : __ldcs(vp + (size_t)(jc + jb + u) * 32);
+          }
 #pragma unroll
-        for (int u = 0; u < BK_CH; ++u) {
-          xa[u] = __ldg(x + min(max(rr0 + off[u], 0), n_cols - 1));
-          xb[u] = __ldg(x + min(max(rr1 + off[u], 0), n_cols - 1));
+          for (int u = 0; u < SPMV_U; ++u) {
+            const int32_t off = __shfl_sync(0xffffffffu, offl, (jb + u) & 31);
+            xa[u] = xb[u] = 0.0;
+            if (u < bs && jb + u < nb) {
+              xa[u] = __ldg(x + min(max(rr0 + off, 0), n_cols - 1));
+              xb[u] = __ldg(x + min(max(rr1 + off, 0), n_cols - 1));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < SPMV_U; ++u) { a0 += v[u].x * xa[u]; a1 += v[u].y * xb[u]; }
         }
       } else {
         const int2 *cp = reinterpret_cast<const int2 *>(ip) + lane;
-        int2 cc[BK_CH];
+        for (int32_t jb = 0; jb < nb; jb += bs) {
+          int2 c[SPMV_U];
+          double2 v[SPMV_U];
+          double xa[SPMV_U], xb[SPMV_U];
 #pragma unroll
-        for (int u = 0; u < BK_CH; ++u) cc[u] = __ldcs(cp + (size_t)min(c + u, W - 1) * 32);
+          for (int u = 0; u < SPMV_U; ++u) {
+            c[u] = make_int2(0, 0);
+            v[u] = make_double2(0.0, 0.0);
+            if (u < bs && jb + u < nb) {
+              c[u] = __ldcs(cp + (size_t)(jc + jb + u) * 32);
+              v[u] = __ldcs(vp + (size_t)(jc + jb + u) * 32);
+            }
+          }
 #pragma unroll
-        for (int u = 0; u < BK_CH; ++u) { xa[u] = __ldg(x + cc[u].x); xb[u] = __ldg(x + cc[u].y); }
-      }
-      const uint32_t st = c_k % STAGES, par = (c_k / STAGES) & 1u;
-      while (!mbar_try_wait(bar_u + 8 * st, par)) {}
-      const double2 *vb = reinterpret_cast<const double2 *>(ring + (size_t)st * BK_CH * 64) + lane;
+          for (int u = 0; u < SPMV_U; ++u) { xa[u] = __ldg(x + c[u].x); xb[u] = __ldg(x + c[u].y); }
 #pragma unroll
-      for (int u = 0; u < BK_CH; ++u)
-        if (u < cols) {
-          const double2 v = vb[u * 32];
-          a0 += v.x * xa[u];
-          a1 += v.y * xb[u];
+          for (int u = 0; u < SPMV_U; ++u) { a0 += v[u].x * xa[u]; a1 += v[u].y * xb[u]; }
         }
-      __syncwarp();   // every lane has consumed the stage: lane 0 may overwrite it
-      ++c_k;
-      produce();
+      }
+    }
+    if (SYM && M > 0) {
+      // mirror table behind the (16-byte padded) offsets: (offset, posA, posB, split); the value of local row k is
+      // val[(k < split ? posA : posB) + k]
+      const int4 *tab = reinterpret_cast<const int4 *>(ip + ((W + 3) & ~3));
+      const int k0 = 2 * lane, k1 = 2 * lane + 1;
+      for (int32_t jc = 0; jc < M; jc += 32) {
+        const int32_t nb = min(32, M - jc);
+        const int32_t nbt = (nb + SPMV_U - 1) / SPMV_U, bs = (nb + nbt - 1) / nbt;
+        const int4 tl = __ldg(tab + jc + min(lane, nb - 1));
+        for (int32_t jb = 0; jb < nb; jb += bs) {
+          double m0[SPMV_U], m1[SPMV_U], xa[SPMV_U], xb[SPMV_U];
+#pragma unroll
+          for (int u = 0; u < SPMV_U; ++u) {
+            const int src = (jb + u) & 31;
+            const int32_t off = __shfl_sync(0xffffffffu, tl.x, src);
+            const int32_t pA = __shfl_sync(0xffffffffu, tl.y, src);
+            const int32_t pB = __shfl_sync(0xffffffffu, tl.z, src);
+            const int32_t sp = __shfl_sync(0xffffffffu, tl.w, src);
+            m0[u] = m1[u] = xa[u] = xb[u] = 0.0;
+            if (u < bs && jb + u < nb) {
+              m0[u] = __ldg(val + ((k0 < sp ? pA : pB) + k0));
+              m1[u] = __ldg(val + ((k1 < sp ? pA : pB) + k1));
+              xa[u] = __ldg(x + min(max(rr0 + off, 0), n_cols - 1));
+              xb[u] = __ldg(x + min(max(rr1 + off, 0), n_cols - 1));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < SPMV_U; ++u) { a0 += m0[u] * xa[u]; a1 += m1[u] * xb[u]; }
+        }
+      }
     }
     if (r0 < row1) {
       y[r0] = a0;
@@ -833,21 +701,6 @@ static Comm comm_of(apdx_plan *pl) {
   return c;
 }
 
-// SpMV kernel variants (A/B switch APDX_SPMV = reg4 | reg9 | bulk8x6 | bulk16x3; the default is the measured winner)
-enum { SPMV_REG_4 = 0, SPMV_REG_9, SPMV_BULK_8x6, SPMV_BULK_16x3 };
-static int spmv_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("APDX_SPMV");
-    v = SPMV_REG_9;
-    if (e && !strcmp(e, "reg4")) v = SPMV_REG_4;
-    else if (e && !strcmp(e, "reg9")) v = SPMV_REG_9;
-    else if (e && !strcmp(e, "bulk8x6")) v = SPMV_BULK_8x6;
-    else if (e && !strcmp(e, "bulk16x3")) v = SPMV_BULK_16x3;
-  }
-  return v;
-}
-
 static unsigned spmv_grid(int64_t n_slices) {
   const int64_t warps_per_block = VEC_BLOCK / 32;
   int64_t nb = (n_slices + warps_per_block - 1) / warps_per_block;
@@ -871,37 +724,19 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
     else { rg = SliceRange{0, S.lo_end, S.hi_begin, S.n_slices, (int)g_int, (int)(g_int + g_bnd), 1}; grid = g_bnd; }
   }
   const int epoch = (NDOT > 0 && c.p2p && stage >= 0) ? ++pl->p2p.red_epoch : 0;
-  const int variant = spmv_variant();
 #define APDX_SPMV_ARGS                                                                                                 \
-  S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free,        \
-      k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,                                        \
+  S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices,                   \
+      (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,                   \
       (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch, rg
-#define APDX_SPMV_BULK(NFV, WARPS, STAGES)                                                                             \
-  do {                                                                                                                 \
-    constexpr int smem = WARPS * STAGES * BK_CH * 512;                                                                 \
-    static bool attr_set = false;                                                                                      \
-    if (!attr_set) {                                                                                                   \
-      APDX_CUDA(cudaFuncSetAttribute(k_spmv_sell_bulk<NDOT, NFV, WARPS, STAGES>,                                       \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                              \
-      attr_set = true;                                                                                                 \
-    }                                                                                                                  \
-    if (part == 0) grid = (unsigned)std::min<int64_t>(148, (S.n_slices + WARPS - 1) / WARPS);                          \
-    else grid = std::min(grid, 148u);                                                                                  \
-    if (grid == 0) grid = 1;                                                                                           \
-    k_spmv_sell_bulk<NDOT, NFV, WARPS, STAGES><<<grid, WARPS * 32, smem, pl->stream>>>(APDX_SPMV_ARGS);                \
-  } while (0)
 #define APDX_SPMV_NF(NFV)                                                                                              \
   do {                                                                                                                 \
-    if (variant == SPMV_BULK_8x6) APDX_SPMV_BULK(NFV, 8, 6);                                                           \
-    else if (variant == SPMV_BULK_16x3) APDX_SPMV_BULK(NFV, 16, 3);                                                    \
-    else if (variant == SPMV_REG_4) k_spmv_sell<NDOT, NFV, 4><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);     \
-    else k_spmv_sell<NDOT, NFV, 9><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                                \
+    if (S.sym && S.n_mirrored > 0) k_spmv_sell<NDOT, NFV, true><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);   \
+    else k_spmv_sell<NDOT, NFV, false><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                            \
   } while (0)
   if (S.nf == 1) APDX_SPMV_NF(1);
   else if (S.nf == 2) APDX_SPMV_NF(2);
   else APDX_SPMV_NF(3);
 #undef APDX_SPMV_NF
-#undef APDX_SPMV_BULK
 #undef APDX_SPMV_ARGS
   pl->stats.spmv_launches += 1;
   pl->stats.kernel_launches += 1;
@@ -1105,10 +940,13 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
           unsigned grid = (unsigned)(nb < 148ll * 32 ? (nb > 0 ? nb : 1) : 148ll * 32);
           const int e1 = ++P.red_epoch;
           // (the opt-in p2p-fused CG is only wired for scalar problems)
-          k_spmv_sell<1, 1, 9><<<grid, VEC_BLOCK, 0, s>>>(S.sl_w.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p,
-                                                       pl->f0, pl->f1, S.n_slices, (int32_t)pl->n_free, k.partial.p, k.ticket.p,
-                                                       k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he,
-                                                       SliceRange{0, S.n_slices, 0, 0, 0, -1, 1});
+#define APDX_PF_ARGS                                                                                                   \
+  S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p, pl->f0, pl->f1, S.n_slices,       \
+      (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he, \
+      SliceRange{0, S.n_slices, 0, 0, 0, -1, 1}
+          if (S.sym && S.n_mirrored > 0) k_spmv_sell<1, 1, true><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
+          else k_spmv_sell<1, 1, false><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
+#undef APDX_PF_ARGS
           TR(1);
           pl->stats.spmv_launches += 1;
           StageCtx c1{k.st_sc.p + par * S_COUNT, k.st_sc.p + (par ^ 1) * S_COUNT, k.st_fl.p + par * F_COUNT,

@@ -184,6 +184,12 @@ int apdx_newton(apdx_plan *plan, const apdx_krylov_opts *opts, double *dofs_d,
  * out[7]=bytes of the sliced-ELL matrix the SpMV streams (values + compressed indices)    */
 int apdx_plan_stats(const apdx_plan *plan, double out[8]);
 
+/* layout of the sliced-ELL copy of the reduced matrix (built by the first assembly that needs it):
+ * out[0]=slices out[1]=stored values (incl. padding) out[2]=index ints (offsets, mirror tables, explicit columns)
+ * out[3]=entries read from their transposed position instead of being stored (symmetric storage; 0 with
+ * APDX_SELL_SYM=0) out[4]=1 if symmetric storage is enabled out[5]=dofs per node the slices interleave */
+int apdx_plan_sell_info(const apdx_plan *plan, int64_t out[6]);
+
 /* average device time (ms, CUDA events on the plan's stream) of `reps` launches of the SpMV kernel
  * exactly as the CG loop launches it (fused p.Ap dot product included) */
 int apdx_time_spmv(apdx_plan *plan, int32_t reps, double *ms_avg);
