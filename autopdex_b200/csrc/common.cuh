@@ -146,6 +146,8 @@ struct KrylovGraph {
   double kernel_launches = 0, spmv_launches = 0;
 };
 
+constexpr int32_t SELL_MB7 = 1 << 30;   // Sell::sl_m flag: mirror table padded to a multiple of 7 entries (else 8)
+
 // sliced-ELL copy of the owned rows of the reduced system (sell.cu)
 struct Sell {
   bool built = false;
@@ -154,7 +156,7 @@ struct Sell {
   int nf = 1;                 // slices interleave the nf dofs per node (sell.cu)
   int64_t lo_end = 0, hi_begin = 0;  // slices [lo_end, hi_begin) reference no ghost column (multi-GPU overlap)
   DevBuf<int32_t> sl_w;       // [n_slices] stored width | (offset mode ? 1<<31 : 0)
-  DevBuf<int32_t> sl_m;       // [n_slices] number of mirrored lower columns (table behind the slice's offsets)
+  DevBuf<int32_t> sl_m;       // [n_slices] padded number of mirrored lower columns | SELL_MB7 (table behind the offsets)
   DevBuf<int64_t> valptr;     // [n_slices+1] start of the slice's value block (doubles)
   DevBuf<int64_t> idxptr;     // [n_slices+1] start of the slice's index block (int32)
   DevBuf<double> val;         // [n_val + 64] column-major per slice, then 64 zeros

@@ -255,12 +255,43 @@ struct SliceRange {
 
 // Loads are issued in batches of up to SPMV_U slice columns before the first FMA.  The warp issues in order, so a
 // loop that alternates load / FMA keeps only one 512-byte value row in flight per warp (measured: 62 % of the DRAM
-// peak, long-scoreboard bound; batching: 96 % of the measured copy bandwidth).  A slice's columns are taken in chunks of
-// 32 (lane u holds the offset / mirror-table entry of column u of the chunk, handed out by shuffles: no dependent
-// broadcast load per column) and every chunk in equal batches of at most SPMV_U columns.
-// SYM: lower columns of offset-mode slices are read from their transposed position (sell.cu); the value stream then
-// uses the default L2 policy (the partner slices re-read it from the L2 a few MB later) instead of evict-first.
+// peak, long-scoreboard bound; batching: 96 % of the measured copy bandwidth).  A slice's stored columns are taken in
+// chunks of 32 (lane u holds the offset of column u of the chunk, handed out by shuffles: no dependent broadcast load
+// per column) and every chunk in equal batches of at most SPMV_U columns.
+//
+// SYM: lower columns of offset-mode slices are read from their transposed position (sell.cu): the mirror table
+// (offset, posA, posB, split) is padded to full batches of MB = 7 or 8 entries, read with warp-uniform 16-byte loads
+// (its cache lines are prefetched into the L1 while the stored columns stream), and the value of local row k is
+// val[(k < split ? posA : posB) + k].  The value stream then uses the default L2 policy instead of evict-first: the
+// partner slices re-read it from the L2 a few MB later.
+//
+// Work distribution: block b owns the consecutive slices [b * spb, (b + 1) * spb), warp w takes slices w, w + 8, ...
+// of them.  Blocks are dispatched in index order, so the slices in flight form one narrow window that moves through
+// the matrix: the x entries and the mirrored values a slice needs were touched moments ago by its neighbours and are
+// L2 hits.  (A grid-stride loop keeps ~7 distant fronts alive; 30 % of the mirrored reads then missed the L2.)
 constexpr int SPMV_U = 9;
+
+template <int MB>
+__device__ __forceinline__ void spmv_mirrored(const int4 *__restrict__ tab, int32_t M, const double *__restrict__ val,
+                                              const double *__restrict__ x, int lane, int32_t rr0, int32_t rr1,
+                                              int32_t n_cols, double &a0, double &a1) {
+  const int k0 = 2 * lane, k1 = 2 * lane + 1;
+  for (int32_t jb = 0; jb < M; jb += MB) {
+    int4 t[MB];
+#pragma unroll
+    for (int u = 0; u < MB; ++u) t[u] = __ldg(tab + jb + u);   // same address in every lane: one broadcast transaction
+    double m0[MB], m1[MB], xa[MB], xb[MB];
+#pragma unroll
+    for (int u = 0; u < MB; ++u) {
+      m0[u] = __ldg(val + ((k0 < t[u].w ? t[u].y : t[u].z) + k0));
+      m1[u] = __ldg(val + ((k1 < t[u].w ? t[u].y : t[u].z) + k1));
+      xa[u] = __ldg(x + min(max(rr0 + t[u].x, 0), n_cols - 1));
+      xb[u] = __ldg(x + min(max(rr1 + t[u].x, 0), n_cols - 1));
+    }
+#pragma unroll
+    for (int u = 0; u < MB; ++u) { a0 += m0[u] * xa[u]; a1 += m1[u] * xb[u]; }
+  }
+}
 
 template <int NDOT, int NF, bool SYM>
 __global__ void __launch_bounds__(VEC_BLOCK, 2)
@@ -269,7 +300,7 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, int64_t row0,
                 int64_t row1, int64_t n_slices, int32_t n_cols, double *partial, unsigned int *ticket, double *sc,
                 int32_t *fl, int stage, int fused, int check_done, const P2PDev *pd, int epoch, int halo_epoch,
-                SliceRange rg) {
+                SliceRange rg, int spb) {
   if (check_done && fl[F_DONE]) return;
   if (pd && halo_epoch > 0) {
     // ghost entries of x are written by the neighbours' k_halo_push over NVLink: wait for this epoch's flags
@@ -280,30 +311,56 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int WPB = VEC_BLOCK / 32;
   double acc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
   for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
   // rg: this launch covers slices [a0,a1) and [b0,b1) (interior launch: one range; boundary launch: the two ends)
   const int64_t n_mine = (rg.a1 - rg.a0) + (rg.b1 - rg.b0);
-  for (int64_t si = warp0; si < n_mine; si += nwarps) {
+  const int64_t si_begin = (int64_t)blockIdx.x * spb + (threadIdx.x >> 5);
+  const int64_t si_end = min((int64_t)(blockIdx.x + 1) * spb, n_mine);
+  // The per-slice metadata is a chain of dependent loads (header -> offsets -> x gathers): the header of the warp's
+  // NEXT slice is requested before the current slice is processed, its first 32 offsets half-way through.
+  struct Hdr { int32_t wenc, M; int64_t vp, ip; };
+  auto load_hdr = [&](int64_t si, Hdr &h) {
+    h.wenc = 0; h.M = 0; h.vp = 0; h.ip = 0;
+    if (si < si_end) {
+      const int64_t s = si < rg.a1 - rg.a0 ? rg.a0 + si : rg.b0 + (si - (rg.a1 - rg.a0));
+      h.wenc = sl_w[s];
+      if (SYM) h.M = sl_m[s];
+      h.vp = valptr[s];
+      h.ip = idxptr[s];
+    }
+  };
+  auto load_offsets = [&](const Hdr &h) -> int32_t {
+    const int32_t W = h.wenc & 0x7fffffff;
+    return (h.wenc < 0 && W > 0) ? __ldg(idx + h.ip + min(lane, min(32, W) - 1)) : 0;
+  };
+  Hdr cur;
+  load_hdr(si_begin, cur);
+  int32_t offl0 = load_offsets(cur);
+  for (int64_t si = si_begin; si < si_end; si += WPB) {
+    Hdr nxt;
+    load_hdr(si + WPB, nxt);
     const int64_t s = si < rg.a1 - rg.a0 ? rg.a0 + si : rg.b0 + (si - (rg.a1 - rg.a0));
-    const int32_t wenc = sl_w[s];
+    const int32_t wenc = cur.wenc;
     const int32_t W = wenc & 0x7fffffff;
-    const int32_t M = SYM ? sl_m[s] : 0;
-    const double2 *vp = reinterpret_cast<const double2 *>(val + valptr[s]) + lane;
+    const int32_t M = SYM ? (cur.M & ~SELL_MB7) : 0;
+    const double2 *vp = reinterpret_cast<const double2 *>(val + cur.vp) + lane;
     // rows of the slice: one field component of 64 consecutive nodes (sell.cu), two rows per lane
     const int64_t r0 = row0 + (s / NF) * (int64_t)64 * NF + (s % NF) + (int64_t)NF * (2 * lane);
     const int64_t r1 = r0 + NF;   // lane owns rows k = 2 lane and 2 lane + 1 of the slice: warp-contiguous x / y accesses
     const int32_t rr0 = (int32_t)r0, rr1 = (int32_t)r1;
-    const int32_t *ip = idx + idxptr[s];
+    const int32_t *ip = idx + cur.ip;
+    const int4 *tab = reinterpret_cast<const int4 *>(ip + ((W + 3) & ~3));
+    if (SYM && lane * 8 < M)   // one lane per 128-byte line of the mirror table
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(tab + lane * 8));
     double a0 = 0.0, a1 = 0.0;
     for (int32_t jc = 0; jc < W; jc += 32) {
       const int32_t nb = min(32, W - jc);
       const int32_t nbt = (nb + SPMV_U - 1) / SPMV_U, bs = (nb + nbt - 1) / nbt;   // equal batches of <= SPMV_U columns
       if (wenc < 0) {
-        const int32_t offl = __ldg(ip + jc + min(lane, nb - 1));
+        const int32_t offl = jc == 0 ? offl0 : __ldg(ip + jc + min(lane, nb - 1));
         for (int32_t jb = 0; jb < nb; jb += bs) {
           double2 v[SPMV_U];
           double xa[SPMV_U], xb[SPMV_U];
@@ -346,37 +403,14 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
         }
       }
     }
+    // the next slice's header has arrived by now: request its offsets
+    const int32_t offl_n = load_offsets(nxt);
     if (SYM && M > 0) {
-      // mirror table behind the (16-byte padded) offsets: (offset, posA, posB, split); the value of local row k is
-      // val[(k < split ? posA : posB) + k]
-      const int4 *tab = reinterpret_cast<const int4 *>(ip + ((W + 3) & ~3));
-      const int k0 = 2 * lane, k1 = 2 * lane + 1;
-      for (int32_t jc = 0; jc < M; jc += 32) {
-        const int32_t nb = min(32, M - jc);
-        const int32_t nbt = (nb + SPMV_U - 1) / SPMV_U, bs = (nb + nbt - 1) / nbt;
-        const int4 tl = __ldg(tab + jc + min(lane, nb - 1));
-        for (int32_t jb = 0; jb < nb; jb += bs) {
-          double m0[SPMV_U], m1[SPMV_U], xa[SPMV_U], xb[SPMV_U];
-#pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) {
-            const int src = (jb + u) & 31;
-            const int32_t off = __shfl_sync(0xffffffffu, tl.x, src);
-            const int32_t pA = __shfl_sync(0xffffffffu, tl.y, src);
-            const int32_t pB = __shfl_sync(0xffffffffu, tl.z, src);
-            const int32_t sp = __shfl_sync(0xffffffffu, tl.w, src);
-            m0[u] = m1[u] = xa[u] = xb[u] = 0.0;
-            if (u < bs && jb + u < nb) {
-              m0[u] = __ldg(val + ((k0 < sp ? pA : pB) + k0));
-              m1[u] = __ldg(val + ((k1 < sp ? pA : pB) + k1));
-              xa[u] = __ldg(x + min(max(rr0 + off, 0), n_cols - 1));
-              xb[u] = __ldg(x + min(max(rr1 + off, 0), n_cols - 1));
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) { a0 += m0[u] * xa[u]; a1 += m1[u] * xb[u]; }
-        }
-      }
+      if (cur.M & SELL_MB7) spmv_mirrored<7>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
+      else spmv_mirrored<8>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
     }
+    cur = nxt;
+    offl0 = offl_n;
     if (r0 < row1) {
       y[r0] = a0;
       if (NDOT >= 1) acc[0] += w[r0] * a0;
@@ -658,7 +692,11 @@ int krylov_alloc(apdx_plan *pl) {
     APDX_CHECK(k.s.alloc(n));
     APDX_CUDA(cudaMemsetAsync(k.z.p, 0, n * sizeof(double), pl->stream));
   }
-  APDX_CHECK(k.partial.alloc(4 * 2 * (size_t)(VEC_GRID > 148 * 32 ? VEC_GRID : 148 * 32)));   // x2: interior + boundary launches
+  {  // per-block partial sums of the fused dot products: up to 4 sums, SpMV grids of the interior + boundary launches
+    const int64_t rows = pl->n_free;   // >= the owned rows of any later partition
+    const size_t spmv_blocks = (size_t)(rows / (64 * 8) + 2 * pl->nf + 4);   // >= slices / 8 (smallest spb), + slack
+    APDX_CHECK(k.partial.alloc(4 * 2 * std::max((size_t)VEC_GRID, spmv_blocks)));
+  }
   APDX_CHECK(k.st_sc.alloc(2 * S_COUNT));
   APDX_CHECK(k.st_fl.alloc(2 * F_COUNT));
   APDX_CHECK(k.scratch.alloc(S_COUNT));
@@ -701,11 +739,21 @@ static Comm comm_of(apdx_plan *pl) {
   return c;
 }
 
+// slices per block of the SpMV (8 warps: spb / 8 slices per warp).  The blocks in flight (2 per SM) cover
+// 296 * spb consecutive slices; 16 keeps that window at ~34 MB of values on one B200 while giving every warp a second
+// slice to prefetch metadata for.  APDX_SPMV_SPB overrides (multiples of 8) for measurements.
+static int spmv_spb() {
+  static int v = 0;
+  if (!v) {
+    const char *e = getenv("APDX_SPMV_SPB");
+    v = e ? atoi(e) : 16;
+    if (v < 8 || v % 8) v = 16;
+  }
+  return v;
+}
 static unsigned spmv_grid(int64_t n_slices) {
-  const int64_t warps_per_block = VEC_BLOCK / 32;
-  int64_t nb = (n_slices + warps_per_block - 1) / warps_per_block;
-  const int64_t cap = 148ll * 32;
-  return (unsigned)(nb < cap ? (nb > 0 ? nb : 1) : cap);
+  const int64_t nb = (n_slices + spmv_spb() - 1) / spmv_spb();
+  return (unsigned)(nb > 0 ? nb : 1);
 }
 
 // part: 0 = all slices in one launch; 1 = interior slices only (deposits its dot partials); 2 = the boundary slices
@@ -727,7 +775,7 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
 #define APDX_SPMV_ARGS                                                                                                 \
   S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices,                   \
       (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,                   \
-      (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch, rg
+      (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch, rg, spmv_spb()
 #define APDX_SPMV_NF(NFV)                                                                                              \
   do {                                                                                                                 \
     if (S.sym && S.n_mirrored > 0) k_spmv_sell<NDOT, NFV, true><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);   \
@@ -935,15 +983,13 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
         {
           // SpMV posts (p.q) with epoch e1; it reads the done flag of the current state half
           Sell &S = pl->sell;
-          const int64_t wpb = VEC_BLOCK / 32;
-          int64_t nb = (S.n_slices + wpb - 1) / wpb;
-          unsigned grid = (unsigned)(nb < 148ll * 32 ? (nb > 0 ? nb : 1) : 148ll * 32);
+          const unsigned grid = spmv_grid(S.n_slices);
           const int e1 = ++P.red_epoch;
           // (the opt-in p2p-fused CG is only wired for scalar problems)
 #define APDX_PF_ARGS                                                                                                   \
   S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p, pl->f0, pl->f1, S.n_slices,       \
       (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he, \
-      SliceRange{0, S.n_slices, 0, 0, 0, -1, 1}
+      SliceRange{0, S.n_slices, 0, 0, 0, -1, 1}, spmv_spb()
           if (S.sym && S.n_mirrored > 0) k_spmv_sell<1, 1, true><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
           else k_spmv_sell<1, 1, false><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
 #undef APDX_PF_ARGS

@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(256) k_sell_layout(const int32_t *__restrict__
                                                      int32_t *__restrict__ sz_val, int32_t *__restrict__ sz_idx,
                                                      const int64_t *__restrict__ valptr, const int64_t *__restrict__ idxptr,
                                                      int32_t *__restrict__ sell_idx, int32_t *__restrict__ sell_src,
-                                                     int32_t *__restrict__ sell_diag, uint8_t *__restrict__ ghost) {
+                                                     int32_t *__restrict__ sell_diag, uint8_t *__restrict__ ghost,
+                                                     int64_t zero_base, unsigned long long *__restrict__ n_mirrored) {
   const int lane = threadIdx.x & 31;
   const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (s >= G.n_slices) return;
@@ -217,16 +218,27 @@ __global__ void __launch_bounds__(256) k_sell_layout(const int32_t *__restrict__
     if (has[0]) ++p[0];
     if (has[1]) ++p[1];
   }
+  // the mirror table is padded to a multiple of the SpMV's mirrored batch (7 or 8 columns, whichever pads less;
+  // bit 30 of sl_m = batch of 7) with entries that point at the block of zeros, so that the kernel's inner loop
+  // has a compile-time trip count and no predicates
+  const int32_t pad7 = (nM + 6) / 7 * 7, pad8 = (nM + 7) / 8 * 8;
+  const int32_t m_pad = pad7 < pad8 ? pad7 : pad8;
   if (PASS == 0 && lane == 0) {
     const int32_t w = nU + nL;
     sl_w[s] = w | (int32_t)0x80000000;
-    sl_m[s] = nM;
+    sl_m[s] = m_pad | (pad7 < pad8 ? SELL_MB7 : 0);
     sl_u[s] = nU;
     sz_val[s] = w * SELL_C;
-    sz_idx[s] = ((w + 3) & ~3) + 4 * nM;   // offsets padded to 16 bytes, then the mirror table (int4 entries)
+    sz_idx[s] = ((w + 3) & ~3) + 4 * m_pad;   // offsets padded to 16 bytes, then the mirror table (int4 entries)
+    if (nM > 0) atomicAdd(n_mirrored, (unsigned long long)nM * SELL_C);
   }
-  if (PASS == 1 && lane == 0)
+  if (PASS == 1 && lane == 0) {
     for (int32_t j = w_tot; j < w_al; ++j) sell_idx[ip + j] = 0;
+    for (int32_t i = nM; i < m_pad; ++i) {
+      int32_t *tab = sell_idx + ip + w_al + 4 * (int64_t)i;
+      tab[0] = 0; tab[1] = (int32_t)zero_base; tab[2] = (int32_t)zero_base; tab[3] = SELL_C;
+    }
+  }
 }
 
 // pass D: positions of the mirrored columns.  One thread per slice.
@@ -237,13 +249,14 @@ __global__ void __launch_bounds__(256) k_sell_mirror(SliceGeo G, const uint8_t *
                                                      int64_t zero_base) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= G.n_slices) return;
-  const int32_t M = sl_m[s];
+  const int32_t M = sl_m[s] & ~SELL_MB7;
   if (M == 0) return;
   const int32_t w_al = ((sl_w[s] & 0x7fffffff) + 3) & ~3;
   int32_t *tab = sell_idx + idxptr[s] + w_al;
   const int64_t n_blocks = G.n_slices / G.nf;
   for (int32_t i = 0; i < M; ++i) {
     const int32_t d = -tab[4 * i];
+    if (d == 0) break;                                         // padding entries (already complete)
     // partner of local row k: owned-row index t_k = t0 + nf k, t0 = row(s,0) - d - row0 (may be negative)
     const int64_t t0 = G.row(s, 0) - d - G.row0;
     int64_t cp = t0 % G.nf; if (cp < 0) cp += G.nf;            // field component of the partner rows
@@ -333,11 +346,14 @@ int sell_build(apdx_plan *pl) {
   APDX_CHECK(szi.alloc(ns + 1));
   APDX_CUDA(cudaMemsetAsync(szv.p, 0, (ns + 1) * sizeof(int32_t), s));
   APDX_CUDA(cudaMemsetAsync(szi.p, 0, (ns + 1) * sizeof(int32_t), s));
+  DevBuf<unsigned long long> n_mir;
+  APDX_CHECK(n_mir.alloc(1));
+  APDX_CUDA(cudaMemsetAsync(n_mir.p, 0, sizeof(unsigned long long), s));
   const unsigned grid = (unsigned)((ns * 32 + 255) / 256);
   k_sell_mode<<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, G, sl_mode.p);
   k_sell_layout<0><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, G, S.sym ? 1 : 0, sl_mode.p,
                                         S.sl_w.p, S.sl_m.p, sl_u.p, szv.p, szi.p, nullptr, nullptr, nullptr, nullptr,
-                                        nullptr, nullptr);
+                                        nullptr, nullptr, 0, n_mir.p);
   APDX_CHECK(scan64(szv.p, S.valptr.p, ns + 1, s));
   APDX_CHECK(scan64(szi.p, S.idxptr.p, ns + 1, s));
   int64_t tot[2];
@@ -352,17 +368,15 @@ int sell_build(apdx_plan *pl) {
   APDX_CHECK(S.idx.alloc(S.n_idx > 0 ? S.n_idx : 1));
   k_sell_layout<1><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, G, S.sym ? 1 : 0, sl_mode.p,
                                         S.sl_w.p, S.sl_m.p, sl_u.p, nullptr, nullptr, S.valptr.p, S.idxptr.p, S.idx.p,
-                                        S.src.p, S.diag.p, ghost.p);
+                                        S.src.p, S.diag.p, ghost.p, S.n_val, n_mir.p);
   if (S.sym && ns > 0)
     k_sell_mirror<<<(unsigned)((ns + 255) / 256), 256, 0, s>>>(G, sl_mode.p, S.sl_w.p, S.sl_m.p, sl_u.p, S.valptr.p,
                                                                S.idxptr.p, S.idx.p, S.n_val);
   APDX_CUDA(cudaStreamSynchronize(s));
-  {
-    // number of mirrored columns (diagnostics: apdx_plan_stats, tests)
-    std::vector<int32_t> mh((size_t)ns);
-    APDX_CUDA(cudaMemcpy(mh.data(), S.sl_m.p, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    S.n_mirrored = 0;
-    for (int64_t q = 0; q < ns; ++q) S.n_mirrored += (int64_t)mh[q] * SELL_C;
+  {  // entries read from their transposed position (diagnostics: apdx_plan_sell_info, tests)
+    unsigned long long nm = 0;
+    APDX_CUDA(cudaMemcpy(&nm, n_mir.p, sizeof(nm), cudaMemcpyDeviceToHost));
+    S.n_mirrored = (int64_t)nm;
   }
   {  // leading / trailing runs of slices that touch ghost columns; everything in between is "interior"
     std::vector<uint8_t> gh((size_t)ns);

@@ -20,8 +20,8 @@ def _plan(p, sym):
         from autopdex_b200 import backend
         plan = gpu_util.make_plan(p)
         n = p["mask"].size
-        dofs = np.random.default_rng(3).uniform(-1e-2, 1e-2, n)
-        d, r = backend.DeviceArray.from_host(dofs), backend.DeviceArray(n)
+        dofs = np.random.default_rng(3).uniform(-1e-2, 1e-2, p["mask"].shape)
+        d, r = backend.DeviceArray.from_host(dofs.ravel()), backend.DeviceArray(n)
         plan.assemble(d, True, r)
     finally:
         if old is None:
