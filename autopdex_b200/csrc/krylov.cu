@@ -6,7 +6,7 @@
 // jax.scipy.sparse.linalg: ||r||_2^2 <= max(rtol^2 ||b||^2, atol^2).  No positivity checks:
 // the reference's tangents are negative definite on mesher quad meshes.
 //
-// SpMV: sliced-ELL with per-slice compressed column indices (sell.cu), 128-bit value loads, the dot
+// SpMV: sliced-ELL with per-slice compressed column indices (sell.cu), warp-contiguous value loads, the dot
 // product(s) that follow the SpMV fused into the same kernel (warp-shuffle + fixed-order block reduction).  Vector updates are
 // fused axpy+dot kernels.  Dot products are reduced per block, then by the last block in a fixed
 // order (deterministic for a given grid), then -- multi-GPU -- by ncclAllReduce.
@@ -244,9 +244,9 @@ __device__ __forceinline__ void reduce_finalize(double (&v)[NV], double *partial
   }
 }
 
-// Sliced-ELL SpMV (layout: sell.cu).  One warp per slice of 64 rows, two rows per lane, values read as
-// 128-bit double2 (512 contiguous bytes per warp instruction).  Offset mode: column = row + off[j]
-// (one broadcast int per slice column, x gathers coalesced); explicit mode: int2 column pairs.
+// Sliced-ELL SpMV (layout: sell.cu).  One warp per slice of 64 rows; lane owns the local rows lane and lane + 32, so
+// each load instruction of the warp covers 256 contiguous bytes.  Offset mode: column = row + off[j] (offsets held one
+// per lane, x gathers coalesced); explicit mode: one int32 column per stored entry.
 // n_cols: length of x (clamp target of the padded offsets, whose values are exact zeros).
 struct SliceRange {
   int64_t a0, a1, b0, b1;
@@ -275,7 +275,7 @@ template <int MB>
 __device__ __forceinline__ void spmv_mirrored(const int4 *__restrict__ tab, int32_t M, const double *__restrict__ val,
                                               const double *__restrict__ x, int lane, int32_t rr0, int32_t rr1,
                                               int32_t n_cols, double &a0, double &a1) {
-  const int k0 = 2 * lane, k1 = 2 * lane + 1;
+  const int k0 = lane, k1 = lane + 32;
   for (int32_t jb = 0; jb < M; jb += MB) {
     int4 t[MB];
 #pragma unroll
@@ -346,10 +346,12 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     const int32_t wenc = cur.wenc;
     const int32_t W = wenc & 0x7fffffff;
     const int32_t M = SYM ? (cur.M & ~SELL_MB7) : 0;
-    const double2 *vp = reinterpret_cast<const double2 *>(val + cur.vp) + lane;
-    // rows of the slice: one field component of 64 consecutive nodes (sell.cu), two rows per lane
-    const int64_t r0 = row0 + (s / NF) * (int64_t)64 * NF + (s % NF) + (int64_t)NF * (2 * lane);
-    const int64_t r1 = r0 + NF;   // lane owns rows k = 2 lane and 2 lane + 1 of the slice: warp-contiguous x / y accesses
+    const double *vp = val + cur.vp + lane;
+    // rows of the slice: one field component of 64 consecutive nodes (sell.cu); lane owns local rows k = lane and
+    // lane + 32, so that every x gather, value load and y store of the warp covers one contiguous run of 32 entries
+    // (half the L1 tag traffic of an interleaved (2 lane, 2 lane + 1) ownership, which bounded the kernel)
+    const int64_t r0 = row0 + (s / NF) * (int64_t)64 * NF + (s % NF) + (int64_t)NF * lane;
+    const int64_t r1 = r0 + (int64_t)32 * NF;
     const int32_t rr0 = (int32_t)r0, rr1 = (int32_t)r1;
     const int32_t *ip = idx + cur.ip;
     const int4 *tab = reinterpret_cast<const int4 *>(ip + ((W + 3) & ~3));
@@ -362,12 +364,15 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
       if (wenc < 0) {
         const int32_t offl = jc == 0 ? offl0 : __ldg(ip + jc + min(lane, nb - 1));
         for (int32_t jb = 0; jb < nb; jb += bs) {
-          double2 v[SPMV_U];
-          double xa[SPMV_U], xb[SPMV_U];
+          double va[SPMV_U], vb[SPMV_U], xa[SPMV_U], xb[SPMV_U];
 #pragma unroll
           for (int u = 0; u < SPMV_U; ++u) {
-            v[u] = make_double2(0.0, 0.0);
-            if (u < bs && jb + u < nb) v[u] = SYM ? __ldg(vp + (size_t)(jc + jb + u) * 32) : __ldcs(vp + (size_t)(jc + jb + u) * 32);
+            va[u] = vb[u] = 0.0;
+            if (u < bs && jb + u < nb) {
+              const double *q = vp + (size_t)(jc + jb + u) * 64;
+              va[u] = SYM ? __ldg(q) : __ldcs(q);
+              vb[u] = SYM ? __ldg(q + 32) : __ldcs(q + 32);
+            }
           }
 #pragma unroll
           for (int u = 0; u < SPMV_U; ++u) {
@@ -379,27 +384,27 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
             }
           }
 #pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) { a0 += v[u].x * xa[u]; a1 += v[u].y * xb[u]; }
+          for (int u = 0; u < SPMV_U; ++u) { a0 += va[u] * xa[u]; a1 += vb[u] * xb[u]; }
         }
       } else {
-        const int2 *cp = reinterpret_cast<const int2 *>(ip) + lane;
+        const int32_t *cp = ip + lane;
         for (int32_t jb = 0; jb < nb; jb += bs) {
-          int2 c[SPMV_U];
-          double2 v[SPMV_U];
-          double xa[SPMV_U], xb[SPMV_U];
+          int32_t ca[SPMV_U], cb[SPMV_U];
+          double va[SPMV_U], vb[SPMV_U], xa[SPMV_U], xb[SPMV_U];
 #pragma unroll
           for (int u = 0; u < SPMV_U; ++u) {
-            c[u] = make_int2(0, 0);
-            v[u] = make_double2(0.0, 0.0);
+            ca[u] = cb[u] = 0;
+            va[u] = vb[u] = 0.0;
             if (u < bs && jb + u < nb) {
-              c[u] = __ldcs(cp + (size_t)(jc + jb + u) * 32);
-              v[u] = __ldcs(vp + (size_t)(jc + jb + u) * 32);
+              const size_t o = (size_t)(jc + jb + u) * 64;
+              ca[u] = __ldcs(cp + o); cb[u] = __ldcs(cp + o + 32);
+              va[u] = __ldcs(vp + o); vb[u] = __ldcs(vp + o + 32);
             }
           }
 #pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) { xa[u] = __ldg(x + c[u].x); xb[u] = __ldg(x + c[u].y); }
+          for (int u = 0; u < SPMV_U; ++u) { xa[u] = __ldg(x + ca[u]); xb[u] = __ldg(x + cb[u]); }
 #pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) { a0 += v[u].x * xa[u]; a1 += v[u].y * xb[u]; }
+          for (int u = 0; u < SPMV_U; ++u) { a0 += va[u] * xa[u]; a1 += vb[u] * xb[u]; }
         }
       }
     }
