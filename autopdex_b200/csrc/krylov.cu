@@ -265,10 +265,12 @@ struct SliceRange {
 // val[(k < split ? posA : posB) + k].  The value stream then uses the default L2 policy instead of evict-first: the
 // partner slices re-read it from the L2 a few MB later.
 //
-// Work distribution: block b owns the consecutive slices [b * spb, (b + 1) * spb), warp w takes slices w, w + 8, ...
-// of them.  Blocks are dispatched in index order, so the slices in flight form one narrow window that moves through
-// the matrix: the x entries and the mirrored values a slice needs were touched moments ago by its neighbours and are
-// L2 hits.  (A grid-stride loop keeps ~7 distant fronts alive; 30 % of the mirrored reads then missed the L2.)
+// Work distribution: a persistent grid of exactly the resident blocks (SMs x blocks per SM), slices strided over all
+// its warps.  At any time the slices in flight form one narrow window (~2400 slices) that moves through the matrix:
+// the x entries and the mirrored values a slice needs were touched moments ago by its neighbours and are L2 hits, and
+// every warp has ~100 slices over which the metadata prefetch and the block-level reduction are amortised.
+// (A larger grid-stride grid keeps several distant fronts alive -- 30 % of the mirrored reads then missed the L2 --
+// and one block per 8..32 consecutive slices pays the start-up latency chain per block: 0.83 / 0.69 / 0.64 ms.)
 constexpr int SPMV_U = 9;
 
 template <int MB>
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, int64_t row0,
                 int64_t row1, int64_t n_slices, int32_t n_cols, double *partial, unsigned int *ticket, double *sc,
                 int32_t *fl, int stage, int fused, int check_done, const P2PDev *pd, int epoch, int halo_epoch,
-                SliceRange rg, int spb) {
+                SliceRange rg) {
   if (check_done && fl[F_DONE]) return;
   if (pd && halo_epoch > 0) {
     // ghost entries of x are written by the neighbours' k_halo_push over NVLink: wait for this epoch's flags
@@ -317,8 +319,9 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
   for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
   // rg: this launch covers slices [a0,a1) and [b0,b1) (interior launch: one range; boundary launch: the two ends)
   const int64_t n_mine = (rg.a1 - rg.a0) + (rg.b1 - rg.b0);
-  const int64_t si_begin = (int64_t)blockIdx.x * spb + (threadIdx.x >> 5);
-  const int64_t si_end = min((int64_t)(blockIdx.x + 1) * spb, n_mine);
+  const int64_t si_begin = (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5);
+  const int64_t si_end = n_mine;
+  const int64_t si_step = (int64_t)gridDim.x * WPB;
   // The per-slice metadata is a chain of dependent loads (header -> offsets -> x gathers): the header of the warp's
   // NEXT slice is requested before the current slice is processed, its first 32 offsets half-way through.
   struct Hdr { int32_t wenc, M; int64_t vp, ip; };
@@ -339,9 +342,9 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
   Hdr cur;
   load_hdr(si_begin, cur);
   int32_t offl0 = load_offsets(cur);
-  for (int64_t si = si_begin; si < si_end; si += WPB) {
+  for (int64_t si = si_begin; si < si_end; si += si_step) {
     Hdr nxt;
-    load_hdr(si + WPB, nxt);
+    load_hdr(si + si_step, nxt);
     const int64_t s = si < rg.a1 - rg.a0 ? rg.a0 + si : rg.b0 + (si - (rg.a1 - rg.a0));
     const int32_t wenc = cur.wenc;
     const int32_t W = wenc & 0x7fffffff;
@@ -698,9 +701,7 @@ int krylov_alloc(apdx_plan *pl) {
     APDX_CUDA(cudaMemsetAsync(k.z.p, 0, n * sizeof(double), pl->stream));
   }
   {  // per-block partial sums of the fused dot products: up to 4 sums, SpMV grids of the interior + boundary launches
-    const int64_t rows = pl->n_free;   // >= the owned rows of any later partition
-    const size_t spmv_blocks = (size_t)(rows / (64 * 8) + 2 * pl->nf + 4);   // >= slices / 8 (smallest spb), + slack
-    APDX_CHECK(k.partial.alloc(4 * 2 * std::max((size_t)VEC_GRID, spmv_blocks)));
+    APDX_CHECK(k.partial.alloc(4 * 2 * std::max((size_t)VEC_GRID, (size_t)148 * 32)));
   }
   APDX_CHECK(k.st_sc.alloc(2 * S_COUNT));
   APDX_CHECK(k.st_fl.alloc(2 * F_COUNT));
@@ -744,21 +745,20 @@ static Comm comm_of(apdx_plan *pl) {
   return c;
 }
 
-// slices per block of the SpMV (8 warps: spb / 8 slices per warp).  The blocks in flight (2 per SM) cover
-// 296 * spb consecutive slices; 16 keeps that window at ~34 MB of values on one B200 while giving every warp a second
-// slice to prefetch metadata for.  APDX_SPMV_SPB overrides (multiples of 8) for measurements.
-static int spmv_spb() {
-  static int v = 0;
-  if (!v) {
-    const char *e = getenv("APDX_SPMV_SPB");
-    v = e ? atoi(e) : 16;
-    if (v < 8 || v % 8) v = 16;
-  }
-  return v;
-}
+// persistent SpMV grid: the blocks that are resident at once (the kernels are compiled for 2 blocks of 256 threads per
+// SM; APDX_SPMV_BPS overrides the blocks per SM for measurements)
 static unsigned spmv_grid(int64_t n_slices) {
-  const int64_t nb = (n_slices + spmv_spb() - 1) / spmv_spb();
-  return (unsigned)(nb > 0 ? nb : 1);
+  static int resident = 0;
+  if (!resident) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char *e = getenv("APDX_SPMV_BPS");
+    const int bps = e && atoi(e) > 0 ? atoi(e) : 2;
+    resident = sms * bps;
+  }
+  const int64_t nb = (n_slices + VEC_BLOCK / 32 - 1) / (VEC_BLOCK / 32);
+  return (unsigned)(nb < resident ? (nb > 0 ? nb : 1) : resident);
 }
 
 // part: 0 = all slices in one launch; 1 = interior slices only (deposits its dot partials); 2 = the boundary slices
@@ -780,7 +780,7 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
 #define APDX_SPMV_ARGS                                                                                                 \
   S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices,                   \
       (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,                   \
-      (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch, rg, spmv_spb()
+      (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch, rg
 #define APDX_SPMV_NF(NFV)                                                                                              \
   do {                                                                                                                 \
     if (S.sym && S.n_mirrored > 0) k_spmv_sell<NDOT, NFV, true><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);   \
@@ -994,7 +994,7 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
 #define APDX_PF_ARGS                                                                                                   \
   S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p, pl->f0, pl->f1, S.n_slices,       \
       (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he, \
-      SliceRange{0, S.n_slices, 0, 0, 0, -1, 1}, spmv_spb()
+      SliceRange{0, S.n_slices, 0, 0, 0, -1, 1}
           if (S.sym && S.n_mirrored > 0) k_spmv_sell<1, 1, true><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
           else k_spmv_sell<1, 1, false><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
 #undef APDX_PF_ARGS
