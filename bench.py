@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 UNIT_CUBE = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_spmv_sell<1> launch from `ncu --set full` (profiles/), by mesh size
-NCU_TRAFFIC = {256: 3.8625e9}     # profiles/r01c_k_spmv_sell_p256_full.txt: 3.750 GB read + 0.112 GB written
+NCU_TRAFFIC = {256: 2.2391e9}     # profiles/r01e_k_spmv_sell_sym_p256_full.txt: 2.108 GB read + 0.131 GB written
 # SASS count of k_elem_scalar_reg<3,8,8,true>: 2592 DFMA + 368 DMUL + 316 DADD per element
 HEX8_POISSON_FLOP = 2 * 2592 + 368 + 316
 METRIC = "elements/s through one Newton step (sparse assembly + Jacobi-PCG to 1e-8)"
@@ -304,11 +304,13 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
                 "plan_build_s_first_call": t_plan, "mesh_generation_s": t_mesh},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_spmv_sell<1> (sliced-ELL SpMV, compressed column indices, fused p.Ap)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm,
+        "roofline": {"kernel": "k_spmv_sell<1> (sliced-ELL SpMV, compressed column indices, symmetric storage, fused p.Ap)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm,
                      "unit": "GB/s", "frac": spmv_gbs / hbm, "frac_of_nominal_8TBs": spmv_gbs / 8000.0, "peak_source": which,
                      "traffic": NCU_TRAFFIC.get(m) if world == 1 else None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
                      "note": "achieved uses the ALGORITHMIC CSR bytes nnz*12+n*16+(n+1)*4 (SURVEY.md 8d); the kernel streams fewer "
-                             "bytes because column indices are stored once per 64-row slice",
+                             "bytes: column offsets are stored once per 64-row slice and, the tangent being symmetric, only the columns with "
+                             "offset >= 0 are stored -- the lower ones are read from their transposed position, which the L2 serves",
+                     "sell": plan.sell_info(),
                      "implementation_bytes_per_launch": impl_bytes, "implementation_gbs": impl_gbs,
                      "implementation_frac_of_peak": impl_gbs / hbm},
         "newton_step_ms": ms,
