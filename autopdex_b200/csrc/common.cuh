@@ -147,17 +147,17 @@ struct KrylovGraph {
 };
 
 constexpr int32_t SELL_MB7 = 1 << 30;   // Sell::sl_m flag: mirror table padded to a multiple of 7 entries (else 8)
+constexpr int32_t SELL_FAST = 1 << 29;  // Sell::sl_m flag: offset-mode slice whose columns all lie inside [0, n_cols): no clamps
+constexpr int32_t SELL_MMASK = 0x0fffffff;
 
 // sliced-ELL copy of the owned rows of the reduced system (sell.cu)
 struct Sell {
   bool built = false;
   bool sym = true;            // lower columns read from the transposed position where possible (sell.cu)
   int64_t row0 = 0, n_rows = 0, n_slices = 0, n_val = 0, n_idx = 0, n_mirrored = 0;
-  int64_t win_cap = 0;        // largest number of x entries a slice stages in shared memory (0: windows unusable)
   int nf = 1;                 // slices interleave the nf dofs per node (sell.cu)
   int64_t lo_end = 0, hi_begin = 0;  // slices [lo_end, hi_begin) reference no ghost column (multi-GPU overlap)
   DevBuf<int32_t> sl_w;       // [n_slices] stored width | (offset mode ? 1<<31 : 0)
-  DevBuf<int32_t> sl_x;       // [n_slices] x windows of the slice | staged entries << 8 (record layout: sell.cu)
   DevBuf<int32_t> sl_m;       // [n_slices] padded number of mirrored lower columns | SELL_MB7 (table behind the offsets)
   DevBuf<int64_t> valptr;     // [n_slices+1] start of the slice's value block (doubles)
   DevBuf<int64_t> idxptr;     // [n_slices+1] start of the slice's index block (int32)
@@ -166,7 +166,7 @@ struct Sell {
   DevBuf<int32_t> src;        // [n_val] full-CSR entry behind each position, -1 = padding
   DevBuf<int32_t> diag;       // [n_rows] diagonal position relative to the slice's value block, -1 = none
   void release() {
-    sl_w.release(); sl_m.release(); sl_x.release(); valptr.release(); idxptr.release(); val.release(); idx.release(); src.release(); diag.release();
+    sl_w.release(); sl_m.release(); valptr.release(); idxptr.release(); val.release(); idx.release(); src.release(); diag.release();
     built = false;
   }
 };

@@ -14,7 +14,6 @@
 #include <string.h>
 
 #include <algorithm>
-#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -274,6 +273,52 @@ struct SliceRange {
 // and one block per 8..32 consecutive slices pays the start-up latency chain per block: 0.83 / 0.69 / 0.64 ms.)
 constexpr int SPMV_U = 9;
 
+// Fast paths for slices flagged SELL_FAST (every column of every row inside x: no index clamps) whose column count is
+// a multiple of the batch B: compile-time trip counts, no predicates, offsets / table entries read with warp-uniform
+// loads from cache lines prefetched when the slice's header arrived.  Half the instructions of the generic path.
+template <int B, bool SYM>
+__device__ __forceinline__ void spmv_stored_fast(const int32_t *__restrict__ offs, const double *__restrict__ vpc, int32_t nb,
+                                                 const double *__restrict__ xr0, const double *__restrict__ xr1, double &a0,
+                                                 double &a1) {
+  for (int32_t jb = 0; jb < nb; jb += B) {
+    int32_t off[B];
+    double va[B], vb[B], xa[B], xb[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) off[u] = __ldg(offs + jb + u);
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const double *q = vpc + (size_t)(jb + u) * 64;
+      va[u] = SYM ? __ldg(q) : __ldcs(q);
+      vb[u] = SYM ? __ldg(q + 32) : __ldcs(q + 32);
+    }
+#pragma unroll
+    for (int u = 0; u < B; ++u) { xa[u] = __ldg(xr0 + off[u]); xb[u] = __ldg(xr1 + off[u]); }
+#pragma unroll
+    for (int u = 0; u < B; ++u) { a0 += va[u] * xa[u]; a1 += vb[u] * xb[u]; }
+  }
+}
+template <int MB>
+__device__ __forceinline__ void spmv_mirrored_fast(const int4 *__restrict__ tab, int32_t M, const double *__restrict__ val,
+                                                   const double *__restrict__ xr0, const double *__restrict__ xr1, int lane,
+                                                   double &a0, double &a1) {
+  const int k0 = lane, k1 = lane + 32;
+  for (int32_t jb = 0; jb < M; jb += MB) {
+    int4 t[MB];
+#pragma unroll
+    for (int u = 0; u < MB; ++u) t[u] = __ldg(tab + jb + u);
+    double m0[MB], m1[MB], xa[MB], xb[MB];
+#pragma unroll
+    for (int u = 0; u < MB; ++u) {
+      m0[u] = __ldg(val + ((k0 < t[u].w ? t[u].y : t[u].z) + k0));
+      m1[u] = __ldg(val + ((k1 < t[u].w ? t[u].y : t[u].z) + k1));
+      xa[u] = __ldg(xr0 + t[u].x);
+      xb[u] = __ldg(xr1 + t[u].x);
+    }
+#pragma unroll
+    for (int u = 0; u < MB; ++u) { a0 += m0[u] * xa[u]; a1 += m1[u] * xb[u]; }
+  }
+}
+
 template <int MB>
 __device__ __forceinline__ void spmv_mirrored(const int4 *__restrict__ tab, int32_t M, const double *__restrict__ val,
                                               const double *__restrict__ x, int lane, int32_t rr0, int32_t rr1,
@@ -286,9 +331,8 @@ __device__ __forceinline__ void spmv_mirrored(const int4 *__restrict__ tab, int3
     double m0[MB], m1[MB], xa[MB], xb[MB];
 #pragma unroll
     for (int u = 0; u < MB; ++u) {
-      const int32_t sp = t[u].w & 0xff;   // rows k < split read posA + k, the others posB + k (bits 8..: window position)
-      m0[u] = __ldg(val + ((k0 < sp ? t[u].y : t[u].z) + k0));
-      m1[u] = __ldg(val + ((k1 < sp ? t[u].y : t[u].z) + k1));
+      m0[u] = __ldg(val + ((k0 < t[u].w ? t[u].y : t[u].z) + k0));
+      m1[u] = __ldg(val + ((k1 < t[u].w ? t[u].y : t[u].z) + k1));
       xa[u] = __ldg(x + min(max(rr0 + t[u].x, 0), n_cols - 1));
       xb[u] = __ldg(x + min(max(rr1 + t[u].x, 0), n_cols - 1));
     }
@@ -299,8 +343,8 @@ __device__ __forceinline__ void spmv_mirrored(const int4 *__restrict__ tab, int3
 
 template <int NDOT, int NF, bool SYM>
 __global__ void __launch_bounds__(VEC_BLOCK, 2)
-    k_spmv_sell(const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_m, const int32_t *__restrict__ sl_x,
-                const int64_t *__restrict__ valptr, const int64_t *__restrict__ idxptr, const double *__restrict__ val, const int32_t *__restrict__ idx,
+    k_spmv_sell(const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_m, const int64_t *__restrict__ valptr,
+                const int64_t *__restrict__ idxptr, const double *__restrict__ val, const int32_t *__restrict__ idx,
                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, int64_t row0,
                 int64_t row1, int64_t n_slices, int32_t n_cols, double *partial, unsigned int *ticket, double *sc,
                 int32_t *fl, int stage, int fused, int check_done, const P2PDev *pd, int epoch, int halo_epoch,
@@ -326,20 +370,24 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
   const int64_t si_step = (int64_t)gridDim.x * WPB;
   // The per-slice metadata is a chain of dependent loads (header -> offsets -> x gathers): the header of the warp's
   // NEXT slice is requested before the current slice is processed, its first 32 offsets half-way through.
-  struct Hdr { int32_t wenc, M; int64_t vp, ip; };   // ip: start of the slice's offset list (behind its window table)
+  struct Hdr { int32_t wenc, M; int64_t vp, ip; };
   auto load_hdr = [&](int64_t si, Hdr &h) {
     h.wenc = 0; h.M = 0; h.vp = 0; h.ip = 0;
     if (si < si_end) {
       const int64_t s = si < rg.a1 - rg.a0 ? rg.a0 + si : rg.b0 + (si - (rg.a1 - rg.a0));
       h.wenc = sl_w[s];
-      if (SYM) h.M = sl_m[s];
+      h.M = sl_m[s];
       h.vp = valptr[s];
-      h.ip = idxptr[s] + 4 * (sl_x[s] & 0xff);
+      h.ip = idxptr[s];
     }
   };
   auto load_offsets = [&](const Hdr &h) -> int32_t {
     const int32_t W = h.wenc & 0x7fffffff;
-    return (h.wenc < 0 && W > 0) ? __ldg(idx + h.ip + min(lane, min(32, W) - 1)) : 0;
+    if (h.wenc >= 0 || W == 0) return 0;
+    // pull the slice's offsets and mirror table into the L1: the fast paths read them with warp-uniform loads
+    const int32_t rec_ints = ((W + 3) & ~3) + 4 * (h.M & SELL_MMASK);
+    if (lane * 32 < rec_ints) asm volatile("prefetch.global.L1 [%0];" ::"l"(idx + h.ip + lane * 32));
+    return __ldg(idx + h.ip + min(lane, min(32, W) - 1));
   };
   Hdr cur;
   load_hdr(si_begin, cur);
@@ -350,7 +398,8 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     const int64_t s = si < rg.a1 - rg.a0 ? rg.a0 + si : rg.b0 + (si - (rg.a1 - rg.a0));
     const int32_t wenc = cur.wenc;
     const int32_t W = wenc & 0x7fffffff;
-    const int32_t M = SYM ? (cur.M & ~SELL_MB7) : 0;
+    const int32_t M = SYM ? (cur.M & SELL_MMASK) : 0;
+    const bool fast = (cur.M & SELL_FAST) != 0;
     const double *vp = val + cur.vp + lane;
     // rows of the slice: one field component of 64 consecutive nodes (sell.cu); lane owns local rows k = lane and
     // lane + 32, so that every x gather, value load and y store of the warp covers one contiguous run of 32 entries
@@ -358,15 +407,22 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     const int64_t r0 = row0 + (s / NF) * (int64_t)64 * NF + (s % NF) + (int64_t)NF * lane;
     const int64_t r1 = r0 + (int64_t)32 * NF;
     const int32_t rr0 = (int32_t)r0, rr1 = (int32_t)r1;
+    const double *xr0 = x + r0, *xr1 = x + r1;
     const int32_t *ip = idx + cur.ip;
-    const int4 *tab = reinterpret_cast<const int4 *>(ip + 2 * ((W + 3) & ~3));   // behind the offsets and window positions
+    const int4 *tab = reinterpret_cast<const int4 *>(ip + ((W + 3) & ~3));
     if (SYM && lane * 8 < M)   // one lane per 128-byte line of the mirror table
       asm volatile("prefetch.global.L1 [%0];" ::"l"(tab + lane * 8));
     double a0 = 0.0, a1 = 0.0;
     for (int32_t jc = 0; jc < W; jc += 32) {
       const int32_t nb = min(32, W - jc);
       const int32_t nbt = (nb + SPMV_U - 1) / SPMV_U, bs = (nb + nbt - 1) / nbt;   // equal batches of <= SPMV_U columns
-      if (wenc < 0) {
+      if (fast && nb % 9 == 0) {
+        spmv_stored_fast<9, SYM>(ip + jc, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+      } else if (fast && nb % 8 == 0) {
+        spmv_stored_fast<8, SYM>(ip + jc, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+      } else if (fast && nb % 7 == 0) {
+        spmv_stored_fast<7, SYM>(ip + jc, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+      } else if (wenc < 0) {
         const int32_t offl = jc == 0 ? offl0 : __ldg(ip + jc + min(lane, nb - 1));
         for (int32_t jb = 0; jb < nb; jb += bs) {
           double va[SPMV_U], vb[SPMV_U], xa[SPMV_U], xb[SPMV_U];
@@ -416,8 +472,13 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     // the next slice's header has arrived by now: request its offsets
     const int32_t offl_n = load_offsets(nxt);
     if (SYM && M > 0) {
-      if (cur.M & SELL_MB7) spmv_mirrored<7>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
-      else spmv_mirrored<8>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
+      if (fast) {
+        if (cur.M & SELL_MB7) spmv_mirrored_fast<7>(tab, M, val, xr0, xr1, lane, a0, a1);
+        else spmv_mirrored_fast<8>(tab, M, val, xr0, xr1, lane, a0, a1);
+      } else {
+        if (cur.M & SELL_MB7) spmv_mirrored<7>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
+        else spmv_mirrored<8>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
+      }
     }
     cur = nxt;
     offl0 = offl_n;
@@ -432,218 +493,6 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
       if (NDOT >= 2) acc[1] += a1 * a1;
     }
   }
-  if constexpr (NDOT > 0)
-    reduce_finalize<NDOT>(acc, partial, ticket, sc, fl, stage, fused, pd, epoch, 0, rg.blk0, rg.nblk_total, rg.finalize);
-}
-
-// ---- SpMV with the x windows of a slice staged in shared memory ------------------------------------------------
-// In offset mode the operands of column j are x[rbase + off_j + nf k], k = 0..63: columns whose offsets are close
-// (the -1/0/+1 neighbours along a mesh line, the nf components of a node) read overlapping runs of x.  The build
-// (sell.cu) groups the offsets of a slice into windows; this kernel copies each window ONCE into shared memory with
-// cp.async (zero-filled outside [0, n_cols): no clamps) -- for the NEXT slice of the warp while the current one is
-// being multiplied (two buffers per warp, metadata prefetched two slices ahead) -- and the FMAs take their x operand
-// from shared memory.  Against the gather kernel: a third of the global x load instructions (P256: 594 staged entries
-// serve 27 x 64 operands; nf = 3: 1782 serve 81 x 64, and the strided gathers that touched 7 lines per instruction
-// are gone), and the registers hold matrix values only, so a whole slice's stored columns (up to WIN_U) are in
-// flight per warp.  Explicit-mode slices take the gather path inside the same kernel.
-constexpr int WIN_U = 14;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int NDOT, int NF, bool SYM>
-__global__ void __launch_bounds__(VEC_BLOCK, 2)
-    k_spmv_sell_win(const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_m, const int32_t *__restrict__ sl_x,
-                    const int64_t *__restrict__ valptr, const int64_t *__restrict__ idxptr, const double *__restrict__ val,
-                    const int32_t *__restrict__ idx, const double *__restrict__ x, double *__restrict__ y,
-                    const double *__restrict__ w, int64_t row0, int64_t row1, int64_t n_slices, int32_t n_cols,
-                    double *partial, unsigned int *ticket, double *sc, int32_t *fl, int stage, int fused, int check_done,
-                    const P2PDev *pd, int epoch, int halo_epoch, SliceRange rg, int wcap) {
-  if (check_done && fl[F_DONE]) return;
-  if (pd && halo_epoch > 0) {
-    if (threadIdx.x == 0) {
-      if (pd->has_lo) p2p_wait(pd->hflag_self + 0, halo_epoch, pd->err);
-      if (pd->has_hi) p2p_wait(pd->hflag_self + 1, halo_epoch, pd->err);
-    }
-    __syncthreads();
-  }
-  extern __shared__ __align__(16) double win_smem[];   // [warps][2 buffers][wcap]
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  constexpr int WPB = VEC_BLOCK / 32;
-  double *const wbuf = win_smem + (size_t)wid * 2 * wcap;
-  const uint32_t wbuf_u = smem_u32(wbuf);
-  double acc[NDOT > 0 ? NDOT : 1];
-#pragma unroll
-  for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
-  const int64_t n_a = rg.a1 - rg.a0;
-  const int64_t n_mine = n_a + (rg.b1 - rg.b0);
-  const int64_t si_begin = (int64_t)blockIdx.x * WPB + wid;
-  const int64_t si_step = (int64_t)gridDim.x * WPB;
-  auto slice_of = [&](int64_t si) { return si < n_a ? rg.a0 + si : rg.b0 + (si - n_a); };
-
-  struct Hdr { int32_t wenc, M, xc; int64_t vp, ip; };   // ip: start of the slice's record (window table first)
-  struct Meta { int4 cl; int32_t xposl; };               // lane c: window c; lane j: staged position of stored column j
-  auto load_hdr = [&](int64_t si, Hdr &h) {
-    h.wenc = 0; h.M = 0; h.xc = 0; h.vp = 0; h.ip = 0;
-    if (si < n_mine) {
-      const int64_t s = slice_of(si);
-      h.wenc = sl_w[s];
-      if (SYM) h.M = sl_m[s];
-      h.xc = sl_x[s];
-      h.vp = valptr[s];
-      h.ip = idxptr[s];
-    }
-  };
-  auto load_meta = [&](const Hdr &h, Meta &m) {
-    const int32_t W = h.wenc & 0x7fffffff, nC = h.xc & 0xff;
-    m.cl = make_int4(0, 0, 0, 0);
-    m.xposl = 0;
-    if (h.wenc < 0 && nC > 0) m.cl = __ldg(reinterpret_cast<const int4 *>(idx + h.ip) + min(lane, nC - 1));
-    if (h.wenc < 0 && W > 0) m.xposl = __ldg(idx + h.ip + 4 * nC + ((W + 3) & ~3) + min(lane, min(32, W) - 1));
-  };
-  // stage the x windows of slice si into buffer `b`; always commits one cp.async group
-  auto issue_windows = [&](int64_t si, const Hdr &h, const Meta &m, int b) {
-    if (h.wenc < 0) {
-      const int64_t s = slice_of(si);
-      const int64_t rbase = row0 + (s / NF) * (int64_t)64 * NF + (s % NF);
-      const int32_t nC = h.xc & 0xff;
-      const uint32_t dst0 = wbuf_u + (uint32_t)b * (uint32_t)wcap * 8u;
-      for (int32_t c = 0; c < nC; ++c) {
-        const int32_t woff = __shfl_sync(0xffffffffu, m.cl.x, c);
-        const int32_t wlen = __shfl_sync(0xffffffffu, m.cl.y, c);
-        const int32_t wpos = __shfl_sync(0xffffffffu, m.cl.z, c);
-        const int64_t g0 = rbase + woff;
-        for (int32_t t = lane; t < wlen; t += 32) {
-          const int64_t g = g0 + t;
-          const bool inr = g >= 0 && g < n_cols;
-          const double *src = x + (inr ? g : 0);
-          const uint32_t nbytes = inr ? 8u : 0u;     // 0: the 8 destination bytes are zero-filled
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst0 + (uint32_t)(wpos + t) * 8u), "l"(src), "r"(nbytes)
-                       : "memory");
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  Hdr h0, h1;
-  Meta m0, m1;
-  load_hdr(si_begin, h0);
-  load_hdr(si_begin + si_step, h1);
-  load_meta(h0, m0);
-  issue_windows(si_begin, h0, m0, 0);
-  load_meta(h1, m1);
-  int b = 0;
-  for (int64_t si = si_begin; si < n_mine; si += si_step) {
-    Hdr h2;
-    load_hdr(si + 2 * si_step, h2);
-    issue_windows(si + si_step, h1, m1, b ^ 1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
-    const int64_t s = slice_of(si);
-    const int32_t wenc = h0.wenc;
-    const int32_t W = wenc & 0x7fffffff;
-    const int32_t M = SYM ? (h0.M & ~SELL_MB7) : 0;
-    const double *vp = val + h0.vp + lane;
-    const int64_t r0 = row0 + (s / NF) * (int64_t)64 * NF + (s % NF) + (int64_t)NF * lane;
-    const int64_t r1 = r0 + (int64_t)32 * NF;
-    double a0 = 0.0, a1 = 0.0;
-    if (wenc < 0) {
-      const int32_t nC = h0.xc & 0xff, w_al = (W + 3) & ~3;
-      const int32_t *xpl = idx + h0.ip + 4 * nC + w_al;
-      const int4 *tab = reinterpret_cast<const int4 *>(xpl + w_al);
-      if (SYM && lane * 8 < M) asm volatile("prefetch.global.L1 [%0];" ::"l"(tab + lane * 8));
-      const double *xw = wbuf + (size_t)b * wcap + NF * lane;   // row lane reads xw[xpos], row lane + 32 xw[xpos + 32 nf]
-      for (int32_t jc = 0; jc < W; jc += 32) {
-        const int32_t nb = min(32, W - jc);
-        const int32_t nbt = (nb + WIN_U - 1) / WIN_U, bs = (nb + nbt - 1) / nbt;
-        const int32_t xposl = jc == 0 ? m0.xposl : __ldg(xpl + jc + min(lane, nb - 1));
-        for (int32_t jb = 0; jb < nb; jb += bs) {
-          double va[WIN_U], vb[WIN_U];
-#pragma unroll
-          for (int u = 0; u < WIN_U; ++u) {
-            va[u] = vb[u] = 0.0;
-            if (u < bs && jb + u < nb) {
-              const double *q = vp + (size_t)(jc + jb + u) * 64;
-              va[u] = SYM ? __ldg(q) : __ldcs(q);
-              vb[u] = SYM ? __ldg(q + 32) : __ldcs(q + 32);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < WIN_U; ++u) {
-            const int32_t xp = __shfl_sync(0xffffffffu, xposl, (jb + u) & 31);
-            if (u < bs && jb + u < nb) {
-              a0 += va[u] * xw[xp];
-              a1 += vb[u] * xw[xp + 32 * NF];
-            }
-          }
-        }
-      }
-      if (SYM && M > 0) {
-        const int k0 = lane, k1 = lane + 32;
-        auto mirrored = [&](auto mb_tag) {
-          constexpr int MB = decltype(mb_tag)::value;
-          for (int32_t jb = 0; jb < M; jb += MB) {
-            int4 t[MB];
-#pragma unroll
-            for (int u = 0; u < MB; ++u) t[u] = __ldg(tab + jb + u);   // warp-uniform 16-byte loads
-            double q0[MB], q1[MB];
-#pragma unroll
-            for (int u = 0; u < MB; ++u) {
-              const int32_t sp = t[u].w & 0xff;
-              q0[u] = __ldg(val + ((k0 < sp ? t[u].y : t[u].z) + k0));
-              q1[u] = __ldg(val + ((k1 < sp ? t[u].y : t[u].z) + k1));
-            }
-#pragma unroll
-            for (int u = 0; u < MB; ++u) {
-              const int32_t xp = t[u].w >> 8;
-              a0 += q0[u] * xw[xp];
-              a1 += q1[u] * xw[xp + 32 * NF];
-            }
-          }
-        };
-        if (h0.M & SELL_MB7) mirrored(std::integral_constant<int, 7>{});
-        else mirrored(std::integral_constant<int, 8>{});
-      }
-    } else {
-      // explicit columns: gathers, batched as in k_spmv_sell
-      const int32_t *cp = idx + h0.ip + lane;
-      for (int32_t jb = 0; jb < W; jb += SPMV_U) {
-        int32_t ca[SPMV_U], cb[SPMV_U];
-        double va[SPMV_U], vb[SPMV_U], xa[SPMV_U], xb[SPMV_U];
-#pragma unroll
-        for (int u = 0; u < SPMV_U; ++u) {
-          ca[u] = cb[u] = 0;
-          va[u] = vb[u] = 0.0;
-          if (jb + u < W) {
-            const size_t o = (size_t)(jb + u) * 64;
-            ca[u] = __ldcs(cp + o); cb[u] = __ldcs(cp + o + 32);
-            va[u] = __ldcs(vp + o); vb[u] = __ldcs(vp + o + 32);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < SPMV_U; ++u) { xa[u] = __ldg(x + ca[u]); xb[u] = __ldg(x + cb[u]); }
-#pragma unroll
-        for (int u = 0; u < SPMV_U; ++u) { a0 += va[u] * xa[u]; a1 += vb[u] * xb[u]; }
-      }
-    }
-    Meta m2;
-    load_meta(h2, m2);
-    if (r0 < row1) {
-      y[r0] = a0;
-      if (NDOT >= 1) acc[0] += w[r0] * a0;
-      if (NDOT >= 2) acc[1] += a0 * a0;
-    }
-    if (r1 < row1) {
-      y[r1] = a1;
-      if (NDOT >= 1) acc[0] += w[r1] * a1;
-      if (NDOT >= 2) acc[1] += a1 * a1;
-    }
-    __syncwarp();   // every lane is done with buffer b before the next iteration refills it
-    h0 = h1; h1 = h2;
-    m0 = m1; m1 = m2;
-    b ^= 1;
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if constexpr (NDOT > 0)
     reduce_finalize<NDOT>(acc, partial, ticket, sc, fl, stage, fused, pd, epoch, 0, rg.blk0, rg.nblk_total, rg.finalize);
 }
@@ -959,42 +808,20 @@ static Comm comm_of(apdx_plan *pl) {
   return c;
 }
 
-static int spmv_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
-}
 // persistent SpMV grid: the blocks that are resident at once (the kernels are compiled for 2 blocks of 256 threads per
 // SM; APDX_SPMV_BPS overrides the blocks per SM for measurements)
 static unsigned spmv_grid(int64_t n_slices) {
   static int resident = 0;
   if (!resident) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char *e = getenv("APDX_SPMV_BPS");
     const int bps = e && atoi(e) > 0 ? atoi(e) : 2;
-    resident = spmv_sms() * bps;
+    resident = sms * bps;
   }
   const int64_t nb = (n_slices + VEC_BLOCK / 32 - 1) / (VEC_BLOCK / 32);
   return (unsigned)(nb < resident ? (nb > 0 ? nb : 1) : resident);
-}
-// shared-memory x windows (k_spmv_sell_win): usable if every offset-mode slice has a window table and two buffers per
-// warp fit; two blocks per SM while they fit in half of the 227 KB, else one.  APDX_SPMV_WIN=0 forces the gather kernel.
-struct SpmvWin { bool use; int wcap, smem, bps; };
-static SpmvWin spmv_win(const Sell &S) {
-  SpmvWin w{false, 0, 0, 2};
-  const char *e = getenv("APDX_SPMV_WIN");
-  if ((e && e[0] == '0') || S.win_cap <= 0) return w;
-  w.wcap = (int)((S.win_cap + 1) & ~(int64_t)1);
-  w.smem = (VEC_BLOCK / 32) * 2 * w.wcap * (int)sizeof(double);
-  const int limit = 227 * 1024 - 1024;   // static shared memory of the reduction
-  if (w.smem > limit) return w;
-  w.bps = 2 * (w.smem + 1024) <= 227 * 1024 ? 2 : 1;
-  w.use = true;
-  return w;
 }
 
 // part: 0 = all slices in one launch; 1 = interior slices only (deposits its dot partials); 2 = the boundary slices
@@ -1014,37 +841,18 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
   }
   const int epoch = (NDOT > 0 && c.p2p && stage >= 0) ? ++pl->p2p.red_epoch : 0;
 #define APDX_SPMV_ARGS                                                                                                 \
-  S.sl_w.p, S.sl_m.p, S.sl_x.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices,         \
+  S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices,                   \
       (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,                   \
       (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch, rg
-  const SpmvWin win = spmv_win(S);
-#define APDX_SPMV_WIN(NFV, SYMV)                                                                                       \
-  do {                                                                                                                 \
-    static int attr_smem = 0;                                                                                          \
-    if (attr_smem < win.smem) {                                                                                        \
-      APDX_CUDA(cudaFuncSetAttribute(k_spmv_sell_win<NDOT, NFV, SYMV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                     win.smem));                                                                       \
-      attr_smem = win.smem;                                                                                            \
-    }                                                                                                                  \
-    k_spmv_sell_win<NDOT, NFV, SYMV><<<grid, VEC_BLOCK, win.smem, pl->stream>>>(APDX_SPMV_ARGS, win.wcap);             \
-  } while (0)
 #define APDX_SPMV_NF(NFV)                                                                                              \
   do {                                                                                                                 \
-    const bool symk = S.sym && S.n_mirrored > 0;                                                                       \
-    if (win.use) {                                                                                                     \
-      if (part == 0) grid = std::min(grid, (unsigned)(spmv_sms() * win.bps));                                          \
-      if (symk) APDX_SPMV_WIN(NFV, true); else APDX_SPMV_WIN(NFV, false);                                              \
-    } else if (symk) {                                                                                                 \
-      k_spmv_sell<NDOT, NFV, true><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                                \
-    } else {                                                                                                           \
-      k_spmv_sell<NDOT, NFV, false><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                               \
-    }                                                                                                                  \
+    if (S.sym && S.n_mirrored > 0) k_spmv_sell<NDOT, NFV, true><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);   \
+    else k_spmv_sell<NDOT, NFV, false><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                            \
   } while (0)
   if (S.nf == 1) APDX_SPMV_NF(1);
   else if (S.nf == 2) APDX_SPMV_NF(2);
   else APDX_SPMV_NF(3);
 #undef APDX_SPMV_NF
-#undef APDX_SPMV_WIN
 #undef APDX_SPMV_ARGS
   pl->stats.spmv_launches += 1;
   pl->stats.kernel_launches += 1;
@@ -1247,7 +1055,7 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
           const int e1 = ++P.red_epoch;
           // (the opt-in p2p-fused CG is only wired for scalar problems)
 #define APDX_PF_ARGS                                                                                                   \
-  S.sl_w.p, S.sl_m.p, S.sl_x.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p, pl->f0, pl->f1, S.n_slices, \
+  S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p, pl->f0, pl->f1, S.n_slices,       \
       (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he, \
       SliceRange{0, S.n_slices, 0, 0, 0, -1, 1}
           if (S.sym && S.n_mirrored > 0) k_spmv_sell<1, 1, true><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);

@@ -48,7 +48,7 @@ __device__ __forceinline__ int32_t warp_max(int32_t v) {
 // Row segments without any entry point at a block of 64 zeros appended to the value array.
 
 struct SliceGeo {
-  int64_t row0, row1, n_rows, n_slices;
+  int64_t row0, row1, n_rows, n_slices, n_cols;
   int nf;
   __device__ __forceinline__ int64_t row(int64_t s, int k) const {
     return row0 + (s / nf) * (int64_t)SELL_C * nf + (s % nf) + (int64_t)nf * k;
@@ -111,8 +111,7 @@ __global__ void __launch_bounds__(256) k_sell_layout(const int32_t *__restrict__
                                                      const int32_t *__restrict__ red2full, SliceGeo G, int sym,
                                                      const uint8_t *__restrict__ sl_mode, int32_t *__restrict__ sl_w,
                                                      int32_t *__restrict__ sl_m, int32_t *__restrict__ sl_u,
-                                                     int32_t *__restrict__ sl_x, int32_t *__restrict__ sz_val,
-                                                     int32_t *__restrict__ sz_idx,
+                                                     int32_t *__restrict__ sz_val, int32_t *__restrict__ sz_idx,
                                                      const int64_t *__restrict__ valptr, const int64_t *__restrict__ idxptr,
                                                      int32_t *__restrict__ sell_idx, int32_t *__restrict__ sell_src,
                                                      int32_t *__restrict__ sell_diag, uint8_t *__restrict__ ghost,
@@ -139,7 +138,7 @@ __global__ void __launch_bounds__(256) k_sell_layout(const int32_t *__restrict__
   if (!offset_mode) {
     const int32_t w = warp_max(max(e[0] - b[0], e[1] - b[1]));
     if (PASS == 0) {
-      if (lane == 0) { sl_w[s] = w; sl_m[s] = 0; sl_u[s] = 0; sl_x[s] = 0; sz_val[s] = w * SELL_C; sz_idx[s] = w * SELL_C; }
+      if (lane == 0) { sl_w[s] = w; sl_m[s] = 0; sl_u[s] = 0; sz_val[s] = w * SELL_C; sz_idx[s] = w * SELL_C; }
       return;
     }
     const int64_t vp = valptr[s], ip = idxptr[s];
@@ -163,44 +162,20 @@ __global__ void __launch_bounds__(256) k_sell_layout(const int32_t *__restrict__
     return;
   }
   // ---- offset mode: walk the union of offsets in ascending order ------------------------------------------------
-  // Record of an offset-mode slice in the index array (ints, every part 16-byte aligned):
-  //   [4 nC]     x-window table (woff, wlen, wpos, 0): offsets closer than 64 nf share one window of x
-  //              (x[rbase + woff .. + wlen)), which the SpMV stages in shared memory at wpos
-  //   [W_al]     offsets of the stored columns (>= 0 first, ascending, then stored lower ones)
-  //   [W_al]     position of each stored column inside the staged windows (row k reads window[xpos + nf k])
-  //   [4 M_pad]  mirror table (offset, posA, posB, split | xpos << 8)
   int32_t p[2] = {b[0], b[1]};
-  int32_t nU = 0, nL = 0, nM = 0;
-  int32_t nU_tot = 0, w_tot = 0, nC_tot = 0;
+  int32_t nU = 0, nL = 0, nM = 0, off_min = 0, off_max = 0;
+  int32_t nU_tot = 0, w_tot = 0;
   int64_t vp = 0, ip = 0;
-  if (PASS == 1) { nU_tot = sl_u[s]; w_tot = sl_w[s] & 0x7fffffff; nC_tot = sl_x[s] & 0xff; vp = valptr[s]; ip = idxptr[s]; }
+  if (PASS == 1) { nU_tot = sl_u[s]; w_tot = sl_w[s] & 0x7fffffff; vp = valptr[s]; ip = idxptr[s]; }
   const int32_t w_al = (w_tot + 3) & ~3;
-  int32_t *const cl_tab = sell_idx + ip;
-  int32_t *const off_l = cl_tab + 4 * nC_tot;
-  int32_t *const xpos_l = off_l + w_al;
-  int32_t *const mir_tab = xpos_l + w_al;
-  int32_t nC = 0, c_first = 0, c_last = 0, wpos = 0;   // current window: offsets [c_first, c_last], staged at wpos
-  const int32_t wext = G.nf * (SELL_C - 1) + 1;         // rows k = 0..63 reach nf*63 entries past the offset
   while (true) {
     const int32_t c0 = p[0] < e[0] ? col[p[0]] - (int32_t)r[0] : SELL_BIG;
     const int32_t c1 = p[1] < e[1] ? col[p[1]] - (int32_t)r[1] : SELL_BIG;
     const int32_t m = warp_min(min(c0, c1));
     if (m == SELL_BIG) break;
     const bool has[2] = {c0 == m, c1 == m};
-    if (nC == 0 || m - c_last > SELL_C * G.nf) {          // open a new window (close the previous one)
-      if (nC > 0) {
-        const int32_t wlen = c_last - c_first + wext;
-        if (PASS == 1 && lane == 0 && nC <= nC_tot) {
-          int32_t *ce = cl_tab + 4 * (nC - 1);
-          ce[0] = c_first; ce[1] = wlen; ce[2] = wpos; ce[3] = 0;
-        }
-        wpos += wlen;
-      }
-      ++nC;
-      c_first = m;
-    }
-    c_last = m;
-    const int32_t xpos = wpos + (m - c_first);
+    if (nU + nL + nM == 0) off_min = m;
+    off_max = m;
     bool mirrored = false;
     if (m < 0 && sym) {
       bool ok = true;
@@ -222,14 +197,14 @@ __global__ void __launch_bounds__(256) k_sell_layout(const int32_t *__restrict__
     }
     if (mirrored) {
       if (PASS == 1 && lane == 0) {
-        int32_t *tab = mir_tab + 4 * (int64_t)nM;
-        tab[0] = m; tab[1] = 0; tab[2] = 0; tab[3] = xpos << 8;        // positions and split: k_sell_mirror
+        int32_t *tab = sell_idx + ip + w_al + 4 * (int64_t)nM;
+        tab[0] = m; tab[1] = 0; tab[2] = 0; tab[3] = 0;                // positions: k_sell_mirror
       }
       ++nM;
     } else {
       const int32_t j = (m >= 0) ? nU : nU_tot + nL;                   // stored column index
       if (PASS == 1) {
-        if (lane == 0) { off_l[j] = m; xpos_l[j] = xpos; }
+        if (lane == 0) sell_idx[ip + j] = m;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           int32_t src = -1;
@@ -245,15 +220,6 @@ __global__ void __launch_bounds__(256) k_sell_layout(const int32_t *__restrict__
     if (has[0]) ++p[0];
     if (has[1]) ++p[1];
   }
-  int32_t wtot = wpos;
-  if (nC > 0) {
-    const int32_t wlen = c_last - c_first + wext;
-    if (PASS == 1 && lane == 0 && nC <= nC_tot) {
-      int32_t *ce = cl_tab + 4 * (nC - 1);
-      ce[0] = c_first; ce[1] = wlen; ce[2] = wpos; ce[3] = 0;
-    }
-    wtot += wlen;
-  }
   // the mirror table is padded to a multiple of the SpMV's mirrored batch (7 or 8 columns, whichever pads less;
   // bit 30 of sl_m = batch of 7) with entries that point at the block of zeros, so that the kernel's inner loop
   // has a compile-time trip count and no predicates
@@ -262,19 +228,19 @@ __global__ void __launch_bounds__(256) k_sell_layout(const int32_t *__restrict__
   if (PASS == 0 && lane == 0) {
     const int32_t w = nU + nL;
     sl_w[s] = w | (int32_t)0x80000000;
-    sl_m[s] = m_pad | (pad7 < pad8 ? SELL_MB7 : 0);
+    // every column of every row inside x: the SpMV may skip the index clamps (all but the first / last mesh planes)
+    const int64_t rb = G.row(s, 0);
+    const bool interior = w > 0 && rb + off_min >= 0 && rb + (int64_t)G.nf * (SELL_C - 1) + off_max < G.n_cols;
+    sl_m[s] = m_pad | (pad7 < pad8 ? SELL_MB7 : 0) | (interior ? SELL_FAST : 0);
     sl_u[s] = nU;
-    // more than 32 windows or > 2^20 staged entries: the plan falls back to the gather kernel (x_windows = 0)
-    const bool win_ok = nC <= 32 && wtot < (1 << 20);
-    sl_x[s] = (win_ok ? nC : 0) | ((win_ok ? wtot : 0x7fffff) << 8);
     sz_val[s] = w * SELL_C;
-    sz_idx[s] = 4 * (win_ok ? nC : 0) + 2 * ((w + 3) & ~3) + 4 * m_pad;
+    sz_idx[s] = ((w + 3) & ~3) + 4 * m_pad;   // offsets padded to 16 bytes, then the mirror table (int4 entries)
     if (nM > 0) atomicAdd(n_mirrored, (unsigned long long)nM * SELL_C);
   }
   if (PASS == 1 && lane == 0) {
-    for (int32_t j = w_tot; j < w_al; ++j) { off_l[j] = 0; xpos_l[j] = 0; }
+    for (int32_t j = w_tot; j < w_al; ++j) sell_idx[ip + j] = 0;
     for (int32_t i = nM; i < m_pad; ++i) {
-      int32_t *tab = mir_tab + 4 * (int64_t)i;
+      int32_t *tab = sell_idx + ip + w_al + 4 * (int64_t)i;
       tab[0] = 0; tab[1] = (int32_t)zero_base; tab[2] = (int32_t)zero_base; tab[3] = SELL_C;
     }
   }
@@ -283,16 +249,15 @@ __global__ void __launch_bounds__(256) k_sell_layout(const int32_t *__restrict__
 // pass D: positions of the mirrored columns.  One thread per slice.
 __global__ void __launch_bounds__(256) k_sell_mirror(SliceGeo G, const uint8_t *__restrict__ sl_mode,
                                                      const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_m,
-                                                     const int32_t *__restrict__ sl_u, const int32_t *__restrict__ sl_x,
-                                                     const int64_t *__restrict__ valptr,
+                                                     const int32_t *__restrict__ sl_u, const int64_t *__restrict__ valptr,
                                                      const int64_t *__restrict__ idxptr, int32_t *__restrict__ sell_idx,
                                                      int64_t zero_base) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= G.n_slices) return;
-  const int32_t M = sl_m[s] & ~SELL_MB7;
+  const int32_t M = sl_m[s] & SELL_MMASK;
   if (M == 0) return;
   const int32_t w_al = ((sl_w[s] & 0x7fffffff) + 3) & ~3;
-  int32_t *tab = sell_idx + idxptr[s] + 4 * (sl_x[s] & 0xff) + 2 * w_al;
+  int32_t *tab = sell_idx + idxptr[s] + w_al;
   const int64_t n_blocks = G.n_slices / G.nf;
   for (int32_t i = 0; i < M; ++i) {
     const int32_t d = -tab[4 * i];
@@ -312,7 +277,7 @@ __global__ void __launch_bounds__(256) k_sell_mirror(SliceGeo G, const uint8_t *
       if (bb >= 0 && bb < n_blocks) {
         sp = bb * G.nf + cp;
         if (sl_mode[sp]) {
-          const int32_t *ol = sell_idx + idxptr[sp] + 4 * (sl_x[sp] & 0xff);   // offsets >= 0 first, ascending
+          const int32_t *ol = sell_idx + idxptr[sp];           // offsets >= 0 first, ascending
           int32_t lo = 0, hi = sl_u[sp];
           while (lo < hi) {
             const int32_t mid = (lo + hi) >> 1;
@@ -326,7 +291,7 @@ __global__ void __launch_bounds__(256) k_sell_mirror(SliceGeo G, const uint8_t *
     }
     tab[4 * i + 1] = pos[0];
     tab[4 * i + 2] = pos[1];
-    tab[4 * i + 3] = (tab[4 * i + 3] & ~0xff) | (int32_t)(SELL_C - dl);   // rows k < split use posA; xpos << 8 kept
+    tab[4 * i + 3] = (int32_t)(SELL_C - dl);                   // rows k < split use posA
   }
 }
 
@@ -370,10 +335,9 @@ int sell_build(apdx_plan *pl) {
     S.sym = !(e && e[0] == '0');
   }
   const int64_t ns = S.n_slices;
-  const SliceGeo G{pl->f0, pl->f1, rows, ns, S.nf};
+  const SliceGeo G{pl->f0, pl->f1, rows, ns, pl->n_free, S.nf};
   APDX_CHECK(S.sl_w.alloc(ns));
   APDX_CHECK(S.sl_m.alloc(ns));
-  APDX_CHECK(S.sl_x.alloc(ns));
   APDX_CHECK(S.valptr.alloc(ns + 1));
   APDX_CHECK(S.idxptr.alloc(ns + 1));
   APDX_CHECK(S.diag.alloc(rows));
@@ -393,8 +357,8 @@ int sell_build(apdx_plan *pl) {
   const unsigned grid = (unsigned)((ns * 32 + 255) / 256);
   k_sell_mode<<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, G, sl_mode.p);
   k_sell_layout<0><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, G, S.sym ? 1 : 0, sl_mode.p,
-                                        S.sl_w.p, S.sl_m.p, sl_u.p, S.sl_x.p, szv.p, szi.p, nullptr, nullptr, nullptr,
-                                        nullptr, nullptr, nullptr, 0, n_mir.p);
+                                        S.sl_w.p, S.sl_m.p, sl_u.p, szv.p, szi.p, nullptr, nullptr, nullptr, nullptr,
+                                        nullptr, nullptr, 0, n_mir.p);
   APDX_CHECK(scan64(szv.p, S.valptr.p, ns + 1, s));
   APDX_CHECK(scan64(szi.p, S.idxptr.p, ns + 1, s));
   int64_t tot[2];
@@ -408,24 +372,12 @@ int sell_build(apdx_plan *pl) {
   APDX_CHECK(S.src.alloc(S.n_val > 0 ? S.n_val : 1));
   APDX_CHECK(S.idx.alloc(S.n_idx > 0 ? S.n_idx : 1));
   k_sell_layout<1><<<grid, 256, 0, s>>>(pl->red_row_ptr.p, pl->red_col.p, pl->red2full.p, G, S.sym ? 1 : 0, sl_mode.p,
-                                        S.sl_w.p, S.sl_m.p, sl_u.p, S.sl_x.p, nullptr, nullptr, S.valptr.p, S.idxptr.p,
-                                        S.idx.p, S.src.p, S.diag.p, ghost.p, S.n_val, n_mir.p);
+                                        S.sl_w.p, S.sl_m.p, sl_u.p, nullptr, nullptr, S.valptr.p, S.idxptr.p, S.idx.p,
+                                        S.src.p, S.diag.p, ghost.p, S.n_val, n_mir.p);
   if (S.sym && ns > 0)
-    k_sell_mirror<<<(unsigned)((ns + 255) / 256), 256, 0, s>>>(G, sl_mode.p, S.sl_w.p, S.sl_m.p, sl_u.p, S.sl_x.p, S.valptr.p,
+    k_sell_mirror<<<(unsigned)((ns + 255) / 256), 256, 0, s>>>(G, sl_mode.p, S.sl_w.p, S.sl_m.p, sl_u.p, S.valptr.p,
                                                                S.idxptr.p, S.idx.p, S.n_val);
   APDX_CUDA(cudaStreamSynchronize(s));
-  {  // largest number of x entries a slice stages in shared memory (0 = some slice cannot: gather kernel)
-    std::vector<int32_t> xh((size_t)ns);
-    APDX_CUDA(cudaMemcpy(xh.data(), S.sl_x.p, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    int64_t cap = 0;
-    bool ok = true;
-    for (int64_t q = 0; q < ns; ++q) {
-      const int32_t wt = (int32_t)((uint32_t)xh[q] >> 8);
-      if (wt == 0x7fffff) ok = false;
-      else if (wt > cap) cap = wt;
-    }
-    S.win_cap = ok ? cap : 0;
-  }
   {  // entries read from their transposed position (diagnostics: apdx_plan_sell_info, tests)
     unsigned long long nm = 0;
     APDX_CUDA(cudaMemcpy(&nm, n_mir.p, sizeof(nm), cudaMemcpyDeviceToHost));

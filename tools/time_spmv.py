@@ -13,7 +13,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-VARIANTS = [("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")]   # (APDX_SELL_SYM, APDX_SPMV_WIN)
+VARIANTS = ["1", "0"]   # APDX_SELL_SYM: mirrored (symmetric) storage on / off
 CUBE = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
 
 
@@ -46,7 +46,7 @@ def main(model, n, reps):
     ms = plan.time_spmv(reps)
     alg = nnz * 12 + n_free * 16 + (n_free + 1) * 4
     impl = plan.stats().get("sell_bytes", 0.0) + n_free * 16
-    print(json.dumps({"sell_sym": os.environ.get("APDX_SELL_SYM", "default"), "win": os.environ.get("APDX_SPMV_WIN", "default"), "sell": plan.sell_info(), "model": model, "n": n, "n_free": n_free,
+    print(json.dumps({"sell_sym": os.environ.get("APDX_SELL_SYM", "default"), "sell": plan.sell_info(), "model": model, "n": n, "n_free": n_free,
                       "nnz": nnz, "ms": ms, "algorithmic_gbs": alg / ms * 1e-6, "implementation_gbs": impl / ms * 1e-6,
                       "y_sha1": hashlib.sha1(yh.tobytes()).hexdigest()[:16], "y_sum": float(yh.sum())}))
 
@@ -54,7 +54,7 @@ def main(model, n, reps):
 if __name__ == "__main__":
     if sys.argv[1] == "all":
         for v in VARIANTS:
-            env = dict(os.environ, APDX_SELL_SYM=v[0], APDX_SPMV_WIN=v[1])
+            env = dict(os.environ, APDX_SELL_SYM=v)
             subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[2:], env=env, check=False)
     else:
         main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 50)
