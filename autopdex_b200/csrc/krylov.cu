@@ -276,15 +276,17 @@ constexpr int SPMV_U = 9;
 // Fast paths for slices flagged SELL_FAST (every column of every row inside x: no index clamps) whose column count is
 // a multiple of the batch B: compile-time trip counts, no predicates, offsets / table entries read with warp-uniform
 // loads from cache lines prefetched when the slice's header arrived.  Half the instructions of the generic path.
-template <int B, bool SYM>
-__device__ __forceinline__ void spmv_stored_fast(const int32_t *__restrict__ offs, const double *__restrict__ vpc, int32_t nb,
+// XG: the x operands are fetched in groups of XG columns AFTER all B value loads of the batch have been issued (x
+// gathers are L1/L2 hits, the values come from HBM): with XG < B the registers hold twice as many value loads in
+// flight (B = 14: a whole slice of the symmetric P256 matrix in one round trip) at the price of short, cached
+// latencies in series.
+template <int B, int XG, bool SYM>
+__device__ __forceinline__ void spmv_stored_fast(int32_t offl, const double *__restrict__ vpc, int32_t nb,
                                                  const double *__restrict__ xr0, const double *__restrict__ xr1, double &a0,
                                                  double &a1) {
+  static_assert(B % XG == 0, "x groups must tile the batch");
   for (int32_t jb = 0; jb < nb; jb += B) {
-    int32_t off[B];
-    double va[B], vb[B], xa[B], xb[B];
-#pragma unroll
-    for (int u = 0; u < B; ++u) off[u] = __ldg(offs + jb + u);
+    double va[B], vb[B];
 #pragma unroll
     for (int u = 0; u < B; ++u) {
       const double *q = vpc + (size_t)(jb + u) * 64;
@@ -292,9 +294,17 @@ __device__ __forceinline__ void spmv_stored_fast(const int32_t *__restrict__ off
       vb[u] = SYM ? __ldg(q + 32) : __ldcs(q + 32);
     }
 #pragma unroll
-    for (int u = 0; u < B; ++u) { xa[u] = __ldg(xr0 + off[u]); xb[u] = __ldg(xr1 + off[u]); }
+    for (int g = 0; g < B; g += XG) {
+      int32_t off[XG];
+      double xa[XG], xb[XG];
 #pragma unroll
-    for (int u = 0; u < B; ++u) { a0 += va[u] * xa[u]; a1 += vb[u] * xb[u]; }
+      for (int u = 0; u < XG; ++u) off[u] = __shfl_sync(0xffffffffu, offl, jb + g + u);   // lane j holds column j's offset
+#pragma unroll
+      for (int u = 0; u < XG; ++u) { xa[u] = __ldg(xr0 + off[u]); xb[u] = __ldg(xr1 + off[u]); }
+#pragma unroll
+      for (int u = 0; u < XG; ++u) { a0 += va[g + u] * xa[u]; a1 += vb[g + u] * xb[u]; }
+      if (XG < B) asm volatile("" ::: "memory");   // keep the next group's gathers behind this group's FMAs
+    }
   }
 }
 template <int MB>
@@ -416,12 +426,11 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     for (int32_t jc = 0; jc < W; jc += 32) {
       const int32_t nb = min(32, W - jc);
       const int32_t nbt = (nb + SPMV_U - 1) / SPMV_U, bs = (nb + nbt - 1) / nbt;   // equal batches of <= SPMV_U columns
-      if (fast && nb % 9 == 0) {
-        spmv_stored_fast<9, SYM>(ip + jc, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
-      } else if (fast && nb % 8 == 0) {
-        spmv_stored_fast<8, SYM>(ip + jc, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
-      } else if (fast && nb % 7 == 0) {
-        spmv_stored_fast<7, SYM>(ip + jc, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+      if (fast && (nb % 9 == 0 || nb % 8 == 0 || nb % 7 == 0)) {
+        const int32_t offl = jc == 0 ? offl0 : __ldg(ip + jc + min(lane, nb - 1));
+        if (nb % 9 == 0) spmv_stored_fast<9, 9, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+        else if (nb % 8 == 0) spmv_stored_fast<8, 8, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+        else spmv_stored_fast<7, 7, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
       } else if (wenc < 0) {
         const int32_t offl = jc == 0 ? offl0 : __ldg(ip + jc + min(lane, nb - 1));
         for (int32_t jb = 0; jb < nb; jb += bs) {
