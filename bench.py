@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 UNIT_CUBE = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_spmv_sell<1> launch from `ncu --set full` (profiles/), by mesh size
-NCU_TRAFFIC = {256: 2.2391e9}     # profiles/r01e_k_spmv_sell_sym_p256_full.txt: 2.108 GB read + 0.131 GB written
+NCU_TRAFFIC = {256: 2.2391e9}     # profiles/r01f_k_spmv_sell_sym_p256_full.txt: 2.106 GB read + 0.133 GB written
 # SASS count of k_elem_scalar_reg<3,8,8,true>: 2592 DFMA + 368 DMUL + 316 DADD per element
 HEX8_POISSON_FLOP = 2 * 2592 + 368 + 316
 METRIC = "elements/s through one Newton step (sparse assembly + Jacobi-PCG to 1e-8)"
