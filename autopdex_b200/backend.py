@@ -269,6 +269,14 @@ class Plan:
         _lib.check(_lib.load().apdx_linear_step(self.h, C.byref(opts.c), dofs_d.ptr, dv, delta_d.ptr, C.byref(it)))
         return it.value
 
+    def tangent_solve(self, opts, dofs_d, rhs_d, out_d, transpose=False):
+        """out[free] = K(dofs)^-1 rhs[free] (K^-T with transpose; the in-scope tangents are symmetric), zeros on Dirichlet
+        dofs.  dofs_d=None reuses the tangent of the last assembly (implicit_diff.py:225-234)."""
+        it = C.c_int32(0)
+        _lib.check(_lib.load().apdx_tangent_solve(self.h, C.byref(opts.c), dofs_d.ptr if dofs_d is not None else None,
+                                                  rhs_d.ptr, int(bool(transpose)), out_d.ptr, C.byref(it)))
+        return it.value
+
     def newton(self, opts, dofs_d, dirichlet_values_d, newton_tol=1e-8, maxiter=30, damping=1.0):
         it, rn, dv = C.c_int32(0), C.c_double(0.0), C.c_int32(0)
         dvals = dirichlet_values_d.ptr if dirichlet_values_d is not None else None

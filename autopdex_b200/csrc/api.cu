@@ -55,6 +55,20 @@ __global__ void k_mixed_vector(const double *__restrict__ dofs, const int32_t *_
   int32_t q = free_id[i];
   out[i] = q >= 0 ? x[q] : dofs[i];  // solver.py:648-656
 }
+__global__ void k_rhs_gather(const double *__restrict__ rhs_full, const int32_t *__restrict__ free_list, int64_t n_free,
+                             double *__restrict__ rhs, double *__restrict__ x0) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_free) return;
+  rhs[q] = rhs_full[free_list[q]];
+  x0[q] = 0.0;
+}
+__global__ void k_free_scatter(const int32_t *__restrict__ free_id, const double *__restrict__ x, int64_t n,
+                               double *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t q = free_id[i];
+  out[i] = q >= 0 ? x[q] : 0.0;  // utility.mask_op(zeros, free_dofs_flat, u_f, 'set') (implicit_diff.py:229-232)
+}
 constexpr int NORM_GRID = 592;
 __global__ void __launch_bounds__(256) k_norm_partial(const double *__restrict__ residual,
                                                       const int32_t *__restrict__ free_list, int64_t q0, int64_t q1,
@@ -615,6 +629,34 @@ int apdx_linear_step(apdx_plan *pl, const apdx_krylov_opts *opts, const double *
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaStreamSynchronize(s));
   pl->stats.total_ms = pl->stats.asm_tangent_ms + pl->stats.krylov_ms;
+  return APDX_OK;
+}
+
+int apdx_tangent_solve(apdx_plan *pl, const apdx_krylov_opts *opts, const double *dofs_d, const double *rhs_d,
+                       int transpose, double *out_d, int32_t *krylov_iters) {
+  APDX_REQUIRE(pl && opts && rhs_d && out_d, APDX_ERR_INVALID, "NULL argument");
+  (void)transpose;   // A = A^T for every in-scope model (see the header)
+  APDX_CHECK(ensure_newton_buffers(pl));
+  cudaStream_t s = pl->stream;
+  pl->stats = Stats();
+  APDX_CUDA(cudaEventRecord(pl->ev[0], s));
+  if (dofs_d) APDX_CHECK(assemble_internal(pl, dofs_d, 4, pl->residual.p));
+  APDX_REQUIRE(pl->have_sell_values, APDX_ERR_STATE, "no assembled tangent: pass dofs_d or run a Newton step first");
+  k_rhs_gather<<<g1(pl->n_free), 256, 0, s>>>(rhs_d, pl->free_list.p, pl->n_free, pl->rhs_red.p, pl->x_red.p);
+  pl->stats.kernel_launches += 1;
+  APDX_CUDA(cudaEventRecord(pl->ev[1], s));
+  int32_t it = 0;
+  double rr = 0;
+  APDX_CHECK(krylov_solve(pl, opts, pl->rhs_red.p, pl->x_red.p, &it, &rr));
+  if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, pl->x_red.p, s));
+  k_free_scatter<<<g1(pl->n_dofs), 256, 0, s>>>(pl->free_id.p, pl->x_red.p, pl->n_dofs, out_d);
+  pl->stats.kernel_launches += 1;
+  APDX_CUDA(cudaEventRecord(pl->ev[2], s));
+  APDX_CUDA(cudaEventSynchronize(pl->ev[2]));
+  pl->stats.asm_tangent_ms = elapsed(pl->ev[0], pl->ev[1]);
+  pl->stats.krylov_ms = elapsed(pl->ev[1], pl->ev[2]);
+  pl->stats.total_ms = pl->stats.asm_tangent_ms + pl->stats.krylov_ms;
+  if (krylov_iters) *krylov_iters = it;
   return APDX_OK;
 }
 

@@ -332,6 +332,39 @@ def solver(dofs, settings, static_settings, newton_tol=1e-8, maxiter=30, damping
     return wrap(sol), infos
 
 
+def tangent_solve(dofs, rhs, settings, static_settings, transpose=False, tol=1e-10, atol=0.0, krylov_maxiter=0):
+    """Linear solve with the tangent at `dofs` for sensitivities: what the reference's implicit
+    differentiation asks of a solver backend, `solve_fun(mat, rhs, free_dofs_flat)` and `solve_fun(mat.T, ...)` with
+    `mat = assemble_tangent(sol)` (implicit_diff.py:139-183, 225-234, 274-304; backend dispatch solver.py:232-283).
+
+    `dofs` is the state the tangent is taken at (Dirichlet values are imposed as in the Newton step), `rhs` a dof-shaped
+    array (dict dofs: dict).  Returns the dof-shaped solution with zeros on the Dirichlet dofs, i.e.
+    `mask_op(zeros, free_dofs_flat, u_f, 'set')`.  `transpose=True` is the adjoint solve `A^T u = v` of `_root_vjp`; the
+    in-scope tangents are symmetric, so both run the same device solve.  The plan of `solver()` is reused."""
+    global last_stats
+    cfg = _Config(static_settings)
+    st = _state_for(cfg, dofs, settings)
+    st.update_fields(settings)
+    plan = st.plan
+    d0 = np.array(st._unwrap(dofs), dtype=np.float64)
+    if cfg.nodal_imposition:
+        dv = np.asarray(st._unwrap(settings["dirichlet conditions"]), dtype=np.float64).reshape(d0.shape)
+        mask = np.asarray(st._unwrap(settings["dirichlet dofs"]), dtype=bool).reshape(d0.shape)
+        d0[mask] = dv[mask]                                    # solver.py:586-604
+    r0 = np.ascontiguousarray(st._unwrap(rhs), dtype=np.float64)
+    if r0.shape != d0.shape:
+        raise ValueError("tangent_solve: rhs has shape %s, the dofs %s" % (r0.shape, d0.shape))
+    st.dofs_d.upload(d0.ravel())
+    st.vals_d.upload(r0.ravel())                               # staging buffer of the same size
+    st.h2d_bytes += d0.nbytes + r0.nbytes
+    opts = backend.KrylovOptions(cfg.krylov, rtol=tol, atol=atol, maxiter=krylov_maxiter, jacobi=cfg.jacobi)
+    plan.tangent_solve(opts, st.dofs_d, st.vals_d, st.out_d, transpose=transpose)
+    out = st.out_d.download().reshape(d0.shape)
+    st.d2h_bytes = out.nbytes
+    last_stats = dict(plan.stats(), h2d_bytes=st.h2d_bytes, d2h_bytes=st.d2h_bytes)
+    return {st.dict_key: out} if st.dict_key is not None else out
+
+
 def adaptive_load_stepping(dofs, settings, static_settings,
                            multiplier_settings=lambda settings, multiplier: (settings.update({"load multiplier": multiplier}), settings)[1],
                            path_dependent=True, implicit_diff_mode=None, max_multiplier=1.0, min_increment=0.01,

@@ -178,6 +178,14 @@ int apdx_linear_step(apdx_plan *plan, const apdx_krylov_opts *opts, const double
 int apdx_newton(apdx_plan *plan, const apdx_krylov_opts *opts, double *dofs_d,
                 const double *dirichlet_values_d, double newton_tol, int32_t maxiter, double damping,
                 int32_t *iters, double *res_norm, int32_t *diverged);
+/* Linear solve with the tangent for sensitivities (row N3 of SURVEY.md 8f): the device analogue of
+ * `solve_fun(mat, rhs, free_dofs_flat)` / `solve_fun(mat.T, ...)` inside implicit_diff._root_vjp / _root_jvp
+ * (implicit_diff.py:139-183, 225-234, 274-304) with mat = tangent at dofs_d:
+ *   out[free] = K[free][:, free]^-1 (or ^-T) rhs[free],  out[dirichlet] = 0   (utility.mask_op(zeros, free, u_f, 'set')).
+ * dofs_d == NULL reuses the tangent of the plan's last assembly.  transpose != 0 asks for the transposed solve: every
+ * in-scope tangent is symmetric (that is what the symmetric sliced-ELL storage relies on), so it is the same solve.   */
+int apdx_tangent_solve(apdx_plan *plan, const apdx_krylov_opts *opts, const double *dofs_d, const double *rhs_d,
+                       int transpose, double *out_d, int32_t *krylov_iters);
 /* timings (ms, CUDA events) and counters of the last apdx_newton / apdx_linear_step:
  * out[0]=assembly(tangent+residual) out[1]=assembly(residual only) out[2]=krylov
  * out[3]=krylov iterations out[4]=spmv launches out[5]=total out[6]=kernel launches

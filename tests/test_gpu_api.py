@@ -166,3 +166,28 @@ def test_assembler_module_matches_oracle():
     assert np.array_equal(K.indptr, full.indptr) and np.array_equal(K.indices, full.indices)
     assert np.abs(K.data - full.data).max() / np.abs(full.data).max() < 1e-12
     assert np.abs(R.ravel() - Ro).max() / np.abs(Ro).max() < 1e-12
+
+
+@pytest.mark.parametrize("transpose", [False, True])
+def test_tangent_solve_matches_reference_sensitivity_solve(transpose):
+    """`solve_fun(mat or mat.T, rhs, free_dofs_flat)` of implicit_diff._root_vjp/_root_jvp
+    (implicit_diff.py:139-183, 225-234) with mat = tangent at the converged Cook's membrane state, against SciPy."""
+    import scipy.sparse.linalg as spla
+    from autopdex_b200 import solver
+    p, settings, static_settings = _cook_settings("bicgstab")
+    settings = dict(settings, **{"load multiplier": 4.0})
+    sol, infos = solver.solver(np.zeros(p["mask"].shape), settings, static_settings, tol=1e-12)
+    assert not infos[2]
+    rhs = np.random.default_rng(11).standard_normal(p["mask"].shape)
+    u = solver.tangent_solve(sol, rhs, settings, static_settings, transpose=transpose, tol=1e-13)
+    # oracle tangent at the same state (sets carry the load multiplier through the traction parameter)
+    p4 = problems.cook_g2(q0=4.0)
+    n = p["mask"].size
+    free = ~p["mask"].ravel()
+    _, data = oasm.assemble(p4["sets"], p4["coords"], sol, {})
+    rows, cols = oasm.coo_indices(p4["sets"])
+    K = oasm.scipy_assembling(data, rows, cols, n, free)
+    ref = np.zeros(n)
+    ref[free] = spla.spsolve((K.T if transpose else K).tocsc(), rhs.ravel()[free])
+    assert np.all(u.ravel()[~free] == 0.0)
+    assert np.linalg.norm(u.ravel() - ref) < 1e-8 * np.linalg.norm(ref)
