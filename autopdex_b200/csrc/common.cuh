@@ -163,10 +163,12 @@ struct Sell {
   DevBuf<int64_t> idxptr;     // [n_slices+1] start of the slice's index block (int32)
   DevBuf<double> val;         // [n_val + 64] column-major per slice, then 64 zeros
   DevBuf<int32_t> idx;        // [n_idx] offsets + mirror table (offset mode) or columns (explicit mode)
-  DevBuf<int32_t> src;        // [n_val] full-CSR entry behind each position, -1 = padding
+  DevBuf<int32_t> src;        // [n_val] full-CSR entry behind each position, -1 = padding (build only)
+  DevBuf<int32_t> gl_ptr;     // [n_val+1] gather list of the assembly scatter per position (sell.cu)
+  DevBuf<uint32_t> gl_idx;    // element-stream indices, grouped by position, ascending COO order
   DevBuf<int32_t> diag;       // [n_rows] diagonal position relative to the slice's value block, -1 = none
   void release() {
-    sl_w.release(); sl_m.release(); valptr.release(); idxptr.release(); val.release(); idx.release(); src.release(); diag.release();
+    sl_w.release(); sl_m.release(); valptr.release(); idxptr.release(); val.release(); idx.release(); src.release(); diag.release(); gl_ptr.release(); gl_idx.release();
     built = false;
   }
 };
