@@ -5,7 +5,7 @@
 // gathered straight into registers, the shape tables live in the kernel-argument constant bank
 // (so dN/dxi and the weights are immediate operands of the DFMAs), the symmetric element tangent
 // (NEN(NEN+1)/2 accumulators) and the residual stay in registers over the fully unrolled Gauss
-// loop, and the results are stored entry-major (ke[ij][element]) so that every global store
+// loop, and the results are stored entry-major (ke[upper-triangle slot][element]) so that every global store
 // instruction of a warp writes 256 contiguous bytes.  Same closed forms as the generic kernel
 // (elements.cu), same reference citations: models.py:96-134 (poisson_weak), the README potential,
 // signed w*det J of models.py:1691-1694, 1257-1261.
@@ -114,16 +114,13 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_elem_scalar_reg(const __grid_con
     }
   }
 
-  // ---- entry-major stores: ke[ij][e], re[i][e]: consecutive threads (elements) write consecutive addresses ----
+  // ---- entry-major stores: ke[slot][e], re[i][e]: consecutive threads (elements) write consecutive addresses.  Only
+  // the NSYM upper-triangle slots exist: the gather lists address entry (a,b) and (b,a) through the same slot
+  // (pattern.cu: k_to_soa), which saves 28 of the 64 stores of a hex8 matrix ----
   if (!active) return;
   if constexpr (TANGENT) {
 #pragma unroll
-    for (int a = 0; a < NEN; ++a)
-#pragma unroll
-      for (int b = 0; b < NEN; ++b) {
-        const int lo = a < b ? a : b, hi = a < b ? b : a;
-        A.ke[(int64_t)(a * NEN + b) * A.n_rows + e] = K[lo * NEN - lo * (lo - 1) / 2 + (hi - lo)];
-      }
+    for (int i = 0; i < NSYM; ++i) A.ke[(int64_t)i * A.n_rows + e] = K[i];
   }
 #pragma unroll
   for (int a = 0; a < NEN; ++a) A.re[(int64_t)a * A.n_rows + e] = R[a];

@@ -50,6 +50,8 @@ __global__ void k_res_keys(const int32_t *__restrict__ conn, int64_t n_entries, 
 struct SoaSet {
   int64_t off, n_rows;
   int32_t width;   // ndof^2 (matrix stream) or ndof (vector stream)
+  int32_t sym_n;   // matrix stream of a register-kernel set: element matrices are stored as their upper triangle
+                   // (sym_n = ndof; entry (a,b) and (b,a) share slot lo*n - lo(lo-1)/2 + hi - lo); 0 = full storage
 };
 struct SoaTable {
   int n;
@@ -63,7 +65,13 @@ __global__ void k_to_soa(uint32_t *__restrict__ list, int64_t n, SoaTable t) {
   while (q + 1 < t.n && k >= t.s[q + 1].off) ++q;
   if (t.s[q].n_rows == 0) return;   // this set keeps the reference (element-major) layout
   const int64_t local = k - t.s[q].off;
-  const int64_t e = local / t.s[q].width, ij = local - e * t.s[q].width;
+  const int64_t e = local / t.s[q].width;
+  int64_t ij = local - e * t.s[q].width;
+  if (t.s[q].sym_n > 0) {
+    const int nn = t.s[q].sym_n, a = (int)(ij / nn), b = (int)(ij - (int64_t)a * nn);
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    ij = lo * nn - lo * (lo - 1) / 2 + (hi - lo);
+  }
   list[i] = (uint32_t)(t.s[q].off + ij * t.s[q].n_rows + e);
 }
 
@@ -247,7 +255,7 @@ int build_pattern(apdx_plan *pl, const uint8_t *mask_h) {
     SoaTable t{};
     for (auto &st : pl->sets) {
       if (st.d.n_rows == 0) continue;
-      t.s[t.n++] = SoaSet{st.res_offset, st.soa ? st.d.n_rows : 0, st.ndof_e};
+      t.s[t.n++] = SoaSet{st.res_offset, st.soa ? st.d.n_rows : 0, st.ndof_e, 0};
     }
     k_to_soa<<<grid_for(m, B), B, 0, s>>>(pl->rperm.p, m, t);
     APDX_CUDA(cudaStreamSynchronize(s));
@@ -301,7 +309,7 @@ int build_pattern(apdx_plan *pl, const uint8_t *mask_h) {
     SoaTable t{};
     for (auto &st : pl->sets) {
       if (st.d.n_rows == 0) continue;
-      t.s[t.n++] = SoaSet{st.coo_offset, st.soa ? st.d.n_rows : 0, st.ndof_e * st.ndof_e};
+      t.s[t.n++] = SoaSet{st.coo_offset, st.soa ? st.d.n_rows : 0, st.ndof_e * st.ndof_e, st.soa ? st.ndof_e : 0};
     }
     k_to_soa<<<grid_for(nc, B), B, 0, s>>>(pl->perm.p, nc, t);   // after k_unique_fill, which needs reference-order indices
     APDX_CUDA(cudaStreamSynchronize(s));
