@@ -121,9 +121,11 @@ struct P2PDev {
   int *mflag[P2P_MAX_RANKS];     // rank r's mailbox flags: int [2 slots][P2P_MAX_RANKS senders]
   int *hflag_self;               // my halo flags: [0] written by the lower neighbour, [1] by the upper one
   int *err;                      // my time-out flag
+  int *epoch_self;               // device-resident reduction counter of the mailbox all-reduce (mbox mode)
 };
 struct P2P {
-  bool enabled = false;
+  bool enabled = false;          // Krylov vectors in the heap, halo by peer stores, mailbox reductions (APDX_COMM=p2p|fused)
+  bool mbox = false;             // only the dot-product all-reduces go through the mailboxes; halo stays on NCCL
   char *heap = nullptr;          // symmetric heap: [mailboxes | flags | 3 Krylov vectors of `stride` doubles]
   size_t heap_bytes = 0;
   void *peer_base[P2P_MAX_RANKS]{};

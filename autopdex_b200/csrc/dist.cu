@@ -131,6 +131,7 @@ static inline double *hdr_mbox(void *base) { return reinterpret_cast<double *>(b
 static inline int *hdr_mflag(void *base) { return reinterpret_cast<int *>(static_cast<char *>(base) + 2 * P2P_MAX_RANKS * 4 * sizeof(double)); }
 static inline int *hdr_hflag(void *base) { return hdr_mflag(base) + 2 * P2P_MAX_RANKS; }
 static inline int *hdr_err(void *base) { return hdr_hflag(base) + 2; }
+static inline int *hdr_epoch(void *base) { return hdr_err(base) + 1; }
 static inline double *hdr_vec(void *base) { return reinterpret_cast<double *>(static_cast<char *>(base) + P2P_HDR); }
 
 bool p2p_is_heap_vector(const apdx_plan *pl, const double *v) {
@@ -162,8 +163,11 @@ static void p2p_free_parked() {
 int p2p_setup(apdx_plan *pl) {
   P2P &P = pl->p2p;
   const char *mode = getenv("APDX_COMM");
-  // opt-in A/B variants of the Krylov loop (APDX_COMM=p2p | fused); the default multi-GPU path is NCCL
-  if (!mode || (strcmp(mode, "p2p") != 0 && strcmp(mode, "fused") != 0)) return APDX_OK;
+  // APDX_COMM: mbox = dot-product all-reduces through peer-memory mailboxes, halo on NCCL; p2p | fused = opt-in A/B
+  // variants that also move the halo to peer stores; nccl / cg2 = NCCL only
+  const bool full = mode && (strcmp(mode, "p2p") == 0 || strcmp(mode, "fused") == 0);
+  const bool mbox = mode && strcmp(mode, "mbox") == 0;
+  if (!full && !mbox) return APDX_OK;
   if (g_nccl.nranks > P2P_MAX_RANKS) return APDX_OK;
   p2p_teardown(pl);
   cudaStream_t s = pl->stream;
@@ -177,7 +181,7 @@ int p2p_setup(apdx_plan *pl) {
   APDX_CUDA(cudaStreamSynchronize(s));
   APDX_CUDA(cudaMemcpy(&nf, dmax, sizeof(double), cudaMemcpyDeviceToHost));
   cudaFree(dmax);
-  P.stride = (int64_t)nf;
+  P.stride = full ? (int64_t)nf : 0;   // mbox mode: header only
   P.heap_bytes = P2P_HDR + 3 * (size_t)P.stride * sizeof(double);
   APDX_CUDA(cudaMalloc((void **)&P.heap, P.heap_bytes));
   APDX_CUDA(cudaMemset(P.heap, 0, P.heap_bytes));
@@ -231,11 +235,13 @@ int p2p_setup(apdx_plan *pl) {
   for (int r = 0; r < nr; ++r) { d.mbox[r] = hdr_mbox(P.peer_base[r]); d.mflag[r] = hdr_mflag(P.peer_base[r]); }
   d.hflag_self = hdr_hflag(P.heap);
   d.err = P.err_d;
+  d.epoch_self = hdr_epoch(P.heap);
   APDX_CUDA(cudaMalloc((void **)&P.dev, sizeof(P2PDev)));
   APDX_CUDA(cudaMemcpy(P.dev, &d, sizeof(P2PDev), cudaMemcpyHostToDevice));
   P.red_epoch = 0;
   P.halo_epoch = 0;
-  P.enabled = true;
+  P.enabled = full;
+  P.mbox = mbox;
   if (getenv("APDX_VERBOSE")) fprintf(stderr, "[apdx_b200] rank %d: peer-to-peer Krylov loop enabled (heap %.1f MB, stride %lld)\n", me, P.heap_bytes / 1e6, (long long)P.stride);
   return APDX_OK;
 }

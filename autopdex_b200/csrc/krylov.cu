@@ -146,6 +146,37 @@ __global__ void k_apply_stage_p2p(int stage, int nv, double *sc, int32_t *fl, co
   }
 }
 
+// mbox mode: the whole all-reduce of a dot-product stage in ONE small kernel -- post the local sums into every rank's
+// mailbox (peer stores over NVLink), raise the flags, wait for every rank's post, sum in rank order (identical bits on
+// all ranks), run the scalar recurrence.  The reduction counter lives on the device (every rank runs the same
+// sequence of reductions), so the kernel has no per-launch argument and can be replayed inside the CUDA graph of a
+// Krylov chunk.  Replaces ncclAllReduce (8-24 bytes, ~22 us) + k_apply_stage.  Mailboxes are double-buffered by the
+// parity of the counter: a rank can be at most one reduction ahead of the slowest one.
+__global__ void k_allreduce_mbox_apply(int stage, int nv, double *sc, int32_t *fl, const P2PDev *pd) {
+  if (fl[F_DONE] && stage != ST_CG_INIT && stage != ST_BI_INIT && stage != ST_CG2_INIT) return;
+  const int e = *pd->epoch_self + 1;
+  const int slot = e & 1;
+  const int r = threadIdx.x;
+  if (r < pd->nranks) {
+    double *mb = pd->mbox[r] + ((size_t)slot * P2P_MAX_RANKS + pd->rank) * 4;
+    for (int i = 0; i < nv; ++i) mb[i] = sc[S_PEND + i];
+    __threadfence_system();
+    *(volatile int *)(pd->mflag[r] + slot * P2P_MAX_RANKS + pd->rank) = e;
+    p2p_wait(pd->mflag[pd->rank] + slot * P2P_MAX_RANKS + r, e, pd->err);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const volatile double *mbs = pd->mbox[pd->rank] + (size_t)slot * P2P_MAX_RANKS * 4;
+    for (int i = 0; i < nv; ++i) {
+      double s = 0.0;
+      for (int q = 0; q < pd->nranks; ++q) s += mbs[q * 4 + i];
+      sc[S_PEND + i] = s;
+    }
+    apply_stage(stage, sc, fl);
+    *pd->epoch_self = e;
+  }
+}
+
 // copy the owned boundary entries of a heap vector into the neighbours' ghost ranges (peer stores over
 // NVLink), then raise their halo flags for this epoch
 __global__ void __launch_bounds__(VEC_BLOCK) k_halo_push(const double *__restrict__ v, int64_t f0, int64_t f1,
@@ -804,8 +835,8 @@ static int krylov_alloc_bicgstab(apdx_plan *pl) {
 // comm modes: single GPU (dot products finalised inside the kernel), NCCL (ncclSend/Recv halo + ncclAllReduce
 // + one-thread scalar kernel), P2P (peer stores over NVLink: k_halo_push + mailbox all-reduce, no NCCL in the loop)
 struct Comm {
-  bool multi, p2p;
-  const P2PDev *pd;
+  bool multi, p2p, mbox;
+  const P2PDev *pd, *mpd;
   int fused;
 };
 static Comm comm_of(apdx_plan *pl) {
@@ -813,6 +844,8 @@ static Comm comm_of(apdx_plan *pl) {
   c.multi = comm_active();
   c.p2p = c.multi && pl->p2p.enabled;
   c.pd = c.p2p ? pl->p2p.dev : nullptr;
+  c.mbox = c.multi && !c.p2p && pl->p2p.mbox;
+  c.mpd = c.mbox ? pl->p2p.dev : nullptr;
   c.fused = c.multi ? 0 : 1;
   return c;
 }
@@ -896,6 +929,8 @@ static int finish_stage(apdx_plan *pl, int stage, int nv) {
   KrylovWork &k = pl->kw;
   if (c.p2p) {
     k_apply_stage_p2p<<<1, 32, 0, pl->stream>>>(stage, nv, k.scal.p, k.flags.p, c.pd, pl->p2p.red_epoch);
+  } else if (c.mbox) {
+    k_allreduce_mbox_apply<<<1, 32, 0, pl->stream>>>(stage, nv, k.scal.p, k.flags.p, c.mpd);
   } else {
     APDX_CHECK(comm_allreduce_sum(k.scal.p + S_PEND, nv, pl->stream));
     k_apply_stage<<<1, 1, 0, pl->stream>>>(stage, k.scal.p, k.flags.p);
@@ -1138,7 +1173,7 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
     };
     // CUDA graph of one chunk of iterations: the loop is launch-bound for small systems and at high GPU counts.
     // Kernels turn into no-ops once the device-side done flag is set, so replaying a whole chunk is always safe.
-    const int mode_id = cg2 ? 1 : (c.multi ? 2 : 0);
+    const int mode_id = cg2 ? 1 : (c.mbox ? 3 : (c.multi ? 2 : 0));
     const bool graph_ok = graphs_on && !tracing && !c.p2p && todo == chunk;
     KrylovGraph &G = pl->kgraph[bi ? 1 : 0];
     if (graph_ok && G.exec && G.rhs == rhs && G.x == x && G.mode == mode_id && G.chunk == chunk && G.i0 == i0 && G.i1 == i1) {
@@ -1183,7 +1218,7 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
     }
   }
   APDX_CUDA(cudaGetLastError());
-  if (c.p2p) {
+  if (c.p2p || c.mbox) {
     int err = 0;
     APDX_CUDA(cudaMemcpy(&err, pl->p2p.err_d, sizeof(int), cudaMemcpyDeviceToHost));
     APDX_REQUIRE(err == 0, APDX_ERR_NCCL, "peer-to-peer wait timed out (a rank stopped posting halos / reductions)");
