@@ -351,9 +351,21 @@ int sell_build(apdx_plan *pl) {
   S.n_rows = rows;
   S.nf = pl->nf;
   S.n_slices = ((rows + (int64_t)SELL_C * S.nf - 1) / ((int64_t)SELL_C * S.nf)) * S.nf;
-  {  // symmetric storage is the default; APDX_SELL_SYM=0 keeps every column (A/B measurements, unsymmetric operators)
+  {  // symmetric storage is the default; APDX_SELL_SYM=0 keeps every column (A/B measurements)
     const char *e = getenv("APDX_SELL_SYM");
     S.sym = !(e && e[0] == '0');
+    // the premise, per set: the element tangent of the model is symmetric.  True for every model of the C ABI today
+    // (potential Hessians, Galerkin forms with symmetric constitutive tensors, the capacity matrix; Neumann sets have
+    // no tangent); a model that is not listed here switches the whole plan to full storage.
+    for (const SetData &st : pl->sets) {
+      switch (st.d.model) {
+        case APDX_MODEL_POISSON_POTENTIAL: case APDX_MODEL_POISSON_WEAK: case APDX_MODEL_LINEAR_ELASTICITY:
+        case APDX_MODEL_NEO_HOOKE: case APDX_MODEL_NEUMANN: case APDX_MODEL_CAPACITY:
+          break;
+        default:
+          S.sym = false;
+      }
+    }
   }
   const int64_t ns = S.n_slices;
   const SliceGeo G{pl->f0, pl->f1, rows, ns, pl->n_free, S.nf};
