@@ -27,7 +27,7 @@ enum {
   S_PEND = 16,  // pending (locally reduced) sums of the running stage, up to 4
   S_COUNT = 24
 };
-enum { F_DONE = 0, F_ITERS = 1, F_BREAKDOWN = 2, F_MAXITER = 3, F_COUNT = 4 };
+enum { F_DONE = 0, F_ITERS = 1, F_BREAKDOWN = 2, F_MAXITER = 3, F_FINAL = 4, F_COUNT = 5 };   // F_FINAL: see k_cg_p
 // stages of the scalar recurrences
 enum { ST_CG_INIT = 0, ST_CG_PQ, ST_CG_UPDATE, ST_BI_INIT, ST_BI_R0V, ST_BI_S, ST_BI_T, ST_BI_X, ST_CG2_INIT, ST_CG2_ITER };
 
@@ -554,32 +554,96 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_cg_init(const double *__restrict_
   }
   reduce_finalize<3>(acc, partial, ticket, sc, fl, stage, fused, pd, epoch);
 }
-// x += alpha p ; r -= alpha q ; sums (r.(minv r), r.r)
-__global__ void __launch_bounds__(VEC_BLOCK) k_cg_update(const double *__restrict__ p, const double *__restrict__ q,
-                                                         const double *__restrict__ minv, double *__restrict__ x,
-                                                         double *__restrict__ r, int64_t i0, int64_t i1,
-                                                         double *partial, unsigned int *ticket, double *sc,
-                                                         int32_t *fl, int fused, const P2PDev *pd, int epoch) {
+// The two vector kernels of a CG iteration.  x += alpha p rides with the p-update, where p is read anyway (10 vector
+// streams per iteration instead of 11):
+//   k_cg_update:  r -= alpha q ; sums (r.(minv r), r.r)                       reads q r minv, writes r
+//   k_cg_p:       x += alpha p ; p = minv r + beta p                           reads p x r minv, writes x p
+// The iteration that sets the done flag (in the scalar stage after k_cg_update) still owes x its update: k_cg_p applies
+// it regardless of the flag and its last block then raises F_FINAL, which turns the k_cg_p launches of the remaining
+// (no-op) iterations of a replayed chunk off.  VEC: 16-byte accesses over the even-aligned body of [i0, i1).
+template <bool VEC>
+__global__ void __launch_bounds__(VEC_BLOCK) k_cg_update(const double *__restrict__ q, const double *__restrict__ minv,
+                                                         double *__restrict__ r, int64_t i0, int64_t i1, double *partial,
+                                                         unsigned int *ticket, double *sc, int32_t *fl, int fused,
+                                                         const P2PDev *pd, int epoch) {
   if (fl[F_DONE]) return;
   const double alpha = sc[S_ALPHA];
   double acc[2] = {0.0, 0.0};
-  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
-    x[i] += alpha * p[i];
-    double ri = r[i] - alpha * q[i];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  auto one = [&](int64_t i) {
+    const double ri = r[i] - alpha * q[i];
     r[i] = ri;
     acc[0] += ri * (minv[i] * ri);
     acc[1] += ri * ri;
+  };
+  if (VEC) {
+    const int64_t a0 = (i0 + 1) & ~(int64_t)1;
+    int64_t a1 = i1 & ~(int64_t)1;
+    if (a1 < a0) a1 = a0;
+    const double2 *q2 = reinterpret_cast<const double2 *>(q), *m2 = reinterpret_cast<const double2 *>(minv);
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    for (int64_t j = a0 / 2 + tid; j < a1 / 2; j += nth) {
+      const double2 qv = q2[j], mv = m2[j];
+      double2 rv = r2[j];
+      rv.x -= alpha * qv.x;
+      rv.y -= alpha * qv.y;
+      r2[j] = rv;
+      acc[0] += rv.x * (mv.x * rv.x) + rv.y * (mv.y * rv.y);
+      acc[1] += rv.x * rv.x + rv.y * rv.y;
+    }
+    if (tid == 0 && i0 < a0 && i0 < i1) one(i0);
+    if (tid == 1 && a1 < i1 && a1 >= a0) one(a1);
+  } else {
+    for (int64_t i = i0 + tid; i < i1; i += nth) one(i);
   }
   reduce_finalize<2>(acc, partial, ticket, sc, fl, ST_CG_UPDATE, fused, pd, epoch);
 }
-// p = minv r + beta p
+template <bool VEC>
 __global__ void __launch_bounds__(VEC_BLOCK) k_cg_p(const double *__restrict__ r, const double *__restrict__ minv,
-                                                    double *__restrict__ p, int64_t i0, int64_t i1, const double *sc,
-                                                    const int32_t *fl) {
-  if (fl[F_DONE]) return;
-  const double beta = sc[S_BETA];
-  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = minv[i] * r[i] + beta * p[i];
+                                                    double *__restrict__ p, double *__restrict__ x, int64_t i0, int64_t i1,
+                                                    const double *sc, int32_t *fl, unsigned int *ticket) {
+  if (fl[F_FINAL]) return;
+  const bool done = fl[F_DONE] != 0;
+  const double alpha = sc[S_ALPHA], beta = sc[S_BETA];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  auto one = [&](int64_t i) {
+    const double pi = p[i];
+    x[i] += alpha * pi;
+    if (!done) p[i] = minv[i] * r[i] + beta * pi;
+  };
+  if (VEC) {
+    const int64_t a0 = (i0 + 1) & ~(int64_t)1;
+    int64_t a1 = i1 & ~(int64_t)1;
+    if (a1 < a0) a1 = a0;
+    const double2 *r2 = reinterpret_cast<const double2 *>(r), *m2 = reinterpret_cast<const double2 *>(minv);
+    double2 *p2 = reinterpret_cast<double2 *>(p), *x2 = reinterpret_cast<double2 *>(x);
+    for (int64_t j = a0 / 2 + tid; j < a1 / 2; j += nth) {
+      const double2 pv = p2[j];
+      double2 xv = x2[j];
+      xv.x += alpha * pv.x;
+      xv.y += alpha * pv.y;
+      x2[j] = xv;
+      if (!done) {
+        const double2 rv = r2[j], mv = m2[j];
+        p2[j] = make_double2(mv.x * rv.x + beta * pv.x, mv.y * rv.y + beta * pv.y);
+      }
+    }
+    if (tid == 0 && i0 < a0 && i0 < i1) one(i0);
+    if (tid == 1 && a1 < i1 && a1 >= a0) one(a1);
+  } else {
+    for (int64_t i = i0 + tid; i < i1; i += nth) one(i);
+  }
+  if (done) {   // the last block to finish marks x as final (every block has read F_FINAL before taking its ticket)
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+      *ticket = 0u;
+      fl[F_FINAL] = 1;
+    }
+  }
 }
 
 // ---- single-reduction CG (Chronopoulos & Gear) for the multi-GPU path: one vector kernel + one SpMV and ONE
@@ -1015,7 +1079,7 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
   double sc_h[S_COUNT] = {0};
   sc_h[S_TOL2] = o->rtol * o->rtol;
   sc_h[S_SS] = o->atol * o->atol;
-  int32_t fl_h[F_COUNT] = {0, 0, 0, maxiter};
+  int32_t fl_h[F_COUNT] = {0, 0, 0, maxiter, 0};
   APDX_CUDA(cudaMemcpyAsync(k.scal.p, sc_h, sizeof(sc_h), cudaMemcpyHostToDevice, s));
   APDX_CUDA(cudaMemcpyAsync(k.flags.p, fl_h, sizeof(fl_h), cudaMemcpyHostToDevice, s));
   pl->stats.kernel_launches += 1;
@@ -1055,6 +1119,8 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
   const char *ge = getenv("APDX_GRAPH");
   const bool graphs_on = !(ge && strcmp(ge, "0") == 0);
   std::vector<std::pair<cudaEvent_t, int>> trace;
+  // 16-byte vector accesses in the CG vector kernels need every vector 16-byte aligned at even indices
+  const bool vec16 = (((uintptr_t)x | (uintptr_t)k.r.p | (uintptr_t)k.p.p | (uintptr_t)k.q.p | (uintptr_t)k.minv.p) & 15) == 0;
   // p2p-fused CG keeps the scalar state double-buffered in st_sc / st_fl; half 0 aliases k.scal / k.flags
   const bool pfused = !bi && c.p2p && pl->sell.nf == 1 && p2p_is_heap_vector(pl, k.p.p) && !(cm && strcmp(cm, "p2p") == 0);
   while (true) {
@@ -1137,12 +1203,15 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
         TR(1);
         APDX_CHECK(finish_stage(pl, ST_CG_PQ, 1));
         TR(2);
-        k_cg_update<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.p.p, k.q.p, k.minv.p, x, k.r.p, i0, i1, k.partial.p,
-                                                   k.ticket.p, k.scal.p, k.flags.p, fused, pd, next_red_epoch(pl));
+        if (vec16) k_cg_update<true><<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.q.p, k.minv.p, k.r.p, i0, i1, k.partial.p, k.ticket.p, k.scal.p,
+                                                                   k.flags.p, fused, pd, next_red_epoch(pl));
+        else k_cg_update<false><<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.q.p, k.minv.p, k.r.p, i0, i1, k.partial.p, k.ticket.p, k.scal.p,
+                                                               k.flags.p, fused, pd, next_red_epoch(pl));
         TR(3);
         APDX_CHECK(finish_stage(pl, ST_CG_UPDATE, 2));
         TR(4);
-        k_cg_p<<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.minv.p, k.p.p, i0, i1, k.scal.p, k.flags.p);
+        if (vec16) k_cg_p<true><<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.minv.p, k.p.p, x, i0, i1, k.scal.p, k.flags.p, k.ticket.p + 1);
+        else k_cg_p<false><<<VEC_GRID, VEC_BLOCK, 0, s>>>(k.r.p, k.minv.p, k.p.p, x, i0, i1, k.scal.p, k.flags.p, k.ticket.p + 1);
         TR(5);
         pl->stats.kernel_launches += 2;
       } else {
