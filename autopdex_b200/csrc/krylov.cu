@@ -537,212 +537,6 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     reduce_finalize<NDOT>(acc, partial, ticket, sc, fl, stage, fused, pd, epoch, 0, rg.blk0, rg.nblk_total, rg.finalize);
 }
 
-// ---- SpMV with the stored values streamed by bulk async copies (TMA) ------------------------------------------------
-// Same storage and the same arithmetic per row as k_spmv_sell.  With symmetric storage k_spmv_sell is bound by the
-// loads a warp can keep in flight in REGISTERS (16 warps x 7 columns per SM, long-scoreboard stalls, DRAM 55 % busy).
-// Here the stored value block of a slice -- one contiguous run of W x 512 bytes -- is streamed HBM -> shared memory
-// by 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) in chunks of TMA_CH columns: every warp is an
-// independent pipeline with a ring of TMA_STAGES chunks that lane 0 keeps full (16 KB in flight per warp, no
-// registers), so the value stream is decoupled from the consumer.  The lanes gather the x operands of a chunk (L1/L2
-// hits), wait on the chunk's mbarrier and run the FMAs out of shared memory; the mirrored columns (L2 hits) follow as
-// in k_spmv_sell.  One block of TMA_WARPS warps per SM.
-constexpr int TMA_WARPS = 12, TMA_CH = 8, TMA_STAGES = 4;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-template <int NDOT, int NF>
-__global__ void __launch_bounds__(TMA_WARPS * 32, 1)
-    k_spmv_sell_tma(const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_m, const int64_t *__restrict__ valptr,
-                    const int64_t *__restrict__ idxptr, const double *__restrict__ val, const int32_t *__restrict__ idx,
-                    const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, int64_t row0,
-                    int64_t row1, int64_t n_slices, int32_t n_cols, double *partial, unsigned int *ticket, double *sc,
-                    int32_t *fl, int stage, int fused, int check_done, const P2PDev *pd, int epoch, int halo_epoch,
-                    SliceRange rg) {
-  if (check_done && fl[F_DONE]) return;
-  if (pd && halo_epoch > 0) {
-    if (threadIdx.x == 0) {
-      if (pd->has_lo) p2p_wait(pd->hflag_self + 0, halo_epoch, pd->err);
-      if (pd->has_hi) p2p_wait(pd->hflag_self + 1, halo_epoch, pd->err);
-    }
-    __syncthreads();
-  }
-  extern __shared__ __align__(128) unsigned char tma_smem[];
-  __shared__ __align__(8) uint64_t tma_bar[TMA_WARPS][TMA_STAGES];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double *const ring = reinterpret_cast<double *>(tma_smem) + (size_t)wid * TMA_STAGES * TMA_CH * 64;
-  const uint32_t ring_u = smem_u32(ring), bar_u = smem_u32(&tma_bar[wid][0]);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < TMA_STAGES; ++i) mbar_init(bar_u + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncwarp();
-  const int64_t n_a = rg.a1 - rg.a0;
-  const int64_t n_mine = n_a + (rg.b1 - rg.b0);
-  const int64_t si_begin = (int64_t)blockIdx.x * TMA_WARPS + wid;
-  const int64_t si_step = (int64_t)gridDim.x * TMA_WARPS;
-  auto slice_of = [&](int64_t si) { return si < n_a ? rg.a0 + si : rg.b0 + (si - n_a); };
-
-  // ---- producer cursor (warp-uniform; only lane 0 issues): chunks of the warp's slices in consumption order ----
-  int64_t p_si = si_begin, p_vp = 0, pn_vp = 0;
-  int32_t p_W = 0, p_c = 0, pn_W = 0;
-  uint32_t p_k = 0, c_k = 0;
-  if (p_si < n_mine) { const int64_t s = slice_of(p_si); p_W = sl_w[s] & 0x7fffffff; p_vp = valptr[s]; }
-  if (p_si + si_step < n_mine) { const int64_t s = slice_of(p_si + si_step); pn_W = sl_w[s] & 0x7fffffff; pn_vp = valptr[s]; }
-  auto produce = [&]() {
-    while (p_si < n_mine && p_c >= p_W) {   // next slice (its header was requested one slice ago)
-      p_si += si_step;
-      p_W = pn_W; p_vp = pn_vp; p_c = 0;
-      pn_W = 0;
-      if (p_si + si_step < n_mine) { const int64_t s = slice_of(p_si + si_step); pn_W = sl_w[s] & 0x7fffffff; pn_vp = valptr[s]; }
-    }
-    if (p_si >= n_mine) return;
-    const int32_t cols = min(TMA_CH, p_W - p_c);
-    if (lane == 0) {
-      const uint32_t st = p_k % TMA_STAGES;
-      mbar_expect_tx(bar_u + 8 * st, (uint32_t)cols * 512u);
-      bulk_g2s(ring_u + st * (TMA_CH * 512), val + p_vp + (int64_t)p_c * 64, (uint32_t)cols * 512u, bar_u + 8 * st);
-    }
-    p_c += cols;
-    ++p_k;
-  };
-#pragma unroll 1
-  for (int i = 0; i < TMA_STAGES; ++i) produce();
-
-  double acc[NDOT > 0 ? NDOT : 1];
-#pragma unroll
-  for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
-  struct Hdr { int32_t wenc, M; int64_t ip; };
-  auto load_hdr = [&](int64_t si, Hdr &h) {
-    h.wenc = 0; h.M = 0; h.ip = 0;
-    if (si < n_mine) {
-      const int64_t s = slice_of(si);
-      h.wenc = sl_w[s];
-      h.M = sl_m[s];
-      h.ip = idxptr[s];
-    }
-  };
-  auto load_offsets = [&](const Hdr &h) -> int32_t {
-    const int32_t W = h.wenc & 0x7fffffff;
-    if (h.wenc >= 0 || W == 0) return 0;
-    const int32_t rec_ints = ((W + 3) & ~3) + 4 * (h.M & SELL_MMASK);
-    if (lane * 32 < rec_ints) asm volatile("prefetch.global.L1 [%0];" ::"l"(idx + h.ip + lane * 32));
-    return __ldg(idx + h.ip + min(lane, min(32, W) - 1));
-  };
-  Hdr cur;
-  load_hdr(si_begin, cur);
-  int32_t offl0 = load_offsets(cur);
-  for (int64_t si = si_begin; si < n_mine; si += si_step) {
-    Hdr nxt;
-    load_hdr(si + si_step, nxt);
-    const int64_t s = slice_of(si);
-    const int32_t wenc = cur.wenc;
-    const int32_t W = wenc & 0x7fffffff;
-    const int32_t M = cur.M & SELL_MMASK;
-    const bool fast = (cur.M & SELL_FAST) != 0;
-    const int64_t r0 = row0 + (s / NF) * (int64_t)64 * NF + (s % NF) + (int64_t)NF * lane;
-    const int64_t r1 = r0 + (int64_t)32 * NF;
-    const int32_t rr0 = (int32_t)r0, rr1 = (int32_t)r1;
-    const double *xr0 = x + r0, *xr1 = x + r1;
-    const int32_t *ip = idx + cur.ip;
-    const int4 *tab = reinterpret_cast<const int4 *>(ip + ((W + 3) & ~3));
-    double a0 = 0.0, a1 = 0.0;
-    int32_t offl = offl0;
-    for (int32_t c = 0; c < W; c += TMA_CH) {
-      const int32_t cols = min(TMA_CH, W - c);
-      // the x operands of the chunk first: they do not depend on the values
-      double xa[TMA_CH], xb[TMA_CH];
-      if (wenc < 0) {
-        if ((c & 31) == 0 && c > 0) offl = __ldg(ip + c + min(lane, min(32, W - c) - 1));   // next 32 offsets, one per lane
-        if (fast) {
-#pragma unroll
-          for (int u = 0; u < TMA_CH; ++u) {
-            const int32_t off = __shfl_sync(0xffffffffu, offl, min(c + u, W - 1) & 31);
-            xa[u] = __ldg(xr0 + off);
-            xb[u] = __ldg(xr1 + off);
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < TMA_CH; ++u) {
-            const int32_t off = __shfl_sync(0xffffffffu, offl, min(c + u, W - 1) & 31);
-            xa[u] = __ldg(x + min(max(rr0 + off, 0), n_cols - 1));
-            xb[u] = __ldg(x + min(max(rr1 + off, 0), n_cols - 1));
-          }
-        }
-      } else {
-        const int32_t *cp = ip + lane;
-#pragma unroll
-        for (int u = 0; u < TMA_CH; ++u) {
-          const size_t o = (size_t)min(c + u, W - 1) * 64;
-          xa[u] = __ldg(x + __ldcs(cp + o));
-          xb[u] = __ldg(x + __ldcs(cp + o + 32));
-        }
-      }
-      const uint32_t st = c_k % TMA_STAGES, par = (c_k / TMA_STAGES) & 1u;
-      while (!mbar_try_wait(bar_u + 8 * st, par)) {}
-      const double *vs = ring + (size_t)st * TMA_CH * 64 + lane;
-#pragma unroll
-      for (int u = 0; u < TMA_CH; ++u)
-        if (u < cols) {
-          a0 += vs[u * 64] * xa[u];
-          a1 += vs[u * 64 + 32] * xb[u];
-        }
-      __syncwarp();   // every lane has consumed the stage: lane 0 may refill it
-      ++c_k;
-      produce();
-    }
-    const int32_t offl_n = load_offsets(nxt);
-    if (M > 0) {
-      if (fast) {
-        if (cur.M & SELL_MB7) spmv_mirrored_fast<7>(tab, M, val, xr0, xr1, lane, a0, a1);
-        else spmv_mirrored_fast<8>(tab, M, val, xr0, xr1, lane, a0, a1);
-      } else {
-        if (cur.M & SELL_MB7) spmv_mirrored<7>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
-        else spmv_mirrored<8>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
-      }
-    }
-    cur = nxt;
-    offl0 = offl_n;
-    if (r0 < row1) {
-      y[r0] = a0;
-      if (NDOT >= 1) acc[0] += w[r0] * a0;
-      if (NDOT >= 2) acc[1] += a0 * a0;
-    }
-    if (r1 < row1) {
-      y[r1] = a1;
-      if (NDOT >= 1) acc[0] += w[r1] * a1;
-      if (NDOT >= 2) acc[1] += a1 * a1;
-    }
-  }
-  if constexpr (NDOT > 0)
-    reduce_finalize<NDOT>(acc, partial, ticket, sc, fl, stage, fused, pd, epoch, 0, rg.blk0, rg.nblk_total, rg.finalize);
-}
-
 // ---- CG vector kernels -----------------------------------------------------------------------
 // r = b - q ; z = minv r ; p = z ; sums (r.z, r.r, b.b)
 __global__ void __launch_bounds__(VEC_BLOCK) k_cg_init(const double *__restrict__ b, const double *__restrict__ q,
@@ -1120,33 +914,17 @@ static Comm comm_of(apdx_plan *pl) {
   return c;
 }
 
-static int spmv_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
-}
-// A/B switch: APDX_SPMV_TMA=1 streams the stored values with bulk async copies (k_spmv_sell_tma)
-static bool spmv_use_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("APDX_SPMV_TMA");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
 // persistent SpMV grid: the blocks that are resident at once (the kernels are compiled for 2 blocks of 256 threads per
 // SM; APDX_SPMV_BPS overrides the blocks per SM for measurements)
 static unsigned spmv_grid(int64_t n_slices) {
   static int resident = 0;
   if (!resident) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char *e = getenv("APDX_SPMV_BPS");
     const int bps = e && atoi(e) > 0 ? atoi(e) : 2;
-    resident = spmv_sms() * bps;
+    resident = sms * bps;
   }
   const int64_t nb = (n_slices + VEC_BLOCK / 32 - 1) / (VEC_BLOCK / 32);
   return (unsigned)(nb < resident ? (nb > 0 ? nb : 1) : resident);
@@ -1174,20 +952,8 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
       (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch, rg
 #define APDX_SPMV_NF(NFV)                                                                                              \
   do {                                                                                                                 \
-    if (spmv_use_tma() && part == 0) {                                                                                 \
-      constexpr int smem = TMA_WARPS * TMA_STAGES * TMA_CH * 512;                                                      \
-      static bool attr_set = false;                                                                                    \
-      if (!attr_set) {                                                                                                 \
-        APDX_CUDA(cudaFuncSetAttribute(k_spmv_sell_tma<NDOT, NFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        attr_set = true;                                                                                               \
-      }                                                                                                                \
-      const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>(spmv_sms(), (S.n_slices + TMA_WARPS - 1) / TMA_WARPS)); \
-      k_spmv_sell_tma<NDOT, NFV><<<g, TMA_WARPS * 32, smem, pl->stream>>>(APDX_SPMV_ARGS);                             \
-    } else if (S.sym && S.n_mirrored > 0) {                                                                            \
-      k_spmv_sell<NDOT, NFV, true><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                                \
-    } else {                                                                                                           \
-      k_spmv_sell<NDOT, NFV, false><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                               \
-    }                                                                                                                  \
+    if (S.sym && S.n_mirrored > 0) k_spmv_sell<NDOT, NFV, true><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);   \
+    else k_spmv_sell<NDOT, NFV, false><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                            \
   } while (0)
   if (S.nf == 1) APDX_SPMV_NF(1);
   else if (S.nf == 2) APDX_SPMV_NF(2);

@@ -46,7 +46,7 @@ def main(model, n, reps):
     ms = plan.time_spmv(reps)
     alg = nnz * 12 + n_free * 16 + (n_free + 1) * 4
     impl = plan.stats().get("sell_bytes", 0.0) + n_free * 16
-    print(json.dumps({"sell_sym": os.environ.get("APDX_SELL_SYM", "default"), "tma": os.environ.get("APDX_SPMV_TMA", "default"), "sell": plan.sell_info(), "model": model, "n": n, "n_free": n_free,
+    print(json.dumps({"sell_sym": os.environ.get("APDX_SELL_SYM", "default"), "sell": plan.sell_info(), "model": model, "n": n, "n_free": n_free,
                       "nnz": nnz, "ms": ms, "algorithmic_gbs": alg / ms * 1e-6, "implementation_gbs": impl / ms * 1e-6,
                       "y_sha1": hashlib.sha1(yh.tobytes()).hexdigest()[:16], "y_sum": float(yh.sum())}))
 
