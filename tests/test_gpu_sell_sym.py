@@ -91,3 +91,48 @@ def test_krylov_solution_same_with_mirrored_storage(method):
         plan.destroy()
     assert abs(iters[0] - iters[1]) <= 2
     assert np.linalg.norm(sols[0] - sols[1]) < 1e-8 * np.linalg.norm(sols[1])
+
+
+def _permute_nodes(p, perm):
+    """Renumber the nodes of a problem dict: new id of old node i is perm[i]."""
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    q = dict(p)
+    q["coords"] = p["coords"][inv]
+    q["mask"] = p["mask"][inv]
+    q["values"] = p["values"][inv]
+    q["sets"] = [dict(st, conn=perm[st["conn"]]) for st in p["sets"]]
+    return q
+
+
+@pytest.mark.parametrize("fraction", [0.03, 1.0])
+def test_mirrored_storage_on_irregular_numbering(fraction):
+    """Node numbers partly (3 %) or fully shuffled: slices fall back to explicit columns, lower columns whose partner rows
+    live in such slices must stay stored, and the product must still match SciPy."""
+    from autopdex_b200 import backend
+    p = problems.poisson_hex(12, distort=0.1)
+    n_nodes = p["coords"].shape[0]
+    rng = np.random.default_rng(17)
+    perm = np.arange(n_nodes)
+    pick = rng.choice(n_nodes, size=max(2, int(fraction * n_nodes)), replace=False)
+    perm[pick] = perm[rng.permutation(pick)]
+    q = _permute_nodes(p, perm)
+    plan_s, dofs = _plan(q, True)
+    plan_f, _ = _plan(q, False)
+    info_s, info_f = plan_s.sell_info(), plan_f.sell_info()
+    assert info_s["stored_values"] + info_s["mirrored_entries"] == info_f["stored_values"]
+    if fraction < 0.5:
+        assert 0 < info_s["mirrored_entries"] < 0.5 * info_f["stored_values"]
+    n = q["mask"].size
+    free = ~q["mask"].ravel()
+    _, data = oasm.assemble(q["sets"], q["coords"], dofs, {})
+    rows, cols = oasm.coo_indices(q["sets"])
+    red = oasm.scipy_assembling(data, rows, cols, n, free)
+    x = rng.standard_normal(plan_s.n_free)
+    xd = backend.DeviceArray.from_host(x)
+    for plan in (plan_s, plan_f):
+        yd = backend.DeviceArray(plan.n_free)
+        plan.spmv(xd, yd)
+        ref = red @ x
+        assert np.abs(yd.download() - ref).max() < 1e-12 * np.abs(ref).max()
+        plan.destroy()
