@@ -49,6 +49,49 @@ def pin_if_repeated(arr):
             _SEEN.clear()
 
 
+# ---- recycled, page-locked host blocks for large results ------------------------------------------------
+# A device->host copy into a fresh np.empty pays the page faults of the new pages and a staged pageable copy
+# (~10 GB/s); into a block that was page-locked once it is one DMA transfer.  Results are handed out as NumPy arrays
+# over such a block; the block goes back to the pool only when the LAST array referring to it is gone: every view
+# NumPy derives from the result has the small _Lease object as its .base, and the lease's finalizer recycles the block.
+_POOL = {}
+_POOL_MAX_BLOCKS = 4
+
+
+class _Lease:
+    def __init__(self, mem, n, dtype):
+        self._mem = mem
+        self.__array_interface__ = {"data": (mem.ctypes.data, False), "shape": (n,), "typestr": np.dtype(dtype).str,
+                                    "version": 3}
+
+
+def _recycle(nbytes, mem):
+    blocks = _POOL.setdefault(nbytes, [])
+    if len(blocks) < _POOL_MAX_BLOCKS:
+        blocks.append(mem)
+    else:
+        _unpin(mem.ctypes.data)
+
+
+def host_result(n, dtype=np.float64):
+    """An uninitialised host array of n items for a device->host copy (page-locked and recycled when large)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(n) * dtype.itemsize
+    if nbytes < _PIN_MIN_BYTES:
+        return np.empty(n, dtype=dtype)
+    blocks = _POOL.get(nbytes)
+    if blocks:
+        mem = blocks.pop()
+    else:
+        mem = np.empty(nbytes, dtype=np.uint8)
+        ptr = mem.ctypes.data
+        if ptr % dtype.itemsize == 0 and _lib.load().apdx_host_register(C.c_void_p(ptr), nbytes) == 0:
+            _PINNED[ptr] = True
+    lease = _Lease(mem, int(n), dtype)
+    weakref.finalize(lease, _recycle, nbytes, mem)
+    return np.asarray(lease)
+
+
 class DeviceArray:
     """A caller-owned FP64 (or raw byte) buffer in HBM."""
 
@@ -74,7 +117,7 @@ class DeviceArray:
 
     def download(self, out=None):
         if out is None:
-            out = np.empty(self.n, dtype=self.dtype)
+            out = host_result(self.n, self.dtype)
         _lib.check(_lib.load().apdx_memcpy_d2h(out.ctypes.data_as(C.c_void_p), self.ptr, self.n * self.dtype.itemsize))
         return out
 

@@ -185,3 +185,24 @@ def test_utility_and_slab_partition():
         assert (p["rank_lo"] == -1) == (r == 0) and (p["rank_hi"] == -1) == (r == world - 1)
     assert owned[0][0] == 0 and owned[-1][1] == (m + 1) ** 3
     assert all(owned[i][1] == owned[i + 1][0] for i in range(world - 1))
+
+
+def test_host_result_blocks_are_recycled_only_after_the_last_view_died():
+    """backend.host_result: large device->host results land in recycled (page-locked on a GPU box) blocks; a block must
+    not be reused while any array derived from the result is alive."""
+    import gc
+    from autopdex_b200 import backend
+    n = 1 << 18
+    a = backend.host_result(n)
+    a[:] = 3.0
+    ptr = a.ctypes.data
+    view = a.reshape(-1, 1)[5:9]
+    del a
+    gc.collect()
+    b = backend.host_result(n)
+    assert b.ctypes.data != ptr and np.all(view == 3.0)
+    del view
+    gc.collect()
+    c = backend.host_result(n)
+    assert c.ctypes.data == ptr
+    assert backend.host_result(16).base is None      # small results are plain arrays
