@@ -105,16 +105,16 @@ def _permute_nodes(p, perm):
     return q
 
 
-@pytest.mark.parametrize("fraction", [0.03, 1.0])
+@pytest.mark.parametrize("fraction", [0.002, 1.0])
 def test_mirrored_storage_on_irregular_numbering(fraction):
-    """Node numbers partly (3 %) or fully shuffled: slices fall back to explicit columns, lower columns whose partner rows
+    """Node numbers of a few nodes (0.2 %) or of all nodes shuffled: slices fall back to explicit columns, lower columns whose partner rows
     live in such slices must stay stored, and the product must still match SciPy."""
     from autopdex_b200 import backend
-    p = problems.poisson_hex(12, distort=0.1)
+    p = problems.poisson_hex(14, distort=0.1)
     n_nodes = p["coords"].shape[0]
     rng = np.random.default_rng(17)
     perm = np.arange(n_nodes)
-    pick = rng.choice(n_nodes, size=max(2, int(fraction * n_nodes)), replace=False)
+    pick = rng.choice(n_nodes, size=max(6, int(fraction * n_nodes)), replace=False)
     perm[pick] = perm[rng.permutation(pick)]
     q = _permute_nodes(p, perm)
     plan_s, dofs = _plan(q, True)
