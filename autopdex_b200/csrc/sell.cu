@@ -1,15 +1,17 @@
 // Sliced-ELL storage of the reduced system for the Krylov solve, built once per plan on device.
 //
-// Slices of 64 consecutive rows (one warp, two rows per lane -> 128-bit value loads).  Inside a
-// slice the entries are stored column-major, so every warp load is one contiguous 512-byte run.
+// Slices of 64 rows (one warp of the SpMV; lane owns local rows lane and lane + 32).  Inside a slice the
+// entries are stored column-major, so a column is one contiguous 512-byte run (two 256-byte warp loads).
 // Column indices are compressed per slice: if the union of (col - row) over the slice's rows is
 // small ("offset mode"), the slice stores that list of offsets ONCE (W ints instead of 64*W) and
 // entry j of every row means column row + off[j]; rows that do not have an offset hold an explicit
 // zero.  Finite-element matrices on structured or well-ordered meshes are almost entirely in
 // offset mode, which cuts the per-nonzero traffic from 12 to ~8 bytes and makes the x gathers
 // coalesced.  Slices with irregular columns fall back to explicit int32 columns ("explicit mode").
-// The reference has no device SpMV at all; this is the storage behind the
-// `north_star`'s "sliced-ELL ... with 128-bit loads and warp-shuffle row reductions".
+// Offset-mode slices store only the columns with offset >= 0 (symmetric tangents, see below).
+// The reference has no device SpMV at all; this is the storage behind the `north_star`'s
+// sliced-ELL SpMV (its "128-bit loads" were measured against contiguous 8-byte-per-lane loads in session 2: the
+// interleaved row ownership they need doubles the L1 tag traffic of the x gathers).
 #include <cub/cub.cuh>
 #include <stdlib.h>
 
@@ -101,8 +103,8 @@ __global__ void __launch_bounds__(256) k_sell_mode(const int32_t *__restrict__ r
 // One warp per slice.  PASS 0: count (stored width W, mirrored columns M, columns with offset >= 0, sizes).
 // PASS 1: fill offsets / explicit columns / sources / diagonal / the offsets of the mirror table.
 // Slices interleave the nf dofs of a node: slice s = b*nf + c holds the 64 rows row0 + b*64*nf + c + nf*k,
-// k = 0..63 (lane handles k = 2*lane and 2*lane + 1, stored side by side as one double2 so that the x gathers
-// and y stores of a warp are contiguous), i.e. rows of ONE field component -- for vector problems the offsets col - row
+// k = 0..63 (in THIS build kernel lane handles k = 2*lane and 2*lane + 1; the value array is indexed [column][k], so the
+// SpMV is free to own rows (lane, lane + 32)), i.e. rows of ONE field component -- for vector problems the offsets col - row
 // of such rows coincide (3 dn + (c' - c)), which keeps elasticity matrices in offset mode.  nf = 1 gives
 // 64 consecutive rows.  A row's CSR columns ascend, hence so do its offsets: the union over the slice is
 // produced by repeated warp-wide min extraction.
