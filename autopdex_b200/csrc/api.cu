@@ -178,6 +178,7 @@ static int linear_step_internal(apdx_plan *pl, const apdx_krylov_opts *opts, con
   APDX_CUDA(cudaEventRecord(pl->ev[0], s));
   APDX_CHECK(assemble_internal(pl, dofs_d, 4, pl->residual.p));
   k_rhs_reduced<<<g1(pl->n_free), 256, 0, s>>>(pl->residual.p, pl->free_list.p, pl->n_free, pl->rhs_red.p, pl->x_red.p);
+  pl->x0_is_zero = true;
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaEventRecord(pl->ev[1], s));
   int32_t it = 0;
@@ -602,6 +603,7 @@ int apdx_krylov(apdx_plan *pl, const apdx_krylov_opts *opts, const double *rhs_d
   APDX_REQUIRE(pl && opts && rhs_d && x_d, APDX_ERR_INVALID, "NULL argument");
   cudaStream_t s = pl->stream;
   APDX_CHECK(krylov_alloc(pl));
+  pl->x0_is_zero = false;   // x_d is the caller's initial guess
   APDX_CUDA(cudaEventRecord(pl->ev[1], s));
   APDX_CHECK(krylov_solve(pl, opts, rhs_d, x_d, iters, relres));
   APDX_CUDA(cudaEventRecord(pl->ev[2], s));
@@ -643,6 +645,7 @@ int apdx_tangent_solve(apdx_plan *pl, const apdx_krylov_opts *opts, const double
   if (dofs_d) APDX_CHECK(assemble_internal(pl, dofs_d, 4, pl->residual.p));
   APDX_REQUIRE(pl->have_sell_values, APDX_ERR_STATE, "no assembled tangent: pass dofs_d or run a Newton step first");
   k_rhs_gather<<<g1(pl->n_free), 256, 0, s>>>(rhs_d, pl->free_list.p, pl->n_free, pl->rhs_red.p, pl->x_red.p);
+  pl->x0_is_zero = true;
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaEventRecord(pl->ev[1], s));
   int32_t it = 0;

@@ -226,6 +226,7 @@ struct apdx_plan {
   apdx::P2P p2p;
   apdx::KrylovGraph kgraph[2];   // [0] CG, [1] BiCGSTAB
   bool have_sell_values = false, have_red_values = false;
+  bool x0_is_zero = false;                 // the caller of krylov_solve has just zeroed the whole initial guess
   double *pinned = nullptr;                // small pinned host staging
   apdx::Stats stats;
 

@@ -1089,9 +1089,15 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
   // APDX_COMM: cg2 = single-reduction CG; p2p / fused = CUDA-IPC peer stores instead of NCCL
   const bool cg2 = !bi && c.multi && !c.p2p && cm && strcmp(cm, "cg2") == 0;
 
-  // q = A x0 (x is the caller's buffer: its ghost entries travel with NCCL)
-  if (c.multi) APDX_CHECK(comm_halo_exchange(pl, x, s));
-  APDX_CHECK(launch_spmv<0>(pl, x, bi ? k.t.p : k.q.p, nullptr, 0, 0));
+  // q = A x0 (x is the caller's buffer: its ghost entries travel with NCCL).  The Newton paths start from x0 = 0
+  // (k_rhs_reduced / k_rhs_gather zero it, ghosts included) and say so: q = 0 without a product.
+  if (pl->x0_is_zero) {
+    APDX_CUDA(cudaMemsetAsync(bi ? k.t.p : k.q.p, 0, (size_t)pl->n_free * sizeof(double), s));
+    pl->x0_is_zero = false;
+  } else {
+    if (c.multi) APDX_CHECK(comm_halo_exchange(pl, x, s));
+    APDX_CHECK(launch_spmv<0>(pl, x, bi ? k.t.p : k.q.p, nullptr, 0, 0));
+  }
   if (cg2) {
     k_cg2_init<<<VEC_GRID, VEC_BLOCK, 0, s>>>(rhs, k.q.p, k.minv.p, k.r.p, k.z.p, k.p.p, k.s.p, i0, i1, k.partial.p,
                                               k.ticket.p, k.scal.p, k.flags.p);
