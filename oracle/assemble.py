@@ -15,7 +15,7 @@ from . import elements
 def global_dofs(conn, nf):
     """(n_rows, nen*nf) global dof ids, node-major / component-minor (assembler.py:130-131)."""
     conn = np.asarray(conn, dtype=np.int64)
-    return (conn[:, :, None] * nf + np.arange(nf)).reshape(conn.shape[0], -1)
+    return (conn[:, :, None] * nf + np.arange(nf)).reshape(conn.shape[0], conn.shape[1] * nf)   # also for 0 elements
 
 
 def coo_indices(sets):
