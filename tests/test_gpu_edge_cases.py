@@ -63,3 +63,49 @@ def test_zero_right_hand_side_converges_immediately():
     _, (steps, _, _) = osolve.damped_newton(prob, np.zeros(p["mask"].shape))
     assert it == steps
     plan.destroy()
+
+
+def _pcg_iterates(A, b, minv, k):
+    """k iterations of Jacobi-preconditioned CG from x0 = 0 (jax.scipy.sparse.linalg.cg's recurrence, solver.py:1093-1126)."""
+    x = np.zeros_like(b)
+    r = b.copy()
+    z = minv * r
+    p = z.copy()
+    rz = r @ z
+    for _ in range(k):
+        q = A @ p
+        alpha = rz / (p @ q)
+        x += alpha * p
+        r -= alpha * q
+        z = minv * r
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x
+
+
+@pytest.mark.parametrize("k", [1, 5, 31, 32, 33, 70])
+def test_cg_stopped_by_maxiter_returns_the_kth_iterate(k):
+    """The x-update of an iteration is applied by the kernel that follows the convergence test (k_cg_p); a solve that is
+    cut off by maxiter -- inside a replayed 32-iteration chunk or exactly at its end -- must still return iterate k."""
+    from autopdex_b200 import backend
+    from oracle import assemble as oasm
+    from tests import gpu_util
+    p = problems.poisson_hex(9, distort=0.15)
+    plan = gpu_util.make_plan(p)
+    n = p["mask"].size
+    free = ~p["mask"].ravel()
+    dofs = np.random.default_rng(4).uniform(-1, 1, p["mask"].shape)
+    d, r = backend.DeviceArray.from_host(dofs.ravel()), backend.DeviceArray(n)
+    plan.assemble(d, True, r)
+    _, data = oasm.assemble(p["sets"], p["coords"], dofs, {})
+    rows, cols = oasm.coo_indices(p["sets"])
+    A = oasm.scipy_assembling(data, rows, cols, n, free)
+    b = np.random.default_rng(8).standard_normal(plan.n_free)
+    bd, xd = backend.DeviceArray.from_host(b), backend.DeviceArray(plan.n_free)
+    xd.zero()
+    it, _ = plan.krylov(backend.KrylovOptions("cg", rtol=1e-30, maxiter=k), bd, xd)
+    assert it == k
+    ref = _pcg_iterates(A, b, 1.0 / A.diagonal(), k)
+    assert np.linalg.norm(xd.download() - ref) < 1e-9 * np.linalg.norm(ref)
+    plan.destroy()
