@@ -136,3 +136,54 @@ def test_mirrored_storage_on_irregular_numbering(fraction):
         ref = red @ x
         assert np.abs(yd.download() - ref).max() < 1e-12 * np.abs(ref).max()
         plan.destroy()
+
+
+@pytest.mark.parametrize("nf_case", ["poisson", "neo_hooke"])
+def test_mirrored_storage_on_an_owned_row_range(nf_case):
+    """A partitioned plan multiplies only its owned rows [f0, f1) and reads ghost columns on both sides.
+    Lower columns whose partner row is not owned must stay stored; checked here on ONE GPU by restricting a plan to a
+    slab of its rows (no communicator: the caller's x already holds the ghost entries)."""
+    from autopdex_b200 import backend
+    m = 10
+    p = problems.poisson_hex(m, distort=0.1) if nf_case == "poisson" else problems.neo_hooke_brick(6)
+    nf = p["nf"]
+    n_side = (m if nf_case == "poisson" else 6) + 1
+    plane = n_side * n_side * nf                       # dofs per node plane (i slowest, mesher.py:160)
+    lo, hi = 3 * plane, (n_side - 2) * plane
+    results = {}
+    for sym in (True, False):
+        from tests import gpu_util
+        old = os.environ.get("APDX_SELL_SYM")
+        os.environ["APDX_SELL_SYM"] = "1" if sym else "0"
+        try:
+            plan = gpu_util.make_plan(p)
+            plan.set_partition(lo, hi, 0, 1)            # neighbour ranks are only labels without a communicator
+            n = p["mask"].size
+            dofs = np.random.default_rng(3).uniform(-1e-2, 1e-2, p["mask"].shape)
+            d, r = backend.DeviceArray.from_host(dofs.ravel()), backend.DeviceArray(n)
+            plan.assemble(d, True, r)
+        finally:
+            if old is None:
+                os.environ.pop("APDX_SELL_SYM")
+            else:
+                os.environ["APDX_SELL_SYM"] = old
+        f0, f1 = plan.f0, plan.f1
+        assert 0 < f0 < f1 < plan.n_free
+        x = np.random.default_rng(6).standard_normal(plan.n_free)
+        xd, yd = backend.DeviceArray.from_host(x), backend.DeviceArray(plan.n_free)
+        yd.zero()
+        plan.spmv(xd, yd)
+        results[sym] = (yd.download()[f0:f1], plan.sell_info(), (f0, f1), dofs)
+        plan.destroy()
+    (ys, info_s, rng_s, dofs), (yf, info_f, rng_f, _) = results[True], results[False]
+    assert rng_s == rng_f and info_s["mirrored_entries"] > 0
+    assert info_s["stored_values"] + info_s["mirrored_entries"] == info_f["stored_values"]
+    n = p["mask"].size
+    free = ~p["mask"].ravel()
+    _, data = oasm.assemble(p["sets"], p["coords"], dofs, {})
+    rows, cols = oasm.coo_indices(p["sets"])
+    red = oasm.scipy_assembling(data, rows, cols, n, free)
+    x = np.random.default_rng(6).standard_normal(red.shape[0])
+    ref = (red @ x)[rng_s[0]:rng_s[1]]
+    assert np.abs(ys - ref).max() < 1e-12 * np.abs(ref).max()
+    assert np.abs(yf - ref).max() < 1e-12 * np.abs(ref).max()
