@@ -59,3 +59,54 @@ def dof_select(dirichlet_nodes, selected_fields):
     if isinstance(selected_fields, bool):
         return dirichlet_nodes * selected_fields
     return np.outer(dirichlet_nodes, np.asarray(selected_fields))
+
+
+# ---- result export -------------------------------------------------------------------------------
+# The reference recommends meshio for VTK files (autopdex/plotter.py:16); meshio is not a dependency here, so the
+# solutions that come back from the device are written by this small legacy-VTK writer.  The reference's node
+# orders (spaces.py:1913-1949, mesher.py:332-360) are VTK's for every element below.
+_VTK_CELL = {(1, 2): 3, (1, 3): 21, (2, 3): 5, (2, 6): 22, (2, 4): 9, (2, 9): 28, (3, 4): 10, (3, 10): 24, (3, 8): 12,
+             (3, 27): 29}
+
+
+def write_vtk(path, node_coordinates, connectivity, point_data=None, cell_dim=None):
+    """Write an unstructured grid with nodal fields as a binary legacy VTK file.
+
+    node_coordinates (n_nodes, dim); connectivity (n_elem, nen) of ONE element type; point_data
+    {name: (n_nodes,) or (n_nodes, k)} with k <= 3 written as a vector, otherwise as k scalars name_0 ...;
+    cell_dim: topological dimension of the elements (default: the space dimension; pass dim - 1 for the
+    surface sets of a 'user element' problem)."""
+    x = np.asarray(node_coordinates, dtype=np.float64)
+    conn = np.asarray(connectivity)
+    if x.ndim != 2 or conn.ndim != 2:
+        raise ValueError("write_vtk: node_coordinates (n_nodes, dim) and connectivity (n_elem, nen) expected")
+    n, dim = x.shape
+    ne, nen = conn.shape
+    key = (dim if cell_dim is None else cell_dim, nen)
+    if key not in _VTK_CELL:
+        raise ValueError("write_vtk: no VTK cell for a %d-dimensional element with %d nodes" % key)
+    if ne and (conn.min() < 0 or conn.max() >= n):
+        raise ValueError("write_vtk: connectivity refers to nodes outside node_coordinates")
+    pts = np.zeros((n, 3), dtype=">f8")
+    pts[:, :dim] = x
+    cells = np.empty((ne, nen + 1), dtype=">i4")
+    cells[:, 0] = nen
+    cells[:, 1:] = conn
+    with open(path, "wb") as f:
+        f.write(b"# vtk DataFile Version 3.0\nautopdex_b200 result\nBINARY\nDATASET UNSTRUCTURED_GRID\n")
+        f.write(b"POINTS %d double\n" % n + pts.tobytes() + b"\n")
+        f.write(b"CELLS %d %d\n" % (ne, ne * (nen + 1)) + cells.tobytes() + b"\n")
+        f.write(b"CELL_TYPES %d\n" % ne + np.full(ne, _VTK_CELL[key], dtype=">i4").tobytes() + b"\n")
+        if point_data:
+            f.write(b"POINT_DATA %d\n" % n)
+            for name, v in point_data.items():
+                v = np.asarray(v, dtype=np.float64).reshape(n, -1)
+                tag = str(name).replace(" ", "_").encode()
+                if 1 < v.shape[1] <= 3:
+                    vec = np.zeros((n, 3), dtype=">f8")
+                    vec[:, :v.shape[1]] = v
+                    f.write(b"VECTORS " + tag + b" double\n" + vec.tobytes() + b"\n")
+                else:
+                    for k in range(v.shape[1]):
+                        t = tag if v.shape[1] == 1 else tag + b"_%d" % k
+                        f.write(b"SCALARS " + t + b" double 1\nLOOKUP_TABLE default\n" + v[:, k].astype(">f8").tobytes() + b"\n")

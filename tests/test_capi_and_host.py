@@ -206,3 +206,64 @@ def test_host_result_blocks_are_recycled_only_after_the_last_view_died():
     c = backend.host_result(n)
     assert c.ctypes.data == ptr
     assert backend.host_result(16).base is None      # small results are plain arrays
+
+
+def _read_legacy_vtk(path):
+    """Minimal reader of the binary legacy files utility.write_vtk produces (test helper)."""
+    raw = open(path, "rb").read()
+    out, pos = {}, 0
+
+    def line():
+        nonlocal pos
+        end = raw.index(b"\n", pos)
+        s = raw[pos:end].decode()
+        pos = end + 1
+        return s
+
+    def block(dtype, count):
+        nonlocal pos
+        a = np.frombuffer(raw, dtype=dtype, count=count, offset=pos)
+        pos += a.nbytes + 1
+        return a
+    assert line().startswith("# vtk DataFile") and line() and line() == "BINARY" and line() == "DATASET UNSTRUCTURED_GRID"
+    n = int(line().split()[1])
+    out["points"] = block(">f8", 3 * n).reshape(n, 3)
+    ne, tot = map(int, line().split()[1:])
+    out["cells"] = block(">i4", tot).reshape(ne, -1)
+    assert int(line().split()[1]) == ne
+    out["types"] = block(">i4", ne)
+    while pos < len(raw):
+        w = line().split()
+        if w[0] == "POINT_DATA":
+            continue
+        if w[0] == "VECTORS":
+            out[w[1]] = block(">f8", 3 * n).reshape(n, 3)
+        elif w[0] == "SCALARS":
+            assert line() == "LOOKUP_TABLE default"
+            out[w[1]] = block(">f8", n)
+    return out
+
+
+def test_write_vtk_round_trip(tmp_path):
+    from autopdex_b200 import mesher, utility
+    coords, elems = mesher.structured_mesh((2, 3, 2), [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.],
+                                                       [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]], "brick")
+    rng = np.random.default_rng(0)
+    u, theta, s6 = rng.normal(size=(coords.shape[0], 3)), rng.normal(size=coords.shape[0]), rng.normal(size=(coords.shape[0], 6))
+    utility.write_vtk(tmp_path / "brick.vtk", coords, elems, {"u": u, "theta": theta, "stress": s6})
+    got = _read_legacy_vtk(tmp_path / "brick.vtk")
+    assert np.array_equal(got["points"], coords) and np.array_equal(got["cells"][:, 1:], elems)
+    assert (got["cells"][:, 0] == 8).all() and (got["types"] == 12).all()
+    assert np.array_equal(got["u"], u) and np.array_equal(got["theta"], theta) and np.array_equal(got["stress_4"], s6[:, 4])
+    # 2-D mesh, quad9 after elevation; surface set of a 3-D problem; rejections
+    c2, e2 = mesher.structured_mesh((2, 2), [[0., 0.], [1., 0.], [1., 1.], [0., 1.]], "quad")
+    c9, e9 = mesher.elevate_quads(c2, e2)
+    utility.write_vtk(tmp_path / "q9.vtk", c9, e9, {"u": np.zeros((c9.shape[0], 2))})
+    got = _read_legacy_vtk(tmp_path / "q9.vtk")
+    assert (got["types"] == 28).all() and got["points"][:, 2].max() == 0.0 and got["u"].shape == (c9.shape[0], 3)
+    utility.write_vtk(tmp_path / "face.vtk", coords, mesher.boundary_faces((2, 3, 2), 0, 1), cell_dim=2)
+    assert (_read_legacy_vtk(tmp_path / "face.vtk")["types"] == 9).all()
+    with pytest.raises(ValueError):
+        utility.write_vtk(tmp_path / "bad.vtk", coords, elems[:, :5])
+    with pytest.raises(ValueError):
+        utility.write_vtk(tmp_path / "bad.vtk", coords, elems + coords.shape[0])
