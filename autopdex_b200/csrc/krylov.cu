@@ -382,8 +382,57 @@ __device__ __forceinline__ void spmv_mirrored(const int4 *__restrict__ tab, int3
   }
 }
 
-template <int NDOT, int NF, bool SYM>
-__global__ void __launch_bounds__(VEC_BLOCK, 2)
+// Occupancy variants (OCC = blocks of 256 threads per SM the kernel is compiled for: 2 -> 128 registers, 3 -> 80,
+// 4 -> 64; APDX_SPMV_BPS selects one).  The r01f capture shows 4 warps per scheduler that sit in long-scoreboard
+// stalls (issue slots 34 % used): OCC 3 / 4 trade the depth of a warp's load batch for more warps.  The mirrored
+// batches are then taken in sub-batches of SUB table entries, the generic paths in batches of fewer columns; the
+// order of the FMAs into a0 / a1 is the same in every variant, so the results are bit-identical.
+template <int N, bool CLAMP>
+__device__ __forceinline__ void spmv_mirrored_chunk(const int4 *__restrict__ tab, const double *__restrict__ val,
+                                                    const double *__restrict__ x, const double *__restrict__ xr0,
+                                                    const double *__restrict__ xr1, int k0, int k1, int32_t rr0,
+                                                    int32_t rr1, int32_t n_cols, double &a0, double &a1) {
+  int4 t[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) t[u] = __ldg(tab + u);
+  double m0[N], m1[N], xa[N], xb[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    m0[u] = __ldg(val + ((k0 < t[u].w ? t[u].y : t[u].z) + k0));
+    m1[u] = __ldg(val + ((k1 < t[u].w ? t[u].y : t[u].z) + k1));
+    if (CLAMP) {
+      xa[u] = __ldg(x + min(max(rr0 + t[u].x, 0), n_cols - 1));
+      xb[u] = __ldg(x + min(max(rr1 + t[u].x, 0), n_cols - 1));
+    } else {
+      xa[u] = __ldg(xr0 + t[u].x);
+      xb[u] = __ldg(xr1 + t[u].x);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) { a0 += m0[u] * xa[u]; a1 += m1[u] * xb[u]; }
+}
+template <int MB, int SUB, int S0, bool CLAMP>
+__device__ __forceinline__ void spmv_mirrored_steps(const int4 *__restrict__ tab, const double *__restrict__ val,
+                                                    const double *__restrict__ x, const double *__restrict__ xr0,
+                                                    const double *__restrict__ xr1, int k0, int k1, int32_t rr0,
+                                                    int32_t rr1, int32_t n_cols, double &a0, double &a1) {
+  if constexpr (S0 < MB) {
+    constexpr int N = (MB - S0 < SUB) ? MB - S0 : SUB;
+    spmv_mirrored_chunk<N, CLAMP>(tab + S0, val, x, xr0, xr1, k0, k1, rr0, rr1, n_cols, a0, a1);
+    spmv_mirrored_steps<MB, SUB, S0 + N, CLAMP>(tab, val, x, xr0, xr1, k0, k1, rr0, rr1, n_cols, a0, a1);
+  }
+}
+template <int MB, int SUB, bool CLAMP>
+__device__ __forceinline__ void spmv_mirrored_sub(const int4 *__restrict__ tab, int32_t M, const double *__restrict__ val,
+                                                  const double *__restrict__ x, const double *__restrict__ xr0,
+                                                  const double *__restrict__ xr1, int lane, int32_t rr0, int32_t rr1,
+                                                  int32_t n_cols, double &a0, double &a1) {
+  for (int32_t jb = 0; jb < M; jb += MB)
+    spmv_mirrored_steps<MB, SUB, 0, CLAMP>(tab + jb, val, x, xr0, xr1, lane, lane + 32, rr0, rr1, n_cols, a0, a1);
+}
+
+template <int NDOT, int NF, bool SYM, int OCC>
+__global__ void __launch_bounds__(VEC_BLOCK, OCC)
     k_spmv_sell(const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_m, const int64_t *__restrict__ valptr,
                 const int64_t *__restrict__ idxptr, const double *__restrict__ val, const int32_t *__restrict__ idx,
                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, int64_t row0,
@@ -401,6 +450,10 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
   }
   const int lane = threadIdx.x & 31;
   constexpr int WPB = VEC_BLOCK / 32;
+  // batch sizes of the occupancy variants (OCC == 2: the measured default)
+  constexpr int U = OCC == 2 ? SPMV_U : (OCC == 3 ? 5 : 3);          // generic paths: columns per batch
+  constexpr int XG9 = OCC == 2 ? 9 : 3, XG8 = OCC == 2 ? 8 : 4, XG7 = OCC == 2 ? 7 : 1;
+  constexpr int MSUB = OCC == 2 ? 8 : (OCC == 3 ? 4 : 2);            // mirrored table entries per sub-batch
   double acc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
   for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
@@ -456,18 +509,25 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     double a0 = 0.0, a1 = 0.0;
     for (int32_t jc = 0; jc < W; jc += 32) {
       const int32_t nb = min(32, W - jc);
-      const int32_t nbt = (nb + SPMV_U - 1) / SPMV_U, bs = (nb + nbt - 1) / nbt;   // equal batches of <= SPMV_U columns
-      if (fast && (nb % 9 == 0 || nb % 8 == 0 || nb % 7 == 0)) {
+      const int32_t nbt = (nb + U - 1) / U, bs = (nb + nbt - 1) / nbt;   // equal batches of <= U columns
+      if (OCC == 4 && fast && (nb % 7 == 0 || nb % 4 == 0 || nb % 3 == 0 || nb % 5 == 0)) {
+        // 64 registers: value batches of at most 7 columns, the x operands of a 7-batch one column at a time
         const int32_t offl = jc == 0 ? offl0 : __ldg(ip + jc + min(lane, nb - 1));
-        if (nb % 9 == 0) spmv_stored_fast<9, 9, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
-        else if (nb % 8 == 0) spmv_stored_fast<8, 8, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
-        else spmv_stored_fast<7, 7, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+        if (nb % 7 == 0) spmv_stored_fast<7, 1, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+        else if (nb % 4 == 0) spmv_stored_fast<4, 4, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+        else if (nb % 3 == 0) spmv_stored_fast<3, 3, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+        else spmv_stored_fast<5, 5, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+      } else if (OCC != 4 && fast && (nb % 9 == 0 || nb % 8 == 0 || nb % 7 == 0)) {
+        const int32_t offl = jc == 0 ? offl0 : __ldg(ip + jc + min(lane, nb - 1));
+        if (nb % 9 == 0) spmv_stored_fast<9, XG9, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+        else if (nb % 8 == 0) spmv_stored_fast<8, XG8, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
+        else spmv_stored_fast<7, XG7, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
       } else if (wenc < 0) {
         const int32_t offl = jc == 0 ? offl0 : __ldg(ip + jc + min(lane, nb - 1));
         for (int32_t jb = 0; jb < nb; jb += bs) {
-          double va[SPMV_U], vb[SPMV_U], xa[SPMV_U], xb[SPMV_U];
+          double va[U], vb[U], xa[U], xb[U];
 #pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) {
+          for (int u = 0; u < U; ++u) {
             va[u] = vb[u] = 0.0;
             if (u < bs && jb + u < nb) {
               const double *q = vp + (size_t)(jc + jb + u) * 64;
@@ -476,7 +536,7 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
             }
           }
 #pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) {
+          for (int u = 0; u < U; ++u) {
             const int32_t off = __shfl_sync(0xffffffffu, offl, (jb + u) & 31);
             xa[u] = xb[u] = 0.0;
             if (u < bs && jb + u < nb) {
@@ -485,15 +545,15 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
             }
           }
 #pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) { a0 += va[u] * xa[u]; a1 += vb[u] * xb[u]; }
+          for (int u = 0; u < U; ++u) { a0 += va[u] * xa[u]; a1 += vb[u] * xb[u]; }
         }
       } else {
         const int32_t *cp = ip + lane;
         for (int32_t jb = 0; jb < nb; jb += bs) {
-          int32_t ca[SPMV_U], cb[SPMV_U];
-          double va[SPMV_U], vb[SPMV_U], xa[SPMV_U], xb[SPMV_U];
+          int32_t ca[U], cb[U];
+          double va[U], vb[U], xa[U], xb[U];
 #pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) {
+          for (int u = 0; u < U; ++u) {
             ca[u] = cb[u] = 0;
             va[u] = vb[u] = 0.0;
             if (u < bs && jb + u < nb) {
@@ -503,21 +563,31 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
             }
           }
 #pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) { xa[u] = __ldg(x + ca[u]); xb[u] = __ldg(x + cb[u]); }
+          for (int u = 0; u < U; ++u) { xa[u] = __ldg(x + ca[u]); xb[u] = __ldg(x + cb[u]); }
 #pragma unroll
-          for (int u = 0; u < SPMV_U; ++u) { a0 += va[u] * xa[u]; a1 += vb[u] * xb[u]; }
+          for (int u = 0; u < U; ++u) { a0 += va[u] * xa[u]; a1 += vb[u] * xb[u]; }
         }
       }
     }
     // the next slice's header has arrived by now: request its offsets
     const int32_t offl_n = load_offsets(nxt);
     if (SYM && M > 0) {
-      if (fast) {
-        if (cur.M & SELL_MB7) spmv_mirrored_fast<7>(tab, M, val, xr0, xr1, lane, a0, a1);
-        else spmv_mirrored_fast<8>(tab, M, val, xr0, xr1, lane, a0, a1);
+      if constexpr (OCC == 2) {
+        if (fast) {
+          if (cur.M & SELL_MB7) spmv_mirrored_fast<7>(tab, M, val, xr0, xr1, lane, a0, a1);
+          else spmv_mirrored_fast<8>(tab, M, val, xr0, xr1, lane, a0, a1);
+        } else {
+          if (cur.M & SELL_MB7) spmv_mirrored<7>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
+          else spmv_mirrored<8>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
+        }
       } else {
-        if (cur.M & SELL_MB7) spmv_mirrored<7>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
-        else spmv_mirrored<8>(tab, M, val, x, lane, rr0, rr1, n_cols, a0, a1);
+        if (fast) {
+          if (cur.M & SELL_MB7) spmv_mirrored_sub<7, MSUB, false>(tab, M, val, x, xr0, xr1, lane, rr0, rr1, n_cols, a0, a1);
+          else spmv_mirrored_sub<8, MSUB, false>(tab, M, val, x, xr0, xr1, lane, rr0, rr1, n_cols, a0, a1);
+        } else {
+          if (cur.M & SELL_MB7) spmv_mirrored_sub<7, MSUB, true>(tab, M, val, x, xr0, xr1, lane, rr0, rr1, n_cols, a0, a1);
+          else spmv_mirrored_sub<8, MSUB, true>(tab, M, val, x, xr0, xr1, lane, rr0, rr1, n_cols, a0, a1);
+        }
       }
     }
     cur = nxt;
@@ -916,15 +986,23 @@ static Comm comm_of(apdx_plan *pl) {
 
 // persistent SpMV grid: the blocks that are resident at once (the kernels are compiled for 2 blocks of 256 threads per
 // SM; APDX_SPMV_BPS overrides the blocks per SM for measurements)
+static int spmv_bps() {
+  static int bps = 0;
+  if (!bps) {
+    const char *e = getenv("APDX_SPMV_BPS");
+    bps = e && atoi(e) > 0 ? atoi(e) : 2;
+  }
+  return bps;
+}
+// kernel variant compiled for that many resident blocks per SM (2 = default; 3 and 4: fewer registers, more warps)
+static int spmv_occ() { const int b = spmv_bps(); return b <= 2 ? 2 : (b == 3 ? 3 : 4); }
 static unsigned spmv_grid(int64_t n_slices) {
   static int resident = 0;
   if (!resident) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char *e = getenv("APDX_SPMV_BPS");
-    const int bps = e && atoi(e) > 0 ? atoi(e) : 2;
-    resident = sms * bps;
+    resident = sms * spmv_bps();
   }
   const int64_t nb = (n_slices + VEC_BLOCK / 32 - 1) / (VEC_BLOCK / 32);
   return (unsigned)(nb < resident ? (nb > 0 ? nb : 1) : resident);
@@ -950,15 +1028,24 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
   S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices,                   \
       (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done,                   \
       (NDOT > 0 && stage >= 0) ? c.pd : (halo_epoch ? c.pd : nullptr), epoch, halo_epoch, rg
+#define APDX_SPMV_OCC(NFV, OCCV)                                                                                       \
+  do {                                                                                                                 \
+    if (S.sym && S.n_mirrored > 0)                                                                                     \
+      k_spmv_sell<NDOT, NFV, true, OCCV><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                          \
+    else k_spmv_sell<NDOT, NFV, false, OCCV><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                      \
+  } while (0)
 #define APDX_SPMV_NF(NFV)                                                                                              \
   do {                                                                                                                 \
-    if (S.sym && S.n_mirrored > 0) k_spmv_sell<NDOT, NFV, true><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);   \
-    else k_spmv_sell<NDOT, NFV, false><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);                            \
+    const int occ = spmv_occ();                                                                                        \
+    if (occ == 2) APDX_SPMV_OCC(NFV, 2);                                                                               \
+    else if (occ == 3) APDX_SPMV_OCC(NFV, 3);                                                                          \
+    else APDX_SPMV_OCC(NFV, 4);                                                                                        \
   } while (0)
   if (S.nf == 1) APDX_SPMV_NF(1);
   else if (S.nf == 2) APDX_SPMV_NF(2);
   else APDX_SPMV_NF(3);
 #undef APDX_SPMV_NF
+#undef APDX_SPMV_OCC
 #undef APDX_SPMV_ARGS
   pl->stats.spmv_launches += 1;
   pl->stats.kernel_launches += 1;
@@ -1174,8 +1261,8 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
   S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, k.p.p, k.q.p, k.p.p, pl->f0, pl->f1, S.n_slices,       \
       (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scratch.p, k.st_fl.p + par * F_COUNT, ST_CG_PQ, 0, 1, pd, e1, he, \
       SliceRange{0, S.n_slices, 0, 0, 0, -1, 1}
-          if (S.sym && S.n_mirrored > 0) k_spmv_sell<1, 1, true><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
-          else k_spmv_sell<1, 1, false><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
+          if (S.sym && S.n_mirrored > 0) k_spmv_sell<1, 1, true, 2><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
+          else k_spmv_sell<1, 1, false, 2><<<grid, VEC_BLOCK, 0, s>>>(APDX_PF_ARGS);
 #undef APDX_PF_ARGS
           TR(1);
           pl->stats.spmv_launches += 1;
