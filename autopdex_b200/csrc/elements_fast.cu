@@ -9,6 +9,8 @@
 // instruction of a warp writes 256 contiguous bytes.  Same closed forms as the generic kernel
 // (elements.cu), same reference citations: models.py:96-134 (poisson_weak), the README potential,
 // signed w*det J of models.py:1691-1694, 1257-1261.
+#include <cstdlib>
+
 #include "elements.cuh"
 
 namespace apdx {
@@ -136,9 +138,17 @@ static int launch_fast(apdx_plan *pl, SetData &st, const ElemArgs &a) {
   for (int i = 0; i < NGP * NEN; ++i) F.tab.N[i] = st.h_shape_n[i];
   for (int i = 0; i < NGP * NEN * DIM; ++i) F.tab.dN[i] = st.h_shape_dn[i];
   for (int i = 0; i < NGP; ++i) F.tab.w[i] = st.h_gp_w[i];
-  const unsigned grid = (unsigned)((a.n_rows + FAST_BLOCK - 1) / FAST_BLOCK);
-  if (a.want_tangent) k_elem_scalar_reg<DIM, NEN, NGP, true><<<grid, FAST_BLOCK, 0, pl->stream>>>(F);
-  else k_elem_scalar_reg<DIM, NEN, NGP, false><<<grid, FAST_BLOCK, 0, pl->stream>>>(F);
+  // APDX_ELEM_BLOCK=32|64 (measurement aid): smaller blocks at the same 8 warps per SM, so that the gather, FMA and
+  // store phases of the resident blocks are staggered instead of two blocks of four warps moving in step
+  static int block = 0;
+  if (!block) {
+    const char *e = getenv("APDX_ELEM_BLOCK");
+    const int b = e ? atoi(e) : 0;
+    block = (b == 32 || b == 64) ? b : FAST_BLOCK;
+  }
+  const unsigned grid = (unsigned)((a.n_rows + block - 1) / block);
+  if (a.want_tangent) k_elem_scalar_reg<DIM, NEN, NGP, true><<<grid, block, 0, pl->stream>>>(F);
+  else k_elem_scalar_reg<DIM, NEN, NGP, false><<<grid, block, 0, pl->stream>>>(F);
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaGetLastError());
   return APDX_OK;
