@@ -237,7 +237,9 @@ def run_b200(args):
     t_plan = time.perf_counter()
     sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)       # builds + caches the plan
     t_plan = time.perf_counter() - t_plan
-    for _ in range(max(args.warmup - 1, 0)):
+    # the settings buffers are page-locked in place the second time they are uploaded (backend.pin_if_repeated):
+    # at least two untimed calls after the plan-building one, whatever --warmup says, so that no timed call pays for it
+    for _ in range(max(args.warmup - 1, 2)):
         sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)
     sampler = ClockSampler(local_rank)
     sampler.start()
