@@ -351,6 +351,26 @@ class Plan:
         _lib.check(_lib.load().apdx_plan_query(self.h, q))
         self.f0, self.f1 = q[5], q[6]
 
+    def set_partition_lists(self, owned_dof_end, neighbour_ranks, send_dofs, recv_dof_ranges):
+        """General partition (mesher.rcb_partition): local dofs are [owned | ghosts grouped by owner]; send_dofs[i] are
+        the local dof ids neighbour i ghosts (in its ghost order), recv_dof_ranges[i] = (begin, end) of its block here."""
+        nn = len(neighbour_ranks)
+        if len(send_dofs) != nn or len(recv_dof_ranges) != nn:
+            raise ValueError("one send list and one ghost range per neighbour expected")
+        ranks = np.ascontiguousarray(neighbour_ranks, dtype=np.int32)
+        lists = [np.ascontiguousarray(v, dtype=np.int64).ravel() for v in send_dofs]
+        ptr = np.zeros(nn + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum([v.size for v in lists])
+        flat = np.concatenate(lists) if nn and ptr[-1] else np.zeros(1, dtype=np.int64)
+        rb = np.ascontiguousarray([r[0] for r in recv_dof_ranges], dtype=np.int64)
+        re = np.ascontiguousarray([r[1] for r in recv_dof_ranges], dtype=np.int64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a.size else None
+        _lib.check(_lib.load().apdx_plan_set_partition_lists(self.h, int(owned_dof_end), nn, vp(ranks), vp(ptr), vp(flat),
+                                                             vp(rb), vp(re)))
+        q = (C.c_int64 * 8)()
+        _lib.check(_lib.load().apdx_plan_query(self.h, q))
+        self.f0, self.f1 = q[5], q[6]
+
 
 # ---- multi-GPU plumbing (one process per GPU) ---------------------------------------------------------
 def comm_unique_id():

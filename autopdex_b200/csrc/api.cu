@@ -415,6 +415,7 @@ int apdx_plan_destroy(apdx_plan *pl) {
   pl->red2full.release(); pl->red_diag.release(); pl->ke.release(); pl->re.release(); pl->vals.release();
   for (auto &g : pl->kgraph) if (g.exec) cudaGraphExecDestroy(g.exec);
   p2p_teardown(pl);
+  pl->hl.send_idx.release(); pl->hl.sendbuf.release();
   pl->sell.release();
   pl->red_vals.release(); pl->residual.release(); pl->rhs_red.release(); pl->x_red.release(); pl->dofs_trial.release();
   KrylovWork &k = pl->kw;
@@ -761,6 +762,72 @@ int apdx_plan_set_partition(apdx_plan *pl, int64_t owned_dof_begin, int64_t owne
   if (comm_active()) {
     APDX_CHECK(comm_halo_setup(pl));
     APDX_REQUIRE(!pl->kw.r.p, APDX_ERR_STATE, "apdx_plan_set_partition must precede the first solve");
+    APDX_CHECK(p2p_setup(pl));
+  }
+  return APDX_OK;
+}
+
+int apdx_plan_set_partition_lists(apdx_plan *pl, int64_t owned_dof_end, int32_t n_neighbours,
+                                  const int32_t *neighbour_rank, const int64_t *send_ptr_h, const int64_t *send_dof_h,
+                                  const int64_t *recv_dof_begin_h, const int64_t *recv_dof_end_h) {
+  APDX_REQUIRE(pl, APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(0 < owned_dof_end && owned_dof_end <= pl->n_dofs, APDX_ERR_INVALID, "bad owned range");
+  APDX_REQUIRE(n_neighbours >= 0, APDX_ERR_INVALID, "negative neighbour count");
+  APDX_REQUIRE(n_neighbours == 0 || (neighbour_rank && send_ptr_h && recv_dof_begin_h && recv_dof_end_h),
+               APDX_ERR_INVALID, "NULL neighbour list");
+  APDX_REQUIRE(!pl->kw.r.p, APDX_ERR_STATE, "apdx_plan_set_partition_lists must precede the first solve");
+  const int nn = n_neighbours;
+  APDX_REQUIRE(nn == 0 || send_ptr_h[0] == 0, APDX_ERR_INVALID, "send_ptr must start at 0");
+  for (int i = 0; i < nn; ++i) {
+    APDX_REQUIRE(send_ptr_h[i + 1] >= send_ptr_h[i], APDX_ERR_INVALID, "send_ptr must be non-decreasing");
+    APDX_REQUIRE(neighbour_rank[i] >= 0 && (!comm_active() || neighbour_rank[i] < comm_size()), APDX_ERR_INVALID,
+                 "neighbour rank %d out of range", neighbour_rank[i]);
+    APDX_REQUIRE(owned_dof_end <= recv_dof_begin_h[i] && recv_dof_begin_h[i] <= recv_dof_end_h[i] &&
+                     recv_dof_end_h[i] <= pl->n_dofs, APDX_ERR_INVALID, "ghost block of neighbour %d outside the ghost range", i);
+  }
+  APDX_REQUIRE(nn == 0 || send_ptr_h[nn] == 0 || send_dof_h, APDX_ERR_INVALID, "NULL send list");
+  // reduced numbering: free_id[dof] = reduced index or -1 (Dirichlet)
+  std::vector<int32_t> fid((size_t)pl->n_dofs);
+  APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  APDX_CUDA(cudaMemcpy(fid.data(), pl->free_id.p, fid.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  auto lower = [&](int64_t dof) -> int64_t {   // number of free dofs below `dof`
+    for (int64_t j = dof; j < pl->n_dofs; ++j)
+      if (fid[(size_t)j] >= 0) return fid[(size_t)j];
+    return pl->n_free;
+  };
+  auto &H = pl->hl;
+  H.rank.assign(neighbour_rank, neighbour_rank + nn);
+  H.send_ptr.assign((size_t)nn + 1, 0);
+  H.recv_begin.assign((size_t)nn, 0);
+  H.recv_count.assign((size_t)nn, 0);
+  std::vector<int32_t> sidx;
+  for (int i = 0; i < nn; ++i) {
+    for (int64_t k = send_ptr_h[i]; k < send_ptr_h[i + 1]; ++k) {
+      const int64_t d = send_dof_h[k];
+      APDX_REQUIRE(0 <= d && d < owned_dof_end, APDX_ERR_INVALID, "send list of neighbour %d holds dof %lld, which this rank does not own",
+                   i, (long long)d);
+      if (fid[(size_t)d] >= 0) sidx.push_back(fid[(size_t)d]);
+    }
+    H.send_ptr[(size_t)i + 1] = (int64_t)sidx.size();
+    H.recv_begin[(size_t)i] = lower(recv_dof_begin_h[i]);
+    H.recv_count[(size_t)i] = lower(recv_dof_end_h[i]) - H.recv_begin[(size_t)i];
+  }
+  APDX_CHECK(H.send_idx.alloc(sidx.size() > 0 ? sidx.size() : 1));
+  APDX_CHECK(H.sendbuf.alloc(sidx.size() > 0 ? sidx.size() : 1));
+  if (!sidx.empty())
+    APDX_CUDA(cudaMemcpy(H.send_idx.p, sidx.data(), sidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  H.active = true;
+  for (auto &g : pl->kgraph) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+  pl->sell.release();
+  pl->have_sell_values = false;
+  pl->owned_begin = 0; pl->owned_end = owned_dof_end;
+  pl->f0 = 0; pl->f1 = lower(owned_dof_end);
+  pl->rank_lo = pl->rank_hi = -1;
+  pl->halo_lo = pl->halo_hi = 0;
+  pl->send_lo = pl->send_hi = 0;
+  APDX_REQUIRE(pl->f1 > pl->f0, APDX_ERR_INVALID, "rank owns no free dof");
+  if (comm_active()) {
+    APDX_CHECK(comm_halo_setup_lists(pl));
     APDX_CHECK(p2p_setup(pl));
   }
   return APDX_OK;

@@ -236,6 +236,16 @@ struct apdx_plan {
   int32_t rank_lo = -1, rank_hi = -1;
   int64_t halo_lo = 0, halo_hi = 0;        // ghost free-dof counts below / above
   int64_t send_lo = 0, send_hi = 0;        // owned free dofs the lower / upper neighbour ghosts
+  // general partition (apdx_plan_set_partition_lists: RCB / unstructured meshes): local order [owned | ghosts grouped by
+  // owner]; the owned entries neighbour i ghosts are packed through send_idx[send_ptr[i] .. send_ptr[i+1]) into sendbuf,
+  // its entries arrive in the contiguous block [recv_begin[i], recv_begin[i] + recv_count[i]) of the reduced numbering
+  struct HaloLists {
+    bool active = false;
+    std::vector<int32_t> rank;
+    std::vector<int64_t> send_ptr, recv_begin, recv_count;
+    apdx::DevBuf<int32_t> send_idx;
+    apdx::DevBuf<double> sendbuf;
+  } hl;
 };
 
 namespace apdx {
@@ -263,6 +273,7 @@ int comm_size();
 int comm_allreduce_sum(double *buf_d, int count, cudaStream_t s);
 int comm_halo_exchange(apdx_plan *pl, double *x_d, cudaStream_t s);
 int comm_halo_setup(apdx_plan *pl);
+int comm_halo_setup_lists(apdx_plan *pl);
 int p2p_setup(apdx_plan *pl);
 void p2p_teardown(apdx_plan *pl);
 bool p2p_is_heap_vector(const apdx_plan *pl, const double *v);

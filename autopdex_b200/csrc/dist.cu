@@ -80,8 +80,65 @@ int comm_allreduce_sum(double *buf_d, int count, cudaStream_t s) {
   return APDX_OK;
 }
 
-// x_d is a vector in the local reduced numbering: [ghost_lo | owned | ghost_hi]
+// general partition: sendbuf[k] = x[send_idx[k]] (owned entries the neighbours ghost, grouped by neighbour)
+__global__ void k_halo_pack(const double *__restrict__ x, const int32_t *__restrict__ send_idx, int64_t n,
+                            double *__restrict__ sendbuf) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    sendbuf[k] = x[send_idx[k]];
+}
+
+static int comm_halo_exchange_lists(apdx_plan *pl, double *x_d, cudaStream_t s) {
+  auto &H = pl->hl;
+  const int nn = (int)H.rank.size();
+  if (nn == 0) return APDX_OK;
+  const int64_t n_send = H.send_ptr[nn];
+  if (n_send > 0) {
+    const unsigned grid = (unsigned)((n_send + 255) / 256 < 1184 ? (n_send + 255) / 256 : 1184);
+    k_halo_pack<<<grid, 256, 0, s>>>(x_d, H.send_idx.p, n_send, H.sendbuf.p);
+    pl->stats.kernel_launches += 1;
+    APDX_CUDA(cudaGetLastError());
+  }
+  APDX_NCCL(g_nccl.GroupStart());
+  for (int i = 0; i < nn; ++i) {
+    const int64_t cs = H.send_ptr[i + 1] - H.send_ptr[i];
+    if (cs > 0) APDX_NCCL(g_nccl.Send(H.sendbuf.p + H.send_ptr[i], (size_t)cs, ncclFloat64, H.rank[i], g_nccl.comm, s));
+    if (H.recv_count[i] > 0)
+      APDX_NCCL(g_nccl.Recv(x_d + H.recv_begin[i], (size_t)H.recv_count[i], ncclFloat64, H.rank[i], g_nccl.comm, s));
+  }
+  APDX_NCCL(g_nccl.GroupEnd());
+  return APDX_OK;
+}
+
+// every pair of neighbours must agree on the message lengths (a mismatch would be undefined behaviour inside NCCL):
+// each rank tells neighbour i how many entries it expects from it and compares the answer with what it will send
+int comm_halo_setup_lists(apdx_plan *pl) {
+  auto &H = pl->hl;
+  const int nn = (int)H.rank.size();
+  if (nn == 0) return APDX_OK;
+  int64_t *buf = nullptr;
+  APDX_CUDA(cudaMalloc((void **)&buf, 2 * (size_t)nn * sizeof(int64_t)));
+  APDX_CUDA(cudaMemcpy(buf, H.recv_count.data(), (size_t)nn * sizeof(int64_t), cudaMemcpyHostToDevice));
+  cudaStream_t s = pl->stream;
+  APDX_NCCL(g_nccl.GroupStart());
+  for (int i = 0; i < nn; ++i) {
+    APDX_NCCL(g_nccl.Send(buf + i, 1, ncclInt64, H.rank[i], g_nccl.comm, s));
+    APDX_NCCL(g_nccl.Recv(buf + nn + i, 1, ncclInt64, H.rank[i], g_nccl.comm, s));
+  }
+  APDX_NCCL(g_nccl.GroupEnd());
+  APDX_CUDA(cudaStreamSynchronize(s));
+  std::vector<int64_t> expect(nn);
+  APDX_CUDA(cudaMemcpy(expect.data(), buf + nn, (size_t)nn * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  cudaFree(buf);
+  for (int i = 0; i < nn; ++i)
+    APDX_REQUIRE(expect[i] == H.send_ptr[i + 1] - H.send_ptr[i], APDX_ERR_INVALID,
+                 "halo lists disagree: rank %d expects %lld entries from this rank, the send list holds %lld", H.rank[i],
+                 (long long)expect[i], (long long)(H.send_ptr[i + 1] - H.send_ptr[i]));
+  return APDX_OK;
+}
+
+// x_d is a vector in the local reduced numbering: [ghost_lo | owned | ghost_hi] (slabs) or [owned | ghosts by owner]
 int comm_halo_exchange(apdx_plan *pl, double *x_d, cudaStream_t s) {
+  if (pl->hl.active) return comm_halo_exchange_lists(pl, x_d, s);
   if (pl->rank_lo < 0 && pl->rank_hi < 0) return APDX_OK;
   APDX_NCCL(g_nccl.GroupStart());
   if (pl->rank_lo >= 0) {
@@ -165,7 +222,8 @@ int p2p_setup(apdx_plan *pl) {
   const char *mode = getenv("APDX_COMM");
   // APDX_COMM: mbox = dot-product all-reduces through peer-memory mailboxes, halo on NCCL; p2p | fused = opt-in A/B
   // variants that also move the halo to peer stores; nccl / cg2 = NCCL only
-  const bool full = mode && (strcmp(mode, "p2p") == 0 || strcmp(mode, "fused") == 0);
+  // the peer-store halo variants assume slab neighbours (contiguous send ranges): list partitions stay on NCCL
+  const bool full = mode && (strcmp(mode, "p2p") == 0 || strcmp(mode, "fused") == 0) && !pl->hl.active;
   const bool mbox = mode && strcmp(mode, "mbox") == 0;
   if (!full && !mbox) return APDX_OK;
   if (g_nccl.nranks > P2P_MAX_RANKS) return APDX_OK;

@@ -1098,7 +1098,7 @@ static int spmv_exchange(apdx_plan *pl, double *v, double *y, const double *w, i
   Sell &S = pl->sell;
   const char *ov = getenv("APDX_OVERLAP");
   // measured on 2 B200s: no gain over the in-order exchange, so opt-in (APDX_OVERLAP=1)
-  const bool overlap = !c.p2p && (ov && strcmp(ov, "1") == 0) && S.hi_begin > S.lo_end &&
+  const bool overlap = !c.p2p && !pl->hl.active && (ov && strcmp(ov, "1") == 0) && S.hi_begin > S.lo_end &&
                        (S.lo_end + (S.n_slices - S.hi_begin)) > 0;
   if (!overlap) {
     int he = 0;

@@ -136,3 +136,73 @@ def slab_partition(n_elements, rank, nranks):
                 node_lo=g0 * per_plane, node_hi=g1 * per_plane, owned_node_lo=p0 * per_plane,
                 owned_node_hi=p1 * per_plane, rank_lo=rank - 1 if rank > 0 else -1,
                 rank_hi=rank + 1 if rank < nranks - 1 else -1, per_plane=per_plane)
+
+
+# ---- general partition: recursive coordinate bisection (north_star: "slab/RCB partitions") -------------
+def rcb_owner(coords, nranks):
+    """Recursive coordinate bisection of the NODES: owner[n] in [0, nranks).  Every cut is perpendicular to the longest
+    extent of the current box and splits the node count in proportion to the ranks on either side; ties are broken by
+    the node id, so that every process computes the same owners."""
+    coords = np.asarray(coords, dtype=np.float64)
+    owner = np.zeros(coords.shape[0], dtype=np.int32)
+    stack = [(np.arange(coords.shape[0], dtype=np.int64), 0, int(nranks))]
+    while stack:
+        ids, r0, nr = stack.pop()
+        if nr == 1 or ids.size == 0:
+            owner[ids] = r0
+            continue
+        x = coords[ids]
+        ax = int(np.argmax(x.max(axis=0) - x.min(axis=0)))
+        nl = nr // 2
+        k = (ids.size * nl) // nr
+        order = np.lexsort((ids, x[:, ax]))            # by coordinate, then by node id
+        ids = ids[order]
+        stack.append((ids[:k], r0, nl))
+        stack.append((ids[k:], r0 + nl, nr - nl))
+    return owner
+
+
+def rcb_partition(coords, connectivity, rank, nranks, owner=None):
+    """Part `rank` of a node-based partition of an arbitrary mesh (default owners: rcb_owner).
+
+    connectivity: tuple of (n_elem, nen) arrays (one per element set, global node ids).  The local mesh holds every
+    element that touches an owned node ("ghost elements" are assembled redundantly, so the owned rows need no
+    communication) and numbers its nodes [owned, ascending global id | ghosts by (owner, global id)].
+    Returns a dict: nodes (global id per local node), n_owned, elements (local connectivity per set), element_ids
+    (global element index per local element, per set), neighbours, send_nodes (per neighbour: local ids of the owned
+    nodes it ghosts, in ITS ghost order), recv_node_ranges (per neighbour: local id range of the ghosts it owns), and
+    the settings['b200 partition'] dict of the b200 backend under 'b200 partition'."""
+    coords = np.asarray(coords)
+    if owner is None:
+        owner = rcb_owner(coords, nranks)
+    owner = np.asarray(owner)
+    conns = [np.asarray(c) for c in connectivity]
+    local_rows = [np.flatnonzero((owner[c] == rank).any(axis=1)) for c in conns]
+    owned = np.flatnonzero(owner == rank)
+    touched = np.unique(np.concatenate([conns[i][local_rows[i]].ravel() for i in range(len(conns))] + [owned]))
+    ghosts = touched[owner[touched] != rank]
+    ghosts = ghosts[np.lexsort((ghosts, owner[ghosts]))]
+    nodes = np.concatenate([owned, ghosts]).astype(np.int64)
+    local_of = np.full(coords.shape[0], -1, dtype=np.int64)
+    local_of[nodes] = np.arange(nodes.size)
+    elements = [local_of[conns[i][local_rows[i]]] for i in range(len(conns))]
+    neighbours = [int(q) for q in np.unique(owner[ghosts])]
+    # ghosts of neighbour q are contiguous here; what q ghosts of mine: my nodes in elements that touch a q-owned node
+    send_nodes, recv_ranges = [], []
+    go = owner[ghosts]
+    for q in neighbours:
+        b = owned.size + int(np.searchsorted(go, q, side="left"))
+        e = owned.size + int(np.searchsorted(go, q, side="right"))
+        recv_ranges.append((b, e))
+        mine = []
+        for i in range(len(conns)):
+            c = conns[i][local_rows[i]]
+            oc = owner[c]
+            rows = (oc == q).any(axis=1)
+            mine.append(c[rows][oc[rows] == rank])
+        send_nodes.append(local_of[np.unique(np.concatenate(mine))])
+    part = dict(owned_node_begin=0, owned_node_end=int(owned.size), neighbours=neighbours, send_nodes=send_nodes,
+                recv_node_ranges=recv_ranges)
+    return {"nodes": nodes, "n_owned": int(owned.size), "elements": elements, "element_ids": local_rows,
+            "neighbours": neighbours, "send_nodes": send_nodes, "recv_node_ranges": recv_ranges, "owner": owner,
+            "b200 partition": part}

@@ -185,12 +185,22 @@ class _State:
         self.mask = mask
         self.keepalive = [settings.get("dirichlet dofs")]      # the cache key uses id(): keep the object alive
         self.plan = backend.Plan(self.dim, self.n_nodes, self.nf, specs, mask)
-        # multi-GPU: this process holds one slab (owned nodes + ghost planes, local ids in global order)
+        # multi-GPU: this process holds one slab (owned nodes + ghost planes, local ids in global order) or one part of
+        # a general partition (mesher.rcb_partition: owned nodes first, then the ghosts grouped by owning rank)
         self.partition = settings.get("b200 partition")
         if self.partition:
             pt = self.partition
-            self.plan.set_partition(pt["owned_node_begin"] * self.nf, pt["owned_node_end"] * self.nf,
-                                    pt.get("rank_lo", -1), pt.get("rank_hi", -1))
+            if "neighbours" in pt:
+                nf = self.nf
+                dofs_of = lambda nodes: (np.asarray(nodes, dtype=np.int64)[:, None] * nf + np.arange(nf)).ravel()
+                if pt.get("owned_node_begin", 0) != 0:
+                    raise ValueError("b200 backend: a list partition numbers its owned nodes first")
+                self.plan.set_partition_lists(pt["owned_node_end"] * nf, pt["neighbours"],
+                                              [dofs_of(v) for v in pt["send_nodes"]],
+                                              [(b * nf, e * nf) for b, e in pt["recv_node_ranges"]])
+            else:
+                self.plan.set_partition(pt["owned_node_begin"] * self.nf, pt["owned_node_end"] * self.nf,
+                                        pt.get("rank_lo", -1), pt.get("rank_hi", -1))
         n = self.plan.n_dofs
         self.dofs_d = backend.DeviceArray(n)
         self.vals_d = backend.DeviceArray(n)

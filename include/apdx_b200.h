@@ -218,6 +218,15 @@ int apdx_comm_destroy(void);
 int apdx_comm_allreduce_host(double *inout_h, int32_t count, int32_t op);
 int apdx_plan_set_partition(apdx_plan *plan, int64_t owned_dof_begin, int64_t owned_dof_end,
                             int32_t rank_lo, int32_t rank_hi);
+/* General partition (recursive coordinate bisection, unstructured meshes): the local mesh numbers the owned nodes
+ * first ([0, owned_dof_end) in dof units) and then the ghost nodes grouped by owning rank.  For neighbour i
+ * (neighbour_rank[i]) send_dof_h[send_ptr_h[i] .. send_ptr_h[i+1]) lists the LOCAL dof ids (owned, ascending in the
+ * order the neighbour stores them as ghosts) whose values it needs, and the ghost dofs it owns are the local dof range
+ * [recv_dof_begin_h[i], recv_dof_end_h[i]).  Dirichlet dofs are dropped from both sides (the masks of a shared node must
+ * agree across ranks).  The halo exchange is then a pack kernel + one grouped ncclSend/ncclRecv per neighbour.        */
+int apdx_plan_set_partition_lists(apdx_plan *plan, int64_t owned_dof_end, int32_t n_neighbours,
+                                  const int32_t *neighbour_rank, const int64_t *send_ptr_h, const int64_t *send_dof_h,
+                                  const int64_t *recv_dof_begin_h, const int64_t *recv_dof_end_h);
 
 #ifdef __cplusplus
 }
