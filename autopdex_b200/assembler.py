@@ -1,4 +1,5 @@
-"""assembler.assemble_residual / assemble_tangent of the reference interface on the b200 backend.
+"""assembler.assemble_residual / assemble_tangent / assemble_tangent_diagonal of the reference interface on the b200
+backend.
 
 assemble_residual (assembler.py:587-637) returns a dofs-shaped array; assemble_tangent
 (assembler.py:682-777) returns the tangent with duplicates ALREADY SUMMED, as a CSR triple in
@@ -39,4 +40,23 @@ def assemble_tangent(dofs, settings, static_settings, reduced=False):
     return CSR(st.plan.values(reduced), indices, indptr, (n, n))
 
 
-__all__ = ["assemble_residual", "assemble_tangent", "CSR", "backend"]
+def csr_diagonal(csr):
+    """Diagonal of a CSR triple in canonical form (absent diagonal entries are zeros)."""
+    n = csr.shape[0]
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(csr.indptr))
+    on_diag = csr.indices == rows
+    diag = np.zeros(n, dtype=np.float64)
+    diag[rows[on_diag]] = csr.data[on_diag]
+    return diag
+
+
+def assemble_tangent_diagonal(dofs, settings, static_settings):
+    """assembler.assemble_tangent_diagonal (assembler.py:639-680): the flat (dict_flatten order) diagonal of the
+    tangent WITHOUT Dirichlet reduction, i.e. the sum over the sets of the element-matrix diagonals scattered to
+    their dofs (_get_tangent_diagonal, assembler.py:219-329).  Read off the device-assembled, duplicate-summed CSR
+    matrix: index bookkeeping on the host, no arithmetic (the Jacobi preconditioner of the Krylov solve takes its
+    diagonal from the sliced-ELL matrix on the device and never comes through here)."""
+    return csr_diagonal(assemble_tangent(dofs, settings, static_settings))
+
+
+__all__ = ["assemble_residual", "assemble_tangent", "assemble_tangent_diagonal", "csr_diagonal", "CSR", "backend"]

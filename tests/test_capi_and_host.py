@@ -294,3 +294,15 @@ def test_jax_ffi_shim_compiles_and_binds_only_declared_entry_points():
     except ImportError:
         with pytest.raises(ImportError, match="jax.ffi"):
             importlib.import_module("autopdex_b200.jax_ffi")
+
+
+def test_csr_diagonal_reads_the_diagonal_of_a_canonical_csr():
+    import scipy.sparse as sp
+    from autopdex_b200 import assembler
+    rng = np.random.default_rng(2)
+    A = sp.random(40, 40, density=0.15, random_state=3, format="csr")
+    A = A + sp.diags(rng.standard_normal(40) * (rng.uniform(size=40) > 0.3))     # some diagonal entries are absent
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    got = assembler.csr_diagonal(assembler.CSR(A.data, A.indices.astype(np.int64), A.indptr.astype(np.int64), A.shape))
+    assert np.array_equal(got, A.diagonal())

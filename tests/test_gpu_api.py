@@ -209,6 +209,9 @@ def test_assembler_module_matches_oracle():
     assert np.array_equal(K.indptr, full.indptr) and np.array_equal(K.indices, full.indices)
     assert np.abs(K.data - full.data).max() / np.abs(full.data).max() < 1e-12
     assert np.abs(R.ravel() - Ro).max() / np.abs(Ro).max() < 1e-12
+    # assemble_tangent_diagonal (assembler.py:639-680): flat diagonal of the unreduced tangent
+    D = assembler.assemble_tangent_diagonal(dofs, settings, static_settings)
+    assert D.shape == (dofs.size,) and np.abs(D - full.diagonal()).max() / np.abs(full.diagonal()).max() < 1e-12
 
 
 @pytest.mark.parametrize("transpose", [False, True])
