@@ -154,49 +154,6 @@ def test_sparse_mode_backward_euler_steps(dim, order, mode):
     assert len(solver._PLAN_CACHE) >= 1
 
 
-def test_user_element_hex8_backward_euler_steps():
-    """BASELINE config 3 at parity size: transient heat conduction on a hex8 mesh as three 'user element' sets
-    (poisson_weak conduction, forward_backward_euler_weak capacity, neumann_weak inflow on the face x = 1),
-    'solver type': 'linear', backward-Euler steps with the pattern reused (maze_backward_euler.py:308-374)."""
-    from autopdex_b200 import mesher, models, seeder, solver, spaces
-    from oracle import quadrature as oquad
-    n, dt, inflow = 4, 50.0 / 250.0, -1.0e3
-    coords, elems = mesher.structured_mesh((n, n, n), problems.UNIT_CUBE, "brick")
-    face = problems.boundary_faces_x1(n)
-    gp3, gp2 = seeder.gauss_legendre_nd(3, 2), seeder.gauss_legendre_nd(2, 2)
-    cond = models.isoparametric_domain_element_galerkin(models.poisson_weak(lambda x, s: 1.0), spaces.fem_iso_line_quad_brick, *gp3)
-    cap = models.isoparametric_domain_element_galerkin(models.forward_backward_euler_weak(lambda x, s: 0.1),
-                                                       spaces.fem_iso_line_quad_brick, *gp3)
-    flux = models.isoparametric_surface_element_galerkin(models.neumann_weak(lambda x: inflow), spaces.fem_iso_line_quad_brick,
-                                                         *gp2, tangent_contributions=False)
-    static_settings = {"assembling mode": ("user element",) * 3, "solution structure": ("nodal imposition",) * 3,
-                       "model": (cond, cap, flux), "solver type": "linear", "solver backend": "b200", "solver": "cg",
-                       "type of preconditioner": "jacobi", "verbose": -1}
-    mask = (np.abs(coords[:, 0]) < 1e-9)[:, None]
-    values = np.zeros(mask.shape)
-    dofs = np.zeros(mask.shape)
-    settings = {"connectivity": (elems, elems, face), "node coordinates": coords, "dirichlet dofs": mask,
-                "dirichlet conditions": values, "time increment": dt, "dofs n": dofs}
-    osets = [dict(kind="domain", etype="hex8", conn=elems, nf=1, gp=oquad.gauss_legendre_nd(3, 2),
-                  model=dict(name="poisson_weak", coefficient=1.0, source=0.0)),
-             dict(kind="domain", etype="hex8", conn=elems, nf=1, gp=oquad.gauss_legendre_nd(3, 2),
-                  model=dict(name="capacity", coefficient=0.1)),
-             dict(kind="surface", etype="quad4", conn=face, nf=1, gp=oquad.gauss_legendre_nd(2, 2),
-                  model=dict(name="neumann", traction=np.asarray([inflow])))]
-    prob = osolve.Problem(osets, coords, mask, values, {"time increment": dt, "dofs n": dofs.copy()})
-    ref = dofs.copy()
-    n_plans = None
-    for step in range(3):
-        settings["dofs n"] = dofs
-        dofs = dofs + solver.solver(dofs, settings, static_settings, tol=1e-13)[0]          # maze_backward_euler.py:362
-        prob.settings["dofs n"] = ref
-        ref = ref + osolve.solve_linear(prob, ref)
-        assert np.linalg.norm(dofs - ref) / np.linalg.norm(ref) < 1e-8
-        n_plans = len(solver._PLAN_CACHE) if n_plans is None else n_plans
-        assert len(solver._PLAN_CACHE) == n_plans          # the plan (pattern) of step 1 serves the later steps
-    assert ref.max() > 1.0                                  # the inflow heats the bar: a non-trivial state was compared
-
-
 def test_assembler_module_matches_oracle():
     from autopdex_b200 import assembler
     p, settings, static_settings = _cook_settings()
@@ -209,9 +166,6 @@ def test_assembler_module_matches_oracle():
     assert np.array_equal(K.indptr, full.indptr) and np.array_equal(K.indices, full.indices)
     assert np.abs(K.data - full.data).max() / np.abs(full.data).max() < 1e-12
     assert np.abs(R.ravel() - Ro).max() / np.abs(Ro).max() < 1e-12
-    # assemble_tangent_diagonal (assembler.py:639-680): flat diagonal of the unreduced tangent
-    D = assembler.assemble_tangent_diagonal(dofs, settings, static_settings)
-    assert D.shape == (dofs.size,) and np.abs(D - full.diagonal()).max() / np.abs(full.diagonal()).max() < 1e-12
 
 
 @pytest.mark.parametrize("transpose", [False, True])
