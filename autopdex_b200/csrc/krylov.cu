@@ -315,7 +315,7 @@ template <int B, int XG, bool SYM>
 __device__ __forceinline__ void spmv_stored_fast(int32_t offl, const double *__restrict__ vpc, int32_t nb,
                                                  const double *__restrict__ xr0, const double *__restrict__ xr1, double &a0,
                                                  double &a1) {
-  static_assert(B % XG == 0, "x groups must tile the batch");
+  static_assert(XG >= 1 && XG <= B, "x groups are taken out of the batch");   // the last group may be shorter
   for (int32_t jb = 0; jb < nb; jb += B) {
     double va[B], vb[B];
 #pragma unroll
@@ -329,11 +329,14 @@ __device__ __forceinline__ void spmv_stored_fast(int32_t offl, const double *__r
       int32_t off[XG];
       double xa[XG], xb[XG];
 #pragma unroll
-      for (int u = 0; u < XG; ++u) off[u] = __shfl_sync(0xffffffffu, offl, jb + g + u);   // lane j holds column j's offset
+      for (int u = 0; u < XG; ++u)
+        if (g + u < B) off[u] = __shfl_sync(0xffffffffu, offl, jb + g + u);   // lane j holds column j's offset
 #pragma unroll
-      for (int u = 0; u < XG; ++u) { xa[u] = __ldg(xr0 + off[u]); xb[u] = __ldg(xr1 + off[u]); }
+      for (int u = 0; u < XG; ++u)
+        if (g + u < B) { xa[u] = __ldg(xr0 + off[u]); xb[u] = __ldg(xr1 + off[u]); }
 #pragma unroll
-      for (int u = 0; u < XG; ++u) { a0 += va[g + u] * xa[u]; a1 += vb[g + u] * xb[u]; }
+      for (int u = 0; u < XG; ++u)
+        if (g + u < B) { a0 += va[g + u] * xa[u]; a1 += vb[g + u] * xb[u]; }
       if (XG < B) asm volatile("" ::: "memory");   // keep the next group's gathers behind this group's FMAs
     }
   }
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(VEC_BLOCK, OCC)
   constexpr int WPB = VEC_BLOCK / 32;
   // batch sizes of the occupancy variants (OCC == 2: the measured default)
   constexpr int U = OCC == 2 ? SPMV_U : (OCC == 3 ? 5 : 3);          // generic paths: columns per batch
-  constexpr int XG9 = OCC == 2 ? 9 : 3, XG8 = OCC == 2 ? 8 : 4, XG7 = OCC == 2 ? 7 : 1;
+  constexpr int XG9 = OCC == 2 ? 9 : 3, XG8 = OCC == 2 ? 8 : 4, XG7 = OCC == 2 ? 7 : 4;   // (OCC 4 takes its own path)
   constexpr int MSUB = OCC == 2 ? 8 : (OCC == 3 ? 4 : 2);            // mirrored table entries per sub-batch
   double acc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
