@@ -341,6 +341,56 @@ __device__ __forceinline__ void spmv_stored_fast(int32_t offl, const double *__r
     }
   }
 }
+// PIPE variant (APDX_SPMV_PIPE=1): the values of a slice's first B columns were requested while the warp was still
+// in the mirrored phase of its previous slice (pa / pb), so that one HBM round trip of every slice overlaps the L2
+// round trips of the slice before.  Same column order as spmv_stored_fast<B, XG>: bit-identical sums.
+template <int B, int XG, bool SYM>
+__device__ __forceinline__ void spmv_stored_fast_pre(const double (&pa)[B], const double (&pb)[B], int32_t offl,
+                                                     const double *__restrict__ vpc, int32_t nb,
+                                                     const double *__restrict__ xr0, const double *__restrict__ xr1,
+                                                     double &a0, double &a1) {
+  static_assert(XG >= 1 && XG <= B, "x groups are taken out of the batch");
+#pragma unroll
+  for (int g = 0; g < B; g += XG) {
+    int32_t off[XG];
+    double xa[XG], xb[XG];
+#pragma unroll
+    for (int u = 0; u < XG; ++u)
+      if (g + u < B) off[u] = __shfl_sync(0xffffffffu, offl, g + u);
+#pragma unroll
+    for (int u = 0; u < XG; ++u)
+      if (g + u < B) { xa[u] = __ldg(xr0 + off[u]); xb[u] = __ldg(xr1 + off[u]); }
+#pragma unroll
+    for (int u = 0; u < XG; ++u)
+      if (g + u < B) { a0 += pa[g + u] * xa[u]; a1 += pb[g + u] * xb[u]; }
+  }
+  for (int32_t jb = B; jb < nb; jb += B) {
+    double va[B], vb[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const double *q = vpc + (size_t)(jb + u) * 64;
+      va[u] = SYM ? __ldg(q) : __ldcs(q);
+      vb[u] = SYM ? __ldg(q + 32) : __ldcs(q + 32);
+    }
+#pragma unroll
+    for (int g = 0; g < B; g += XG) {
+      int32_t off[XG];
+      double xa[XG], xb[XG];
+#pragma unroll
+      for (int u = 0; u < XG; ++u)
+        if (g + u < B) off[u] = __shfl_sync(0xffffffffu, offl, jb + g + u);
+#pragma unroll
+      for (int u = 0; u < XG; ++u)
+        if (g + u < B) { xa[u] = __ldg(xr0 + off[u]); xb[u] = __ldg(xr1 + off[u]); }
+#pragma unroll
+      for (int u = 0; u < XG; ++u)
+        if (g + u < B) { a0 += va[g + u] * xa[u]; a1 += vb[g + u] * xb[u]; }
+    }
+  }
+}
+// chunks of 32 columns that the fast paths take in batches of 7 (not 9, not 8)
+__device__ __forceinline__ bool spmv_takes_7(int32_t nb) { return nb > 0 && nb % 7 == 0 && nb % 9 != 0 && nb % 8 != 0; }
+
 template <int MB>
 __device__ __forceinline__ void spmv_mirrored_fast(const int4 *__restrict__ tab, int32_t M, const double *__restrict__ val,
                                                    const double *__restrict__ xr0, const double *__restrict__ xr1, int lane,
@@ -434,8 +484,8 @@ __device__ __forceinline__ void spmv_mirrored_sub(const int4 *__restrict__ tab, 
     spmv_mirrored_steps<MB, SUB, 0, CLAMP>(tab + jb, val, x, xr0, xr1, lane, lane + 32, rr0, rr1, n_cols, a0, a1);
 }
 
-template <int NDOT, int NF, bool SYM, int OCC>
-__global__ void __launch_bounds__(VEC_BLOCK, OCC)
+template <int NDOT, int NF, bool SYM, int OCCV>
+__global__ void __launch_bounds__(VEC_BLOCK, OCCV == 5 ? 2 : OCCV)
     k_spmv_sell(const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_m, const int64_t *__restrict__ valptr,
                 const int64_t *__restrict__ idxptr, const double *__restrict__ val, const int32_t *__restrict__ idx,
                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, int64_t row0,
@@ -453,10 +503,14 @@ __global__ void __launch_bounds__(VEC_BLOCK, OCC)
   }
   const int lane = threadIdx.x & 31;
   constexpr int WPB = VEC_BLOCK / 32;
+  constexpr bool PIPE = OCCV == 5;          // 2 blocks per SM + first value batch of the next slice requested early
+  constexpr int OCC = PIPE ? 2 : OCCV;
   // batch sizes of the occupancy variants (OCC == 2: the measured default)
-  constexpr int U = OCC == 2 ? SPMV_U : (OCC == 3 ? 5 : 3);          // generic paths: columns per batch
-  constexpr int XG9 = OCC == 2 ? 9 : 3, XG8 = OCC == 2 ? 8 : 4, XG7 = OCC == 2 ? 7 : 4;   // (OCC 4 takes its own path)
-  constexpr int MSUB = OCC == 2 ? 8 : (OCC == 3 ? 4 : 2);            // mirrored table entries per sub-batch
+  // (PIPE keeps 14 prefetched values alive through the stored phase: shallower batches there, like OCC 3)
+  constexpr int U = PIPE ? 5 : (OCC == 2 ? SPMV_U : (OCC == 3 ? 5 : 3));          // generic paths: columns per batch
+  constexpr bool DEEP = OCC == 2 && !PIPE;
+  constexpr int XG9 = DEEP ? 9 : 3, XG8 = DEEP ? 8 : 4, XG7 = DEEP ? 7 : 4;       // (OCC 4 takes its own path)
+  constexpr int MSUB = PIPE ? 4 : (OCC == 2 ? 8 : (OCC == 3 ? 4 : 2));   // mirrored table entries per sub-batch
   double acc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
   for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
@@ -489,6 +543,23 @@ __global__ void __launch_bounds__(VEC_BLOCK, OCC)
   Hdr cur;
   load_hdr(si_begin, cur);
   int32_t offl0 = load_offsets(cur);
+  double pva[7], pvb[7];                    // PIPE: the first seven value columns of the coming slice
+  auto prefetch_values = [&](const Hdr &h) {
+    const bool take = (h.M & SELL_FAST) != 0 && spmv_takes_7(min(32, h.wenc & 0x7fffffff));   // warp-uniform
+    if (take) {
+      const double *q = val + h.vp + lane;
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        pva[u] = SYM ? __ldg(q + (size_t)u * 64) : __ldcs(q + (size_t)u * 64);
+        pvb[u] = SYM ? __ldg(q + (size_t)u * 64 + 32) : __ldcs(q + (size_t)u * 64 + 32);
+      }
+    }
+  };
+  if constexpr (PIPE) {
+#pragma unroll
+    for (int u = 0; u < 7; ++u) pva[u] = pvb[u] = 0.0;
+    prefetch_values(cur);
+  }
   for (int64_t si = si_begin; si < si_end; si += si_step) {
     Hdr nxt;
     load_hdr(si + si_step, nxt);
@@ -513,7 +584,9 @@ __global__ void __launch_bounds__(VEC_BLOCK, OCC)
     for (int32_t jc = 0; jc < W; jc += 32) {
       const int32_t nb = min(32, W - jc);
       const int32_t nbt = (nb + U - 1) / U, bs = (nb + nbt - 1) / nbt;   // equal batches of <= U columns
-      if (OCC == 4 && fast && (nb % 7 == 0 || nb % 4 == 0 || nb % 3 == 0 || nb % 5 == 0)) {
+      if (PIPE && jc == 0 && fast && spmv_takes_7(nb)) {
+        spmv_stored_fast_pre<7, 4, SYM>(pva, pvb, offl0, vp, nb, xr0, xr1, a0, a1);
+      } else if (OCC == 4 && fast && (nb % 7 == 0 || nb % 4 == 0 || nb % 3 == 0 || nb % 5 == 0)) {
         // 64 registers: value batches of at most 7 columns, the x operands of a 7-batch one column at a time
         const int32_t offl = jc == 0 ? offl0 : __ldg(ip + jc + min(lane, nb - 1));
         if (nb % 7 == 0) spmv_stored_fast<7, 1, SYM>(offl, vp + (size_t)jc * 64, nb, xr0, xr1, a0, a1);
@@ -574,8 +647,9 @@ __global__ void __launch_bounds__(VEC_BLOCK, OCC)
     }
     // the next slice's header has arrived by now: request its offsets
     const int32_t offl_n = load_offsets(nxt);
+    if constexpr (PIPE) prefetch_values(nxt);   // in flight during the mirrored phase below
     if (SYM && M > 0) {
-      if constexpr (OCC == 2) {
+      if constexpr (OCC == 2 && !PIPE) {
         if (fast) {
           if (cur.M & SELL_MB7) spmv_mirrored_fast<7>(tab, M, val, xr0, xr1, lane, a0, a1);
           else spmv_mirrored_fast<8>(tab, M, val, xr0, xr1, lane, a0, a1);
@@ -998,7 +1072,16 @@ static int spmv_bps() {
   return bps;
 }
 // kernel variant compiled for that many resident blocks per SM (2 = default; 3 and 4: fewer registers, more warps)
-static int spmv_occ() { const int b = spmv_bps(); return b <= 2 ? 2 : (b == 3 ? 3 : 4); }
+// 5 = the default occupancy with the pipelined value prefetch (APDX_SPMV_PIPE=1)
+static int spmv_occ() {
+  static int occ = 0;
+  if (!occ) {
+    const int b = spmv_bps();
+    const char *e = getenv("APDX_SPMV_PIPE");
+    occ = b <= 2 ? ((e && atoi(e) == 1) ? 5 : 2) : (b == 3 ? 3 : 4);
+  }
+  return occ;
+}
 static unsigned spmv_grid(int64_t n_slices) {
   static int resident = 0;
   if (!resident) {
@@ -1042,6 +1125,7 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
     const int occ = spmv_occ();                                                                                        \
     if (occ == 2) APDX_SPMV_OCC(NFV, 2);                                                                               \
     else if (occ == 3) APDX_SPMV_OCC(NFV, 3);                                                                          \
+    else if (occ == 5) APDX_SPMV_OCC(NFV, 5);                                                                          \
     else APDX_SPMV_OCC(NFV, 4);                                                                                        \
   } while (0)
   if (S.nf == 1) APDX_SPMV_NF(1);

@@ -19,6 +19,7 @@ for b in 128 64 32; do APDX_ELEM_BLOCK=$b run asm_block_$b python tools/time_ass
 # 4. the bench line with the default kernels and with each occupancy variant
 run bench_default python bench.py --steps 3 --warmup 3
 for b in 3 4; do APDX_SPMV_BPS=$b run bench_bps$b python bench.py --steps 3 --warmup 3 --no-cpu; done
+APDX_SPMV_PIPE=1 run bench_pipe python bench.py --steps 3 --warmup 3 --no-cpu
 # 5. launch list of the bench command (shares only: ncu serialises and cold-starts every launch)
 run ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/s3_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu
