@@ -179,6 +179,57 @@ def case_elements(out):
                  settings_extra=mat, dofs_scale=0.05)
 
 
+def potential_case(out, tag, coords, elems, ansatz, gp, dim):
+    """README-style 'user potential' with dict dofs on a 3-D (or any) isoparametric element: the route on which the
+    reference itself can run the scalar Poisson problem of BASELINE config 4 on hex elements (poisson_weak as a 'user
+    element' with array dofs fails inside the reference: jnp.dot of (1,3) gradients for (n,1) dofs, dofs.shape[-1] in
+    assembler._get_residual for (n,) dofs)."""
+    shift = jnp.asarray([0.3, -0.2, 0.5][:dim])
+
+    def integrand_fun(x_int, ansatz_fun, settings, static_settings, elem_number, set):   # short_example.py:23-33, in 3-D
+        x = ansatz_fun["physical coor"](x_int)
+        phi_fun = ansatz_fun["phi"]
+        phi = phi_fun(x_int)
+        dphi_dx = jax.jacrev(phi_fun)(x_int)
+        source_term = 3.0 * jnp.sin(2.0 * x @ x) - jnp.cos((x - shift) @ (x - shift))
+        return (1 / 2) * dphi_dx @ dphi_dx - source_term * phi
+
+    user_potential = models.mixed_reference_domain_potential(integrand_fun, {"phi": ansatz}, *gp, "phi")
+    static_settings = flax.core.FrozenDict({"assembling mode": ("user potential",), "solution structure": ("nodal imposition",),
+                                            "model": (user_potential,), "solver type": "newton", "solver backend": "scipy",
+                                            "solver": "lapack", "verbose": -1})
+    n = coords.shape[0]
+    settings = {"connectivity": ({"phi": jnp.asarray(elems)},), "dirichlet dofs": {"phi": jnp.zeros(n, dtype=bool)},
+                "node coordinates": {"phi": jnp.asarray(coords)}, "dirichlet conditions": {"phi": jnp.zeros(n)}}
+    rng = np.random.default_rng(11)
+    dofs = {"phi": jnp.asarray(rng.uniform(-1, 1, n))}
+    t = time.time()
+    R = assembler.assemble_residual(dofs, settings, static_settings)
+    K = assembler.assemble_tangent(dofs, settings, static_settings)
+    data, rows, cols = bcoo_arrays(K)
+    out.update({tag + "_coords": A(coords), tag + "_elems": A(elems), tag + "_gp_x": A(gp[0]), tag + "_gp_w": A(gp[1]),
+                tag + "_dofs": A(dofs["phi"]), tag + "_R": A(R["phi"]), tag + "_K_data": data, tag + "_K_rows": rows,
+                tag + "_K_cols": cols})
+    print("  %s: %d dofs, %.1f s" % (tag, n, time.time() - t), flush=True)
+
+
+def case_potential3d(out):
+    cube2 = [[0, 0, 0], [1, 0, 0], [1.1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1.2], [1, 1, 1], [0, 1, 1]]
+    c, e = mesher.structured_mesh((1, 2, 2), cube2, "brick")
+    potential_case(out, "pot_hex8", A(c), A(e), spaces.fem_iso_line_quad_brick, seeder.gauss_legendre_nd(dimension=3, order=2), 3)
+    c1, e1 = mesher.structured_mesh((1, 1, 1), cube2, "brick")
+    c27, e27 = mesher.elevate_mesh_order(c1, e1)
+    potential_case(out, "pot_hex27", A(c27), A(e27), spaces.fem_iso_line_quad_brick, seeder.gauss_legendre_nd(dimension=3, order=4), 3)
+    # tetrahedra: the 5 hard-coded nodes of two tets sharing a face (the mesher has no tet meshes)
+    ct = np.array([[0., 0., 0.], [1., 0., 0.1], [0.1, 1., 0.], [0., 0.2, 1.], [1.1, 1.2, 0.9]])
+    et = np.array([[0, 1, 2, 3], [1, 2, 3, 4]])
+    potential_case(out, "pot_tet4", ct, et, spaces.fem_iso_line_tri_tet, seeder.int_pts_ref_tet(2), 3)
+    cq, eq = mesher.structured_mesh((2, 1), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "tri")
+    potential_case(out, "pot_tri3", A(cq), A(eq), spaces.fem_iso_line_tri_tet, seeder.int_pts_ref_tri(2), 2)
+    cq6, eq6 = mesher.elevate_mesh_order(cq, eq)
+    potential_case(out, "pot_tri6", A(cq6), A(eq6), spaces.fem_iso_line_tri_tet, seeder.int_pts_ref_tri(2), 2)
+
+
 def case_sparse_compiled(out):
     """'sparse' assembling mode (assembler.py:874-1035 -> variational_schemes.weak_form_galerkin ->
     solution_structures 'compiled' shape functions): conduction + Euler capacity + surface inflow on P1 triangles,
@@ -252,7 +303,7 @@ def case_newton_semantics(out):
 
 
 CASES = {"tables": case_tables, "readme3": lambda o: readme_case(3, o, "readme3"),
-         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
+         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 
 if __name__ == "__main__":

@@ -184,6 +184,39 @@ def test_user_elements_against_reference_run(tag):
     assert rel(data, FIX[tag + "_K_data"]) < TANGENT_RTOL
 
 
+# ---- README-style 'user potential' with dict dofs on hex8 / hex27 / tet4 / tri3 / tri6 (session 3): the route on which the
+# reference itself runs the scalar Poisson problem on isoparametric elements (generator: case_potential3d)
+POTENTIAL_TAGS = ["pot_hex8", "pot_hex27", "pot_tet4", "pot_tri3", "pot_tri6"]
+
+
+def _potential_source(x):
+    shift = np.array([0.3, -0.2, 0.5][:x.shape[-1]])
+    return 3.0 * np.sin(2.0 * np.sum(x * x, axis=-1)) - np.cos(np.sum((x - shift) ** 2, axis=-1))
+
+
+def potential_problem(tag):
+    from oracle import elements as oel
+    coords, elems = FIX[tag + "_coords"], FIX[tag + "_elems"]
+    st = dict(kind="domain", etype=tag[4:], conn=elems, nf=1, gp=(FIX[tag + "_gp_x"], FIX[tag + "_gp_w"]),
+              model=dict(name="poisson_potential"))
+    st["model"]["source"] = _potential_source(oel.gauss_point_coordinates(st, coords))
+    mask = np.zeros((coords.shape[0], 1), dtype=bool)
+    return dict(sets=[st], coords=coords, mask=mask, values=np.zeros(mask.shape), nf=1)
+
+
+@pytest.mark.parametrize("tag", POTENTIAL_TAGS)
+def test_user_potential_3d_and_simplex_against_reference_run(tag):
+    if tag + "_R" not in FIX:
+        pytest.skip("fixture %s not generated yet" % tag)
+    p = potential_problem(tag)
+    dofs = FIX[tag + "_dofs"][:, None]
+    R, data = oasm.assemble(p["sets"], p["coords"], dofs, {})
+    rows, cols = oasm.coo_indices(p["sets"])
+    assert np.array_equal(rows, FIX[tag + "_K_rows"]) and np.array_equal(cols, FIX[tag + "_K_cols"])
+    assert rel(R, FIX[tag + "_R"].ravel()) < 1e-11
+    assert rel(data, FIX[tag + "_K_data"]) < TANGENT_RTOL
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", ELEMENT_TAGS + ["readme3", "readme5"])
 def test_gpu_against_reference_run(tag):

@@ -66,3 +66,29 @@ def test_assemble_tangent_diagonal_matches_oracle():
     full = oasm.scipy_assembling(data, rows, cols, dofs.size)
     D = assembler.assemble_tangent_diagonal(dofs, settings, static_settings)
     assert D.shape == (dofs.size,) and np.abs(D - full.diagonal()).max() / np.abs(full.diagonal()).max() < 1e-12
+
+
+@pytest.mark.parametrize("tag", ["pot_hex8", "pot_hex27", "pot_tet4", "pot_tri3", "pot_tri6"])
+def test_gpu_against_reference_run_user_potential(tag):
+    """The CUDA path against the reference's own outputs for the README-style 'user potential' on hex8 (the register
+    kernel of BASELINE config 4), hex27, tet4, tri3 and tri6 elements (fixtures of case_potential3d)."""
+    import scipy.sparse as sp
+    from autopdex_b200 import backend
+    from tests import gpu_util
+    from tests import test_reference_fixtures as trf
+    FIX = trf.FIX
+    if tag + "_R" not in FIX:
+        pytest.skip("fixture %s not generated yet" % tag)
+    p = trf.potential_problem(tag)
+    p["mask"][0] = True                       # any mask: the full-CSR values do not depend on it
+    plan = gpu_util.make_plan(p)
+    n = p["mask"].size
+    d, r = backend.DeviceArray.from_host(FIX[tag + "_dofs"]), backend.DeviceArray(n)
+    plan.assemble(d, True, r)
+    ref = sp.csr_matrix(sp.coo_matrix((FIX[tag + "_K_data"], (FIX[tag + "_K_rows"], FIX[tag + "_K_cols"])), shape=(n, n)))
+    ref.sort_indices()
+    indptr, indices = plan.csr(False)
+    assert np.array_equal(indptr, ref.indptr) and np.array_equal(indices, ref.indices)
+    assert trf.rel(plan.values(False), ref.data) < trf.TANGENT_RTOL
+    assert trf.rel(r.download(), FIX[tag + "_R"].ravel()) < 1e-11
+    plan.destroy()
