@@ -230,6 +230,33 @@ def case_potential3d(out):
     potential_case(out, "pot_tri6", A(cq6), A(eq6), spaces.fem_iso_line_tri_tet, seeder.int_pts_ref_tri(2), 2)
 
 
+def case_potential_more(out):
+    """quad9 and tet10 on the same route (tet10 mid-edge nodes in the order of spaces.fem_iso_line_tri_tet: edges
+    (0,1), (1,2), (0,2), (0,3), (1,3), (2,3); slightly curved edges)."""
+    cq, eq = mesher.structured_mesh((2, 1), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "quad")
+    c9, e9 = problems_elevate_quads(A(cq), A(eq))
+    potential_case(out, "pot_quad9", c9, e9, spaces.fem_iso_line_quad_brick, seeder.gauss_legendre_nd(dimension=2, order=4), 2)
+    ct = np.array([[0., 0., 0.], [1., 0., 0.1], [0.1, 1., 0.], [0., 0.2, 1.], [1.1, 1.2, 0.9]])
+    et = np.array([[0, 1, 2, 3], [1, 2, 3, 4]])
+    pts, edges, rows = [p for p in ct], {}, []
+    rng = np.random.default_rng(4)
+    for el in et:
+        row = list(el)
+        for a, b in ((0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)):
+            key = (min(el[a], el[b]), max(el[a], el[b]))
+            if key not in edges:
+                edges[key] = len(pts)
+                pts.append(0.5 * (ct[el[a]] + ct[el[b]]) + rng.uniform(-0.03, 0.03, 3))
+            row.append(edges[key])
+        rows.append(row)
+    potential_case(out, "pot_tet10", np.array(pts), np.array(rows), spaces.fem_iso_line_tri_tet, seeder.int_pts_ref_tet(2), 3)
+
+
+def problems_elevate_quads(coords, elems):
+    from oracle import mesher as omesh          # quad4 -> quad9 in the node order of spaces.py:1924 (DATA for the reference run)
+    return omesh.elevate_quads(coords, elems)
+
+
 def case_sparse_compiled(out):
     """'sparse' assembling mode (assembler.py:874-1035 -> variational_schemes.weak_form_galerkin ->
     solution_structures 'compiled' shape functions): conduction + Euler capacity + surface inflow on P1 triangles,
@@ -303,7 +330,7 @@ def case_newton_semantics(out):
 
 
 CASES = {"tables": case_tables, "readme3": lambda o: readme_case(3, o, "readme3"),
-         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
+         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 
 if __name__ == "__main__":

@@ -186,7 +186,7 @@ def test_user_elements_against_reference_run(tag):
 
 # ---- README-style 'user potential' with dict dofs on hex8 / hex27 / tet4 / tri3 / tri6 (session 3): the route on which the
 # reference itself runs the scalar Poisson problem on isoparametric elements (generator: case_potential3d)
-POTENTIAL_TAGS = ["pot_hex8", "pot_hex27", "pot_tet4", "pot_tri3", "pot_tri6"]
+POTENTIAL_TAGS = ["pot_hex8", "pot_hex27", "pot_tet4", "pot_tri3", "pot_tri6", "pot_quad9", "pot_tet10"]
 
 
 def _potential_source(x):

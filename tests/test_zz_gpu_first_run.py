@@ -68,7 +68,7 @@ def test_assemble_tangent_diagonal_matches_oracle():
     assert D.shape == (dofs.size,) and np.abs(D - full.diagonal()).max() / np.abs(full.diagonal()).max() < 1e-12
 
 
-@pytest.mark.parametrize("tag", ["pot_hex8", "pot_hex27", "pot_tet4", "pot_tri3", "pot_tri6"])
+@pytest.mark.parametrize("tag", ["pot_hex8", "pot_hex27", "pot_tet4", "pot_tri3", "pot_tri6", "pot_quad9", "pot_tet10"])
 def test_gpu_against_reference_run_user_potential(tag):
     """The CUDA path against the reference's own outputs for the README-style 'user potential' on hex8 (the register
     kernel of BASELINE config 4), hex27, tet4, tri3 and tri6 elements (fixtures of case_potential3d)."""
