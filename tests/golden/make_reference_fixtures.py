@@ -257,6 +257,31 @@ def problems_elevate_quads(coords, elems):
     return omesh.elevate_quads(coords, elems)
 
 
+def case_elements_more(out):
+    """Q1 quads + line2 traction (Cook Q1 set-up), tet4 neo-Hooke + tri3 traction face, tri3 plain-stress elasticity."""
+    E = lambda x, settings: settings["youngs modulus"]
+    nu = lambda x, settings: settings["poisson ratio"]
+    mat = {"youngs modulus": 100.0, "poisson ratio": 0.3, "load multiplier": 4.0}
+    cq, eq = mesher.structured_mesh((2, 2), [[0., 0.], [48., 44.], [48., 60.], [0., 44.]], "quad")
+    weak = models.hyperelastic_steady_state_weak(models.neo_hooke, E, nu, "plain strain")
+    trac = models.neumann_weak(lambda x, settings: jnp.asarray([0., settings["load multiplier"]]))
+    right = np.array([[6, 7], [7, 8]])                      # nodes with i = 2 (x = 48)
+    element_case(out, "quad4_neo_line2", A(cq), A(eq), 2, weak, spaces.fem_iso_line_quad_brick,
+                 seeder.gauss_legendre_nd(dimension=2, order=2),
+                 surf=(right, trac, seeder.gauss_legendre_nd(dimension=1, order=2)), settings_extra=mat, dofs_scale=0.5)
+    ct = np.array([[0., 0., 0.], [1., 0., 0.1], [0.1, 1., 0.], [0., 0.2, 1.], [1.1, 1.2, 0.9]])
+    et = np.array([[0, 1, 2, 3], [1, 2, 3, 4]])
+    weak3 = models.hyperelastic_steady_state_weak(models.neo_hooke, E, nu, "3d")
+    trac3 = models.neumann_weak(lambda x, settings: jnp.asarray([0.2, 0.5, -settings["load multiplier"]]))
+    element_case(out, "tet4_neo_tri3", ct, et, 3, weak3, spaces.fem_iso_line_tri_tet, seeder.int_pts_ref_tet(2),
+                 surf=(np.array([[1, 2, 4]]), trac3, seeder.int_pts_ref_tri(2)), settings_extra=mat, dofs_scale=0.03)
+    c3, e3 = mesher.structured_mesh((2, 1), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "tri")
+    w = models.linear_elasticity_weak(E, nu, "plain stress", lambda x: jnp.asarray([0.3, -1.0]))
+    element_case(out, "tri3_linel", A(c3), A(e3), 2, w, spaces.fem_iso_line_tri_tet, seeder.int_pts_ref_tri(2),
+                 settings_extra=mat, dofs_scale=0.05)
+    out["tet_rule_2_x"], out["tet_rule_2_w"] = A(seeder.int_pts_ref_tet(2)[0]), A(seeder.int_pts_ref_tet(2)[1])
+
+
 def case_sparse_compiled(out):
     """'sparse' assembling mode (assembler.py:874-1035 -> variational_schemes.weak_form_galerkin ->
     solution_structures 'compiled' shape functions): conduction + Euler capacity + surface inflow on P1 triangles,
@@ -330,7 +355,7 @@ def case_newton_semantics(out):
 
 
 CASES = {"tables": case_tables, "readme3": lambda o: readme_case(3, o, "readme3"),
-         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
+         "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "elements_more": case_elements_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 
 if __name__ == "__main__":

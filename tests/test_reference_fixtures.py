@@ -165,13 +165,33 @@ def _element_problem(tag):
         gp = (FIX["tri_rule_2_x"], FIX["tri_rule_2_w"])
         return [dict(kind="domain", etype="tri6", conn=e, nf=2, gp=gp,
                      model=dict(name="neo_hooke", mode="plain strain", **mat))], c, 2
+    # ---- session 3 (generator: case_elements_more) ----
+    tets = (np.array([[0., 0., 0.], [1., 0., 0.1], [0.1, 1., 0.], [0., 0.2, 1.], [1.1, 1.2, 0.9]]), np.array([[0, 1, 2, 3], [1, 2, 3, 4]]))
+    if tag == "quad4_neo_line2":
+        c, e = om.structured_mesh((2, 2), [[0., 0.], [48., 44.], [48., 60.], [0., 44.]], "quad")
+        sets = [dict(kind="domain", etype="quad4", conn=e, nf=2, gp=oq.gauss_legendre_nd(2, 2),
+                     model=dict(name="neo_hooke", mode="plain strain", **mat)),
+                dict(kind="surface", etype="line2", conn=np.array([[6, 7], [7, 8]]), nf=2, gp=oq.gauss_legendre_nd(1, 2),
+                     model=dict(name="neumann", traction=np.array([0.0, 4.0])))]
+        return sets, c, 2
+    if tag == "tet4_neo_tri3":
+        sets = [dict(kind="domain", etype="tet4", conn=tets[1], nf=3, gp=(FIX["tet_rule_2_x"], FIX["tet_rule_2_w"]),
+                     model=dict(name="neo_hooke", mode="3d", **mat)),
+                dict(kind="surface", etype="tri3", conn=np.array([[1, 2, 4]]), nf=3, gp=(FIX["tri_rule_2_x"], FIX["tri_rule_2_w"]),
+                     model=dict(name="neumann", traction=np.array([0.2, 0.5, -4.0])))]
+        return sets, tets[0], 3
+    if tag == "tri3_linel":
+        c, e = om.structured_mesh((2, 1), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "tri")
+        return [dict(kind="domain", etype="tri3", conn=e, nf=2, gp=(FIX["tri_rule_2_x"], FIX["tri_rule_2_w"]),
+                     model=dict(name="linear_elasticity", mode="plain stress", body_load=np.array([0.3, -1.0]), **mat))], c, 2
     raise KeyError(tag)
 
 
 ELEMENT_TAGS = ["cook_q9", "hex8_neo", "linel_plain_strain", "linel_plain_stress", "linel_3d", "tri6_neo"]
+ELEMENT_TAGS_MORE = ["quad4_neo_line2", "tet4_neo_tri3", "tri3_linel"]     # session 3: GPU half in test_zz_gpu_first_run.py
 
 
-@pytest.mark.parametrize("tag", ELEMENT_TAGS)
+@pytest.mark.parametrize("tag", ELEMENT_TAGS + ELEMENT_TAGS_MORE)
 def test_user_elements_against_reference_run(tag):
     if tag + "_R" not in FIX:
         pytest.skip("fixture %s not generated yet" % tag)

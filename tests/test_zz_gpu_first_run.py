@@ -68,22 +68,16 @@ def test_assemble_tangent_diagonal_matches_oracle():
     assert D.shape == (dofs.size,) and np.abs(D - full.diagonal()).max() / np.abs(full.diagonal()).max() < 1e-12
 
 
-@pytest.mark.parametrize("tag", ["pot_hex8", "pot_hex27", "pot_tet4", "pot_tri3", "pot_tri6", "pot_quad9", "pot_tet10"])
-def test_gpu_against_reference_run_user_potential(tag):
-    """The CUDA path against the reference's own outputs for the README-style 'user potential' on hex8 (the register
-    kernel of BASELINE config 4), hex27, tet4, tri3 and tri6 elements (fixtures of case_potential3d)."""
+def _gpu_vs_reference_run(tag, p):
+    """Full CSR pattern (exact), values and residual of the CUDA path against the reference's own outputs."""
     import scipy.sparse as sp
     from autopdex_b200 import backend
     from tests import gpu_util
     from tests import test_reference_fixtures as trf
     FIX = trf.FIX
-    if tag + "_R" not in FIX:
-        pytest.skip("fixture %s not generated yet" % tag)
-    p = trf.potential_problem(tag)
-    p["mask"][0] = True                       # any mask: the full-CSR values do not depend on it
     plan = gpu_util.make_plan(p)
     n = p["mask"].size
-    d, r = backend.DeviceArray.from_host(FIX[tag + "_dofs"]), backend.DeviceArray(n)
+    d, r = backend.DeviceArray.from_host(FIX[tag + "_dofs"].ravel()), backend.DeviceArray(n)
     plan.assemble(d, True, r)
     ref = sp.csr_matrix(sp.coo_matrix((FIX[tag + "_K_data"], (FIX[tag + "_K_rows"], FIX[tag + "_K_cols"])), shape=(n, n)))
     ref.sort_indices()
@@ -92,3 +86,27 @@ def test_gpu_against_reference_run_user_potential(tag):
     assert trf.rel(plan.values(False), ref.data) < trf.TANGENT_RTOL
     assert trf.rel(r.download(), FIX[tag + "_R"].ravel()) < 1e-11
     plan.destroy()
+
+
+@pytest.mark.parametrize("tag", ["pot_hex8", "pot_hex27", "pot_tet4", "pot_tri3", "pot_tri6", "pot_quad9", "pot_tet10"])
+def test_gpu_against_reference_run_user_potential(tag):
+    """The CUDA path against the reference's own outputs for the README-style 'user potential' on hex8 (the register
+    kernel of BASELINE config 4), hex27, tet4, tet10, tri3, tri6 and quad9 elements (fixtures of case_potential3d)."""
+    from tests import test_reference_fixtures as trf
+    if tag + "_R" not in trf.FIX:
+        pytest.skip("fixture %s not generated yet" % tag)
+    p = trf.potential_problem(tag)
+    p["mask"][0] = True                       # any mask: the full-CSR values do not depend on it
+    _gpu_vs_reference_run(tag, p)
+
+
+@pytest.mark.parametrize("tag", ["quad4_neo_line2", "tet4_neo_tri3", "tri3_linel"])
+def test_gpu_against_reference_run_more_user_elements(tag):
+    """Q1 quads + line2 traction, tet4 neo-Hooke + tri3 traction face, tri3 plain-stress elasticity (case_elements_more)."""
+    from tests import test_reference_fixtures as trf
+    if tag + "_R" not in trf.FIX:
+        pytest.skip("fixture %s not generated yet" % tag)
+    sets, coords, nf = trf._element_problem(tag)
+    mask = np.zeros((coords.shape[0], nf), dtype=bool)
+    mask[0] = True
+    _gpu_vs_reference_run(tag, dict(sets=sets, coords=coords, mask=mask, values=np.zeros(mask.shape), nf=nf))
