@@ -163,3 +163,48 @@ def test_rcb_halo_exchange_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [True, True]
+
+
+def _reduced_halo_lists(part, mask_local, nf):
+    """Python restatement of the index bookkeeping of apdx_plan_set_partition_lists (csrc/api.cu): local dof lists ->
+    lists in the reduced (Dirichlet-free) numbering.  Returns (f1, send_idx per neighbour, (recv_begin, count))."""
+    m = np.asarray(mask_local).ravel()
+    fid = np.where(m, -1, np.cumsum(~m) - 1)                       # free_id: reduced index or -1
+    n_free = int((~m).sum())
+
+    def lower(dof):
+        nxt = np.flatnonzero(~m[dof:])
+        return int(fid[dof + nxt[0]]) if nxt.size else n_free
+    dofs_of = lambda nodes: (np.asarray(nodes)[:, None] * nf + np.arange(nf)).ravel()
+    send = [fid[dofs_of(v)][fid[dofs_of(v)] >= 0] for v in part["send_nodes"]]
+    recv = [(lower(b * nf), lower(e * nf) - lower(b * nf)) for b, e in part["recv_node_ranges"]]
+    return lower(part["n_owned"] * nf), send, recv
+
+
+@pytest.mark.parametrize("name,nranks", [("neo_hooke_brick", 4), ("poisson_hex", 3)])
+def test_rcb_halo_in_reduced_numbering_with_dirichlet_dofs(name, nranks):
+    """With Dirichlet dofs removed on both sides (the device works in the reduced numbering) the packed send lists
+    still line up with the receivers' ghost blocks, and the message lengths agree pairwise (what comm_halo_setup_lists
+    cross-checks at set-up)."""
+    p = _problem(name)
+    nf = p["nf"]
+    conns = tuple(s["conn"] for s in p["sets"])
+    mask = np.asarray(p["mask"]).reshape(-1, nf).copy()
+    mask[::7, 0] = True                                            # a few more constrained dofs, partially constrained nodes
+    parts = [mesher.rcb_partition(p["coords"], conns, r, nranks) for r in range(nranks)]
+    xg = np.random.default_rng(3).standard_normal(mask.shape)      # a global dof field
+    red = []
+    for pt in parts:
+        ml = mask[pt["nodes"]]
+        f1, send, recv = _reduced_halo_lists(pt, ml, nf)
+        xl = xg[pt["nodes"]].ravel()[~ml.ravel()]                  # local reduced vector [owned | ghosts]
+        assert f1 == int((~ml[:pt["n_owned"]]).sum())
+        red.append((send, recv, xl))
+    for r, pt in enumerate(parts):
+        send_r, recv_r, x_r = red[r]
+        for i, q in enumerate(pt["neighbours"]):
+            send_q, _, x_q = red[q]
+            j = parts[q]["neighbours"].index(r)
+            b, cnt = recv_r[i]
+            assert cnt == send_q[j].size                           # pairwise message lengths agree
+            assert np.array_equal(x_q[send_q[j]], x_r[b:b + cnt])  # k_halo_pack on q == ghost block on r
