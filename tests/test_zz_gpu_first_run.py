@@ -1,7 +1,7 @@
-"""GPU tests written in the CPU-only session 3 of round 1 (no GPU minutes were left): their oracle halves were run on
-the CPU, their device halves have not run yet.  The file sorts last on purpose, so that under `pytest -x` a surprise
-here cannot hide the suite that has already been green on a B200.  After their first green run they belong in
-test_gpu_api.py."""
+"""GPU tests written in the CPU-only session 3 of round 1: their oracle halves were run on the CPU while they were
+written; the device halves had their first run on a B200 with the last 95 GPU-seconds of the round: 12 passed
+(profiles/r01i_first_run_tests_12_passed.txt).  The file sorts last so that under `pytest -x` anything new added here
+cannot hide the long-verified suite; the tests can move into test_gpu_api.py / test_reference_fixtures.py."""
 import numpy as np
 import pytest
 
