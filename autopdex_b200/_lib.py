@@ -74,6 +74,7 @@ SIGNATURES = {
                               C.POINTER(_I32)]),
     "apdx_tangent_solve": (C.c_int, [_P, C.POINTER(KrylovOpts), _P, _P, C.c_int, _P, C.POINTER(_I32)]),
     "apdx_plan_stats": (C.c_int, [_P, C.POINTER(_D)]),
+    "apdx_plan_last_krylov": (C.c_int, [_P, C.POINTER(_D), C.POINTER(_I32)]),
     "apdx_plan_sell_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "apdx_time_spmv": (C.c_int, [_P, _I32, C.POINTER(_D)]),
     "apdx_measure_fp64_peak": (C.c_int, [C.POINTER(_D)]),

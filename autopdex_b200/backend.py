@@ -337,7 +337,11 @@ class Plan:
         _lib.check(_lib.load().apdx_plan_stats(self.h, out))
         keys = ("assembly_tangent_ms", "assembly_residual_ms", "krylov_ms", "krylov_iters", "spmv_launches",
                 "total_ms", "kernel_launches", "sell_bytes")
-        return dict(zip(keys, list(out)[:8]))
+        d = dict(zip(keys, list(out)[:8]))
+        rr, ok = C.c_double(0.0), C.c_int32(1)
+        _lib.check(_lib.load().apdx_plan_last_krylov(self.h, C.byref(rr), C.byref(ok)))
+        d["krylov_relres"], d["krylov_converged"] = rr.value, bool(ok.value)
+        return d
 
     def sell_info(self):
         out = (C.c_int64 * 6)()

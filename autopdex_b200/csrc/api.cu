@@ -6,9 +6,15 @@
 #include <algorithm>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace apdx {
+
+// NVTX v3 is header-only: the ranges cost a function-pointer test unless a profiler injected its library
+void nvtx_push(const char *name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
 
 size_t g_plan_bytes = 0;
 // live plans: apdx_comm_destroy must drop their captured CUDA graphs (they hold NCCL operations of the communicator)
@@ -16,7 +22,6 @@ static std::vector<apdx_plan *> g_plans;
 void drop_all_krylov_graphs() {
   for (apdx_plan *pl : g_plans) {
     if (pl->stream) cudaStreamSynchronize(pl->stream);
-    if (pl->stream2) cudaStreamSynchronize(pl->stream2);
     for (auto &g : pl->kgraph)
       if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
   }
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters) {
 static inline unsigned g1(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 static int assemble_internal(apdx_plan *pl, const double *dofs_d, int tangent_flags, double *residual_d) {
+  struct Range { Range(const char *n) { nvtx_push(n); } ~Range() { nvtx_pop(); } } range(tangent_flags ? "apdx:assemble_tangent" : "apdx:assemble_residual");
   APDX_CHECK(launch_element_kernels(pl, dofs_d, tangent_flags != 0));
   // tangent_flags: bit 0 full CSR values, bit 1 reduced CSR values (cold paths), bit 2 sliced-ELL values (solver)
   APDX_CHECK(launch_gather_reduce(pl, tangent_flags & 3, residual_d));
@@ -320,9 +326,6 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
     return fail(APDX_ERR_CUDA);
   }
   for (auto &e : pl->ev) cudaEventCreate(&e);
-  cudaStreamCreateWithFlags(&pl->stream2, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming);
   if (cudaMallocHost((void **)&pl->pinned, 64 * sizeof(double)) != cudaSuccess) {
     set_error("cudaMallocHost failed");
     return fail(APDX_ERR_CUDA);
@@ -346,7 +349,13 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
       if (st.d.conn_itemsize == 8) {
         tmp.resize(cn);
         const int64_t *c64 = static_cast<const int64_t *>(st.d.conn_h);
-        for (int64_t k = 0; k < cn; ++k) tmp[k] = (int32_t)c64[k];
+        for (int64_t k = 0; k < cn; ++k) {
+          if (c64[k] < 0 || c64[k] >= n_nodes) {   // check the 64-bit value: narrowing first could alias a corrupt id into range
+            set_error("set %d: node id %lld out of range [0,%lld)", i, (long long)c64[k], (long long)n_nodes);
+            return fail(APDX_ERR_INVALID);
+          }
+          tmp[k] = (int32_t)c64[k];
+        }
         src32 = tmp.data();
       } else {
         src32 = static_cast<const int32_t *>(st.d.conn_h);
@@ -403,7 +412,6 @@ int apdx_plan_destroy(apdx_plan *pl) {
   if (!pl) return APDX_OK;
   g_plans.erase(std::remove(g_plans.begin(), g_plans.end(), pl), g_plans.end());
   if (pl->stream) cudaStreamSynchronize(pl->stream);
-  if (pl->stream2) cudaStreamSynchronize(pl->stream2);
   for (auto &st : pl->sets) {
     st.conn.release(); st.shape_n.release(); st.shape_dn.release(); st.gp_w.release();
     st.ip_n.release(); st.ip_dndx.release(); st.ip_w.release();
@@ -419,14 +427,11 @@ int apdx_plan_destroy(apdx_plan *pl) {
   pl->sell.release();
   pl->red_vals.release(); pl->residual.release(); pl->rhs_red.release(); pl->x_red.release(); pl->dofs_trial.release();
   KrylovWork &k = pl->kw;
-  k.r.release(); k.p.release(); k.q.release(); k.z.release(); k.s.release(); k.t.release(); k.phat.release();
+  k.r.release(); k.p.release(); k.q.release(); k.s.release(); k.t.release(); k.phat.release();
   k.shat.release(); k.r0.release(); k.minv.release(); k.partial.release(); k.scal.release(); k.ticket.release();
-  k.flags.release(); k.st_sc.release(); k.st_fl.release(); k.scratch.release();
+  k.flags.release();
   if (pl->pinned) cudaFreeHost(pl->pinned);
   for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
-  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
-  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
-  if (pl->stream2) cudaStreamDestroy(pl->stream2);
   if (pl->stream) cudaStreamDestroy(pl->stream);
   delete pl;
   return APDX_OK;
@@ -579,7 +584,7 @@ int apdx_measure_fp64_peak(double *tflops) {
   cudaEvent_t e0, e1;
   APDX_CUDA(cudaEventCreate(&e0));
   APDX_CUDA(cudaEventCreate(&e1));
-  const int blocks = 148 * 8, iters = 20000;
+  const int blocks = sm_count() * 8, iters = 20000;
   k_fp64_peak<<<blocks, 256>>>(d, 1000);
   double best = 0.0;
   for (int rep = 0; rep < 3; ++rep) {
@@ -736,11 +741,19 @@ int apdx_plan_stats(const apdx_plan *pl, double out[8]) {
   return APDX_OK;
 }
 
+int apdx_plan_last_krylov(const apdx_plan *pl, double *relres, int32_t *converged) {
+  APDX_REQUIRE(pl && relres && converged, APDX_ERR_INVALID, "NULL argument");
+  *relres = pl->stats.krylov_relres;
+  *converged = pl->stats.krylov_converged != 0.0 ? 1 : 0;
+  return APDX_OK;
+}
+
 int apdx_plan_set_partition(apdx_plan *pl, int64_t owned_dof_begin, int64_t owned_dof_end, int32_t rank_lo,
                             int32_t rank_hi) {
   APDX_REQUIRE(pl, APDX_ERR_INVALID, "NULL argument");
   APDX_REQUIRE(0 <= owned_dof_begin && owned_dof_begin < owned_dof_end && owned_dof_end <= pl->n_dofs, APDX_ERR_INVALID,
                "bad owned range");
+  APDX_REQUIRE(!pl->kw.r.p, APDX_ERR_STATE, "apdx_plan_set_partition must precede the first solve");
   int64_t *out = reinterpret_cast<int64_t *>(pl->pinned + 48);
   int64_t *tmp_d = nullptr;
   APDX_CUDA(cudaMalloc((void **)&tmp_d, 2 * sizeof(int64_t)));
@@ -761,7 +774,6 @@ int apdx_plan_set_partition(apdx_plan *pl, int64_t owned_dof_begin, int64_t owne
   if (rank_hi < 0) APDX_REQUIRE(pl->halo_hi == 0, APDX_ERR_INVALID, "ghost dofs above the owned range but no upper neighbour");
   if (comm_active()) {
     APDX_CHECK(comm_halo_setup(pl));
-    APDX_REQUIRE(!pl->kw.r.p, APDX_ERR_STATE, "apdx_plan_set_partition must precede the first solve");
     APDX_CHECK(p2p_setup(pl));
   }
   return APDX_OK;

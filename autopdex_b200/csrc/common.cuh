@@ -103,40 +103,30 @@ struct SetData {
 };
 
 struct KrylovWork {
-  DevBuf<double> r, p, q, z, s, t, phat, shat, r0, minv;
+  DevBuf<double> r, p, q, s, t, phat, shat, r0, minv;
   DevBuf<double> partial;     // per-block partial sums of the fused dot products
   DevBuf<double> scal;        // device scalars (see krylov.cu)
-  DevBuf<double> st_sc, scratch;  // double-buffered scalar state of the p2p-fused CG, reduction scratch
-  DevBuf<int32_t> st_fl;
   DevBuf<unsigned int> ticket;
-  DevBuf<int32_t> flags;      // [0]=done [1]=iterations [2]=breakdown
+  DevBuf<int32_t> flags;      // [0]=done [1]=iterations [2]=breakdown [3]=maxiter [4]=final
 };
 
-// ---- peer-to-peer (NVLink) plumbing of the multi-GPU Krylov loop (dist.cu, krylov.cu) ------------------
+// ---- peer-memory (NVLink) plumbing of the multi-GPU Krylov loop (dist.cu, krylov.cu) ------------------
 constexpr int P2P_MAX_RANKS = 16;
 // device-visible descriptor; every pointer is dereferenceable from this GPU (peer memory mapped through CUDA IPC)
 struct P2PDev {
-  int rank, nranks, has_lo, has_hi;
+  int rank, nranks;
   double *mbox[P2P_MAX_RANKS];   // rank r's mailboxes: double [2 slots][P2P_MAX_RANKS senders][4]
   int *mflag[P2P_MAX_RANKS];     // rank r's mailbox flags: int [2 slots][P2P_MAX_RANKS senders]
-  int *hflag_self;               // my halo flags: [0] written by the lower neighbour, [1] by the upper one
   int *err;                      // my time-out flag
-  int *epoch_self;               // device-resident reduction counter of the mailbox all-reduce (mbox mode)
+  int *epoch_self;               // device-resident reduction counter of the mailbox all-reduce
 };
 struct P2P {
-  bool enabled = false;          // Krylov vectors in the heap, halo by peer stores, mailbox reductions (APDX_COMM=p2p|fused)
-  bool mbox = false;             // only the dot-product all-reduces go through the mailboxes; halo stays on NCCL
-  char *heap = nullptr;          // symmetric heap: [mailboxes | flags | 3 Krylov vectors of `stride` doubles]
+  bool mbox = false;             // the dot-product all-reduces go through the mailboxes; halo stays on NCCL
+  char *heap = nullptr;          // exported block: [mailboxes | flags]
   size_t heap_bytes = 0;
   void *peer_base[P2P_MAX_RANKS]{};
   P2PDev *dev = nullptr;
   int *err_d = nullptr;
-  double *vec_base = nullptr;
-  int64_t stride = 0;
-  double *peer_vec[2]{};         // vec_base of the lower / upper neighbour
-  int *peer_hflag[2]{};          // lower neighbour's hflag[1], upper neighbour's hflag[0]
-  int64_t peer_lo_f1 = 0;        // lower neighbour's owned end = start of its upper ghost range
-  int red_epoch = 0, halo_epoch = 0;
 };
 
 // instantiated CUDA graph of one chunk of Krylov iterations (krylov.cu)
@@ -158,7 +148,6 @@ struct Sell {
   bool sym = true;            // lower columns read from the transposed position where possible (sell.cu)
   int64_t row0 = 0, n_rows = 0, n_slices = 0, n_val = 0, n_idx = 0, n_mirrored = 0;
   int nf = 1;                 // slices interleave the nf dofs per node (sell.cu)
-  int64_t lo_end = 0, hi_begin = 0;  // slices [lo_end, hi_begin) reference no ghost column (multi-GPU overlap)
   DevBuf<int32_t> sl_w;       // [n_slices] stored width | (offset mode ? 1<<31 : 0)
   DevBuf<int32_t> sl_m;       // [n_slices] padded number of mirrored lower columns | SELL_MB7 (table behind the offsets)
   DevBuf<int64_t> valptr;     // [n_slices+1] start of the slice's value block (doubles)
@@ -178,7 +167,13 @@ struct Sell {
 struct Stats {
   double asm_tangent_ms = 0, asm_residual_ms = 0, krylov_ms = 0, total_ms = 0;
   double krylov_iters = 0, spmv_launches = 0, kernel_launches = 0;
+  double krylov_relres = 0, krylov_converged = 1;   // outcome of the last Krylov solve
 };
+
+// NVTX ranges around assemble / krylov / halo (visible in nsys / ncu --nvtx; no-ops without a profiler attached)
+void nvtx_push(const char *name);
+void nvtx_pop();
+int sm_count();   // multiprocessors of the current device (grids are sized in multiples of it)
 
 }  // namespace apdx
 
@@ -187,9 +182,7 @@ struct apdx_plan {
   int64_t n_nodes = 0, n_dofs = 0, n_free = 0, nnz = 0, nnz_red = 0, n_coo = 0, n_res = 0;
   std::vector<apdx::SetData> sets;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;   // halo exchange overlapping the interior SpMV
   cudaEvent_t ev[4]{};
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   // fields
   apdx::DevBuf<double> coords, dofs_n;
@@ -276,5 +269,4 @@ int comm_halo_setup(apdx_plan *pl);
 int comm_halo_setup_lists(apdx_plan *pl);
 int p2p_setup(apdx_plan *pl);
 void p2p_teardown(apdx_plan *pl);
-bool p2p_is_heap_vector(const apdx_plan *pl, const double *v);
 }  // namespace apdx

@@ -93,7 +93,8 @@ static int comm_halo_exchange_lists(apdx_plan *pl, double *x_d, cudaStream_t s) 
   if (nn == 0) return APDX_OK;
   const int64_t n_send = H.send_ptr[nn];
   if (n_send > 0) {
-    const unsigned grid = (unsigned)((n_send + 255) / 256 < 1184 ? (n_send + 255) / 256 : 1184);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    const unsigned grid = (unsigned)((n_send + 255) / 256 < cap ? (n_send + 255) / 256 : cap);
     k_halo_pack<<<grid, 256, 0, s>>>(x_d, H.send_idx.p, n_send, H.sendbuf.p);
     pl->stats.kernel_launches += 1;
     APDX_CUDA(cudaGetLastError());
@@ -176,28 +177,20 @@ int comm_halo_setup(apdx_plan *pl) {
   cudaFree(buf);
   pl->send_lo = pl->rank_lo >= 0 ? h[4] : 0;  // lower neighbour's upper-ghost count
   pl->send_hi = pl->rank_hi >= 0 ? h[6] : 0;  // upper neighbour's lower-ghost count
-  pl->p2p.peer_lo_f1 = pl->rank_lo >= 0 ? h[5] : 0;
   APDX_REQUIRE(pl->send_lo <= pl->f1 - pl->f0 && pl->send_hi <= pl->f1 - pl->f0, APDX_ERR_INVALID,
                "neighbour ghosts more dofs than this rank owns");
   return APDX_OK;
 }
 
-// ---- peer-to-peer heap: CUDA IPC mapping of every rank's mailbox / flag / Krylov-vector block -----------------
+// ---- peer memory: CUDA IPC mapping of every rank's mailbox / flag block ----------------------------------------
 constexpr size_t P2P_HDR = 4096;
 static inline double *hdr_mbox(void *base) { return reinterpret_cast<double *>(base); }
 static inline int *hdr_mflag(void *base) { return reinterpret_cast<int *>(static_cast<char *>(base) + 2 * P2P_MAX_RANKS * 4 * sizeof(double)); }
-static inline int *hdr_hflag(void *base) { return hdr_mflag(base) + 2 * P2P_MAX_RANKS; }
-static inline int *hdr_err(void *base) { return hdr_hflag(base) + 2; }
+static inline int *hdr_err(void *base) { return hdr_mflag(base) + 2 * P2P_MAX_RANKS; }
 static inline int *hdr_epoch(void *base) { return hdr_err(base) + 1; }
-static inline double *hdr_vec(void *base) { return reinterpret_cast<double *>(static_cast<char *>(base) + P2P_HDR); }
 
-bool p2p_is_heap_vector(const apdx_plan *pl, const double *v) {
-  const P2P &P = pl->p2p;
-  return P.enabled && v >= P.vec_base && v < P.vec_base + 3 * P.stride;
-}
-
-// A heap may still be mapped by the peers when its plan dies, so it is only parked here; apdx_comm_destroy
-// (a collective call) frees the parked heaps after a barrier.
+// A block may still be mapped by the peers when its plan dies, so it is only parked here; apdx_comm_destroy
+// (a collective call) frees the parked blocks after a barrier.
 static std::vector<P2P> g_parked;
 
 void p2p_teardown(apdx_plan *pl) {
@@ -217,30 +210,18 @@ static void p2p_free_parked() {
   g_parked.clear();
 }
 
+// APDX_COMM=mbox: dot-product all-reduces through peer-memory mailboxes (k_allreduce_mbox_apply, krylov.cu); the
+// default (nccl) uses ncclAllReduce.  Collective: every rank of the communicator must call it.
 int p2p_setup(apdx_plan *pl) {
   P2P &P = pl->p2p;
   const char *mode = getenv("APDX_COMM");
-  // APDX_COMM: mbox = dot-product all-reduces through peer-memory mailboxes, halo on NCCL; p2p | fused = opt-in A/B
-  // variants that also move the halo to peer stores; nccl / cg2 = NCCL only
-  // the peer-store halo variants assume slab neighbours (contiguous send ranges): list partitions stay on NCCL
-  const bool full = mode && (strcmp(mode, "p2p") == 0 || strcmp(mode, "fused") == 0) && !pl->hl.active;
   const bool mbox = mode && strcmp(mode, "mbox") == 0;
-  if (!full && !mbox) return APDX_OK;
+  if (!mbox) return APDX_OK;
   if (g_nccl.nranks > P2P_MAX_RANKS) return APDX_OK;
   p2p_teardown(pl);
   cudaStream_t s = pl->stream;
   const int me = g_nccl.rank, nr = g_nccl.nranks;
-  // common vector stride = max n_free over ranks (rounded up to 512 doubles)
-  double *dmax = nullptr;
-  APDX_CUDA(cudaMalloc((void **)&dmax, sizeof(double)));
-  double nf = (double)((pl->n_free + 511) / 512 * 512);
-  APDX_CUDA(cudaMemcpy(dmax, &nf, sizeof(double), cudaMemcpyHostToDevice));
-  APDX_NCCL(g_nccl.AllReduce(dmax, dmax, 1, ncclFloat64, ncclMax, g_nccl.comm, s));
-  APDX_CUDA(cudaStreamSynchronize(s));
-  APDX_CUDA(cudaMemcpy(&nf, dmax, sizeof(double), cudaMemcpyDeviceToHost));
-  cudaFree(dmax);
-  P.stride = full ? (int64_t)nf : 0;   // mbox mode: header only
-  P.heap_bytes = P2P_HDR + 3 * (size_t)P.stride * sizeof(double);
+  P.heap_bytes = P2P_HDR;
   APDX_CUDA(cudaMalloc((void **)&P.heap, P.heap_bytes));
   APDX_CUDA(cudaMemset(P.heap, 0, P.heap_bytes));
   // exchange IPC handles
@@ -284,23 +265,15 @@ int p2p_setup(apdx_plan *pl) {
     P = P2P();
     return APDX_OK;
   }
-  P.vec_base = hdr_vec(P.heap);
   P.err_d = hdr_err(P.heap);
-  if (pl->rank_lo >= 0) { P.peer_vec[0] = hdr_vec(P.peer_base[pl->rank_lo]); P.peer_hflag[0] = hdr_hflag(P.peer_base[pl->rank_lo]) + 1; }
-  if (pl->rank_hi >= 0) { P.peer_vec[1] = hdr_vec(P.peer_base[pl->rank_hi]); P.peer_hflag[1] = hdr_hflag(P.peer_base[pl->rank_hi]) + 0; }
   P2PDev d{};
-  d.rank = me; d.nranks = nr; d.has_lo = pl->rank_lo >= 0; d.has_hi = pl->rank_hi >= 0;
+  d.rank = me; d.nranks = nr;
   for (int r = 0; r < nr; ++r) { d.mbox[r] = hdr_mbox(P.peer_base[r]); d.mflag[r] = hdr_mflag(P.peer_base[r]); }
-  d.hflag_self = hdr_hflag(P.heap);
   d.err = P.err_d;
   d.epoch_self = hdr_epoch(P.heap);
   APDX_CUDA(cudaMalloc((void **)&P.dev, sizeof(P2PDev)));
   APDX_CUDA(cudaMemcpy(P.dev, &d, sizeof(P2PDev), cudaMemcpyHostToDevice));
-  P.red_epoch = 0;
-  P.halo_epoch = 0;
-  P.enabled = full;
-  P.mbox = mbox;
-  if (getenv("APDX_VERBOSE")) fprintf(stderr, "[apdx_b200] rank %d: peer-to-peer Krylov loop enabled (heap %.1f MB, stride %lld)\n", me, P.heap_bytes / 1e6, (long long)P.stride);
+  P.mbox = true;
   return APDX_OK;
 }
 
@@ -347,7 +320,7 @@ int apdx_comm_destroy(void) {
   if (g_nccl.comm) {
     drop_all_krylov_graphs();   // captured graphs hold NCCL operations of this communicator
     cudaDeviceSynchronize();
-    if (!g_parked.empty()) {  // barrier: no rank may still be storing into a heap that is about to be freed
+    if (g_nccl.nranks > 1) {  // barrier on EVERY rank (parked state may differ): no rank may still be storing into a block that is about to be freed
       double *b = nullptr;
       APDX_CUDA(cudaMalloc((void **)&b, sizeof(double)));
       APDX_CUDA(cudaMemset(b, 0, sizeof(double)));

@@ -364,7 +364,7 @@ static int launch_one(apdx_plan *pl, SetData &st, const ElemArgs &args_in) {
   args.epb = epb;
   APDX_CUDA(cudaFuncSetAttribute(k_elements<DIM, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = (st.d.n_rows + epb - 1) / epb;
-  int64_t cap = 148ll * 16;
+  int64_t cap = (int64_t)sm_count() * 16;
   unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
   k_elements<DIM, NF><<<grid, 256, smem, pl->stream>>>(args);
   pl->stats.kernel_launches += 1;

@@ -138,14 +138,9 @@ static int launch_fast(apdx_plan *pl, SetData &st, const ElemArgs &a) {
   for (int i = 0; i < NGP * NEN; ++i) F.tab.N[i] = st.h_shape_n[i];
   for (int i = 0; i < NGP * NEN * DIM; ++i) F.tab.dN[i] = st.h_shape_dn[i];
   for (int i = 0; i < NGP; ++i) F.tab.w[i] = st.h_gp_w[i];
-  // APDX_ELEM_BLOCK=32|64 (measurement aid): smaller blocks at the same 8 warps per SM, so that the gather, FMA and
-  // store phases of the resident blocks are staggered instead of two blocks of four warps moving in step
-  static int block = 0;
-  if (!block) {
-    const char *e = getenv("APDX_ELEM_BLOCK");
-    const int b = e ? atoi(e) : 0;
-    block = (b == 32 || b == 64) ? b : FAST_BLOCK;
-  }
+  // (blocks of 32 / 64 threads at the same 8 warps per SM were measured in round 2: 13.37 / 13.38 / 13.38 ms per
+  // apdx_assemble pass at P256, profiles/r02a_asm_elem_block_128_32_64.jsonl -- no difference, removed)
+  const int block = FAST_BLOCK;
   const unsigned grid = (unsigned)((a.n_rows + block - 1) / block);
   if (a.want_tangent) k_elem_scalar_reg<DIM, NEN, NGP, true><<<grid, block, 0, pl->stream>>>(F);
   else k_elem_scalar_reg<DIM, NEN, NGP, false><<<grid, block, 0, pl->stream>>>(F);

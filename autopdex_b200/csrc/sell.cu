@@ -418,28 +418,6 @@ int sell_build(apdx_plan *pl) {
     APDX_CUDA(cudaMemcpy(&nm, n_mir.p, sizeof(nm), cudaMemcpyDeviceToHost));
     S.n_mirrored = (int64_t)nm;
   }
-  {  // leading / trailing runs of slices that touch ghost columns; everything in between is "interior"
-    std::vector<uint8_t> gh((size_t)ns);
-    APDX_CUDA(cudaMemcpy(gh.data(), ghost.p, (size_t)ns, cudaMemcpyDeviceToHost));
-    int64_t first_clean = 0, last_clean = ns;
-    while (first_clean < ns && gh[first_clean]) ++first_clean;
-    while (last_clean > first_clean && gh[last_clean - 1]) --last_clean;
-    bool clean = true;
-    for (int64_t q = first_clean; q < last_clean; ++q) clean = clean && !gh[q];
-    // pad the runs a little so that flagged slices scattered just behind the ghost planes stay in the boundary part
-    if (!clean) {
-      int64_t lo = first_clean, hi = last_clean;
-      for (int64_t q = first_clean; q < last_clean; ++q)
-        if (gh[q]) { if (q < ns / 2) lo = q + 1; else { hi = q; break; } }
-      first_clean = lo;
-      last_clean = hi > lo ? hi : lo;
-      clean = true;
-      for (int64_t q = first_clean; q < last_clean; ++q) clean = clean && !gh[q];
-      if (!clean) { first_clean = ns; last_clean = ns; }   // irregular partition: no overlap, one launch
-    }
-    S.lo_end = first_clean;
-    S.hi_begin = last_clean;
-  }
   if (S.n_val > 0) {  // compose the gather lists of the scatter; the position -> CSR entry map is not needed afterwards
     const unsigned g = (unsigned)((S.n_val + 1 + 255) / 256);
     APDX_CHECK(S.gl_ptr.alloc(S.n_val + 1));

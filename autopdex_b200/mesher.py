@@ -138,6 +138,29 @@ def slab_partition(n_elements, rank, nranks):
                 rank_hi=rank + 1 if rank < nranks - 1 else -1, per_plane=per_plane)
 
 
+def slab_partition_mesh(coords, connectivity, n_elements, rank, nranks):
+    """Slab `rank` of an already generated structured mesh with any number of element sets (domain and surface sets,
+    scalar or vector problems): the local mesh keeps the node planes [plane_lo, plane_hi) of slab_partition in global
+    order (local id = global id - node_lo) and every element of every set that touches an owned node.  Returns the
+    same keys as rcb_partition (nodes, n_owned, elements, element_ids, 'b200 partition')."""
+    part = slab_partition(n_elements, rank, nranks)
+    lo, hi = part["node_lo"], part["node_hi"]
+    olo, ohi = part["owned_node_lo"], part["owned_node_hi"]
+    nodes = np.arange(lo, hi, dtype=np.int64)
+    elements, element_ids = [], []
+    for c in connectivity:
+        c = np.asarray(c)
+        rows = np.flatnonzero(((c >= olo) & (c < ohi)).any(axis=1))
+        loc = c[rows]
+        if loc.size and (loc.min() < lo or loc.max() >= hi):
+            raise ValueError("slab_partition_mesh: an element spans more than two adjacent node planes")
+        elements.append(loc - lo)
+        element_ids.append(rows)
+    bp = dict(owned_node_begin=olo - lo, owned_node_end=ohi - lo, rank_lo=part["rank_lo"], rank_hi=part["rank_hi"])
+    return {"nodes": nodes, "n_owned": int(ohi - olo), "elements": elements, "element_ids": element_ids,
+            "slab": part, "b200 partition": bp}
+
+
 # ---- general partition: recursive coordinate bisection (north_star: "slab/RCB partitions"; SURVEY.md 8e) -------------
 def rcb_owner(coords, nranks):
     """Recursive coordinate bisection of the NODES: owner[n] in [0, nranks).  Every cut is perpendicular to the longest

@@ -191,6 +191,11 @@ int apdx_tangent_solve(apdx_plan *plan, const apdx_krylov_opts *opts, const doub
  * out[3]=krylov iterations out[4]=spmv launches out[5]=total out[6]=kernel launches
  * out[7]=bytes of the sliced-ELL matrix the SpMV streams (values + compressed indices)    */
 int apdx_plan_stats(const apdx_plan *plan, double out[8]);
+/* outcome of the plan's LAST Krylov solve (inside apdx_newton: of the last Newton step): relative residual
+ * ||b - A x|| / ||b|| of the recurrence and whether the stopping rule of jax.scipy.sparse.linalg.cg / bicgstab
+ * (||r|| <= max(rtol ||b||, atol), solver.py:1116-1126) was met -- 0 when the loop ended on maxiter or broke down.
+ * The reference's jax solvers return info = None (no signal at all); the host layer warns. */
+int apdx_plan_last_krylov(const apdx_plan *plan, double *relres, int32_t *converged);
 
 /* layout of the sliced-ELL copy of the reduced matrix (built by the first assembly that needs it):
  * out[0]=slices out[1]=stored values (incl. padding) out[2]=index ints (offsets, mirror tables, explicit columns)

@@ -1,10 +1,13 @@
 """Multi-GPU parity worker (launched by torchrun, one rank per GPU).
 
-    torchrun --nproc-per-node N tests/multi_gpu_worker.py [M] [cg|bicgstab] [slab|rcb]
+    torchrun --nproc-per-node N tests/multi_gpu_worker.py [poisson|neohooke] [M] [cg|bicgstab] [slab|rcb]
 
-Every rank assembles and solves its slab (or its recursive-coordinate-bisection part) of the M^3 hex8 Poisson problem
-through the public API (settings['b200 partition']); the owned parts are summed into a global vector with the library's
-host all-reduce and compared on rank 0 with the oracle ('scipy'/'lapack' reference path) on the whole mesh.
+poisson   M^3 hex8 Poisson problem, nf = 1 (BASELINE config 4 family)
+neohooke  M^3 hex8 neo-Hooke brick clamped at x = 0 with a traction face at x = 1, nf = 3, a domain and a surface set
+          (BASELINE config 5 family)
+Every rank assembles and solves its slab (or its recursive-coordinate-bisection part) through the public API
+(settings['b200 partition']); the owned parts are summed into a global vector with the library's host all-reduce and
+compared on rank 0 with the oracle ('scipy'/'lapack' reference path) on the whole mesh.
 Exit code 0 = parity within 1e-8 relative L2 and equal Newton step counts.
 """
 import os
@@ -16,11 +19,34 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def neohooke_api_problem(p):
+    """settings / static_settings of the public API for problems.neo_hooke_brick (global mesh)."""
+    from autopdex_b200 import models, seeder, spaces
+    dom, sur = p["sets"]
+    t = np.asarray(sur["model"]["traction"], dtype=np.float64)
+    Em, nu = dom["model"]["youngs_modulus"], dom["model"]["poisson_ratio"]
+    weak = models.hyperelastic_steady_state_weak(models.neo_hooke, lambda x, s: Em, lambda x, s: nu, "3d")
+    el = models.isoparametric_domain_element_galerkin(weak, spaces.fem_iso_line_quad_brick, *seeder.gauss_legendre_nd(3, 2))
+    tr = models.neumann_weak(lambda x, s: t)
+    sf = models.isoparametric_surface_element_galerkin(tr, spaces.fem_iso_line_quad_brick, *seeder.gauss_legendre_nd(2, 2),
+                                                       tangent_contributions=False)
+    static_settings = {"assembling mode": ("user element", "user element"), "solution structure": ("nodal imposition",) * 2,
+                       "model": (el, sf), "solver type": "newton", "solver backend": "b200", "solver": "bicgstab",
+                       "type of preconditioner": "jacobi", "verbose": -1}
+    return static_settings
+
+
 def main():
     import bench
-    from autopdex_b200 import backend, solver
-    m = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    krylov = sys.argv[2] if len(sys.argv) > 2 else "cg"
+    from autopdex_b200 import backend, mesher, solver
+    from tests import problems
+    argv = sys.argv[1:]
+    problem = "poisson"
+    if argv and not argv[0].isdigit():
+        problem, argv = argv[0], argv[1:]
+    m = int(argv[0]) if len(argv) > 0 else 20
+    krylov = argv[1] if len(argv) > 1 else "cg"
+    partition = argv[2] if len(argv) > 2 else "slab"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     backend.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     from torch.distributed import TCPStore
@@ -29,44 +55,47 @@ def main():
     if rank == 0:
         store.set("id", backend.comm_unique_id())
     backend.comm_init(bytes(store.get("id")), rank, world)
-    partition = sys.argv[3] if len(sys.argv) > 3 else "slab"
-    from autopdex_b200 import mesher
-    if partition == "rcb":
-        # general partition: recursive coordinate bisection of the whole mesh, halo through neighbour lists
-        # (apdx_plan_set_partition_lists); every rank builds the global mesh and keeps its part
-        from tests import problems
-        pg = problems.poisson_hex(m)
-        _, static_settings, _ = bench.build_problem(2, 0, 1)
-        pt = mesher.rcb_partition(pg["coords"], (pg["sets"][0]["conn"],), rank, world)
-        nodes = pt["nodes"]
-        settings = {"connectivity": (pt["elements"][0].astype(np.int32),), "node coordinates": pg["coords"][nodes],
-                    "dirichlet dofs": pg["mask"][nodes], "dirichlet conditions": np.zeros((nodes.size, 1)),
-                    "b200 partition": pt["b200 partition"]}
-    else:
+
+    pg = problems.poisson_hex(m) if problem == "poisson" else problems.neo_hooke_brick(m)
+    nf = pg["nf"]
+    conns = tuple(s["conn"] for s in pg["sets"])
+    if problem == "poisson" and partition == "slab":
+        # the bench's memory-lean slab construction (never materialises the global mesh)
         settings, static_settings, _ = bench.build_problem(m, rank, world)
+        sp = mesher.slab_partition((m, m, m), rank, world)
+        nodes = np.arange(sp["node_lo"], sp["node_hi"])
+    else:
+        if partition == "rcb":
+            pt = mesher.rcb_partition(pg["coords"], conns, rank, world)
+        else:
+            pt = mesher.slab_partition_mesh(pg["coords"], conns, (m, m, m), rank, world)
+        nodes = pt["nodes"]
+        if problem == "poisson":
+            _, static_settings, _ = bench.build_problem(2, 0, 1)
+        else:
+            static_settings = neohooke_api_problem(pg)
+        settings = {"connectivity": tuple(e.astype(np.int32) for e in pt["elements"]), "node coordinates": pg["coords"][nodes],
+                    "dirichlet dofs": pg["mask"][nodes], "dirichlet conditions": np.zeros((nodes.size, nf)),
+                    "b200 partition": pt["b200 partition"]}
     static_settings = dict(static_settings, solver=krylov)
     n_local = settings["node coordinates"].shape[0]
-    sol, (steps, res, div) = solver.solver(np.zeros((n_local, 1)), settings, static_settings, tol=1e-12)
+    sol, (steps, res, div) = solver.solver(np.zeros((n_local, nf)), settings, static_settings, tol=1e-12)
+    st = dict(solver.last_stats)
     part = settings["b200 partition"]
-    glob = np.zeros((m + 1) ** 3)
+    glob = np.zeros((pg["coords"].shape[0], nf))
     own = slice(part["owned_node_begin"], part["owned_node_end"])
-    if partition == "rcb":
-        glob[nodes[own]] = sol[own, 0]
-    else:
-        sp = mesher.slab_partition((m, m, m), rank, world)
-        glob[sp["owned_node_lo"]:sp["owned_node_hi"]] = sol[own, 0]
-    glob = backend.comm_allreduce_host(glob)
+    glob[nodes[own]] = np.asarray(sol).reshape(n_local, nf)[own]
+    glob = backend.comm_allreduce_host(glob.ravel()).reshape(glob.shape)
     ok = True
     if rank == 0:
         from oracle import solve as osolve
-        from tests import problems
-        p = problems.poisson_hex(m)
-        prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
-        ref, (rsteps, _, rdiv) = osolve.damped_newton(prob, np.zeros(p["mask"].shape))
-        err = np.linalg.norm(glob - ref.ravel()) / np.linalg.norm(ref)
+        prob = osolve.Problem(pg["sets"], pg["coords"], pg["mask"], pg["values"])
+        ref, (rsteps, _, rdiv) = osolve.damped_newton(prob, np.zeros(pg["mask"].shape))
+        err = np.linalg.norm(glob.ravel() - ref.ravel()) / np.linalg.norm(ref)
         ok = err < 1e-8 and steps == rsteps and div == rdiv
-        print("multi-gpu parity: ranks=%d m=%d %s %s steps=%d/%d res=%.2e rel-L2=%.2e -> %s"
-              % (world, m, krylov, partition, steps, rsteps, res, err, "OK" if ok else "FAIL"))
+        print("multi-gpu parity: ranks=%d %s m=%d nf=%d %s %s steps=%d/%d res=%.2e krylov_iters=%d rel-L2=%.2e -> %s"
+              % (world, problem, m, nf, krylov, partition, steps, rsteps, res, int(st["krylov_iters"]), err,
+                 "OK" if ok else "FAIL"), flush=True)
     solver.clear_plan_cache()
     backend.comm_destroy()
     sys.exit(0 if ok else 1)

@@ -135,6 +135,22 @@ def test_callable_evaluation_reference_vs_physical_points():
         solver._eval_points(g, pts, {}, 1, vectorized=True)
 
 
+def test_callables_that_reduce_over_the_point_axis_are_evaluated_per_point():
+    """The reference calls coefficient callables per point: a callable that reduces over the batch axis (prod / sum /
+    norm) or indexes it must not be taken for a constant or a point-wise batch result."""
+    pts = np.random.default_rng(2).uniform(0.1, 0.9, (200, 2))
+    for f in (lambda x: np.prod(np.sin(np.pi * x)), lambda x: np.sum(x * x), lambda x: np.linalg.norm(x)):
+        v = solver._eval_points(f, pts, {}, 1)
+        assert v.shape == (200,) and np.allclose(v, [f(p) for p in pts], rtol=1e-14)
+    h = lambda x: x[0] * np.array([1.0, 0.0])          # dim == ncomp: batch call returns the value at point 0, shape (2,)
+    v = solver._eval_points(h, pts, {}, 2)
+    assert v.shape == (200, 2) and np.allclose(v, [h(p) for p in pts])
+    k = lambda x: np.cumsum(np.atleast_2d(x), axis=0)[..., 0].squeeze() if np.ndim(x) > 1 else x[0]   # position-dependent
+    v = solver._eval_points(k, pts, {}, 1)
+    assert np.allclose(v, pts[:, 0])
+    assert solver._eval_points(lambda x, s: np.array([0.0, s["q"]]), pts, {"q": 3.0}, 2).shape == (2,)   # true constant
+
+
 # ---- host restatements agree with the oracle's independent ones -------------------------------------
 @pytest.mark.parametrize("family,dim,nen,name", [
     ("quad_brick", 1, 2, "line2"), ("quad_brick", 1, 3, "line3"), ("quad_brick", 2, 4, "quad4"),

@@ -187,24 +187,3 @@ def test_mirrored_storage_on_an_owned_row_range(nf_case):
     ref = (red @ x)[rng_s[0]:rng_s[1]]
     assert np.abs(ys - ref).max() < 1e-12 * np.abs(ref).max()
     assert np.abs(yf - ref).max() < 1e-12 * np.abs(ref).max()
-
-
-@pytest.mark.skipif(os.environ.get("APDX_TEST_EXPERIMENTAL") != "1",
-                    reason="opt-in kernel variants written without access to a GPU: run with APDX_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("model,n", [("poisson", 20), ("neohooke", 9), ("linel", 7)])
-def test_spmv_occupancy_variants_are_bit_identical(model, n):
-    """APDX_SPMV_BPS = 3 / 4 select SpMV kernels compiled for more resident warps with shallower load batches,
-    APDX_SPMV_PIPE = 1 one that requests the next slice's first value batch early; the order of the FMAs is unchanged,
-    so y = A x must agree with the default kernel bit for bit (both storage modes)."""
-    import json
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "time_spmv.py"), "all", model, str(n), "3"],
-                         capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr
-    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
-    assert len(lines) == 8, out.stdout + out.stderr
-    for sym in ("1", "0"):
-        sums = {(l["spmv_bps"], l["spmv_pipe"]): l["y_sha1"] for l in lines if l["sell_sym"] == sym}
-        assert set(sums) == {("2", "0"), ("3", "0"), ("4", "0"), ("2", "1")} and len(set(sums.values())) == 1, (sym, sums)

@@ -1,10 +1,8 @@
 #!/usr/bin/env python
-"""Time the sliced-ELL SpMV of a 3-D problem with symmetric (mirrored) storage on or off (APDX_SELL_SYM) and with the
-kernel compiled for 2 (default), 3 or 4 resident blocks per SM (APDX_SPMV_BPS) or with the pipelined value prefetch
-(APDX_SPMV_PIPE=1), and print a checksum of y = A x for a
-fixed x (the variants must agree bit for bit within one storage mode).
-   APDX_SELL_SYM=0 APDX_SPMV_BPS=3 python tools/time_spmv.py poisson|neohooke|linel N [reps]
-   python tools/time_spmv.py all poisson N [reps]     # every variant in its own process, one JSON line each"""
+"""Time the sliced-ELL SpMV of a 3-D problem with symmetric (mirrored) storage on or off (APDX_SELL_SYM) and print a
+checksum of y = A x for a fixed x.
+   APDX_SELL_SYM=0 python tools/time_spmv.py poisson|neohooke|linel N [reps]
+   python tools/time_spmv.py all poisson N [reps]     # both storage modes, each in its own process, one JSON line each"""
 import hashlib
 import json
 import os
@@ -15,10 +13,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-# (APDX_SELL_SYM: mirrored storage on / off, APDX_SPMV_BPS: occupancy variant of the kernel)
-# APDX_SPMV_PIPE=1 (with BPS 2): first value batch of the next slice requested during the mirrored phase
-VARIANTS = [("1", "2", "0"), ("0", "2", "0"), ("1", "3", "0"), ("1", "4", "0"), ("1", "2", "1"), ("0", "3", "0"),
-            ("0", "4", "0"), ("0", "2", "1")]
+VARIANTS = ["1", "0"]   # APDX_SELL_SYM: mirrored storage on / off
 CUBE = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
 
 
@@ -51,15 +46,15 @@ def main(model, n, reps):
     ms = plan.time_spmv(reps)
     alg = nnz * 12 + n_free * 16 + (n_free + 1) * 4
     impl = plan.stats().get("sell_bytes", 0.0) + n_free * 16
-    print(json.dumps({"sell_sym": os.environ.get("APDX_SELL_SYM", "default"), "spmv_bps": os.environ.get("APDX_SPMV_BPS", "2"), "spmv_pipe": os.environ.get("APDX_SPMV_PIPE", "0"), "sell": plan.sell_info(), "model": model, "n": n, "n_free": n_free,
+    print(json.dumps({"sell_sym": os.environ.get("APDX_SELL_SYM", "default"), "sell": plan.sell_info(), "model": model, "n": n, "n_free": n_free,
                       "nnz": nnz, "ms": ms, "algorithmic_gbs": alg / ms * 1e-6, "implementation_gbs": impl / ms * 1e-6,
                       "y_sha1": hashlib.sha1(yh.tobytes()).hexdigest()[:16], "y_sum": float(yh.sum())}))
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "all":
-        for sym, bps, pipe in VARIANTS:
-            env = dict(os.environ, APDX_SELL_SYM=sym, APDX_SPMV_BPS=bps, APDX_SPMV_PIPE=pipe)
+        for sym in VARIANTS:
+            env = dict(os.environ, APDX_SELL_SYM=sym)
             subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[2:], env=env, check=False)
     else:
         main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 50)
