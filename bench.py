@@ -31,7 +31,8 @@ sys.path.insert(0, ROOT)
 
 UNIT_CUBE = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_spmv_sell<1> launch from `ncu --set full` (profiles/), by mesh size
-NCU_TRAFFIC = {256: 2.2391e9}     # profiles/r01f_k_spmv_sell_sym_p256_full.txt: 2.106 GB read + 0.133 GB written
+NCU_TRAFFIC = {256: 2.2265e9}     # 2.0938 GB read + 0.1327 GB written
+NCU_TRAFFIC_SOURCE = "profiles/r02a_k_spmv_sell_p256_full.txt"
 # SASS count of k_elem_scalar_reg<3,8,8,true>: 2592 DFMA + 368 DMUL + 316 DADD per element
 HEX8_POISSON_FLOP = 2 * 2592 + 368 + 316
 METRIC = "elements/s through one Newton step (sparse assembly + Jacobi-PCG to 1e-8)"
@@ -137,70 +138,170 @@ def build_problem(m, rank, nranks):
 
 
 # ---- CPU reference path (oracle + the reference's SciPy calls) --------------------------------------------------
-def cpu_reference_step(m, solver="lapack"):
-    """One Newton step of the same problem on an m^3 sample with the reference 'scipy' backend semantics.
-    Returns (seconds, elements, breakdown dict)."""
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_step(m, solver="cg", rtol=1e-8, threads=None):
+    """One Newton step of the same problem on an m^3 sample, reference loop semantics (solver.py:872-937) on the CPU:
+    B-asm (NumPy restatement of the JAX assembly, element chunks on `threads` threads), B-dup (the reference's own SciPy
+    calls), then B-cg = SciPy cg with the Jacobi preconditioner to the GPU arm's tolerance (solver='cg', the CPU analogue
+    of solver.linear_solve_jax, solver.py:1093-1126) or B-direct = spsolve (solver='lapack', solver.py:1520), the update
+    and the second residual assembly + norm.  Returns (seconds, elements, breakdown dict)."""
     from oracle import assemble as oasm
     from oracle import solve as osolve
     from tests import problems
+    threads = threads or host_threads()
     p = problems.poisson_hex(m)
     prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+    prob.threads = threads
+    rows, cols = prob.coo()                                                     # index arrays: built once per mesh
+    free = ~p["mask"].ravel()
     dofs = np.zeros(p["mask"].shape)
     t0, c0 = time.perf_counter(), time.process_time()
     dofs[p["mask"]] = p["values"][p["mask"]]
-    R, data = oasm.assemble(p["sets"], p["coords"], dofs, {})                  # B-asm (restated JAX half)
+    R, data = oasm.assemble(p["sets"], p["coords"], dofs, {}, threads=threads)  # B-asm (restated JAX half)
     t1 = time.perf_counter()
-    rows, cols = prob.coo()
-    free = ~p["mask"].ravel()
     csr = oasm.scipy_assembling(data, rows, cols, dofs.size, free)             # B-dup (reference's own SciPy calls)
     t2 = time.perf_counter()
     import scipy.sparse.linalg as spla
     b = -R[free]
+    iters = [0]
     if solver == "lapack":
         x = spla.spsolve(csr, b)                                               # B-direct (SuperLU, solver.py:1520)
     else:
         d = csr.diagonal()
-        x, _ = spla.cg(csr, b, M=spla.LinearOperator(csr.shape, matvec=lambda v: v / d), rtol=1e-8, atol=0.0)
+
+        def count(_):
+            iters[0] += 1
+        x, _ = spla.cg(csr, b, M=spla.LinearOperator(csr.shape, matvec=lambda v: v / d), rtol=rtol, atol=0.0,
+                       callback=count)                                         # B-cg
     t3 = time.perf_counter()
     dofs.ravel()[free] += x
     R2 = prob.residual(dofs)                                                   # 2nd residual assembly of the step
-    np.linalg.norm(R2[free])
+    rn = float(np.linalg.norm(R2[free]))
     t4 = time.perf_counter()
     n_el = p["sets"][0]["conn"].shape[0]
-    # threads actually busy: process CPU time (all threads) over wall time; SuperLU and the einsum assembly are serial
-    busy = (time.process_time() - c0) / max(t4 - t0, 1e-9)
+    busy = (time.process_time() - c0) / max(t4 - t0, 1e-9)   # threads busy on average: process CPU time / wall time
     return t4 - t0, n_el, {"assembly_s": t1 - t0, "dup_sum_s": t2 - t1, "solve_s": t3 - t2, "residual_s": t4 - t3,
+                           "krylov_iterations": iters[0], "res_norm": rn, "nnz_reduced": int(csr.nnz),
                            "threads_busy": busy}
+
+
+REF_SIZES = (128, 112, 96, 80, 64, 48, 32)
+
+
+def pick_ref_size(n_steps, budget_s, cap, threads):
+    """Largest sample size whose n_steps Newton steps fit budget_s, predicted from one calibration step at 32^3:
+    assembly, duplicate summing and the residual scale with the elements, Jacobi-PCG with elements^(4/3)."""
+    dt, n_el, br = cpu_reference_step(32, "cg", threads=threads)
+    lin = br["assembly_s"] + br["dup_sum_s"] + br["residual_s"]
+    for m in REF_SIZES:
+        if m > cap:
+            continue
+        f = (m / 32.0) ** 3
+        est = lin * f + br["solve_s"] * f ** (4.0 / 3.0)
+        if est * n_steps <= budget_s or m == REF_SIZES[-1]:
+            return m, est
+    return 32, dt
+
+
+def cpu_sample_note(m, size, n_el):
+    return ("%d^3 hex8 Poisson sample (%d elements) of the %d^3 workload, one Newton step with the GPU arm's solver: NumPy "
+            "restatement of the JAX assembly (oracle/, element chunks on all host threads) + the reference's scipy "
+            "coo->csr->[:,free][free] + SciPy cg with Jacobi M to rtol 1e-8 + update + residual; the full 256^3 step does "
+            "not fit the host (25.8 GB of COO before SciPy's copies, BASELINE.md section 4) nor the time bound"
+            % (m, n_el, size))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    m = args.ref_size
-    times = []
-    for i in range(args.warmup + args.steps):
-        dt, n_el, br = cpu_reference_step(m, "lapack")
+    threads = host_threads()
+    n_steps = args.warmup + args.steps
+    m, est = pick_ref_size(n_steps, args.ref_budget_s, args.ref_size, threads)
+    times, br = [], None
+    for i in range(n_steps):
+        dt, n_el, br_i = cpu_reference_step(m, "cg", args.rtol, threads)
         if i >= args.warmup:
             times.append(dt)
+            br = br_i if br is None or dt <= min(times) else br
     dt = float(np.mean(times))
-    cg_dt, _, cg_br = cpu_reference_step(m, "cg")
     value = n_el / dt
-    sample = ("%d^3 hex8 Poisson sample of the %d^3 workload (%d elements), reference 'scipy'/'lapack' path: "
-              "NumPy restatement of the JAX assembly + scipy coo->csr->[:,free][free] + spsolve" % (m, args.size, n_el))
+    direct = None
+    if args.ref_direct:    # B-direct at 32^3 (3-D SuperLU fill-in: minutes and tens of GB beyond 64^3)
+        d_dt, d_el, d_br = cpu_reference_step(32, "lapack", threads=threads)
+        direct = {"size": 32, "value": d_el / d_dt, "unit": UNIT, "breakdown_s": d_br,
+                  "note": "the reference's default 'scipy'/'lapack' backend (spsolve) on a 32^3 sample"}
     cores = max(1, int(round(br["threads_busy"])))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D Poisson Q1 hex %d^3 Newton step (sample %d^3 on CPU)" % (args.size, m)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "breakdown_s": br, "host_cores": os.cpu_count(),
-                             "threads_used": "cores = process CPU time / wall time of the step: NumPy/SciPy use BLAS threads "
-                                             "only, SuperLU (spsolve) is serial, as in the reference's 'scipy' backend",
-                             "jacobi_pcg_variant": {"value": n_el / cg_dt, "unit": UNIT, "breakdown_s": cg_br}},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "best_ms_per_step": min(times) * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.size, args.rtol, 1),
+                       "sample": "CPU arm times a %d^3 sample of it per step (largest of %s whose %d steps fit %d s on %d host "
+                                 "threads); same element, same solver (Jacobi-PCG, rtol %.0e), same Newton-step semantics; the "
+                                 "ratio of the two arms is therefore per element, not per 256^3 step (PCG iterations grow "
+                                 "with the mesh: %d here, 350 at 256^3)"
+                                 % (m, "/".join(str(v) for v in REF_SIZES), n_steps, args.ref_budget_s, threads, args.rtol,
+                                    br["krylov_iterations"])},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_note(m, args.size, n_el),
+                             "breakdown_s": br, "host_cores": os.cpu_count(), "threads_available": threads,
+                             "threads_used": "assembly: element chunks on %d threads; scipy coo->csr, cg (SpMV) are serial, as "
+                                             "in the reference's 'scipy' backend; cores = process CPU time / wall time" % threads,
+                             "direct_solve_variant": direct},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def workload_name(m, rtol, world):
+    return ("3D Poisson Q1 hex %d^3 (%d dofs), Newton + Jacobi-PCG rtol %.0e, slab-partitioned over %d GPU(s)"
+            % (m, (m + 1) ** 3, rtol, world))
+
+
+# ncu (profiles/r02a_k_elements_neohooke64_full.txt): k_elements<3,3> executes 2436 DFMA + 1386 DMUL + 791 DADD thread
+# instructions per elapsed cycle over 2.144 M cycles for 262 144 hex8 neo-Hooke elements = 57.7 kflop per element
+HEX8_NEOHOOKE_FLOP_EXECUTED = 57662.0
+
+
+def vector_problem_figures(args, hbm, fp64_peak, n=64):
+    """Bounded nf = 3 run (BASELINE config 5 family at n^3): hex8 neo-Hooke tangent pass (generic element kernel
+    k_elements<3,3> + deterministic scatter) and the nf = 3 sliced-ELL SpMV, both through the C ABI."""
+    from autopdex_b200 import backend, mesher, seeder
+    coords, elems = mesher.structured_mesh((n, n, n), UNIT_CUBE, "brick")
+    mask = np.repeat((np.abs(coords[:, 0]) < 1e-12)[:, None], 3, axis=1)
+    st = backend.SetSpec("domain", "neo_hooke", elems.astype(np.int32), family="quad_brick", gp=seeder.gauss_legendre_nd(3, 2),
+                         mode="3d", params={"youngs_modulus": 100.0, "poisson_ratio": 0.3})
+    plan = backend.Plan(3, coords.shape[0], 3, [st], mask)
+    plan.set_coords(coords)
+    rng = np.random.default_rng(0)
+    d = backend.DeviceArray.from_host(rng.uniform(-1e-3, 1e-3, mask.size))
+    r = backend.DeviceArray(mask.size)
+    tan = []
+    for i in range(5):
+        plan.assemble(d, True, r)
+        tan.append(plan.stats()["assembly_tangent_ms"])
+    tan_ms = float(np.mean(tan[2:]))
+    spmv_ms = plan.time_spmv(50)
+    rows, nnz = plan.f1 - plan.f0, plan.nnz_reduced
+    phys = plan.stats()["sell_bytes"] + rows * 24
+    n_el = elems.shape[0]
+    tfl = n_el * HEX8_NEOHOOKE_FLOP_EXECUTED / (tan_ms * 1e-3) / 1e12
+    out = {"workload": "3D neo-Hooke Q1 hex %d^3 (%d dofs), bounded sample of BASELINE config 5" % (n, mask.size),
+           "assembly": {"tangent_pass_ms": tan_ms, "elements_per_s": n_el / (tan_ms * 1e-3),
+                        "flop_per_element_executed": HEX8_NEOHOOKE_FLOP_EXECUTED, "tflops_fp64": tfl,
+                        "frac_of_fp64_peak": tfl / fp64_peak,
+                        "note": "whole apdx_assemble pass (element kernel + scatter into full CSR and sliced-ELL + residual); flops "
+                                "per element from ncu's sass_thread_inst_executed_op_d{fma,mul,add} of the element kernel"},
+           "spmv": {"ms_per_launch": spmv_ms, "bytes_per_launch": phys, "achieved_gbs": phys / (spmv_ms * 1e-3) / 1e9,
+                    "frac": phys / (spmv_ms * 1e-3) / 1e9 / hbm, "nnz_reduced": nnz, "n_free": plan.n_free,
+                    "algorithmic_gbs": (nnz * 12 + rows * 16 + (rows + 1) * 4) / (spmv_ms * 1e-3) / 1e9}}
+    plan.destroy()
+    return out
 
 
 # ---- own arm -----------------------------------------------------------------------------------------------------
@@ -282,18 +383,26 @@ def run_b200(args):
 
     nnz, nfree = plan.nnz_reduced, plan.n_free
     rows = plan.f1 - plan.f0
-    spmv_bytes = nnz * 12 + rows * 16 + (rows + 1) * 4            # per rank (local reduced system incl. ghost columns)
     hbm, which = peaks()
+    # SpMV roofline.  PHYSICAL bytes per launch = what the kernel streams from / to HBM: the sliced-ELL arrays (stored
+    # values, compressed indices, mirror tables, slice headers) + x read + y written + the dot-product operand read;
+    # cross-checked by ncu's dram__bytes (profiles/r02a_k_spmv_sell_p256_full.txt: 2.227 GB against 2.327 GB computed at
+    # 256^3 on one GPU).  The ALGORITHMIC figure of SURVEY.md 8d (CSR bytes nnz*12 + n*16 + (n+1)*4) is reported beside
+    # it: it exceeds the peak because symmetric storage + per-slice index compression stream fewer bytes than CSR.
+    spmv_alg_bytes = nnz * 12 + rows * 16 + (rows + 1) * 4
+    spmv_bytes = plan.stats()["sell_bytes"] + rows * 24
     spmv_gbs = spmv_bytes / (spmv_ms * 1e-3) / 1e9
-    impl_bytes = plan.stats()["sell_bytes"] + rows * 24     # what the sliced-ELL kernel streams: matrix + x + y + w
-    impl_gbs = impl_bytes / (spmv_ms * 1e-3) / 1e9
-    cg_iter_bytes = spmv_bytes + 72 * rows
+    spmv_alg_gbs = spmv_alg_bytes / (spmv_ms * 1e-3) / 1e9
     mean_iters = float(np.mean(iters))
+    # CG iteration: SpMV + the two vector kernels (k_cg_update: q r minv -> r; k_cg_p: p x r minv -> x p = 10 streams)
+    cg_iter_bytes = spmv_bytes + 80 * rows
     cg_gbs = cg_iter_bytes * mean_iters / (np.mean(kry_ms) * 1e-3) / 1e9
+    cg_alg_gbs = (spmv_alg_bytes + 72 * rows) * mean_iters / (np.mean(kry_ms) * 1e-3) / 1e9
     asm_elems = state.plan.sets[0].conn.shape[0]
     asm_gbs = asm_elems * 290.0 / (np.mean(asm_ms) * 1e-3) / 1e9
     fp64_peak = backend.measure_fp64_peak()                        # TFLOP/s, measured here (not in MEASURED_PEAKS.json)
     asm_tflops = asm_elems * HEX8_POISSON_FLOP / (np.mean(asm_ms) * 1e-3) / 1e12
+    vector = vector_problem_figures(args, hbm, fp64_peak) if (world == 1 and not args.no_vector) else None
 
     if rank != 0:
         return
@@ -301,8 +410,7 @@ def run_b200(args):
         "metric": METRIC, "value": total_elems / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D Poisson Q1 hex %d^3 (%d dofs), Newton + Jacobi-PCG rtol %.0e, slab-partitioned over %d GPU(s)"
-                               % (m, (m + 1) ** 3, args.rtol, world),
+        "config": {"workload": workload_name(m, args.rtol, world),
                    "l2": "inputs larger than L2 (reduced CSR %.2f GB per rank)" % (nnz * 12 / 1e9),
                    "parity_guard": {"newton_steps": info[0], "res_norm": info[1], "diverged": bool(info[2]), "ok": bool(ok),
                                     "solution_sum": sol_sum}},
@@ -311,15 +419,20 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
                 "plan_build_s_first_call": t_plan, "mesh_generation_s": t_mesh},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_spmv_sell<1> (sliced-ELL SpMV, compressed column indices, symmetric storage, fused p.Ap)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm,
-                     "unit": "GB/s", "frac": spmv_gbs / hbm, "frac_of_nominal_8TBs": spmv_gbs / 8000.0, "peak_source": which,
-                     "traffic": NCU_TRAFFIC.get(m) if world == 1 else None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
-                     "note": "achieved uses the ALGORITHMIC CSR bytes nnz*12+n*16+(n+1)*4 (SURVEY.md 8d); the kernel streams fewer "
-                             "bytes: column offsets are stored once per 64-row slice and, the tangent being symmetric, only the columns with "
-                             "offset >= 0 are stored -- the lower ones are read from their transposed position, which the L2 serves",
-                     "sell": plan.sell_info(),
-                     "implementation_bytes_per_launch": impl_bytes, "implementation_gbs": impl_gbs,
-                     "implementation_frac_of_peak": impl_gbs / hbm},
+        "roofline": {"kernel": "k_spmv_sell<1> (sliced-ELL SpMV, compressed column indices, symmetric storage, fused p.Ap)",
+                     "bound": "hbm", "achieved": spmv_gbs, "peak": hbm, "unit": "GB/s", "frac": spmv_gbs / hbm,
+                     "frac_of_nominal_8TBs": spmv_gbs / 8000.0, "peak_source": which,
+                     "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
+                     "traffic": NCU_TRAFFIC.get(m) if world == 1 else spmv_bytes,
+                     "traffic_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, " + NCU_TRAFFIC_SOURCE)
+                                       if (world == 1 and m in NCU_TRAFFIC) else
+                                       "computed from the plan's array sizes (no ncu capture at this rank count / size)",
+                     "note": "achieved = PHYSICAL bytes streamed per launch (sliced-ELL arrays + x + y + dot operand) / CUDA-event "
+                             "time: an HBM utilisation.  algorithmic_* uses the CSR bytes nnz*12+n*16+(n+1)*4 of SURVEY.md 8d, which "
+                             "the kernel does not move (symmetric storage: lower columns are read from their transposed position in "
+                             "the L2; column offsets stored once per 64-row slice)",
+                     "algorithmic_bytes_per_launch": spmv_alg_bytes, "algorithmic_gbs": spmv_alg_gbs,
+                     "algorithmic_frac": spmv_alg_gbs / hbm, "sell": plan.sell_info()},
         "newton_step_ms": ms,
         "assembly": {"elements_per_s": asm_elems / (np.mean(asm_ms) * 1e-3), "ms": float(np.mean(asm_ms)),
                      "residual_only_ms": float(np.mean(res_ms)), "algorithmic_gbs": asm_gbs,
@@ -328,17 +441,19 @@ def run_b200(args):
                      "frac_of_fp64_peak": asm_tflops / fp64_peak,
                      "note": "fused pass = element kernel (FP64-FMA bound) + deterministic segmented-reduction scatter (HBM bound)"},
         "cg": {"iterations": mean_iters, "ms_per_iteration": float(np.mean(kry_ms)) / max(mean_iters, 1),
-               "algorithmic_gbs": cg_gbs, "frac_of_hbm": cg_gbs / hbm, "krylov_ms": float(np.mean(kry_ms))},
+               "streamed_gbs": cg_gbs, "frac_of_hbm": cg_gbs / hbm, "algorithmic_gbs": cg_alg_gbs,
+               "algorithmic_frac": cg_alg_gbs / hbm, "krylov_ms": float(np.mean(kry_ms)),
+               "note": "streamed = SpMV physical bytes + 80 B/row of vector streams per iteration"},
+        "vector_problem": vector,
         "system": {"n_free": nfree, "nnz_reduced": nnz, "plan_device_gb": plan.device_bytes / 1e9},
     }
     if world == 1 and not args.no_cpu:
-        dt, n_el, br = cpu_reference_step(args.ref_size, "lapack")
+        threads = host_threads()
+        mref, _ = pick_ref_size(1, 25.0, args.ref_size, threads)
+        dt, n_el, br = cpu_reference_step(mref, "cg", args.rtol, threads)
         line["cpu_baseline"] = {"value": n_el / dt, "unit": UNIT, "cores": max(1, int(round(br["threads_busy"]))),
-                                "host_cores": os.cpu_count(), "kind": "port",
-                                "sample": "%d^3 hex8 Poisson Newton step, reference 'scipy'/'lapack' path restated "
-                                          "(NumPy assembly + SciPy duplicate summing + spsolve), %d elements, %.1f s"
-                                          % (args.ref_size, n_el, dt),
-                                "breakdown_s": br}
+                                "host_cores": os.cpu_count(), "threads_available": threads, "kind": "port",
+                                "sample": cpu_sample_note(mref, m, n_el) + " (%.1f s)" % dt, "breakdown_s": br}
     print(json.dumps(line))
 
 
@@ -354,7 +469,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=256, help="elements per direction (BASELINE: 256)")
-    ap.add_argument("--ref-size", type=int, default=32, help="elements per direction of the bounded CPU sample")
+    ap.add_argument("--ref-size", type=int, default=128, help="largest CPU sample (elements per direction)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="time bound of the whole --impl reference run")
+    ap.add_argument("--ref-direct", action="store_true", help="--impl reference: also time spsolve on a 32^3 sample")
+    ap.add_argument("--no-vector", action="store_true", help="skip the bounded 64^3 neo-Hooke figures")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nx", type=int, default=0, help="diagnostic: elements along the slowest index (default: --size)")

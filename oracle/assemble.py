@@ -30,15 +30,33 @@ def coo_indices(sets):
     return np.concatenate(rows), np.concatenate(cols)
 
 
-def assemble(sets, coords, dofs, settings, want_tangent=True):
-    """Global residual (n_dofs,) and COO tangent data in reference order (or None)."""
+def _set_contributions_chunked(st, coords, dofs, settings, want_tangent, threads, chunk=16384):
+    """set_contributions over row chunks on a thread pool (NumPy's einsum / matmul loops release the GIL): the same
+    arithmetic per element, so the results are bit-identical to the unchunked call."""
+    n = np.asarray(st["conn"]).shape[0]
+    per_row = any(isinstance(v, np.ndarray) and v.ndim >= 2 and v.shape[0] == n for v in st["model"].values())
+    if threads <= 1 or st["kind"] == "intpoint" or n <= chunk or per_row:
+        return elements.set_contributions(st, coords, dofs, settings, want_tangent)
+    from concurrent.futures import ThreadPoolExecutor
+    parts = [slice(a, min(a + chunk, n)) for a in range(0, n, chunk)]
+    with ThreadPoolExecutor(threads) as ex:
+        out = list(ex.map(lambda sl: elements.set_contributions(st, coords, dofs, settings, want_tangent, sl), parts))
+    Re = np.concatenate([o[0] for o in out])
+    Ke = None if out[0][1] is None else np.concatenate([o[1] for o in out])
+    return Re, Ke
+
+
+def assemble(sets, coords, dofs, settings, want_tangent=True, threads=1):
+    """Global residual (n_dofs,) and COO tangent data in reference order (or None).
+    threads > 1: element chunks on a thread pool (bench.py's CPU baseline; parameters must not be per-element arrays)."""
     dofs = np.asarray(dofs, dtype=np.float64)
     nf = dofs.shape[1]
     R = np.zeros(dofs.size)
     data = []
     for st in sets:
-        Re, Ke = elements.set_contributions(st, np.asarray(coords, float), dofs, settings)
-        np.add.at(R, global_dofs(st["conn"], nf).ravel(), Re.ravel())   # assembler.py:431
+        Re, Ke = _set_contributions_chunked(st, np.asarray(coords, float), dofs, settings, want_tangent, threads)
+        # assembler.py:431 (segment sum of the element vectors); bincount adds in the same ascending order as add.at
+        R += np.bincount(global_dofs(st["conn"], nf).ravel(), weights=Re.ravel(), minlength=R.size)
         if want_tangent:
             data.append(Ke.ravel())                                      # assembler.py:1383
     return R, (np.concatenate(data) if want_tangent else None)

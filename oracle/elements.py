@@ -115,8 +115,10 @@ def _bmatrix(G):
     return B.reshape(n, nv, nen * dim)
 
 
-def point_contribution(model, N, G, s, u, g, settings):
+def point_contribution(model, N, G, s, u, g, settings, want_tangent=True):
     """Residual/tangent contribution of one integration point for all rows.
+    want_tangent=False: the Poisson models skip the element matrix (K is returned as None), as the reference's
+    residual-only assembly does (assembler.py:587-637); the other models still form it.
 
     N (n, nen) shape values, G (n, nen, dim) physical gradients, s (n,) weight (signed
     w*detJ for domain elements, models.py:1691-1694), u (n, nen, nf) local dofs.
@@ -130,7 +132,11 @@ def point_contribution(model, N, G, s, u, g, settings):
         # weak:      -c grad(theta).grad(dtheta) + f dtheta (models.py:124-130)
         c = _par(model, "coefficient", n, g, 1.0)
         f = _par(model, "source", n, g, 0.0)
-        GG = np.einsum("nad,nbd->nab", G, G)
+        if not want_tangent:
+            gu = np.einsum("nad,na->nd", G, u[:, :, 0])
+            R = (s * c)[:, None] * np.einsum("nad,nd->na", G, gu) - (s * f)[:, None] * N
+            return (-R if name == "poisson_weak" else R), None
+        GG = np.matmul(G, np.swapaxes(G, 1, 2))
         K = (s * c)[:, None, None] * GG
         R = np.einsum("nab,nb->na", K, u[:, :, 0]) - (s * f)[:, None] * N
         if name == "poisson_weak":
@@ -184,10 +190,14 @@ def point_contribution(model, N, G, s, u, g, settings):
     return R, K
 
 
-def set_contributions(st, coords, dofs, settings):
+def set_contributions(st, coords, dofs, settings, want_tangent=True, rows=None):
     """Element (or integration-point) residuals and tangents of one set.
-    coords (n_nodes, dim), dofs (n_nodes, nf) -> Re (n_rows, ndof_e), Ke (n_rows, ndof_e, ndof_e)."""
+    coords (n_nodes, dim), dofs (n_nodes, nf) -> Re (n_rows, ndof_e), Ke (n_rows, ndof_e, ndof_e) (None if the model
+    skipped it, see point_contribution).  rows: slice of the set's rows (chunked / threaded assembly; only for sets whose
+    model parameters are scalars or per-Gauss-point tables)."""
     conn = np.asarray(st["conn"])
+    if rows is not None:
+        conn = conn[rows]
     n, nen = conn.shape
     nf = st["nf"]
     u = dofs[conn].reshape(n, nen, nf)
@@ -198,11 +208,12 @@ def set_contributions(st, coords, dofs, settings):
     if st["kind"] == "intpoint":
         # one row per integration point (assembler.py:874-924,978-1035); weights are
         # physical and positive (seeder.py:3473-3488), gradients are physical.
+        assert rows is None
         return point_contribution(model, st["N"], st["dNdx"], np.asarray(st["w"], float), u, 0, settings)
     X = coords[conn]                                    # (n, nen, dim)
     xi, w = st["gp"]
     Nt, dNt = shapes.shape_tables(st["etype"], xi)
-    Re, Ke = np.zeros((n, ndof)), np.zeros((n, ndof, ndof))
+    Re, Ke = np.zeros((n, ndof)), (np.zeros((n, ndof, ndof)) if want_tangent else None)
     for g in range(len(w)):
         Jm = np.einsum("nad,ak->ndk", X, dNt[g])        # dX_d / dxi_k
         Nn = np.broadcast_to(Nt[g], (n, nen))
@@ -217,9 +228,12 @@ def set_contributions(st, coords, dofs, settings):
                 scal = np.linalg.norm(np.cross(Jm[:, :, 0], Jm[:, :, 1]), axis=1)
             G = np.zeros((n, nen, X.shape[2]))
             s = w[g] * scal
-        r, k = point_contribution(model, Nn, G, s, u, g, settings)
+        r, k = point_contribution(model, Nn, G, s, u, g, settings, want_tangent)
         Re += r
-        Ke += k
+        if k is not None and Ke is not None:
+            Ke += k
+        elif Ke is not None:
+            Ke = None
     return Re, Ke
 
 

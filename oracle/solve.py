@@ -21,6 +21,7 @@ class Problem:
         self.values = np.asarray(dirichlet_values, dtype=np.float64)
         self.settings = dict(settings or {})
         self._coo = None
+        self.threads = 1        # bench.py's CPU baseline sets this (chunked element loops on a thread pool)
 
     def coo(self):
         if self._coo is None:
@@ -28,7 +29,7 @@ class Problem:
         return self._coo
 
     def residual(self, dofs):
-        return asm.assemble(self.sets, self.coords, dofs, self.settings, want_tangent=False)[0]
+        return asm.assemble(self.sets, self.coords, dofs, self.settings, want_tangent=False, threads=self.threads)[0]
 
 
 def linear_solve_scipy(prob, data, rhs, free, solver="lapack", krylov_tol=None):

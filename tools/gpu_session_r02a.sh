@@ -17,3 +17,6 @@ python tools/time_assembly.py neohooke 64 5 > $OUT/r02a_asm_neohooke64.txt 2>&1
 python tools/time_assembly.py neohooke 128 3 > $OUT/r02a_asm_neohooke128.txt 2>&1
 python tools/time_spmv.py all poisson 256 50 > $OUT/r02a_spmv_p256.txt 2>&1
 ls -la $OUT
+timeout 600 python bench.py --no-cpu > $OUT/r02a_bench_n1.json 2> $OUT/r02a_bench_n1.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/r02a_launches_p256.csv python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/r02a_bench_ncu.log 2>&1
+tail -3 $OUT/r02a_pytest_gpu.txt; cat $OUT/r02a_bench_n1.json
