@@ -36,26 +36,10 @@ def neohooke_api_problem(p):
     return static_settings
 
 
-def main():
+def run_case(problem, m, krylov, partition, rank, world):
     import bench
     from autopdex_b200 import backend, mesher, solver
     from tests import problems
-    argv = sys.argv[1:]
-    problem = "poisson"
-    if argv and not argv[0].isdigit():
-        problem, argv = argv[0], argv[1:]
-    m = int(argv[0]) if len(argv) > 0 else 20
-    krylov = argv[1] if len(argv) > 1 else "cg"
-    partition = argv[2] if len(argv) > 2 else "slab"
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    backend.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-    from torch.distributed import TCPStore
-    store = TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")) + 1,
-                     world, rank == 0)
-    if rank == 0:
-        store.set("id", backend.comm_unique_id())
-    backend.comm_init(bytes(store.get("id")), rank, world)
-
     pg = problems.poisson_hex(m) if problem == "poisson" else problems.neo_hooke_brick(m)
     nf = pg["nf"]
     conns = tuple(s["conn"] for s in pg["sets"])
@@ -97,6 +81,43 @@ def main():
               % (world, problem, m, nf, krylov, partition, steps, rsteps, res, int(st["krylov_iters"]), err,
                  "OK" if ok else "FAIL"), flush=True)
     solver.clear_plan_cache()
+    return bool(backend.comm_allreduce_host([0.0 if ok else 1.0], "max")[0] == 0.0)
+
+
+def main():
+    """argv: [poisson|neohooke] [M] [cg|bicgstab] [slab|rcb]   one case
+             matrix [Mp] [Mn]                                   {poisson Mp, neohooke Mn} x {cg, bicgstab} x {slab, rcb}"""
+    from autopdex_b200 import backend
+    argv = sys.argv[1:]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    backend.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    from torch.distributed import TCPStore
+    store = TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")) + 1,
+                     world, rank == 0)
+    if rank == 0:
+        store.set("id", backend.comm_unique_id())
+    backend.comm_init(bytes(store.get("id")), rank, world)
+    if argv and argv[0] == "matrix":
+        mp = int(argv[1]) if len(argv) > 1 else 20
+        mn = int(argv[2]) if len(argv) > 2 else 12
+        cases = [(pb, m, k, pt) for pb, m in (("poisson", mp), ("neohooke", mn)) for k in ("cg", "bicgstab")
+                 for pt in ("slab", "rcb")]
+    else:
+        problem = "poisson"
+        if argv and not argv[0].isdigit():
+            problem, argv = argv[0], argv[1:]
+        cases = [(problem, int(argv[0]) if len(argv) > 0 else 20, argv[1] if len(argv) > 1 else "cg",
+                  argv[2] if len(argv) > 2 else "slab")]
+    ok = True
+    for c in cases:
+        try:
+            ok = run_case(*c, rank, world) and ok
+        except Exception as e:   # keep the remaining cases running; every rank raises alike (collective set-up errors)
+            ok = False
+            print("multi-gpu parity: ranks=%d %s m=%d %s %s -> ERROR on rank %d: %s" % (world, c[0], c[1], c[2], c[3], rank, e),
+                  flush=True)
+            from autopdex_b200 import solver
+            solver.clear_plan_cache()
     backend.comm_destroy()
     sys.exit(0 if ok else 1)
 

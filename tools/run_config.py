@@ -124,7 +124,28 @@ def poisson(n):
             "newton": list(map(float, info)), "sum": float(sol.sum()), **solver.last_stats}
 
 
-def neohooke(n, load_steps=2, traction=-1.0):
+def _dist():
+    """(rank, world) -- under torchrun the NCCL communicator of the library is initialised (one rank per GPU)."""
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not getattr(_dist, "done", False):
+        from autopdex_b200 import backend
+        backend.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        from torch.distributed import TCPStore  # plumbing only: ships the NCCL id between ranks
+        store = TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")) + 1,
+                         world, rank == 0)
+        if rank == 0:
+            store.set("id", backend.comm_unique_id())
+        backend.comm_init(bytes(store.get("id")), rank, world)
+        _dist.done = True
+    return rank, world
+
+
+def neohooke(n, load_steps=2, traction=-1.0, partition="slab"):
+    """BASELINE config 5.  Under torchrun (WORLD_SIZE > 1) the brick is split into slabs (or RCB parts) and every rank
+    solves its part through the public API (settings['b200 partition']): halo exchange + all-reduces inside the Krylov
+    loop; times are the max over ranks, the checksums are sums over the owned nodes."""
+    from autopdex_b200 import backend
+    rank, world = _dist()
     coords, elems = mesher.structured_mesh((n, n, n), UNIT_CUBE, "brick")
     face = mesher.boundary_faces((n, n, n), 0, 1)
     weak = models.hyperelastic_steady_state_weak(models.neo_hooke, lambda x, s: 100.0, lambda x, s: 0.3, "3d")
@@ -135,20 +156,43 @@ def neohooke(n, load_steps=2, traction=-1.0):
     mask = np.repeat((np.abs(coords[:, 0]) < 1e-9)[:, None], 3, axis=1)
     settings = {"connectivity": (elems, face), "node coordinates": coords, "dirichlet dofs": mask,
                 "dirichlet conditions": np.zeros(mask.shape), "load multiplier": 0.0}
-    dofs = np.zeros(mask.shape)
+    own = slice(0, coords.shape[0])
+    if world > 1:
+        pt = (mesher.rcb_partition(coords, (elems, face), rank, world) if partition == "rcb"
+              else mesher.slab_partition_mesh(coords, (elems, face), (n, n, n), rank, world))
+        nodes = pt["nodes"]
+        settings.update({"connectivity": tuple(e.astype(np.int32) for e in pt["elements"]), "node coordinates": coords[nodes],
+                         "dirichlet dofs": mask[nodes], "dirichlet conditions": np.zeros((nodes.size, 3)),
+                         "b200 partition": pt["b200 partition"]})
+        own = slice(pt["b200 partition"]["owned_node_begin"], pt["b200 partition"]["owned_node_end"])
+    dofs = np.zeros(settings["dirichlet dofs"].shape)
     hist = []
     t0 = time.perf_counter()
     for k in range(1, load_steps + 1):
         settings["load multiplier"] = traction * k / load_steps
         t = time.perf_counter()
         dofs, info = solver.solver(dofs, settings, st, newton_tol=1e-8, tol=1e-8)
-        hist.append({"newton_steps": int(info[0]), "res_norm": float(info[1]), "diverged": bool(info[2]),
-                     "step_s": time.perf_counter() - t, **{k2: solver.last_stats[k2] for k2 in
-                                                            ("assembly_tangent_ms", "assembly_residual_ms", "krylov_ms", "krylov_iters", "total_ms")}})
-    return {"config": "3D neo-Hooke %d^3 hex8 (%d dofs), Newton + Jacobi-BiCGSTAB 1e-8, %d load steps" % (n, mask.size, load_steps),
-            "total_s": time.perf_counter() - t0, "load_steps": hist, "tip_uz": float(dofs[-1, 2])}
+        ls = solver.last_stats
+        tm = backend.comm_allreduce_host([time.perf_counter() - t, ls["assembly_tangent_ms"], ls["assembly_residual_ms"],
+                                          ls["krylov_ms"], ls["total_ms"]], "max")
+        hist.append({"newton_steps": int(info[0]), "res_norm": float(info[1]), "diverged": bool(info[2]), "step_s": float(tm[0]),
+                     "assembly_tangent_ms": float(tm[1]), "assembly_residual_ms": float(tm[2]), "krylov_ms": float(tm[3]),
+                     "krylov_iters": int(ls["krylov_iters"]), "total_ms": float(tm[4]),
+                     "ms_per_krylov_iteration": float(tm[3]) / max(int(ls["krylov_iters"]), 1),
+                     "ms_per_newton_step": float(tm[4]) / max(int(info[0]), 1)})
+    d = np.asarray(dofs)[own]
+    sums = backend.comm_allreduce_host([float((d * d).sum()), float(d[:, 2].sum())])
+    out = {"config": "3D neo-Hooke %d^3 hex8 (%d dofs), Newton + Jacobi-BiCGSTAB 1e-8, %d load steps, %d GPU(s), %s partition"
+                     % (n, mask.size, load_steps, world, partition if world > 1 else "no"),
+           "n_gpus": world, "total_s": time.perf_counter() - t0, "load_steps": hist, "u_dot_u": float(sums[0]), "sum_uz": float(sums[1])}
+    if world > 1:
+        solver.clear_plan_cache()
+        backend.comm_destroy()
+    return out if rank == 0 else None
 
 
 if __name__ == "__main__":
-    name, args = sys.argv[1], [int(a) for a in sys.argv[2:]]
-    print(json.dumps({"readme": readme, "cook": cook, "heat": heat, "poisson": poisson, "neohooke": neohooke}[name](*args)))
+    name, args = sys.argv[1], [int(a) if a.lstrip("-").isdigit() else a for a in sys.argv[2:]]
+    res = {"readme": readme, "cook": cook, "heat": heat, "poisson": poisson, "neohooke": neohooke}[name](*args)
+    if res is not None:
+        print(json.dumps(res), flush=True)
