@@ -67,6 +67,7 @@ SIGNATURES = {
     "apdx_set_dofs_n": (C.c_int, [_P, _P]),
     "apdx_assemble": (C.c_int, [_P, _P, C.c_int, _P]),
     "apdx_get_values": (C.c_int, [_P, C.c_int, _P]),
+    "apdx_get_coo_values": (C.c_int, [_P, _I64, _I64, _P]),
     "apdx_spmv": (C.c_int, [_P, _P, _P]),
     "apdx_krylov": (C.c_int, [_P, C.POINTER(KrylovOpts), _P, _P, C.POINTER(_I32), C.POINTER(_D)]),
     "apdx_linear_step": (C.c_int, [_P, C.POINTER(KrylovOpts), _P, _P, _P, C.POINTER(_I32)]),

@@ -298,6 +298,14 @@ class Plan:
         _lib.check(_lib.load().apdx_get_values(self.h, int(reduced), out.ctypes.data_as(C.c_void_p)))
         return out[:nnz]
 
+    def coo_values(self, offset=0, count=None):
+        """Element-tangent entries of the last tangent assembly in the reference's COO order, duplicates not summed
+        (the `data` of the BCOO that assembler.assemble_tangent returns, assembler.py:749-777)."""
+        count = self.n_coo - offset if count is None else count
+        out = np.empty(max(count, 1), dtype=np.float64)
+        _lib.check(_lib.load().apdx_get_coo_values(self.h, int(offset), int(count), out.ctypes.data_as(C.c_void_p)))
+        return out[:count]
+
     def spmv(self, x_d, y_d):
         _lib.check(_lib.load().apdx_spmv(self.h, x_d.ptr, y_d.ptr))
 

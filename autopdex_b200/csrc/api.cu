@@ -143,6 +143,7 @@ static int assemble_internal(apdx_plan *pl, const double *dofs_d, int tangent_fl
     pl->have_sell_values = true;
   }
   if (tangent_flags) {
+    pl->have_ke = true;
     pl->have_values = (tangent_flags & 1) != 0;
     pl->have_red_values = (tangent_flags & 2) != 0;
   }
@@ -561,6 +562,23 @@ int apdx_get_values(const apdx_plan *pl, int reduced, double *values_h) {
   } else {
     APDX_REQUIRE(pl->have_values, APDX_ERR_STATE, "full CSR values not assembled: call apdx_assemble first");
     APDX_CUDA(cudaMemcpy(values_h, pl->vals.p, pl->nnz * 8, cudaMemcpyDeviceToHost));
+  }
+  return APDX_OK;
+}
+
+int apdx_get_coo_values(apdx_plan *pl, int64_t offset, int64_t count, double *values_h) {
+  APDX_REQUIRE(pl && (values_h || count == 0), APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(pl->have_ke, APDX_ERR_STATE, "no element matrices: call apdx_assemble with want_tangent first");
+  APDX_REQUIRE(offset >= 0 && count >= 0 && offset + count <= pl->n_coo, APDX_ERR_INVALID,
+               "COO range [%lld, %lld) outside [0, %lld)", (long long)offset, (long long)(offset + count), (long long)pl->n_coo);
+  const int64_t chunk = 1ll << 24;   // 128 MB of staging
+  apdx::DevBuf<double> tmp;
+  APDX_CHECK(tmp.alloc(std::min<int64_t>(chunk, std::max<int64_t>(count, 1))));
+  for (int64_t o = 0; o < count; o += chunk) {
+    const int64_t c = std::min<int64_t>(chunk, count - o);
+    APDX_CHECK(apdx::coo_export(pl, offset + o, c, tmp.p));
+    APDX_CUDA(cudaMemcpyAsync(values_h + o, tmp.p, c * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+    APDX_CUDA(cudaStreamSynchronize(pl->stream));
   }
   return APDX_OK;
 }

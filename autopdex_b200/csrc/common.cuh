@@ -143,8 +143,17 @@ constexpr int32_t SELL_FAST = 1 << 29;  // Sell::sl_m flag: offset-mode slice wh
 constexpr int32_t SELL_MMASK = 0x0fffffff;
 
 // sliced-ELL copy of the owned rows of the reduced system (sell.cu)
+// Work distribution of the sliced-ELL SpMV (krylov.cu): block step t of the persistent grid -> the slices of its 8 warps.
+struct SpmvSched {
+  int planes = 1;               // G: consecutive mesh planes whose slices share a block step (1, 2, 4 or 8)
+  int32_t delta = 0;            // slices per mesh plane (distance to the partner slice of the farthest mirrored column)
+  int32_t steps_per_group = 0;  // block steps per group of G planes = ceil(delta / (8 / G))
+  int32_t n_steps = 0;
+};
+
 struct Sell {
   bool built = false;
+  SpmvSched sched;
   bool sym = true;            // lower columns read from the transposed position where possible (sell.cu)
   int64_t row0 = 0, n_rows = 0, n_slices = 0, n_val = 0, n_idx = 0, n_mirrored = 0;
   int nf = 1;                 // slices interleave the nf dofs per node (sell.cu)
@@ -211,6 +220,7 @@ struct apdx_plan {
   apdx::DevBuf<double> ke, re;             // element matrices / vectors (streams in COO order)
   apdx::DevBuf<double> vals, red_vals;     // summed CSR data
   bool have_values = false;
+  bool have_ke = false;              // element matrices of the last tangent assembly are in `ke` (apdx_get_coo_values)
 
   // Newton / Krylov work
   apdx::DevBuf<double> residual, rhs_red, x_red, dofs_trial;
@@ -246,6 +256,7 @@ namespace apdx {
 void drop_all_krylov_graphs();
 // pattern.cu
 int build_pattern(apdx_plan *pl, const uint8_t *mask_h);
+int coo_export(apdx_plan *pl, int64_t offset, int64_t count, double *dst_d);
 // elements_fast.cu
 bool fast_kernel_applies(int dim, int nf, const apdx_set_desc &d);
 // elements.cu

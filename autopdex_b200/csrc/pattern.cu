@@ -57,13 +57,11 @@ struct SoaTable {
   int n;
   SoaSet s[16];
 };
-__global__ void k_to_soa(uint32_t *__restrict__ list, int64_t n, SoaTable t) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int64_t k = list[i];
+// stream address of the reference-order COO (or element-vector) index k
+__device__ __forceinline__ int64_t soa_address(int64_t k, const SoaTable &t) {
   int q = 0;
   while (q + 1 < t.n && k >= t.s[q + 1].off) ++q;
-  if (t.s[q].n_rows == 0) return;   // this set keeps the reference (element-major) layout
+  if (t.s[q].n_rows == 0) return k;   // this set keeps the reference (element-major) layout
   const int64_t local = k - t.s[q].off;
   const int64_t e = local / t.s[q].width;
   int64_t ij = local - e * t.s[q].width;
@@ -72,7 +70,27 @@ __global__ void k_to_soa(uint32_t *__restrict__ list, int64_t n, SoaTable t) {
     const int lo = a < b ? a : b, hi = a < b ? b : a;
     ij = lo * nn - lo * (lo - 1) / 2 + (hi - lo);
   }
-  list[i] = (uint32_t)(t.s[q].off + ij * t.s[q].n_rows + e);
+  return t.s[q].off + ij * t.s[q].n_rows + e;
+}
+__global__ void k_to_soa(uint32_t *__restrict__ list, int64_t n, SoaTable t) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  list[i] = (uint32_t)soa_address(list[i], t);
+}
+// element-matrix entries [k0, k0 + n) in the reference's COO order (assembler.py:1383: data = tangent_contributions.flatten())
+__global__ void k_coo_export(const double *__restrict__ ke, int64_t k0, int64_t n, SoaTable t, double *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = ke[soa_address(k0 + i, t)];
+}
+
+static SoaTable matrix_soa_table(const apdx_plan *pl) {
+  SoaTable t{};
+  for (auto &st : pl->sets) {
+    if (st.d.n_rows == 0) continue;
+    t.s[t.n++] = SoaSet{st.coo_offset, st.soa ? st.d.n_rows : 0, st.ndof_e * st.ndof_e, st.soa ? st.ndof_e : 0};
+  }
+  return t;
 }
 
 template <typename K>
@@ -306,11 +324,7 @@ int build_pattern(apdx_plan *pl, const uint8_t *mask_h) {
     APDX_CUDA(cudaMemcpyAsync(pl->seg_ptr.p + pl->nnz, &nc32, sizeof(int32_t), cudaMemcpyHostToDevice, s));
     APDX_CHECK(pl->row_ptr.alloc(n + 1));
     k_row_ptr<<<grid_for(pl->nnz, B), B, 0, s>>>(sorted.p, pl->seg_ptr.p, pl->nnz, bits, n, pl->row_ptr.p);
-    SoaTable t{};
-    for (auto &st : pl->sets) {
-      if (st.d.n_rows == 0) continue;
-      t.s[t.n++] = SoaSet{st.coo_offset, st.soa ? st.d.n_rows : 0, st.ndof_e * st.ndof_e, st.soa ? st.ndof_e : 0};
-    }
+    const SoaTable t = matrix_soa_table(pl);
     k_to_soa<<<grid_for(nc, B), B, 0, s>>>(pl->perm.p, nc, t);   // after k_unique_fill, which needs reference-order indices
     APDX_CUDA(cudaStreamSynchronize(s));
   }
@@ -336,6 +350,15 @@ int build_pattern(apdx_plan *pl, const uint8_t *mask_h) {
                                                  pl->red_col.p, pl->red2full.p, pl->red_diag.p);
     APDX_CUDA(cudaStreamSynchronize(s));
   }
+  APDX_CUDA(cudaGetLastError());
+  return APDX_OK;
+}
+
+// The BCOO wire format of assembler.assemble_tangent (assembler.py:749-777): values of the element-local pairs
+// [offset, offset + count) in reference order, duplicates NOT summed, copied out of the element streams.
+int coo_export(apdx_plan *pl, int64_t offset, int64_t count, double *dst_d) {
+  if (count <= 0) return APDX_OK;
+  k_coo_export<<<grid_for(count, 256), 256, 0, pl->stream>>>(pl->ke.p, offset, count, matrix_soa_table(pl), dst_d);
   APDX_CUDA(cudaGetLastError());
   return APDX_OK;
 }

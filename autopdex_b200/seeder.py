@@ -40,25 +40,33 @@ def gauss_legendre_nd(dimension, order):
 
 
 # ---- integration points in simplex / line meshes ('sparse' assembling mode) ------------------------
+_RULES = None
+
+
+def _simplex_rule(name, order):
+    """Tabulated reference-simplex rules of autopdex.seeder (triangle: seeder.py:1813-2285, rules of
+    mathsfromnothing.au; tetrahedron: seeder.py:2288-3421, Jaskowiec and Sukumar 2020), orders 1-10, same points in the
+    same order, same weights to the last digit: autopdex_b200/data/simplex_rules.npz holds the outputs of the
+    reference functions themselves (tools/make_simplex_rules.py)."""
+    global _RULES
+    if _RULES is None:
+        import os
+        _RULES = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "simplex_rules.npz")))
+    key = "%s_%d_x" % (name, order)
+    if key not in _RULES:
+        raise ValueError("Quadrature order not implemented")
+    return _RULES[key].copy(), _RULES["%s_%d_w" % (name, order)].copy()
+
+
 def int_pts_ref_tri(order):
-    """Reference-triangle rule (weights sum to 1/2).  Orders 1-2 coincide with autopdex.seeder.int_pts_ref_tri
-    (seeder.py:1813-1835); higher orders are not tabulated here -- pass your own points in `settings`."""
-    if order == 1:
-        return np.array([[1 / 3, 1 / 3]]), np.array([0.5])
-    if order == 2:
-        return np.array([[1 / 6, 1 / 6], [1 / 6, 2 / 3], [2 / 3, 1 / 6]]), np.full(3, 1 / 6)
-    raise NotImplementedError("triangle rule of order %d: supply 'integration coordinates' yourself" % order)
+    """autopdex.seeder.int_pts_ref_tri: (points (n, 2), weights (n,)) on the reference triangle, weights sum to 1/2."""
+    return _simplex_rule("tri", order)
 
 
 def int_pts_ref_tet(order):
-    """Reference-tetrahedron rule (weights sum to 1/6).  Order 1 coincides with the reference; order 2 is the
-    classical symmetric 4-point rule (the reference tabulates an asymmetric one, seeder.py:2303-2325)."""
-    if order == 1:
-        return np.array([[0.25, 0.25, 0.25]]), np.array([1 / 6])
-    if order == 2:
-        a, b = 0.1381966011250105, 0.5854101966249685
-        return np.array([[a, a, a], [b, a, a], [a, b, a], [a, a, b]]), np.full(4, 1 / 24)
-    raise NotImplementedError("tetrahedron rule of order %d: supply 'integration coordinates' yourself" % order)
+    """autopdex.seeder.int_pts_ref_tet: (points (n, 3), weights (n,)) on the reference tetrahedron, weights sum to
+    1/6 -- the reference's (asymmetric) Jaskowiec-Sukumar tables, order 2 included."""
+    return _simplex_rule("tet", order)
 
 
 def _int_pts_in_mesh(x_nodes, elem, ref_pts, ref_w, nv):

@@ -160,6 +160,10 @@ int apdx_set_dofs_n(apdx_plan *plan, const double *dofs_n_h);            /* sett
  * With want_tangent the summed values are kept inside the plan (full and reduced CSR).    */
 int apdx_assemble(apdx_plan *plan, const double *dofs_d, int want_tangent, double *residual_d);
 int apdx_get_values(const apdx_plan *plan, int reduced, double *values_h); /* [nnz] after assemble */
+/* The BCOO wire format of assembler.assemble_tangent (autopdex/assembler.py:749-777, data = the flattened element
+ * tangents of assembler.py:1383, duplicates NOT summed): values of the element-local pairs [offset, offset+count) of
+ * the last tangent assembly in the reference's COO order (set-major, element-major, local row, local column). */
+int apdx_get_coo_values(apdx_plan *plan, int64_t offset, int64_t count, double *values_h);
 
 /* ---- linear algebra on the assembled reduced system ---------------------------------- */
 int apdx_spmv(apdx_plan *plan, const double *x_d, double *y_d);           /* [n_free] each */

@@ -73,6 +73,16 @@ def case_tables(out):
     out["indices_nf2"] = A(assembler._get_indices(jnp.asarray(conn), jnp.zeros((6, 2)))).astype(np.int64)
 
 
+def case_indices_dict(out):
+    """dict-dof COO index emission with TWO fields of different dofs per node and different connectivities
+    (assembler.py:61-121: field offsets in key order, blocks `for field_i: for field_j:`)."""
+    from autopdex import assembler
+    cu = np.array([[0, 3, 4, 1], [1, 4, 5, 2], [3, 6, 7, 4]])
+    cp = np.array([[0, 1, 2], [1, 2, 3], [2, 3, 0]])
+    dofs = {"u": jnp.zeros((8, 2)), "p": jnp.zeros(4)}
+    out["indices_dict_up"] = A(assembler._get_indices({"u": jnp.asarray(cu), "p": jnp.asarray(cp)}, dofs)).astype(np.int64)
+
+
 def readme_case(n, out, tag):
     pts = [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]
     coords, elems = mesher.structured_mesh((n, n), pts, "quad")
@@ -354,7 +364,7 @@ def case_newton_semantics(out):
     out["newton_maxiter"] = np.array(run([1.0] * 10, maxiter=3))
 
 
-CASES = {"tables": case_tables, "readme3": lambda o: readme_case(3, o, "readme3"),
+CASES = {"tables": case_tables, "indices_dict": case_indices_dict, "readme3": lambda o: readme_case(3, o, "readme3"),
          "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "elements_more": case_elements_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 

@@ -322,3 +322,32 @@ def test_csr_diagonal_reads_the_diagonal_of_a_canonical_csr():
     A.sort_indices()
     got = assembler.csr_diagonal(assembler.CSR(A.data, A.indices.astype(np.int64), A.indptr.astype(np.int64), A.shape))
     assert np.array_equal(got, A.diagonal())
+
+
+def test_get_indices_array_and_dict_block_order():
+    """assembler._get_indices (assembler.py:41-141): array dofs against the oracle's COO order; dict dofs (two fields,
+    different dofs per node and different connectivities) against a literal transcription of the reference loop."""
+    from autopdex_b200 import assembler
+    from oracle import assemble as oasm
+    rng = np.random.default_rng(5)
+    conn = rng.integers(0, 11, size=(7, 4))
+    idx = assembler._get_indices(conn, np.zeros((11, 2)))
+    r, c = oasm.coo_indices([{"conn": conn, "nf": 2}])
+    assert idx.dtype == np.int64 and np.array_equal(idx[:, 0], r) and np.array_equal(idx[:, 1], c)
+    idx1 = assembler._get_indices(conn, np.zeros(11))
+    r, c = oasm.coo_indices([{"conn": conn, "nf": 1}])
+    assert np.array_equal(idx1[:, 0], r) and np.array_equal(idx1[:, 1], c)
+    # dict: fields u (11 nodes x 2) and p (5 nodes, scalar) with their own connectivities
+    dofs = {"u": np.zeros((11, 2)), "p": np.zeros(5)}
+    cn = {"u": conn, "p": rng.integers(0, 5, size=(7, 3))}
+    got = assembler._get_indices(cn, dofs)
+    off = {"u": 0, "p": 22}
+    nfd = {"u": 2, "p": 1}
+    want = []
+    for fi in dofs:                      # assembler.py:79-80
+        for fj in dofs:
+            for e in range(7):           # vmap over elements, assembler.py:116-117
+                gi = (off[fi] + cn[fi][e][:, None] * nfd[fi] + np.arange(nfd[fi])).ravel()
+                gj = (off[fj] + cn[fj][e][:, None] * nfd[fj] + np.arange(nfd[fj])).ravel()
+                want.append(np.stack([np.repeat(gi, gj.size), np.tile(gj, gi.size)], axis=-1))
+    assert np.array_equal(got, np.concatenate(want))

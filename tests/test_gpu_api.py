@@ -159,13 +159,38 @@ def test_assembler_module_matches_oracle():
     p, settings, static_settings = _cook_settings()
     dofs = np.random.default_rng(0).uniform(-0.05, 0.05, p["mask"].shape)
     R = assembler.assemble_residual(dofs, settings, static_settings)
-    K = assembler.assemble_tangent(dofs, settings, static_settings)
+    B = assembler.assemble_tangent(dofs, settings, static_settings)          # the reference's wire format (BCOO)
     Ro, data = oasm.assemble(p["sets"], p["coords"], dofs, {})
     rows, cols = oasm.coo_indices(p["sets"])
+    # element-local pairs in reference order, duplicates not summed: indices bit-exact, values <= 1e-12
+    assert B.indices.shape == (rows.size, 2) and B.indices.dtype == np.int64 and B.nse == rows.size
+    assert np.array_equal(B.indices[:, 0], rows) and np.array_equal(B.indices[:, 1], cols)
+    assert B.shape == (dofs.size, dofs.size)
+    assert np.abs(B.data - data).max() / np.abs(data).max() < 1e-12
     full = oasm.scipy_assembling(data, rows, cols, dofs.size)
-    assert np.array_equal(K.indptr, full.indptr) and np.array_equal(K.indices, full.indices)
-    assert np.abs(K.data - full.data).max() / np.abs(full.data).max() < 1e-12
+    # what solver.scipy_assembling makes of it (solver.py:1207-1211): the reference's own SciPy calls on OUR BCOO
+    mine = oasm.scipy_assembling(B.data, B.indices[:, 0], B.indices[:, 1], dofs.size)
+    assert np.array_equal(mine.indptr, full.indptr) and np.array_equal(mine.indices, full.indices)
+    assert np.abs(mine.data - full.data).max() / np.abs(full.data).max() < 1e-12
+    for K in (B.sum_duplicates(), assembler.assemble_tangent(dofs, settings, static_settings, format="csr")):
+        assert np.array_equal(K.indptr, full.indptr) and np.array_equal(K.indices, full.indices)
+        assert np.abs(K.data - full.data).max() / np.abs(full.data).max() < 1e-12
     assert np.abs(R.ravel() - Ro).max() / np.abs(Ro).max() < 1e-12
+
+
+def test_bcoo_of_register_kernel_set_matches_oracle():
+    """hex8 Poisson goes through the register kernel, whose element stream is entry-major and upper-triangle only:
+    apdx_get_coo_values must hand back the reference's element-major full matrices."""
+    from autopdex_b200 import assembler
+    import bench
+    settings, static_settings, _ = bench.build_problem(5, 0, 1)
+    p = problems.poisson_hex(5)
+    dofs = np.random.default_rng(3).uniform(-1, 1, p["mask"].shape)
+    B = assembler.assemble_tangent(dofs, settings, static_settings)
+    _, data = oasm.assemble(p["sets"], p["coords"], dofs, {})
+    rows, cols = oasm.coo_indices(p["sets"])
+    assert np.array_equal(B.indices[:, 0], rows) and np.array_equal(B.indices[:, 1], cols)
+    assert np.abs(B.data - data).max() / np.abs(data).max() < 1e-12
 
 
 @pytest.mark.parametrize("transpose", [False, True])

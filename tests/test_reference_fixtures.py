@@ -38,24 +38,28 @@ def test_gauss_rules_match_reference_tables():
 
 
 def test_simplex_rules_low_order_match_reference():
-    x, w = seeder.int_pts_ref_tri(1)
-    assert np.allclose(x, FIX["tri_rule_1_x"]) and np.allclose(w, FIX["tri_rule_1_w"])
-    x, w = seeder.int_pts_ref_tri(2)
-    # same rule, possibly another point order: compare as sets
-    assert np.allclose(sorted(map(tuple, np.round(x, 12))), sorted(map(tuple, np.round(FIX["tri_rule_2_x"], 12))))
-    assert np.allclose(w, FIX["tri_rule_2_w"], atol=1e-15)
-    x, w = seeder.int_pts_ref_tet(1)
-    assert np.allclose(x, FIX["tet_rule_1_x"][:, :3] if FIX["tet_rule_1_x"].shape[1] > 3 else FIX["tet_rule_1_x"])
-
-
-@pytest.mark.parametrize("fam,dim,nen,name", [
-    ("quad_brick", 1, 2, "line2"), ("quad_brick", 1, 3, "line3"), ("quad_brick", 2, 4, "quad4"),
-    ("quad_brick", 2, 9, "quad9"), ("quad_brick", 3, 8, "hex8"), ("quad_brick", 3, 27, "hex27"),
-    ("tri_tet", 2, 3, "tri3"), ("tri_tet", 2, 6, "tri6"), ("tri_tet", 3, 4, "tet4"), ("tri_tet", 3, 10, "tet10")])
-def test_shape_functions_match_reference_generated_code(fam, dim, nen, name):
-    xi, N = FIX["shape_%s_%d_%d_xi" % (fam, dim, nen)], FIX["shape_%s_%d_%d_N" % (fam, dim, nen)]
-    assert np.abs(spaces.shape_tables(fam, nen, dim, xi)[0] - N).max() < 1e-13      # product host tables
-    assert np.abs(oshapes.shape_tables(name, xi)[0] - N).max() < 1e-13              # oracle
+    # the simplex rules are the reference's tables themselves, point order included: exact equality with the
+    # reference-run fixtures (orders 1 and 2 of both families are in the fixture file; all ten orders are checked for
+    # their polynomial exactness below)
+    for fam, fun in (("tri", seeder.int_pts_ref_tri), ("tet", seeder.int_pts_ref_tet)):
+        for order in (1, 2):
+            x, w = fun(order)
+            assert np.array_equal(x, FIX["%s_rule_%d_x" % (fam, order)]) and np.array_equal(w, FIX["%s_rule_%d_w" % (fam, order)])
+    import math
+    for order in range(1, 11):
+        x, w = seeder.int_pts_ref_tri(order)
+        for a in range(order + 1):
+            for b in range(order + 1 - a):       # integral of x^a y^b over the reference triangle = a! b! / (a+b+2)!
+                exact = math.factorial(a) * math.factorial(b) / math.factorial(a + b + 2)
+                assert abs(np.sum(w * x[:, 0] ** a * x[:, 1] ** b) - exact) < 2e-13, (order, a, b)
+        x, w = seeder.int_pts_ref_tet(order)
+        for a in range(order + 1):
+            for b in range(order + 1 - a):
+                for c in range(order + 1 - a - b):
+                    exact = math.factorial(a) * math.factorial(b) * math.factorial(c) / math.factorial(a + b + c + 3)
+                    assert abs(np.sum(w * x[:, 0] ** a * x[:, 1] ** b * x[:, 2] ** c) - exact) < 2e-13, (order, a, b, c)
+    with pytest.raises(ValueError):
+        seeder.int_pts_ref_tri(11)
 
 
 def test_meshes_match_reference_mesher():
@@ -84,6 +88,19 @@ def test_coo_index_order_matches_reference_get_indices():
     conn = np.array([[0, 3, 4, 1], [1, 4, 5, 2]])
     rows, cols = oasm.coo_indices([dict(conn=conn, nf=2)])
     assert np.array_equal(np.stack([rows, cols], axis=1), FIX["indices_nf2"])
+
+
+def test_get_indices_two_fields_matches_reference_run():
+    """a7: the product's host-side _get_indices against the unmodified reference function run on dict dofs with two
+    fields (u: 8 nodes x 2, p: 4 nodes scalar; tests/golden/make_reference_fixtures.py:case_indices_dict)."""
+    from autopdex_b200 import assembler
+    cu = np.array([[0, 3, 4, 1], [1, 4, 5, 2], [3, 6, 7, 4]])
+    cp = np.array([[0, 1, 2], [1, 2, 3], [2, 3, 0]])
+    got = assembler._get_indices({"u": cu, "p": cp}, {"u": np.zeros((8, 2)), "p": np.zeros(4)})
+    assert got.dtype == np.int64 and np.array_equal(got, FIX["indices_dict_up"])
+    # array dofs too
+    conn = np.array([[0, 3, 4, 1], [1, 4, 5, 2]])
+    assert np.array_equal(assembler._get_indices(conn, np.zeros((6, 2))), FIX["indices_nf2"])
 
 
 # ---- assembled residuals / tangents / solutions produced by the reference's assembler and solver ---------------
