@@ -143,17 +143,8 @@ constexpr int32_t SELL_FAST = 1 << 29;  // Sell::sl_m flag: offset-mode slice wh
 constexpr int32_t SELL_MMASK = 0x0fffffff;
 
 // sliced-ELL copy of the owned rows of the reduced system (sell.cu)
-// Work distribution of the sliced-ELL SpMV (krylov.cu): block step t of the persistent grid -> the slices of its 8 warps.
-struct SpmvSched {
-  int planes = 1;               // G: consecutive mesh planes whose slices share a block step (1, 2, 4 or 8)
-  int32_t delta = 0;            // slices per mesh plane (distance to the partner slice of the farthest mirrored column)
-  int32_t steps_per_group = 0;  // block steps per group of G planes = ceil(delta / (8 / G))
-  int32_t n_steps = 0;
-};
-
 struct Sell {
   bool built = false;
-  SpmvSched sched;
   bool sym = true;            // lower columns read from the transposed position where possible (sell.cu)
   int64_t row0 = 0, n_rows = 0, n_slices = 0, n_val = 0, n_idx = 0, n_mirrored = 0;
   int nf = 1;                 // slices interleave the nf dofs per node (sell.cu)

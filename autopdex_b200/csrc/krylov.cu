@@ -214,7 +214,10 @@ constexpr int SPMV_U = 9;
 // Fast paths for slices flagged SELL_FAST (every column of every row inside x: no index clamps) whose column count is
 // a multiple of the batch B: compile-time trip counts, no predicates, offsets held one per lane and handed out by
 // shuffles.  Half the instructions of the generic path.
-// (Measured and removed in round 2, profiles/r02a_spmv_variants_*.jsonl: kernels compiled for 3 / 4 resident blocks per
+// (Measured and removed in round 2: a schedule that gave the 8 warps of a block the same in-plane position of 2/4/8
+// consecutive mesh planes, so that the plane-distance mirrored columns and x windows would hit this SM's L1 instead of
+// the L2 -- L2->L1 traffic fell only from 4.39 to 4.05 GB per launch and the time did not move, 0.483 -> 0.493-0.501 ms,
+// profiles/r02d_spmv_planes_*.jsonl.  Also, profiles/r02a_spmv_variants_*.jsonl: kernels compiled for 3 / 4 resident blocks per
 // SM with shallower batches -- 0.500 / 0.695 ms against 0.486 ms at P256 -- and a variant that requested the next
 // slice's first value batch during the mirrored phase -- 0.501 ms; nf = 3 at 96^3: 0.297 / 0.325 / 0.275 against 0.246.)
 template <int B, bool SYM>
@@ -288,8 +291,8 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     k_spmv_sell(const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_m, const int64_t *__restrict__ valptr,
                 const int64_t *__restrict__ idxptr, const double *__restrict__ val, const int32_t *__restrict__ idx,
                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, int64_t row0,
-                int64_t row1, int64_t n_slices, int32_t n_cols, SpmvSched sch, double *partial, unsigned int *ticket,
-                double *sc, int32_t *fl, int stage, int fused, int check_done) {
+                int64_t row1, int64_t n_slices, int32_t n_cols, double *partial, unsigned int *ticket, double *sc,
+                int32_t *fl, int stage, int fused, int check_done) {
   if (check_done && fl[F_DONE]) return;
   const int lane = threadIdx.x & 31;
   constexpr int WPB = VEC_BLOCK / 32;
@@ -297,24 +300,9 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
   double acc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
   for (int i = 0; i < (NDOT > 0 ? NDOT : 1); ++i) acc[i] = 0.0;
-  // Block step t -> slice of this warp (SpmvSched, common.cuh).  planes == 1: 8 consecutive slices per block step.
-  // planes = G > 1: the warps of a block take the slices pos, pos + delta, ..., pos + (G-1) delta -- the same in-plane
-  // position of G consecutive mesh planes (delta = slices per plane, found when the plan is built) -- so that the
-  // mirrored columns that reach one plane back (9 of the 13 lower columns of a 27-point row) and the x windows of the
-  // neighbouring planes are found in this SM's L1, where the neighbouring warp has just streamed them, instead of in
-  // the L2 (whose ~6300 B/clk cap, not the HBM, bounds this kernel: ncu l1tex__m_xbar2l1tex_read_bytes 4.39 GB per launch
-  // against 2.23 GB of DRAM traffic at 256^3, profiles/r02a_k_spmv_sell_p256_full.txt).
-  const int wib = threadIdx.x >> 5;
+  const int64_t si_begin = (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5);
   const int64_t si_end = n_slices;
-  auto slice_of_step = [&](int32_t t) -> int64_t {
-    if (t >= sch.n_steps) return si_end;
-    if (sch.planes <= 1) return (int64_t)t * WPB + wib;
-    const int32_t g = t / sch.steps_per_group, q = t - g * sch.steps_per_group;
-    const int32_t pos = q * (WPB / sch.planes) + wib / sch.planes;
-    if (pos >= sch.delta) return si_end;
-    return (int64_t)((g * sch.planes + wib % sch.planes) * sch.delta + pos);
-  };
-  const int64_t si_begin = slice_of_step(blockIdx.x);
+  const int64_t si_step = (int64_t)gridDim.x * WPB;
   // The per-slice metadata is a chain of dependent loads (header -> offsets -> x gathers): the header of the warp's
   // NEXT slice is requested before the current slice is processed, its first 32 offsets half-way through.
   struct Hdr { int32_t wenc, M; int64_t vp, ip; };
@@ -338,11 +326,9 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
   Hdr cur;
   load_hdr(si_begin, cur);
   int32_t offl0 = load_offsets(cur);
-  int64_t s = si_begin;
-  for (int32_t t = blockIdx.x; t < sch.n_steps; t += gridDim.x) {
-    const int64_t s_next = slice_of_step(t + (int32_t)gridDim.x);
+  for (int64_t s = si_begin; s < si_end; s += si_step) {
     Hdr nxt;
-    load_hdr(s_next, nxt);
+    load_hdr(s + si_step, nxt);
     const int32_t wenc = cur.wenc;
     const int32_t W = wenc & 0x7fffffff;
     const int32_t M = SYM ? (cur.M & SELL_MMASK) : 0;
@@ -428,14 +414,12 @@ __global__ void __launch_bounds__(VEC_BLOCK, 2)
     }
     cur = nxt;
     offl0 = offl_n;
-    const bool live = s < si_end;
-    s = s_next;
-    if (live && r0 < row1) {
+    if (r0 < row1) {
       y[r0] = a0;
       if (NDOT >= 1) acc[0] += w[r0] * a0;
       if (NDOT >= 2) acc[1] += a0 * a0;
     }
-    if (live && r1 < row1) {
+    if (r1 < row1) {
       y[r1] = a1;
       if (NDOT >= 1) acc[0] += w[r1] * a1;
       if (NDOT >= 2) acc[1] += a1 * a1;
@@ -691,9 +675,10 @@ static Comm comm_of(apdx_plan *pl) {
 
 // persistent SpMV grid: exactly the blocks that are resident at once (the kernel is compiled for 2 blocks of 256
 // threads per SM)
-static unsigned spmv_grid(int64_t n_steps) {
+static unsigned spmv_grid(int64_t n_slices) {
   const int resident = sm_count() * 2;
-  return (unsigned)(n_steps < resident ? (n_steps > 0 ? n_steps : 1) : resident);
+  const int64_t nb = (n_slices + VEC_BLOCK / 32 - 1) / (VEC_BLOCK / 32);
+  return (unsigned)(nb < resident ? (nb > 0 ? nb : 1) : resident);
 }
 
 template <int NDOT>
@@ -701,10 +686,10 @@ static int launch_spmv(apdx_plan *pl, const double *x, double *y, const double *
   KrylovWork &k = pl->kw;
   Sell &S = pl->sell;
   const Comm c = comm_of(pl);
-  const unsigned grid = spmv_grid(S.sched.n_steps);
+  const unsigned grid = spmv_grid(S.n_slices);
 #define APDX_SPMV_ARGS                                                                                                 \
   S.sl_w.p, S.sl_m.p, S.valptr.p, S.idxptr.p, S.val.p, S.idx.p, x, y, w, pl->f0, pl->f1, S.n_slices,                   \
-      (int32_t)pl->n_free, S.sched, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done
+      (int32_t)pl->n_free, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, stage, c.fused, check_done
 #define APDX_SPMV_NF(NFV)                                                                                              \
   do {                                                                                                                 \
     if (S.sym && S.n_mirrored > 0) k_spmv_sell<NDOT, NFV, true><<<grid, VEC_BLOCK, 0, pl->stream>>>(APDX_SPMV_ARGS);   \

@@ -15,7 +15,6 @@
 #include <cub/cub.cuh>
 #include <stdlib.h>
 
-#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -333,29 +332,6 @@ __global__ void k_gather_reduce_sell(const double *__restrict__ ke, const uint32
   sell_val[t] = acc;
 }
 
-// Distance to the next mesh plane as seen by an offset-mode slice: its stored offsets >= 0 ascend and, on a mesh numbered
-// plane by plane, fall into clusters (same line / neighbouring lines / next plane); the centre of the cluster behind the
-// largest gap is the plane stride in dofs (0: explicit-mode slice or a single cluster).  sell_build turns the most
-// frequent value into the slices per mesh plane of the SpMV schedule.
-__global__ void k_sell_reach(const int32_t *__restrict__ sl_w, const int32_t *__restrict__ sl_u,
-                             const int64_t *__restrict__ idxptr, const int32_t *__restrict__ idx, int64_t ns,
-                             int32_t *__restrict__ reach) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= ns) return;
-  int32_t r = 0;
-  const int32_t nu = sl_u[s];
-  if (sl_w[s] < 0 && nu > 1) {
-    const int32_t *o = idx + idxptr[s];
-    int32_t gap = 0, first = 0;
-    for (int32_t j = 1; j < nu; ++j) {
-      const int32_t g = o[j] - o[j - 1];
-      if (g > gap) { gap = g; first = o[j]; }
-    }
-    if (gap > 1) r = (int32_t)(((int64_t)first + o[nu - 1]) / 2);
-  }
-  reach[s] = r;
-}
-
 static int scan64(const int32_t *in, int64_t *out, int64_t n, cudaStream_t s) {
   size_t tb = 0;
   cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *> it(in, cub::CastOp<int64_t>());
@@ -437,47 +413,6 @@ int sell_build(apdx_plan *pl) {
     k_sell_mirror<<<(unsigned)((ns + 255) / 256), 256, 0, s>>>(G, sl_mode.p, S.sl_w.p, S.sl_m.p, sl_u.p, S.valptr.p,
                                                                S.idxptr.p, S.idx.p, S.n_val);
   APDX_CUDA(cudaStreamSynchronize(s));
-  {  // SpMV schedule: slices per mesh plane = the most frequent reach of the farthest stored column, in slices
-    S.sched = SpmvSched();
-    S.sched.n_steps = (int32_t)((ns + 7) / 8);
-    int planes = 8;
-    if (const char *e = getenv("APDX_SPMV_PLANES")) planes = atoi(e);
-    if (planes != 2 && planes != 4 && planes != 8) planes = 1;
-    if (planes > 1 && ns >= 64) {
-      DevBuf<int32_t> reach;
-      APDX_CHECK(reach.alloc(ns));
-      k_sell_reach<<<(unsigned)((ns + 255) / 256), 256, 0, s>>>(S.sl_w.p, sl_u.p, S.idxptr.p, S.idx.p, ns, reach.p);
-      std::vector<int32_t> h((size_t)ns);
-      APDX_CUDA(cudaMemcpyAsync(h.data(), reach.p, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      APDX_CUDA(cudaStreamSynchronize(s));
-      reach.release();
-      // reach in node blocks of 64 rows of one component (rows of a slice are nf dofs apart), rounded
-      const int64_t unit = (int64_t)SELL_C * S.nf;
-      for (auto &v : h) v = (int32_t)((v + unit / 2) / unit);
-      std::vector<int32_t> srt(h);
-      std::sort(srt.begin(), srt.end());
-      int32_t best = 0; int64_t best_n = 0;
-      for (size_t i = 0; i < srt.size();) {
-        size_t j = i;
-        while (j < srt.size() && srt[j] == srt[i]) ++j;
-        if ((int64_t)(j - i) > best_n) { best_n = (int64_t)(j - i); best = srt[i]; }
-        i = j;
-      }
-      // worth it only if a plane is much longer than a block step and the matrix has several planes
-      const int64_t delta = (int64_t)best * S.nf;
-      if (best >= 16 && 2 * best_n >= ns && ns >= 2 * delta) {
-        S.sched.planes = planes;
-        S.sched.delta = (int32_t)delta;
-        const int64_t per_step = 8 / planes;
-        S.sched.steps_per_group = (int32_t)((delta + per_step - 1) / per_step);
-        const int64_t groups = (ns + planes * delta - 1) / (planes * delta);
-        S.sched.n_steps = (int32_t)(groups * S.sched.steps_per_group);
-      }
-      if (getenv("APDX_TRACE"))
-        fprintf(stderr, "[apdx trace] spmv schedule: planes %d, slices per plane %d (seen in %lld of %lld slices), %d block steps\n",
-                S.sched.planes, S.sched.delta, (long long)best_n, (long long)ns, S.sched.n_steps);
-    }
-  }
   {  // entries read from their transposed position (diagnostics: apdx_plan_sell_info, tests)
     unsigned long long nm = 0;
     APDX_CUDA(cudaMemcpy(&nm, n_mir.p, sizeof(nm), cudaMemcpyDeviceToHost));
