@@ -68,6 +68,8 @@ SIGNATURES = {
     "apdx_assemble": (C.c_int, [_P, _P, C.c_int, _P]),
     "apdx_get_values": (C.c_int, [_P, C.c_int, _P]),
     "apdx_get_coo_values": (C.c_int, [_P, _I64, _I64, _P]),
+    "apdx_plan_set_coarse": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "apdx_plan_set_multigrid": (C.c_int, [_P, _I32, _I32, _I32, _D, _D]),
     "apdx_spmv": (C.c_int, [_P, _P, _P]),
     "apdx_krylov": (C.c_int, [_P, C.POINTER(KrylovOpts), _P, _P, C.POINTER(_I32), C.POINTER(_D)]),
     "apdx_linear_step": (C.c_int, [_P, C.POINTER(KrylovOpts), _P, _P, _P, C.POINTER(_I32)]),

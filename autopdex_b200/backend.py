@@ -161,10 +161,11 @@ class SetSpec:
 
 class KrylovOptions:
     def __init__(self, method="cg", rtol=1e-8, atol=0.0, maxiter=0, jacobi=True, check_every=0):
+        """jacobi: True / False, or the preconditioner by name: 'jacobi', 'none', 'multigrid' (APDX_PRECOND_*)."""
         if method not in _lib.APDX_KRYLOV:
             raise ValueError("'solver' must be 'cg' or 'bicgstab' for the b200 backend, got %r" % (method,))
-        self.c = _lib.KrylovOpts(_lib.APDX_KRYLOV[method], int(maxiter), float(rtol), float(atol),
-                                 1 if jacobi else 0, int(check_every))
+        pc = {"none": 0, "jacobi": 1, "multigrid": 2}[jacobi] if isinstance(jacobi, str) else (1 if jacobi else 0)
+        self.c = _lib.KrylovOpts(_lib.APDX_KRYLOV[method], int(maxiter), float(rtol), float(atol), pc, int(check_every))
 
 
 class Plan:
@@ -297,6 +298,28 @@ class Plan:
         out = np.empty(max(nnz, 1), dtype=np.float64)
         _lib.check(_lib.load().apdx_get_values(self.h, int(reduced), out.ctypes.data_as(C.c_void_p)))
         return out[:nnz]
+
+    def device_bytes_now(self):
+        """Bytes held by ALL plans of this process right now (apdx_plan_query out[7])."""
+        q = (C.c_int64 * 8)()
+        _lib.check(_lib.load().apdx_plan_query(self.h, q))
+        return int(q[7])
+
+    def set_coarse(self, coarse, P, R, inject):
+        """Link `coarse` (a Plan of the same model on the next-coarser mesh) below this plan: P, R = CSR triples
+        (indptr int32, indices int32, data) over the reduced dofs, inject = fine full dof of every coarse full dof."""
+        arrs = [np.ascontiguousarray(P[0], dtype=np.int32), np.ascontiguousarray(P[1], dtype=np.int32),
+                np.ascontiguousarray(P[2], dtype=np.float64), np.ascontiguousarray(R[0], dtype=np.int32),
+                np.ascontiguousarray(R[1], dtype=np.int32), np.ascontiguousarray(R[2], dtype=np.float64),
+                np.ascontiguousarray(inject, dtype=np.int64)]
+        if arrs[0].size != self.n_free + 1 or arrs[3].size != coarse.n_free + 1 or arrs[6].size != coarse.n_dofs:
+            raise ValueError("set_coarse: transfer operators do not match the two plans")
+        _lib.check(_lib.load().apdx_plan_set_coarse(self.h, coarse.h, *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
+        self.coarse = coarse
+
+    def set_multigrid(self, pre=0, post=0, coarsest=0, ratio=0.0, coarsest_ratio=0.0):
+        _lib.check(_lib.load().apdx_plan_set_multigrid(self.h, int(pre), int(post), int(coarsest), float(ratio),
+                                                       float(coarsest_ratio)))
 
     def coo_values(self, offset=0, count=None):
         """Element-tangent entries of the last tangent assembly in the reference's COO order, duplicates not summed

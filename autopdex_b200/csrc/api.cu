@@ -141,6 +141,7 @@ static int assemble_internal(apdx_plan *pl, const double *dofs_d, int tangent_fl
   if (tangent_flags & 4) {
     APDX_CHECK(sell_gather_reduce(pl));
     pl->have_sell_values = true;
+    pl->mg.ready = false;   // a multigrid hierarchy hanging off this plan belongs to the previous tangent
   }
   if (tangent_flags) {
     pl->have_ke = true;
@@ -179,6 +180,21 @@ static float elapsed(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
+// Multigrid set-up after a tangent assembly at dofs_d: smoother data of this level, then the coarser levels' operators
+// re-discretised at the injected state (multigrid.cu)
+static int mg_prepare(apdx_plan *pl, const double *dofs_d) {
+  APDX_CHECK(mg_level_setup(pl));
+  if (apdx_plan *c = pl->mg.coarse) {
+    APDX_CHECK(ensure_newton_buffers(c));
+    APDX_CHECK(mg_inject(pl, dofs_d, c->mg.dofs.p));
+    APDX_CHECK(assemble_internal(c, c->mg.dofs.p, 4, c->residual.p));
+    pl->stats.kernel_launches += c->stats.kernel_launches;
+    c->stats = Stats();
+    APDX_CHECK(mg_prepare(c, c->mg.dofs.p));
+  }
+  return APDX_OK;
+}
+
 // one linear step on dofs (already holding the imposed Dirichlet values): assemble, solve; x_red = delta
 static int linear_step_internal(apdx_plan *pl, const apdx_krylov_opts *opts, const double *dofs_d, int32_t *kiters) {
   cudaStream_t s = pl->stream;
@@ -188,6 +204,7 @@ static int linear_step_internal(apdx_plan *pl, const apdx_krylov_opts *opts, con
   pl->x0_is_zero = true;
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaEventRecord(pl->ev[1], s));
+  if (opts->jacobi == APDX_PRECOND_MULTIGRID) APDX_CHECK(mg_prepare(pl, dofs_d));   // counted with the Krylov time
   int32_t it = 0;
   double rr = 0;
   APDX_CHECK(krylov_solve(pl, opts, pl->rhs_red.p, pl->x_red.p, &it, &rr));
@@ -412,7 +429,8 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
 int apdx_plan_destroy(apdx_plan *pl) {
   if (!pl) return APDX_OK;
   g_plans.erase(std::remove(g_plans.begin(), g_plans.end(), pl), g_plans.end());
-  if (pl->stream) cudaStreamSynchronize(pl->stream);
+  if (pl->stream && !pl->mg.stream_borrowed) cudaStreamSynchronize(pl->stream);
+  pl->mg.release();
   for (auto &st : pl->sets) {
     st.conn.release(); st.shape_n.release(); st.shape_dn.release(); st.gp_w.release();
     st.ip_n.release(); st.ip_dndx.release(); st.ip_w.release();
@@ -433,7 +451,7 @@ int apdx_plan_destroy(apdx_plan *pl) {
   k.flags.release();
   if (pl->pinned) cudaFreeHost(pl->pinned);
   for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
-  if (pl->stream) cudaStreamDestroy(pl->stream);
+  if (pl->stream && !pl->mg.stream_borrowed) cudaStreamDestroy(pl->stream);
   delete pl;
   return APDX_OK;
 }
@@ -672,6 +690,10 @@ int apdx_tangent_solve(apdx_plan *pl, const apdx_krylov_opts *opts, const double
   pl->x0_is_zero = true;
   pl->stats.kernel_launches += 1;
   APDX_CUDA(cudaEventRecord(pl->ev[1], s));
+  if (opts->jacobi == APDX_PRECOND_MULTIGRID && !pl->mg.ready) {
+    APDX_REQUIRE(dofs_d, APDX_ERR_STATE, "multigrid: pass dofs_d (the hierarchy is re-discretised at the state)");
+    APDX_CHECK(mg_prepare(pl, dofs_d));
+  }
   int32_t it = 0;
   double rr = 0;
   APDX_CHECK(krylov_solve(pl, opts, pl->rhs_red.p, pl->x_red.p, &it, &rr));
@@ -739,6 +761,28 @@ int apdx_newton(apdx_plan *pl, const apdx_krylov_opts *opts, double *dofs_d, con
   *iters = itt;
   *res_norm = rn;
   *diverged = div ? 1 : 0;
+  return APDX_OK;
+}
+
+int apdx_plan_set_coarse(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_indptr_h, const int32_t *p_indices_h,
+                         const double *p_data_h, const int32_t *r_indptr_h, const int32_t *r_indices_h,
+                         const double *r_data_h, const int64_t *inject_h) {
+  APDX_REQUIRE(fine && coarse && fine != coarse && p_indptr_h && r_indptr_h && inject_h, APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(p_indptr_h[fine->n_free] == r_indptr_h[coarse->n_free], APDX_ERR_INVALID,
+               "P and R = P^T disagree on the number of entries (%d, %d)", p_indptr_h[fine->n_free], r_indptr_h[coarse->n_free]);
+  return mg_link(fine, coarse, p_indptr_h, p_indices_h, p_data_h, r_indptr_h, r_indices_h, r_data_h, inject_h);
+}
+
+int apdx_plan_set_multigrid(apdx_plan *pl, int32_t pre_degree, int32_t post_degree, int32_t coarsest_degree,
+                            double smoother_ratio, double coarsest_ratio) {
+  APDX_REQUIRE(pl, APDX_ERR_INVALID, "NULL argument");
+  for (apdx_plan *l = pl; l; l = l->mg.coarse) {
+    if (pre_degree > 0) l->mg.pre = pre_degree;
+    if (post_degree > 0) l->mg.post = post_degree;
+    if (coarsest_degree > 0) l->mg.coarsest = coarsest_degree;
+    if (smoother_ratio > 1.0) l->mg.ratio = smoother_ratio;
+    if (coarsest_ratio > 1.0) l->mg.coarsest_ratio = coarsest_ratio;
+  }
   return APDX_OK;
 }
 

@@ -164,6 +164,26 @@ struct Sell {
   }
 };
 
+// ---- multigrid hierarchy (multigrid.cu) ---------------------------------------------------------------------------
+struct CsrDev {
+  int64_t n_rows = 0, nnz = 0;
+  DevBuf<int32_t> ptr, idx;
+  DevBuf<double> val;
+  void release() { ptr.release(); idx.release(); val.release(); n_rows = nnz = 0; }
+};
+struct MgLevel {
+  apdx_plan *coarse = nullptr;     // next coarser level (not owned)
+  bool stream_borrowed = false;    // this plan is a coarse level: it runs on its finer level's stream
+  CsrDev P, R;                     // P [n_free x n_free(coarse)], R = P^T
+  DevBuf<int32_t> inject;          // [n_dofs(coarse)] fine full dof coinciding with each coarse full dof
+  DevBuf<double> x, b, r, d, minv, ev, dofs;   // level work vectors [n_free] (ev: kept power-iteration vector); dofs [n_dofs]: injected state of a coarse level
+  double lmax = 0.0;               // largest eigenvalue of D^-1 A (power iteration after every assembly)
+  int pre = 2, post = 2, coarsest = 12;
+  double ratio = 3.0, coarsest_ratio = 40.0;
+  bool ready = false;              // values, minv and lmax belong to the current tangent
+  void release() { P.release(); R.release(); inject.release(); x.release(); b.release(); r.release(); d.release(); minv.release(); ev.release(); dofs.release(); }
+};
+
 struct Stats {
   double asm_tangent_ms = 0, asm_residual_ms = 0, krylov_ms = 0, total_ms = 0;
   double krylov_iters = 0, spmv_launches = 0, kernel_launches = 0;
@@ -219,6 +239,7 @@ struct apdx_plan {
   apdx::Sell sell;
   apdx::P2P p2p;
   apdx::KrylovGraph kgraph[2];   // [0] CG, [1] BiCGSTAB
+  apdx::MgLevel mg;
   bool have_sell_values = false, have_red_values = false;
   bool x0_is_zero = false;                 // the caller of krylov_solve has just zeroed the whole initial guess
   double *pinned = nullptr;                // small pinned host staging
@@ -259,6 +280,12 @@ int spmv_reduced(apdx_plan *pl, const double *x, double *y);
 int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, double *x,
                  int32_t *iters, double *relres);
 int time_spmv(apdx_plan *pl, int reps, double *ms_avg);
+// multigrid.cu
+int mg_pcg_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, double *x, int32_t *iters, double *relres);
+int mg_level_setup(apdx_plan *pl);     // minv + lambda_max of this level's current sliced-ELL matrix
+int mg_inject(apdx_plan *fine, const double *fine_dofs, double *coarse_dofs);
+int mg_link(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_ptr, const int32_t *p_idx, const double *p_val,
+            const int32_t *r_ptr, const int32_t *r_idx, const double *r_val, const int64_t *inject_h);
 // sell.cu
 int sell_build(apdx_plan *pl);
 int sell_gather_reduce(apdx_plan *pl);

@@ -62,9 +62,15 @@ class _Config:
             raise ValueError("b200 backend: 'solver' must be 'cg' or 'bicgstab' (Jacobi-preconditioned Krylov), got %r"
                              % (self.krylov,))
         pc = _get(static_settings, "type of preconditioner", None)
-        if pc not in (None, "jacobi", "none"):
-            raise ValueError("b200 backend: 'type of preconditioner' %r not supported (jacobi)" % (pc,))
+        if pc not in (None, "jacobi", "none", "multigrid"):
+            raise ValueError("b200 backend: 'type of preconditioner' %r not supported (jacobi, multigrid, none)" % (pc,))
         self.jacobi = pc == "jacobi"
+        # geometric multigrid V-cycle on a hierarchy derived from settings['b200 multigrid'] (multigrid.py), the
+        # device counterpart of the reference's pyamg / PETSc preconditioners (solver.py:1399-1491, 1224-1333)
+        self.multigrid = pc == "multigrid"
+        if self.multigrid and self.krylov != "cg":
+            raise ValueError("b200 backend: 'type of preconditioner': 'multigrid' needs 'solver': 'cg' (symmetric V-cycle)")
+        self.precond = "multigrid" if self.multigrid else ("jacobi" if self.jacobi else "none")
         self.verbose = _get(static_settings, "verbose", 0)
         modes = _get(static_settings, "assembling mode", required=True)
         self.n_sets = len(modes)
@@ -103,8 +109,19 @@ class _Config:
             else:
                 raise ValueError("b200 backend: assembling mode %r of domain %d is not supported "
                                  "(user element, user potential, sparse)" % (mode, i))
-        self.key = (self.solver_type, self.krylov, self.jacobi, self.nodal_imposition, self.shape_mode,
+        self.key = (self.solver_type, self.krylov, self.precond, self.nodal_imposition, self.shape_mode,
                     tuple(id(model_list[i]) for i in range(self.n_sets)), tuple(modes))
+
+
+    def coarse(self, kept):
+        """Configuration of a coarse multigrid level: the kept (domain) sets, Jacobi inside (the level is driven by the
+        V-cycle of the finest plan)."""
+        import copy
+        c = copy.copy(self)
+        c.sets = [self.sets[i] for i in kept]
+        c.n_sets = len(kept)
+        c.multigrid, c.jacobi, c.precond = False, True, "jacobi"
+        return c
 
 
 def validate(static_settings):
@@ -179,6 +196,7 @@ class _State:
                 raise ValueError("b200 backend: dict dofs with %d fields are not supported (single field only)" % len(keys))
             self.dict_key = keys[0]
         d0 = self._unwrap(dofs)
+        self.dofs_ndim = d0.ndim
         coords = np.asarray(self._unwrap(settings["node coordinates"]), dtype=np.float64)
         self.n_nodes, self.dim = coords.shape
         self.nf = 1 if d0.ndim == 1 else d0.shape[-1]
@@ -220,6 +238,71 @@ class _State:
         self.out_d = backend.DeviceArray(n)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.coarse_state = None
+        if cfg.multigrid:
+            self._build_hierarchy(settings)
+
+    # -- multigrid hierarchy (multigrid.py): a chain of coarse _State objects below this one -----------------------
+    def _wrap(self, arr):
+        return {self.dict_key: arr} if self.dict_key is not None else arr
+
+    def _mg_kinds(self):
+        kinds = []
+        for route, m in self.cfg.sets:
+            if route != "element":
+                raise ValueError("b200 backend: the multigrid preconditioner supports isoparametric element sets only")
+            kinds.append(m.kind)
+        return kinds
+
+    def _build_hierarchy(self, settings):
+        from . import multigrid
+        opt = settings.get("b200 multigrid")
+        if not isinstance(opt, Mapping) or "n_elements" not in opt:
+            raise ValueError("b200 backend: 'type of preconditioner': 'multigrid' needs settings['b200 multigrid'] = "
+                             "{'n_elements': (nx, ny[, nz])} (the structured mesh the hierarchy is derived from)")
+        if self.partition:
+            raise ValueError("b200 backend: the multigrid preconditioner runs on one GPU (no 'b200 partition')")
+        shapes = multigrid.level_shapes(opt["n_elements"], opt.get("levels"))
+        if multigrid.node_count(shapes[0]) != self.n_nodes:
+            raise ValueError("b200 backend: settings['b200 multigrid']['n_elements'] = %s does not match the %d nodes"
+                             % (shapes[0], self.n_nodes))
+        self.mg_shape = shapes[0]
+        if len(shapes) > 1:
+            self._mg_cache = {}
+            cs, kept, fine_nodes = multigrid.coarse_level_settings(settings, shapes[0], self._mg_kinds(), self._unwrap, self._wrap,
+                                                                   self._mg_cache)
+            cs["b200 multigrid"] = dict(opt, n_elements=shapes[1], levels=len(shapes) - 1)
+            ccfg = self.cfg.coarse(kept)
+            ccfg.multigrid = True                                    # recurse: the coarse state builds its own coarse level
+            n_c = multigrid.node_count(shapes[1])
+            d_c = self._wrap(np.zeros((n_c, self.nf)) if self.dofs_ndim > 1 else np.zeros(n_c))
+            self.coarse_state = _State(ccfg, d_c, cs)
+            free_f = np.ones((self.n_nodes, self.nf), dtype=bool) if self.mask is None else ~self.mask.reshape(self.n_nodes, self.nf)
+            cm = self.coarse_state.mask
+            free_c = np.ones((n_c, self.nf), dtype=bool) if cm is None else ~cm.reshape(n_c, self.nf)
+            P, R = multigrid.prolongation(shapes[0], self.nf, free_f, free_c)
+            inject = (fine_nodes[:, None] * self.nf + np.arange(self.nf)).ravel()
+            self.plan.set_coarse(self.coarse_state.plan, P, R, inject)
+            self.mg_kept = kept
+        self.plan.set_multigrid(opt.get("pre", 0), opt.get("post", 0), opt.get("coarsest", 0), opt.get("ratio", 0.0),
+                                opt.get("coarsest ratio", 0.0))
+
+    def update_coarse_fields(self, settings):
+        """Per-call upload of the coarse levels' fields (injected coordinates, coefficient values at the coarse Gauss
+        points, 'dofs n')."""
+        if self.coarse_state is None:
+            return
+        from . import multigrid
+        cs, _, _ = multigrid.coarse_level_settings(settings, self.mg_shape, self._mg_kinds(), self._unwrap, self._wrap,
+                                                   self._mg_cache)
+        self.coarse_state.update_fields(cs)
+        self.h2d_bytes += self.coarse_state.h2d_bytes
+
+    def destroy(self):
+        if self.coarse_state is not None:
+            self.coarse_state.destroy()
+            self.coarse_state = None
+        self.plan.destroy()
 
     def _unwrap(self, x):
         if isinstance(x, Mapping):
@@ -268,6 +351,7 @@ class _State:
                 dn = np.asarray(settings["dofs n"], dtype=np.float64)
                 plan.set_dofs_n(dn)
                 self.h2d_bytes += dn.nbytes
+        self.update_coarse_fields(settings)
 
     def _upload_intpoint_tables(self, i, settings, conn, coords, x_int):
         w = np.asarray(settings["integration weights"][i], dtype=np.float64)
@@ -299,7 +383,7 @@ def _state_for(cfg, dofs, settings):
         _PLAN_CACHE[key] = st
         while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
             _, old = _PLAN_CACHE.popitem(last=False)
-            old.plan.destroy()
+            old.destroy()
     else:
         _PLAN_CACHE.move_to_end(key)
     return st
@@ -308,7 +392,7 @@ def _state_for(cfg, dofs, settings):
 def clear_plan_cache():
     while _PLAN_CACHE:
         _, old = _PLAN_CACHE.popitem()
-        old.plan.destroy()
+        old.destroy()
 
 
 def _warn_unconverged(stats, where):
@@ -342,7 +426,7 @@ def solver(dofs, settings, static_settings, newton_tol=1e-8, maxiter=30, damping
         st.vals_d.upload(dv.ravel())
         st.h2d_bytes += dv.nbytes
         vals_d = st.vals_d
-    opts = backend.KrylovOptions(cfg.krylov, rtol=tol, atol=atol, maxiter=krylov_maxiter, jacobi=cfg.jacobi)
+    opts = backend.KrylovOptions(cfg.krylov, rtol=tol, atol=atol, maxiter=krylov_maxiter, jacobi=cfg.precond)
 
     def wrap(flat):
         arr = flat.reshape(d0.shape)
@@ -392,7 +476,7 @@ def tangent_solve(dofs, rhs, settings, static_settings, transpose=False, tol=1e-
     st.dofs_d.upload(d0.ravel())
     st.vals_d.upload(r0.ravel())                               # staging buffer of the same size
     st.h2d_bytes += d0.nbytes + r0.nbytes
-    opts = backend.KrylovOptions(cfg.krylov, rtol=tol, atol=atol, maxiter=krylov_maxiter, jacobi=cfg.jacobi)
+    opts = backend.KrylovOptions(cfg.krylov, rtol=tol, atol=atol, maxiter=krylov_maxiter, jacobi=cfg.precond)
     plan.tangent_solve(opts, st.dofs_d, st.vals_d, st.out_d, transpose=transpose)
     out = st.out_d.download().reshape(d0.shape)
     st.d2h_bytes = out.nbytes

@@ -304,6 +304,53 @@ def vector_problem_figures(args, hbm, fp64_peak, n=64):
     return out
 
 
+def multigrid_figures(args, sol_jacobi):
+    """The same Newton step with 'type of preconditioner': 'multigrid' (opt-in: the headline above
+    is BASELINE's Jacobi-PCG): geometric V-cycle on the structured hierarchy M^3 -> (M/2)^3 -> ..., Chebyshev smoothing,
+    re-discretised coarse operators.  Device-resident step time, end-to-end time through solver.solver, and the distance
+    of its solution from the Jacobi-PCG one."""
+    from autopdex_b200 import backend, solver
+    solver.clear_plan_cache()                     # the Jacobi plan's 70 GB go first
+    m = args.size
+    settings, static_settings, _ = build_problem(m, 0, 1)
+    static_settings = dict(static_settings, **{"type of preconditioner": "multigrid"})
+    settings["b200 multigrid"] = {"n_elements": (m, m, m)}
+    dofs0 = np.zeros((settings["node coordinates"].shape[0], 1))
+    t = time.perf_counter()
+    sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)
+    t_build = time.perf_counter() - t
+    for _ in range(2):
+        sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)
+    e2e_ms = (time.perf_counter() - t) / args.steps * 1e3
+    st = dict(solver.last_stats)
+    state = next(iter(solver._PLAN_CACHE.values()))
+    opts = backend.KrylovOptions("cg", rtol=args.rtol, jacobi="multigrid")
+    step, kry, its = [], [], []
+    for i in range(args.warmup + args.steps):
+        state.dofs_d.zero()
+        state.plan.newton(opts, state.dofs_d, state.vals_d, 1e-8, 30, 1.0)
+        q = state.plan.stats()
+        if i >= args.warmup:
+            step.append(q["total_ms"]); kry.append(q["krylov_ms"]); its.append(q["krylov_iters"])
+    levels, stt = 0, state
+    while stt is not None:
+        levels, stt = levels + 1, stt.coarse_state
+    dev_gb = state.plan.device_bytes_now() / 1e9
+    diff = float(np.linalg.norm(np.asarray(sol).ravel() - np.asarray(sol_jacobi).ravel()) / np.linalg.norm(np.asarray(sol_jacobi).ravel()))
+    out = {"workload": workload_name(m, args.rtol, 1).replace("Jacobi-PCG", "multigrid-PCG"),
+           "newton_step_ms": float(np.mean(step)), "elements_per_s": m ** 3 / (float(np.mean(step)) * 1e-3),
+           "e2e_ms_per_step": e2e_ms, "krylov_ms": float(np.mean(kry)), "krylov_iterations": float(np.mean(its)),
+           "levels": levels, "hierarchy_build_s_first_call": t_build, "newton_steps": info[0], "res_norm": info[1],
+           "rel_l2_vs_jacobi_pcg_solution": diff, "h2d_bytes_per_step": int(st["h2d_bytes"]), "plan_device_gb": dev_gb,
+           "note": "krylov_ms includes the per-step set-up (coarse operators re-assembled at the injected state, power "
+                   "iteration for the Chebyshev bounds)"}
+    solver.clear_plan_cache()
+    return out
+
+
 # ---- own arm -----------------------------------------------------------------------------------------------------
 def run_b200(args):
     from autopdex_b200 import backend, solver
@@ -447,6 +494,8 @@ def run_b200(args):
         "vector_problem": vector,
         "system": {"n_free": nfree, "nnz_reduced": nnz, "plan_device_gb": plan.device_bytes / 1e9},
     }
+    if world == 1 and not args.no_multigrid:
+        line["multigrid"] = multigrid_figures(args, sol)
     if world == 1 and not args.no_cpu:
         threads = host_threads()
         mref, _ = pick_ref_size(1, 25.0, args.ref_size, threads)
@@ -473,6 +522,7 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="time bound of the whole --impl reference run")
     ap.add_argument("--ref-direct", action="store_true", help="--impl reference: also time spsolve on a 32^3 sample")
     ap.add_argument("--no-vector", action="store_true", help="skip the bounded 64^3 neo-Hooke figures")
+    ap.add_argument("--no-multigrid", action="store_true", help="skip the multigrid-preconditioned variant of the step")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nx", type=int, default=0, help="diagnostic: elements along the slowest index (default: --size)")

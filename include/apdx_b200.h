@@ -76,6 +76,7 @@ enum {
 };
 
 enum { APDX_KRYLOV_CG = 0, APDX_KRYLOV_BICGSTAB = 1 };
+enum { APDX_PRECOND_NONE = 0, APDX_PRECOND_JACOBI = 1, APDX_PRECOND_MULTIGRID = 2 };
 
 typedef struct apdx_plan apdx_plan;
 
@@ -103,7 +104,8 @@ typedef struct {
   int32_t maxiter;   /* kwargs maxiter of linear_solve_jax, solver.py:1116 */
   double rtol;       /* ||r|| <= max(rtol*||b||, atol), as jax.scipy.sparse.linalg.cg */
   double atol;
-  int32_t jacobi;    /* 1: 'type of preconditioner': 'jacobi' (solver.py:1093-1099) */
+  int32_t jacobi;    /* APDX_PRECOND_*: 1 = 'type of preconditioner': 'jacobi' (solver.py:1093-1099), 0 = none,
+                        2 = multigrid V-cycle over the hierarchy linked with apdx_plan_set_coarse (method must be CG) */
   int32_t check_every; /* iterations between host convergence polls (0 = default) */
 } apdx_krylov_opts;
 
@@ -190,6 +192,22 @@ int apdx_newton(apdx_plan *plan, const apdx_krylov_opts *opts, double *dofs_d,
  * in-scope tangent is symmetric (that is what the symmetric sliced-ELL storage relies on), so it is the same solve.   */
 int apdx_tangent_solve(apdx_plan *plan, const apdx_krylov_opts *opts, const double *dofs_d, const double *rhs_d,
                        int transpose, double *out_d, int32_t *krylov_iters);
+/* ---- multigrid preconditioner (row N4 of SURVEY.md 8f) --------------------------------------------------------------
+ * The reference's stronger-than-Jacobi preconditioners are algebraic multigrid through pyamg (autopdex/solver.py:1399-1491)
+ * and PETSc's pc types (solver.py:1224-1333), both on the host.  Here: a geometric V-cycle on a hierarchy of plans of the
+ * same model on coarser meshes (re-discretised coarse operators, assembled by the same element kernels at the injected
+ * state), Chebyshev-accelerated Jacobi smoothing, used as the preconditioner of CG (APDX_PRECOND_MULTIGRID).
+ * apdx_plan_set_coarse links `coarse` as the next-coarser level of `fine`:
+ *   P (prolongation, CSR over the REDUCED dofs: n_free(fine) rows x n_free(coarse) columns), R = P^T (CSR, n_free(coarse)
+ *   rows), inject[d] = the fine full dof id that coincides with coarse full dof d (state transfer, n_dofs(coarse) entries).
+ * The coarse plan then runs on the fine plan's stream; it must outlive the fine plan's solves and is not owned by it.
+ * apdx_plan_set_multigrid: Chebyshev degree of the pre- and post-smoother, of the coarsest-level solve, and the ratios
+ * lambda_max / lambda_min of the smoothing and coarsest intervals (values <= 0 keep the defaults 2, 2, 12, 3, 40).      */
+int apdx_plan_set_coarse(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_indptr_h, const int32_t *p_indices_h,
+                         const double *p_data_h, const int32_t *r_indptr_h, const int32_t *r_indices_h,
+                         const double *r_data_h, const int64_t *inject_h);
+int apdx_plan_set_multigrid(apdx_plan *plan, int32_t pre_degree, int32_t post_degree, int32_t coarsest_degree,
+                            double smoother_ratio, double coarsest_ratio);
 /* timings (ms, CUDA events) and counters of the last apdx_newton / apdx_linear_step:
  * out[0]=assembly(tangent+residual) out[1]=assembly(residual only) out[2]=krylov
  * out[3]=krylov iterations out[4]=spmv launches out[5]=total out[6]=kernel launches

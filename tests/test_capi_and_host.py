@@ -351,3 +351,42 @@ def test_get_indices_array_and_dict_block_order():
                 gj = (off[fj] + cn[fj][e][:, None] * nfd[fj] + np.arange(nfd[fj])).ravel()
                 want.append(np.stack([np.repeat(gi, gj.size), np.tile(gj, gi.size)], axis=-1))
     assert np.array_equal(got, np.concatenate(want))
+
+
+def test_multigrid_transfer_operators_match_kron_interpolation():
+    """multigrid.prolongation (row-by-row construction on the free dofs) against kron(P1x, P1y[, P1z]) x I_nf restricted
+    to the free rows / columns; coarse meshes are the structured meshes of the halved element counts."""
+    import scipy.sparse as sp
+    from autopdex_b200 import mesher, multigrid as mg
+
+    def p1(n):
+        P = np.zeros((n + 1, n // 2 + 1))
+        for a in range(n + 1):
+            if a % 2 == 0:
+                P[a, a // 2] = 1.0
+            else:
+                P[a, a // 2] = P[a, a // 2 + 1] = 0.5
+        return sp.csr_matrix(P)
+
+    assert mg.level_shapes((16, 8, 8)) == [(16, 8, 8), (8, 4, 4), (4, 2, 2)]
+    assert mg.level_shapes((16, 16), levels=2) == [(16, 16), (8, 8)]
+    quad = [[0., 0.], [2., 0.], [2.5, 1.], [0., 1.]]
+    cube = [[0., 0., 0.], [1., 0., 0.], [1., 1., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 1.], [1., 1., 1.], [0., 1., 1.]]
+    for shape, nf in (((4, 6), 1), ((4, 2, 6), 3), ((8, 4, 4), 1), ((6, 4), 2)):
+        Pk = p1(shape[0])
+        for n in shape[1:]:
+            Pk = sp.kron(Pk, p1(n))
+        Pk = sp.kron(Pk, sp.identity(nf)).tocsr()
+        rng = np.random.default_rng(0)
+        ff = rng.random((mg.node_count(shape), nf)) > 0.2
+        fc = ff[mg.fine_node_ids(shape)]
+        (ip, ix, dt), (rp, ri, rd) = mg.prolongation(shape, nf, ff, fc)
+        P = sp.csr_matrix((dt, ix, ip), shape=(ff.sum(), fc.sum()))
+        assert abs(P - Pk[ff.ravel()][:, fc.ravel()]).max() == 0.0
+        assert abs(sp.csr_matrix((rd, ri, rp), shape=(fc.sum(), ff.sum())) - P.T).max() == 0.0
+        assert ip.dtype == np.int32 and ix.dtype == np.int32
+        verts, et = (quad, "quad") if len(shape) == 2 else (cube, "brick")
+        c, e = mesher.structured_mesh(shape, verts, et)
+        assert np.array_equal(e, mg.structured_connectivity(shape))
+        cc, _ = mesher.structured_mesh(tuple(n // 2 for n in shape), verts, et)
+        assert np.allclose(cc, c[mg.fine_node_ids(shape)])      # injected coordinates = the coarse structured mesh

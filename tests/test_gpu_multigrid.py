@@ -1,0 +1,111 @@
+"""GPU parity of the multigrid-preconditioned CG ('type of preconditioner': 'multigrid'; the
+reference's analogue: pyamg / PETSc preconditioners, autopdex/solver.py:1399-1491, 1224-1333) through the public API:
+same Newton counts and solutions as the oracle ('scipy'/'lapack' path) and as the Jacobi-PCG of the same backend, in
+far fewer Krylov iterations."""
+import numpy as np
+import pytest
+
+from oracle import solve as osolve
+from tests import problems
+
+pytestmark = pytest.mark.gpu
+
+
+def _poisson(m, pc, levels=None):
+    import bench
+    settings, static_settings, _ = bench.build_problem(m, 0, 1)
+    static_settings = dict(static_settings, **{"type of preconditioner": pc})
+    if pc == "multigrid":
+        settings["b200 multigrid"] = {"n_elements": (m, m, m)} if levels is None else {"n_elements": (m, m, m), "levels": levels}
+    return settings, static_settings
+
+
+@pytest.mark.parametrize("m", [8, 16, 24])
+def test_poisson_hex_multigrid_matches_oracle(m):
+    from autopdex_b200 import solver
+    p = problems.poisson_hex(m)
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+    ref, (rsteps, _, rdiv) = osolve.damped_newton(prob, np.zeros(p["mask"].shape))
+    out = {}
+    for pc in ("jacobi", "multigrid"):
+        settings, static_settings = _poisson(m, pc)
+        sol, (steps, res, div) = solver.solver(np.zeros(p["mask"].shape), settings, static_settings, tol=1e-10)
+        assert steps == rsteps and not div and res < 1e-8
+        assert np.linalg.norm(np.asarray(sol).ravel() - ref.ravel()) / np.linalg.norm(ref) < 1e-8
+        out[pc] = int(solver.last_stats["krylov_iters"])
+        assert solver.last_stats["krylov_converged"]
+    assert out["multigrid"] <= 14, out                      # mesh-independent
+    assert m < 16 or out["multigrid"] * 3 <= out["jacobi"], out
+    solver.clear_plan_cache()
+
+
+def test_multigrid_two_level_and_options():
+    from autopdex_b200 import solver
+    p = problems.poisson_hex(16)
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+    ref, _ = osolve.damped_newton(prob, np.zeros(p["mask"].shape))
+    settings, static_settings = _poisson(16, "multigrid", levels=2)
+    settings["b200 multigrid"].update({"pre": 3, "post": 3, "coarsest": 40, "coarsest ratio": 200.0})
+    sol, (steps, res, div) = solver.solver(np.zeros(p["mask"].shape), settings, static_settings, tol=1e-12)
+    assert steps == 1 and not div
+    assert np.linalg.norm(np.asarray(sol).ravel() - ref.ravel()) / np.linalg.norm(ref) < 1e-9
+    solver.clear_plan_cache()
+
+
+def test_neo_hooke_brick_multigrid_newton_counts():
+    """nf = 3, a domain and a surface set (the surface set lives on the finest level only), nonlinear: the coarse
+    tangents are re-discretised at the injected state in every Newton step."""
+    from autopdex_b200 import solver
+    from tests.multi_gpu_worker import neohooke_api_problem
+    m = 8
+    p = problems.neo_hooke_brick(m)
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+    ref, (rsteps, _, rdiv) = osolve.damped_newton(prob, np.zeros(p["mask"].shape))
+    static_settings = dict(neohooke_api_problem(p), solver="cg", **{"type of preconditioner": "multigrid"})
+    settings = {"connectivity": tuple(s["conn"] for s in p["sets"]), "node coordinates": p["coords"], "dirichlet dofs": p["mask"],
+                "dirichlet conditions": p["values"], "b200 multigrid": {"n_elements": (m, m, m)}}
+    sol, (steps, res, div) = solver.solver(np.zeros(p["mask"].shape), settings, static_settings, tol=1e-12)
+    assert steps == rsteps and div == rdiv
+    assert np.linalg.norm(np.asarray(sol).ravel() - ref.ravel()) / np.linalg.norm(ref) < 1e-8
+    solver.clear_plan_cache()
+
+
+def test_readme_quad_potential_multigrid():
+    """2-D, dict dofs, 'user potential' route (README): 16 x 16 Q1 quads."""
+    from autopdex_b200 import mesher, models, seeder, solver, spaces, utility
+    n = 16
+    pts = [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]
+    coords, elems = mesher.structured_mesh((n, n), pts, "quad")
+    p = problems.readme_poisson(n)
+    dirichlet_dofs = {"phi": p["mask"][:, 0]}
+    integrand = models.poisson_potential("phi", source_fun=problems.readme_source)
+    pot = models.mixed_reference_domain_potential(integrand, {"phi": spaces.fem_iso_line_quad_brick},
+                                                  *seeder.gauss_legendre_nd(dimension=2, order=2), "phi")
+    sols = {}
+    for pc in ("jacobi", "multigrid"):
+        static_settings = {"assembling mode": ("user potential",), "solution structure": ("nodal imposition",),
+                           "model": (pot,), "solver type": "newton", "solver backend": "b200", "solver": "cg",
+                           "type of preconditioner": pc, "verbose": -1}
+        settings = {"connectivity": ({"phi": elems},), "dirichlet dofs": dirichlet_dofs, "node coordinates": {"phi": coords},
+                    "dirichlet conditions": utility.dict_zeros_like(dirichlet_dofs, dtype=np.float64),
+                    "b200 multigrid": {"n_elements": (n, n)}}
+        sol, infos = solver.solver(utility.dict_zeros_like(dirichlet_dofs, dtype=np.float64), settings, static_settings, tol=1e-12)
+        assert infos[0] == 1 and not infos[2]
+        sols[pc] = sol["phi"]
+    assert np.linalg.norm(sols["multigrid"] - sols["jacobi"]) / np.linalg.norm(sols["jacobi"]) < 1e-9
+    solver.clear_plan_cache()
+
+
+def test_multigrid_rejections():
+    from autopdex_b200 import solver
+    settings, static_settings = _poisson(8, "multigrid")
+    with pytest.raises(ValueError):
+        solver.solver(np.zeros((9 ** 3, 1)), settings, dict(static_settings, solver="bicgstab"))
+    s2 = dict(settings)
+    s2.pop("b200 multigrid")
+    with pytest.raises(ValueError):
+        solver.solver(np.zeros((9 ** 3, 1)), s2, static_settings)
+    s3 = dict(settings, **{"b200 multigrid": {"n_elements": (8, 8, 4)}})
+    with pytest.raises(ValueError):
+        solver.solver(np.zeros((9 ** 3, 1)), s3, static_settings)
+    solver.clear_plan_cache()

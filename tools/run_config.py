@@ -113,14 +113,25 @@ def heat(n, steps):
             "theta_sum": float(dofs.sum()), "theta_max": float(dofs.max()), **solver.last_stats}
 
 
-def poisson(n):
+def poisson(n, precond="jacobi", pre=0, post=0, coarsest=0, ratio=0, coarsest_ratio=0, levels=0):
+    """python tools/run_config.py poisson 256 multigrid [pre post coarsest ratio coarsest_ratio levels]"""
     import bench
     settings, st, _ = bench.build_problem(n, 0, 1)
+    st = dict(st, **{"type of preconditioner": precond})
+    if precond == "multigrid":
+        settings["b200 multigrid"] = {"n_elements": (n, n, n), "pre": pre, "post": post, "coarsest": coarsest,
+                                      "ratio": float(ratio), "coarsest ratio": float(coarsest_ratio)}
+        if levels:
+            settings["b200 multigrid"]["levels"] = levels
     dofs = np.zeros((settings["node coordinates"].shape[0], 1))
+    t = time.perf_counter()
+    solver.solver(dofs, settings, st, tol=1e-8)
+    t_first = time.perf_counter() - t
     solver.solver(dofs, settings, st, tol=1e-8)
     t = time.perf_counter()
     sol, info = solver.solver(dofs, settings, st, tol=1e-8)
-    return {"config": "3D Poisson %d^3 hex8, Newton + Jacobi-PCG 1e-8" % n, "e2e_ms": (time.perf_counter() - t) * 1e3,
+    return {"config": "3D Poisson %d^3 hex8, Newton + %s-PCG 1e-8" % (n, precond), "e2e_ms": (time.perf_counter() - t) * 1e3,
+            "first_call_s": t_first, "mg": settings.get("b200 multigrid"),
             "newton": list(map(float, info)), "sum": float(sol.sum()), **solver.last_stats}
 
 
