@@ -68,6 +68,7 @@ SIGNATURES = {
     "apdx_assemble": (C.c_int, [_P, _P, C.c_int, _P]),
     "apdx_get_values": (C.c_int, [_P, C.c_int, _P]),
     "apdx_get_coo_values": (C.c_int, [_P, _I64, _I64, _P]),
+    "apdx_plan_newton_history": (C.c_int, [_P, _P, _I32, C.POINTER(_I32)]),
     "apdx_plan_set_coarse": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "apdx_plan_set_multigrid": (C.c_int, [_P, _I32, _I32, _I32, _D, _D]),
     "apdx_spmv": (C.c_int, [_P, _P, _P]),

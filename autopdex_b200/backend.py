@@ -299,6 +299,13 @@ class Plan:
         _lib.check(_lib.load().apdx_get_values(self.h, int(reduced), out.ctypes.data_as(C.c_void_p)))
         return out[:nnz]
 
+    def newton_history(self):
+        """Residual norms after every iteration of the last newton() call."""
+        n = C.c_int32(0)
+        buf = np.zeros(64)
+        _lib.check(_lib.load().apdx_plan_newton_history(self.h, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(n)))
+        return buf[:min(n.value, buf.size)].copy()
+
     def device_bytes_now(self):
         """Bytes held by ALL plans of this process right now (apdx_plan_query out[7])."""
         q = (C.c_int64 * 8)()

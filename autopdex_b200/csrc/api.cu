@@ -349,7 +349,7 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
     return fail(APDX_ERR_CUDA);
   }
   pl->sets.resize(n_sets);
-  int64_t coo = 0, res = 0;
+  int64_t coo = 0, res = 0, kes = 0;
   for (int i = 0; i < n_sets; ++i) {
     SetData &st = pl->sets[i];
     st.d = sets[i];
@@ -357,6 +357,9 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
     st.soa = fast_kernel_applies(dim, nf, st.d);
     st.coo_offset = coo;
     st.res_offset = res;
+    st.ke_offset = kes;
+    // element-matrix stream: register-kernel sets store the upper triangle only (pattern.cu: soa_address)
+    kes += st.d.n_rows * (int64_t)(st.soa ? st.ndof_e * (st.ndof_e + 1) / 2 : st.ndof_e * st.ndof_e);
     coo += st.d.n_rows * (int64_t)st.ndof_e * st.ndof_e;
     res += st.d.n_rows * (int64_t)st.ndof_e;
     const int64_t cn = st.d.n_rows * st.d.nen;
@@ -403,14 +406,15 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
     st.d.conn_h = nullptr; st.d.shape_n_h = st.d.shape_dn_h = st.d.gp_w_h = nullptr;
   }
   pl->n_coo = coo;
+  pl->n_ke = kes;
   pl->n_res = res;
   if (coo == 0) {
     set_error("no element in any set");
     return fail(APDX_ERR_INVALID);
   }
   if ((rc = build_pattern(pl, dirichlet_mask_h)) != APDX_OK) return fail(rc);
-  if ((rc = pl->ke.alloc(pl->n_coo)) != APDX_OK || (rc = pl->re.alloc(pl->n_res)) != APDX_OK ||
-      (rc = pl->vals.alloc(pl->nnz)) != APDX_OK || (rc = pl->red_vals.alloc(pl->nnz_red > 0 ? pl->nnz_red : 1)) != APDX_OK)
+  // vals / red_vals (CSR-ordered copies for apdx_assemble / apdx_get_values) are allocated on first use (elements.cu)
+  if ((rc = pl->ke.alloc(pl->n_ke > 0 ? pl->n_ke : 1)) != APDX_OK || (rc = pl->re.alloc(pl->n_res)) != APDX_OK)
     return fail(rc);
   // surface sets never write their (all-zero) tangent block: zero the stream once
   cudaMemsetAsync(pl->ke.p, 0, pl->ke.bytes(), pl->stream);
@@ -437,7 +441,7 @@ int apdx_plan_destroy(apdx_plan *pl) {
     for (auto &p : st.params) p.release();
   }
   pl->coords.release(); pl->dofs_n.release(); pl->mask.release(); pl->free_id.release(); pl->free_list.release();
-  pl->row_ptr.release(); pl->col.release(); pl->elem_map.release(); pl->perm.release(); pl->seg_ptr.release();
+  pl->row_ptr.release(); pl->col.release(); pl->perm.release(); pl->seg_ptr.release();
   pl->rperm.release(); pl->rseg_ptr.release(); pl->red_row_ptr.release(); pl->red_col.release();
   pl->red2full.release(); pl->red_diag.release(); pl->ke.release(); pl->re.release(); pl->vals.release();
   for (auto &g : pl->kgraph) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -485,7 +489,16 @@ int apdx_plan_get_csr(const apdx_plan *pl, int reduced, int64_t *indptr_h, int64
 int apdx_plan_get_elem_map(const apdx_plan *pl, int64_t offset, int64_t count, int64_t *pos_h) {
   APDX_REQUIRE(pl && pos_h, APDX_ERR_INVALID, "NULL argument");
   APDX_REQUIRE(offset >= 0 && count >= 0 && offset + count <= pl->n_coo, APDX_ERR_INVALID, "range outside the COO stream");
-  return copy_i32_as_i64(pl->elem_map.p + offset, count, pos_h);
+  const int64_t chunk = 1ll << 24;
+  apdx::DevBuf<int32_t> tmp;
+  APDX_CHECK(tmp.alloc(std::min<int64_t>(chunk, std::max<int64_t>(count, 1))));
+  for (int64_t o = 0; o < count; o += chunk) {
+    const int64_t c = std::min<int64_t>(chunk, count - o);
+    APDX_CHECK(apdx::elem_map_export(pl, offset + o, c, tmp.p));
+    APDX_CUDA(cudaStreamSynchronize(pl->stream));
+    APDX_CHECK(copy_i32_as_i64(tmp.p, c, pos_h + o));
+  }
+  return APDX_OK;
 }
 
 // ---- fields ------------------------------------------------------------------------------------------
@@ -721,6 +734,7 @@ int apdx_newton(apdx_plan *pl, const apdx_krylov_opts *opts, double *dofs_d, con
   int32_t itt = 0;
   bool not_stop = true, div = false;
   double rn = 0.0;
+  pl->newton_history.clear();
   while (not_stop) {
     const double rn_old = rn;
     // --- lin_solve_fun: impose Dirichlet values, assemble, solve (solver.py:586-656) ---
@@ -741,6 +755,7 @@ int apdx_newton(apdx_plan *pl, const apdx_krylov_opts *opts, double *dofs_d, con
     APDX_CHECK(residual_norm(pl, pl->residual.p, &rn2));
     pl->stats.asm_residual_ms += elapsed(pl->ev[0], pl->ev[1]);
     rn = sqrt(rn2);
+    pl->newton_history.push_back(rn);   // "Residual after Newton iteration {itt+1}" (solver.py:906-909)
     not_stop = rn > newton_tol;  // :904 (NaN compares false, handled by the divergence flag below)
     bool next_step;
     if (itt < maxiter) {  // :930
@@ -800,6 +815,13 @@ int apdx_plan_stats(const apdx_plan *pl, double out[8]) {
   out[3] = pl->stats.krylov_iters; out[4] = pl->stats.spmv_launches; out[5] = pl->stats.total_ms;
   out[6] = pl->stats.kernel_launches;
   out[7] = (double)(pl->sell.n_val * 8 + pl->sell.n_idx * 4 + pl->sell.n_slices * 24);  // bytes of the sliced-ELL matrix
+  return APDX_OK;
+}
+
+int apdx_plan_newton_history(const apdx_plan *pl, double *res_norms, int32_t capacity, int32_t *count) {
+  APDX_REQUIRE(pl && count && (res_norms || capacity == 0), APDX_ERR_INVALID, "NULL argument");
+  *count = (int32_t)pl->newton_history.size();
+  for (int32_t i = 0; i < *count && i < capacity; ++i) res_norms[i] = pl->newton_history[(size_t)i];
   return APDX_OK;
 }
 

@@ -42,6 +42,17 @@ struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
   bool owned = true;
+  DevBuf() = default;
+  // Scope-bound: a buffer that goes out of scope frees its memory (the build passes use many temporaries; before this
+  // destructor existed the ones without an explicit release() leaked ~30 GB per 256^3 plan).  Move-only.
+  ~DevBuf() { release(); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; o.owned = true; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; o.owned = true; }
+    return *this;
+  }
   int alloc(size_t count);
   void release();
   void adopt(T *ptr, size_t count) {  // non-owning alias (vectors living in the peer-to-peer heap)
@@ -91,7 +102,8 @@ struct ParamView {
 struct SetData {
   apdx_set_desc d{};          // host copy of the descriptor (pointers invalid after create)
   int32_t ndof_e = 0;         // nen * nf
-  int64_t coo_offset = 0;     // offset of this set's block in the COO / Ke stream
+  int64_t coo_offset = 0;     // offset of this set's block in the reference-order COO numbering
+  int64_t ke_offset = 0;      // offset of this set's block in the element-matrix stream `ke` (upper triangle only for soa sets)
   int64_t res_offset = 0;     // offset of this set's block in the Re stream
   bool soa = false;           // element streams stored entry-major (sets handled by the register kernels)
   DevBuf<int32_t> conn;       // [n_rows][nen]
@@ -199,7 +211,7 @@ int sm_count();   // multiprocessors of the current device (grids are sized in m
 
 struct apdx_plan {
   int32_t dim = 0, nf = 0, n_sets = 0;
-  int64_t n_nodes = 0, n_dofs = 0, n_free = 0, nnz = 0, nnz_red = 0, n_coo = 0, n_res = 0;
+  int64_t n_nodes = 0, n_dofs = 0, n_free = 0, nnz = 0, nnz_red = 0, n_coo = 0, n_ke = 0, n_res = 0;
   std::vector<apdx::SetData> sets;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4]{};
@@ -216,7 +228,6 @@ struct apdx_plan {
 
   // full CSR pattern + element map + gather lists of the deterministic scatter
   apdx::DevBuf<int32_t> row_ptr, col;      // [n_dofs+1], [nnz]
-  apdx::DevBuf<int32_t> elem_map;          // [n_coo] -> position in full CSR data
   apdx::DevBuf<uint32_t> perm;             // [n_coo] COO entries grouped by CSR entry
   apdx::DevBuf<int32_t> seg_ptr;           // [nnz+1] hmm: n_coo < 2^31 required
   apdx::DevBuf<uint32_t> rperm;            // [n_res] element-vector entries grouped by dof
@@ -244,6 +255,7 @@ struct apdx_plan {
   bool x0_is_zero = false;                 // the caller of krylov_solve has just zeroed the whole initial guess
   double *pinned = nullptr;                // small pinned host staging
   apdx::Stats stats;
+  std::vector<double> newton_history;      // residual norm after every step of the last apdx_newton
 
   // partition (multi-GPU)
   int64_t owned_begin = 0, owned_end = 0;  // local dof range
@@ -269,6 +281,7 @@ void drop_all_krylov_graphs();
 // pattern.cu
 int build_pattern(apdx_plan *pl, const uint8_t *mask_h);
 int coo_export(apdx_plan *pl, int64_t offset, int64_t count, double *dst_d);
+int elem_map_export(const apdx_plan *pl, int64_t offset, int64_t count, int32_t *dst_d);
 // elements_fast.cu
 bool fast_kernel_applies(int dim, int nf, const apdx_set_desc &d);
 // elements.cu

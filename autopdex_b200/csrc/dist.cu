@@ -210,12 +210,15 @@ static void p2p_free_parked() {
   g_parked.clear();
 }
 
-// APDX_COMM=mbox: dot-product all-reduces through peer-memory mailboxes (k_allreduce_mbox_apply, krylov.cu); the
-// default (nccl) uses ncclAllReduce.  Collective: every rank of the communicator must call it.
+// Dot-product all-reduces of the Krylov loop through peer-memory mailboxes over NVLink (k_allreduce_mbox_apply,
+// krylov.cu) -- the default since round 2: 256^3 Newton step 145.3 -> 143.7 ms on 2, 89.3 -> 86.1 ms on 4 and
+// 65.9 -> 58.0 ms on 8 B200s against ncclAllReduce + a one-thread stage kernel (profiles/r02b_bench_n{2,4,8}*_sample.json).
+// APDX_COMM=nccl keeps the NCCL all-reduce; if CUDA IPC peer mapping is unavailable every rank stays on NCCL (collective
+// decision below).  Collective: every rank of the communicator must call it.
 int p2p_setup(apdx_plan *pl) {
   P2P &P = pl->p2p;
   const char *mode = getenv("APDX_COMM");
-  const bool mbox = mode && strcmp(mode, "mbox") == 0;
+  const bool mbox = !(mode && strcmp(mode, "nccl") == 0);
   if (!mbox) return APDX_OK;
   if (g_nccl.nranks > P2P_MAX_RANKS) return APDX_OK;
   p2p_teardown(pl);

@@ -386,7 +386,7 @@ int launch_element_kernels(apdx_plan *pl, const double *dofs_d, bool want_tangen
     a.coords = pl->coords.p; a.dofs = dofs_d; a.dofs_n = pl->dofs_n.p;
     a.inv_dt = 1.0 / pl->time_increment;
     for (int p = 0; p < APDX_PARAM_COUNT; ++p) a.par[p] = st.pview[p];
-    a.ke = pl->ke.p + st.coo_offset;
+    a.ke = pl->ke.p + st.ke_offset;
     a.re = pl->re.p + st.res_offset;
     if (st.d.kind == APDX_SET_INTPOINT)
       APDX_REQUIRE(st.ip_n.p && st.ip_w.p, APDX_ERR_STATE, "integration-point tables of a 'sparse' set are missing");
@@ -418,11 +418,13 @@ int launch_gather_reduce(apdx_plan *pl, int tangent_flags, double *residual_d) {
     pl->stats.kernel_launches += 1;
   }
   if (tangent_flags & 1) {
+    if (!pl->vals.p) APDX_CHECK(pl->vals.alloc(pl->nnz > 0 ? pl->nnz : 1));
     k_gather_reduce_full<<<(unsigned)((pl->nnz + B - 1) / B), B, 0, s>>>(pl->ke.p, pl->perm.p, pl->seg_ptr.p,
                                                                          pl->nnz, pl->vals.p);
     pl->stats.kernel_launches += 1;
   }
   if ((tangent_flags & 2) && pl->nnz_red > 0) {
+    if (!pl->red_vals.p) APDX_CHECK(pl->red_vals.alloc(pl->nnz_red));
     k_gather_reduce_red<<<(unsigned)((pl->nnz_red + B - 1) / B), B, 0, s>>>(
         pl->ke.p, pl->perm.p, pl->seg_ptr.p, pl->red2full.p, pl->nnz_red, pl->red_vals.p);
     pl->stats.kernel_launches += 1;

@@ -48,7 +48,7 @@ __global__ void k_res_keys(const int32_t *__restrict__ conn, int64_t n_entries, 
 // reference-order COO indices k = e*nd2 + ij (needed for the element->CSR map); afterwards the gather lists are
 // rewritten to SoA addresses off + ij*n_rows + e.
 struct SoaSet {
-  int64_t off, n_rows;
+  int64_t off, koff, n_rows;   // off: first reference-order index of the set; koff: start of its block in the stream
   int32_t width;   // ndof^2 (matrix stream) or ndof (vector stream)
   int32_t sym_n;   // matrix stream of a register-kernel set: element matrices are stored as their upper triangle
                    // (sym_n = ndof; entry (a,b) and (b,a) share slot lo*n - lo(lo-1)/2 + hi - lo); 0 = full storage
@@ -61,8 +61,8 @@ struct SoaTable {
 __device__ __forceinline__ int64_t soa_address(int64_t k, const SoaTable &t) {
   int q = 0;
   while (q + 1 < t.n && k >= t.s[q + 1].off) ++q;
-  if (t.s[q].n_rows == 0) return k;   // this set keeps the reference (element-major) layout
   const int64_t local = k - t.s[q].off;
+  if (t.s[q].n_rows == 0) return t.s[q].koff + local;   // this set keeps the reference (element-major) layout
   const int64_t e = local / t.s[q].width;
   int64_t ij = local - e * t.s[q].width;
   if (t.s[q].sym_n > 0) {
@@ -70,7 +70,7 @@ __device__ __forceinline__ int64_t soa_address(int64_t k, const SoaTable &t) {
     const int lo = a < b ? a : b, hi = a < b ? b : a;
     ij = lo * nn - lo * (lo - 1) / 2 + (hi - lo);
   }
-  return t.s[q].off + ij * t.s[q].n_rows + e;
+  return t.s[q].koff + ij * t.s[q].n_rows + e;
 }
 __global__ void k_to_soa(uint32_t *__restrict__ list, int64_t n, SoaTable t) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,7 +88,7 @@ static SoaTable matrix_soa_table(const apdx_plan *pl) {
   SoaTable t{};
   for (auto &st : pl->sets) {
     if (st.d.n_rows == 0) continue;
-    t.s[t.n++] = SoaSet{st.coo_offset, st.soa ? st.d.n_rows : 0, st.ndof_e * st.ndof_e, st.soa ? st.ndof_e : 0};
+    t.s[t.n++] = SoaSet{st.coo_offset, st.ke_offset, st.soa ? st.d.n_rows : 0, st.ndof_e * st.ndof_e, st.soa ? st.ndof_e : 0};
   }
   return t;
 }
@@ -103,12 +103,10 @@ __global__ void k_head_flags(const K *__restrict__ sorted, int64_t n, int32_t *_
 // uid = inclusive scan of the head flags (1-based); writes segment starts, columns and the map
 __global__ void k_unique_fill(const uint64_t *__restrict__ sorted, const uint32_t *__restrict__ perm,
                               const int32_t *__restrict__ uid_incl, int64_t n, int bits,
-                              int32_t *__restrict__ seg_ptr, int32_t *__restrict__ col,
-                              int32_t *__restrict__ elem_map) {
+                              int32_t *__restrict__ seg_ptr, int32_t *__restrict__ col) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int32_t u = uid_incl[i] - 1;
-  elem_map[perm[i]] = u;
   bool head = (i == 0) || (uid_incl[i - 1] != uid_incl[i]);
   if (head) {
     seg_ptr[u] = (int32_t)i;
@@ -273,7 +271,7 @@ int build_pattern(apdx_plan *pl, const uint8_t *mask_h) {
     SoaTable t{};
     for (auto &st : pl->sets) {
       if (st.d.n_rows == 0) continue;
-      t.s[t.n++] = SoaSet{st.res_offset, st.soa ? st.d.n_rows : 0, st.ndof_e, 0};
+      t.s[t.n++] = SoaSet{st.res_offset, st.res_offset, st.soa ? st.d.n_rows : 0, st.ndof_e, 0};
     }
     k_to_soa<<<grid_for(m, B), B, 0, s>>>(pl->rperm.p, m, t);
     APDX_CUDA(cudaStreamSynchronize(s));
@@ -317,9 +315,8 @@ int build_pattern(apdx_plan *pl, const uint8_t *mask_h) {
     pl->nnz = nnz;
     APDX_CHECK(pl->seg_ptr.alloc(pl->nnz + 1));
     APDX_CHECK(pl->col.alloc(pl->nnz));
-    APDX_CHECK(pl->elem_map.alloc(nc));
     k_unique_fill<<<grid_for(nc, B), B, 0, s>>>(sorted.p, pl->perm.p, uid.p, nc, bits, pl->seg_ptr.p,
-                                                 pl->col.p, pl->elem_map.p);
+                                                 pl->col.p);
     int32_t nc32 = (int32_t)nc;
     APDX_CUDA(cudaMemcpyAsync(pl->seg_ptr.p + pl->nnz, &nc32, sizeof(int32_t), cudaMemcpyHostToDevice, s));
     APDX_CHECK(pl->row_ptr.alloc(n + 1));
@@ -350,6 +347,54 @@ int build_pattern(apdx_plan *pl, const uint8_t *mask_h) {
                                                  pl->red_col.p, pl->red2full.p, pl->red_diag.p);
     APDX_CUDA(cudaStreamSynchronize(s));
   }
+  APDX_CUDA(cudaGetLastError());
+  return APDX_OK;
+}
+
+// The element-local -> CSR position map (the north-star "index map") for the COO entries
+// [k0, k0 + n): position of (row, col) of entry k inside the sorted, duplicate-free pattern that the radix sort + unique
+// pass built.  The scatter itself runs through the INVERSE lists (perm / seg_ptr, gather form); the forward map is
+// only exported (parity tests, apdx_plan_get_elem_map), so it is materialised on request instead of holding
+// 4 bytes per COO entry (4.3 GB at 256^3).
+struct MapSet {
+  int64_t off;
+  const int32_t *conn;
+  int32_t nen, ndof;
+};
+struct MapTable {
+  int n, nf;
+  MapSet s[16];
+};
+__global__ void k_elem_map_range(MapTable t, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, int64_t k0,
+                                 int64_t n, int32_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t k = k0 + i;
+  int q = 0;
+  while (q + 1 < t.n && k >= t.s[q + 1].off) ++q;
+  const MapSet &S = t.s[q];
+  const int64_t local = k - S.off, nd2 = (int64_t)S.ndof * S.ndof;
+  const int64_t e = local / nd2;
+  const int rem = (int)(local - e * nd2), a = rem / S.ndof, b = rem - a * S.ndof;
+  const int32_t row = S.conn[e * S.nen + a / t.nf] * t.nf + a % t.nf;
+  const int32_t c = S.conn[e * S.nen + b / t.nf] * t.nf + b % t.nf;
+  int32_t lo = row_ptr[row], hi = row_ptr[row + 1];
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (col[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  out[i] = lo;
+}
+int elem_map_export(const apdx_plan *pl, int64_t offset, int64_t count, int32_t *dst_d) {
+  if (count <= 0) return APDX_OK;
+  MapTable t{};
+  t.nf = pl->nf;
+  for (auto &st : pl->sets) {
+    if (st.d.n_rows == 0) continue;
+    APDX_REQUIRE(t.n < 16, APDX_ERR_UNSUPPORTED, "more than 16 non-empty sets");
+    t.s[t.n++] = MapSet{st.coo_offset, st.conn.p, st.d.nen, st.ndof_e};
+  }
+  k_elem_map_range<<<grid_for(count, 256), 256, 0, pl->stream>>>(t, pl->row_ptr.p, pl->col.p, offset, count, dst_d);
   APDX_CUDA(cudaGetLastError());
   return APDX_OK;
 }

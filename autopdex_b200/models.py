@@ -110,6 +110,58 @@ class poisson_potential:
         return 0.5 * c * dphi @ dphi - f * phi_fun(x_int)
 
 
+class poisson_residual:
+    """Tagged weak-form integrand  c grad(phi).grad(dphi) - f dphi  for mixed_reference_domain_residual
+    ('user residual' assembling mode, models.py:1272-1357 / assembler.py:1217-1308): the variation of poisson_potential,
+    same element arithmetic.  Also a valid JAX integrand for the reference (signature of models.py:1330-1338)."""
+
+    def __init__(self, field, source_fun=None, coefficient_fun=None, vectorized=True):
+        self.field, self.source_fun, self.coefficient_fun, self.vectorized = field, source_fun, coefficient_fun, vectorized
+
+    def __call__(self, x_int, trial_ansatz, test_ansatz, settings, static_settings, elem_number, set):
+        import jax  # only reachable on the reference backend
+        x = trial_ansatz["physical coor"](x_int)
+        dphi = jax.jacfwd(trial_ansatz[self.field])(x_int)
+        dtest = jax.jacfwd(test_ansatz[self.field])(x_int)
+        c = 1.0 if self.coefficient_fun is None else self.coefficient_fun(x)
+        f = 0.0 if self.source_fun is None else self.source_fun(x)
+        return c * dphi @ dtest - f * test_ansatz[self.field](x_int)
+
+
+class heat_conduction_time:
+    """Tagged TIME-DEPENDENT weak-form integrand  c theta_t dtheta + k grad(theta).grad(dtheta) - f dtheta  for
+    mixed_reference_domain_residual_time (models.py:1854-1914), the 'user residual' that dae.TimeSteppingManager
+    assembles (dae.py:1809-1876): theta_t comes from the field's time integrator.  Coefficient callables receive the
+    physical coordinate (and settings).  Also a valid JAX integrand for the reference."""
+
+    def __init__(self, field, conductivity_fun=None, capacity_fun=None, source_fun=None, vectorized=True):
+        self.field, self.conductivity_fun, self.capacity_fun, self.source_fun = field, conductivity_fun, capacity_fun, source_fun
+        self.vectorized = vectorized
+
+    def __call__(self, x_int, trial_ansatz, test_ansatz, settings, static_settings, elem_number, set):
+        import jax  # only reachable on the reference backend
+        t = settings["current time"]
+        x = trial_ansatz["physical coor"](x_int)
+        theta = trial_ansatz[self.field]
+        theta_t = jax.jacfwd(lambda tt: theta(x_int, tt))(t)
+        dtheta = jax.jacfwd(lambda xx: theta(xx, t))(x_int)
+        test = test_ansatz[self.field]
+        k = 1.0 if self.conductivity_fun is None else self.conductivity_fun(x)
+        c = 1.0 if self.capacity_fun is None else self.capacity_fun(x)
+        f = 0.0 if self.source_fun is None else self.source_fun(x)
+        return c * theta_t * test(x_int) + k * dtheta @ jax.jacfwd(test)(x_int) - f * test(x_int)
+
+
+class TimeElementModel:
+    """A transient 'user residual' domain: one reference domain served by TWO device sets on the same connectivity --
+    the steady part (conduction + source, positive sign: the poisson_potential kernel) and the capacity kernel, whose
+    backward-difference form  c (a q + b)  is fed by the time integrator (dae.py of this package)."""
+
+    def __init__(self, steady, capacity, field):
+        self.steady, self.capacity, self.field = steady, capacity, field
+        self.kind = "domain"
+
+
 # ---- element factories ----------------------------------------------------------------------------
 def _family(ansatz_fun):
     name = getattr(ansatz_fun, "__name__", "")
@@ -155,6 +207,35 @@ def mixed_reference_domain_potential(integrand_fun, ansatz_fun, ref_int_coor, re
                         physical_x=True, field=integrand_fun.field)
 
 
+def mixed_reference_domain_residual(integrand_fun, ansatz_fun, ref_int_coor, ref_int_weights, mapping_key):
+    """'user residual' route (models.py:1272-1357): tagged integrands only."""
+    if not isinstance(integrand_fun, poisson_residual):
+        _unsupported("a user-written weak-form integrand (use a tagged integrand such as models.poisson_residual)")
+    if list(ansatz_fun.keys()) != [integrand_fun.field] or mapping_key != integrand_fun.field:
+        _unsupported("multi-field residuals")
+    weak = WeakForm("poisson_potential", {"coefficient": integrand_fun.coefficient_fun, "source": integrand_fun.source_fun})
+    weak.vectorized = integrand_fun.vectorized
+    m = ElementModel("domain", weak, _family(ansatz_fun[integrand_fun.field]), (ref_int_coor, ref_int_weights),
+                     physical_x=True, field=integrand_fun.field)
+    m.route = "user residual"
+    return m
+
+
+def mixed_reference_domain_residual_time(integrand_fun, ansatz_fun, ref_int_coor, ref_int_weights, mapping_key):
+    """Time-dependent 'user residual' of dae.TimeSteppingManager (models.py:1854-1914): tagged integrands only."""
+    if not isinstance(integrand_fun, heat_conduction_time):
+        _unsupported("a user-written time-dependent integrand (use a tagged one such as models.heat_conduction_time)")
+    if list(ansatz_fun.keys()) != [integrand_fun.field] or mapping_key != integrand_fun.field:
+        _unsupported("multi-field residuals")
+    fam = _family(ansatz_fun[integrand_fun.field])
+    steady = WeakForm("poisson_potential", {"coefficient": integrand_fun.conductivity_fun, "source": integrand_fun.source_fun})
+    cap = WeakForm("capacity", {"coefficient": integrand_fun.capacity_fun if integrand_fun.capacity_fun is not None else 1.0})
+    steady.vectorized = cap.vectorized = integrand_fun.vectorized
+    gp = (ref_int_coor, ref_int_weights)
+    return TimeElementModel(ElementModel("domain", steady, fam, gp, physical_x=True, field=integrand_fun.field),
+                            ElementModel("domain", cap, fam, gp, physical_x=True, field=integrand_fun.field), integrand_fun.field)
+
+
 # ---- recognition of the reference's own closures ---------------------------------------------------
 def _cells(fn):
     code, clo = getattr(fn, "__code__", None), getattr(fn, "__closure__", None)
@@ -197,7 +278,7 @@ def recognise_weak_form(fn):
 
 def recognise(model):
     """ElementModel / WeakForm for one entry of static_settings['model'], or ValueError."""
-    if isinstance(model, (ElementModel, WeakForm)):
+    if isinstance(model, (ElementModel, WeakForm, TimeElementModel)):
         return model
     qn = getattr(model, "__qualname__", "")
     c = _cells(model)
@@ -211,6 +292,12 @@ def recognise(model):
     if _made_by(qn, "mixed_reference_domain_potential"):
         return mixed_reference_domain_potential(c.get("integrand_fun"), c.get("ansatz_fun"), c.get("ref_int_coor"),
                                                 c.get("ref_int_weights"), c.get("mapping_key"))
+    if _made_by(qn, "mixed_reference_domain_residual"):
+        return mixed_reference_domain_residual(c.get("integrand_fun"), c.get("ansatz_fun"), c.get("ref_int_coor"),
+                                               c.get("ref_int_weights"), c.get("mapping_key"))
+    if _made_by(qn, "mixed_reference_domain_residual_time"):
+        return mixed_reference_domain_residual_time(c.get("integrand_fun"), c.get("ansatz_fun"), c.get("ref_int_coor"),
+                                                    c.get("ref_int_weights"), c.get("mapping_key"))
     return recognise_weak_form(model)
 
 

@@ -126,8 +126,8 @@ def prolongation(shape_fine, nf, free_fine, free_coarse):
 
 def coarse_level_settings(settings, shape_fine, set_kinds, unwrap, wrap, cache=None):
     """`settings` of the next-coarser level: injected node coordinates / Dirichlet flags, structured connectivity for the
-    domain sets, every other entry passed through (coefficient callables read `settings`).  set_kinds: 'domain' /
-    'surface' per set of the fine level; returns (coarse settings, kept set indices, fine node ids).
+    domain sets, every other entry passed through (coefficient callables read `settings`).  set_kinds: ('domain' |
+    'surface', index into settings['connectivity']) per device set of the fine level; returns (coarse settings, kept set indices, fine node ids).
     cache: dict kept by the caller; the injected arrays are reused while the fine coordinate / mask objects are the same
     (no copies per solver call, and the backend can page-lock buffers it sees twice)."""
     cache = cache if cache is not None else {}
@@ -138,10 +138,10 @@ def coarse_level_settings(settings, shape_fine, set_kinds, unwrap, wrap, cache=N
     fine_nodes, conn_c = cache["fine_nodes"], cache["conn"]
     n_el = int(np.prod(shape_fine))
     kept, conns = [], []
-    for i, kind in enumerate(set_kinds):
+    for i, (kind, dom) in enumerate(set_kinds):
         if kind != "domain":
             continue
-        c = unwrap(settings["connectivity"][i])
+        c = unwrap(settings["connectivity"][dom])
         if np.shape(c) != (n_el, 1 << len(shape_fine)):
             raise ValueError("b200 multigrid: domain %d has connectivity %s, expected one %d-node element per cell of the "
                              "structured %s mesh" % (i, np.shape(c), 1 << len(shape_fine), "x".join(map(str, shape_fine))))

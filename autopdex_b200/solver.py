@@ -86,15 +86,26 @@ class _Config:
         if _get(static_settings, "known sparsity pattern", "none") != "none":
             raise ValueError("b200 backend: 'known sparsity pattern' is not supported")
         self.shape_mode = _get(static_settings, "shape function mode", None)
+        # device sets: (route, model, domain) -- `domain` indexes settings['connectivity'] etc.; a transient 'user
+        # residual' domain (dae.TimeSteppingManager) is served by two device sets on the same connectivity
         self.sets = []
+        self.transient = False
         for i, mode in enumerate(modes):
             m = models.recognise(model_list[i])
-            if mode in ("user element", "user potential"):
+            if mode == "user residual" and isinstance(m, models.TimeElementModel):
+                if not getattr(self, "_dae", False) and not static_settings.get("time integrators"):
+                    raise ValueError("b200 backend: domain %d: a time-dependent 'user residual' is driven by "
+                                     "autopdex_b200.dae.TimeSteppingManager ('time integrators' in static_settings)" % i)
+                self.sets.append(("element", m.steady, i))
+                self.sets.append(("element", m.capacity, i))
+                self.transient = True
+            elif mode in ("user element", "user potential", "user residual"):
                 if not isinstance(m, models.ElementModel):
                     raise ValueError("b200 backend: domain %d: assembling mode %r needs an isoparametric element model" % (i, mode))
-                if (mode == "user potential") != (m.weak.name == "poisson_potential"):
+                route = getattr(m, "route", "user potential" if m.weak.name == "poisson_potential" else "user element")
+                if route != mode:
                     raise ValueError("b200 backend: domain %d: model %r does not match assembling mode %r" % (i, m.weak, mode))
-                self.sets.append(("element", m))
+                self.sets.append(("element", m, i))
             elif mode == "sparse":
                 if not isinstance(m, models.WeakForm):
                     raise ValueError("b200 backend: domain %d: 'sparse' mode needs a weak form" % i)
@@ -105,10 +116,10 @@ class _Config:
                                      "only, got %r / %r" % (i, scheme, space))
                 if self.shape_mode not in ("direct", "compiled"):
                     raise ValueError("b200 backend: 'shape function mode' must be 'direct' or 'compiled'")
-                self.sets.append(("sparse", m))
+                self.sets.append(("sparse", m, i))
             else:
                 raise ValueError("b200 backend: assembling mode %r of domain %d is not supported "
-                                 "(user element, user potential, sparse)" % (mode, i))
+                                 "(user element, user potential, user residual, sparse)" % (mode, i))
         self.key = (self.solver_type, self.krylov, self.precond, self.nodal_imposition, self.shape_mode,
                     tuple(id(model_list[i]) for i in range(self.n_sets)), tuple(modes))
 
@@ -118,7 +129,7 @@ class _Config:
         V-cycle of the finest plan)."""
         import copy
         c = copy.copy(self)
-        c.sets = [self.sets[i] for i in kept]
+        c.sets = [(self.sets[i][0], self.sets[i][1], j) for j, i in enumerate(kept)]   # coarse settings: one entry per kept set
         c.n_sets = len(kept)
         c.multigrid, c.jacobi, c.precond = False, True, "jacobi"
         return c
@@ -202,9 +213,9 @@ class _State:
         self.nf = 1 if d0.ndim == 1 else d0.shape[-1]
         if d0.size != self.n_nodes * self.nf:
             raise ValueError("b200 backend: dofs and node coordinates disagree on the number of nodes")
-        self.conn_refs = [self._unwrap(c) for c in settings["connectivity"]]
+        self.conn_refs = [self._unwrap(settings["connectivity"][dom]) for _, _, dom in cfg.sets]   # per DEVICE set
         specs = []
-        for i, (route, m) in enumerate(cfg.sets):
+        for i, (route, m, dom) in enumerate(cfg.sets):
             conn = np.asarray(self.conn_refs[i])
             if route == "element":
                 specs.append(backend.SetSpec(m.kind, m.weak.name, conn, family=m.family, gp=m.gp, mode=m.weak.mode))
@@ -248,10 +259,10 @@ class _State:
 
     def _mg_kinds(self):
         kinds = []
-        for route, m in self.cfg.sets:
+        for route, m, dom in self.cfg.sets:
             if route != "element":
                 raise ValueError("b200 backend: the multigrid preconditioner supports isoparametric element sets only")
-            kinds.append(m.kind)
+            kinds.append((m.kind, dom))
         return kinds
 
     def _build_hierarchy(self, settings):
@@ -318,7 +329,7 @@ class _State:
         coords = np.ascontiguousarray(self._unwrap(settings["node coordinates"]), dtype=np.float64)
         plan.set_coords(coords)
         self.h2d_bytes += coords.nbytes
-        for i, (route, m) in enumerate(cfg.sets):
+        for i, (route, m, dom) in enumerate(cfg.sets):
             weak = m.weak if route == "element" else m
             conn = np.asarray(self.conn_refs[i])
             if route == "element":
@@ -331,12 +342,12 @@ class _State:
                 n_gp = xi.shape[0]
             else:
                 n_gp = 1
-                x_int = np.asarray(settings["integration coordinates"][i], dtype=np.float64)
+                x_int = np.asarray(settings["integration coordinates"][dom], dtype=np.float64)
                 if cfg.shape_mode == "compiled":
                     pts = np.zeros((1, self.dim))                   # variational_schemes.py:214-215
                 else:
                     pts = x_int
-                self._upload_intpoint_tables(i, settings, conn, coords, x_int)
+                self._upload_intpoint_tables(i, dom, settings, conn, coords, x_int)
             for name, fun in weak.funs.items():
                 ncomp = self.nf if name in _NCOMP_NF else 1
                 v = _eval_points(fun, pts, settings, ncomp, getattr(weak, "vectorized", None))
@@ -353,10 +364,10 @@ class _State:
                 self.h2d_bytes += dn.nbytes
         self.update_coarse_fields(settings)
 
-    def _upload_intpoint_tables(self, i, settings, conn, coords, x_int):
-        w = np.asarray(settings["integration weights"][i], dtype=np.float64)
+    def _upload_intpoint_tables(self, i, dom, settings, conn, coords, x_int):
+        w = np.asarray(settings["integration weights"][dom], dtype=np.float64)
         if self.cfg.shape_mode == "compiled":
-            f, df = settings["compiled shape functions"][i][:2]
+            f, df = settings["compiled shape functions"][dom][:2]
             N, dN = np.asarray(f, dtype=np.float64), np.asarray(df, dtype=np.float64)
         else:
             N, dN = spaces.simplex_physical_tables(x_int, coords[conn])
@@ -441,8 +452,11 @@ def solver(dofs, settings, static_settings, newton_tol=1e-8, maxiter=30, damping
         n_it, res, div = plan.newton(opts, st.dofs_d, vals_d, newton_tol, maxiter, damping)
         sol = st.dofs_d.download()
         infos = (n_it, res, div)
-        if cfg.verbose > 0:
-            print("Residual after Newton iteration %d: %s" % (n_it, res))
+        if cfg.verbose > 0:                      # solver.py:906-912, one line per iteration (printed after the device loop)
+            for i, r in enumerate(plan.newton_history()):
+                print("Residual after Newton iteration %d: %s" % (i + 1, r))
+                if cfg.verbose > 1:
+                    print("")
         if div and n_it > maxiter:
             print("Warning: Newton scheme could not converge!")
     st.d2h_bytes = sol.nbytes

@@ -213,6 +213,10 @@ int apdx_plan_set_multigrid(apdx_plan *plan, int32_t pre_degree, int32_t post_de
  * out[3]=krylov iterations out[4]=spmv launches out[5]=total out[6]=kernel launches
  * out[7]=bytes of the sliced-ELL matrix the SpMV streams (values + compressed indices)    */
 int apdx_plan_stats(const apdx_plan *plan, double out[8]);
+/* residual norms after every iteration of the last apdx_newton: what solver.damped_newton prints with verbose > 0
+ * ("Residual after Newton iteration {i}: {res}", autopdex/solver.py:906-909).  count = iterations run; at most
+ * `capacity` values are written. */
+int apdx_plan_newton_history(const apdx_plan *plan, double *res_norms, int32_t capacity, int32_t *count);
 /* outcome of the plan's LAST Krylov solve (inside apdx_newton: of the last Newton step): relative residual
  * ||b - A x|| / ||b|| of the recurrence and whether the stopping rule of jax.scipy.sparse.linalg.cg / bicgstab
  * (||r|| <= max(rtol ||b||, atol), solver.py:1116-1126) was met -- 0 when the loop ended on maxiter or broke down.

@@ -109,7 +109,14 @@ def main():
         cases = [(problem, int(argv[0]) if len(argv) > 0 else 20, argv[1] if len(argv) > 1 else "cg",
                   argv[2] if len(argv) > 2 else "slab")]
     ok = True
+    import signal
+
+    def _watchdog(signum, frame):   # a rank that raised leaves the others inside a collective: bound every case
+        print("multi-gpu parity: rank %d: case timed out (a peer probably failed) -> FAIL" % rank, flush=True)
+        os._exit(3)
+    signal.signal(signal.SIGALRM, _watchdog)
     for c in cases:
+        signal.alarm(int(os.environ.get("APDX_CASE_TIMEOUT", "150")))
         try:
             ok = run_case(*c, rank, world) and ok
         except Exception as e:   # keep the remaining cases running; every rank raises alike (collective set-up errors)
@@ -118,6 +125,7 @@ def main():
                   flush=True)
             from autopdex_b200 import solver
             solver.clear_plan_cache()
+    signal.alarm(0)
     backend.comm_destroy()
     sys.exit(0 if ok else 1)
 

@@ -1,23 +1,23 @@
 #!/usr/bin/env bash
 # multi-GPU session: gpurun --gpus N -- 'bash tools/gpu_session_multi.sh N [tag]'
 #   parity matrix {poisson, neohooke} x {cg, bicgstab} x {slab, rcb} against the oracle, config 5 (128^3 neo-Hooke),
-#   bench at N ranks (default loop, APDX_COMM=mbox, APDX_TRACE component times)
+#   bench at N ranks (default = mailbox all-reduce, APDX_COMM=nccl, APDX_TRACE component times)
 set -u
 cd "$(dirname "$0")/.."
 N=${1:-2}; TAG=${2:-r02b}
 OUT=gpurun_out; mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 900 $TR --master-port 29511 tests/multi_gpu_worker.py matrix 24 12 > $OUT/${TAG}_parity_n$N.txt 2>&1; echo "parity exit $?"
+timeout 400 $TR --master-port 29511 tests/multi_gpu_worker.py matrix 24 12 > $OUT/${TAG}_parity_n$N.txt 2>&1; echo "parity exit $?"
 grep "multi-gpu parity" $OUT/${TAG}_parity_n$N.txt
-timeout 900 $TR --master-port 29521 tools/run_config.py neohooke ${CFG5_SIZE:-128} 2 > $OUT/${TAG}_config5_n$N.json 2> $OUT/${TAG}_config5_n$N.err; echo "config5 exit $?"
+timeout 300 $TR --master-port 29521 tools/run_config.py neohooke ${CFG5_SIZE:-128} 2 > $OUT/${TAG}_config5_n$N.json 2> $OUT/${TAG}_config5_n$N.err; echo "config5 exit $?"
 cat $OUT/${TAG}_config5_n$N.json | cut -c1-1500
-timeout 600 $TR --master-port 29531 bench.py --gpus $N --steps 5 --warmup 3 > $OUT/${TAG}_bench_n$N.json 2> $OUT/${TAG}_bench_n$N.err; echo "bench exit $?"
-APDX_COMM=mbox timeout 600 $TR --master-port 29541 bench.py --gpus $N --steps 5 --warmup 3 > $OUT/${TAG}_bench_n${N}_mbox.json 2> $OUT/${TAG}_bench_n${N}_mbox.err; echo "bench mbox exit $?"
-APDX_TRACE=1 timeout 600 $TR --master-port 29551 bench.py --gpus $N --steps 1 --warmup 1 > /dev/null 2> $OUT/${TAG}_trace_n$N.txt
+timeout 240 $TR --master-port 29531 bench.py --gpus $N --steps 5 --warmup 3 > $OUT/${TAG}_bench_n$N.json 2> $OUT/${TAG}_bench_n$N.err; echo "bench exit $?"
+APDX_COMM=nccl timeout 240 $TR --master-port 29541 bench.py --gpus $N --steps 5 --warmup 3 > $OUT/${TAG}_bench_n${N}_nccl.json 2> $OUT/${TAG}_bench_n${N}_nccl.err; echo "bench nccl exit $?"
+APDX_TRACE=1 timeout 240 $TR --master-port 29551 bench.py --gpus $N --steps 1 --warmup 1 > /dev/null 2> $OUT/${TAG}_trace_n$N.txt
 grep -h "apdx trace" $OUT/${TAG}_trace_n$N.txt | sort | uniq -c | head
 python - <<PY
 import json
-for f in ("$OUT/${TAG}_bench_n$N.json", "$OUT/${TAG}_bench_n${N}_mbox.json"):
+for f in ("$OUT/${TAG}_bench_n$N.json", "$OUT/${TAG}_bench_n${N}_nccl.json"):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, "step ms", d["ms_per_step"], "e2e ms", d["e2e"]["ms_per_step"], "cg ms/it", d["cg"]["ms_per_iteration"], "ok", d["config"]["parity_guard"]["ok"])
