@@ -99,7 +99,7 @@ def assemble_residual(dofs, settings, static_settings):
     st, d0 = _prepare(dofs, settings, static_settings)
     st.plan.assemble(st.dofs_d, False, st.out_d)
     r = st.out_d.download().reshape(d0.shape)
-    return {st.dict_key: r} if st.dict_key is not None else r
+    return st._wrap(r)
 
 
 def assemble_tangent(dofs, settings, static_settings, reduced=False, format="bcoo"):
@@ -111,11 +111,40 @@ def assemble_tangent(dofs, settings, static_settings, reduced=False, format="bco
         indptr, indices = st.plan.csr(reduced)
         n = st.plan.n_free if reduced else st.plan.n_dofs
         return CSR(st.plan.values(reduced), indices, indptr, (n, n))
+    n = st.plan.n_dofs
+    if st.fields is not None:
+        return _multi_field_bcoo(st, dofs, settings, n)
     # sets in order (assembler.py:715-752); the unwrapped single field has the numbering of dict_flatten
     idx = [_get_indices(np.asarray(c), d0) for c in st.conn_refs]
     indices = np.concatenate(idx, axis=0) if idx else np.zeros((0, 2), dtype=np.int64)
-    n = st.plan.n_dofs
     return BCOO(st.plan.coo_values(), indices, (n, n), st.plan)
+
+
+def _multi_field_bcoo(st, dofs, settings, n):
+    """BCOO of a multi-field dict-dof problem in the reference's order (assembler.py:715-752 per domain, :79-117 inside a
+    domain: blocks `for field_i: for field_j:`, each element-major).  The device holds the model's (field, field) block of
+    every domain element-major, which is exactly the order inside that block; every other block is an explicit zero."""
+    nf = st.nf
+    offs, o = [], 0
+    for c in st.conn_refs:                                     # COO offsets of the device sets
+        offs.append(o)
+        o += c.shape[0] * (c.shape[1] * nf) ** 2
+    data, indices = [], []
+    doms = sorted({d for _, _, d in st.cfg.sets})
+    if len(doms) != len(st.cfg.sets):
+        raise ValueError("b200 backend: BCOO export of a multi-field problem needs one model per domain")
+    for i, (route, m, dom) in enumerate(st.cfg.sets):
+        conn = settings["connectivity"][dom]
+        indices.append(_get_indices({k: np.asarray(conn[k]) for k in st.fields}, dofs))
+        n_e = np.asarray(conn[m.field]).shape[0]
+        for fi in st.fields:
+            for fj in st.fields:
+                cnt = n_e * (np.asarray(conn[fi]).shape[1] * nf) * (np.asarray(conn[fj]).shape[1] * nf)
+                if fi == m.field and fj == m.field:
+                    data.append(st.plan.coo_values(offs[i], cnt))
+                else:
+                    data.append(np.zeros(cnt))
+    return BCOO(np.concatenate(data), np.concatenate(indices, axis=0), (n, n), st.plan)
 
 
 def csr_diagonal(csr):

@@ -189,6 +189,9 @@ class Plan:
             d.conn_h = st.conn.ctypes.data_as(C.c_void_p)
             if st.kind == "intpoint":
                 d.n_gp, d.dim_ref = 1, dim
+            elif st.model == "pattern_only":
+                d.n_gp, d.dim_ref = 1, dim          # no arithmetic, no shape tables
+                st.n_gp = 1
             else:
                 xi, w = st.gp
                 dr = dim if st.kind == "domain" else dim - 1

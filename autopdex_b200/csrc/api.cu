@@ -286,12 +286,17 @@ int apdx_mem_info(size_t *free_bytes, size_t *total_bytes) {
 // ---- plan ------------------------------------------------------------------------------------------
 static int validate_set(const apdx_set_desc &d, int dim, int nf, int idx) {
   APDX_REQUIRE(d.kind >= APDX_SET_DOMAIN && d.kind <= APDX_SET_INTPOINT, APDX_ERR_INVALID, "set %d: bad kind %d", idx, d.kind);
-  APDX_REQUIRE(d.model >= APDX_MODEL_POISSON_POTENTIAL && d.model <= APDX_MODEL_CAPACITY, APDX_ERR_UNSUPPORTED,
+  APDX_REQUIRE(d.model >= APDX_MODEL_POISSON_POTENTIAL && d.model <= APDX_MODEL_PATTERN_ONLY, APDX_ERR_UNSUPPORTED,
                "set %d: model id %d is not a supported closed-form model", idx, d.model);
-  APDX_REQUIRE(d.nen >= 2 && d.nen <= 27, APDX_ERR_UNSUPPORTED, "set %d: %d nodes per element not supported", idx, d.nen);
   APDX_REQUIRE(d.n_rows >= 0, APDX_ERR_INVALID, "set %d: negative row count", idx);
   APDX_REQUIRE(d.conn_itemsize == 4 || d.conn_itemsize == 8, APDX_ERR_INVALID, "set %d: connectivity itemsize must be 4 or 8", idx);
   APDX_REQUIRE(d.conn_h || d.n_rows == 0, APDX_ERR_INVALID, "set %d: connectivity pointer is NULL", idx);
+  if (d.model == APDX_MODEL_PATTERN_ONLY) {   // no arithmetic: the set only contributes its all-pairs block to the pattern
+    APDX_REQUIRE(d.kind == APDX_SET_DOMAIN, APDX_ERR_INVALID, "set %d: a pattern-only set is a domain set", idx);
+    APDX_REQUIRE(d.nen >= 1 && d.nen <= 64, APDX_ERR_UNSUPPORTED, "set %d: %d nodes per pattern-only row not supported", idx, d.nen);
+    return APDX_OK;
+  }
+  APDX_REQUIRE(d.nen >= 2 && d.nen <= 27, APDX_ERR_UNSUPPORTED, "set %d: %d nodes per element not supported", idx, d.nen);
   const bool scalar = d.model == APDX_MODEL_POISSON_POTENTIAL || d.model == APDX_MODEL_POISSON_WEAK || d.model == APDX_MODEL_CAPACITY;
   const bool vector = d.model == APDX_MODEL_LINEAR_ELASTICITY || d.model == APDX_MODEL_NEO_HOOKE;
   if (scalar) APDX_REQUIRE(nf == 1, APDX_ERR_UNSUPPORTED, "set %d: scalar model needs one dof per node, got %d", idx, nf);
@@ -391,7 +396,7 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
         return fail(APDX_ERR_CUDA);
       }
     }
-    if (st.d.kind != APDX_SET_INTPOINT) {
+    if (st.d.kind != APDX_SET_INTPOINT && st.d.model != APDX_MODEL_PATTERN_ONLY) {
       size_t a = (size_t)st.d.n_gp * st.d.nen, b = a * st.d.dim_ref, c = st.d.n_gp;
       if ((rc = st.shape_n.alloc(a)) != APDX_OK || (rc = st.shape_dn.alloc(b)) != APDX_OK ||
           (rc = st.gp_w.alloc(c)) != APDX_OK)
@@ -832,6 +837,26 @@ int apdx_plan_last_krylov(const apdx_plan *pl, double *relres, int32_t *converge
   return APDX_OK;
 }
 
+// A partition whose set-up fails on ONE rank must fail on ALL of them: the ranks that passed would otherwise wait for
+// the failed one inside the collectives of the halo set-up (measured the hard way: a 13-plane brick on 8 ranks left
+// rank 0 with Dirichlet dofs only, and seven GPUs idling until the job's timeout).  Sum of the local failure flags.
+static int partition_agree(apdx_plan *pl, bool ok_local, const char *what) {
+  double bad = ok_local ? 0.0 : 1.0;
+  if (comm_active()) {
+    double *d = nullptr;
+    APDX_CUDA(cudaMalloc((void **)&d, sizeof(double)));
+    APDX_CUDA(cudaMemcpyAsync(d, &bad, sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    int rc = comm_allreduce_sum(d, 1, pl->stream);
+    if (rc == APDX_OK && cudaMemcpyAsync(&bad, d, sizeof(double), cudaMemcpyDeviceToHost, pl->stream) != cudaSuccess) rc = APDX_ERR_CUDA;
+    if (rc == APDX_OK && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = APDX_ERR_CUDA;
+    cudaFree(d);
+    APDX_CHECK(rc);
+  }
+  if (!ok_local) APDX_REQUIRE(false, APDX_ERR_INVALID, "%s", what);
+  APDX_REQUIRE(bad == 0.0, APDX_ERR_INVALID, "partition set-up failed on %d other rank(s): %s there", (int)bad, what);
+  return APDX_OK;
+}
+
 int apdx_plan_set_partition(apdx_plan *pl, int64_t owned_dof_begin, int64_t owned_dof_end, int32_t rank_lo,
                             int32_t rank_hi) {
   APDX_REQUIRE(pl, APDX_ERR_INVALID, "NULL argument");
@@ -853,9 +878,9 @@ int apdx_plan_set_partition(apdx_plan *pl, int64_t owned_dof_begin, int64_t owne
   pl->f0 = out[0]; pl->f1 = out[1];
   pl->rank_lo = rank_lo; pl->rank_hi = rank_hi;
   pl->halo_lo = pl->f0; pl->halo_hi = pl->n_free - pl->f1;
-  APDX_REQUIRE(pl->f1 > pl->f0, APDX_ERR_INVALID, "rank owns no free dof");
-  if (rank_lo < 0) APDX_REQUIRE(pl->halo_lo == 0, APDX_ERR_INVALID, "ghost dofs below the owned range but no lower neighbour");
-  if (rank_hi < 0) APDX_REQUIRE(pl->halo_hi == 0, APDX_ERR_INVALID, "ghost dofs above the owned range but no upper neighbour");
+  APDX_CHECK(partition_agree(pl, pl->f1 > pl->f0 && (rank_lo >= 0 || pl->halo_lo == 0) && (rank_hi >= 0 || pl->halo_hi == 0),
+                             "a rank owns no free dof (every dof of its part is a Dirichlet dof), or has ghost dofs on a "
+                             "side without a neighbour"));
   if (comm_active()) {
     APDX_CHECK(comm_halo_setup(pl));
     APDX_CHECK(p2p_setup(pl));
@@ -921,7 +946,7 @@ int apdx_plan_set_partition_lists(apdx_plan *pl, int64_t owned_dof_end, int32_t 
   pl->rank_lo = pl->rank_hi = -1;
   pl->halo_lo = pl->halo_hi = 0;
   pl->send_lo = pl->send_hi = 0;
-  APDX_REQUIRE(pl->f1 > pl->f0, APDX_ERR_INVALID, "rank owns no free dof");
+  APDX_CHECK(partition_agree(pl, pl->f1 > pl->f0, "a rank owns no free dof (every dof of its part is a Dirichlet dof)"));
   if (comm_active()) {
     APDX_CHECK(comm_halo_setup_lists(pl));
     APDX_CHECK(p2p_setup(pl));

@@ -375,6 +375,7 @@ int launch_element_kernels(apdx_plan *pl, const double *dofs_d, bool want_tangen
   APDX_REQUIRE(pl->have_coords, APDX_ERR_STATE, "apdx_set_coords must be called before assembling");
   for (auto &st : pl->sets) {
     if (st.d.n_rows == 0) continue;
+    if (st.d.model == APDX_MODEL_PATTERN_ONLY) continue;   // its streams were zeroed when the plan was created
     ElemArgs a{};
     a.conn = st.conn.p;
     a.n_rows = st.d.n_rows;

@@ -362,7 +362,7 @@ int sell_build(apdx_plan *pl) {
     for (const SetData &st : pl->sets) {
       switch (st.d.model) {
         case APDX_MODEL_POISSON_POTENTIAL: case APDX_MODEL_POISSON_WEAK: case APDX_MODEL_LINEAR_ELASTICITY:
-        case APDX_MODEL_NEO_HOOKE: case APDX_MODEL_NEUMANN: case APDX_MODEL_CAPACITY:
+        case APDX_MODEL_NEO_HOOKE: case APDX_MODEL_NEUMANN: case APDX_MODEL_CAPACITY: case APDX_MODEL_PATTERN_ONLY:
           break;
         default:
           S.sym = false;

@@ -198,8 +198,10 @@ def isoparametric_surface_element_galerkin(weak_form_fun, ansatz_fun, ref_int_co
 def mixed_reference_domain_potential(integrand_fun, ansatz_fun, ref_int_coor, ref_int_weights, mapping_key):
     if not isinstance(integrand_fun, poisson_potential):
         _unsupported("a user-written integrand (use a tagged integrand such as models.poisson_potential)")
-    if list(ansatz_fun.keys()) != [integrand_fun.field] or mapping_key != integrand_fun.field:
-        _unsupported("multi-field potentials")
+    # multi-field dict dofs: ansatz_fun names every field (models.py:1236-1243 builds an ansatz per key); the tagged
+    # integrand acts on ONE of them, and that field also carries the isoparametric mapping
+    if integrand_fun.field not in ansatz_fun or mapping_key != integrand_fun.field:
+        _unsupported("a potential whose field %r is not in ansatz_fun / is not the mapping key" % (integrand_fun.field,))
     weak = WeakForm("poisson_potential", {"coefficient": integrand_fun.coefficient_fun,
                                           "source": integrand_fun.source_fun})
     weak.vectorized = integrand_fun.vectorized
@@ -211,8 +213,8 @@ def mixed_reference_domain_residual(integrand_fun, ansatz_fun, ref_int_coor, ref
     """'user residual' route (models.py:1272-1357): tagged integrands only."""
     if not isinstance(integrand_fun, poisson_residual):
         _unsupported("a user-written weak-form integrand (use a tagged integrand such as models.poisson_residual)")
-    if list(ansatz_fun.keys()) != [integrand_fun.field] or mapping_key != integrand_fun.field:
-        _unsupported("multi-field residuals")
+    if integrand_fun.field not in ansatz_fun or mapping_key != integrand_fun.field:
+        _unsupported("a residual whose field %r is not in ansatz_fun / is not the mapping key" % (integrand_fun.field,))
     weak = WeakForm("poisson_potential", {"coefficient": integrand_fun.coefficient_fun, "source": integrand_fun.source_fun})
     weak.vectorized = integrand_fun.vectorized
     m = ElementModel("domain", weak, _family(ansatz_fun[integrand_fun.field]), (ref_int_coor, ref_int_weights),

@@ -120,6 +120,7 @@ class _Config:
             else:
                 raise ValueError("b200 backend: assembling mode %r of domain %d is not supported "
                                  "(user element, user potential, user residual, sparse)" % (mode, i))
+        self.model_objects = tuple(model_list)     # their id() is part of the cache key: kept alive with the plan
         self.key = (self.solver_type, self.krylov, self.precond, self.nodal_imposition, self.shape_mode,
                     tuple(id(model_list[i]) for i in range(self.n_sets)), tuple(modes))
 
@@ -201,11 +202,31 @@ class _State:
     def __init__(self, cfg, dofs, settings):
         self.cfg = cfg
         self.dict_key = None
+        # Multi-field dict dofs (assembler.py:61-121, utility.dict_flatten utility.py:104-128): the global numbering is
+        # field-major -- all dofs of the first key, then the second, ... -- so with the SAME number of dofs per node in
+        # every field the problem is a single-field problem on the concatenated node set (node k of field f becomes
+        # node node_offset[f] + k).  A domain whose (recognised, single-field) model acts on field f gets its connectivity
+        # shifted accordingly; the structural entries the reference emits for the field pairs the integrand does not
+        # couple (explicit zero blocks of jacfwd, assembler.py:79-117) come from one pattern-only device set per domain
+        # with the element's nodes of ALL fields, which makes the CSR pattern identical to the reference's.
+        self.fields = None
         if isinstance(dofs, Mapping):
             keys = list(dofs.keys())
-            if len(keys) != 1:
-                raise ValueError("b200 backend: dict dofs with %d fields are not supported (single field only)" % len(keys))
-            self.dict_key = keys[0]
+            if len(keys) == 1:
+                self.dict_key = keys[0]
+            elif len(keys) == 0:
+                raise ValueError("b200 backend: empty dofs dict")
+            else:
+                self.fields = keys
+                shapes = [np.shape(dofs[k]) for k in keys]
+                nfs = {1 if len(sh) == 1 else sh[-1] for sh in shapes}
+                if len(nfs) != 1 or len({len(sh) for sh in shapes}) != 1:
+                    raise ValueError("b200 backend: multi-field dict dofs need the same number of dofs per node in every "
+                                     "field (got shapes %s)" % (dict(zip(keys, shapes)),))
+                self.field_nodes = [sh[0] for sh in shapes]
+                self.node_off = dict(zip(keys, np.concatenate([[0], np.cumsum(self.field_nodes)[:-1]]).astype(np.int64)))
+                if settings.get("b200 partition") or cfg.multigrid:
+                    raise ValueError("b200 backend: multi-field dict dofs run on one GPU with the Jacobi preconditioner")
         d0 = self._unwrap(dofs)
         self.dofs_ndim = d0.ndim
         coords = np.asarray(self._unwrap(settings["node coordinates"]), dtype=np.float64)
@@ -213,7 +234,10 @@ class _State:
         self.nf = 1 if d0.ndim == 1 else d0.shape[-1]
         if d0.size != self.n_nodes * self.nf:
             raise ValueError("b200 backend: dofs and node coordinates disagree on the number of nodes")
-        self.conn_refs = [self._unwrap(settings["connectivity"][dom]) for _, _, dom in cfg.sets]   # per DEVICE set
+        if self.fields is None:
+            self.conn_refs = [self._unwrap(settings["connectivity"][dom]) for _, _, dom in cfg.sets]   # per DEVICE set
+        else:
+            self.conn_refs = [self._field_connectivity(settings["connectivity"][dom], m, route, dom) for route, m, dom in cfg.sets]
         specs = []
         for i, (route, m, dom) in enumerate(cfg.sets):
             conn = np.asarray(self.conn_refs[i])
@@ -221,11 +245,18 @@ class _State:
                 specs.append(backend.SetSpec(m.kind, m.weak.name, conn, family=m.family, gp=m.gp, mode=m.weak.mode))
             else:
                 specs.append(backend.SetSpec("intpoint", m.name, conn, mode=m.mode))
+        self.n_model_sets = len(specs)
+        if self.fields is not None:      # one pattern-only set per domain: the element's nodes of every field
+            for dom in sorted({d for _, _, d in cfg.sets}):
+                c = settings["connectivity"][dom]
+                allc = np.concatenate([np.asarray(c[k], dtype=np.int64) + self.node_off[k] for k in self.fields], axis=1)
+                self.conn_refs.append(allc)
+                specs.append(backend.SetSpec("domain", "pattern_only", allc))
         mask = None
         if cfg.nodal_imposition:
             mask = np.asarray(self._unwrap(settings["dirichlet dofs"])).astype(bool).ravel()
         self.mask = mask
-        self.keepalive = [settings.get("dirichlet dofs")]      # the cache key uses id(): keep the object alive
+        self.keepalive = []                                     # filled by _state_for: objects behind the cache key
         self.plan = backend.Plan(self.dim, self.n_nodes, self.nf, specs, mask)
         # multi-GPU: this process holds one slab (owned nodes + ghost planes, local ids in global order) or one part of
         # a general partition (mesher.rcb_partition: owned nodes first, then the ghosts grouped by owning rank)
@@ -255,6 +286,10 @@ class _State:
 
     # -- multigrid hierarchy (multigrid.py): a chain of coarse _State objects below this one -----------------------
     def _wrap(self, arr):
+        if self.fields is not None:              # split the concatenated node axis back into the fields
+            arr = np.asarray(arr)
+            bounds = np.cumsum(self.field_nodes)[:-1]
+            return dict(zip(self.fields, np.split(arr, bounds, axis=0)))
         return {self.dict_key: arr} if self.dict_key is not None else arr
 
     def _mg_kinds(self):
@@ -317,10 +352,31 @@ class _State:
 
     def _unwrap(self, x):
         if isinstance(x, Mapping):
+            if self.fields is not None:          # multi-field: concatenate over the node axis in key order
+                if list(x.keys()) != self.fields:
+                    raise ValueError("b200 backend: dict-valued settings must have the fields %s of the dofs dict, in that "
+                                     "order (got %s)" % (self.fields, list(x.keys())))
+                parts = [np.asarray(x[k]) for k in self.fields]
+                for k, a, n in zip(self.fields, parts, self.field_nodes):
+                    if a.shape[0] != n:
+                        raise ValueError("b200 backend: field %r has %d nodes in the dofs but %d here" % (k, n, a.shape[0]))
+                return np.concatenate(parts, axis=0)
             if self.dict_key is None or list(x.keys()) != [self.dict_key]:
                 raise ValueError("b200 backend: dict-valued settings must have exactly the field of the dofs dict")
             return np.asarray(x[self.dict_key])
         return np.asarray(x)
+
+    def _field_connectivity(self, conn, m, route, dom):
+        """Connectivity of the device set of a multi-field domain: the nodes of the field the model acts on, shifted
+        into the concatenated node numbering."""
+        if route != "element" or getattr(m, "field", None) is None:
+            raise ValueError("b200 backend: domain %d: multi-field dict dofs need models built on a named field "
+                             "(mixed_reference_domain_potential / _residual with a tagged integrand)" % dom)
+        if not isinstance(conn, Mapping) or list(conn.keys()) != self.fields:
+            raise ValueError("b200 backend: domain %d: settings['connectivity'] must be a dict with the fields %s" % (dom, self.fields))
+        if m.field not in self.fields:
+            raise ValueError("b200 backend: domain %d: the model acts on field %r, the dofs have %s" % (dom, m.field, self.fields))
+        return np.asarray(conn[m.field], dtype=np.int64) + self.node_off[m.field]
 
     # -- per-call upload of everything that lives in `settings` --------------------------------------
     def update_fields(self, settings):
@@ -375,22 +431,43 @@ class _State:
         self.h2d_bytes += N.nbytes + dN.nbytes + w.nbytes
 
 
+def _fingerprint(arr, full_bytes=1 << 20):
+    """Cheap content fingerprint of an index / mask array for the plan-cache key: shape, dtype and a hash of the bytes
+    (all of them up to 1 MiB, else ~64 Ki evenly strided items plus both ends).  id() alone can be reused after garbage
+    collection and does not see in-place edits."""
+    a = np.asarray(arr)
+    flat = a.reshape(-1)
+    if flat.nbytes <= full_bytes:
+        sample = np.ascontiguousarray(flat)
+    else:
+        step = max(1, flat.size // 65536)
+        sample = np.ascontiguousarray(np.concatenate([flat[::step], flat[:1024], flat[-1024:]]))
+    return (a.shape, a.dtype.str, hash(sample.tobytes()))
+
+
 def _state_for(cfg, dofs, settings):
     conns = settings["connectivity"]
-    ids = []
+    ids, keep = [], []
     for c in conns:
-        arr = next(iter(c.values())) if isinstance(c, Mapping) else c
-        ids.append((id(arr), tuple(np.shape(arr))))
+        for arr in (c.values() if isinstance(c, Mapping) else (c,)):
+            ids.append((id(arr),) + _fingerprint(arr))
+            keep.append(arr)
     dd = settings.get("dirichlet dofs") if cfg.nodal_imposition else None
-    if isinstance(dd, Mapping):
-        dd = next(iter(dd.values()))
-    # fingerprint of the Dirichlet mask (the plan bakes it): identity + shape + number of constrained dofs
-    mask_key = None if dd is None else (id(dd), tuple(np.shape(dd)), int(np.count_nonzero(dd)))
+    mask_key = None
+    if dd is not None:
+        parts = list(dd.values()) if isinstance(dd, Mapping) else [dd]
+        # the plan bakes the Dirichlet mask: identity + content
+        mask_key = tuple((id(p),) + _fingerprint(p) for p in parts)
+        keep.extend(parts)
     d0 = next(iter(dofs.values())) if isinstance(dofs, Mapping) else dofs
-    key = (cfg.key, tuple(ids), mask_key, tuple(np.shape(d0)))
+    mg = settings.get("b200 multigrid") if cfg.multigrid else None
+    mg_key = None if mg is None else tuple(sorted((k, tuple(v) if isinstance(v, (tuple, list)) else v) for k, v in mg.items()))
+    key = (cfg.key, tuple(ids), mask_key, tuple(np.shape(d0)), mg_key)
     st = _PLAN_CACHE.get(key)
     if st is None:
         st = _State(cfg, dofs, settings)
+        # keep every object whose id() is part of the key alive as long as the plan (a freed object's id can be reused)
+        st.keepalive = keep + [m for m in (settings.get("b200 partition"),) if m is not None] + list(cfg.model_objects)
         _PLAN_CACHE[key] = st
         while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
             _, old = _PLAN_CACHE.popitem(last=False)
@@ -440,8 +517,7 @@ def solver(dofs, settings, static_settings, newton_tol=1e-8, maxiter=30, damping
     opts = backend.KrylovOptions(cfg.krylov, rtol=tol, atol=atol, maxiter=krylov_maxiter, jacobi=cfg.precond)
 
     def wrap(flat):
-        arr = flat.reshape(d0.shape)
-        return {st.dict_key: arr} if st.dict_key is not None else arr
+        return st._wrap(flat.reshape(d0.shape))
 
     if cfg.solver_type == "linear":
         plan.linear_step(opts, st.dofs_d, vals_d, st.out_d)
@@ -496,7 +572,7 @@ def tangent_solve(dofs, rhs, settings, static_settings, transpose=False, tol=1e-
     st.d2h_bytes = out.nbytes
     last_stats = dict(plan.stats(), h2d_bytes=st.h2d_bytes, d2h_bytes=st.d2h_bytes)
     _warn_unconverged(last_stats, "tangent_solve")
-    return {st.dict_key: out} if st.dict_key is not None else out
+    return st._wrap(out)
 
 
 def adaptive_load_stepping(dofs, settings, static_settings,

@@ -54,7 +54,12 @@ enum {
   APDX_MODEL_LINEAR_ELASTICITY = 2, /* models.linear_elasticity_weak, models.py:510-635 */
   APDX_MODEL_NEO_HOOKE = 3,         /* hyperelastic_steady_state_weak + neo_hooke, models.py:917-1000,1122-1146 */
   APDX_MODEL_NEUMANN = 4,           /* models.neumann_weak, models.py:744-779 */
-  APDX_MODEL_CAPACITY = 5           /* models.forward_backward_euler_weak, models.py:1946-2010 */
+  APDX_MODEL_CAPACITY = 5,          /* models.forward_backward_euler_weak, models.py:1946-2010 */
+  APDX_MODEL_PATTERN_ONLY = 6       /* structural entries only (values and residual are zero): the all-pairs block an element
+                                       of a MULTI-FIELD dict-dof problem emits for the field pairs its integrand does not
+                                       couple (assembler._get_indices, assembler.py:79-117: every (field_i, field_j) block
+                                       is part of the BCOO, jacfwd of an uncoupled pair is an explicit zero block).  nen up
+                                       to 64, no shape tables, APDX_SET_DOMAIN. */
 };
 
 enum { APDX_MODE_NONE = 0, APDX_MODE_PLAIN_STRAIN = 1, APDX_MODE_PLAIN_STRESS = 2, APDX_MODE_3D = 3 };

@@ -200,6 +200,10 @@ def set_contributions(st, coords, dofs, settings, want_tangent=True, rows=None):
         conn = conn[rows]
     n, nen = conn.shape
     nf = st["nf"]
+    if st["model"]["name"] == "pattern_only":
+        # structural entries only: the explicit zero blocks the reference's BCOO holds for the field pairs of a
+        # multi-field problem that an integrand does not couple (assembler.py:79-117)
+        return np.zeros((n, nen * nf)), (np.zeros((n, nen * nf, nen * nf)) if want_tangent else None)
     u = dofs[conn].reshape(n, nen, nf)
     model = dict(st["model"])
     if model["name"] == "capacity":

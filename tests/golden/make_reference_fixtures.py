@@ -223,6 +223,46 @@ def potential_case(out, tag, coords, elems, ansatz, gp, dim):
     print("  %s: %d dofs, %.1f s" % (tag, n, time.time() - t), flush=True)
 
 
+def case_two_fields(out):
+    """MULTI-FIELD dict dofs executed by the reference: fields 'phi' and 'psi' (scalar, 2-D Q1 quads, the same element
+    topology but different node coordinates), two 'user potential' domains -- the first integrand touches phi only, the
+    second psi only -- so that the BCOO holds explicit zero blocks for the uncoupled field pairs (assembler.py:79-117)."""
+    c_phi, e = mesher.structured_mesh((3, 2), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "quad")
+    c_phi, e = A(c_phi), A(e)
+    c_psi = c_phi * np.array([1.0, 0.7]) + np.array([0.1, 0.2]) + 0.05 * np.sin(3.0 * c_phi[:, ::-1])
+    gp = seeder.gauss_legendre_nd(dimension=2, order=2)
+
+    def make(field, coef, a, b):
+        def integrand_fun(x_int, ansatz_fun, settings, static_settings, elem_number, set):
+            x = ansatz_fun["physical coor"](x_int)
+            f_fun = ansatz_fun[field]
+            df = jax.jacrev(f_fun)(x_int)
+            return 0.5 * coef * df @ df - (a * jnp.sin(2.0 * x @ x) + b) * f_fun(x_int)
+        return integrand_fun
+
+    ans = {"phi": spaces.fem_iso_line_quad_brick, "psi": spaces.fem_iso_line_quad_brick}
+    pot1 = models.mixed_reference_domain_potential(make("phi", 1.0, 3.0, -1.0), ans, *gp, "phi")
+    pot2 = models.mixed_reference_domain_potential(make("psi", 2.5, -2.0, 0.5), ans, *gp, "psi")
+    static_settings = flax.core.FrozenDict({"assembling mode": ("user potential", "user potential"),
+                                            "solution structure": ("nodal imposition", "nodal imposition"),
+                                            "model": (pot1, pot2), "solver type": "newton", "solver backend": "scipy",
+                                            "solver": "lapack", "verbose": -1})
+    n = c_phi.shape[0]
+    conn = {"phi": jnp.asarray(e), "psi": jnp.asarray(e)}
+    settings = {"connectivity": (conn, conn), "dirichlet dofs": {"phi": jnp.zeros(n, dtype=bool), "psi": jnp.zeros(n, dtype=bool)},
+                "node coordinates": {"phi": jnp.asarray(c_phi), "psi": jnp.asarray(c_psi)},
+                "dirichlet conditions": {"phi": jnp.zeros(n), "psi": jnp.zeros(n)}}
+    rng = np.random.default_rng(5)
+    dofs = {"phi": jnp.asarray(rng.uniform(-1, 1, n)), "psi": jnp.asarray(rng.uniform(-1, 1, n))}
+    R = assembler.assemble_residual(dofs, settings, static_settings)
+    K = assembler.assemble_tangent(dofs, settings, static_settings)
+    data, rows, cols = bcoo_arrays(K)
+    out.update({"two_fields_c_phi": c_phi, "two_fields_c_psi": c_psi, "two_fields_elems": e, "two_fields_gp_x": A(gp[0]),
+                "two_fields_gp_w": A(gp[1]), "two_fields_dofs_phi": A(dofs["phi"]), "two_fields_dofs_psi": A(dofs["psi"]),
+                "two_fields_R_phi": A(R["phi"]), "two_fields_R_psi": A(R["psi"]), "two_fields_K_data": data,
+                "two_fields_K_rows": rows, "two_fields_K_cols": cols})
+
+
 def case_potential3d(out):
     cube2 = [[0, 0, 0], [1, 0, 0], [1.1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1.2], [1, 1, 1], [0, 1, 1]]
     c, e = mesher.structured_mesh((1, 2, 2), cube2, "brick")
@@ -364,7 +404,7 @@ def case_newton_semantics(out):
     out["newton_maxiter"] = np.array(run([1.0] * 10, maxiter=3))
 
 
-CASES = {"tables": case_tables, "indices_dict": case_indices_dict, "readme3": lambda o: readme_case(3, o, "readme3"),
+CASES = {"tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
          "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "elements_more": case_elements_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 

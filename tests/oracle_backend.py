@@ -55,7 +55,7 @@ class FakePlan:
         for st in self.sets:
             assert st.conn.ndim == 2 and st.conn.min() >= 0 and st.conn.max() < self.n_nodes, "connectivity out of range"
             if st.kind != "intpoint":
-                st.n_gp = len(st.gp[1])
+                st.n_gp = 1 if st.model == "pattern_only" else len(st.gp[1])
         self.n_coo = sum(st.conn.shape[0] * (st.conn.shape[1] * self.nf) ** 2 for st in self.sets)
         self.params = [dict(st.params) for st in self.sets]
         self.coords, self.dt, self.dofs_n = None, None, None
@@ -97,7 +97,9 @@ class FakePlan:
         sets = []
         for i, st in enumerate(self.sets):
             model = dict(name=st.model, mode=st.mode, **{k: v for k, v in self.params[i].items() if v is not None})
-            if st.kind == "intpoint":
+            if st.model == "pattern_only":
+                sets.append(dict(kind="domain", etype=None, conn=st.conn, nf=self.nf, gp=None, model=model))
+            elif st.kind == "intpoint":
                 N, dN, w = st.tables
                 sets.append(dict(kind="intpoint", conn=st.conn, nf=self.nf, N=N, dNdx=dN, w=w, model=model))
             else:

@@ -119,3 +119,16 @@ def test_multigrid_rejections_host(fake):
 
 def test_verbose_lines_host(fake, capsys):
     dae_cases.test_verbose_prints_one_line_per_newton_iteration(capsys)
+
+
+def test_two_field_dict_dofs_host(fake):
+    """Multi-field dict dofs: concatenated node space, shifted connectivities, one pattern-only set per domain -- residual,
+    BCOO order / zero blocks / values and the CSR pattern against the outputs of the unmodified reference."""
+    dae_cases.test_two_field_dict_dofs_match_reference_run()
+    plan = fake.instances[0]
+    assert [s.model for s in plan.sets] == ["poisson_potential", "poisson_potential", "pattern_only", "pattern_only"]
+    assert plan.sets[2].conn.shape[1] == 8 and plan.n_nodes == 24 and plan.nf == 1
+
+
+def test_two_field_dict_dofs_newton_host(fake):
+    dae_cases.test_two_field_dict_dofs_newton_solve()

@@ -177,3 +177,82 @@ def test_verbose_prints_one_line_per_newton_iteration(capsys):
     assert np.isclose(float(lines[-1].split(": ")[1]), res)
     hist = [float(l.split(": ")[1]) for l in lines]
     assert hist[-1] < 1e-8 < hist[0]
+
+
+# ---- multi-field dict dofs -------------------------------------------------------------
+def _two_field_case():
+    """The problem of tests/golden/make_reference_fixtures.py:case_two_fields with the tagged integrands."""
+    from autopdex_b200 import models, seeder, spaces
+    from tests.test_reference_fixtures import FIX
+    e = FIX["two_fields_elems"]
+    gp = seeder.gauss_legendre_nd(dimension=2, order=2)
+    ans = {"phi": spaces.fem_iso_line_quad_brick, "psi": spaces.fem_iso_line_quad_brick}
+    src = lambda a, b: (lambda x: a * np.sin(2.0 * np.sum(x * x, axis=-1)) + b)
+    pot1 = models.mixed_reference_domain_potential(models.poisson_potential("phi", source_fun=src(3.0, -1.0)), ans, *gp, "phi")
+    pot2 = models.mixed_reference_domain_potential(
+        models.poisson_potential("psi", source_fun=src(-2.0, 0.5), coefficient_fun=lambda x: 2.5 + 0.0 * x[..., 0]), ans, *gp, "psi")
+    static_settings = {"assembling mode": ("user potential", "user potential"),
+                       "solution structure": ("nodal imposition", "nodal imposition"), "model": (pot1, pot2),
+                       "solver type": "newton", "solver backend": "b200", "solver": "cg", "type of preconditioner": "jacobi",
+                       "verbose": -1}
+    n = FIX["two_fields_c_phi"].shape[0]
+    conn = {"phi": e, "psi": e}
+    settings = {"connectivity": (conn, conn), "dirichlet dofs": {"phi": np.zeros(n, dtype=bool), "psi": np.zeros(n, dtype=bool)},
+                "node coordinates": {"phi": FIX["two_fields_c_phi"], "psi": FIX["two_fields_c_psi"]},
+                "dirichlet conditions": {"phi": np.zeros(n), "psi": np.zeros(n)}}
+    dofs = {"phi": FIX["two_fields_dofs_phi"], "psi": FIX["two_fields_dofs_psi"]}
+    return FIX, settings, static_settings, dofs, n
+
+
+def test_two_field_dict_dofs_match_reference_run():
+    """Residual, BCOO (order, explicit zero blocks, values) and CSR pattern of a two-field dict-dof problem against the
+    outputs of the unmodified reference (reference-run fixture `two_fields_*`)."""
+    import scipy.sparse as sp
+    from autopdex_b200 import assembler
+    FIX, settings, static_settings, dofs, n = _two_field_case()
+    R = assembler.assemble_residual(dofs, settings, static_settings)
+    assert set(R.keys()) == {"phi", "psi"}
+    for k in ("phi", "psi"):
+        assert np.abs(R[k] - FIX["two_fields_R_" + k]).max() / np.abs(FIX["two_fields_R_" + k]).max() < 1e-11
+    B = assembler.assemble_tangent(dofs, settings, static_settings)
+    assert np.array_equal(B.indices[:, 0], FIX["two_fields_K_rows"]) and np.array_equal(B.indices[:, 1], FIX["two_fields_K_cols"])
+    ref = FIX["two_fields_K_data"]
+    assert np.array_equal(B.data == 0.0, ref == 0.0)                       # the same explicit zero blocks
+    assert np.abs(B.data - ref).max() / np.abs(ref).max() < 2e-7           # numerical AD in the fixture generator
+    want = sp.csr_matrix(sp.coo_matrix((ref, (FIX["two_fields_K_rows"], FIX["two_fields_K_cols"])), shape=(2 * n, 2 * n)))
+    want.sort_indices()
+    K = B.sum_duplicates()
+    assert np.array_equal(K.indptr, want.indptr) and np.array_equal(K.indices, want.indices)   # pattern bit-exact
+    assert np.abs(K.data - want.data).max() / np.abs(want.data).max() < 2e-7
+
+
+def test_two_field_dict_dofs_newton_solve():
+    """The coupled (block-diagonal) system solved as ONE Newton problem: each field equals its stand-alone solve."""
+    from autopdex_b200 import models, seeder, solver, spaces
+    FIX, settings, static_settings, dofs, n = _two_field_case()
+    c = FIX["two_fields_c_phi"]
+    m_phi = np.abs(c[:, 0]) < 1e-12
+    m_psi = np.abs(c[:, 1]) < 1e-12
+    settings = dict(settings, **{"dirichlet dofs": {"phi": m_phi, "psi": m_psi},
+                                 "dirichlet conditions": {"phi": np.where(m_phi, 0.5, 0.0), "psi": np.where(m_psi, -1.0, 0.0)}})
+    zero = {"phi": np.zeros(n), "psi": np.zeros(n)}
+    sol, (steps, res, div) = solver.solver(zero, settings, static_settings, tol=1e-13)
+    assert steps == 1 and not div and res < 1e-9
+    for k, j in (("phi", 0), ("psi", 1)):
+        st1 = dict(static_settings, **{"assembling mode": ("user potential",), "solution structure": ("nodal imposition",)})
+        gp = seeder.gauss_legendre_nd(dimension=2, order=2)
+        integ = static_settings["model"][j]
+        st1["model"] = (integ,)
+        s1 = {"connectivity": ({k: settings["connectivity"][j][k]},), "dirichlet dofs": {k: settings["dirichlet dofs"][k]},
+              "node coordinates": {k: settings["node coordinates"][k]}, "dirichlet conditions": {k: settings["dirichlet conditions"][k]}}
+        # the single-field factory checks are the same object: build a one-field model of the same integrand
+        w = integ.weak
+        one = models.mixed_reference_domain_potential(
+            models.poisson_potential(k, source_fun=w.funs["source"], coefficient_fun=w.funs["coefficient"]),
+            {k: spaces.fem_iso_line_quad_brick}, *gp, k)
+        st1["model"] = (one,)
+        alone, _ = solver.solver({k: np.zeros(n)}, s1, st1, tol=1e-13)
+        assert np.linalg.norm(sol[k] - alone[k]) / np.linalg.norm(alone[k]) < 1e-9
+    with pytest.raises(ValueError):                                   # different dofs per node across the fields
+        solver.solver({"phi": np.zeros(n), "psi": np.zeros((n, 2))}, settings, static_settings)
+    solver.clear_plan_cache()
