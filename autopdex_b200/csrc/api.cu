@@ -74,7 +74,6 @@ __global__ void k_free_scatter(const int32_t *__restrict__ free_id, const double
   int32_t q = free_id[i];
   out[i] = q >= 0 ? x[q] : 0.0;  // utility.mask_op(zeros, free_dofs_flat, u_f, 'set') (implicit_diff.py:229-232)
 }
-constexpr int NORM_GRID = 592;
 __global__ void __launch_bounds__(256) k_norm_partial(const double *__restrict__ residual,
                                                       const int32_t *__restrict__ free_list, int64_t q0, int64_t q1,
                                                       double *__restrict__ partial) {

@@ -114,6 +114,8 @@ struct SetData {
   ParamView pview[APDX_PARAM_COUNT]{};
 };
 
+constexpr int NORM_GRID = 592;   // blocks of the residual-norm reduction (api.cu); KrylovWork::partial holds its partial sums + the result
+
 struct KrylovWork {
   DevBuf<double> r, p, q, s, t, phat, shat, r0, minv;
   DevBuf<double> partial;     // per-block partial sums of the fused dot products

@@ -515,7 +515,7 @@ int krylov_alloc(apdx_plan *pl) {
   APDX_CHECK(k.q.alloc(n));
   APDX_CHECK(k.minv.alloc(n));
   // per-block partial sums of the fused dot products: up to 4 sums per kernel
-  APDX_CHECK(k.partial.alloc(4 * std::max((size_t)vec_grid(), (size_t)sm_count() * 32)));
+  APDX_CHECK(k.partial.alloc(std::max({4 * (size_t)vec_grid(), 4 * (size_t)sm_count() * 32, (size_t)NORM_GRID + 8})));
   APDX_CHECK(k.scal.alloc(S_COUNT));
   APDX_CHECK(k.flags.alloc(F_COUNT));
   APDX_CHECK(k.ticket.alloc(2));

@@ -1,0 +1,72 @@
+"""The product's CUDA source, executed on the host (tests/emu): the .cu translation units are compiled with g++ against a
+functional stand-in for the CUDA runtime (threads of a block run as fibers; shuffles, votes and __syncthreads are real
+rendezvous points; stream capture records and cudaGraphLaunch replays; device buffers sit in front of inaccessible
+pages), and the -m gpu parity tests are run against that build through the unchanged C ABI.
+
+This is test infrastructure for a container without a GPU: it checks indexing, buffer sizes, launch logic, capture
+legality and numerics of the very source that nvcc compiles for sm_100a.  It is not a CPU path of the product (nothing in
+autopdex_b200 refers to it; the library is only ever loaded through an explicit APDX_LIB) and it is no substitute for the
+-m gpu run on a B200, which remains the parity gate.
+
+The quick subset below runs in the CPU suite; `bash tools/emu_suite.sh` runs every -m gpu test (except the 256^3 ones) under
+all three memory-guard modes and keeps the log under profiles/.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# the slowest emulated tests (20-40 s each: Cook's membrane load stepping, 1000+ Krylov iterations) stay in tools/emu_suite.sh
+SLOW = [
+    "tests/test_gpu_fullsize.py",
+    "tests/test_gpu_api.py::test_cook_adaptive_load_stepping_golden",
+    "tests/test_gpu_parity.py::test_g2_cook_load_stepping_golden",
+    "tests/test_gpu_api.py::test_newton_maxiter_flags_divergence_like_reference",
+    "tests/test_gpu_api.py::test_damped_newton_iteration_count_matches_oracle",
+    "tests/test_gpu_api.py::test_tangent_solve_matches_reference_sensitivity_solve",
+    "tests/test_gpu_multigrid.py::test_poisson_hex_multigrid_matches_oracle",
+    "tests/test_gpu_multigrid.py::test_neo_hooke_brick_multigrid_newton_counts",
+    "tests/test_zz_gpu_r02_dae.py::test_verbose_prints_one_line_per_newton_iteration",
+]
+
+
+def _build():
+    if shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    try:
+        import build as emu_build
+    finally:
+        sys.path.pop(0)
+    lib, n_sites = emu_build.build()
+    assert n_sites >= 60          # every kernel launch of the product goes through the stand-in
+    return lib
+
+
+def test_gpu_suite_subset_on_emulated_cuda_source():
+    lib = _build()
+    env = dict(os.environ, APDX_LIB=lib, EMU_GUARD="1")
+    cmd = [sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
+    for s in SLOW:
+        cmd += ["--deselect", s]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500)
+    out = r.stdout.decode()
+    assert r.returncode == 0, out[-4000:]
+    assert " passed" in out and "failed" not in out
+    summary = [l for l in out.splitlines() if l.startswith("[emu]")]
+    assert summary, out[-2000:]
+    # nothing leaked (every plan of the suite was destroyed), no shuffle / vote named an exited lane
+    assert "live device blocks 0 " in summary[0] and "violations 0" in summary[0], summary[0]
+
+
+def test_capture_rules_of_the_stand_in():
+    """The stand-in must be as strict as the runtime where the product depends on it: an allocation or a synchronisation
+    while a stream captures invalidates the capture (a scope-bound temporary freed inside the Krylov capture would be
+    exactly this bug)."""
+    import ctypes as C
+    lib = C.CDLL(_build())
+    assert lib.emu_selftest_capture() == 0

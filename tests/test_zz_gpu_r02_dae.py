@@ -76,6 +76,7 @@ def _settings(n):
 def test_time_stepping_manager_heat_conduction_matches_scipy_loop(scheme):
     from autopdex_b200 import dae, solver
     n, dt, n_steps = 6, 0.05, 3
+    solver.clear_plan_cache()                                      # plans of earlier tests must not count below
     coords, K, M, F, mask, values, res, settings = _settings(n)
     integ, coeffs = (dae.BackwardEuler(), [1.0, -1.0]) if scheme == "backward_euler" else (dae.BackwardDiffFormula(2), [1.5, -2.0, 0.5])
     static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": integ},

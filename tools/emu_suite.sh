@@ -1,0 +1,21 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE: every -m gpu test (except the 256^3 ones) against the emulated build of the CUDA source
+# (tests/emu), once per memory-guard mode:
+#   EMU_GUARD=1  every device block ends right in front of an inaccessible page  (over-runs fault, kernel/block/thread printed)
+#   EMU_GUARD=2  every device block starts right behind one                        (under-runs fault)
+#   EMU_GUARD=0  malloc'ed blocks between red zones, filled with 0xFF, freed blocks scribbled; 5 emulated SMs
+# The container has no GPU and no compute-sanitizer target; this is the memcheck that can run here.  Log -> profiles/.
+set -u
+cd "$(dirname "$0")/.."
+python tests/emu/build.py || exit 1
+LIB=$PWD/tests/emu/build/libapdx_b200_emu.so
+OUT=${1:-profiles/r02f_emulated_cuda_source_suite.txt}
+{
+  echo "# $(date -u +%FT%TZ)  $(git rev-parse --short HEAD)  emulated CUDA source, -m gpu suite without tests/test_gpu_fullsize.py"
+  for mode in "1 2" "2 2" "0 5"; do
+    set -- $mode
+    echo "## EMU_GUARD=$1 EMU_SMS=$2"
+    EMU_GUARD=$1 EMU_SMS=$2 APDX_LIB=$LIB python -m pytest tests -q -m gpu --deselect tests/test_gpu_fullsize.py -p no:cacheprovider 2>&1 \
+      | grep -E "^\[emu\]|passed|failed|error" 
+  done
+} | tee "$OUT"
