@@ -49,8 +49,10 @@ static Nccl g_nccl;
 
 static int load_nccl() {
   if (g_nccl.lib) return APDX_OK;
-  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  // APDX_NCCL_LIB: path of another NCCL build (like APDX_LIB for this library)
+  const char *names[] = {getenv("APDX_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char *nm : names) {
+    if (!nm || !*nm) continue;
     g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
     if (g_nccl.lib) break;
   }
@@ -233,7 +235,10 @@ int p2p_setup(apdx_plan *pl) {
   char *hd = nullptr;
   APDX_CUDA(cudaMalloc((void **)&hd, (size_t)(nr + 1) * sizeof(cudaIpcMemHandle_t)));
   int ok_local = (ce == cudaSuccess) ? 1 : 0;
-  if (!ok_local) memset(&mine, 0, sizeof(mine));
+  if (!ok_local) {
+    cudaGetLastError();   // the fallback is not an error: do not leave it for the next cudaGetLastError() check
+    memset(&mine, 0, sizeof(mine));
+  }
   APDX_CUDA(cudaMemcpy(hd + (size_t)nr * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
   APDX_NCCL(g_nccl.AllGather(hd + (size_t)nr * sizeof(mine), hd, sizeof(mine), 0 /*ncclInt8*/, g_nccl.comm, s));
   APDX_CUDA(cudaStreamSynchronize(s));

@@ -93,6 +93,10 @@ def build(force=False, verbose=False):
         raise RuntimeError("emulated build failed")
     if jobs or not os.path.exists(LIB):
         subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + ["-ldl"])
+    # stand-in for libnccl.so.2 (the product dlopen()s NCCL; multi-rank emulated runs name this file in APDX_NCCL_LIB)
+    nccl_src, nccl_lib = os.path.join(HERE, "fake_nccl.cpp"), os.path.join(OUT_DIR, "libfakenccl.so")
+    if force or newer(nccl_src, nccl_lib):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wall", nccl_src, "-o", nccl_lib, "-ldl"])
     return LIB, n_launch
 
 

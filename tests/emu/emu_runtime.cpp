@@ -300,9 +300,17 @@ const char *cudaGetErrorString(cudaError_t e) {
 }
 cudaError_t cudaGetLastError() { cudaError_t e = g_last_error; g_last_error = cudaSuccess; return e; }
 cudaError_t cudaPeekAtLastError() { return g_last_error; }
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : fail(cudaErrorInvalidValue); }
-cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+// every process emulates its own device; the index only has to be one a box could have (multi-rank runs: LOCAL_RANK)
+static int g_device = 0;
+cudaError_t cudaGetDeviceCount(int *n) { const char *e = getenv("EMU_DEVICES"); *n = e ? atoi(e) : 8; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) {
+  int n = 0;
+  cudaGetDeviceCount(&n);
+  if (d < 0 || d >= n) return fail(cudaErrorInvalidValue);
+  g_device = d;
+  return cudaSuccess;
+}
+cudaError_t cudaGetDevice(int *d) { *d = g_device; return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) {
   if (a == cudaDevAttrMultiProcessorCount) {
     const char *e = getenv("EMU_SMS");
@@ -492,6 +500,16 @@ int emu_check_red_zones(void) {
       if (u[-(ptrdiff_t)emu::RED + (ptrdiff_t)i] != 0xA5 || u[kv.second.bytes + i] != 0xA5) { ++bad; break; }
   }
   return bad;
+}
+// tests/emu/fake_nccl.cpp: run fn(arg) in stream order -- now, or as a node of the graph the stream is capturing (1 = kept)
+int emu_stream_enqueue(void *stream, void (*fn)(void *), void *arg) {
+  emu::Stream *st = emu::S((cudaStream_t)stream);
+  if (st->capture) {
+    st->capture->nodes.push_back([fn, arg]() { fn(arg); });
+    return 1;
+  }
+  fn(arg);
+  return 0;
 }
 // self-test of the capture rules (tests/test_emu_cuda_source.py): 0 = the stand-in is as strict as the runtime
 int emu_selftest_capture(void) {

@@ -101,6 +101,7 @@ def main():
         mp = int(argv[1]) if len(argv) > 1 else 20
         mn = int(argv[2]) if len(argv) > 2 else 12
         mn = max(mn, 2 * world)      # the brick is clamped at x = 0: every slab needs a free node plane of its own
+        mp = max(mp, 2 * world)      # all faces are Dirichlet faces: the first and last slab need an interior plane
         cases = [(pb, m, k, pt) for pb, m in (("poisson", mp), ("neohooke", mn)) for k in ("cg", "bicgstab")
                  for pt in ("slab", "rcb")]
     else:
