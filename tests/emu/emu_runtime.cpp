@@ -8,7 +8,9 @@
 //     synchronous copies / synchronisation on a capturing stream return the error the real runtime returns.
 #include <cuda_runtime.h>
 #include <signal.h>
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -113,7 +115,11 @@ void sync_warp(unsigned mask) { yield_to_scheduler(WAIT_WARP, mask); }
 uint64_t *warp_slots() { return g_slots[g_cur >> 5]; }
 int lane_id() { return g_cur & 31; }
 void *dyn_smem() { return g_dyn_smem.data(); }
-long long clock() { return g_clock += 1000; }
+long long clock() {   // ~2 "cycles" per nanosecond of real time: device-side time-outs (peer waits) keep their meaning
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 2 * ((long long)ts.tv_sec * 1000000000ll + ts.tv_nsec) + (++g_clock & 1);
+}
 unsigned live_mask() {
   unsigned m = 0;
   const int w0 = g_cur & ~31;
@@ -251,7 +257,8 @@ void submit(const Cfg &c, const char *name, std::function<void()> body) {
 // ---------------------------------------------------------------------------------------------------------------------
 // device memory
 // ---------------------------------------------------------------------------------------------------------------------
-struct Block { size_t bytes; void *base; size_t map_bytes; };
+struct Block { size_t bytes; void *base; size_t map_bytes; std::string shm; };
+static std::map<void *, size_t> g_ipc_maps;   // peer blocks mapped by cudaIpcOpenMemHandle
 static std::map<void *, Block> g_blocks;
 static size_t g_live_bytes = 0;
 static constexpr size_t RED = 64;
@@ -331,7 +338,7 @@ cudaError_t cudaMalloc(void **p, size_t bytes) {
   install_handler();
   if (any_capture()) return illegal_in_capture(nullptr);
   if (bytes == 0) { *p = nullptr; return cudaSuccess; }
-  Block b{bytes, nullptr, 0};
+  Block b{bytes, nullptr, 0, std::string()};
   char *user = nullptr;
   const int gm = guard_mode();
   if (gm == 1 || gm == 2) {
@@ -372,6 +379,7 @@ cudaError_t cudaFree(void *p) {
   g_live_bytes -= b.bytes;
   if (b.map_bytes) {
     munmap(b.base, b.map_bytes);
+    if (!b.shm.empty()) shm_unlink(b.shm.c_str());
   } else {
     const unsigned char *u = (const unsigned char *)p;
     for (size_t i = 0; i < RED; ++i)
@@ -480,9 +488,53 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
   *ms = (float)(b->t_ms - a->t_ms);
   return cudaSuccess;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return fail(cudaErrorNotSupported); }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return fail(cudaErrorNotSupported); }
-cudaError_t cudaIpcCloseMemHandle(void *) { return fail(cudaErrorNotSupported); }
+// CUDA IPC: a page-aligned block of the guard modes is re-mapped in place onto a POSIX shared-memory object, which the
+// peers (other host processes = other emulated GPUs) map in turn -- peer stores and volatile spins then work for real.
+// Blocks of the malloc mode cannot be shared: not supported, and the product falls back to NCCL (that path is tested too).
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+  auto it = g_blocks.find(p);
+  if (it == g_blocks.end()) return fail(cudaErrorInvalidValue);
+  Block &b = it->second;
+  if (!b.map_bytes || ((uintptr_t)p & 4095)) return fail(cudaErrorNotSupported);
+  const size_t len = (b.bytes + 4095) & ~(size_t)4095;
+  if (b.shm.empty()) {
+    static int counter = 0;
+    char name[48];
+    snprintf(name, sizeof(name), "/emuipc-%d-%d", (int)getpid(), counter++);
+    int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)len) != 0) { if (fd >= 0) close(fd); return fail(cudaErrorNotSupported); }
+    std::vector<char> keep((const char *)p, (const char *)p + b.bytes);
+    void *m = mmap(p, len, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0);
+    close(fd);
+    if (m != p) return fail(cudaErrorUnknown);
+    memcpy(p, keep.data(), b.bytes);
+    b.shm = name;
+  }
+  memset(h, 0, sizeof(*h));
+  snprintf(h->reserved, 48, "%s", b.shm.c_str());
+  memcpy(h->reserved + 48, &len, sizeof(len));
+  return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+  size_t len = 0;
+  memcpy(&len, h.reserved + 48, sizeof(len));
+  if (h.reserved[0] != '/' || len == 0) return fail(cudaErrorInvalidValue);
+  int fd = shm_open(h.reserved, O_RDWR, 0600);
+  if (fd < 0) return fail(cudaErrorInvalidValue);
+  void *m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return fail(cudaErrorMemoryAllocation);
+  g_ipc_maps[m] = len;
+  *p = m;
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *p) {
+  auto it = g_ipc_maps.find(p);
+  if (it == g_ipc_maps.end()) return fail(cudaErrorInvalidValue);
+  munmap(p, it->second);
+  g_ipc_maps.erase(it);
+  return cudaSuccess;
+}
 
 // ---- introspection for the tests ------------------------------------------------------------------------------------
 extern "C" {

@@ -72,9 +72,9 @@ long long clock();
 // ---- device built-ins ----------------------------------------------------------------------------------------------
 static inline void __syncthreads() { emu::sync_block(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::sync_warp(mask); }
-static inline void __threadfence() {}
-static inline void __threadfence_block() {}
-static inline void __threadfence_system() {}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }   // peers are other processes (shared mappings)
 static inline long long clock64() { return emu::clock(); }
 
 template <typename T> static inline T __ldg(const T *p) { return *p; }

@@ -63,11 +63,7 @@ def test_gpu_suite_subset_on_emulated_cuda_source():
     assert "live device blocks 0 " in summary[0] and "violations 0" in summary[0], summary[0]
 
 
-def test_multi_gpu_code_on_two_emulated_ranks():
-    """dist.cu + the multi-rank Krylov loop (halo exchange of slab and list partitions, all-reduces, the collective
-    partition check, CUDA graphs holding communication nodes) on two host processes: tests/multi_gpu_worker.py -- the
-    script that runs on 2/4/8 B200s -- with the emulated build and tests/emu/fake_nccl.cpp behind APDX_NCCL_LIB.
-    {Poisson nf=1, neo-Hooke nf=3} x {CG, BiCGSTAB} x {slab, RCB} against the oracle."""
+def _run_ranks(n, worker_args, extra_env=None, timeout=1500):
     lib = _build()
     import socket
     with socket.socket() as sk:
@@ -75,12 +71,30 @@ def test_multi_gpu_code_on_two_emulated_ranks():
         port = sk.getsockname()[1]
     env = dict(os.environ, APDX_LIB=lib, APDX_NCCL_LIB=os.path.join(os.path.dirname(lib), "libfakenccl.so"), EMU_GUARD="1",
                APDX_CASE_TIMEOUT="300")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), "matrix", "8", "4"]
-    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500)
+    env.pop("APDX_COMM", None)
+    env.update(extra_env or {})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py")] + worker_args
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
     out = r.stdout.decode()
-    lines = [l for l in out.splitlines() if l.startswith("multi-gpu parity")]
-    assert r.returncode == 0 and len(lines) == 8 and all(l.endswith("-> OK") for l in lines), out[-4000:]
+    return r.returncode, [l for l in out.splitlines() if l.startswith("multi-gpu parity")], out
+
+
+def test_multi_gpu_code_on_two_emulated_ranks():
+    """dist.cu + the multi-rank Krylov loop (halo exchange of slab and list partitions, the collective partition check,
+    CUDA graphs holding communication nodes, dot products through the peer-memory mailboxes = the default) on two host
+    processes: tests/multi_gpu_worker.py -- the script that runs on 2/4/8 B200s -- with the emulated build, CUDA IPC
+    emulated by POSIX shared memory and tests/emu/fake_nccl.cpp behind APDX_NCCL_LIB.
+    {Poisson nf=1, neo-Hooke nf=3} x {CG, BiCGSTAB} x {slab, RCB} against the oracle."""
+    rc, lines, out = _run_ranks(2, ["matrix", "8", "4"])
+    assert rc == 0 and len(lines) == 8 and all(l.endswith("-> OK") for l in lines), out[-4000:]
+    assert "peer mapping unavailable" not in out      # the mailbox kernels ran (not the NCCL fall-back)
+
+
+def test_nccl_allreduce_mode_on_three_emulated_ranks():
+    """APDX_COMM=nccl (ncclAllReduce + one-thread stage kernel) and an odd rank count."""
+    rc, lines, out = _run_ranks(3, ["neohooke", "6", "bicgstab", "rcb"], {"APDX_COMM": "nccl"})
+    assert rc == 0 and len(lines) == 1 and lines[0].endswith("-> OK"), out[-4000:]
 
 
 def test_capture_rules_of_the_stand_in():

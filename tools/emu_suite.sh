@@ -19,7 +19,7 @@ OUT=${1:-profiles/r02f_emulated_cuda_source_suite.txt}
       | grep -E "^\[emu\]|passed|failed|error" 
   done
   for n in 2 4 8; do
-    echo "## multi-rank: tests/multi_gpu_worker.py matrix on $n emulated ranks (fake NCCL over Unix sockets, EMU_GUARD=1)"
+    echo "## multi-rank: tests/multi_gpu_worker.py matrix on $n emulated ranks (fake NCCL over Unix sockets, CUDA IPC over POSIX shm: mailbox all-reduce, EMU_GUARD=1)"
     EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=600 \
       python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29800 + n)) \
       tests/multi_gpu_worker.py matrix 12 8 2>&1 | grep "multi-gpu parity"
