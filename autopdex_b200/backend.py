@@ -439,6 +439,18 @@ def comm_allreduce_host(values, op="sum"):
     return v
 
 
+def comm_exchange_planes(arr, lo_count, hi_count, rank_lo, rank_hi):
+    """Slab neighbours swap the boundary blocks of a host array laid out [ghost_lo | owned | ghost_hi] (flattened; counts
+    in items): returns a float64 copy whose ghost blocks hold the neighbours' adjacent owned blocks
+    (apdx_comm_exchange_planes).  Without a communicator the array comes back unchanged."""
+    v = np.ascontiguousarray(arr, dtype=np.float64)
+    d = DeviceArray.from_host(v.ravel())
+    _lib.check(_lib.load().apdx_comm_exchange_planes(d.ptr, v.size, int(lo_count), int(hi_count), int(rank_lo), int(rank_hi)))
+    out = np.array(d.download()).reshape(v.shape)
+    d.free()
+    return out
+
+
 def measure_fp64_peak():
     tf = C.c_double(0.0)
     _lib.check(_lib.load().apdx_measure_fp64_peak(C.byref(tf)))

@@ -186,6 +186,11 @@ static int mg_prepare(apdx_plan *pl, const double *dofs_d) {
   if (apdx_plan *c = pl->mg.coarse) {
     APDX_CHECK(ensure_newton_buffers(c));
     APDX_CHECK(mg_inject(pl, dofs_d, c->mg.dofs.p));
+    // partitioned hierarchy: a coarse ghost plane may coincide with a fine plane this rank does not hold (two planes
+    // beyond its owned range) -- the neighbour, which owns that coarse plane, sends its injected values
+    if (comm_active())
+      APDX_CHECK(comm_exchange_planes(c->mg.dofs.p, c->n_dofs, c->owned_begin, c->n_dofs - c->owned_end, c->rank_lo, c->rank_hi,
+                                      pl->stream));
     APDX_CHECK(assemble_internal(c, c->mg.dofs.p, 4, c->residual.p));
     pl->stats.kernel_launches += c->stats.kernel_launches;
     c->stats = Stats();

@@ -309,6 +309,7 @@ bool comm_active();
 int comm_size();
 int comm_allreduce_sum(double *buf_d, int count, cudaStream_t s);
 int comm_halo_exchange(apdx_plan *pl, double *x_d, cudaStream_t s);
+int comm_exchange_planes(double *buf_d, int64_t n, int64_t lo, int64_t hi, int rank_lo, int rank_hi, cudaStream_t s);
 int comm_halo_setup(apdx_plan *pl);
 int comm_halo_setup_lists(apdx_plan *pl);
 int p2p_setup(apdx_plan *pl);

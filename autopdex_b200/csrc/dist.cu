@@ -156,6 +156,29 @@ int comm_halo_exchange(apdx_plan *pl, double *x_d, cudaStream_t s) {
   return APDX_OK;
 }
 
+// Slab neighbours swap boundary blocks of ANY device vector laid out [ghost_lo | owned | ghost_hi] (full-dof vectors:
+// the injected state of a coarse multigrid level, coordinates / masks of a partitioned hierarchy): the first `lo` owned
+// entries go to rank_lo and its answer fills [0, lo); the last `hi` owned entries go to rank_hi and its answer fills
+// [n - hi, n).  Both sides of an interface must pass the same count (one node plane).
+int comm_exchange_planes(double *buf_d, int64_t n, int64_t lo, int64_t hi, int rank_lo, int rank_hi, cudaStream_t s) {
+  if (!comm_active()) return APDX_OK;
+  APDX_REQUIRE(lo >= 0 && hi >= 0 && n - lo - hi >= lo && n - lo - hi >= hi, APDX_ERR_INVALID,
+               "plane exchange: the owned block of a vector of %lld entries with %lld + %lld ghost entries is smaller than a plane",
+               (long long)n, (long long)lo, (long long)hi);
+  if ((rank_lo < 0 || lo == 0) && (rank_hi < 0 || hi == 0)) return APDX_OK;
+  APDX_NCCL(g_nccl.GroupStart());
+  if (rank_lo >= 0 && lo > 0) {
+    APDX_NCCL(g_nccl.Send(buf_d + lo, (size_t)lo, ncclFloat64, rank_lo, g_nccl.comm, s));
+    APDX_NCCL(g_nccl.Recv(buf_d, (size_t)lo, ncclFloat64, rank_lo, g_nccl.comm, s));
+  }
+  if (rank_hi >= 0 && hi > 0) {
+    APDX_NCCL(g_nccl.Send(buf_d + n - 2 * hi, (size_t)hi, ncclFloat64, rank_hi, g_nccl.comm, s));
+    APDX_NCCL(g_nccl.Recv(buf_d + n - hi, (size_t)hi, ncclFloat64, rank_hi, g_nccl.comm, s));
+  }
+  APDX_NCCL(g_nccl.GroupEnd());
+  return APDX_OK;
+}
+
 // neighbours tell each other how many owned entries the other side ghosts, and where their owned range ends
 int comm_halo_setup(apdx_plan *pl) {
   int64_t *buf = nullptr;
@@ -321,6 +344,13 @@ int apdx_comm_allreduce_host(double *inout_h, int32_t count, int32_t op) {
   APDX_CUDA(cudaStreamSynchronize(0));
   APDX_CUDA(cudaMemcpy(inout_h, buf, count * sizeof(double), cudaMemcpyDeviceToHost));
   cudaFree(buf);
+  return APDX_OK;
+}
+
+int apdx_comm_exchange_planes(double *buf_d, int64_t n, int64_t lo_count, int64_t hi_count, int32_t rank_lo, int32_t rank_hi) {
+  APDX_REQUIRE(buf_d || n == 0, APDX_ERR_INVALID, "NULL argument");
+  APDX_CHECK(comm_exchange_planes(buf_d, n, lo_count, hi_count, rank_lo, rank_hi, 0));
+  APDX_CUDA(cudaStreamSynchronize(0));
   return APDX_OK;
 }
 

@@ -596,7 +596,7 @@ int spmv_launch(apdx_plan *pl, const double *x, double *y, const double *w, int 
 }
 
 // after a dot-product kernel: multi-GPU reduction of the pending sums + scalar stage
-static int finish_stage(apdx_plan *pl, int stage, int nv) {
+int krylov_finish_stage(apdx_plan *pl, int stage, int nv) {
   const Comm c = comm_of(pl);
   if (!c.multi) return APDX_OK;
   KrylovWork &k = pl->kw;
@@ -686,12 +686,12 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
     k_cg_init<<<VG, VEC_BLOCK, 0, s>>>(rhs, k.q.p, k.minv.p, k.r.p, k.p.p, i0, i1, k.partial.p, k.ticket.p, k.scal.p,
                                        k.flags.p, ST_CG_INIT, fused);
     pl->stats.kernel_launches += 1;
-    APDX_CHECK(finish_stage(pl, ST_CG_INIT, 3));
+    APDX_CHECK(krylov_finish_stage(pl, ST_CG_INIT, 3));
   } else {
     k_bi_init<<<VG, VEC_BLOCK, 0, s>>>(rhs, k.t.p, k.r.p, k.r0.p, k.p.p, k.q.p, i0, i1, k.partial.p, k.ticket.p,
                                        k.scal.p, k.flags.p, fused);
     pl->stats.kernel_launches += 1;
-    APDX_CHECK(finish_stage(pl, ST_BI_INIT, 3));
+    APDX_CHECK(krylov_finish_stage(pl, ST_BI_INIT, 3));
   }
 
   int32_t *fl_pin = reinterpret_cast<int32_t *>(pl->pinned);
@@ -724,14 +724,14 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
         TR(0);
         APDX_CHECK(launch_spmv<1>(pl, k.p.p, k.q.p, k.p.p, ST_CG_PQ, 1));
         TR(1);
-        APDX_CHECK(finish_stage(pl, ST_CG_PQ, 1));
+        APDX_CHECK(krylov_finish_stage(pl, ST_CG_PQ, 1));
         TR(2);
         if (vec16) k_cg_update<true><<<VG, VEC_BLOCK, 0, s>>>(k.q.p, k.minv.p, k.r.p, i0, i1, k.partial.p, k.ticket.p, k.scal.p,
                                                              k.flags.p, fused);
         else k_cg_update<false><<<VG, VEC_BLOCK, 0, s>>>(k.q.p, k.minv.p, k.r.p, i0, i1, k.partial.p, k.ticket.p, k.scal.p,
                                                          k.flags.p, fused);
         TR(3);
-        APDX_CHECK(finish_stage(pl, ST_CG_UPDATE, 2));
+        APDX_CHECK(krylov_finish_stage(pl, ST_CG_UPDATE, 2));
         TR(4);
         if (vec16) k_cg_p<true><<<VG, VEC_BLOCK, 0, s>>>(k.r.p, k.minv.p, k.p.p, x, i0, i1, k.scal.p, k.flags.p, k.ticket.p + 1);
         else k_cg_p<false><<<VG, VEC_BLOCK, 0, s>>>(k.r.p, k.minv.p, k.p.p, x, i0, i1, k.scal.p, k.flags.p, k.ticket.p + 1);
@@ -744,23 +744,23 @@ int krylov_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
         TR(0);
         APDX_CHECK(launch_spmv<1>(pl, k.phat.p, k.q.p, k.r0.p, ST_BI_R0V, 1));
         TR(1);
-        APDX_CHECK(finish_stage(pl, ST_BI_R0V, 1));
+        APDX_CHECK(krylov_finish_stage(pl, ST_BI_R0V, 1));
         TR(2);
         k_bi_s<<<VG, VEC_BLOCK, 0, s>>>(k.r.p, k.q.p, k.minv.p, k.s.p, k.shat.p, i0, i1, k.partial.p, k.ticket.p, k.scal.p,
                                         k.flags.p, fused);
         TR(3);
-        APDX_CHECK(finish_stage(pl, ST_BI_S, 1));
+        APDX_CHECK(krylov_finish_stage(pl, ST_BI_S, 1));
         TR(4);
         if (c.multi) APDX_CHECK(comm_halo_exchange(pl, k.shat.p, s));
         TR(0);
         APDX_CHECK(launch_spmv<2>(pl, k.shat.p, k.t.p, k.s.p, ST_BI_T, 1));
         TR(1);
-        APDX_CHECK(finish_stage(pl, ST_BI_T, 2));
+        APDX_CHECK(krylov_finish_stage(pl, ST_BI_T, 2));
         TR(2);
         k_bi_x<<<VG, VEC_BLOCK, 0, s>>>(k.phat.p, k.shat.p, k.s.p, k.t.p, k.r0.p, x, k.r.p, i0, i1, k.partial.p, k.ticket.p,
                                         k.scal.p, k.flags.p, fused);
         TR(3);
-        APDX_CHECK(finish_stage(pl, ST_BI_X, 2));
+        APDX_CHECK(krylov_finish_stage(pl, ST_BI_X, 2));
         TR(4);
         pl->stats.kernel_launches += 3;
       }

@@ -153,5 +153,8 @@ unsigned vec_grid();   // grid of the streaming vector kernels (krylov.cu)
 // y = A x on the plan's sliced-ELL matrix, optionally with fused dot products (w.y [, y.y]) reduced into sc[S_PEND ..]
 // and the scalar stage applied by the last block; check_done: no-op once the done flag is set (krylov.cu)
 int spmv_launch(apdx_plan *pl, const double *x, double *y, const double *w, int ndot, int stage, int check_done);
+// after a kernel that left locally reduced sums in sc[S_PEND ..]: multi-GPU all-reduce of the nv sums (peer-memory
+// mailboxes or ncclAllReduce) followed by the scalar stage; no-op on one GPU, where the producing kernel applied it
+int krylov_finish_stage(apdx_plan *pl, int stage, int nv);
 
 }  // namespace apdx

@@ -12,8 +12,14 @@
 //     iteration after every assembly; the same polynomial before and after the coarse correction, so the cycle is a
 //     symmetric operator and plain PCG applies;
 //   * coarsest level: a Chebyshev polynomial of higher degree over a wider interval.
-// Every level's products run through the sliced-ELL SpMV of krylov.cu.  Single GPU (the partitioned variant needs a
-// halo exchange per level and transfer; not built).
+// Every level's products run through the sliced-ELL SpMV of krylov.cu.
+//
+// Multi-GPU (slab partitions): every level is partitioned like the finest one -- the rank that owns fine
+// node plane 2I owns coarse plane I, one ghost plane per side -- so a level's vectors are [ghost_lo | owned | ghost_hi] in
+// its reduced numbering, every kernel works on the owned range [f0, f1), every product is preceded by the level's halo
+// exchange, the restriction by a halo exchange of the fine residual (R = P^T needs the ghost plane's rows), the
+// prolongation by one of the coarse correction, and the dot products of the PCG loop / the power iteration are
+// all-reduced.  The iterates are those of the single-GPU cycle up to the summation order of the dot products.
 #include <math.h>
 
 #include <vector>
@@ -27,8 +33,9 @@ namespace apdx {
 // Chebyshev / Jacobi step:  r = b - y (y == nullptr: r = b) ; d = cd d + cr minv r ; x = (zero_x ? 0 : x) + d
 __global__ void __launch_bounds__(VEC_BLOCK) k_cheb_step(const double *__restrict__ b, const double *__restrict__ y,
                                                          const double *__restrict__ minv, double *__restrict__ d,
-                                                         double *__restrict__ x, double cd, double cr, int zero_x, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+                                                         double *__restrict__ x, double cd, double cr, int zero_x, int64_t i0,
+                                                         int64_t i1) {
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
     const double r = y ? b[i] - y[i] : b[i];
     const double di = (cd != 0.0 ? cd * d[i] : 0.0) + cr * minv[i] * r;
     d[i] = di;
@@ -36,17 +43,19 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_cheb_step(const double *__restric
   }
 }
 // r = b - y (r may alias y)
-__global__ void __launch_bounds__(VEC_BLOCK) k_residual(const double *__restrict__ b, const double *y, double *r, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+__global__ void __launch_bounds__(VEC_BLOCK) k_residual(const double *__restrict__ b, const double *y, double *r, int64_t i0,
+                                                        int64_t i1) {
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x)
     r[i] = b[i] - y[i];
 }
-// y (+)= M x for a CSR matrix, one thread per row (transfer operators: 1..8 nf entries per row of P, <= 27 of R)
+// y (+)= M x for the rows [r0, r1) of a CSR matrix, one thread per row (transfer operators: 1..8 nf entries per row of
+// P, <= 27 of R)
 template <bool ADD>
 __global__ void __launch_bounds__(256) k_csr_spmv(const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
                                                   const double *__restrict__ val, const double *__restrict__ x,
-                                                  double *__restrict__ y, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                                                  double *__restrict__ y, int64_t r0, int64_t r1) {
+  const int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r1) return;
   double acc = 0.0;
   for (int32_t j = ptr[i]; j < ptr[i + 1]; ++j) acc += val[j] * __ldg(x + idx[j]);
   y[i] = ADD ? y[i] + acc : acc;
@@ -57,19 +66,19 @@ __global__ void k_inject(const double *__restrict__ fine, const int32_t *__restr
   if (i < n) coarse[i] = fine[inject[i]];
 }
 // deterministic start vector of the power iteration
-__global__ void k_power_start(double *__restrict__ x, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+__global__ void k_power_start(double *__restrict__ x, int64_t i0, int64_t i1, uint64_t seed) {
+  const int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i1) return;
+  uint64_t h = ((uint64_t)i + seed) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
   h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
   x[i] = 0.5 + (double)(h & 0xfffff) / 1048576.0;
 }
 // x <- v = scale * minv * y (y = A x); sums (x.x, v.v): |v| / |x| -> scale * lambda_max(D^-1 A)
 __global__ void __launch_bounds__(VEC_BLOCK) k_power_step(const double *__restrict__ y, const double *__restrict__ minv,
-                                                          double *__restrict__ x, int64_t n, double scale, double *partial,
-                                                          unsigned int *ticket, double *sc, int32_t *fl) {
+                                                          double *__restrict__ x, int64_t i0, int64_t i1, double scale,
+                                                          double *partial, unsigned int *ticket, double *sc, int32_t *fl) {
   double acc[2] = {0.0, 0.0};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
     const double v = scale * minv[i] * y[i], xi = x[i];
     acc[0] += xi * xi;
     acc[1] += v * v;
@@ -77,61 +86,62 @@ __global__ void __launch_bounds__(VEC_BLOCK) k_power_step(const double *__restri
   }
   reduce_finalize<2>(acc, partial, ticket, sc, fl, ST_NONE, 1);
 }
+// the sliced-ELL matrix holds the owned rows [row0, row0 + n) of the level (all rows on one GPU)
 __global__ void k_jacobi_inv_mg(const double *__restrict__ sell_val, const int64_t *__restrict__ valptr,
-                                const int32_t *__restrict__ diag, int64_t n, int nf, double *__restrict__ minv) {
+                                const int32_t *__restrict__ diag, int64_t row0, int64_t n, int nf, double *__restrict__ minv) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t slice = (i / (64 * nf)) * nf + (i % nf);
-  minv[i] = diag[i] >= 0 ? 1.0 / sell_val[valptr[slice] + diag[i]] : 1.0;
+  minv[row0 + i] = diag[i] >= 0 ? 1.0 / sell_val[valptr[slice] + diag[i]] : 1.0;
 }
 
 // ---- multigrid-PCG vector kernels -------------------------------------------------------------------------------
 // r = b - q (q == nullptr: r = b) ; sums (r.r, b.b)
 __global__ void __launch_bounds__(VEC_BLOCK) k_mg_init(const double *__restrict__ b, const double *__restrict__ q,
-                                                       double *__restrict__ r, int64_t n, double *partial,
-                                                       unsigned int *ticket, double *sc, int32_t *fl) {
+                                                       double *__restrict__ r, int64_t i0, int64_t i1, double *partial,
+                                                       unsigned int *ticket, double *sc, int32_t *fl, int fused) {
   double acc[2] = {0.0, 0.0};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
     const double bi = b[i], ri = q ? bi - q[i] : bi;
     r[i] = ri;
     acc[0] += ri * ri; acc[1] += bi * bi;
   }
-  reduce_finalize<2>(acc, partial, ticket, sc, fl, ST_MG_INIT, 1);
+  reduce_finalize<2>(acc, partial, ticket, sc, fl, ST_MG_INIT, fused);
 }
 // sums (r.z); first != 0: p = z as well
 __global__ void __launch_bounds__(VEC_BLOCK) k_mg_rz(const double *__restrict__ r, const double *__restrict__ z,
-                                                     double *__restrict__ p, int first, int64_t n, double *partial,
-                                                     unsigned int *ticket, double *sc, int32_t *fl) {
+                                                     double *__restrict__ p, int first, int64_t i0, int64_t i1, double *partial,
+                                                     unsigned int *ticket, double *sc, int32_t *fl, int fused) {
   if (!first && fl[F_DONE]) return;
   double acc[1] = {0.0};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
     const double zi = z[i];
     acc[0] += r[i] * zi;
     if (first) p[i] = zi;
   }
-  reduce_finalize<1>(acc, partial, ticket, sc, fl, first ? ST_MG_RZ0 : ST_MG_RZ, 1);
+  reduce_finalize<1>(acc, partial, ticket, sc, fl, first ? ST_MG_RZ0 : ST_MG_RZ, fused);
 }
 // x += alpha p ; r -= alpha q ; sums (r.r)
 __global__ void __launch_bounds__(VEC_BLOCK) k_mg_update(const double *__restrict__ p, const double *__restrict__ q,
-                                                         double *__restrict__ x, double *__restrict__ r, int64_t n,
-                                                         double *partial, unsigned int *ticket, double *sc, int32_t *fl) {
+                                                         double *__restrict__ x, double *__restrict__ r, int64_t i0, int64_t i1,
+                                                         double *partial, unsigned int *ticket, double *sc, int32_t *fl, int fused) {
   if (fl[F_DONE]) return;
   const double alpha = sc[S_ALPHA];
   double acc[1] = {0.0};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
     x[i] += alpha * p[i];
     const double ri = r[i] - alpha * q[i];
     r[i] = ri;
     acc[0] += ri * ri;
   }
-  reduce_finalize<1>(acc, partial, ticket, sc, fl, ST_MG_RR, 1);
+  reduce_finalize<1>(acc, partial, ticket, sc, fl, ST_MG_RR, fused);
 }
 // p = z + beta p
-__global__ void __launch_bounds__(VEC_BLOCK) k_mg_p(const double *__restrict__ z, double *__restrict__ p, int64_t n,
+__global__ void __launch_bounds__(VEC_BLOCK) k_mg_p(const double *__restrict__ z, double *__restrict__ p, int64_t i0, int64_t i1,
                                                     const double *sc, const int32_t *fl) {
   if (fl[F_DONE]) return;
   const double beta = sc[S_BETA];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = z[i] + beta * p[i];
 }
 
@@ -140,6 +150,12 @@ static unsigned vgrid(int64_t n) {
   const int64_t nb = (n + VEC_BLOCK - 1) / VEC_BLOCK;
   const int64_t cap = vec_grid();
   return (unsigned)(nb < 1 ? 1 : (nb < cap ? nb : cap));
+}
+
+// y = A x on the level's owned rows; partitioned levels refresh the ghost entries of x first
+static int mg_spmv(apdx_plan *pl, double *x, double *y) {
+  if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, x, pl->stream));
+  return spmv_launch(pl, x, y, nullptr, 0, ST_NONE, 0);
 }
 
 static int mg_alloc(apdx_plan *pl) {
@@ -152,6 +168,10 @@ static int mg_alloc(apdx_plan *pl) {
     APDX_CHECK(m.x.alloc(n));
     APDX_CHECK(m.b.alloc(n));
     APDX_CHECK(m.ev.alloc(n));
+    if (comm_active()) {   // ghost entries travel through NCCL before they are ever written: keep them finite
+      for (DevBuf<double> *v : {&m.d, &m.r, &m.x, &m.b, &m.ev, &m.minv})
+        APDX_CUDA(cudaMemsetAsync(v->p, 0, (size_t)n * sizeof(double), pl->stream));
+    }
   }
   return krylov_alloc(pl);
 }
@@ -163,22 +183,24 @@ int mg_level_setup(apdx_plan *pl) {
   MgLevel &m = pl->mg;
   KrylovWork &k = pl->kw;
   cudaStream_t s = pl->stream;
-  const int64_t n = pl->n_free;
-  k_jacobi_inv_mg<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pl->sell.val.p, pl->sell.valptr.p, pl->sell.diag.p, n,
+  const int64_t i0 = pl->f0, i1 = pl->f1, n = i1 - i0;
+  APDX_REQUIRE(pl->sell.n_rows == n, APDX_ERR_STATE, "multigrid level: the sliced-ELL matrix does not hold the owned rows");
+  k_jacobi_inv_mg<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pl->sell.val.p, pl->sell.valptr.p, pl->sell.diag.p, i0, n,
                                                               pl->sell.nf, m.minv.p);
   // power iteration on D^-1 A; the last step's |D^-1 A x| / |x| is the estimate.  The first set-up of a plan runs 12
   // steps from a pseudo-random vector; later tangents (Newton steps, load steps: the scaled spectrum hardly moves)
   // refine the kept vector with 3 steps.  The vector is renormalised by the host-free trick of dividing by a power
   // of two of the running estimate, so that it neither over- nor underflows over many Newton steps.
   const bool first = m.lmax == 0.0;
-  if (first) k_power_start<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m.ev.p, n);
+  if (first) k_power_start<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m.ev.p, i0, i1, 0ull);
   const int steps = first ? 12 : 3;
   for (int it = 0; it < steps; ++it) {
-    APDX_CHECK(spmv_launch(pl, m.ev.p, m.r.p, nullptr, 0, ST_NONE, 0));
-    k_power_step<<<vgrid(n), VEC_BLOCK, 0, s>>>(m.r.p, m.minv.p, m.ev.p, n, first ? 1.0 : 1.0 / m.lmax, k.partial.p, k.ticket.p,
-                                                k.scal.p, k.flags.p);
+    APDX_CHECK(mg_spmv(pl, m.ev.p, m.r.p));
+    k_power_step<<<vgrid(n), VEC_BLOCK, 0, s>>>(m.r.p, m.minv.p, m.ev.p, i0, i1, first ? 1.0 : 1.0 / m.lmax, k.partial.p,
+                                                k.ticket.p, k.scal.p, k.flags.p);
     pl->stats.kernel_launches += 1;
   }
+  if (comm_active()) APDX_CHECK(comm_allreduce_sum(k.scal.p + S_PEND, 2, s));   // (x.x, v.v) over all ranks
   double sc_h[2] = {0, 0};
   APDX_CUDA(cudaMemcpyAsync(sc_h, k.scal.p + S_PEND, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   APDX_CUDA(cudaStreamSynchronize(s));
@@ -202,12 +224,12 @@ struct Cheb {
 static int mg_smooth(apdx_plan *pl, const double *b, double *x, bool zero_init, int degree, double ratio) {
   MgLevel &m = pl->mg;
   cudaStream_t s = pl->stream;
-  const int64_t n = pl->n_free;
+  const int64_t i0 = pl->f0, i1 = pl->f1;
   Cheb c(m.lmax, ratio);
   for (int j = 0; j < degree; ++j) {
     const double *y = nullptr;
     if (!(zero_init && j == 0)) {
-      APDX_CHECK(spmv_launch(pl, x, m.r.p, nullptr, 0, ST_NONE, 0));
+      APDX_CHECK(mg_spmv(pl, x, m.r.p));
       y = m.r.p;
     }
     double cd, cr;
@@ -217,7 +239,7 @@ static int mg_smooth(apdx_plan *pl, const double *b, double *x, bool zero_init, 
       cd = rho_n * c.rho; cr = 2.0 * rho_n / c.delta;
       c.rho = rho_n;
     }
-    k_cheb_step<<<vgrid(n), VEC_BLOCK, 0, s>>>(b, y, m.minv.p, m.d.p, x, cd, cr, (zero_init && j == 0) ? 1 : 0, n);
+    k_cheb_step<<<vgrid(i1 - i0), VEC_BLOCK, 0, s>>>(b, y, m.minv.p, m.d.p, x, cd, cr, (zero_init && j == 0) ? 1 : 0, i0, i1);
     pl->stats.kernel_launches += 1;
   }
   return APDX_OK;
@@ -227,18 +249,22 @@ static int mg_smooth(apdx_plan *pl, const double *b, double *x, bool zero_init, 
 static int mg_vcycle(apdx_plan *pl, const double *b, double *x, apdx_plan *top) {
   MgLevel &m = pl->mg;
   cudaStream_t s = pl->stream;
-  const int64_t n = pl->n_free;
+  const int64_t i0 = pl->f0, i1 = pl->f1;
   if (!m.coarse) {
     APDX_CHECK(mg_smooth(pl, b, x, true, m.coarsest, m.coarsest_ratio));
   } else {
     apdx_plan *c = m.coarse;
+    const int64_t c0 = c->f0, c1 = c->f1;
     APDX_CHECK(mg_smooth(pl, b, x, true, m.pre, m.ratio));
-    APDX_CHECK(spmv_launch(pl, x, m.r.p, nullptr, 0, ST_NONE, 0));
-    k_residual<<<vgrid(n), VEC_BLOCK, 0, s>>>(b, m.r.p, m.r.p, n);
-    k_csr_spmv<false><<<(unsigned)((c->n_free + 255) / 256), 256, 0, s>>>(m.R.ptr.p, m.R.idx.p, m.R.val.p, m.r.p, c->mg.b.p,
-                                                                         c->n_free);
+    APDX_CHECK(mg_spmv(pl, x, m.r.p));
+    k_residual<<<vgrid(i1 - i0), VEC_BLOCK, 0, s>>>(b, m.r.p, m.r.p, i0, i1);
+    // R = P^T: an owned coarse row also collects from the fine ghost plane next to it
+    if (comm_active()) APDX_CHECK(comm_halo_exchange(pl, m.r.p, s));
+    k_csr_spmv<false><<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, s>>>(m.R.ptr.p, m.R.idx.p, m.R.val.p, m.r.p, c->mg.b.p, c0, c1);
     APDX_CHECK(mg_vcycle(c, c->mg.b.p, c->mg.x.p, top));
-    k_csr_spmv<true><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m.P.ptr.p, m.P.idx.p, m.P.val.p, c->mg.x.p, x, n);
+    // an owned fine row next to the interface interpolates from the coarse ghost plane
+    if (comm_active()) APDX_CHECK(comm_halo_exchange(c, c->mg.x.p, s));
+    k_csr_spmv<true><<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, s>>>(m.P.ptr.p, m.P.idx.p, m.P.val.p, c->mg.x.p, x, i0, i1);
     top->stats.kernel_launches += 3;
     APDX_CHECK(mg_smooth(pl, b, x, false, m.post, m.ratio));
   }
@@ -254,14 +280,19 @@ static int mg_vcycle(apdx_plan *pl, const double *b, double *x, apdx_plan *top) 
 int mg_pcg_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, double *x, int32_t *iters, double *relres) {
   APDX_REQUIRE(o->method == APDX_KRYLOV_CG, APDX_ERR_UNSUPPORTED,
                "the multigrid preconditioner is used with 'solver': 'cg' (symmetric V-cycle)");
-  APDX_REQUIRE(!comm_active(), APDX_ERR_UNSUPPORTED, "the multigrid preconditioner runs on one GPU (no partitioned hierarchy)");
-  for (apdx_plan *l = pl; l; l = l->mg.coarse)
+  const bool multi = comm_active();
+  for (apdx_plan *l = pl; l; l = l->mg.coarse) {
     APDX_REQUIRE(l->mg.ready, APDX_ERR_STATE, "multigrid hierarchy not set up for the current tangent");
+    APDX_REQUIRE(!multi || !l->hl.active, APDX_ERR_UNSUPPORTED,
+                 "the partitioned multigrid hierarchy needs slab partitions (apdx_plan_set_partition) on every level");
+  }
   KrylovWork &k = pl->kw;
   cudaStream_t s = pl->stream;
-  const int64_t n = pl->n_free;
-  const unsigned VG = vgrid(n);
-  const int maxiter = o->maxiter > 0 ? o->maxiter : (int)std::min<int64_t>(10 * n, 2000000000ll);
+  const int64_t i0 = pl->f0, i1 = pl->f1, n = pl->n_free;
+  const unsigned VG = vgrid(i1 - i0);
+  const int fused = multi ? 0 : 1;
+  const int64_t n_glob_hint = n * (int64_t)(multi ? comm_size() : 1);
+  const int maxiter = o->maxiter > 0 ? o->maxiter : (int)std::min<int64_t>(10 * n_glob_hint, 2000000000ll);
   nvtx_push("apdx:krylov_multigrid");
   double sc_h[S_COUNT] = {0};
   sc_h[S_TOL2] = o->rtol * o->rtol;
@@ -272,13 +303,15 @@ int mg_pcg_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
   double *z = k.minv.p;   // the Jacobi vector of the plain loops is free here: z = V(r)
   if (pl->x0_is_zero) {
     pl->x0_is_zero = false;
-    k_mg_init<<<VG, VEC_BLOCK, 0, s>>>(rhs, nullptr, k.r.p, n, k.partial.p, k.ticket.p, k.scal.p, k.flags.p);
+    k_mg_init<<<VG, VEC_BLOCK, 0, s>>>(rhs, nullptr, k.r.p, i0, i1, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, fused);
   } else {
-    APDX_CHECK(spmv_launch(pl, x, k.q.p, nullptr, 0, ST_NONE, 0));
-    k_mg_init<<<VG, VEC_BLOCK, 0, s>>>(rhs, k.q.p, k.r.p, n, k.partial.p, k.ticket.p, k.scal.p, k.flags.p);
+    APDX_CHECK(mg_spmv(pl, x, k.q.p));
+    k_mg_init<<<VG, VEC_BLOCK, 0, s>>>(rhs, k.q.p, k.r.p, i0, i1, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, fused);
   }
+  APDX_CHECK(krylov_finish_stage(pl, ST_MG_INIT, 2));
   APDX_CHECK(mg_vcycle(pl, k.r.p, z, pl));
-  k_mg_rz<<<VG, VEC_BLOCK, 0, s>>>(k.r.p, z, k.p.p, 1, n, k.partial.p, k.ticket.p, k.scal.p, k.flags.p);
+  k_mg_rz<<<VG, VEC_BLOCK, 0, s>>>(k.r.p, z, k.p.p, 1, i0, i1, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, fused);
+  APDX_CHECK(krylov_finish_stage(pl, ST_MG_RZ0, 1));
   pl->stats.kernel_launches += 2;
   int32_t *fl_pin = reinterpret_cast<int32_t *>(pl->pinned);
   double *sc_pin = pl->pinned + 8;
@@ -291,17 +324,26 @@ int mg_pcg_solve(apdx_plan *pl, const apdx_krylov_opts *o, const double *rhs, do
     if (fl_pin[F_DONE] || launched >= maxiter) break;
     const int todo = maxiter - launched < chunk ? maxiter - launched : chunk;
     for (int it = 0; it < todo; ++it) {
+      if (multi) APDX_CHECK(comm_halo_exchange(pl, k.p.p, s));
       APDX_CHECK(spmv_launch(pl, k.p.p, k.q.p, k.p.p, 1, ST_CG_PQ, 1));
-      k_mg_update<<<VG, VEC_BLOCK, 0, s>>>(k.p.p, k.q.p, x, k.r.p, n, k.partial.p, k.ticket.p, k.scal.p, k.flags.p);
+      APDX_CHECK(krylov_finish_stage(pl, ST_CG_PQ, 1));
+      k_mg_update<<<VG, VEC_BLOCK, 0, s>>>(k.p.p, k.q.p, x, k.r.p, i0, i1, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, fused);
+      APDX_CHECK(krylov_finish_stage(pl, ST_MG_RR, 1));
       APDX_CHECK(mg_vcycle(pl, k.r.p, z, pl));
-      k_mg_rz<<<VG, VEC_BLOCK, 0, s>>>(k.r.p, z, k.p.p, 0, n, k.partial.p, k.ticket.p, k.scal.p, k.flags.p);
-      k_mg_p<<<VG, VEC_BLOCK, 0, s>>>(z, k.p.p, n, k.scal.p, k.flags.p);
+      k_mg_rz<<<VG, VEC_BLOCK, 0, s>>>(k.r.p, z, k.p.p, 0, i0, i1, k.partial.p, k.ticket.p, k.scal.p, k.flags.p, fused);
+      APDX_CHECK(krylov_finish_stage(pl, ST_MG_RZ, 1));
+      k_mg_p<<<VG, VEC_BLOCK, 0, s>>>(z, k.p.p, i0, i1, k.scal.p, k.flags.p);
       pl->stats.kernel_launches += 3;
     }
     launched += todo;
   }
   nvtx_pop();
   APDX_CUDA(cudaGetLastError());
+  if (multi && pl->p2p.mbox) {
+    int err = 0;
+    APDX_CUDA(cudaMemcpy(&err, pl->p2p.err_d, sizeof(int), cudaMemcpyDeviceToHost));
+    APDX_REQUIRE(err == 0, APDX_ERR_NCCL, "peer-to-peer wait timed out (a rank stopped posting reductions)");
+  }
   const double rr = sc_pin[S_BB] > 0 ? sqrt(sc_pin[S_RR] / sc_pin[S_BB]) : sqrt(sc_pin[S_RR]);
   if (iters) *iters = fl_pin[F_ITERS];
   if (relres) *relres = rr;

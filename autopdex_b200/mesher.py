@@ -156,7 +156,8 @@ def slab_partition_mesh(coords, connectivity, n_elements, rank, nranks):
             raise ValueError("slab_partition_mesh: an element spans more than two adjacent node planes")
         elements.append(loc - lo)
         element_ids.append(rows)
-    bp = dict(owned_node_begin=olo - lo, owned_node_end=ohi - lo, rank_lo=part["rank_lo"], rank_hi=part["rank_hi"])
+    bp = dict(owned_node_begin=olo - lo, owned_node_end=ohi - lo, rank_lo=part["rank_lo"], rank_hi=part["rank_hi"],
+              planes=(part["plane_lo"], part["plane_hi"], part["owned_plane_lo"], part["owned_plane_hi"]))
     return {"nodes": nodes, "n_owned": int(ohi - olo), "elements": elements, "element_ids": element_ids,
             "slab": part, "b200 partition": bp}
 

@@ -306,32 +306,62 @@ class _State:
         if not isinstance(opt, Mapping) or "n_elements" not in opt:
             raise ValueError("b200 backend: 'type of preconditioner': 'multigrid' needs settings['b200 multigrid'] = "
                              "{'n_elements': (nx, ny[, nz])} (the structured mesh the hierarchy is derived from)")
+        self._mg_slab = None
         if self.partition:
-            raise ValueError("b200 backend: the multigrid preconditioner runs on one GPU (no 'b200 partition')")
-        shapes = multigrid.level_shapes(opt["n_elements"], opt.get("levels"))
-        if multigrid.node_count(shapes[0]) != self.n_nodes:
-            raise ValueError("b200 backend: settings['b200 multigrid']['n_elements'] = %s does not match the %d nodes"
-                             % (shapes[0], self.n_nodes))
+            # Partitioned hierarchy (slab partitions): every level is split like the finest one -- the rank that owns fine
+            # node plane 2I owns coarse plane I -- and 'n_elements' is the GLOBAL mesh.  The number of levels is agreed
+            # between the ranks (every rank must own free dofs on every level).
+            pt = self.partition
+            if "neighbours" in pt or "planes" not in pt:
+                raise ValueError("b200 backend: the multigrid preconditioner on several GPUs needs a slab partition with "
+                                 "settings['b200 partition']['planes'] = (plane_lo, plane_hi, owned_plane_lo, owned_plane_hi) "
+                                 "(mesher.slab_partition_mesh provides it)")
+            planes = tuple(int(v) for v in pt["planes"])
+            per_plane = int(np.prod([n + 1 for n in opt["n_elements"][1:]]))
+            if (planes[1] - planes[0]) * per_plane != self.n_nodes:
+                raise ValueError("b200 backend: settings['b200 multigrid']['n_elements'] = %s and the slab planes %s do not "
+                                 "match the %d local nodes" % (tuple(opt["n_elements"]), planes, self.n_nodes))
+            levels = multigrid.slab_levels(opt["n_elements"], planes, opt.get("levels"))
+            if not opt.get("_levels_agreed"):
+                n_lev = int(-backend.comm_allreduce_host([-float(len(levels))], "max")[0])     # minimum over the ranks
+                levels = levels[:n_lev]
+            shapes = [lv[0] for lv in levels]
+            if len(levels) > 1:
+                self._mg_slab = dict(planes_f=levels[0][1], planes_c=levels[1][1], rank_lo=pt.get("rank_lo", -1),
+                                     rank_hi=pt.get("rank_hi", -1))
+        else:
+            shapes = multigrid.level_shapes(opt["n_elements"], opt.get("levels"))
+            if multigrid.node_count(shapes[0]) != self.n_nodes:
+                raise ValueError("b200 backend: settings['b200 multigrid']['n_elements'] = %s does not match the %d nodes"
+                                 % (shapes[0], self.n_nodes))
         self.mg_shape = shapes[0]
         if len(shapes) > 1:
             self._mg_cache = {}
             cs, kept, fine_nodes = multigrid.coarse_level_settings(settings, shapes[0], self._mg_kinds(), self._unwrap, self._wrap,
-                                                                   self._mg_cache)
-            cs["b200 multigrid"] = dict(opt, n_elements=shapes[1], levels=len(shapes) - 1)
+                                                                   self._mg_cache, self._mg_slab)
+            cs["b200 multigrid"] = dict(opt, n_elements=shapes[1], levels=len(shapes) - 1, _levels_agreed=True)
             ccfg = self.cfg.coarse(kept)
             ccfg.multigrid = True                                    # recurse: the coarse state builds its own coarse level
-            n_c = multigrid.node_count(shapes[1])
+            n_c = np.asarray(self._unwrap(cs["node coordinates"])).shape[0]
             d_c = self._wrap(np.zeros((n_c, self.nf)) if self.dofs_ndim > 1 else np.zeros(n_c))
             self.coarse_state = _State(ccfg, d_c, cs)
             free_f = np.ones((self.n_nodes, self.nf), dtype=bool) if self.mask is None else ~self.mask.reshape(self.n_nodes, self.nf)
             cm = self.coarse_state.mask
             free_c = np.ones((n_c, self.nf), dtype=bool) if cm is None else ~cm.reshape(n_c, self.nf)
-            P, R = multigrid.prolongation(shapes[0], self.nf, free_f, free_c)
+            slab = None if self._mg_slab is None else (self._mg_slab["planes_f"][:2], self._mg_slab["planes_c"][:2])
+            P, R = multigrid.prolongation(shapes[0], self.nf, free_f, free_c, slab)
             inject = (fine_nodes[:, None] * self.nf + np.arange(self.nf)).ravel()
             self.plan.set_coarse(self.coarse_state.plan, P, R, inject)
             self.mg_kept = kept
-        self.plan.set_multigrid(opt.get("pre", 0), opt.get("post", 0), opt.get("coarsest", 0), opt.get("ratio", 0.0),
-                                opt.get("coarsest ratio", 0.0))
+        coarsest, coarsest_ratio = opt.get("coarsest", 0), opt.get("coarsest ratio", 0.0)
+        nc = max(shapes[-1])
+        if self.partition and not coarsest and not coarsest_ratio and nc > 4:
+            # A partitioned hierarchy ends where a rank would own fewer than two planes, so its coarsest level can be
+            # large (16^3 for 256^3 on 8 GPUs): widen the Chebyshev interval of the coarsest solve to the spectrum of that
+            # mesh (lambda_max / lambda_min of D^-1 A grows like n^2) and raise the degree with its square root.
+            coarsest_ratio = max(40.0, 0.6 * nc * nc)
+            coarsest = int(np.ceil(1.3 * np.sqrt(coarsest_ratio)))
+        self.plan.set_multigrid(opt.get("pre", 0), opt.get("post", 0), coarsest, opt.get("ratio", 0.0), coarsest_ratio)
 
     def update_coarse_fields(self, settings):
         """Per-call upload of the coarse levels' fields (injected coordinates, coefficient values at the coarse Gauss
@@ -340,7 +370,7 @@ class _State:
             return
         from . import multigrid
         cs, _, _ = multigrid.coarse_level_settings(settings, self.mg_shape, self._mg_kinds(), self._unwrap, self._wrap,
-                                                   self._mg_cache)
+                                                   self._mg_cache, self._mg_slab)
         self.coarse_state.update_fields(cs)
         self.h2d_bytes += self.coarse_state.h2d_bytes
 

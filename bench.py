@@ -133,7 +133,9 @@ def build_problem(m, rank, nranks):
     if nranks > 1:
         settings["b200 partition"] = dict(owned_node_begin=part["owned_node_lo"] - part["node_lo"],
                                           owned_node_end=part["owned_node_hi"] - part["node_lo"],
-                                          rank_lo=part["rank_lo"], rank_hi=part["rank_hi"])
+                                          rank_lo=part["rank_lo"], rank_hi=part["rank_hi"],
+                                          planes=(part["plane_lo"], part["plane_hi"], part["owned_plane_lo"],
+                                                  part["owned_plane_hi"]))
     return settings, static_settings, owned_elems
 
 
@@ -304,17 +306,19 @@ def vector_problem_figures(args, hbm, fp64_peak, n=64):
     return out
 
 
-def multigrid_figures(args, sol_jacobi):
+def multigrid_figures(args, sol_jacobi, rank=0, world=1):
     """The same Newton step with 'type of preconditioner': 'multigrid' (opt-in: the headline above
     is BASELINE's Jacobi-PCG): geometric V-cycle on the structured hierarchy M^3 -> (M/2)^3 -> ..., Chebyshev smoothing,
     re-discretised coarse operators.  Device-resident step time, end-to-end time through solver.solver, and the distance
-    of its solution from the Jacobi-PCG one."""
+    of its solution from the Jacobi-PCG one.  On several GPUs the hierarchy is partitioned like the finest level (slabs;
+    halo exchange per level and transfer); times are the maximum over the ranks."""
     from autopdex_b200 import backend, solver
-    solver.clear_plan_cache()                     # the Jacobi plan's 70 GB go first
+    solver.clear_plan_cache()                     # the Jacobi plan's buffers go first
     m = args.size
-    settings, static_settings, _ = build_problem(m, 0, 1)
+    settings, static_settings, _ = build_problem(m, rank, world)
     static_settings = dict(static_settings, **{"type of preconditioner": "multigrid"})
-    settings["b200 multigrid"] = {"n_elements": (m, m, m)}
+    settings["b200 multigrid"] = {"n_elements": (NX_OVERRIDE[0] or m, m, m)}
+    gmax = lambda v: float(backend.comm_allreduce_host([float(v)], "max")[0])
     dofs0 = np.zeros((settings["node coordinates"].shape[0], 1))
     t = time.perf_counter()
     sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)
@@ -324,7 +328,7 @@ def multigrid_figures(args, sol_jacobi):
     t = time.perf_counter()
     for _ in range(args.steps):
         sol, info = solver.solver(dofs0, settings, static_settings, tol=args.rtol)
-    e2e_ms = (time.perf_counter() - t) / args.steps * 1e3
+    e2e_ms = gmax((time.perf_counter() - t) / args.steps * 1e3)
     st = dict(solver.last_stats)
     state = next(iter(solver._PLAN_CACHE.values()))
     opts = backend.KrylovOptions("cg", rtol=args.rtol, jacobi="multigrid")
@@ -339,10 +343,16 @@ def multigrid_figures(args, sol_jacobi):
     while stt is not None:
         levels, stt = levels + 1, stt.coarse_state
     dev_gb = state.plan.device_bytes_now() / 1e9
-    diff = float(np.linalg.norm(np.asarray(sol).ravel() - np.asarray(sol_jacobi).ravel()) / np.linalg.norm(np.asarray(sol_jacobi).ravel()))
-    out = {"workload": workload_name(m, args.rtol, 1).replace("Jacobi-PCG", "multigrid-PCG"),
-           "newton_step_ms": float(np.mean(step)), "elements_per_s": m ** 3 / (float(np.mean(step)) * 1e-3),
-           "e2e_ms_per_step": e2e_ms, "krylov_ms": float(np.mean(kry)), "krylov_iterations": float(np.mean(its)),
+    pt = settings.get("b200 partition", {})
+    own = slice(pt.get("owned_node_begin", 0), pt.get("owned_node_end", np.asarray(sol).shape[0]))
+    a, b = np.asarray(sol)[own].ravel(), np.asarray(sol_jacobi)[own].ravel()
+    d2, n2 = backend.comm_allreduce_host([float(np.dot(a - b, a - b)), float(np.dot(b, b))])
+    diff = float(np.sqrt(d2 / n2))
+    step_ms = gmax(np.mean(step))
+    total = (NX_OVERRIDE[0] or m) * m * m
+    out = {"workload": workload_name(m, args.rtol, world).replace("Jacobi-PCG", "multigrid-PCG"),
+           "newton_step_ms": step_ms, "elements_per_s": total / (step_ms * 1e-3),
+           "e2e_ms_per_step": e2e_ms, "krylov_ms": gmax(np.mean(kry)), "krylov_iterations": float(np.mean(its)),
            "levels": levels, "hierarchy_build_s_first_call": t_build, "newton_steps": info[0], "res_norm": info[1],
            "rel_l2_vs_jacobi_pcg_solution": diff, "h2d_bytes_per_step": int(st["h2d_bytes"]), "plan_device_gb": dev_gb,
            "note": "krylov_ms includes the per-step set-up (coarse operators re-assembled at the injected state, power "
@@ -471,9 +481,7 @@ def run_b200(args):
     asm_tflops = asm_elems * HEX8_POISSON_FLOP / (np.mean(asm_ms) * 1e-3) / 1e12
     vector = optional_section(vector_problem_figures, args, hbm, fp64_peak) if (world == 1 and not args.no_vector) else None
 
-    if rank != 0:
-        return
-    line = {
+    line = None if rank != 0 else {
         "metric": METRIC, "value": total_elems / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -515,8 +523,28 @@ def run_b200(args):
         "system": {"n_free": nfree, "nnz_reduced": nnz, "plan_device_gb": dev_gb_after_solve,
                    "plan_device_gb_note": "all device buffers of the plan after the solves (pattern, gather lists, element streams, sliced-ELL matrix, Krylov vectors)"},
     }
-    if world == 1 and not args.no_multigrid:
-        line["multigrid"] = optional_section(multigrid_figures, args, sol)
+    if not args.no_multigrid:
+        # every rank takes part in the partitioned variant; on several GPUs a watchdog prints the headline line without
+        # the section should a rank stall (the section is optional, the line is not)
+        dog = None
+        if world > 1:
+            import threading
+
+            def bail():
+                if rank == 0:
+                    line["multigrid"] = {"error": "timed out after %.0f s (watchdog)" % args.mg_timeout_s}
+                    print(json.dumps(line), flush=True)
+                os._exit(0)
+            dog = threading.Timer(args.mg_timeout_s, bail)
+            dog.daemon = True
+            dog.start()
+        mg = optional_section(multigrid_figures, args, sol, rank, world)
+        if dog is not None:
+            dog.cancel()
+        if rank == 0:
+            line["multigrid"] = mg
+    if rank != 0:
+        return
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = optional_section(cpu_baseline_section, args, m)
     print(json.dumps(line))
@@ -539,6 +567,7 @@ def main():
     ap.add_argument("--ref-direct", action="store_true", help="--impl reference: also time spsolve on a 32^3 sample")
     ap.add_argument("--no-vector", action="store_true", help="skip the bounded 64^3 neo-Hooke figures")
     ap.add_argument("--no-multigrid", action="store_true", help="skip the multigrid-preconditioned variant of the step")
+    ap.add_argument("--mg-timeout-s", type=float, default=420.0, help="watchdog of the multi-GPU multigrid section")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nx", type=int, default=0, help="diagnostic: elements along the slowest index (default: --size)")

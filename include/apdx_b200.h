@@ -207,7 +207,11 @@ int apdx_tangent_solve(apdx_plan *plan, const apdx_krylov_opts *opts, const doub
  *   rows), inject[d] = the fine full dof id that coincides with coarse full dof d (state transfer, n_dofs(coarse) entries).
  * The coarse plan then runs on the fine plan's stream; it must outlive the fine plan's solves and is not owned by it.
  * apdx_plan_set_multigrid: Chebyshev degree of the pre- and post-smoother, of the coarsest-level solve, and the ratios
- * lambda_max / lambda_min of the smoothing and coarsest intervals (values <= 0 keep the defaults 2, 2, 12, 3, 40).      */
+ * lambda_max / lambda_min of the smoothing and coarsest intervals (values <= 0 keep the defaults 2, 2, 12, 3, 40).
+ * Multi-GPU: every level is a slab-partitioned plan (apdx_plan_set_partition on the fine AND the coarse plans, the rank that
+ * owns fine node plane 2I owns coarse plane I); P, R and inject are then given in the LOCAL numberings of the two slabs
+ * (inject entries of a coarse ghost plane whose fine plane is not local may point at any local dof: the neighbour's values
+ * replace them).  Halo exchanges per product and per transfer, all-reduced dot products (csrc/multigrid.cu).            */
 int apdx_plan_set_coarse(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_indptr_h, const int32_t *p_indices_h,
                          const double *p_data_h, const int32_t *r_indptr_h, const int32_t *r_indices_h,
                          const double *r_data_h, const int64_t *inject_h);
@@ -254,6 +258,11 @@ int apdx_comm_destroy(void);
 int apdx_comm_allreduce_host(double *inout_h, int32_t count, int32_t op);
 int apdx_plan_set_partition(apdx_plan *plan, int64_t owned_dof_begin, int64_t owned_dof_end,
                             int32_t rank_lo, int32_t rank_hi);
+/* Slab neighbours swap boundary blocks of a device vector of n doubles laid out [ghost_lo | owned | ghost_hi]: the first
+ * lo_count owned entries go to rank_lo, whose answer fills [0, lo_count); the last hi_count owned entries go to rank_hi,
+ * whose answer fills [n - hi_count, n).  Collective between neighbours (both sides pass the size of one node plane);
+ * used for the node fields of a partitioned multigrid hierarchy (coordinates, masks, injected state).  Synchronous. */
+int apdx_comm_exchange_planes(double *buf_d, int64_t n, int64_t lo_count, int64_t hi_count, int32_t rank_lo, int32_t rank_hi);
 /* General partition (recursive coordinate bisection, unstructured meshes): the local mesh numbers the owned nodes
  * first ([0, owned_dof_end) in dof units) and then the ghost nodes grouped by owning rank.  For neighbour i
  * (neighbour_rank[i]) send_dof_h[send_ptr_h[i] .. send_ptr_h[i+1]) lists the LOCAL dof ids (owned, ascending in the

@@ -36,14 +36,14 @@ def neohooke_api_problem(p):
     return static_settings
 
 
-def run_case(problem, m, krylov, partition, rank, world):
+def run_case(problem, m, krylov, partition, rank, world, precond="jacobi"):
     import bench
     from autopdex_b200 import backend, mesher, solver
     from tests import problems
     pg = problems.poisson_hex(m) if problem == "poisson" else problems.neo_hooke_brick(m)
     nf = pg["nf"]
     conns = tuple(s["conn"] for s in pg["sets"])
-    if problem == "poisson" and partition == "slab":
+    if problem == "poisson" and partition == "slab" and precond == "jacobi":
         # the bench's memory-lean slab construction (never materialises the global mesh)
         settings, static_settings, _ = bench.build_problem(m, rank, world)
         sp = mesher.slab_partition((m, m, m), rank, world)
@@ -62,6 +62,11 @@ def run_case(problem, m, krylov, partition, rank, world):
                     "dirichlet dofs": pg["mask"][nodes], "dirichlet conditions": np.zeros((nodes.size, nf)),
                     "b200 partition": pt["b200 partition"]}
     static_settings = dict(static_settings, solver=krylov)
+    if precond == "multigrid":       # partitioned geometric multigrid hierarchy (slab partitions only)
+        static_settings["type of preconditioner"] = "multigrid"
+        settings["b200 multigrid"] = {"n_elements": (m, m, m)}
+        if os.environ.get("APDX_TEST_MG_LEVELS"):      # experiments: truncate the hierarchy (large coarsest level)
+            settings["b200 multigrid"]["levels"] = int(os.environ["APDX_TEST_MG_LEVELS"])
     n_local = settings["node coordinates"].shape[0]
     sol, (steps, res, div) = solver.solver(np.zeros((n_local, nf)), settings, static_settings, tol=1e-12)
     st = dict(solver.last_stats)
@@ -77,16 +82,17 @@ def run_case(problem, m, krylov, partition, rank, world):
         ref, (rsteps, _, rdiv) = osolve.damped_newton(prob, np.zeros(pg["mask"].shape))
         err = np.linalg.norm(glob.ravel() - ref.ravel()) / np.linalg.norm(ref)
         ok = err < 1e-8 and steps == rsteps and div == rdiv
-        print("multi-gpu parity: ranks=%d %s m=%d nf=%d %s %s steps=%d/%d res=%.2e krylov_iters=%d rel-L2=%.2e -> %s"
-              % (world, problem, m, nf, krylov, partition, steps, rsteps, res, int(st["krylov_iters"]), err,
-                 "OK" if ok else "FAIL"), flush=True)
+        print("multi-gpu parity: ranks=%d %s m=%d nf=%d %s%s %s steps=%d/%d res=%.2e krylov_iters=%d rel-L2=%.2e -> %s"
+              % (world, problem, m, nf, krylov, "+multigrid" if precond == "multigrid" else "", partition, steps, rsteps, res,
+                 int(st["krylov_iters"]), err, "OK" if ok else "FAIL"), flush=True)
     solver.clear_plan_cache()
     return bool(backend.comm_allreduce_host([0.0 if ok else 1.0], "max")[0] == 0.0)
 
 
 def main():
-    """argv: [poisson|neohooke] [M] [cg|bicgstab] [slab|rcb]   one case
-             matrix [Mp] [Mn]                                   {poisson Mp, neohooke Mn} x {cg, bicgstab} x {slab, rcb}"""
+    """argv: [poisson|neohooke] [M] [cg|bicgstab] [slab|rcb] [jacobi|multigrid]   one case
+             matrix [Mp] [Mn]                                   {poisson Mp, neohooke Mn} x {cg, bicgstab} x {slab, rcb}
+             mgmatrix [Mp] [Mn]                                 {poisson Mp, neohooke Mn}, multigrid-preconditioned CG on slabs"""
     from autopdex_b200 import backend
     argv = sys.argv[1:]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -104,12 +110,16 @@ def main():
         mp = max(mp, 2 * world)      # all faces are Dirichlet faces: the first and last slab need an interior plane
         cases = [(pb, m, k, pt) for pb, m in (("poisson", mp), ("neohooke", mn)) for k in ("cg", "bicgstab")
                  for pt in ("slab", "rcb")]
+    elif argv and argv[0] == "mgmatrix":
+        mp = int(argv[1]) if len(argv) > 1 else 32
+        mn = int(argv[2]) if len(argv) > 2 else 16
+        cases = [("poisson", mp, "cg", "slab", "multigrid"), ("neohooke", mn, "cg", "slab", "multigrid")]
     else:
         problem = "poisson"
         if argv and not argv[0].isdigit():
             problem, argv = argv[0], argv[1:]
         cases = [(problem, int(argv[0]) if len(argv) > 0 else 20, argv[1] if len(argv) > 1 else "cg",
-                  argv[2] if len(argv) > 2 else "slab")]
+                  argv[2] if len(argv) > 2 else "slab", argv[3] if len(argv) > 3 else "jacobi")]
     ok = True
     import signal
 
@@ -120,7 +130,7 @@ def main():
     for c in cases:
         signal.alarm(int(os.environ.get("APDX_CASE_TIMEOUT", "150")))
         try:
-            ok = run_case(*c, rank, world) and ok
+            ok = run_case(*c[:4], rank, world, *c[4:]) and ok
         except Exception as e:   # keep the remaining cases running; every rank raises alike (collective set-up errors)
             ok = False
             print("multi-gpu parity: ranks=%d %s m=%d %s %s -> ERROR on rank %d: %s" % (world, c[0], c[1], c[2], c[3], rank, e),

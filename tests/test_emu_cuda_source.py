@@ -97,6 +97,17 @@ def test_nccl_allreduce_mode_on_three_emulated_ranks():
     assert rc == 0 and len(lines) == 1 and lines[0].endswith("-> OK"), out[-4000:]
 
 
+def test_partitioned_multigrid_on_emulated_ranks():
+    """The multigrid-preconditioned CG with a hierarchy partitioned into slabs (halo exchange per level, restriction and
+    prolongation across the interface, injected coarse state from the neighbour, all-reduced dot products): Poisson 16^3
+    and the nonlinear neo-Hooke brick 8^3 (nf = 3, coarse tangents re-discretised in every Newton step) on 2 ranks against
+    the oracle; the iteration count stays at the single-GPU level."""
+    rc, lines, out = _run_ranks(2, ["mgmatrix", "16", "8"])
+    assert rc == 0 and len(lines) == 2 and all(l.endswith("-> OK") for l in lines), out[-4000:]
+    its = int(lines[0].split("krylov_iters=")[1].split()[0])
+    assert its <= 10, lines[0]
+
+
 def test_capture_rules_of_the_stand_in():
     """The stand-in must be as strict as the runtime where the product depends on it: an allocation or a synchronisation
     while a stream captures invalidates the capture (a scope-bound temporary freed inside the Krylov capture would be

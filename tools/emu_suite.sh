@@ -24,4 +24,10 @@ OUT=${1:-profiles/r02f_emulated_cuda_source_suite.txt}
       python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29800 + n)) \
       tests/multi_gpu_worker.py matrix 12 8 2>&1 | grep "multi-gpu parity"
   done
+  for n in 2 3 4; do
+    echo "## partitioned multigrid: tests/multi_gpu_worker.py mgmatrix on $n emulated ranks"
+    EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=900 \
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29820 + n)) \
+      tests/multi_gpu_worker.py mgmatrix 32 16 2>&1 | grep "multi-gpu parity"
+  done
 } | tee "$OUT"

@@ -14,7 +14,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-UNITS = ["api", "pattern", "elements", "elements_fast", "sell", "krylov", "dist"]
+UNITS = ["api", "pattern", "elements", "elements_fast", "sell", "krylov", "multigrid", "dist"]
 
 
 def kernels(obj):
