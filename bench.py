@@ -535,7 +535,8 @@ def run_b200(args):
                     line["multigrid"] = {"error": "timed out after %.0f s (watchdog)" % args.mg_timeout_s}
                     print(json.dumps(line), flush=True)
                 os._exit(0)
-            dog = threading.Timer(args.mg_timeout_s, bail)
+            # rank 0 gives up first (it owns the line); the others follow a few seconds later
+            dog = threading.Timer(args.mg_timeout_s + (0.0 if rank == 0 else 5.0), bail)
             dog.daemon = True
             dog.start()
         mg = optional_section(multigrid_figures, args, sol, rank, world)
@@ -567,7 +568,7 @@ def main():
     ap.add_argument("--ref-direct", action="store_true", help="--impl reference: also time spsolve on a 32^3 sample")
     ap.add_argument("--no-vector", action="store_true", help="skip the bounded 64^3 neo-Hooke figures")
     ap.add_argument("--no-multigrid", action="store_true", help="skip the multigrid-preconditioned variant of the step")
-    ap.add_argument("--mg-timeout-s", type=float, default=420.0, help="watchdog of the multi-GPU multigrid section")
+    ap.add_argument("--mg-timeout-s", type=float, default=240.0, help="watchdog of the multi-GPU multigrid section")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nx", type=int, default=0, help="diagnostic: elements along the slowest index (default: --size)")

@@ -9,6 +9,11 @@ OUT=gpurun_out; mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 400 $TR --master-port 29511 tests/multi_gpu_worker.py matrix 24 12 > $OUT/${TAG}_parity_n$N.txt 2>&1; echo "parity exit $?"
 grep "multi-gpu parity" $OUT/${TAG}_parity_n$N.txt
+# partitioned multigrid hierarchy (written without hardware, validated on emulated ranks: DESIGN.md 3.6 / 6b)
+timeout 300 $TR --master-port 29515 tests/multi_gpu_worker.py mgmatrix 64 32 > $OUT/${TAG}_mg_parity_n$N.txt 2>&1; echo "mg parity exit $?"
+grep "multi-gpu parity" $OUT/${TAG}_mg_parity_n$N.txt
+timeout 300 $TR --master-port 29517 tools/run_config.py neohooke ${CFG5_SIZE:-128} 2 -1 slab multigrid > $OUT/${TAG}_config5_mg_n$N.json 2> $OUT/${TAG}_config5_mg_n$N.err; echo "config5 multigrid exit $?"
+cat $OUT/${TAG}_config5_mg_n$N.json | cut -c1-1500
 timeout 300 $TR --master-port 29521 tools/run_config.py neohooke ${CFG5_SIZE:-128} 2 > $OUT/${TAG}_config5_n$N.json 2> $OUT/${TAG}_config5_n$N.err; echo "config5 exit $?"
 cat $OUT/${TAG}_config5_n$N.json | cut -c1-1500
 timeout 240 $TR --master-port 29531 bench.py --gpus $N --steps 5 --warmup 3 > $OUT/${TAG}_bench_n$N.json 2> $OUT/${TAG}_bench_n$N.err; echo "bench exit $?"

@@ -73,6 +73,8 @@ def cook(n, order):
     tr = models.neumann_weak(lambda x, s: np.asarray([0.0, s["load multiplier"]]))
     sf = models.isoparametric_surface_element_galerkin(tr, spaces.fem_iso_line_quad_brick, *seeder.gauss_legendre_nd(1, 2 * order), tangent_contributions=False)
     st = base_static(**{"assembling mode": ("user element", "user element"), "model": (el, sf), "solver": "bicgstab"})
+    if precond == "multigrid":
+        st = dict(st, **{"solver": "cg", "type of preconditioner": "multigrid"})
     mask = np.repeat((np.abs(coords[:, 0]) < 1e-9)[:, None], 2, axis=1)
     q0 = 4.0
     settings = {"connectivity": (elems, line), "node coordinates": coords, "dirichlet dofs": mask,
@@ -151,8 +153,9 @@ def _dist():
     return rank, world
 
 
-def neohooke(n, load_steps=2, traction=-1.0, partition="slab"):
-    """BASELINE config 5.  Under torchrun (WORLD_SIZE > 1) the brick is split into slabs (or RCB parts) and every rank
+def neohooke(n, load_steps=2, traction=-1.0, partition="slab", precond="jacobi"):
+    """BASELINE config 5 (precond = 'multigrid': CG preconditioned by the geometric multigrid hierarchy instead of the
+    Jacobi-BiCGSTAB of the config; slab partitions only).  Under torchrun (WORLD_SIZE > 1) the brick is split into slabs (or RCB parts) and every rank
     solves its part through the public API (settings['b200 partition']): halo exchange + all-reduces inside the Krylov
     loop; times are the max over ranks, the checksums are sums over the owned nodes."""
     from autopdex_b200 import backend
@@ -164,9 +167,13 @@ def neohooke(n, load_steps=2, traction=-1.0, partition="slab"):
     tr = models.neumann_weak(lambda x, s: np.asarray([0.0, 0.0, s["load multiplier"]]))
     sf = models.isoparametric_surface_element_galerkin(tr, spaces.fem_iso_line_quad_brick, *seeder.gauss_legendre_nd(2, 2), tangent_contributions=False)
     st = base_static(**{"assembling mode": ("user element", "user element"), "model": (el, sf), "solver": "bicgstab"})
+    if precond == "multigrid":
+        st = dict(st, **{"solver": "cg", "type of preconditioner": "multigrid"})
     mask = np.repeat((np.abs(coords[:, 0]) < 1e-9)[:, None], 3, axis=1)
     settings = {"connectivity": (elems, face), "node coordinates": coords, "dirichlet dofs": mask,
                 "dirichlet conditions": np.zeros(mask.shape), "load multiplier": 0.0}
+    if precond == "multigrid":
+        settings["b200 multigrid"] = {"n_elements": (n, n, n)}
     own = slice(0, coords.shape[0])
     if world > 1:
         pt = (mesher.rcb_partition(coords, (elems, face), rank, world) if partition == "rcb"
@@ -193,8 +200,9 @@ def neohooke(n, load_steps=2, traction=-1.0, partition="slab"):
                      "ms_per_newton_step": float(tm[4]) / max(int(info[0]), 1)})
     d = np.asarray(dofs)[own]
     sums = backend.comm_allreduce_host([float((d * d).sum()), float(d[:, 2].sum())])
-    out = {"config": "3D neo-Hooke %d^3 hex8 (%d dofs), Newton + Jacobi-BiCGSTAB 1e-8, %d load steps, %d GPU(s), %s partition"
-                     % (n, mask.size, load_steps, world, partition if world > 1 else "no"),
+    out = {"config": "3D neo-Hooke %d^3 hex8 (%d dofs), Newton + %s 1e-8, %d load steps, %d GPU(s), %s partition"
+                     % (n, mask.size, "multigrid-PCG" if precond == "multigrid" else "Jacobi-BiCGSTAB", load_steps, world,
+                        partition if world > 1 else "no"),
            "n_gpus": world, "total_s": time.perf_counter() - t0, "load_steps": hist, "u_dot_u": float(sums[0]), "sum_uz": float(sums[1])}
     if world > 1:
         solver.clear_plan_cache()
