@@ -360,7 +360,7 @@ class _State:
             # large (16^3 for 256^3 on 8 GPUs): widen the Chebyshev interval of the coarsest solve to the spectrum of that
             # mesh (lambda_max / lambda_min of D^-1 A grows like n^2) and raise the degree with its square root.
             coarsest_ratio = max(40.0, 0.6 * nc * nc)
-            coarsest = int(np.ceil(1.3 * np.sqrt(coarsest_ratio)))
+            coarsest = max(12, int(np.ceil(1.3 * np.sqrt(coarsest_ratio))))
         self.plan.set_multigrid(opt.get("pre", 0), opt.get("post", 0), coarsest, opt.get("ratio", 0.0), coarsest_ratio)
 
     def update_coarse_fields(self, settings):

@@ -265,9 +265,12 @@ def workload_name(m, rtol, world):
             % (m, (m + 1) ** 3, rtol, world))
 
 
-# ncu (profiles/r02a_k_elements_neohooke64_full.txt): k_elements<3,3> executes 2436 DFMA + 1386 DMUL + 791 DADD thread
-# instructions per elapsed cycle over 2.144 M cycles for 262 144 hex8 neo-Hooke elements = 57.7 kflop per element
-HEX8_NEOHOOKE_FLOP_EXECUTED = 57662.0
+# ncu (profiles/r02a_k_elements_neohooke64_full.txt): the k_elements<3,3> of that capture executed 2436 DFMA + 1386 DMUL +
+# 791 DADD thread instructions per elapsed cycle over 2.144 M cycles for 262 144 hex8 neo-Hooke elements = 57.7 kflop per
+# element, ~51.4 k of them in the node-pair loop (64 pairs x 8 Gauss points x ~100 flop).  The kernel now integrates the
+# 36 upper node pairs only (symmetric tangent, stored twice): 6.3 k + 51.4 k * 36 / 64 = 35.2 kflop per element -- DERIVED
+# from the capture by the trip counts, not re-measured (no GPU time was left).
+HEX8_NEOHOOKE_FLOP_EXECUTED = 35200.0
 
 
 def vector_problem_figures(args, hbm, fp64_peak, n=64):
@@ -298,7 +301,8 @@ def vector_problem_figures(args, hbm, fp64_peak, n=64):
                         "flop_per_element_executed": HEX8_NEOHOOKE_FLOP_EXECUTED, "tflops_fp64": tfl,
                         "frac_of_fp64_peak": tfl / fp64_peak,
                         "note": "whole apdx_assemble pass (element kernel + scatter into full CSR and sliced-ELL + residual); flops "
-                                "per element from ncu's sass_thread_inst_executed_op_d{fma,mul,add} of the element kernel"},
+                                "per element derived from ncu's sass_thread_inst_executed_op_d{fma,mul,add} of the 64-pair "
+                                "kernel (57.7 k) scaled to the 36 node pairs the kernel integrates now"},
            "spmv": {"ms_per_launch": spmv_ms, "bytes_per_launch": phys, "achieved_gbs": phys / (spmv_ms * 1e-3) / 1e9,
                     "frac": phys / (spmv_ms * 1e-3) / 1e9 / hbm, "nnz_reduced": nnz, "n_free": plan.n_free,
                     "algorithmic_gbs": (nnz * 12 + rows * 16 + (rows + 1) * 4) / (spmv_ms * 1e-3) / 1e9}}
