@@ -286,8 +286,10 @@ __global__ void __launch_bounds__(256) k_elements(ElemArgs A) {
         for (int i2 = 0; i2 < NF; ++i2)
 #pragma unroll
           for (int k2 = 0; k2 < NF; ++k2) {
-            out[(int64_t)(a * NF + i2) * ndof + b * NF + k2] = blk[i2][k2];
-            if (a != b) out[(int64_t)(b * NF + k2) * ndof + a * NF + i2] = blk[i2][k2];
+            // diagonal node block: its two triangles differ by the rounding of (c g_k) g_i against (c g_i) g_k -- store the upper one twice
+            const double v = (a == b && k2 < i2) ? blk[k2][i2] : blk[i2][k2];
+            out[(int64_t)(a * NF + i2) * ndof + b * NF + k2] = v;
+            if (a != b) out[(int64_t)(b * NF + k2) * ndof + a * NF + i2] = v;
           }
       }
     }
