@@ -20,6 +20,8 @@ def pytest_sessionfinish(session, exitstatus):
         return
     import ctypes
     import gc
+    if "autopdex_b200.solver" in sys.modules:        # plans kept by the plan cache are not leaks
+        sys.modules["autopdex_b200.solver"].clear_plan_cache()
     gc.collect()
     lib = ctypes.CDLL(lib_path)
     for f in ("emu_kernel_launches", "emu_live_device_bytes", "emu_live_device_blocks", "emu_strict_violations"):

@@ -39,3 +39,44 @@ def test_generic_kernel_tangent_is_bitwise_symmetric_and_matches_oracle(case):
     coo = plan.coo_values()
     assert np.abs(coo - data).max() <= 1e-12 * np.abs(data).max()
     plan.destroy()
+
+
+def test_cook_membrane_q1_multigrid_pcg_matches_jacobi_bicgstab():
+    """BASELINE config 2 family (2-D plane-strain neo-Hooke, a domain and a Neumann line set, adaptive load stepping) with
+    the multigrid-preconditioned CG: same load-step history and tip displacement as the Jacobi-BiCGSTAB of the config, in
+    a fraction of the Krylov iterations (nf = 2 hierarchy in 2-D; the surface set lives on the finest level only)."""
+    from autopdex_b200 import mesher, models, seeder, solver, spaces
+    n = 16
+    pts = [[0., 0.], [48., 44.], [48., 60.], [0., 44.]]
+    coords, elems = mesher.structured_mesh((n, n), pts, "quad")
+    line = mesher.boundary_faces((n, n), 0, 1)
+    lam, mu = 100.0, 40.0
+    Em, nu = mu * (3 * lam + 2 * mu) / (lam + mu), lam / (2 * (lam + mu))
+    weak = models.hyperelastic_steady_state_weak(models.neo_hooke, lambda x, s: s["youngs modulus"], lambda x, s: s["poisson ratio"],
+                                                 "plain strain")
+    el = models.isoparametric_domain_element_galerkin(weak, spaces.fem_iso_line_quad_brick, *seeder.gauss_legendre_nd(2, 2))
+    tr = models.neumann_weak(lambda x, s: np.asarray([0.0, s["load multiplier"]]))
+    sf = models.isoparametric_surface_element_galerkin(tr, spaces.fem_iso_line_quad_brick, *seeder.gauss_legendre_nd(1, 2),
+                                                       tangent_contributions=False)
+    mask = np.repeat((np.abs(coords[:, 0]) < 1e-9)[:, None], 2, axis=1)
+    q0 = 4.0
+
+    def mult(s, m):
+        s["load multiplier"] = m * q0
+        return s
+    out = {}
+    for pc in ("jacobi", "multigrid"):
+        st = {"assembling mode": ("user element", "user element"), "solution structure": ("nodal imposition",) * 2, "model": (el, sf),
+              "solver type": "newton", "solver backend": "b200", "solver": "bicgstab" if pc == "jacobi" else "cg",
+              "type of preconditioner": pc, "verbose": -1}
+        settings = {"connectivity": (elems, line), "node coordinates": coords, "dirichlet dofs": mask,
+                    "dirichlet conditions": np.zeros(mask.shape), "youngs modulus": Em, "poisson ratio": nu, "load multiplier": q0}
+        if pc == "multigrid":
+            settings["b200 multigrid"] = {"n_elements": (n, n)}
+        res = solver.adaptive_load_stepping(np.zeros(mask.shape), settings, st, mult, False, None, newton_tol=1e-8, tol=1e-10)
+        out[pc] = (np.asarray(res[0]), float(res[1]), int(solver.last_stats["krylov_iters"]))
+        solver.clear_plan_cache()
+    (uj, mj, kj), (um, mm, km) = out["jacobi"], out["multigrid"]
+    assert mj == mm == 1.0
+    assert np.linalg.norm(um - uj) <= 1e-8 * np.linalg.norm(uj)
+    assert km * 3 <= kj, (km, kj)

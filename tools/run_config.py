@@ -53,7 +53,8 @@ def readme(n):
             "expected_sum_phi": {5: 1.9066412530282952, 200: 2233.155221149569}.get(n), **solver.last_stats}
 
 
-def cook(n, order):
+def cook(n, order, precond="jacobi"):
+    """BASELINE config 2 (ii).  precond = 'multigrid' (order 1 only): CG preconditioned by the geometric hierarchy."""
     pts = [[0., 0.], [48., 44.], [48., 60.], [0., 44.]]
     coords, elems = mesher.structured_mesh((n, n), pts, "quad")
     line = mesher.boundary_faces((n, n), 0, 1)
@@ -79,6 +80,8 @@ def cook(n, order):
     q0 = 4.0
     settings = {"connectivity": (elems, line), "node coordinates": coords, "dirichlet dofs": mask,
                 "dirichlet conditions": np.zeros(mask.shape), "youngs modulus": Em, "poisson ratio": nu, "load multiplier": q0}
+    if precond == "multigrid":
+        settings["b200 multigrid"] = {"n_elements": (n, n)}
 
     def mult(s, m):
         s["load multiplier"] = m * q0
@@ -87,7 +90,7 @@ def cook(n, order):
     out = solver.adaptive_load_stepping(np.zeros(mask.shape), settings, st, mult, False, None, newton_tol=1e-8, tol=1e-10)
     dofs = out[0]
     tip = dofs[np.argmax(coords[:, 0] + coords[:, 1])]
-    return {"config": "Cook's membrane %dx%d Q%d neo-Hooke, adaptive load stepping" % (n, n, order),
+    return {"config": "Cook's membrane %dx%d Q%d neo-Hooke, adaptive load stepping, %s" % (n, n, order, "multigrid-PCG" if precond == "multigrid" else "Jacobi-BiCGSTAB"),
             "total_s": time.perf_counter() - t, "multiplier": float(out[1]), "tip_displacement": tip.tolist(),
             "dofs": int(mask.size), **solver.last_stats}
 
