@@ -80,6 +80,12 @@ SIGNATURES = {
     "apdx_plan_stats": (C.c_int, [_P, C.POINTER(_D)]),
     "apdx_plan_last_krylov": (C.c_int, [_P, C.POINTER(_D), C.POINTER(_I32)]),
     "apdx_plan_sell_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "apdx_plan_set_stream": (C.c_int, [_P, _P]),
+    "apdx_assemble_async": (C.c_int, [_P, _P, C.c_int, _P]),
+    "apdx_spmv_async": (C.c_int, [_P, _P, _P]),
+    "apdx_stream_create": (C.c_int, [C.POINTER(_P)]),
+    "apdx_stream_synchronize": (C.c_int, [_P]),
+    "apdx_stream_destroy": (C.c_int, [_P]),
     "apdx_time_spmv": (C.c_int, [_P, _I32, C.POINTER(_D)]),
     "apdx_measure_fp64_peak": (C.c_int, [C.POINTER(_D)]),
     "apdx_comm_allreduce_host": (C.c_int, [_P, _I32, _I32]),

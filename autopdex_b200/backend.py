@@ -92,6 +92,28 @@ def host_result(n, dtype=np.float64):
     return np.asarray(lease)
 
 
+class Stream:
+    """A CUDA stream for callers without a CUDA binding of their own (apdx_stream_*)."""
+
+    def __init__(self):
+        self.ptr = C.c_void_p()
+        _lib.check(_lib.load().apdx_stream_create(C.byref(self.ptr)))
+
+    def synchronize(self):
+        _lib.check(_lib.load().apdx_stream_synchronize(self.ptr))
+
+    def destroy(self):
+        if self.ptr:
+            _lib.load().apdx_stream_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 class DeviceArray:
     """A caller-owned FP64 (or raw byte) buffer in HBM."""
 
@@ -341,6 +363,18 @@ class Plan:
 
     def spmv(self, x_d, y_d):
         _lib.check(_lib.load().apdx_spmv(self.h, x_d.ptr, y_d.ptr))
+
+    # -- caller-owned streams: the plan enqueues on `stream` (a Stream, a raw cudaStream_t, or None = its own)
+    def set_stream(self, stream):
+        raw = stream.ptr if isinstance(stream, Stream) else stream
+        _lib.check(_lib.load().apdx_plan_set_stream(self.h, raw))
+
+    def assemble_async(self, dofs_d, want_tangent=True, residual_d=None):
+        rp = residual_d.ptr if residual_d is not None else None
+        _lib.check(_lib.load().apdx_assemble_async(self.h, dofs_d.ptr, int(want_tangent), rp))
+
+    def spmv_async(self, x_d, y_d):
+        _lib.check(_lib.load().apdx_spmv_async(self.h, x_d.ptr, y_d.ptr))
 
     def krylov(self, opts, rhs_d, x_d):
         it, rr = C.c_int32(0), C.c_double(0.0)

@@ -348,10 +348,11 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
     return code;
   };
   pl->dim = dim; pl->nf = nf; pl->n_sets = n_sets; pl->n_nodes = n_nodes; pl->n_dofs = n_nodes * nf;
-  if (cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
     return fail(APDX_ERR_CUDA);
   }
+  pl->stream = pl->own_stream;
   for (auto &e : pl->ev) cudaEventCreate(&e);
   if (cudaMallocHost((void **)&pl->pinned, 64 * sizeof(double)) != cudaSuccess) {
     set_error("cudaMallocHost failed");
@@ -442,7 +443,8 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
 int apdx_plan_destroy(apdx_plan *pl) {
   if (!pl) return APDX_OK;
   g_plans.erase(std::remove(g_plans.begin(), g_plans.end(), pl), g_plans.end());
-  if (pl->stream && !pl->mg.stream_borrowed) cudaStreamSynchronize(pl->stream);
+  // a borrowed stream (the finer level's, or the caller's) may be gone already: the cudaFree calls below synchronise the device
+  if (pl->stream && pl->stream == pl->own_stream) cudaStreamSynchronize(pl->stream);
   pl->mg.release();
   for (auto &st : pl->sets) {
     st.conn.release(); st.shape_n.release(); st.shape_dn.release(); st.gp_w.release();
@@ -464,7 +466,7 @@ int apdx_plan_destroy(apdx_plan *pl) {
   k.flags.release();
   if (pl->pinned) cudaFreeHost(pl->pinned);
   for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
-  if (pl->stream && !pl->mg.stream_borrowed) cudaStreamDestroy(pl->stream);
+  if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
   delete pl;
   return APDX_OK;
 }
@@ -627,6 +629,40 @@ int apdx_spmv(apdx_plan *pl, const double *x_d, double *y_d) {
   APDX_REQUIRE(pl && x_d && y_d, APDX_ERR_INVALID, "NULL argument");
   APDX_CHECK(spmv_reduced(pl, x_d, y_d));
   APDX_CUDA(cudaStreamSynchronize(pl->stream));
+  return APDX_OK;
+}
+
+// ---- caller-owned streams ("every compute call takes a cudaStream_t and is asynchronous on it") ----------
+int apdx_plan_set_stream(apdx_plan *pl, void *cuda_stream) {
+  APDX_REQUIRE(pl, APDX_ERR_INVALID, "NULL argument");
+  APDX_REQUIRE(!pl->mg.stream_borrowed, APDX_ERR_STATE, "this plan is a coarse multigrid level: set the stream of the finest plan");
+  APDX_CUDA(cudaStreamSynchronize(pl->stream));   // work already enqueued finishes on the stream it was enqueued on
+  pl->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : pl->own_stream;
+  for (apdx_plan *l = pl->mg.coarse; l; l = l->mg.coarse) l->stream = pl->stream;
+  return APDX_OK;
+}
+int apdx_assemble_async(apdx_plan *pl, const double *dofs_d, int want_tangent, double *residual_d) {
+  APDX_REQUIRE(pl && dofs_d, APDX_ERR_INVALID, "NULL argument");
+  pl->stats = Stats();
+  return assemble_internal(pl, dofs_d, want_tangent ? 5 : 0, residual_d);   // no host synchronisation, no timing
+}
+int apdx_spmv_async(apdx_plan *pl, const double *x_d, double *y_d) {
+  APDX_REQUIRE(pl && x_d && y_d, APDX_ERR_INVALID, "NULL argument");
+  return spmv_reduced(pl, x_d, y_d);
+}
+int apdx_stream_create(void **cuda_stream) {
+  APDX_REQUIRE(cuda_stream, APDX_ERR_INVALID, "NULL argument");
+  cudaStream_t s = nullptr;
+  APDX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *cuda_stream = s;
+  return APDX_OK;
+}
+int apdx_stream_synchronize(void *cuda_stream) {
+  APDX_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+  return APDX_OK;
+}
+int apdx_stream_destroy(void *cuda_stream) {
+  if (cuda_stream) APDX_CUDA(cudaStreamDestroy(static_cast<cudaStream_t>(cuda_stream)));
   return APDX_OK;
 }
 

@@ -215,7 +215,9 @@ struct apdx_plan {
   int32_t dim = 0, nf = 0, n_sets = 0;
   int64_t n_nodes = 0, n_dofs = 0, n_free = 0, nnz = 0, nnz_red = 0, n_coo = 0, n_ke = 0, n_res = 0;
   std::vector<apdx::SetData> sets;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // the stream all work of the plan is enqueued on
+  cudaStream_t own_stream = nullptr;   // the stream the plan created (stream == own_stream unless apdx_plan_set_stream
+                                       // handed it the caller's stream, or the plan is the coarse level of another plan)
   cudaEvent_t ev[4]{};
 
   // fields

@@ -393,9 +393,10 @@ int mg_link(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_ptr, const int3
   APDX_CUDA(cudaMemcpy(m.inject.p, inj.data(), inj.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   APDX_CHECK(coarse->mg.dofs.alloc(coarse->n_dofs));
   // the coarse plan runs on the fine plan's stream from now on
-  if (coarse->stream && coarse->stream != fine->stream) {
-    cudaStreamSynchronize(coarse->stream);
-    cudaStreamDestroy(coarse->stream);
+  if (coarse->own_stream) {
+    cudaStreamSynchronize(coarse->own_stream);
+    cudaStreamDestroy(coarse->own_stream);
+    coarse->own_stream = nullptr;
   }
   coarse->stream = fine->stream;
   coarse->mg.stream_borrowed = true;

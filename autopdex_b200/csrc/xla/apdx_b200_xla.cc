@@ -7,9 +7,10 @@
 // used by tests/test_capi_and_host.py to keep this file compiling).  autopdex_b200/jax_ffi.py registers the handlers.
 //
 // Contract: CSR storage has data-dependent size, so it lives in the C-side plan (created from Python with
-// apdx_plan_create, keyed by `plan_id` = the plan pointer); only dof-shaped FP64 arrays cross into XLA.  The plan
-// runs on its own stream: every handler first waits for XLA's stream (inputs ready) and returns after the plan's
-// work has completed (the scalar Newton outputs need the host anyway), so results are visible to XLA's stream.
+// apdx_plan_create, keyed by `plan_id` = the plan pointer); only dof-shaped FP64 arrays cross into XLA.  Every handler
+// hands XLA's stream to the plan (apdx_plan_set_stream), so the plan's work is ordered with XLA's without a host wait in
+// front of it: the residual handler is fully asynchronous (apdx_assemble_async); the Newton / linear-step / sensitivity
+// handlers return after their loops have finished (the convergence scalars are read by the host inside them).
 //   apdx_newton_ffi        solver.damped_newton        autopdex/solver.py:837-948
 //   apdx_linear_step_ffi   solver.solve_linear         autopdex/solver.py:586-659
 //   apdx_residual_ffi      assembler.assemble_residual autopdex/assembler.py:587-637
@@ -48,9 +49,9 @@ ffi::Error check_size(const apdx_plan *plan, size_t elements, const char *what) 
   return ffi::Error::Success();
 }
 
-// XLA's stream must have produced the inputs before the plan's stream reads them.
-ffi::Error wait_inputs(cudaStream_t stream) {
-  if (cudaStreamSynchronize(stream) != cudaSuccess) return ffi::Error::Internal("cudaStreamSynchronize failed");
+// The plan enqueues on XLA's stream: inputs produced by earlier XLA operations are ready when the plan's kernels run.
+ffi::Error wait_inputs(apdx_plan *plan, cudaStream_t stream) {
+  if (apdx_plan_set_stream(plan, stream) != APDX_OK) return ffi::Error::Internal(apdx_last_error());
   return ffi::Error::Success();
 }
 
@@ -61,7 +62,7 @@ ffi::Error NewtonImpl(cudaStream_t stream, int64_t plan_id, int32_t method, int3
   if (ffi::Error e = check_size(plan, dofs.element_count(), "dofs must have n_dofs entries"); e.failure()) return e;
   if (infos->element_count() != 3) return ffi::Error::InvalidArgument("infos must have 3 entries");
   cudaMemcpyAsync(dofs_out->typed_data(), dofs.typed_data(), dofs.size_bytes(), cudaMemcpyDeviceToDevice, stream);
-  if (ffi::Error e = wait_inputs(stream); e.failure()) return e;
+  if (ffi::Error e = wait_inputs(plan, stream); e.failure()) return e;
   const apdx_krylov_opts o = krylov_opts(method, rtol, atol, krylov_maxiter, jacobi);
   int32_t it = 0, div = 0;
   double rn = 0.0;
@@ -69,7 +70,8 @@ ffi::Error NewtonImpl(cudaStream_t stream, int64_t plan_id, int32_t method, int3
                   &rn, &div) != APDX_OK)
     return ffi::Error::Internal(apdx_last_error());
   const double h[3] = {static_cast<double>(it), rn, static_cast<double>(div)};   // (n_steps, res_norm, diverged)
-  if (cudaMemcpy(infos->typed_data(), h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess)
+  if (cudaMemcpyAsync(infos->typed_data(), h, sizeof(h), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+      cudaStreamSynchronize(stream) != cudaSuccess)   // `h` lives on this frame
     return ffi::Error::Internal("copy of the Newton infos failed");
   return ffi::Error::Success();
 }
@@ -78,7 +80,7 @@ ffi::Error LinearStepImpl(cudaStream_t stream, int64_t plan_id, int32_t method, 
                           double atol, int32_t krylov_maxiter, F64In dofs, F64In dirichlet_values, F64Out delta) {
   apdx_plan *plan = plan_of(plan_id);
   if (ffi::Error e = check_size(plan, dofs.element_count(), "dofs must have n_dofs entries"); e.failure()) return e;
-  if (ffi::Error e = wait_inputs(stream); e.failure()) return e;
+  if (ffi::Error e = wait_inputs(plan, stream); e.failure()) return e;
   const apdx_krylov_opts o = krylov_opts(method, rtol, atol, krylov_maxiter, jacobi);
   int32_t kit = 0;
   if (apdx_linear_step(plan, &o, dofs.typed_data(), dirichlet_values.typed_data(), delta->typed_data(), &kit) != APDX_OK)
@@ -90,18 +92,17 @@ ffi::Error LinearStepImpl(cudaStream_t stream, int64_t plan_id, int32_t method, 
 ffi::Error ResidualImpl(cudaStream_t stream, int64_t plan_id, F64In dofs, F64Out residual) {
   apdx_plan *plan = plan_of(plan_id);
   if (ffi::Error e = check_size(plan, dofs.element_count(), "dofs must have n_dofs entries"); e.failure()) return e;
-  if (ffi::Error e = wait_inputs(stream); e.failure()) return e;
-  if (apdx_assemble(plan, dofs.typed_data(), /*want_tangent=*/0, residual->typed_data()) != APDX_OK)
+  if (ffi::Error e = wait_inputs(plan, stream); e.failure()) return e;
+  if (apdx_assemble_async(plan, dofs.typed_data(), /*want_tangent=*/0, residual->typed_data()) != APDX_OK)
     return ffi::Error::Internal(apdx_last_error());
-  if (apdx_synchronize() != APDX_OK) return ffi::Error::Internal(apdx_last_error());
-  return ffi::Error::Success();
+  return ffi::Error::Success();   // asynchronous on XLA's stream
 }
 
 ffi::Error TangentSolveImpl(cudaStream_t stream, int64_t plan_id, int32_t method, int32_t jacobi, double rtol,
                             double atol, int32_t krylov_maxiter, int32_t transpose, F64In dofs, F64In rhs, F64Out out) {
   apdx_plan *plan = plan_of(plan_id);
   if (ffi::Error e = check_size(plan, rhs.element_count(), "rhs must have n_dofs entries"); e.failure()) return e;
-  if (ffi::Error e = wait_inputs(stream); e.failure()) return e;
+  if (ffi::Error e = wait_inputs(plan, stream); e.failure()) return e;
   const apdx_krylov_opts o = krylov_opts(method, rtol, atol, krylov_maxiter, jacobi);
   int32_t kit = 0;
   if (apdx_tangent_solve(plan, &o, dofs.typed_data(), rhs.typed_data(), transpose, out->typed_data(), &kit) != APDX_OK)

@@ -238,6 +238,20 @@ int apdx_plan_last_krylov(const apdx_plan *plan, double *relres, int32_t *conver
  * APDX_SELL_SYM=0) out[4]=1 if symmetric storage is enabled out[5]=dofs per node the slices interleave */
 int apdx_plan_sell_info(const apdx_plan *plan, int64_t out[6]);
 
+/* ---- caller-owned streams ------------------------------------------------------------------------------
+ * A plan enqueues all of its work on ONE stream: its own (default) or, after apdx_plan_set_stream, the caller's
+ * (`cuda_stream` is a cudaStream_t; NULL goes back to the plan's own).  The entry points above finish with a host
+ * synchronisation of that stream (the Newton / Krylov loops need their convergence scalars on the host anyway);
+ * apdx_assemble_async and apdx_spmv_async are the same operations enqueued only: results are valid once the stream has
+ * reached that point, no timing statistics are recorded.  An XLA custom call (csrc/xla) hands over XLA's stream this way
+ * instead of blocking it.  apdx_stream_*: a stream for callers without a CUDA binding of their own (ctypes).            */
+int apdx_plan_set_stream(apdx_plan *plan, void *cuda_stream);
+int apdx_assemble_async(apdx_plan *plan, const double *dofs_d, int want_tangent, double *residual_d);
+int apdx_spmv_async(apdx_plan *plan, const double *x_d, double *y_d);
+int apdx_stream_create(void **cuda_stream);
+int apdx_stream_synchronize(void *cuda_stream);
+int apdx_stream_destroy(void *cuda_stream);
+
 /* average device time (ms, CUDA events on the plan's stream) of `reps` launches of the SpMV kernel
  * exactly as the CG loop launches it (fused p.Ap dot product included) */
 int apdx_time_spmv(apdx_plan *plan, int32_t reps, double *ms_avg);

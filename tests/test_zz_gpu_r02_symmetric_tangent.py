@@ -80,3 +80,41 @@ def test_cook_membrane_q1_multigrid_pcg_matches_jacobi_bicgstab():
     assert mj == mm == 1.0
     assert np.linalg.norm(um - uj) <= 1e-8 * np.linalg.norm(uj)
     assert km * 3 <= kj, (km, kj)
+
+
+def test_caller_owned_stream_and_async_entry_points():
+    """compute calls on the caller's stream, asynchronous on it (apdx_plan_set_stream, apdx_assemble_async,
+    apdx_spmv_async): same residual / product as the synchronising entry points, also for a Newton solve on that stream
+    and after switching back to the plan's own stream."""
+    from autopdex_b200 import backend
+    from tests import gpu_util
+    p = problems.neo_hooke_brick(4)
+    plan = gpu_util.make_plan(p)
+    n = p["mask"].size
+    rng = np.random.default_rng(3)
+    dofs = 1e-2 * rng.standard_normal(n)
+    d, r0, r1 = backend.DeviceArray.from_host(dofs), backend.DeviceArray(n), backend.DeviceArray(n)
+    plan.assemble(d, True, r0)                                   # reference: the synchronising entry points
+    x = rng.standard_normal(plan.n_free)
+    xd, y0, y1 = backend.DeviceArray.from_host(x), backend.DeviceArray(plan.n_free), backend.DeviceArray(plan.n_free)
+    plan.spmv(xd, y0)
+    vals0 = plan.values(False).copy()
+    st = backend.Stream()
+    plan.set_stream(st)
+    plan.assemble_async(d, True, r1)
+    plan.spmv_async(xd, y1)
+    st.synchronize()
+    assert np.array_equal(r1.download(), r0.download()) and np.array_equal(y1.download(), y0.download())
+    assert np.array_equal(plan.values(False), vals0)
+    # a whole Newton solve on the caller's stream, then back on the plan's own
+    sols = []
+    for stream in (st, None):
+        plan.set_stream(stream)
+        dd = backend.DeviceArray.from_host(np.zeros(n))
+        vv = backend.DeviceArray.from_host(p["values"])
+        it, rn, div = plan.newton(backend.KrylovOptions("bicgstab", rtol=1e-12), dd, vv)
+        assert not div and rn < 1e-8
+        sols.append((it, dd.download().copy()))
+    assert sols[0][0] == sols[1][0] and np.array_equal(sols[0][1], sols[1][1])
+    plan.destroy()
+    st.destroy()
