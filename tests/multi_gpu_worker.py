@@ -89,6 +89,42 @@ def run_case(problem, m, krylov, partition, rank, world, precond="jacobi"):
     return bool(backend.comm_allreduce_host([0.0 if ok else 1.0], "max")[0] == 0.0)
 
 
+def run_dae_case(m, precond, rank, world):
+    """dae.TimeSteppingManager (BackwardEuler, transient heat conduction through the 'user residual' route) on slab
+    partitions, against a SciPy time loop on the oracle's global mass / stiffness matrices (tests/test_zz_gpu_r02_dae.py)."""
+    from autopdex_b200 import backend, dae, mesher, solver
+    from tests import test_zz_gpu_r02_dae as T
+    dt, n_steps = 0.05, 3
+    coords, K, M, F, mask, values, res, gs = T._settings(m)
+    elems = gs["connectivity"][0]["theta"]
+    pt = mesher.slab_partition_mesh(coords, (elems,), (m, m, m), rank, world)
+    nodes = pt["nodes"]
+    settings = {"connectivity": ({"theta": pt["elements"][0].astype(np.int32)},), "node coordinates": {"theta": coords[nodes]},
+                "dirichlet dofs": {"theta": mask[nodes]}, "dirichlet conditions": {"theta": values[nodes]}, "current time": 0.0,
+                "b200 partition": pt["b200 partition"]}
+    static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": dae.BackwardEuler()},
+                       "solver backend": "b200", "solver": "cg", "type of preconditioner": precond, "verbose": -1}
+    if precond == "multigrid":
+        settings["b200 multigrid"] = {"n_elements": (m, m, m)}
+    q0 = 0.3 * np.cos(coords[:, 1])
+    mgr = dae.TimeSteppingManager(static_settings, tol=1e-13)
+    out = mgr.run({"theta": q0[nodes]}, dt, dt * n_steps, 100, settings)
+    part = settings["b200 partition"]
+    own = slice(part["owned_node_begin"], part["owned_node_end"])
+    glob = np.zeros(coords.shape[0])
+    glob[nodes[own]] = np.asarray(out.q["theta"])[own]
+    glob = backend.comm_allreduce_host(glob)
+    ok = True
+    if rank == 0:
+        ref = T._scipy_steps(K, M, F, mask, values, q0, [1.0, -1.0], dt, n_steps)[-1]
+        err = np.linalg.norm(glob - ref) / np.linalg.norm(ref)
+        ok = err < 1e-9 and out.num_accepted == n_steps and all(it == 1 for it in out.newton_iterations)
+        print("multi-gpu parity: ranks=%d dae backward-euler heat m=%d cg+%s slab steps=%d rel-L2=%.2e -> %s"
+              % (world, m, precond, out.num_accepted, err, "OK" if ok else "FAIL"), flush=True)
+    solver.clear_plan_cache()
+    return bool(backend.comm_allreduce_host([0.0 if ok else 1.0], "max")[0] == 0.0)
+
+
 def main():
     """argv: [poisson|neohooke] [M] [cg|bicgstab] [slab|rcb] [jacobi|multigrid]   one case
              matrix [Mp] [Mn]                                   {poisson Mp, neohooke Mn} x {cg, bicgstab} x {slab, rcb}
@@ -110,6 +146,9 @@ def main():
         mp = max(mp, 2 * world)      # all faces are Dirichlet faces: the first and last slab need an interior plane
         cases = [(pb, m, k, pt) for pb, m in (("poisson", mp), ("neohooke", mn)) for k in ("cg", "bicgstab")
                  for pt in ("slab", "rcb")]
+    elif argv and argv[0] == "dae":       # dae [M]: the time-stepping manager on slabs, Jacobi and multigrid
+        m = max(int(argv[1]) if len(argv) > 1 else 8, 4 * world)
+        cases = [("dae", m, "jacobi"), ("dae", m, "multigrid")]
     elif argv and argv[0] == "mgmatrix":
         mp = int(argv[1]) if len(argv) > 1 else 32
         mn = int(argv[2]) if len(argv) > 2 else 16
@@ -130,10 +169,10 @@ def main():
     for c in cases:
         signal.alarm(int(os.environ.get("APDX_CASE_TIMEOUT", "150")))
         try:
-            ok = run_case(*c[:4], rank, world, *c[4:]) and ok
+            ok = (run_dae_case(c[1], c[2], rank, world) if c[0] == "dae" else run_case(*c[:4], rank, world, *c[4:])) and ok
         except Exception as e:   # keep the remaining cases running; every rank raises alike (collective set-up errors)
             ok = False
-            print("multi-gpu parity: ranks=%d %s m=%d %s %s -> ERROR on rank %d: %s" % (world, c[0], c[1], c[2], c[3], rank, e),
+            print("multi-gpu parity: ranks=%d %s -> ERROR on rank %d: %s" % (world, " ".join(map(str, c)), rank, e),
                   flush=True)
             from autopdex_b200 import solver
             solver.clear_plan_cache()

@@ -109,6 +109,23 @@ def test_partitioned_multigrid_on_emulated_ranks():
     assert its <= 10, lines[0]
 
 
+def test_time_stepping_manager_on_emulated_ranks():
+    """dae.TimeSteppingManager (BackwardEuler heat conduction, 'user residual' route) on two slabs, Jacobi- and
+    multigrid-preconditioned CG (the coarse levels' 'dofs n' travels with the ghost-plane exchange), against the SciPy loop."""
+    rc, lines, out = _run_ranks(2, ["dae", "8"])
+    assert rc == 0 and len(lines) == 2 and all(l.endswith("-> OK") for l in lines), out[-4000:]
+
+
+def test_readme_example_runs_on_the_emulated_build():
+    """The usage example of README.md, at 8^3 instead of 64^3."""
+    lib = _build()
+    code = open(os.path.join(ROOT, "README.md")).read().split("```python")[1].split("```")[0].replace("(64, 64, 64)", "(8, 8, 8)")
+    code += "\nprint('RESULT', n_newton, float(res_norm) < 1e-8, bool(diverged))\n"
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, APDX_LIB=lib, EMU_GUARD="1"),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert r.returncode == 0 and "RESULT 1 True False" in r.stdout.decode(), r.stdout.decode()[-2000:]
+
+
 def test_capture_rules_of_the_stand_in():
     """The stand-in must be as strict as the runtime where the product depends on it: an allocation or a synchronisation
     while a stream captures invalidates the capture (a scope-bound temporary freed inside the Krylov capture would be

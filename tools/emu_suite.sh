@@ -29,5 +29,8 @@ OUT=${1:-profiles/r02f_emulated_cuda_source_suite.txt}
     EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=900 \
       python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29820 + n)) \
       tests/multi_gpu_worker.py mgmatrix 32 16 2>&1 | grep "multi-gpu parity"
+    EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=900 \
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29840 + n)) \
+      tests/multi_gpu_worker.py dae 8 2>&1 | grep "multi-gpu parity"
   done
 } | tee "$OUT"
