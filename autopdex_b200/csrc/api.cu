@@ -365,11 +365,12 @@ int apdx_plan_create(apdx_plan **plan, int32_t dim, int64_t n_nodes, int32_t nf,
     st.d = sets[i];
     st.ndof_e = st.d.nen * nf;
     st.soa = fast_kernel_applies(dim, nf, st.d);
+    st.tri = !st.soa && st.d.model != APDX_MODEL_PATTERN_ONLY;   // generic kernel (elements.cu, phase C)
     st.coo_offset = coo;
     st.res_offset = res;
     st.ke_offset = kes;
     // element-matrix stream: register-kernel sets store the upper triangle only (pattern.cu: soa_address)
-    kes += st.d.n_rows * (int64_t)(st.soa ? st.ndof_e * (st.ndof_e + 1) / 2 : st.ndof_e * st.ndof_e);
+    kes += st.d.n_rows * (int64_t)((st.soa || st.tri) ? st.ndof_e * (st.ndof_e + 1) / 2 : st.ndof_e * st.ndof_e);
     coo += st.d.n_rows * (int64_t)st.ndof_e * st.ndof_e;
     res += st.d.n_rows * (int64_t)st.ndof_e;
     const int64_t cn = st.d.n_rows * st.d.nen;

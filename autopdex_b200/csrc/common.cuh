@@ -103,9 +103,11 @@ struct SetData {
   apdx_set_desc d{};          // host copy of the descriptor (pointers invalid after create)
   int32_t ndof_e = 0;         // nen * nf
   int64_t coo_offset = 0;     // offset of this set's block in the reference-order COO numbering
-  int64_t ke_offset = 0;      // offset of this set's block in the element-matrix stream `ke` (upper triangle only for soa sets)
+  int64_t ke_offset = 0;      // offset of this set's block in the element-matrix stream `ke` (upper triangle only for soa / tri sets)
   int64_t res_offset = 0;     // offset of this set's block in the Re stream
   bool soa = false;           // element streams stored entry-major (sets handled by the register kernels)
+  bool tri = false;           // generic-kernel set: element matrices stored as their upper triangle, element-major
+                              // (ke[e * ndof (ndof + 1) / 2 + slot(i, j)]; every model of the kernel has a symmetric tangent)
   DevBuf<int32_t> conn;       // [n_rows][nen]
   DevBuf<double> shape_n, shape_dn, gp_w;
   std::vector<double> h_shape_n, h_shape_dn, h_gp_w;  // host copies (kernel-argument tables of the fast kernels)

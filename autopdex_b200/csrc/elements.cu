@@ -233,8 +233,9 @@ __global__ void __launch_bounds__(256) k_elements(ElemArgs A) {
     // ---- phase C: tangent blocks, one thread per (element, node pair a <= b) --------------------
     // Every model of this kernel has a symmetric element tangent (K[(a,i),(b,k)] = K[(b,k),(a,i)]: potential Hessians,
     // Galerkin forms with symmetric constitutive tensors, the capacity matrix), so only the nen (nen + 1) / 2 upper node
-    // pairs are integrated (36 of 64 for hex8: phase C is ~97 % of the kernel's flops) and the block is stored twice,
-    // transposed for (b, a) -- which also makes the assembled matrix symmetric to the last bit.
+    // pairs are integrated (36 of 64 for hex8: phase C is ~97 % of the kernel's flops) and only the upper triangle of
+    // the element matrix is stored (300 of 576 entries for hex8 with three dofs per node); the scatter reads entry
+    // (J, I) from the slot of (I, J), so the assembled matrix is symmetric to the last bit.
     if (A.want_tangent && A.model != APDX_MODEL_NEUMANN) {
       const int pairs = nen * (nen + 1) / 2;
       for (int i = threadIdx.x; i < cnt * pairs; i += blockDim.x) {
@@ -281,16 +282,19 @@ __global__ void __launch_bounds__(256) k_elements(ElemArgs A) {
               }
           }
         }
-        double *out = A.ke + row * (int64_t)ndof * ndof;
+        // the element matrix is stored as its upper triangle, row by row (SetData::tri; pattern.cu: soa_address):
+        // slot(I, J) = I ndof - I (I - 1) / 2 + (J - I) for dofs I <= J.  a < b: the whole block lies above the
+        // diagonal; a == b: its upper triangle (the lower one would differ by the rounding of (c g_k) g_i against
+        // (c g_i) g_k only, the gather lists read it from the transposed slot).
+        double *out = A.ke + row * ((int64_t)ndof * (ndof + 1) / 2);
 #pragma unroll
-        for (int i2 = 0; i2 < NF; ++i2)
+        for (int i2 = 0; i2 < NF; ++i2) {
+          const int I = a * NF + i2;
+          double *orow = out + ((int64_t)I * ndof - (int64_t)I * (I - 1) / 2 - I);   // + J gives slot(I, J)
 #pragma unroll
-          for (int k2 = 0; k2 < NF; ++k2) {
-            // diagonal node block: its two triangles differ by the rounding of (c g_k) g_i against (c g_i) g_k -- store the upper one twice
-            const double v = (a == b && k2 < i2) ? blk[k2][i2] : blk[i2][k2];
-            out[(int64_t)(a * NF + i2) * ndof + b * NF + k2] = v;
-            if (a != b) out[(int64_t)(b * NF + k2) * ndof + a * NF + i2] = v;
-          }
+          for (int k2 = 0; k2 < NF; ++k2)
+            if (a != b || k2 >= i2) orow[b * NF + k2] = blk[i2][k2];
+        }
       }
     }
     // ---- phase D: residual, one thread per (element, a) ----------------------------------------

@@ -50,8 +50,9 @@ __global__ void k_res_keys(const int32_t *__restrict__ conn, int64_t n_entries, 
 struct SoaSet {
   int64_t off, koff, n_rows;   // off: first reference-order index of the set; koff: start of its block in the stream
   int32_t width;   // ndof^2 (matrix stream) or ndof (vector stream)
-  int32_t sym_n;   // matrix stream of a register-kernel set: element matrices are stored as their upper triangle
-                   // (sym_n = ndof; entry (a,b) and (b,a) share slot lo*n - lo(lo-1)/2 + hi - lo); 0 = full storage
+  int32_t sym_n;   // matrix stream stored as the upper triangle of every element matrix (sym_n = ndof; entry (a,b) and
+                   // (b,a) share slot lo*n - lo(lo-1)/2 + hi - lo): entry-major for register-kernel sets (n_rows > 0),
+                   // element-major for generic-kernel sets (n_rows == 0); 0 = full storage
 };
 struct SoaTable {
   int n;
@@ -62,13 +63,14 @@ __device__ __forceinline__ int64_t soa_address(int64_t k, const SoaTable &t) {
   int q = 0;
   while (q + 1 < t.n && k >= t.s[q + 1].off) ++q;
   const int64_t local = k - t.s[q].off;
-  if (t.s[q].n_rows == 0) return t.s[q].koff + local;   // this set keeps the reference (element-major) layout
+  if (t.s[q].n_rows == 0 && t.s[q].sym_n == 0) return t.s[q].koff + local;   // reference (element-major, full) layout
   const int64_t e = local / t.s[q].width;
   int64_t ij = local - e * t.s[q].width;
   if (t.s[q].sym_n > 0) {
     const int nn = t.s[q].sym_n, a = (int)(ij / nn), b = (int)(ij - (int64_t)a * nn);
     const int lo = a < b ? a : b, hi = a < b ? b : a;
     ij = lo * nn - lo * (lo - 1) / 2 + (hi - lo);
+    if (t.s[q].n_rows == 0) return t.s[q].koff + e * ((int64_t)nn * (nn + 1) / 2) + ij;   // element-major triangle
   }
   return t.s[q].koff + ij * t.s[q].n_rows + e;
 }
@@ -88,7 +90,8 @@ static SoaTable matrix_soa_table(const apdx_plan *pl) {
   SoaTable t{};
   for (auto &st : pl->sets) {
     if (st.d.n_rows == 0) continue;
-    t.s[t.n++] = SoaSet{st.coo_offset, st.ke_offset, st.soa ? st.d.n_rows : 0, st.ndof_e * st.ndof_e, st.soa ? st.ndof_e : 0};
+    t.s[t.n++] = SoaSet{st.coo_offset, st.ke_offset, st.soa ? st.d.n_rows : 0, st.ndof_e * st.ndof_e,
+                        (st.soa || st.tri) ? st.ndof_e : 0};
   }
   return t;
 }
