@@ -93,6 +93,7 @@ SIGNATURES = {
     "apdx_comm_init": (C.c_int, [_P, _I32, _I32]),
     "apdx_comm_destroy": (C.c_int, []),
     "apdx_plan_set_partition": (C.c_int, [_P, _I64, _I64, _I32, _I32]),
+    "apdx_plan_comm_info": (C.c_int, [_P, C.POINTER(_D)]),
     "apdx_comm_exchange_planes": (C.c_int, [_P, _I64, _I64, _I64, _I32, _I32]),
     "apdx_plan_set_partition_lists": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P]),
 }

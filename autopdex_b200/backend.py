@@ -364,6 +364,13 @@ class Plan:
     def spmv(self, x_d, y_d):
         _lib.check(_lib.load().apdx_spmv(self.h, x_d.ptr, y_d.ptr))
 
+    def comm_info(self):
+        """How this partitioned plan communicates (apdx_plan_comm_info)."""
+        q = (C.c_double * 4)()
+        _lib.check(_lib.load().apdx_plan_comm_info(self.h, q))
+        return {"allreduce": "mailbox" if q[0] else "nccl", "halo": "inbox" if q[1] else "nccl",
+                "halo_inbox_us": q[2], "halo_nccl_us": q[3]}
+
     # -- caller-owned streams (SURVEY.md 8b): the plan enqueues on `stream` (a Stream, a raw cudaStream_t, or None = its own)
     def set_stream(self, stream):
         raw = stream.ptr if isinstance(stream, Stream) else stream

@@ -864,6 +864,12 @@ int apdx_plan_stats(const apdx_plan *pl, double out[8]) {
   return APDX_OK;
 }
 
+int apdx_plan_comm_info(const apdx_plan *pl, double out[4]) {
+  APDX_REQUIRE(pl && out, APDX_ERR_INVALID, "NULL argument");
+  out[0] = pl->p2p.mbox ? 1.0 : 0.0; out[1] = pl->p2p.inbox ? 1.0 : 0.0; out[2] = pl->p2p.inbox_us; out[3] = pl->p2p.nccl_us;
+  return APDX_OK;
+}
+
 int apdx_plan_newton_history(const apdx_plan *pl, double *res_norms, int32_t capacity, int32_t *count) {
   APDX_REQUIRE(pl && count && (res_norms || capacity == 0), APDX_ERR_INVALID, "NULL argument");
   *count = (int32_t)pl->newton_history.size();

@@ -135,9 +135,21 @@ struct P2PDev {
   int *mflag[P2P_MAX_RANKS];     // rank r's mailbox flags: int [2 slots][P2P_MAX_RANKS senders]
   int *err;                      // my time-out flag
   int *epoch_self;               // device-resident reduction counter of the mailbox all-reduce
+  // halo inboxes of a slab partition (dist.cu: k_halo_push / k_halo_pull): a rank stores its boundary entries straight
+  // into the neighbour's inbox over NVLink and raises a flag there; [2 slots][cap] doubles per side, slot = parity of
+  // the exchange counter
+  double *peer_inbox_lo, *peer_inbox_hi;   // rank_lo's upper / rank_hi's lower inbox (nullptr: no neighbour)
+  int *peer_flag_lo, *peer_flag_hi;        // the flag pair [2 slots] that belongs to those inboxes
+  double *my_inbox_lo, *my_inbox_hi;       // where rank_lo / rank_hi deposit my ghost entries
+  int *my_flag_lo, *my_flag_hi;
+  int *halo_epoch;                         // device-resident exchange counter
+  unsigned int *halo_ticket;               // [2] last-block tickets of the push and the pull kernel
+  long long cap;                           // doubles per inbox slot
 };
 struct P2P {
-  bool mbox = false;             // the dot-product all-reduces go through the mailboxes; halo stays on NCCL
+  bool mbox = false;             // the dot-product all-reduces go through the mailboxes
+  bool inbox = false;            // the halo exchange goes through the peer inboxes instead of ncclSend/ncclRecv
+  double inbox_us = 0, nccl_us = 0;   // set-up measurement behind that decision (per exchange, max over ranks)
   char *heap = nullptr;          // exported block: [mailboxes | flags]
   size_t heap_bytes = 0;
   void *peer_base[P2P_MAX_RANKS]{};

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -139,10 +140,89 @@ int comm_halo_setup_lists(apdx_plan *pl) {
   return APDX_OK;
 }
 
+// ---- halo exchange through peer inboxes (slab partitions) ---------------------------------------------------------
+// ncclSend/ncclRecv of one node plane (528 KB at 256^3) costs ~39 us per CG iteration on 8 GPUs -- latency, not bandwidth
+// (profiles/r02b_trace_n8.txt).  Here every rank stores its boundary entries straight into its neighbours' inboxes over
+// NVLink and raises a flag there (k_halo_push), then waits for its own flags and copies the inboxes into the ghost
+// entries of x (k_halo_pull).  Two small kernels, no NCCL, replayable inside the Krylov graph: the exchange counter
+// lives on the device and its parity selects one of two inbox slots (a rank can be at most one exchange ahead of a
+// neighbour: its next push needs the neighbour's previous one).  Two kernels rather than one, so that no block ever
+// waits for a peer while blocks of the same grid still have to post (no co-residency assumption).
+constexpr int HALO_BLOCKS = 16;
+__device__ __forceinline__ void halo_wait(const int *flag, int epoch, int *err) {
+  const long long t0 = clock64();
+  while (*(volatile const int *)flag < epoch) {
+    if (clock64() - t0 > 20000000000ll) {  // ~10 s (ranks may enter a solve seconds apart): a lost peer must not hang the GPU
+      *err = 1;
+      break;
+    }
+  }
+  __threadfence_system();
+}
+__global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ x, int64_t f0, int64_t f1, int64_t send_lo,
+                                                   int64_t send_hi, const P2PDev *pd) {
+  __shared__ bool last;
+  const int e = *pd->halo_epoch + 1;
+  const size_t slot = (size_t)(e & 1) * (size_t)pd->cap;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (pd->peer_inbox_lo)
+    for (int64_t i = tid; i < send_lo; i += nth) pd->peer_inbox_lo[slot + i] = x[f0 + i];
+  if (pd->peer_inbox_hi)
+    for (int64_t i = tid; i < send_hi; i += nth) pd->peer_inbox_hi[slot + i] = x[f1 - send_hi + i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(pd->halo_ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {   // every block's stores are visible system-wide: raise the flags
+    pd->halo_ticket[0] = 0u;
+    __threadfence_system();
+    if (pd->peer_flag_lo) *(volatile int *)(pd->peer_flag_lo + (e & 1)) = e;
+    if (pd->peer_flag_hi) *(volatile int *)(pd->peer_flag_hi + (e & 1)) = e;
+  }
+}
+__global__ void __launch_bounds__(256) k_halo_pull(double *__restrict__ x, int64_t f1, int64_t halo_lo, int64_t halo_hi,
+                                                   const P2PDev *pd) {
+  __shared__ bool last;
+  const int e = *pd->halo_epoch + 1;
+  const size_t slot = (size_t)(e & 1) * (size_t)pd->cap;
+  if (threadIdx.x == 0) {
+    if (pd->my_inbox_lo && halo_lo > 0) halo_wait(pd->my_flag_lo + (e & 1), e, pd->err);
+    if (pd->my_inbox_hi && halo_hi > 0) halo_wait(pd->my_flag_hi + (e & 1), e, pd->err);
+  }
+  __syncthreads();
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (pd->my_inbox_lo)   // written by a peer: read past the L1 (a line of the slot's previous use may still sit there)
+    for (int64_t i = tid; i < halo_lo; i += nth) x[i] = __ldcg(pd->my_inbox_lo + slot + i);
+  if (pd->my_inbox_hi)
+    for (int64_t i = tid; i < halo_hi; i += nth) x[f1 + i] = __ldcg(pd->my_inbox_hi + slot + i);
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(pd->halo_ticket + 1, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {   // every block has read the counter (it is read before the ticket is taken)
+    pd->halo_ticket[1] = 0u;
+    *pd->halo_epoch = e;
+  }
+}
+static int comm_halo_exchange_inbox(apdx_plan *pl, double *x_d, cudaStream_t s) {
+  const P2PDev *pd = pl->p2p.dev;
+  k_halo_push<<<HALO_BLOCKS, 256, 0, s>>>(x_d, pl->f0, pl->f1, pl->rank_lo >= 0 ? pl->send_lo : 0,
+                                          pl->rank_hi >= 0 ? pl->send_hi : 0, pd);
+  k_halo_pull<<<HALO_BLOCKS, 256, 0, s>>>(x_d, pl->f1, pl->rank_lo >= 0 ? pl->halo_lo : 0, pl->rank_hi >= 0 ? pl->halo_hi : 0, pd);
+  pl->stats.kernel_launches += 2;
+  APDX_CUDA(cudaGetLastError());
+  return APDX_OK;
+}
+
+static int comm_halo_exchange_nccl(apdx_plan *pl, double *x_d, cudaStream_t s);
+
 // x_d is a vector in the local reduced numbering: [ghost_lo | owned | ghost_hi] (slabs) or [owned | ghosts by owner]
 int comm_halo_exchange(apdx_plan *pl, double *x_d, cudaStream_t s) {
   if (pl->hl.active) return comm_halo_exchange_lists(pl, x_d, s);
   if (pl->rank_lo < 0 && pl->rank_hi < 0) return APDX_OK;
+  if (pl->p2p.inbox) return comm_halo_exchange_inbox(pl, x_d, s);
+  return comm_halo_exchange_nccl(pl, x_d, s);
+}
+static int comm_halo_exchange_nccl(apdx_plan *pl, double *x_d, cudaStream_t s) {
   APDX_NCCL(g_nccl.GroupStart());
   if (pl->rank_lo >= 0) {
     if (pl->send_lo > 0) APDX_NCCL(g_nccl.Send(x_d + pl->f0, (size_t)pl->send_lo, ncclFloat64, pl->rank_lo, g_nccl.comm, s));
@@ -213,6 +293,18 @@ static inline double *hdr_mbox(void *base) { return reinterpret_cast<double *>(b
 static inline int *hdr_mflag(void *base) { return reinterpret_cast<int *>(static_cast<char *>(base) + 2 * P2P_MAX_RANKS * 4 * sizeof(double)); }
 static inline int *hdr_err(void *base) { return hdr_mflag(base) + 2 * P2P_MAX_RANKS; }
 static inline int *hdr_epoch(void *base) { return hdr_err(base) + 1; }
+// halo part of the block: flags and counters at byte 2048, the inboxes behind the 4 KB header
+static inline int *hdr_hflag_lo(void *base) { return reinterpret_cast<int *>(static_cast<char *>(base) + 2048); }   // [2 slots]
+static inline int *hdr_hflag_hi(void *base) { return hdr_hflag_lo(base) + 2; }                                      // [2 slots]
+static inline int *hdr_hepoch(void *base) { return hdr_hflag_lo(base) + 4; }
+static inline unsigned int *hdr_hticket(void *base) { return reinterpret_cast<unsigned int *>(hdr_hflag_lo(base) + 5); }  // [2]
+static inline double *hdr_inbox_lo(void *base) { return reinterpret_cast<double *>(static_cast<char *>(base) + P2P_HDR); }
+static inline double *hdr_inbox_hi(void *base, int64_t cap) { return hdr_inbox_lo(base) + 2 * cap; }
+
+__global__ void k_halo_test_fill(double *__restrict__ a, double *__restrict__ b, int64_t n, double rank) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    a[i] = b[i] = rank * 1.0e7 + (double)i;
+}
 
 // A block may still be mapped by the peers when its plan dies, so it is only parked here; apdx_comm_destroy
 // (a collective call) frees the parked blocks after a barrier.
@@ -235,6 +327,67 @@ static void p2p_free_parked() {
   g_parked.clear();
 }
 
+// Decide, on the machine the plan runs on, whether its halo exchange goes through the peer inboxes: one exchange of a
+// rank- and index-dependent pattern through NCCL and one through the inboxes must deliver identical ghost entries on
+// every rank (and no wait may time out); then both are timed (CUDA events, maximum over the ranks) and the faster one
+// is kept.  `force`: APDX_HALO=inbox keeps the inboxes whenever they are correct.  Collective.
+static int halo_inbox_selftest(apdx_plan *pl, bool force) {
+  P2P &P = pl->p2p;
+  cudaStream_t s = pl->stream;
+  const int64_t n = pl->n_free;
+  const int64_t hl = pl->rank_lo >= 0 ? pl->halo_lo : 0, hh = pl->rank_hi >= 0 ? pl->halo_hi : 0;
+  double *xa = nullptr, *xb = nullptr;
+  APDX_CUDA(cudaMalloc((void **)&xa, (size_t)n * sizeof(double)));
+  APDX_CUDA(cudaMalloc((void **)&xb, (size_t)n * sizeof(double)));
+  k_halo_test_fill<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8), 256, 0, s>>>(xa, xb, n, (double)g_nccl.rank);
+  int rc = comm_halo_exchange_nccl(pl, xa, s);
+  if (rc == APDX_OK) rc = comm_halo_exchange_inbox(pl, xb, s);
+  if (rc == APDX_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = APDX_ERR_CUDA;
+  double v[3] = {0.0, 0.0, 0.0};   // (bad, inbox us, nccl us)
+  if (rc == APDX_OK) {
+    std::vector<double> ga((size_t)(hl + hh)), gb((size_t)(hl + hh));
+    if (hl > 0) { cudaMemcpy(ga.data(), xa, hl * sizeof(double), cudaMemcpyDeviceToHost); cudaMemcpy(gb.data(), xb, hl * sizeof(double), cudaMemcpyDeviceToHost); }
+    if (hh > 0) { cudaMemcpy(ga.data() + hl, xa + pl->f1, hh * sizeof(double), cudaMemcpyDeviceToHost); cudaMemcpy(gb.data() + hl, xb + pl->f1, hh * sizeof(double), cudaMemcpyDeviceToHost); }
+    int err = 0;
+    cudaMemcpy(&err, P.err_d, sizeof(int), cudaMemcpyDeviceToHost);
+    if (err || (!ga.empty() && memcmp(ga.data(), gb.data(), ga.size() * sizeof(double)) != 0)) v[0] = 1.0;
+    if (err) cudaMemset(P.err_d, 0, sizeof(int));
+    const int reps = 20;
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < reps && rc == APDX_OK; ++i) rc = comm_halo_exchange_inbox(pl, xb, s);
+    cudaEventRecord(e1, s);
+    for (int i = 0; i < reps && rc == APDX_OK; ++i) rc = comm_halo_exchange_nccl(pl, xa, s);
+    cudaEventRecord(e2, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) rc = APDX_ERR_CUDA;
+    float t_in = 0.f, t_nc = 0.f;
+    cudaEventElapsedTime(&t_in, e0, e1);
+    cudaEventElapsedTime(&t_nc, e1, e2);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    v[1] = 1e3 * t_in / reps; v[2] = 1e3 * t_nc / reps;
+    cudaMemcpy(&err, P.err_d, sizeof(int), cudaMemcpyDeviceToHost);
+    if (err) { v[0] = 1.0; cudaMemset(P.err_d, 0, sizeof(int)); }
+  }
+  cudaFree(xa);
+  cudaFree(xb);
+  cudaGetLastError();
+  if (rc != APDX_OK) v[0] = 1.0;   // still take part in the collective decision
+  double *dv = nullptr;
+  APDX_CUDA(cudaMalloc((void **)&dv, sizeof(v)));
+  APDX_CUDA(cudaMemcpy(dv, v, sizeof(v), cudaMemcpyHostToDevice));
+  APDX_NCCL(g_nccl.AllReduce(dv, dv, 3, ncclFloat64, ncclMax, g_nccl.comm, s));
+  APDX_CUDA(cudaStreamSynchronize(s));
+  APDX_CUDA(cudaMemcpy(v, dv, sizeof(v), cudaMemcpyDeviceToHost));
+  cudaFree(dv);
+  P.inbox_us = v[1]; P.nccl_us = v[2];
+  P.inbox = v[0] == 0.0 && (force || v[1] < v[2]);
+  if (g_nccl.rank == 0 && getenv("APDX_TRACE"))
+    fprintf(stderr, "[apdx trace] halo exchange of %lld + %lld entries: peer inboxes %.1f us, nccl %.1f us, %s -> %s\n", (long long)hl,
+            (long long)hh, v[1], v[2], v[0] == 0.0 ? "identical ghost entries" : "MISMATCH or time-out", P.inbox ? "inboxes" : "nccl");
+  return APDX_OK;
+}
+
 // Dot-product all-reduces of the Krylov loop through peer-memory mailboxes over NVLink (k_allreduce_mbox_apply,
 // krylov.cu) -- the default since round 2: 256^3 Newton step 145.3 -> 143.7 ms on 2, 89.3 -> 86.1 ms on 4 and
 // 65.9 -> 58.0 ms on 8 B200s against ncclAllReduce + a one-thread stage kernel (profiles/r02b_bench_n{2,4,8}*_sample.json).
@@ -249,7 +402,23 @@ int p2p_setup(apdx_plan *pl) {
   p2p_teardown(pl);
   cudaStream_t s = pl->stream;
   const int me = g_nccl.rank, nr = g_nccl.nranks;
-  P.heap_bytes = P2P_HDR;
+  // halo inboxes (slab partitions; APDX_HALO=nccl keeps ncclSend/ncclRecv): one capacity for every rank, so that the
+  // block has the same layout everywhere
+  const char *hmode = getenv("APDX_HALO");
+  int64_t cap = 0;
+  {
+    double need = (!pl->hl.active && !(hmode && strcmp(hmode, "nccl") == 0))
+                      ? (double)std::max(pl->rank_lo >= 0 ? pl->halo_lo : 0, pl->rank_hi >= 0 ? pl->halo_hi : 0) : 0.0;
+    double *dn = nullptr;
+    APDX_CUDA(cudaMalloc((void **)&dn, sizeof(double)));
+    APDX_CUDA(cudaMemcpy(dn, &need, sizeof(double), cudaMemcpyHostToDevice));
+    APDX_NCCL(g_nccl.AllReduce(dn, dn, 1, ncclFloat64, ncclMax, g_nccl.comm, s));
+    APDX_CUDA(cudaStreamSynchronize(s));
+    APDX_CUDA(cudaMemcpy(&need, dn, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dn);
+    cap = (int64_t)need;
+  }
+  P.heap_bytes = (P2P_HDR + 4 * (size_t)cap * sizeof(double) + 4095) & ~(size_t)4095;
   APDX_CUDA(cudaMalloc((void **)&P.heap, P.heap_bytes));
   APDX_CUDA(cudaMemset(P.heap, 0, P.heap_bytes));
   // exchange IPC handles
@@ -302,9 +471,23 @@ int p2p_setup(apdx_plan *pl) {
   for (int r = 0; r < nr; ++r) { d.mbox[r] = hdr_mbox(P.peer_base[r]); d.mflag[r] = hdr_mflag(P.peer_base[r]); }
   d.err = P.err_d;
   d.epoch_self = hdr_epoch(P.heap);
+  d.cap = cap;
+  d.halo_epoch = hdr_hepoch(P.heap);
+  d.halo_ticket = hdr_hticket(P.heap);
+  if (cap > 0) {
+    if (pl->rank_lo >= 0) {   // my lowest owned entries are rank_lo's UPPER ghosts, and the other way round
+      d.peer_inbox_lo = hdr_inbox_hi(P.peer_base[pl->rank_lo], cap); d.peer_flag_lo = hdr_hflag_hi(P.peer_base[pl->rank_lo]);
+      d.my_inbox_lo = hdr_inbox_lo(P.heap); d.my_flag_lo = hdr_hflag_lo(P.heap);
+    }
+    if (pl->rank_hi >= 0) {
+      d.peer_inbox_hi = hdr_inbox_lo(P.peer_base[pl->rank_hi]); d.peer_flag_hi = hdr_hflag_lo(P.peer_base[pl->rank_hi]);
+      d.my_inbox_hi = hdr_inbox_hi(P.heap, cap); d.my_flag_hi = hdr_hflag_hi(P.heap);
+    }
+  }
   APDX_CUDA(cudaMalloc((void **)&P.dev, sizeof(P2PDev)));
   APDX_CUDA(cudaMemcpy(P.dev, &d, sizeof(P2PDev), cudaMemcpyHostToDevice));
   P.mbox = true;
+  if (cap > 0) APDX_CHECK(halo_inbox_selftest(pl, hmode && strcmp(hmode, "inbox") == 0));
   return APDX_OK;
 }
 

@@ -454,6 +454,7 @@ def run_b200(args):
     spmv_ms = plan.time_spmv(50)
     spmv_ms = float(backend.comm_allreduce_host([spmv_ms], "max")[0])
     dev_gb_after_solve = plan.device_bytes_now() / 1e9
+    comm_info = plan.comm_info() if world > 1 else None
     clocks = sampler.stop()
 
     # ---- parity guard on the full-size run: residual norm and a discrete maximum principle ----
@@ -524,6 +525,7 @@ def run_b200(args):
                "algorithmic_frac": cg_alg_gbs / hbm, "krylov_ms": float(np.mean(kry_ms)),
                "note": "streamed = SpMV physical bytes + 80 B/row of vector streams per iteration"},
         "vector_problem": vector,
+        "comm": comm_info,      # N > 1: mailbox / NCCL all-reduce, peer-inbox / NCCL halo exchange and the set-up timing behind the choice
         "system": {"n_free": nfree, "nnz_reduced": nnz, "plan_device_gb": dev_gb_after_solve,
                    "plan_device_gb_note": "all device buffers of the plan after the solves (pattern, gather lists, element streams, sliced-ELL matrix, Krylov vectors)"},
     }

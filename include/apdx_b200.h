@@ -272,6 +272,11 @@ int apdx_comm_destroy(void);
 int apdx_comm_allreduce_host(double *inout_h, int32_t count, int32_t op);
 int apdx_plan_set_partition(apdx_plan *plan, int64_t owned_dof_begin, int64_t owned_dof_end,
                             int32_t rank_lo, int32_t rank_hi);
+/* How a partitioned plan communicates (decided when the partition is set): out[0] = 1 if the dot-product all-reduces go
+ * through the peer-memory mailboxes (else ncclAllReduce), out[1] = 1 if the halo exchange goes through the peer inboxes
+ * (else ncclSend/ncclRecv), out[2], out[3] = microseconds per halo exchange through the inboxes / through NCCL measured at
+ * set-up (maximum over the ranks; the faster one is kept unless APDX_HALO=nccl|inbox says otherwise; 0 = not measured). */
+int apdx_plan_comm_info(const apdx_plan *plan, double out[4]);
 /* Slab neighbours swap boundary blocks of a device vector of n doubles laid out [ghost_lo | owned | ghost_hi]: the first
  * lo_count owned entries go to rank_lo, whose answer fills [0, lo_count); the last hi_count owned entries go to rank_hi,
  * whose answer fills [n - hi_count, n).  Collective between neighbours (both sides pass the size of one node plane);
