@@ -31,7 +31,7 @@ __global__ void k_apply_stage(int stage, double *sc, int32_t *fl) {
 __device__ __forceinline__ void p2p_wait(const int *flag, int epoch, int *err) {
   const long long t0 = clock64();
   while (*(volatile const int *)flag < epoch) {
-    if (clock64() - t0 > 4000000000ll) {  // ~2 s
+    if (clock64() - t0 > 20000000000ll) {  // ~10 s (ranks may enter a solve seconds apart)
       *err = 1;
       break;
     }

@@ -19,14 +19,18 @@ OUT=${1:-profiles/r02f_emulated_cuda_source_suite.txt}
       | grep -E "^\[emu\]|passed|failed|error" 
   done
   for n in 2 4 8; do
-    echo "## multi-rank: tests/multi_gpu_worker.py matrix on $n emulated ranks (fake NCCL over Unix sockets, CUDA IPC over POSIX shm: mailbox all-reduce, EMU_GUARD=1)"
-    EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=600 \
+    echo "## multi-rank: tests/multi_gpu_worker.py matrix on $n emulated ranks (fake NCCL over Unix sockets, CUDA IPC over POSIX shm: mailbox all-reduce, peer-inbox halo exchange forced, EMU_GUARD=1)"
+    APDX_HALO=inbox EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=600 \
       python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29800 + n)) \
       tests/multi_gpu_worker.py matrix 12 8 2>&1 | grep "multi-gpu parity"
   done
+  echo "## multi-rank: matrix on 2 emulated ranks, APDX_COMM=nccl APDX_HALO=nccl (ncclAllReduce + ncclSend/ncclRecv only)"
+  APDX_COMM=nccl APDX_HALO=nccl EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=600 \
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29811 \
+    tests/multi_gpu_worker.py matrix 12 8 2>&1 | grep "multi-gpu parity"
   for n in 2 3 4; do
-    echo "## partitioned multigrid: tests/multi_gpu_worker.py mgmatrix on $n emulated ranks"
-    EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=900 \
+    echo "## partitioned multigrid: tests/multi_gpu_worker.py mgmatrix on $n emulated ranks (peer-inbox halo exchange forced)"
+    APDX_HALO=inbox EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=900 \
       python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29820 + n)) \
       tests/multi_gpu_worker.py mgmatrix 32 16 2>&1 | grep "multi-gpu parity"
     EMU_GUARD=1 APDX_LIB=$LIB APDX_NCCL_LIB=$PWD/tests/emu/build/libfakenccl.so APDX_CASE_TIMEOUT=900 \
