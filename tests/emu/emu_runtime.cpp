@@ -128,6 +128,15 @@ unsigned live_mask() {
   return m;
 }
 
+static int exec_order() {   // 0 = ascending, 1 = reverse, 2 = shuffled blocks + reversed threads
+  static int o = -1;
+  if (o < 0) {
+    const char *e = getenv("EMU_ORDER");
+    o = !e ? 0 : (strcmp(e, "reverse") == 0 ? 1 : (strcmp(e, "shuffle") == 0 ? 2 : 0));
+  }
+  return o;
+}
+
 static void run_block() {
   const int n = g_nthreads;
   for (int t = 0; t < n; ++t) prepare(g_fib[t]);
@@ -135,7 +144,8 @@ static void run_block() {
   int done = 0;
   while (done < n) {
     bool progressed = false;
-    for (int t = 0; t < n; ++t) {
+    for (int tt = 0; tt < n; ++tt) {
+      const int t = exec_order() ? n - 1 - tt : tt;
       Fiber &f = g_fib[t];
       if (f.state != NEW && f.state != RUNNABLE) continue;
       g_cur = t;
@@ -233,12 +243,25 @@ static void run_grid(const Cfg &c, const char *name, const std::function<void()>
   bdim = c.block;
   gdim = c.grid;
   g_dyn_smem.assign(c.smem + 16, (char)0xFF);
-  for (unsigned z = 0; z < c.grid.z; ++z)
-    for (unsigned y = 0; y < c.grid.y; ++y)
-      for (unsigned x = 0; x < c.grid.x; ++x) {
-        bid = uint3{x, y, z};
-        run_block();
-      }
+  // EMU_ORDER=reverse|shuffle: blocks (and the threads inside a block) run in another order -- nothing in the product may
+  // depend on the order in which the hardware happens to schedule them (a poor man's racecheck for order dependence)
+  const size_t nblocks = (size_t)c.grid.x * c.grid.y * c.grid.z;
+  const int order = exec_order();
+  uint64_t lcg = 0x9E3779B97F4A7C15ull * (uint64_t)(g_launches + 1);
+  std::vector<uint32_t> perm;
+  if (order == 2) {
+    perm.resize(nblocks);
+    for (size_t i = 0; i < nblocks; ++i) perm[i] = (uint32_t)i;
+    for (size_t i = nblocks; i > 1; --i) {
+      lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+      std::swap(perm[i - 1], perm[(size_t)((lcg >> 33) % i)]);
+    }
+  }
+  for (size_t k = 0; k < nblocks; ++k) {
+    const size_t b = order == 1 ? nblocks - 1 - k : (order == 2 ? perm[k] : k);
+    bid = uint3{(unsigned)(b % c.grid.x), (unsigned)((b / c.grid.x) % c.grid.y), (unsigned)(b / ((size_t)c.grid.x * c.grid.y))};
+    run_block();
+  }
   g_body = nullptr;
   g_kernel = "(none)";
 }

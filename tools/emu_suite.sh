@@ -4,6 +4,8 @@
 #   EMU_GUARD=1  every device block ends right in front of an inaccessible page  (over-runs fault, kernel/block/thread printed)
 #   EMU_GUARD=2  every device block starts right behind one                        (under-runs fault)
 #   EMU_GUARD=0  malloc'ed blocks between red zones, filled with 0xFF, freed blocks scribbled; 5 emulated SMs
+#   EMU_ORDER=shuffle|reverse  blocks run in a shuffled / reversed order, threads of a block in reverse: results (several
+#                tests assert bit-identical outputs) must not depend on the schedule
 # The container has no GPU and no compute-sanitizer target; this is the memcheck that can run here.  Log -> profiles/.
 set -u
 cd "$(dirname "$0")/.."
@@ -12,10 +14,10 @@ LIB=$PWD/tests/emu/build/libapdx_b200_emu.so
 OUT=${1:-profiles/r02f_emulated_cuda_source_suite.txt}
 {
   echo "# $(date -u +%FT%TZ)  $(git rev-parse --short HEAD)  emulated CUDA source, -m gpu suite without tests/test_gpu_fullsize.py"
-  for mode in "1 2" "2 2" "0 5"; do
+  for mode in "1 2 ascending" "2 2 ascending" "0 5 ascending" "1 2 shuffle" "1 2 reverse"; do
     set -- $mode
-    echo "## EMU_GUARD=$1 EMU_SMS=$2"
-    EMU_GUARD=$1 EMU_SMS=$2 APDX_LIB=$LIB python -m pytest tests -q -m gpu --deselect tests/test_gpu_fullsize.py -p no:cacheprovider 2>&1 \
+    echo "## EMU_GUARD=$1 EMU_SMS=$2 EMU_ORDER=$3 (order in which blocks, and threads inside a block, are executed)"
+    EMU_ORDER=$3 EMU_GUARD=$1 EMU_SMS=$2 APDX_LIB=$LIB python -m pytest tests -q -m gpu --deselect tests/test_gpu_fullsize.py -p no:cacheprovider 2>&1 \
       | grep -E "^\[emu\]|passed|failed|error" 
   done
   for n in 2 4 8; do
