@@ -89,6 +89,44 @@ def run_case(problem, m, krylov, partition, rank, world, precond="jacobi"):
     return bool(backend.comm_allreduce_host([0.0 if ok else 1.0], "max")[0] == 0.0)
 
 
+def run_quad_case(n, precond, rank, world):
+    """2-D: the README problem (Q1 quads, dict dofs, 'user potential' route) on slabs, Jacobi or multigrid, against the oracle."""
+    from autopdex_b200 import backend, mesher, models, seeder, solver, spaces
+    from oracle import solve as osolve
+    from tests import problems
+    p = problems.readme_poisson(n)
+    coords, elems = p["coords"], p["sets"][0]["conn"]
+    pt = mesher.slab_partition_mesh(coords, (elems,), (n, n), rank, world)
+    nodes = pt["nodes"]
+    integrand = models.poisson_potential("phi", source_fun=problems.readme_source)
+    pot = models.mixed_reference_domain_potential(integrand, {"phi": spaces.fem_iso_line_quad_brick},
+                                                  *seeder.gauss_legendre_nd(dimension=2, order=2), "phi")
+    static_settings = {"assembling mode": ("user potential",), "solution structure": ("nodal imposition",), "model": (pot,),
+                       "solver type": "newton", "solver backend": "b200", "solver": "cg", "type of preconditioner": precond, "verbose": -1}
+    settings = {"connectivity": ({"phi": pt["elements"][0].astype(np.int32)},), "dirichlet dofs": {"phi": p["mask"][nodes, 0]},
+                "node coordinates": {"phi": coords[nodes]}, "dirichlet conditions": {"phi": np.zeros(nodes.size)},
+                "b200 partition": pt["b200 partition"]}
+    if precond == "multigrid":
+        settings["b200 multigrid"] = {"n_elements": (n, n)}
+    sol, (steps, res, div) = solver.solver({"phi": np.zeros(nodes.size)}, settings, static_settings, tol=1e-12)
+    its = int(solver.last_stats["krylov_iters"])
+    part = settings["b200 partition"]
+    own = slice(part["owned_node_begin"], part["owned_node_end"])
+    glob = np.zeros(coords.shape[0])
+    glob[nodes[own]] = np.asarray(sol["phi"])[own]
+    glob = backend.comm_allreduce_host(glob)
+    ok = True
+    if rank == 0:
+        prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+        ref, (rsteps, _, rdiv) = osolve.damped_newton(prob, np.zeros(p["mask"].shape))
+        err = np.linalg.norm(glob - ref.ravel()) / np.linalg.norm(ref)
+        ok = err < 1e-8 and steps == rsteps and div == rdiv
+        print("multi-gpu parity: ranks=%d readme quad4 n=%d (2-D, dict dofs) cg+%s slab steps=%d/%d krylov_iters=%d rel-L2=%.2e -> %s"
+              % (world, n, precond, steps, rsteps, its, err, "OK" if ok else "FAIL"), flush=True)
+    solver.clear_plan_cache()
+    return bool(backend.comm_allreduce_host([0.0 if ok else 1.0], "max")[0] == 0.0)
+
+
 def run_dae_case(m, precond, rank, world):
     """dae.TimeSteppingManager (BackwardEuler, transient heat conduction through the 'user residual' route) on slab
     partitions, against a SciPy time loop on the oracle's global mass / stiffness matrices (tests/test_zz_gpu_r02_dae.py)."""
@@ -152,7 +190,8 @@ def main():
     elif argv and argv[0] == "mgmatrix":
         mp = int(argv[1]) if len(argv) > 1 else 32
         mn = int(argv[2]) if len(argv) > 2 else 16
-        cases = [("poisson", mp, "cg", "slab", "multigrid"), ("neohooke", mn, "cg", "slab", "multigrid")]
+        cases = [("poisson", mp, "cg", "slab", "multigrid"), ("neohooke", mn, "cg", "slab", "multigrid"),
+                 ("quad", max(mp, 4 * world), "multigrid")]
     else:
         problem = "poisson"
         if argv and not argv[0].isdigit():
@@ -169,7 +208,8 @@ def main():
     for c in cases:
         signal.alarm(int(os.environ.get("APDX_CASE_TIMEOUT", "150")))
         try:
-            ok = (run_dae_case(c[1], c[2], rank, world) if c[0] == "dae" else run_case(*c[:4], rank, world, *c[4:])) and ok
+            ok = (run_dae_case(c[1], c[2], rank, world) if c[0] == "dae" else
+                  run_quad_case(c[1], c[2], rank, world) if c[0] == "quad" else run_case(*c[:4], rank, world, *c[4:])) and ok
         except Exception as e:   # keep the remaining cases running; every rank raises alike (collective set-up errors)
             ok = False
             print("multi-gpu parity: ranks=%d %s -> ERROR on rank %d: %s" % (world, " ".join(map(str, c)), rank, e),
