@@ -273,6 +273,39 @@ def workload_name(m, rtol, world):
 HEX8_NEOHOOKE_FLOP_EXECUTED = 35200.0
 
 
+def vector_newton_figures(n):
+    """Config-5 family through the public API at n^3 (neo-Hooke brick clamped at x = 0, traction face at x = 1, nf = 3):
+    one Newton solve with the config's Jacobi-BiCGSTAB and one with the multigrid-preconditioned CG (SURVEY.md 8f row N4:
+    the reference's pyamg / PETSc preconditioners) -- Newton counts, Krylov iterations, device time, distance of the two
+    solutions."""
+    from autopdex_b200 import solver
+    from tests import problems
+    from tests.multi_gpu_worker import neohooke_api_problem
+    p = problems.neo_hooke_brick(n)
+    base = neohooke_api_problem(p)
+    out, sols, kept = {}, {}, set(solver._PLAN_CACHE)      # the headline plan (bench still reads it) stays
+    for name, st in (("jacobi_bicgstab", dict(base, solver="bicgstab")),
+                     ("multigrid_pcg", dict(base, solver="cg", **{"type of preconditioner": "multigrid"}))):
+        settings = {"connectivity": tuple(s["conn"].astype(np.int32) for s in p["sets"]), "node coordinates": p["coords"],
+                    "dirichlet dofs": p["mask"], "dirichlet conditions": p["values"]}
+        if name == "multigrid_pcg":
+            settings["b200 multigrid"] = {"n_elements": (n, n, n)}
+        d0 = np.zeros(p["mask"].shape)
+        solver.solver(d0, settings, st, tol=1e-8)                     # plan (and hierarchy) build
+        sol, info = solver.solver(d0, settings, st, tol=1e-8)
+        q = dict(solver.last_stats)
+        sols[name] = np.asarray(sol)
+        out[name] = {"newton_steps": int(info[0]), "res_norm": float(info[1]), "diverged": bool(info[2]),
+                     "krylov_iterations": int(q["krylov_iters"]), "device_ms": float(q["total_ms"]), "krylov_ms": float(q["krylov_ms"]),
+                     "assembly_tangent_ms": float(q["assembly_tangent_ms"])}
+        for key in [k for k in solver._PLAN_CACHE if k not in kept]:
+            solver._PLAN_CACHE.pop(key).destroy()
+    a, b = sols["multigrid_pcg"].ravel(), sols["jacobi_bicgstab"].ravel()
+    out["rel_l2_between_the_two_solutions"] = float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    out["workload"] = "3D neo-Hooke Q1 hex %d^3 brick (%d dofs), clamped face + traction face, Newton to 1e-8, Krylov rtol 1e-8" % (n, p["mask"].size)
+    return out
+
+
 def vector_problem_figures(args, hbm, fp64_peak, n=64):
     """Bounded nf = 3 run (BASELINE config 5 family at n^3): hex8 neo-Hooke tangent pass (generic element kernel
     k_elements<3,3> + deterministic scatter) and the nf = 3 sliced-ELL SpMV, both through the C ABI."""
@@ -307,6 +340,7 @@ def vector_problem_figures(args, hbm, fp64_peak, n=64):
                     "frac": phys / (spmv_ms * 1e-3) / 1e9 / hbm, "nnz_reduced": nnz, "n_free": plan.n_free,
                     "algorithmic_gbs": (nnz * 12 + rows * 16 + (rows + 1) * 4) / (spmv_ms * 1e-3) / 1e9}}
     plan.destroy()
+    out["newton"] = optional_section(vector_newton_figures, n)
     return out
 
 
@@ -484,7 +518,7 @@ def run_b200(args):
     asm_gbs = asm_elems * 290.0 / (np.mean(asm_ms) * 1e-3) / 1e9
     fp64_peak = backend.measure_fp64_peak()                        # TFLOP/s, measured here (not in MEASURED_PEAKS.json)
     asm_tflops = asm_elems * HEX8_POISSON_FLOP / (np.mean(asm_ms) * 1e-3) / 1e12
-    vector = optional_section(vector_problem_figures, args, hbm, fp64_peak) if (world == 1 and not args.no_vector) else None
+    vector = optional_section(vector_problem_figures, args, hbm, fp64_peak, args.vector_size) if (world == 1 and not args.no_vector) else None
 
     line = None if rank != 0 else {
         "metric": METRIC, "value": total_elems / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -573,6 +607,7 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=200.0, help="time bound of the whole --impl reference run")
     ap.add_argument("--ref-direct", action="store_true", help="--impl reference: also time spsolve on a 32^3 sample")
     ap.add_argument("--no-vector", action="store_true", help="skip the bounded 64^3 neo-Hooke figures")
+    ap.add_argument("--vector-size", type=int, default=64, help="elements per direction of the bounded neo-Hooke sample")
     ap.add_argument("--no-multigrid", action="store_true", help="skip the multigrid-preconditioned variant of the step")
     ap.add_argument("--mg-timeout-s", type=float, default=240.0, help="watchdog of the multi-GPU multigrid section")
     ap.add_argument("--rtol", type=float, default=1e-8)
