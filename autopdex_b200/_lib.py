@@ -70,6 +70,8 @@ SIGNATURES = {
     "apdx_get_coo_values": (C.c_int, [_P, _I64, _I64, _P]),
     "apdx_plan_newton_history": (C.c_int, [_P, _P, _I32, C.POINTER(_I32)]),
     "apdx_plan_set_coarse": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "apdx_plan_set_coarse_structured": (C.c_int, [_P, _P, _I32, _P, _P, _I64, _I64]),
+    "apdx_plan_get_transfer": (C.c_int, [_P, _I32, C.POINTER(_I64), C.POINTER(_I64), _P, _P, _P, _P]),
     "apdx_plan_set_multigrid": (C.c_int, [_P, _I32, _I32, _I32, _D, _D]),
     "apdx_spmv": (C.c_int, [_P, _P, _P]),
     "apdx_krylov": (C.c_int, [_P, C.POINTER(KrylovOpts), _P, _P, C.POINTER(_I32), C.POINTER(_D)]),

@@ -349,6 +349,32 @@ class Plan:
         _lib.check(_lib.load().apdx_plan_set_coarse(self.h, coarse.h, *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
         self.coarse = coarse
 
+    def set_coarse_structured(self, coarse, dims_f, dims_c, plane_off_f=0, plane_off_c=0):
+        """Link `coarse` below this plan with the transfer operators of a structured hierarchy built on the device
+        (coarse node (I, J, K) = fine node (2I, 2J, 2K)); dims_*: local node counts per direction, slowest first;
+        plane_off_*: global index of local plane 0 (slab partitions)."""
+        df = np.ascontiguousarray(dims_f, dtype=np.int64)
+        dc = np.ascontiguousarray(dims_c, dtype=np.int64)
+        if df.size != dc.size or df.size not in (2, 3):
+            raise ValueError("set_coarse_structured: dims_f / dims_c must have 2 or 3 entries")
+        _lib.check(_lib.load().apdx_plan_set_coarse_structured(self.h, coarse.h, int(df.size), df.ctypes.data_as(C.c_void_p),
+                                                               dc.ctypes.data_as(C.c_void_p), int(plane_off_f), int(plane_off_c)))
+        self.coarse = coarse
+
+    def get_transfer(self, which):
+        """(indptr, indices, data) of the linked P (which = 0) or R (which = 1) and the injection map, copied to the host."""
+        n_rows, nnz = C.c_int64(0), C.c_int64(0)
+        lib = _lib.load()
+        _lib.check(lib.apdx_plan_get_transfer(self.h, int(which), C.byref(n_rows), C.byref(nnz), None, None, None, None))
+        ptr = np.empty(n_rows.value + 1, dtype=np.int32)
+        idx = np.empty(max(nnz.value, 1), dtype=np.int32)
+        val = np.empty(max(nnz.value, 1), dtype=np.float64)
+        inj = np.empty(self.coarse.n_dofs, dtype=np.int32)
+        _lib.check(lib.apdx_plan_get_transfer(self.h, int(which), None, None, ptr.ctypes.data_as(C.c_void_p),
+                                              idx.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p),
+                                              inj.ctypes.data_as(C.c_void_p)))
+        return (ptr, idx[:nnz.value], val[:nnz.value]), inj
+
     def set_multigrid(self, pre=0, post=0, coarsest=0, ratio=0.0, coarsest_ratio=0.0):
         _lib.check(_lib.load().apdx_plan_set_multigrid(self.h, int(pre), int(post), int(coarsest), float(ratio),
                                                        float(coarsest_ratio)))

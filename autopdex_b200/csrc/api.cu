@@ -834,6 +834,27 @@ int apdx_plan_set_coarse(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_in
   return mg_link(fine, coarse, p_indptr_h, p_indices_h, p_data_h, r_indptr_h, r_indices_h, r_data_h, inject_h);
 }
 
+int apdx_plan_set_coarse_structured(apdx_plan *fine, apdx_plan *coarse, int32_t dim, const int64_t *dims_f,
+                                    const int64_t *dims_c, int64_t plane_off_f, int64_t plane_off_c) {
+  APDX_REQUIRE(fine && coarse && fine != coarse && dims_f && dims_c, APDX_ERR_INVALID, "NULL argument");
+  return mg_link_structured(fine, coarse, dim, dims_f, dims_c, plane_off_f, plane_off_c);
+}
+
+int apdx_plan_get_transfer(const apdx_plan *fine, int32_t which, int64_t *n_rows, int64_t *nnz, int32_t *indptr_h,
+                           int32_t *indices_h, double *data_h, int32_t *inject_h) {
+  APDX_REQUIRE(fine && fine->mg.coarse, APDX_ERR_STATE, "no coarse level linked to this plan");
+  const apdx::CsrDev &M = which ? fine->mg.R : fine->mg.P;
+  if (n_rows) *n_rows = M.n_rows;
+  if (nnz) *nnz = M.nnz;
+  APDX_CUDA(cudaStreamSynchronize(fine->stream));
+  if (indptr_h) APDX_CUDA(cudaMemcpy(indptr_h, M.ptr.p, (size_t)(M.n_rows + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (indices_h && M.nnz > 0) APDX_CUDA(cudaMemcpy(indices_h, M.idx.p, (size_t)M.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (data_h && M.nnz > 0) APDX_CUDA(cudaMemcpy(data_h, M.val.p, (size_t)M.nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  if (inject_h)
+    APDX_CUDA(cudaMemcpy(inject_h, fine->mg.inject.p, (size_t)fine->mg.coarse->n_dofs * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return APDX_OK;
+}
+
 int apdx_plan_set_multigrid(apdx_plan *pl, int32_t pre_degree, int32_t post_degree, int32_t coarsest_degree,
                             double smoother_ratio, double coarsest_ratio) {
   APDX_REQUIRE(pl, APDX_ERR_INVALID, "NULL argument");

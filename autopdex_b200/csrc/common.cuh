@@ -300,6 +300,7 @@ void drop_all_krylov_graphs();
 int build_pattern(apdx_plan *pl, const uint8_t *mask_h);
 int coo_export(apdx_plan *pl, int64_t offset, int64_t count, double *dst_d);
 int elem_map_export(const apdx_plan *pl, int64_t offset, int64_t count, int32_t *dst_d);
+int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s);
 // elements_fast.cu
 bool fast_kernel_applies(int dim, int nf, const apdx_set_desc &d);
 // elements.cu
@@ -317,6 +318,8 @@ int mg_level_setup(apdx_plan *pl);     // minv + lambda_max of this level's curr
 int mg_inject(apdx_plan *fine, const double *fine_dofs, double *coarse_dofs);
 int mg_link(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_ptr, const int32_t *p_idx, const double *p_val,
             const int32_t *r_ptr, const int32_t *r_idx, const double *r_val, const int64_t *inject_h);
+int mg_link_structured(apdx_plan *fine, apdx_plan *coarse, int dim, const int64_t *dims_f, const int64_t *dims_c,
+                       int64_t plane_off_f, int64_t plane_off_c);
 // sell.cu
 int sell_build(apdx_plan *pl);
 int sell_gather_reduce(apdx_plan *pl);

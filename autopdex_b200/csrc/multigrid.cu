@@ -376,6 +376,9 @@ static int upload_csr(CsrDev &M, int64_t n_rows, const int32_t *ptr_h, const int
   return APDX_OK;
 }
 
+// the coarse plan runs on the fine plan's stream from now on
+static int mg_link_finish(apdx_plan *fine, apdx_plan *coarse);
+
 int mg_link(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_ptr, const int32_t *p_idx, const double *p_val,
             const int32_t *r_ptr, const int32_t *r_idx, const double *r_val, const int64_t *inject_h) {
   APDX_REQUIRE(fine->nf == coarse->nf && fine->dim == coarse->dim, APDX_ERR_INVALID, "multigrid levels differ in dim / dofs per node");
@@ -391,6 +394,162 @@ int mg_link(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_ptr, const int3
   }
   APDX_CHECK(m.inject.alloc(coarse->n_dofs));
   APDX_CUDA(cudaMemcpy(m.inject.p, inj.data(), inj.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return mg_link_finish(fine, coarse);
+}
+
+// ---- transfer operators of a structured hierarchy, built on the device -------------------------------------------------
+// Coarse node (I, J, K) of a structured mesh coincides with fine node (2I, 2J, 2K); P is (multi-)linear interpolation
+// reduced to the free dofs of the two plans (their own free_id / free_list), R = P^T.  Both are written row by row in
+// ascending column order without a sort: a fine node has 1 or 2 coarse neighbours per direction (visited coarse index
+// first = lexicographic = ascending node id), a coarse node the fine nodes 2I + {-1, 0, 1} per direction.  Weights are
+// products of 1 and 1/2, so the result equals the host construction (multigrid.prolongation) to the last bit.
+// Slab partitions: df[0] / dc[0] are the LOCAL plane counts, off_f / off_c the global index of local plane 0; a neighbour
+// outside the local planes is dropped on both sides (it never is for an owned fine plane).
+struct XferGeom {
+  int32_t nf;
+  int64_t df[3], dc[3];   // node counts per direction, slowest first (2-D meshes: the last one is 1)
+  int64_t off_f, off_c;
+};
+// entries of row `r` of P (fine reduced dof): returns their number, columns ascending
+__device__ __forceinline__ int prolong_row(const XferGeom &g, const int32_t *__restrict__ free_list_f,
+                                           const int32_t *__restrict__ free_id_c, int64_t r, int32_t *col, double *w) {
+  const int64_t dof = free_list_f[r], node = dof / g.nf;
+  const int comp = (int)(dof - node * g.nf);
+  const int64_t a2 = node % g.df[2], a1 = (node / g.df[2]) % g.df[1], A0 = node / (g.df[2] * g.df[1]) + g.off_f;
+  const int o0 = (int)(A0 & 1), o1 = (int)(a1 & 1), o2 = (int)(a2 & 1);
+  const double wt = (o0 ? 0.5 : 1.0) * (o1 ? 0.5 : 1.0) * (o2 ? 0.5 : 1.0);
+  int n = 0;
+  for (int b0 = 0; b0 <= o0; ++b0) {
+    const int64_t c0 = (A0 >> 1) + b0 - g.off_c;
+    if (c0 < 0 || c0 >= g.dc[0]) continue;
+    for (int b1 = 0; b1 <= o1; ++b1)
+      for (int b2 = 0; b2 <= o2; ++b2) {
+        const int64_t cnode = (c0 * g.dc[1] + (a1 >> 1) + b1) * g.dc[2] + (a2 >> 1) + b2;
+        const int32_t q = free_id_c[cnode * g.nf + comp];
+        if (q < 0) continue;
+        col[n] = q; w[n] = wt; ++n;
+      }
+  }
+  return n;
+}
+// entries of row `r` of R = P^T (coarse reduced dof), columns ascending
+__device__ __forceinline__ int restrict_row(const XferGeom &g, const int32_t *__restrict__ free_list_c,
+                                            const int32_t *__restrict__ free_id_f, int64_t r, int32_t *col, double *w) {
+  const int64_t dof = free_list_c[r], node = dof / g.nf;
+  const int comp = (int)(dof - node * g.nf);
+  const int64_t i2 = node % g.dc[2], i1 = (node / g.dc[2]) % g.dc[1], I0 = node / (g.dc[2] * g.dc[1]) + g.off_c;
+  int n = 0;
+  for (int d0 = -1; d0 <= 1; ++d0) {
+    const int64_t a0 = 2 * I0 + d0 - g.off_f;
+    if (a0 < 0 || a0 >= g.df[0]) continue;
+    for (int d1 = -1; d1 <= 1; ++d1) {
+      const int64_t a1 = 2 * i1 + d1;
+      if (a1 < 0 || a1 >= g.df[1]) continue;
+      for (int d2 = -1; d2 <= 1; ++d2) {
+        const int64_t a2 = 2 * i2 + d2;
+        if (a2 < 0 || a2 >= g.df[2]) continue;
+        const int32_t q = free_id_f[((a0 * g.df[1] + a1) * g.df[2] + a2) * g.nf + comp];
+        if (q < 0) continue;
+        col[n] = q; w[n] = (d0 ? 0.5 : 1.0) * (d1 ? 0.5 : 1.0) * (d2 ? 0.5 : 1.0); ++n;
+      }
+    }
+  }
+  return n;
+}
+// RESTRICT = false: rows of P; true: rows of R.  FILL = false: cnt[r] = entries of row r (cnt[n_rows] = 0 for the scan);
+// FILL = true: the row's entries at ptr[r]
+template <bool RESTRICT, bool FILL>
+__global__ void __launch_bounds__(256) k_transfer_rows(XferGeom g, const int32_t *__restrict__ free_list_rows,
+                                                       const int32_t *__restrict__ free_id_cols, int64_t n_rows,
+                                                       int32_t *__restrict__ cnt, const int32_t *__restrict__ ptr,
+                                                       int32_t *__restrict__ idx, double *__restrict__ val) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  if (r == n_rows) { if (!FILL) cnt[r] = 0; return; }
+  int32_t col[RESTRICT ? 27 : 8];
+  double w[RESTRICT ? 27 : 8];
+  const int n = RESTRICT ? restrict_row(g, free_list_rows, free_id_cols, r, col, w)
+                         : prolong_row(g, free_list_rows, free_id_cols, r, col, w);
+  if (!FILL) { cnt[r] = n; return; }
+  const int32_t at = ptr[r];
+  for (int k = 0; k < n; ++k) { idx[at + k] = col[k]; val[at + k] = w[k]; }
+}
+// inject[coarse full dof] = fine full dof of the coinciding node; a coarse ghost plane whose fine plane lies outside the
+// local planes is pointed at the nearest local one (the caller exchanges those values: multigrid.fine_node_ids_slab)
+__global__ void k_inject_map(XferGeom g, int64_t n_dofs_c, int32_t *__restrict__ inject) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_dofs_c) return;
+  const int64_t node = i / g.nf, comp = i - node * g.nf;
+  const int64_t i2 = node % g.dc[2], i1 = (node / g.dc[2]) % g.dc[1], I0 = node / (g.dc[2] * g.dc[1]) + g.off_c;
+  int64_t a0 = 2 * I0 - g.off_f;
+  a0 = a0 < 0 ? 0 : (a0 > g.df[0] - 1 ? g.df[0] - 1 : a0);
+  inject[i] = (int32_t)((((a0 * g.df[1]) + 2 * i1) * g.df[2] + 2 * i2) * g.nf + comp);
+}
+
+template <bool RESTRICT>
+static int build_transfer(CsrDev &M, const XferGeom &g, const apdx_plan *rows, const apdx_plan *cols, cudaStream_t s) {
+  const int64_t n = rows->n_free;
+  const unsigned grid = (unsigned)((n + 1 + 255) / 256);
+  DevBuf<int32_t> cnt;
+  APDX_CHECK(cnt.alloc(n + 1));
+  k_transfer_rows<RESTRICT, false><<<grid, 256, 0, s>>>(g, rows->free_list.p, cols->free_id.p, n, cnt.p, nullptr, nullptr, nullptr);
+  APDX_CUDA(cudaGetLastError());
+  M.n_rows = n;
+  APDX_CHECK(M.ptr.alloc(n + 1));
+  APDX_CHECK(scan_exclusive_i32(cnt.p, M.ptr.p, n + 1, s));   // synchronises the stream
+  cnt.release();
+  int32_t nnz = 0;
+  APDX_CUDA(cudaMemcpy(&nnz, M.ptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  APDX_REQUIRE(nnz >= 0, APDX_ERR_UNSUPPORTED, "transfer operator exceeds the 32-bit index range");
+  M.nnz = nnz;
+  APDX_CHECK(M.idx.alloc(nnz > 0 ? nnz : 1));
+  APDX_CHECK(M.val.alloc(nnz > 0 ? nnz : 1));
+  k_transfer_rows<RESTRICT, true><<<grid, 256, 0, s>>>(g, rows->free_list.p, cols->free_id.p, n, nullptr, M.ptr.p, M.idx.p, M.val.p);
+  APDX_CUDA(cudaGetLastError());
+  return APDX_OK;
+}
+
+int mg_link_structured(apdx_plan *fine, apdx_plan *coarse, int dim, const int64_t *dims_f, const int64_t *dims_c,
+                       int64_t plane_off_f, int64_t plane_off_c) {
+  APDX_REQUIRE(fine->nf == coarse->nf && fine->dim == coarse->dim, APDX_ERR_INVALID, "multigrid levels differ in dim / dofs per node");
+  APDX_REQUIRE(!coarse->mg.stream_borrowed, APDX_ERR_STATE, "this plan already is the coarse level of another plan");
+  APDX_REQUIRE(dim == 2 || dim == 3, APDX_ERR_INVALID, "structured transfer operators: dim = %d (2 or 3)", dim);
+  XferGeom g{};
+  g.nf = fine->nf;
+  g.off_f = plane_off_f; g.off_c = plane_off_c;
+  int64_t nf_nodes = 1, nc_nodes = 1;
+  for (int d = 0; d < 3; ++d) {
+    g.df[d] = d < dim ? dims_f[d] : 1;
+    g.dc[d] = d < dim ? dims_c[d] : 1;
+    APDX_REQUIRE(g.df[d] >= 1 && g.dc[d] >= 1, APDX_ERR_INVALID, "structured transfer operators: empty direction %d", d);
+    // directions that are not split between ranks are halved exactly; the slowest one may carry ghost planes
+    if (d > 0) APDX_REQUIRE(g.df[d] == 2 * (g.dc[d] - 1) + 1, APDX_ERR_INVALID,
+                            "structured transfer operators: %lld fine and %lld coarse nodes in direction %d", (long long)g.df[d],
+                            (long long)g.dc[d], d);
+    nf_nodes *= g.df[d]; nc_nodes *= g.dc[d];
+  }
+  APDX_REQUIRE(nf_nodes == fine->n_nodes && nc_nodes == coarse->n_nodes, APDX_ERR_INVALID,
+               "structured transfer operators: the node counts (%lld, %lld) do not match the plans (%lld, %lld)", (long long)nf_nodes,
+               (long long)nc_nodes, (long long)fine->n_nodes, (long long)coarse->n_nodes);
+  APDX_REQUIRE(plane_off_f >= 0 && plane_off_c >= 0 && 2 * plane_off_c + 1 >= plane_off_f &&
+                   2 * (plane_off_c + g.dc[0] - 1) <= plane_off_f + g.df[0], APDX_ERR_INVALID,
+               "structured transfer operators: coarse planes [%lld, %lld) do not lie over the fine planes [%lld, %lld)",
+               (long long)plane_off_c, (long long)(plane_off_c + g.dc[0]), (long long)plane_off_f, (long long)(plane_off_f + g.df[0]));
+  MgLevel &m = fine->mg;
+  cudaStream_t s = fine->stream;
+  APDX_CHECK(build_transfer<false>(m.P, g, fine, coarse, s));
+  APDX_CHECK(build_transfer<true>(m.R, g, coarse, fine, s));
+  APDX_REQUIRE(m.P.nnz == m.R.nnz, APDX_ERR_STATE, "P and R = P^T disagree on the number of entries (%lld, %lld)",
+               (long long)m.P.nnz, (long long)m.R.nnz);
+  APDX_CHECK(m.inject.alloc(coarse->n_dofs));
+  k_inject_map<<<(unsigned)((coarse->n_dofs + 255) / 256), 256, 0, s>>>(g, coarse->n_dofs, m.inject.p);
+  APDX_CUDA(cudaGetLastError());
+  APDX_CUDA(cudaStreamSynchronize(s));
+  return mg_link_finish(fine, coarse);
+}
+
+static int mg_link_finish(apdx_plan *fine, apdx_plan *coarse) {
+  MgLevel &m = fine->mg;
   APDX_CHECK(coarse->mg.dofs.alloc(coarse->n_dofs));
   // the coarse plan runs on the fine plan's stream from now on
   if (coarse->own_stream) {

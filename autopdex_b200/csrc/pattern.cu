@@ -203,6 +203,9 @@ static int exclusive_scan(const int32_t *in, T *out, int64_t n, cudaStream_t s) 
   tmp.release();
   return APDX_OK;
 }
+// out[i] = in[0] + ... + in[i-1] for i < n (used by multigrid.cu for the row pointers of its transfer operators);
+// returns after the stream has finished
+int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) { return exclusive_scan<int32_t>(in, out, n, s); }
 static int inclusive_scan(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
   size_t tb = 0;
   APDX_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, in, out, n, s));

@@ -215,6 +215,18 @@ int apdx_tangent_solve(apdx_plan *plan, const apdx_krylov_opts *opts, const doub
 int apdx_plan_set_coarse(apdx_plan *fine, apdx_plan *coarse, const int32_t *p_indptr_h, const int32_t *p_indices_h,
                          const double *p_data_h, const int32_t *r_indptr_h, const int32_t *r_indices_h,
                          const double *r_data_h, const int64_t *inject_h);
+/* The same link for STRUCTURED hierarchies (coarse node (I, J, K) = fine node (2I, 2J, 2K): the meshes of
+ * mesher.structured_mesh 'quad' / 'brick'), with P, R and inject built on the device from the two plans' own Dirichlet
+ * maps -- no host construction, no upload (256^3: 22 s of NumPy + 3.4 GB of transfers otherwise).  dims_f / dims_c [dim]:
+ * node counts per direction of the two LOCAL meshes, slowest-varying direction first; plane_off_f / plane_off_c: global
+ * index of local plane 0 along that direction (slab partitions; 0 on one GPU).  Every other direction must satisfy
+ * dims_f = 2 (dims_c - 1) + 1.  The operators equal those of the host construction bit for bit (tests).                */
+int apdx_plan_set_coarse_structured(apdx_plan *fine, apdx_plan *coarse, int32_t dim, const int64_t *dims_f,
+                                    const int64_t *dims_c, int64_t plane_off_f, int64_t plane_off_c);
+/* test / inspection hook: copies of the linked transfer operators (which = 0: P, 1: R) into host arrays; pass NULL
+ * pointers to query the sizes only (n_rows, nnz).                                                                       */
+int apdx_plan_get_transfer(const apdx_plan *fine, int32_t which, int64_t *n_rows, int64_t *nnz, int32_t *indptr_h,
+                           int32_t *indices_h, double *data_h, int32_t *inject_h);
 int apdx_plan_set_multigrid(apdx_plan *plan, int32_t pre_degree, int32_t post_degree, int32_t coarsest_degree,
                             double smoother_ratio, double coarsest_ratio);
 /* timings (ms, CUDA events) and counters of the last apdx_newton / apdx_linear_step:

@@ -17,8 +17,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "autopdex_b200", "csrc")
-OUT_DIR = os.path.join(HERE, "build")
-LIB = os.path.join(OUT_DIR, "libapdx_b200_emu.so")
+# EMU_UBSAN=1: a second build with -fsanitize=undefined (alignment of the vector loads -- a misaligned double2 / int4
+# access is a fault on the device and silently fine on x86 --, static array bounds, shifts, signed overflow, division by
+# zero, float -> int conversions out of range); run with UBSAN_OPTIONS=halt_on_error=1:print_stacktrace=1
+UBSAN = os.environ.get("EMU_UBSAN", "0") not in ("", "0")
+OUT_DIR = os.path.join(HERE, "build_ubsan" if UBSAN else "build")
+LIB = os.path.join(OUT_DIR, "libapdx_b200_emu_ubsan.so" if UBSAN else "libapdx_b200_emu.so")
+SAN_FLAGS = ["-fsanitize=undefined,float-cast-overflow", "-fno-sanitize=vptr"] if UBSAN else []
 UNITS = ["api", "pattern", "elements", "elements_fast", "sell", "krylov", "multigrid", "dist"]
 HEADERS = ["common.cuh", "krylov.cuh", "elements.cuh"]
 
@@ -63,7 +68,7 @@ def build(force=False, verbose=False):
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-omit-frame-pointer", "-Wall", "-Wno-unknown-pragmas",
              "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-Wno-sign-compare",
              "-I" + os.path.join(HERE, "include"), "-I" + OUT_DIR, "-I" + os.path.join(ROOT, "include"),
-             "-include", "cuda_runtime.h"]
+             "-include", "cuda_runtime.h"] + SAN_FLAGS
     objs = []
     jobs = []
     n_launch = 0
@@ -92,7 +97,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("emulated build failed")
     if jobs or not os.path.exists(LIB):
-        subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + ["-ldl"])
+        subprocess.check_call(["g++", "-shared", "-o", LIB] + SAN_FLAGS + objs + ["-ldl"])
     # stand-in for libnccl.so.2 (the product dlopen()s NCCL; multi-rank emulated runs name this file in APDX_NCCL_LIB)
     nccl_src, nccl_lib = os.path.join(HERE, "fake_nccl.cpp"), os.path.join(OUT_DIR, "libfakenccl.so")
     if force or newer(nccl_src, nccl_lib):

@@ -68,6 +68,9 @@ static const std::function<void()> *g_body = nullptr;
 static const char *g_kernel = "(none)";
 static uint64_t g_slots[MAX_THREADS / 32][32];
 static std::vector<char> g_dyn_smem;
+static char *g_dyn_guarded = nullptr;   // EMU_GUARD != 0: the dynamic shared memory of a block ends right in front of an inaccessible page
+static char *g_dyn_ptr = nullptr;
+static constexpr size_t DYN_REGION = 256 * 1024;
 static long long g_clock = 0;
 static long long g_strict_violations = 0;
 
@@ -114,7 +117,7 @@ void sync_block() { yield_to_scheduler(WAIT_BLOCK, 0); }
 void sync_warp(unsigned mask) { yield_to_scheduler(WAIT_WARP, mask); }
 uint64_t *warp_slots() { return g_slots[g_cur >> 5]; }
 int lane_id() { return g_cur & 31; }
-void *dyn_smem() { return g_dyn_smem.data(); }
+void *dyn_smem() { return g_dyn_ptr; }
 long long clock() {   // ~2 "cycles" per nanosecond of real time: device-side time-outs (peer waits) keep their meaning
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -242,7 +245,23 @@ static void run_grid(const Cfg &c, const char *name, const std::function<void()>
   g_nthreads = (int)nthreads;
   bdim = c.block;
   gdim = c.grid;
-  g_dyn_smem.assign(c.smem + 16, (char)0xFF);
+  {
+    const char *gm = getenv("EMU_GUARD");
+    if (gm && atoi(gm) != 0) {   // an over-run of the dynamic shared memory is an out-of-range shared address on the device
+      if (!g_dyn_guarded) {
+        char *m = (char *)mmap(nullptr, DYN_REGION + 4096, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m == MAP_FAILED) { g_last_error = cudaErrorMemoryAllocation; return; }
+        mprotect(m + DYN_REGION, 4096, PROT_NONE);
+        g_dyn_guarded = m;
+      }
+      const size_t payload = (c.smem + 15) & ~(size_t)15;
+      g_dyn_ptr = g_dyn_guarded + DYN_REGION - payload;
+      memset(g_dyn_ptr, 0xFF, payload);
+    } else {
+      g_dyn_smem.assign(c.smem + 16, (char)0xFF);
+      g_dyn_ptr = g_dyn_smem.data();
+    }
+  }
   // EMU_ORDER=reverse|shuffle: blocks (and the threads inside a block) run in another order -- nothing in the product may
   // depend on the order in which the hardware happens to schedule them (a poor man's racecheck for order dependence)
   const size_t nblocks = (size_t)c.grid.x * c.grid.y * c.grid.z;

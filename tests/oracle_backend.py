@@ -165,6 +165,23 @@ class FakePlan:
         assert np.asarray(inject).max() < self.n_dofs
         self.coarse, self.transfer = coarse, (P, R, np.asarray(inject))
 
+    def set_coarse_structured(self, coarse, dims_f, dims_c, plane_off_f=0, plane_off_c=0):
+        """Stand-in of apdx_plan_set_coarse_structured: the host statement of the construction (multigrid.prolongation)."""
+        from autopdex_b200 import multigrid
+        dims_f, dims_c = [int(v) for v in dims_f], [int(v) for v in dims_c]
+        assert int(np.prod(dims_f)) == self.n_nodes and int(np.prod(dims_c)) == coarse.n_nodes
+        shape_f = tuple(2 * (n - 1) for n in dims_c)           # global element counts; the slowest direction is never read
+        free_f = ~np.asarray(self.mask, dtype=bool).reshape(self.n_nodes, -1)
+        free_c = ~np.asarray(coarse.mask, dtype=bool).reshape(coarse.n_nodes, -1)
+        nf = free_f.shape[1]
+        slab = ((plane_off_f, plane_off_f + dims_f[0]), (plane_off_c, plane_off_c + dims_c[0]))
+        P, R = multigrid.prolongation(shape_f, nf, free_f, free_c, slab)
+        i0 = np.clip(2 * (np.arange(dims_c[0]) + plane_off_c) - plane_off_f, 0, dims_f[0] - 1)
+        grids = np.meshgrid(i0, *[np.arange(0, n, 2) for n in dims_f[1:]], indexing="ij")
+        strides = np.cumprod([1] + dims_f[::-1])[::-1][1:]
+        nodes = sum(g.ravel().astype(np.int64) * int(st) for g, st in zip(grids, strides))
+        self.set_coarse(coarse, P, R, (nodes[:, None] * nf + np.arange(nf)).ravel())
+
     def set_multigrid(self, pre=0, post=0, coarsest=0, ratio=0.0, coarsest_ratio=0.0):
         self.mg_options = (pre, post, coarsest, ratio, coarsest_ratio)
 
