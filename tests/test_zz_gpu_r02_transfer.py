@@ -68,8 +68,8 @@ def test_device_transfer_operators_equal_the_host_construction(dims_f, nf, slab,
         (p_ptr, p_idx, p_val), inj = fine.get_transfer(0)
         (r_ptr, r_idx, r_val), _ = fine.get_transfer(1)
     finally:
+        coarse.destroy()             # the order of solver._State.destroy: coarse levels first
         fine.destroy()
-        coarse.destroy()
     # host statement; shape_fine = GLOBAL element counts (the slowest direction is only read through the slab planes)
     shape_fine = tuple(2 * (n - 1) for n in dims_c) if slab is not None else tuple(n - 1 for n in dims_f)
     hslab = None if slab is None else ((off_f, off_f + dims_f[0]), (off_c, off_c + dims_c[0]))
@@ -97,5 +97,5 @@ def test_structured_link_rejects_mismatched_meshes():
         with pytest.raises(Exception, match="do not lie over"):
             fine.set_coarse_structured(coarse, [9, 9, 9], [5, 5, 5], 0, 4)
     finally:
-        for pl in (fine, coarse, other):
+        for pl in (coarse, other, fine):
             pl.destroy()
