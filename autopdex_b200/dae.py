@@ -4,17 +4,21 @@ The reference's manager (dae.py:1734-2240) advances dict dofs with per-field tim
 ('user residual' domains built by models.mixed_reference_domain_residual_time) every stage assembles a sparse tangent
 (`_assemble_sparse_tangent_domain`, dae.py:1826-1876) and hands it to the linear-solver backend inside a Newton
 iteration (`_multi_stage_step`, dae.py:1878-2085; backend dispatch :1923-1942).  This module is that slot for the
-b200 backend, for the integrators whose single implicit stage has the affine form
+b200 backend, for the integrators whose implicit stages are solved one after the other and have the affine form
 
-    q_t = a q + b                      (BackwardEuler dae.py:288-318, BackwardDiffFormula dae.py:537-587)
+    value = x + d,   q_t = a value + b        (x: the unknown of the stage, dae.py `_rule` of the integrator)
 
-so that a tagged transient integrand (models.heat_conduction_time: c theta_t dtheta + k grad theta . grad dtheta -
-f dtheta) maps onto the device's steady + capacity kernels with `time increment` = -1/a and `dofs n` = -b/a: the
-capacity kernel computes -c/dt_eff N_i N_j (theta - theta_n,eff).  Assembly, the Newton loop (dae.newton_solver
-semantics: residual tolerance `atol`, at most `max_iter` updates) and the Krylov solve run on the device; the plan
-(pattern, index maps, multigrid hierarchy if asked for) is built once and reused by every step.
-Multi-stage / explicit integrators, step-size controllers other than the constant one and user-written integrands
-are rejected (ValueError), never routed to a host path.
+-- BackwardEuler (dae.py:288-318), BackwardDiffFormula (:537-587), AdamsMoulton (:420-481; history of derivatives) with
+d = 0, and DiagonallyImplicitRungeKutta (:707-766; the reference solves for x_i = q_n + dt a_ii K_i and evaluates the
+residual at q_n + dt sum_j a_ij K_j, i.e. d = dt sum_{j<i} a_ij K_j) -- so that a tagged transient integrand
+(models.heat_conduction_time: c theta_t dtheta + k grad theta . grad dtheta - f dtheta) maps onto the device's steady +
+capacity kernels with `time increment` = -1/a and `dofs n` = -b/a: the capacity kernel computes
+-c/dt_eff N_i N_j (theta - theta_n,eff).  Assembly, the Newton loop (dae.newton_solver semantics: residual tolerance
+`atol`, at most `max_iter` updates) and the Krylov solve run on the device; the plan (pattern, index maps, multigrid
+hierarchy if asked for) is built once and reused by every stage of every step.
+Coupled-stage (GaussLegendreRungeKutta) / explicit / embedded (Kvaerno, DormandPrince) integrators, Newmark (second
+derivatives), step-size controllers other than the constant one and user-written integrands are rejected (ValueError),
+never routed to a host path.
 """
 from dataclasses import dataclass, field as _field
 from typing import Any
@@ -24,13 +28,27 @@ import numpy as np
 from . import solver as _solver
 
 
-# ---- time integrators (one implicit stage, affine in the new value) ---------------------------------------------------
+# ---- time integrators (implicit stages solved one after the other, each affine in its unknown) ---------------------------
 class TimeIntegrator:
-    num_stages, num_derivs = 1, 1
+    """Mirror of dae.TimeIntegrator (dae.py:208-283) for the b200 backend.  q_n [num_steps, ...]: values of the last steps
+    (q_n[0] = time n), q_t_n [num_steps, 1, ...]: their first derivatives, q_stages [num_stages, ...]: the stage unknowns
+    (stages not solved yet hold q_n[0], dae.py:1887)."""
+    num_stages, num_steps, num_derivs = 1, 1, 1
+    stage_positions = (1.0,)
 
     def rule_coefficients(self, dt):
-        """(a, weights): q_t = a q + sum_j weights[j] q_n[j]."""
+        """One-stage rules without a derivative history: (a, weights) with q_t = a q + sum_j weights[j] q_n[j]."""
         raise NotImplementedError
+
+    def stage_rule(self, s, dt, q_stages, q_n, q_t_n):
+        """(a, b, d) of stage s: the residual is evaluated at value = x + d and q_t = a value + b (x = the stage unknown)."""
+        a, w = self.rule_coefficients(dt)
+        return a, np.einsum("j,j...->...", w, q_n), 0.0
+
+    def update(self, q_stages, q_n, q_t_n, dt):
+        """(q_{n+1}, q_t_{n+1}) from the solved stages (the integrators' `_update`)."""
+        a, b, _ = self.stage_rule(0, dt, q_stages, q_n, q_t_n)
+        return q_stages[0], a * q_stages[0] + b
 
 
 class BackwardEuler(TimeIntegrator):
@@ -56,6 +74,69 @@ class BackwardDiffFormula(TimeIntegrator):
     def rule_coefficients(self, dt):
         c = np.asarray(self._COEFFS[self.num_steps], dtype=np.float64)
         return c[0] / dt, c[1:] / dt
+
+
+class AdamsMoulton(TimeIntegrator):
+    """dae.AdamsMoulton (dae.py:420-481): q_t = ((q - q_n[0]) / dt - sum_{j>=1} c_j q_t_n[j-1]) / c_0 with the
+    Adams-Moulton coefficients of :450-466 (num_steps 1 = trapezoidal rule).  The derivative history starts at zero
+    (dae.py:1805), as in the reference."""
+    name = "adams_moulton"
+    _COEFFS = {1: [1 / 2, 1 / 2], 2: [5 / 12, 8 / 12, -1 / 12], 3: [9 / 24, 19 / 24, -5 / 24, 1 / 24],
+               4: [251 / 720, 646 / 720, -264 / 720, 106 / 720, -19 / 720],
+               5: [475 / 1440, 1427 / 1440, -798 / 1440, 482 / 1440, -173 / 1440, 27 / 1440],
+               6: [19087 / 60480, 65112 / 60480, -46461 / 60480, 37504 / 60480, -20211 / 60480, 6312 / 60480, -863 / 60480]}
+
+    def __init__(self, num_steps):
+        if num_steps not in self._COEFFS:
+            raise ValueError("num_steps=%r is not supported. Supported: %s" % (num_steps, list(self._COEFFS)))
+        self.num_steps, self.order = num_steps, num_steps + 1
+
+    def stage_rule(self, s, dt, q_stages, q_n, q_t_n):
+        c = np.asarray(self._COEFFS[self.num_steps], dtype=np.float64)
+        a = 1.0 / (dt * c[0])
+        b = -a * q_n[0] - np.einsum("j,j...->...", c[1:], q_t_n[:, 0]) / c[0]
+        return a, b, 0.0
+
+
+class DiagonallyImplicitRungeKutta(TimeIntegrator):
+    """dae.DiagonallyImplicitRungeKutta (dae.py:707-766; tableaus of Butcher 2008: implicit midpoint, Crouzeix's 3rd- and
+    4th-order methods).  As in the reference (invert_butcher_with_order, dae.py:147-205: the Butcher matrix is inverted
+    block by block = stage by stage) the unknown of stage i is x_i = q_n + dt a_ii K_i, the residual is evaluated at the
+    stage value q_n + dt sum_{j<=i} a_ij K_j = x_i + d and K_i = (x_i - q_n) / (dt a_ii);
+    q_{n+1} = q_n + dt sum_i b_i K_i, q_t_{n+1} = sum_i b_i K_i."""
+    name, num_steps = "diagonally_implicit_runge_kutta", 1
+
+    def __init__(self, num_stages):
+        if num_stages == 1:
+            c, b, A, self.order = [1 / 2], [1.0], [[1 / 2]], 2
+        elif num_stages == 2:
+            r = np.sqrt(3.0)
+            c, b, A, self.order = [1 / 2 + r / 6, 1 / 2 - r / 6], [1 / 2, 1 / 2], [[1 / 2 + r / 6, 0.0], [-r / 3, 1 / 2 + r / 6]], 3
+        elif num_stages == 3:
+            al = 2 * np.cos(np.pi / 18) / np.sqrt(3.0)
+            c = [(1 + al) / 2, 1 / 2, (1 - al) / 2]
+            b = [1 / (6 * al ** 2), 1 - 1 / (3 * al ** 2), 1 / (6 * al ** 2)]
+            A = [[(1 + al) / 2, 0.0, 0.0], [-al / 2, (1 + al) / 2, 0.0], [1 + al, -(1 + 2 * al), (1 + al) / 2]]
+            self.order = 4
+        else:
+            raise ValueError("num_stages not supported for DiagonallyImplicitRungeKutta. Supported: 1, 2, 3")
+        self.num_stages = num_stages
+        self.stage_positions = tuple(float(v) for v in c)
+        self.butcher_A, self.butcher_b, self.butcher_c = np.asarray(A, dtype=np.float64), np.asarray(b, dtype=np.float64), np.asarray(c)
+
+    def _slopes(self, upto, dt, q_stages, q_n):
+        return [(q_stages[j] - q_n[0]) / (dt * self.butcher_A[j, j]) for j in range(upto)]
+
+    def stage_rule(self, s, dt, q_stages, q_n, q_t_n):
+        K = self._slopes(s, dt, q_stages, q_n)
+        d = dt * sum((self.butcher_A[s, j] * K[j] for j in range(s)), np.zeros_like(q_n[0]))
+        a = 1.0 / (dt * self.butcher_A[s, s])
+        return a, -a * (d + q_n[0]), d
+
+    def update(self, q_stages, q_n, q_t_n, dt):
+        K = self._slopes(self.num_stages, dt, q_stages, q_n)
+        q_t = sum((self.butcher_b[j] * K[j] for j in range(self.num_stages)), np.zeros_like(q_n[0]))
+        return q_n[0] + dt * q_t, q_t
 
 
 class ConstantStepSizeController:
@@ -108,7 +189,8 @@ class TimeSteppingManager:
         for key, integ in self.integrators.items():
             if not isinstance(integ, TimeIntegrator):
                 raise ValueError("b200 backend: time integrator %r of field %r is not supported (BackwardEuler, "
-                                 "BackwardDiffFormula: one implicit stage, first derivative)" % (integ, key))
+                                 "BackwardDiffFormula, AdamsMoulton, DiagonallyImplicitRungeKutta: implicit stages solved "
+                                 "one after the other, first derivative)" % (integ, key))
         self.static_settings = dict(static_settings)
         self.static_settings.setdefault("solver type", "newton")
         if "solution structure" not in self.static_settings:
@@ -136,6 +218,9 @@ class TimeSteppingManager:
             raise ValueError("b200 backend: dofs must be a dict with the field %r of the time integrator" % key)
         q = np.array(dofs[key], dtype=np.float64)
         q_n = np.repeat(q[None, ...], integ.num_steps, axis=0)            # dae.py:1804
+        q_t_n = np.zeros((integ.num_steps, 1) + q.shape)                  # dae.py:1805
+        dd = settings.get("dirichlet dofs")
+        mask = None if dd is None else np.asarray(dd[key] if isinstance(dd, dict) else dd, dtype=bool).reshape(q.shape)
         t, t_n, dt = 0.0, 0.0, float(dt0)
         if self.save_policy is not None:
             self.save_policy.save(t, {key: q})
@@ -144,26 +229,42 @@ class TimeSteppingManager:
         while steps < num_time_steps and t_n < t_max * (1 - 1e-14):
             t = min(t_n + dt, t_max)
             dt_step = t - t_n
-            settings = self.pre_step_updates(t, settings)
-            a, w = integ.rule_coefficients(dt_step)
-            b = np.einsum("j,j...->...", w, q_n)
-            step_settings = dict(settings)
-            step_settings["time increment"] = -1.0 / a             # capacity kernel: -c/dt_eff (theta - theta_n,eff)
-            step_settings["dofs n"] = -b / a
-            sol, (its, res, div) = _solver.solver({key: q_n[0]}, step_settings, self.static_settings, newton_tol=self.atol,
-                                                  maxiter=self.max_iter, tol=self.tol, krylov_maxiter=self.krylov_maxiter)
+            settings = self.pre_step_updates(t, settings)                # dae.py:2156
+            q_stages = np.repeat(q_n[0][None, ...], integ.num_stages, axis=0)    # dae.py:1887
+            its, converged, res = 0, True, 0.0
+            for s in range(integ.num_stages):                            # stage blocks in order (dae.py:1897-2069)
+                settings = self.pre_step_updates(t_n + dt_step * integ.stage_positions[s], settings)
+                a, b, d = integ.stage_rule(s, dt_step, q_stages, q_n, q_t_n)
+                step_settings = dict(settings)
+                step_settings["time increment"] = -1.0 / a         # capacity kernel: -c/dt_eff (theta - theta_n,eff)
+                step_settings["dofs n"] = -b / a
+                shifted = isinstance(d, np.ndarray)
+                if shifted and mask is not None and "dirichlet conditions" in settings:
+                    # the reference constrains the stage UNKNOWN x; the device solves for the stage VALUE x + d
+                    dc = settings["dirichlet conditions"]
+                    vals = np.asarray(dc[key] if isinstance(dc, dict) else dc, dtype=np.float64).reshape(q.shape) + d
+                    step_settings["dirichlet conditions"] = {key: vals} if isinstance(dc, dict) else vals
+                guess = q_n[0] + d if shifted else q_n[0]            # initial guess: x = q (dae.py:1989)
+                sol, (it_s, res, div) = _solver.solver({key: guess}, step_settings, self.static_settings, newton_tol=self.atol,
+                                                       maxiter=self.max_iter, tol=self.tol, krylov_maxiter=self.krylov_maxiter)
+                value = np.asarray(sol[key], dtype=np.float64)
+                q_stages[s] = value - d if shifted else value
+                its = max(its, int(it_s))                          # dae.py:2051
+                converged = converged and (not div) and res < self.atol
             steps += 1
-            converged = (not div) and res < self.atol
-            newton_its.append(int(its))
+            newton_its.append(its)
             if self.verbose >= 1:
                 print("Time %.6e: Newton iterations %d, residual norm %.3e, converged %s" % (t, its, res, converged))
             if not converged:                                       # constant controller: interrupt (dae.py:1486-1497)
                 rejected += 1
                 break
             accepted += 1
-            q = np.asarray(sol[key], dtype=np.float64)
-            q_n = np.roll(q_n, 1, axis=0)
+            q, q_t = integ.update(q_stages, q_n, q_t_n, dt_step)
+            q = np.asarray(q, dtype=np.float64)
+            q_n = np.roll(q_n, 1, axis=0)                           # dae.py:2178-2182
             q_n[0] = q
+            q_t_n = np.roll(q_t_n, 1, axis=0)
+            q_t_n[0, 0] = q_t
             t_n = t
             if self.post_step_updates is not None:
                 settings = self.post_step_updates(lambda tt: {key: q}, t, settings)
@@ -172,5 +273,6 @@ class TimeSteppingManager:
         return TimeSteppingManagerState({key: q}, settings, self.save_policy, steps, accepted, rejected, newton_its)
 
 
-__all__ = ["TimeSteppingManager", "TimeSteppingManagerState", "BackwardEuler", "BackwardDiffFormula",
+__all__ = ["TimeSteppingManager", "TimeSteppingManagerState", "BackwardEuler", "BackwardDiffFormula", "AdamsMoulton",
+           "DiagonallyImplicitRungeKutta",
            "ConstantStepSizeController", "SaveAllPolicy"]

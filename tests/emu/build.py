@@ -21,9 +21,15 @@ CSRC = os.path.join(ROOT, "autopdex_b200", "csrc")
 # access is a fault on the device and silently fine on x86 --, static array bounds, shifts, signed overflow, division by
 # zero, float -> int conversions out of range); run with UBSAN_OPTIONS=halt_on_error=1:print_stacktrace=1
 UBSAN = os.environ.get("EMU_UBSAN", "0") not in ("", "0")
-OUT_DIR = os.path.join(HERE, "build_ubsan" if UBSAN else "build")
-LIB = os.path.join(OUT_DIR, "libapdx_b200_emu_ubsan.so" if UBSAN else "libapdx_b200_emu.so")
-SAN_FLAGS = ["-fsanitize=undefined,float-cast-overflow", "-fno-sanitize=vptr"] if UBSAN else []
+# EMU_ASAN=1: a third build with AddressSanitizer on heap and globals only (--param asan-stack=0: the fibers switch stacks
+# behind the sanitizer's back) -- host-side containers of api.cu / dist.cu / sell.cu, use-after-free across plan
+# destruction, static __shared__ arrays (globals of the stand-in); run with
+#   LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:abort_on_error=1
+ASAN = os.environ.get("EMU_ASAN", "0") not in ("", "0")
+OUT_DIR = os.path.join(HERE, "build_ubsan" if UBSAN else ("build_asan" if ASAN else "build"))
+LIB = os.path.join(OUT_DIR, "libapdx_b200_emu_ubsan.so" if UBSAN else ("libapdx_b200_emu_asan.so" if ASAN else "libapdx_b200_emu.so"))
+SAN_FLAGS = (["-fsanitize=undefined,float-cast-overflow", "-fno-sanitize=vptr"] if UBSAN else
+             (["-fsanitize=address", "--param", "asan-stack=0"] if ASAN else []))
 UNITS = ["api", "pattern", "elements", "elements_fast", "sell", "krylov", "multigrid", "dist"]
 HEADERS = ["common.cuh", "krylov.cuh", "elements.cuh"]
 

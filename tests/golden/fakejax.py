@@ -436,6 +436,9 @@ def install():
     jax.tree = tree
     tree_util = types.ModuleType("jax.tree_util")
     tree_util.tree_map = tree_map
+    # autopdex.dae registers its state dataclasses / the manager as pytrees at import time: bookkeeping of the tracer only
+    tree_util.register_dataclass = lambda cls=None, **kw: (cls if cls is not None else (lambda c: c))
+    tree_util.register_pytree_node = lambda *a, **k: None
     jax.tree_util = tree_util
     exp = types.ModuleType("jax.experimental")
     sparse = types.ModuleType("jax.experimental.sparse")

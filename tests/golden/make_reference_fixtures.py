@@ -404,7 +404,34 @@ def case_newton_semantics(out):
     out["newton_maxiter"] = np.array(run([1.0] * 10, maxiter=3))
 
 
-CASES = {"tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
+def case_dae_rules(out):
+    """autopdex.dae time integrators (dae.py:288-318 BackwardEuler, :420-481 AdamsMoulton, :537-587 BackwardDiffFormula,
+    :707-766 DiagonallyImplicitRungeKutta): the discrete value / first derivative of every stage (`_rule`) and the
+    end-of-step update (`_update`) evaluated by the reference's own classes on random stage values and histories."""
+    from autopdex import dae
+    rng = np.random.default_rng(5)
+    n, dt = 7, 0.37
+    cases = ([("be", dae.BackwardEuler())] + [("bdf%d" % k, dae.BackwardDiffFormula(k)) for k in range(1, 7)]
+             + [("am%d" % k, dae.AdamsMoulton(k)) for k in range(1, 7)]
+             + [("dirk%d" % k, dae.DiagonallyImplicitRungeKutta(k)) for k in (1, 2, 3)])
+    for tag, integ in cases:
+        q_n = rng.normal(size=(integ.num_steps, n))
+        q_t_n = rng.normal(size=(integ.num_steps, 1, n))
+        stages = rng.normal(size=(integ.num_stages, n))
+        # one-stage integrators are called with the stage value itself by `update`, with q_stages[...] by the residual
+        arg = jnp.asarray(stages if integ.num_stages > 1 else stages[0])
+        val, q_t = integ.value_and_derivatives(arg, jnp.asarray(q_n), jnp.asarray(q_t_n), dt)[:2]
+        q_n1, q_t_n1 = integ.update(jnp.asarray(stages), jnp.asarray(q_n), jnp.asarray(q_t_n), dt)
+        q_t_n1 = q_t_n1[0] if isinstance(q_t_n1, tuple) else q_t_n1
+        pre = "dae_%s_" % tag
+        out[pre + "q_n"], out[pre + "q_t_n"], out[pre + "stages"], out[pre + "dt"] = q_n, q_t_n, stages, np.array(dt)
+        out[pre + "value"], out[pre + "q_t"] = A(val).reshape(integ.num_stages, n), A(q_t).reshape(integ.num_stages, n)
+        out[pre + "q_n1"], out[pre + "q_t_n1"] = A(q_n1), A(q_t_n1)
+        out[pre + "positions"] = A(integ.stage_positions).astype(float)
+        out[pre + "order"] = np.array(int(integ.order))
+
+
+CASES = {"dae_rules": case_dae_rules, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
          "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "elements_more": case_elements_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 

@@ -35,34 +35,34 @@ def test_stand_in_reproduces_readme_golden_value(fake):
     assert np.isclose(sol["phi"].sum(), 1.9066412530282952, rtol=1e-10, atol=0)
 
 
-@pytest.mark.parametrize("scheme", ["backward_euler", "bdf2", "bdf3"])
+@pytest.mark.parametrize("scheme", ["backward_euler", "bdf2", "bdf3", "am1", "am2", "am4", "dirk1", "dirk2", "dirk3"])
 def test_time_stepping_manager_host_loop(fake, scheme):
     """dae.TimeSteppingManager: integrator coefficients -> ('time increment', 'dofs n') of the capacity set, history
     roll, save policy, plan reuse -- against a SciPy loop on the oracle's mass / stiffness matrices."""
     from autopdex_b200 import dae, solver
     n, dt, n_steps = 4, 0.05, 4
     coords, K, M, F, mask, values, res, settings = dae_cases._settings(n)
-    integ, coeffs = {"backward_euler": (dae.BackwardEuler(), [1.0, -1.0]),
-                     "bdf2": (dae.BackwardDiffFormula(2), [1.5, -2.0, 0.5]),
-                     "bdf3": (dae.BackwardDiffFormula(3), [11 / 6, -3.0, 1.5, -1 / 3])}[scheme]
+    q0 = 0.3 * np.cos(coords[:, 1])
+    integ, ref = dae_cases._reference_steps(scheme, K, M, F, mask, values, q0, dt, n_steps)
     static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": integ},
                        "solver backend": "b200", "solver": "cg", "type of preconditioner": "jacobi", "verbose": -1}
-    q0 = 0.3 * np.cos(coords[:, 1])
     save = dae.SaveAllPolicy()
     out = dae.TimeSteppingManager(static_settings, save_policy=save).run({"theta": q0}, dt, dt * n_steps, 100, settings)
     assert (out.num_accepted, out.num_rejected, out.num_steps) == (n_steps, 0, n_steps)
     assert out.newton_iterations == [1] * n_steps
-    ref = dae_cases._scipy_steps(K, M, F, mask, values, q0, coeffs, dt, n_steps)
     for k in range(n_steps):
         assert np.linalg.norm(save.q[k + 1]["theta"] - ref[k]) / np.linalg.norm(ref[k]) < 1e-10, (scheme, k)
     assert len(fake.instances) == 1                     # one plan, two device sets on the same connectivity
     plan = fake.instances[0]
     assert [s.model for s in plan.sets] == ["poisson_potential", "capacity"]
-    assert np.isclose(plan.dt, -dt / coeffs[0])         # -1/a
-    assert out.settings["current time"] == pytest.approx(dt * n_steps)
+    a_last = integ.stage_rule(integ.num_stages - 1, dt, np.zeros((integ.num_stages, 1)), np.zeros((integ.num_steps, 1)),
+                              np.zeros((integ.num_steps, 1, 1)))[0]
+    assert np.isclose(plan.dt, -1.0 / a_last)           # 'time increment' of the last stage solved: -1/a
+    # the last pre_step_updates call of a step is the one of its last stage (dae.py:1900-1903): t_n + c_s dt
+    assert out.settings["current time"] == pytest.approx(dt * (n_steps - 1) + dt * integ.stage_positions[-1])
     # t_max cuts the last step short and num_time_steps bounds the loop (dae.py:2133-2136)
     out2 = dae.TimeSteppingManager(static_settings).run({"theta": q0}, dt, 2.5 * dt, 100, settings)
-    assert out2.num_accepted == 3 and out2.settings["current time"] == pytest.approx(2.5 * dt)
+    assert out2.num_accepted == 3 and out2.settings["current time"] == pytest.approx((2 + 0.5 * integ.stage_positions[-1]) * dt)
     out3 = dae.TimeSteppingManager(static_settings).run({"theta": q0}, dt, 10 * dt, 2, settings)
     assert out3.num_steps == 2
 

@@ -311,3 +311,30 @@ def test_fem_ini_simplex_direct_tables_against_reference(name):
         N, dN = impl(x[None, :], xI[None, :, :])
         assert np.abs(N[0] - FIX["simplex_%s_N" % name]).max() < 1e-10
         assert np.abs(dN[0] - FIX["simplex_%s_dN" % name]).max() < 1e-6 * max(1.0, np.abs(dN).max())
+
+
+_DAE_TAGS = (["be"] + ["bdf%d" % k for k in range(1, 7)] + ["am%d" % k for k in range(1, 7)] + ["dirk%d" % k for k in (1, 2, 3)])
+
+
+@pytest.mark.parametrize("tag", _DAE_TAGS)
+def test_time_integrator_rules_against_reference_integrators(tag):
+    """autopdex_b200.dae integrators against the reference's own classes (autopdex/dae.py:288-318, 420-481, 537-587,
+    707-766 executed by tests/golden/make_reference_fixtures.py `dae_rules`): for every stage the value / first derivative
+    the residual is evaluated at (`_rule`) must be value = x + d, q_t = a value + b with this package's (a, b, d), and the
+    end-of-step update (`_update`) must agree."""
+    from autopdex_b200 import dae
+    integ = (dae.BackwardEuler() if tag == "be" else dae.BackwardDiffFormula(int(tag[3:])) if tag.startswith("bdf")
+             else dae.AdamsMoulton(int(tag[2:])) if tag.startswith("am") else dae.DiagonallyImplicitRungeKutta(int(tag[4:])))
+    pre = "dae_%s_" % tag
+    q_n, q_t_n, stages, dt = FIX[pre + "q_n"], FIX[pre + "q_t_n"], FIX[pre + "stages"], float(FIX[pre + "dt"])
+    assert (integ.num_steps, integ.num_stages) == (q_n.shape[0], stages.shape[0])
+    assert np.allclose(integ.stage_positions, FIX[pre + "positions"], rtol=1e-15) and integ.order == int(FIX[pre + "order"])
+    scale = np.abs(FIX[pre + "q_t"]).max()
+    for s in range(integ.num_stages):
+        a, b, d = integ.stage_rule(s, dt, stages, q_n, q_t_n)
+        value = stages[s] + d
+        assert np.abs(value - FIX[pre + "value"][s]).max() < 1e-13 * max(1.0, np.abs(value).max()), (tag, s)
+        assert np.abs(a * value + b - FIX[pre + "q_t"][s]).max() < 1e-13 * scale, (tag, s)
+    q_n1, q_t_n1 = integ.update(stages, q_n, q_t_n, dt)
+    assert np.abs(q_n1 - FIX[pre + "q_n1"]).max() < 1e-13 * max(1.0, np.abs(q_n1).max())
+    assert np.abs(q_t_n1 - FIX[pre + "q_t_n1"].reshape(q_t_n1.shape)).max() < 1e-13 * scale

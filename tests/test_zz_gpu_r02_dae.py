@@ -58,6 +58,66 @@ def _scipy_steps(K, M, F, mask, values, q0, integ_coeffs, dt, n_steps):
     return out
 
 
+def _dirichlet_solve(A, rhs, mask, values):
+    free = ~mask
+    A = A.tocsr()
+    q = np.where(mask, values, 0.0)
+    q[free] = spla.spsolve(A[free][:, free].tocsc(), rhs[free] - A[free][:, mask] @ values[mask])
+    return q
+
+
+def _scipy_steps_adams_moulton(K, M, F, mask, values, q0, num_steps, dt, n_steps):
+    """dae.AdamsMoulton (dae.py:420-481) written out for M q_t + K q = F: q_t = ((q - q_n) / dt - sum_j c_j q_t_hist[j-1]) / c_0,
+    derivative history starting at zero (dae.py:1805)."""
+    from autopdex_b200.dae import AdamsMoulton
+    c = AdamsMoulton._COEFFS[num_steps]
+    q, hist, out = q0.copy(), [np.zeros_like(q0) for _ in range(num_steps)], []
+    for _ in range(n_steps):
+        past = sum(cj * h for cj, h in zip(c[1:], hist))
+        q_new = _dirichlet_solve(M / (dt * c[0]) + K, F + M @ (q / (dt * c[0]) + past / c[0]), mask, values)
+        q_t = ((q_new - q) / dt - past) / c[0]
+        hist = [q_t] + hist[:-1]
+        q = q_new
+        out.append(q)
+    return out
+
+
+def _scipy_steps_dirk(K, M, F, mask, values, q0, num_stages, dt, n_steps):
+    """dae.DiagonallyImplicitRungeKutta (dae.py:707-766) written out in the reference's own variables: stage unknown
+    x_i (constrained to the Dirichlet values), slope K_i = (x_i - q_n) / (dt a_ii), residual at q_n + dt sum_j a_ij K_j."""
+    r, al = np.sqrt(3.0), 2 * np.cos(np.pi / 18) / np.sqrt(3.0)
+    A, b = {1: ([[0.5]], [1.0]),
+            2: ([[0.5 + r / 6, 0.0], [-r / 3, 0.5 + r / 6]], [0.5, 0.5]),
+            3: ([[(1 + al) / 2, 0, 0], [-al / 2, (1 + al) / 2, 0], [1 + al, -(1 + 2 * al), (1 + al) / 2]],
+                [1 / (6 * al ** 2), 1 - 1 / (3 * al ** 2), 1 / (6 * al ** 2)])}[num_stages]
+    q, out = q0.copy(), []
+    for _ in range(n_steps):
+        slopes = []
+        for i in range(num_stages):
+            d = dt * sum(A[i][j] * slopes[j] for j in range(i)) if i else np.zeros_like(q)
+            g = 1.0 / (dt * A[i][i])
+            x = _dirichlet_solve(g * M + K, F + M @ (g * q) - K @ d, mask, values)
+            slopes.append((x - q) * g)
+        q = q + dt * sum(bi * ki for bi, ki in zip(b, slopes))
+        out.append(q)
+    return out
+
+
+def _reference_steps(scheme, K, M, F, mask, values, q0, dt, n_steps):
+    """(integrator of autopdex_b200.dae, SciPy time loop) for a scheme name."""
+    from autopdex_b200 import dae
+    if scheme == "backward_euler":
+        return dae.BackwardEuler(), _scipy_steps(K, M, F, mask, values, q0, [1.0, -1.0], dt, n_steps)
+    if scheme.startswith("bdf"):
+        k = int(scheme[3:])
+        return dae.BackwardDiffFormula(k), _scipy_steps(K, M, F, mask, values, q0, dae.BackwardDiffFormula._COEFFS[k], dt, n_steps)
+    if scheme.startswith("am"):
+        k = int(scheme[2:])
+        return dae.AdamsMoulton(k), _scipy_steps_adams_moulton(K, M, F, mask, values, q0, k, dt, n_steps)
+    k = int(scheme[4:])
+    return dae.DiagonallyImplicitRungeKutta(k), _scipy_steps_dirk(K, M, F, mask, values, q0, k, dt, n_steps)
+
+
 def _settings(n):
     from autopdex_b200 import models, seeder, spaces
     coords, elems, K, M, F = _oracle_matrices(n)
@@ -72,22 +132,21 @@ def _settings(n):
     return coords, K, M, F, mask, values, res, settings
 
 
-@pytest.mark.parametrize("scheme", ["backward_euler", "bdf2"])
+@pytest.mark.parametrize("scheme", ["backward_euler", "bdf2", "am1", "am3", "dirk1", "dirk2", "dirk3"])
 def test_time_stepping_manager_heat_conduction_matches_scipy_loop(scheme):
     from autopdex_b200 import dae, solver
     n, dt, n_steps = 6, 0.05, 3
     solver.clear_plan_cache()                                      # plans of earlier tests must not count below
     coords, K, M, F, mask, values, res, settings = _settings(n)
-    integ, coeffs = (dae.BackwardEuler(), [1.0, -1.0]) if scheme == "backward_euler" else (dae.BackwardDiffFormula(2), [1.5, -2.0, 0.5])
+    q0 = 0.3 * np.cos(coords[:, 1])
+    integ, ref = _reference_steps(scheme, K, M, F, mask, values, q0, dt, n_steps)
     static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": integ},
                        "solver backend": "b200", "solver": "cg", "type of preconditioner": "jacobi", "verbose": -1}
-    q0 = 0.3 * np.cos(coords[:, 1])
     save = dae.SaveAllPolicy()
     mgr = dae.TimeSteppingManager(static_settings, save_policy=save, tol=1e-13)
     out = mgr.run({"theta": q0}, dt, dt * n_steps, 100, settings)
     assert out.num_accepted == n_steps and out.num_rejected == 0 and out.num_steps == n_steps
-    assert all(it == 1 for it in out.newton_iterations)            # linear problem: one solve per step (dae.py:1640-1695)
-    ref = _scipy_steps(K, M, F, mask, values, q0, coeffs, dt, n_steps)
+    assert all(it == 1 for it in out.newton_iterations)            # linear problem: one solve per stage (dae.py:1640-1695)
     assert len(save.q) == n_steps + 1 and np.isclose(save.t[-1], dt * n_steps)
     for k in range(n_steps):
         assert np.linalg.norm(save.q[k + 1]["theta"] - ref[k]) / np.linalg.norm(ref[k]) < 1e-9, (scheme, k)
