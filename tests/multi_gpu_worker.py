@@ -127,8 +127,8 @@ def run_quad_case(n, precond, rank, world):
     return bool(backend.comm_allreduce_host([0.0 if ok else 1.0], "max")[0] == 0.0)
 
 
-def run_dae_case(m, precond, rank, world):
-    """dae.TimeSteppingManager (BackwardEuler, transient heat conduction through the 'user residual' route) on slab
+def run_dae_case(m, precond, rank, world, scheme="backward_euler"):
+    """dae.TimeSteppingManager (BackwardEuler, or another scheme of tests/test_zz_gpu_r02_dae._reference_steps; transient heat conduction through the 'user residual' route) on slab
     partitions, against a SciPy time loop on the oracle's global mass / stiffness matrices (tests/test_zz_gpu_r02_dae.py)."""
     from autopdex_b200 import backend, dae, mesher, solver
     from tests import test_zz_gpu_r02_dae as T
@@ -140,11 +140,13 @@ def run_dae_case(m, precond, rank, world):
     settings = {"connectivity": ({"theta": pt["elements"][0].astype(np.int32)},), "node coordinates": {"theta": coords[nodes]},
                 "dirichlet dofs": {"theta": mask[nodes]}, "dirichlet conditions": {"theta": values[nodes]}, "current time": 0.0,
                 "b200 partition": pt["b200 partition"]}
-    static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": dae.BackwardEuler()},
+    q0 = 0.3 * np.cos(coords[:, 1])
+    integ = T._integrator(scheme)
+    ref_steps = T._reference_steps(scheme, K, M, F, mask, values, q0, dt, n_steps)[1] if rank == 0 else None
+    static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": integ},
                        "solver backend": "b200", "solver": "cg", "type of preconditioner": precond, "verbose": -1}
     if precond == "multigrid":
         settings["b200 multigrid"] = {"n_elements": (m, m, m)}
-    q0 = 0.3 * np.cos(coords[:, 1])
     mgr = dae.TimeSteppingManager(static_settings, tol=1e-13)
     out = mgr.run({"theta": q0[nodes]}, dt, dt * n_steps, 100, settings)
     part = settings["b200 partition"]
@@ -154,11 +156,11 @@ def run_dae_case(m, precond, rank, world):
     glob = backend.comm_allreduce_host(glob)
     ok = True
     if rank == 0:
-        ref = T._scipy_steps(K, M, F, mask, values, q0, [1.0, -1.0], dt, n_steps)[-1]
+        ref = ref_steps[-1]
         err = np.linalg.norm(glob - ref) / np.linalg.norm(ref)
         ok = err < 1e-9 and out.num_accepted == n_steps and all(it == 1 for it in out.newton_iterations)
-        print("multi-gpu parity: ranks=%d dae backward-euler heat m=%d cg+%s slab steps=%d rel-L2=%.2e -> %s"
-              % (world, m, precond, out.num_accepted, err, "OK" if ok else "FAIL"), flush=True)
+        print("multi-gpu parity: ranks=%d dae %s heat m=%d cg+%s slab steps=%d rel-L2=%.2e -> %s"
+              % (world, scheme.replace("_", "-"), m, precond, out.num_accepted, err, "OK" if ok else "FAIL"), flush=True)
     solver.clear_plan_cache()
     return bool(backend.comm_allreduce_host([0.0 if ok else 1.0], "max")[0] == 0.0)
 
@@ -186,7 +188,7 @@ def main():
                  for pt in ("slab", "rcb")]
     elif argv and argv[0] == "dae":       # dae [M]: the time-stepping manager on slabs, Jacobi and multigrid
         m = max(int(argv[1]) if len(argv) > 1 else 8, 4 * world)
-        cases = [("dae", m, "jacobi"), ("dae", m, "multigrid")]
+        cases = [("dae", m, "jacobi"), ("dae", m, "multigrid"), ("dae", m, "jacobi", "dirk2"), ("dae", m, "multigrid", "am2")]
     elif argv and argv[0] == "mgmatrix":
         mp = int(argv[1]) if len(argv) > 1 else 32
         mn = int(argv[2]) if len(argv) > 2 else 16
@@ -208,7 +210,7 @@ def main():
     for c in cases:
         signal.alarm(int(os.environ.get("APDX_CASE_TIMEOUT", "150")))
         try:
-            ok = (run_dae_case(c[1], c[2], rank, world) if c[0] == "dae" else
+            ok = (run_dae_case(c[1], c[2], rank, world, *c[3:]) if c[0] == "dae" else
                   run_quad_case(c[1], c[2], rank, world) if c[0] == "quad" else run_case(*c[:4], rank, world, *c[4:])) and ok
         except Exception as e:   # keep the remaining cases running; every rank raises alike (collective set-up errors)
             ok = False

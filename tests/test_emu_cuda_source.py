@@ -114,10 +114,11 @@ def test_partitioned_multigrid_on_emulated_ranks():
 
 
 def test_time_stepping_manager_on_emulated_ranks():
-    """dae.TimeSteppingManager (BackwardEuler heat conduction, 'user residual' route) on two slabs, Jacobi- and
-    multigrid-preconditioned CG (the coarse levels' 'dofs n' travels with the ghost-plane exchange), against the SciPy loop."""
+    """dae.TimeSteppingManager (heat conduction, 'user residual' route; BackwardEuler, two-stage DIRK, Adams-Moulton 2) on two
+    slabs, Jacobi- and multigrid-preconditioned CG (the coarse levels' 'dofs n' travels with the ghost-plane exchange),
+    against the SciPy loops."""
     rc, lines, out = _run_ranks(2, ["dae", "8"])
-    assert rc == 0 and len(lines) == 2 and all(l.endswith("-> OK") for l in lines), out[-4000:]
+    assert rc == 0 and len(lines) == 4 and all(l.endswith("-> OK") for l in lines), out[-4000:]
 
 
 def test_readme_example_runs_on_the_emulated_build():

@@ -103,19 +103,28 @@ def _scipy_steps_dirk(K, M, F, mask, values, q0, num_stages, dt, n_steps):
     return out
 
 
+def _integrator(scheme):
+    from autopdex_b200 import dae
+    if scheme == "backward_euler":
+        return dae.BackwardEuler()
+    if scheme.startswith("bdf"):
+        return dae.BackwardDiffFormula(int(scheme[3:]))
+    if scheme.startswith("am"):
+        return dae.AdamsMoulton(int(scheme[2:]))
+    return dae.DiagonallyImplicitRungeKutta(int(scheme[4:]))
+
+
 def _reference_steps(scheme, K, M, F, mask, values, q0, dt, n_steps):
     """(integrator of autopdex_b200.dae, SciPy time loop) for a scheme name."""
     from autopdex_b200 import dae
+    integ = _integrator(scheme)
     if scheme == "backward_euler":
-        return dae.BackwardEuler(), _scipy_steps(K, M, F, mask, values, q0, [1.0, -1.0], dt, n_steps)
+        return integ, _scipy_steps(K, M, F, mask, values, q0, [1.0, -1.0], dt, n_steps)
     if scheme.startswith("bdf"):
-        k = int(scheme[3:])
-        return dae.BackwardDiffFormula(k), _scipy_steps(K, M, F, mask, values, q0, dae.BackwardDiffFormula._COEFFS[k], dt, n_steps)
+        return integ, _scipy_steps(K, M, F, mask, values, q0, dae.BackwardDiffFormula._COEFFS[integ.num_steps], dt, n_steps)
     if scheme.startswith("am"):
-        k = int(scheme[2:])
-        return dae.AdamsMoulton(k), _scipy_steps_adams_moulton(K, M, F, mask, values, q0, k, dt, n_steps)
-    k = int(scheme[4:])
-    return dae.DiagonallyImplicitRungeKutta(k), _scipy_steps_dirk(K, M, F, mask, values, q0, k, dt, n_steps)
+        return integ, _scipy_steps_adams_moulton(K, M, F, mask, values, q0, integ.num_steps, dt, n_steps)
+    return integ, _scipy_steps_dirk(K, M, F, mask, values, q0, integ.num_stages, dt, n_steps)
 
 
 def _settings(n):

@@ -11,7 +11,7 @@ set -u
 cd "$(dirname "$0")/.."
 python tests/emu/build.py || exit 1
 LIB=$PWD/tests/emu/build/libapdx_b200_emu.so
-OUT=${1:-profiles/r02f_emulated_cuda_source_suite.txt}
+OUT=${1:-profiles/r02g_emulated_cuda_source_suite.txt}
 {
   echo "# $(date -u +%FT%TZ)  $(git rev-parse --short HEAD)  emulated CUDA source, -m gpu suite without tests/test_gpu_fullsize.py"
   for mode in "1 2 ascending" "2 2 ascending" "0 5 ascending" "1 2 shuffle" "1 2 reverse"; do
