@@ -28,8 +28,8 @@ SLOW = [
     "tests/test_gpu_api.py::test_newton_maxiter_flags_divergence_like_reference",
     "tests/test_gpu_api.py::test_damped_newton_iteration_count_matches_oracle",
     "tests/test_gpu_api.py::test_tangent_solve_matches_reference_sensitivity_solve",
-    "tests/test_gpu_multigrid.py::test_poisson_hex_multigrid_matches_oracle",
-    "tests/test_gpu_multigrid.py::test_neo_hooke_brick_multigrid_newton_counts",
+    "tests/test_zz_gpu_multigrid.py::test_poisson_hex_multigrid_matches_oracle",
+    "tests/test_zz_gpu_multigrid.py::test_neo_hooke_brick_multigrid_newton_counts",
     "tests/test_zz_gpu_r02_dae.py::test_verbose_prints_one_line_per_newton_iteration",
     "tests/test_zz_gpu_r02_symmetric_tangent.py::test_cook_membrane_q1_multigrid_pcg_matches_jacobi_bicgstab",
 ]

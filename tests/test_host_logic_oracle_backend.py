@@ -113,7 +113,7 @@ def test_multigrid_hierarchy_host_construction(fake):
 
 
 def test_multigrid_rejections_host(fake):
-    from tests import test_gpu_multigrid as mgt
+    from tests import test_zz_gpu_multigrid as mgt
     mgt.test_multigrid_rejections()
 
 

@@ -1,4 +1,8 @@
-"""GPU parity of the multigrid-preconditioned CG ('type of preconditioner': 'multigrid'; the
+"""(Ran green on a B200 in round 2 as tests/test_gpu_multigrid.py; renamed so that it sorts behind the validated parity
+suite under `pytest -x`: the hierarchy's transfer operators are now built on the device by kernels that have not run on
+hardware yet -- tests/test_zz_gpu_mg_transfer.py checks them against the host construction.)
+
+GPU parity of the multigrid-preconditioned CG ('type of preconditioner': 'multigrid'; the
 reference's analogue: pyamg / PETSc preconditioners, autopdex/solver.py:1399-1491, 1224-1333) through the public API:
 same Newton counts and solutions as the oracle ('scipy'/'lapack' path) and as the Jacobi-PCG of the same backend, in
 far fewer Krylov iterations."""
