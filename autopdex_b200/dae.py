@@ -16,9 +16,12 @@ capacity kernels with `time increment` = -1/a and `dofs n` = -b/a: the capacity 
 -c/dt_eff N_i N_j (theta - theta_n,eff).  Assembly, the Newton loop (dae.newton_solver semantics: residual tolerance
 `atol`, at most `max_iter` updates) and the Krylov solve run on the device; the plan (pattern, index maps, multigrid
 hierarchy if asked for) is built once and reused by every stage of every step.
-Coupled-stage (GaussLegendreRungeKutta) / explicit / embedded (Kvaerno, DormandPrince) integrators, Newmark (second
-derivatives), step-size controllers other than the constant one and user-written integrands are rejected (ValueError),
-never routed to a host path.
+Step sizes: ConstantStepSizeController (dae.py:1474-1497) or RootIterationController (:1509-1573: proportional control on
+the Newton iteration count, failed steps rejected and repeated with half the step), with the accept / reject / interrupt
+logic of TimeSteppingManager.run (:2150-2249).
+Coupled-stage (GaussLegendreRungeKutta) / explicit / embedded (Kvaerno, DormandPrince: their explicit first stage needs
+the conduction term at a state other than the unknown) integrators, Newmark (second derivatives), the PID controller
+(needs an embedded error estimate) and user-written integrands are rejected (ValueError), never routed to a host path.
 """
 from dataclasses import dataclass, field as _field
 from typing import Any
@@ -140,7 +143,41 @@ class DiagonallyImplicitRungeKutta(TimeIntegrator):
 
 
 class ConstantStepSizeController:
-    """dae.ConstantStepSizeController (dae.py:1474-1497): every converged step is accepted, dt never changes."""
+    """dae.ConstantStepSizeController (dae.py:1474-1497): every converged step is accepted, dt never changes; a step whose
+    root solve did not converge cannot be repeated with a smaller step, so the run is interrupted."""
+
+    def initialize(self):
+        return {"step_scaler": 1.0, "dt": 1.0, "accept": True, "interrupt": False}
+
+    def compute_scaler(self, state, converged, num_iterations, dt):
+        return state
+
+    def check_accept(self, state, converged, verbose):
+        if not converged and not state["interrupt"] and verbose >= 0:
+            print("Root solver did not converge, but stepsize controller can not reduce step size!")
+        return dict(state, accept=bool(converged), interrupt=state["interrupt"] or not converged)
+
+
+class RootIterationController(ConstantStepSizeController):
+    """dae.RootIterationController (dae.py:1509-1573): proportional control of the step size on the number of Newton
+    iterations of the last step, dt *= 1 + gamma (target - iterations) / target, halved when the root solve did not
+    converge, clipped to [min_step_size, max_step_size]; a failed step is rejected and repeated with the new step, the
+    run is interrupted when that fails at the minimum step size."""
+
+    def __init__(self, target_niters=6, gamma=0.5, max_step_size=1e20, min_step_size=1e-6):
+        self.target_niters, self.gamma = target_niters, gamma
+        self.max_step_size, self.min_step_size = max_step_size, min_step_size
+
+    def compute_scaler(self, state, converged, num_iterations, dt):
+        correction = 1 + self.gamma * (self.target_niters - num_iterations) / self.target_niters if converged else 0.5
+        dt_new = float(np.clip(dt * correction, self.min_step_size, self.max_step_size))
+        return dict(state, step_scaler=dt_new / dt, dt=dt_new)
+
+    def check_accept(self, state, converged, verbose):
+        warn = (not converged) and bool(np.isclose(state["dt"], self.min_step_size)) and not state["interrupt"]
+        if warn and verbose >= 0:
+            print("Root solver did not converge, but minimum step_size is reached!")
+        return dict(state, accept=bool(converged), interrupt=state["interrupt"] or warn)
 
 
 class SaveAllPolicy:
@@ -181,8 +218,13 @@ class TimeSteppingManager:
             raise ValueError("autopdex_b200.dae handles 'solver backend': 'b200' only")
         if root_solver is not None:
             raise ValueError("b200 backend: the Newton iteration runs on the device; root_solver cannot be replaced")
-        if step_size_controller is not None and not isinstance(step_size_controller, ConstantStepSizeController):
-            raise ValueError("b200 backend: only ConstantStepSizeController is supported")
+        if step_size_controller is None:
+            step_size_controller = ConstantStepSizeController()
+        if not isinstance(step_size_controller, ConstantStepSizeController):
+            raise ValueError("b200 backend: step-size controller %r is not supported (ConstantStepSizeController, "
+                             "RootIterationController; the PID controller needs an embedded error estimate)"
+                             % (step_size_controller,))
+        self.step_size_controller = step_size_controller
         self.integrators = dict(static_settings["time integrators"])
         if len(self.integrators) != 1:
             raise ValueError("b200 backend: one field (one time integrator) is supported, got %d" % len(self.integrators))
@@ -224,9 +266,12 @@ class TimeSteppingManager:
         t, t_n, dt = 0.0, 0.0, float(dt0)
         if self.save_policy is not None:
             self.save_policy.save(t, {key: q})
-        accepted = rejected = steps = 0
+        accepted = rejected = 0
         newton_its = []
-        while steps < num_time_steps and t_n < t_max * (1 - 1e-14):
+        ctrl = self.step_size_controller.initialize()
+        for _ in range(int(num_time_steps)):                            # fori_loop over num_time_steps attempts (dae.py:2266)
+            if not (t < t_max * (1 - 1e-14)) or ctrl["interrupt"]:      # dae.py:2243
+                break
             t = min(t_n + dt, t_max)
             dt_step = t - t_n
             settings = self.pre_step_updates(t, settings)                # dae.py:2156
@@ -251,28 +296,34 @@ class TimeSteppingManager:
                 q_stages[s] = value - d if shifted else value
                 its = max(its, int(it_s))                          # dae.py:2051
                 converged = converged and (not div) and res < self.atol
-            steps += 1
             newton_its.append(its)
             if self.verbose >= 1:
                 print("Time %.6e: Newton iterations %d, residual norm %.3e, converged %s" % (t, its, res, converged))
-            if not converged:                                       # constant controller: interrupt (dae.py:1486-1497)
+            ctrl = self.step_size_controller.compute_scaler(ctrl, converged, its, dt_step)      # dae.py:2162-2166
+            ctrl = self.step_size_controller.check_accept(ctrl, converged, self.verbose)
+            if ctrl["accept"] and not ctrl["interrupt"]:            # do_accept (dae.py:2175-2196)
+                accepted += 1
+                q, q_t = integ.update(q_stages, q_n, q_t_n, dt_step)
+                q = np.asarray(q, dtype=np.float64)
+                q_n = np.roll(q_n, 1, axis=0)
+                q_n[0] = q
+                q_t_n = np.roll(q_t_n, 1, axis=0)
+                q_t_n[0, 0] = q_t
+                t_n = t
+                if self.post_step_updates is not None:
+                    settings = self.post_step_updates(lambda tt: {key: q}, t, settings)
+                if self.save_policy is not None:
+                    self.save_policy.save(t, {key: q})
+            else:                                                   # do_reject (dae.py:2198-2203): back to t_n, new step size
                 rejected += 1
-                break
-            accepted += 1
-            q, q_t = integ.update(q_stages, q_n, q_t_n, dt_step)
-            q = np.asarray(q, dtype=np.float64)
-            q_n = np.roll(q_n, 1, axis=0)                           # dae.py:2178-2182
-            q_n[0] = q
-            q_t_n = np.roll(q_t_n, 1, axis=0)
-            q_t_n[0, 0] = q_t
-            t_n = t
-            if self.post_step_updates is not None:
-                settings = self.post_step_updates(lambda tt: {key: q}, t, settings)
-            if self.save_policy is not None:
-                self.save_policy.save(t, {key: q})
+                t = t_n
+            dt = ctrl["step_scaler"] * dt_step
+        if ctrl["interrupt"]:                                       # dae.py:2245-2249
+            q = np.full_like(q, np.nan)
+        steps = accepted + rejected
         return TimeSteppingManagerState({key: q}, settings, self.save_policy, steps, accepted, rejected, newton_its)
 
 
 __all__ = ["TimeSteppingManager", "TimeSteppingManagerState", "BackwardEuler", "BackwardDiffFormula", "AdamsMoulton",
-           "DiagonallyImplicitRungeKutta",
+           "DiagonallyImplicitRungeKutta", "RootIterationController",
            "ConstantStepSizeController", "SaveAllPolicy"]

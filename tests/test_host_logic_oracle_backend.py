@@ -67,6 +67,10 @@ def test_time_stepping_manager_host_loop(fake, scheme):
     assert out3.num_steps == 2
 
 
+def test_root_iteration_controller_host(fake):
+    dae_cases.test_root_iteration_controller_grows_and_rejects_like_the_reference()
+
+
 def test_time_stepping_manager_rejections_host(fake):
     dae_cases.test_time_stepping_manager_rejections()
 

@@ -164,6 +164,43 @@ def test_time_stepping_manager_heat_conduction_matches_scipy_loop(scheme):
     solver.clear_plan_cache()
 
 
+def test_root_iteration_controller_grows_and_rejects_like_the_reference():
+    """dae.RootIterationController (dae.py:1509-1573) around the device solve: the linear problem converges in one Newton
+    iteration, so every accepted step scales dt by 1 + gamma (target - 1) / target up to max_step_size; with an
+    unreachable tolerance every attempt is rejected, dt is halved down to min_step_size and the run is interrupted
+    (q -> NaN, dae.py:2245-2249)."""
+    from autopdex_b200 import dae, solver
+    n, dt0 = 4, 0.02
+    coords, K, M, F, mask, values, res, settings = _settings(n)
+    static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": dae.BackwardEuler()},
+                       "solver backend": "b200", "solver": "cg", "type of preconditioner": "jacobi", "verbose": -1}
+    q0 = 0.3 * np.cos(coords[:, 1])
+    ctrl = dae.RootIterationController(target_niters=6, gamma=0.5, max_step_size=0.05)
+    save = dae.SaveAllPolicy()
+    out = dae.TimeSteppingManager(static_settings, save_policy=save, step_size_controller=ctrl, tol=1e-13).run(
+        {"theta": q0}, dt0, 0.2, 100, settings)
+    # the reference's step sequence, written out
+    t, dt, q, times = 0.0, dt0, q0, []
+    while t < 0.2 * (1 - 1e-14):
+        t_new = min(t + dt, 0.2)
+        q = _scipy_steps(K, M, F, mask, values, q, [1.0, -1.0], t_new - t, 1)[0]
+        dt = float(np.clip((t_new - t) * (1 + 0.5 * (6 - 1) / 6), 1e-6, 0.05))
+        t = t_new
+        times.append(t)
+    assert out.num_accepted == len(times) and out.num_rejected == 0
+    assert np.allclose(save.t[1:], times, rtol=1e-13)
+    assert np.linalg.norm(out.q["theta"] - q) / np.linalg.norm(q) < 1e-9
+    # never converging: rejected, halved, interrupted at the minimum step size
+    ctrl = dae.RootIterationController(min_step_size=dt0 / 4)
+    out = dae.TimeSteppingManager(static_settings, step_size_controller=ctrl, atol=1e-300, max_iter=1, tol=1e-13).run(
+        {"theta": q0}, dt0, 0.2, 100, settings)
+    assert (out.num_accepted, out.num_rejected) == (0, 2) and np.isnan(out.q["theta"]).all()
+    # the constant controller cannot repeat a failed step: interrupted at once
+    out = dae.TimeSteppingManager(static_settings, atol=1e-300, max_iter=1, tol=1e-13).run({"theta": q0}, dt0, 0.2, 100, settings)
+    assert (out.num_accepted, out.num_rejected) == (0, 1) and np.isnan(out.q["theta"]).all()
+    solver.clear_plan_cache()
+
+
 def test_time_stepping_manager_with_multigrid():
     from autopdex_b200 import dae, solver
     n, dt = 8, 0.1
