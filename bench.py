@@ -518,7 +518,6 @@ def run_b200(args):
     asm_gbs = asm_elems * 290.0 / (np.mean(asm_ms) * 1e-3) / 1e9
     fp64_peak = backend.measure_fp64_peak()                        # TFLOP/s, measured here (not in MEASURED_PEAKS.json)
     asm_tflops = asm_elems * HEX8_POISSON_FLOP / (np.mean(asm_ms) * 1e-3) / 1e12
-    vector = optional_section(vector_problem_figures, args, hbm, fp64_peak, args.vector_size) if (world == 1 and not args.no_vector) else None
 
     line = None if rank != 0 else {
         "metric": METRIC, "value": total_elems / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -558,36 +557,39 @@ def run_b200(args):
                "streamed_gbs": cg_gbs, "frac_of_hbm": cg_gbs / hbm, "algorithmic_gbs": cg_alg_gbs,
                "algorithmic_frac": cg_alg_gbs / hbm, "krylov_ms": float(np.mean(kry_ms)),
                "note": "streamed = SpMV physical bytes + 80 B/row of vector streams per iteration"},
-        "vector_problem": vector,
+        "vector_problem": None,
         "comm": comm_info,      # N > 1: mailbox / NCCL all-reduce, peer-inbox / NCCL halo exchange and the set-up timing behind the choice
         "system": {"n_free": nfree, "nnz_reduced": nnz, "plan_device_gb": dev_gb_after_solve,
                    "plan_device_gb_note": "all device buffers of the plan after the solves (pattern, gather lists, element streams, sliced-ELL matrix, Krylov vectors)"},
     }
-    if not args.no_multigrid:
-        # every rank takes part in the partitioned variant; on several GPUs a watchdog prints the headline line without
-        # the section should a rank stall (the section is optional, the line is not)
-        dog = None
-        if world > 1:
-            import threading
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = optional_section(cpu_baseline_section, args, m)     # host only; before the optional GPU sections
+    # The optional sections run code that is younger than the headline path; a stall in one of them must not cost the
+    # headline line: a watchdog prints the line without the section (rank 0 owns the line; on several GPUs the other ranks
+    # follow a few seconds later) and ends the process.
+    import threading
 
-            def bail():
-                if rank == 0:
-                    line["multigrid"] = {"error": "timed out after %.0f s (watchdog)" % args.mg_timeout_s}
-                    print(json.dumps(line), flush=True)
-                os._exit(0)
-            # rank 0 gives up first (it owns the line); the others follow a few seconds later
-            dog = threading.Timer(args.mg_timeout_s + (0.0 if rank == 0 else 5.0), bail)
-            dog.daemon = True
-            dog.start()
-        mg = optional_section(multigrid_figures, args, sol, rank, world)
-        if dog is not None:
-            dog.cancel()
+    def section_with_watchdog(name, fun, *a):
+        def bail():
+            if rank == 0:
+                line[name] = {"error": "timed out after %.0f s (watchdog)" % args.mg_timeout_s}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        dog = threading.Timer(args.mg_timeout_s + (0.0 if rank == 0 else 5.0), bail)
+        dog.daemon = True
+        dog.start()
+        out = optional_section(fun, *a)
+        dog.cancel()
         if rank == 0:
-            line["multigrid"] = mg
+            line[name] = out
+
+    if world == 1 and not args.no_vector:
+        section_with_watchdog("vector_problem", vector_problem_figures, args, hbm, fp64_peak, args.vector_size)
+    if not args.no_multigrid:
+        # every rank takes part in the partitioned variant
+        section_with_watchdog("multigrid", multigrid_figures, args, sol, rank, world)
     if rank != 0:
         return
-    if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = optional_section(cpu_baseline_section, args, m)
     print(json.dumps(line))
 
 
@@ -609,7 +611,7 @@ def main():
     ap.add_argument("--no-vector", action="store_true", help="skip the bounded 64^3 neo-Hooke figures")
     ap.add_argument("--vector-size", type=int, default=64, help="elements per direction of the bounded neo-Hooke sample")
     ap.add_argument("--no-multigrid", action="store_true", help="skip the multigrid-preconditioned variant of the step")
-    ap.add_argument("--mg-timeout-s", type=float, default=240.0, help="watchdog of the multi-GPU multigrid section")
+    ap.add_argument("--mg-timeout-s", type=float, default=240.0, help="watchdog of each optional section (nf = 3 figures, multigrid variant)")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nx", type=int, default=0, help="diagnostic: elements along the slowest index (default: --size)")
