@@ -180,15 +180,88 @@ class RootIterationController(ConstantStepSizeController):
         return dict(state, accept=bool(converged), interrupt=state["interrupt"] or warn)
 
 
-class SaveAllPolicy:
-    """dae.SaveAllPolicy (dae.py:1278-1311): history of (t, q) for every accepted step, the initial state included."""
+@dataclass
+class HistoryState:
+    """dae.HistoryState (dae.py:1099-1110): t [n + 1], q {field: [n + 1, ...]}, user {name: [n + 1, ...]}; rows that were
+    never written hold NaN, as in the reference's pre-allocated arrays."""
+    t: Any
+    q: Any
+    user: Any
+
+
+class SavePolicy:
+    """Interface of dae.SavePolicy (dae.py:1112-1157): initialize -> state, save_step(state, t, q, user_data) -> state,
+    finalize(state) -> HistoryState."""
+
+    def initialize(self, q, t_max, max_steps, user_data=None):
+        return None
+
+    def save_step(self, state, t, q, user_data=None):
+        return state
+
+    def finalize(self, state):
+        return None
+
+
+class SaveNothingPolicy(SavePolicy):
+    """dae.SaveNothingPolicy (dae.py:1160-1170)."""
+
+
+class _ArrayHistory(SavePolicy):
+    def _allocate(self, n, q, user_data):
+        user_data = user_data or {}
+        return {"n": int(n), "idx": 0, "t": np.full(n + 1, np.nan),
+                "q": {k: np.full((n + 1,) + np.shape(v), np.nan) for k, v in q.items()},
+                "user": {k: np.full((n + 1,) + np.shape(v), np.nan) for k, v in user_data.items()}}
+
+    def _write(self, state, t, q, user_data):
+        i = state["idx"]
+        state["t"][i] = t
+        for k in state["q"]:
+            state["q"][k][i] = q[k]
+        for k in state["user"]:
+            state["user"][k][i] = (user_data or {})[k]
+        state["idx"] = min(i + 1, state["n"])                      # clipped like the reference's index
+        return state
+
+    def finalize(self, state):
+        return HistoryState(state["t"], state["q"], state["user"])
+
+
+class SaveAllPolicy(_ArrayHistory):
+    """dae.SaveAllPolicy (dae.py:1278-1311): (t, q, user data) of the initial state and of every accepted step, in arrays
+    of max_steps + 1 rows.  For convenience the policy object also keeps the saved steps as Python lists `t` / `q`."""
 
     def __init__(self):
         self.t, self.q = [], []
 
-    def save(self, t, q):
+    def initialize(self, q, t_max, max_steps, user_data=None):
+        self.t, self.q = [], []
+        return self._allocate(max_steps, q, user_data)
+
+    def save_step(self, state, t, q, user_data=None):
         self.t.append(float(t))
         self.q.append({k: np.array(v) for k, v in q.items()})
+        return self._write(state, t, q, user_data)
+
+
+class SaveEquidistantPolicy(_ArrayHistory):
+    """dae.SaveEquidistantPolicy (dae.py:1186-1264): saves the first accepted step at or after each of the num_points + 1
+    equidistant target times linspace(0, t_max, num_points + 1) (num_points defaults to the maximum number of steps)."""
+
+    def __init__(self, num_points=None, tol=1e-6):
+        self.tol, self.num_points = tol, num_points
+
+    def initialize(self, q, t_max, max_steps, user_data=None):
+        n = self.num_points if self.num_points is not None else max_steps
+        state = self._allocate(n, q, user_data)
+        state["targets"] = np.linspace(0.0, t_max, n + 1)
+        return state
+
+    def save_step(self, state, t, q, user_data=None):
+        if t >= state["targets"][state["idx"]] - self.tol:
+            state = self._write(state, t, q, user_data)
+        return state
 
 
 @dataclass
@@ -238,7 +311,7 @@ class TimeSteppingManager:
         if "solution structure" not in self.static_settings:
             self.static_settings["solution structure"] = ("nodal imposition",) * len(static_settings["assembling mode"])
         self.save_policy = save_policy
-        self.postprocessing_fun = postprocessing_fun
+        self.postprocessing_fun = postprocessing_fun if postprocessing_fun is not None else (lambda q_fun, t, settings: {})
         if pre_step_updates is None:
             def pre_step_updates(t, settings):                 # dae.py:1768-1772
                 settings["current time"] = t
@@ -264,8 +337,12 @@ class TimeSteppingManager:
         dd = settings.get("dirichlet dofs")
         mask = None if dd is None else np.asarray(dd[key] if isinstance(dd, dict) else dd, dtype=bool).reshape(q.shape)
         t, t_n, dt = 0.0, 0.0, float(dt0)
-        if self.save_policy is not None:
-            self.save_policy.save(t, {key: q})
+        q_fun = lambda tt: {key: q}                                    # the discrete value (dae.py:2137-2138)
+        history = None
+        if self.save_policy is not None:                             # dae.py:2140-2144
+            user_data = self.postprocessing_fun(q_fun, t, settings)
+            history = self.save_policy.initialize({key: q}, t_max, int(num_time_steps), user_data)
+            history = self.save_policy.save_step(history, t, {key: q}, user_data)
         accepted = rejected = 0
         newton_its = []
         ctrl = self.step_size_controller.initialize()
@@ -310,10 +387,11 @@ class TimeSteppingManager:
                 q_t_n = np.roll(q_t_n, 1, axis=0)
                 q_t_n[0, 0] = q_t
                 t_n = t
+                user_data = self.postprocessing_fun(q_fun, t, settings)       # dae.py:2188-2191
                 if self.post_step_updates is not None:
-                    settings = self.post_step_updates(lambda tt: {key: q}, t, settings)
+                    settings = self.post_step_updates(q_fun, t, settings)
                 if self.save_policy is not None:
-                    self.save_policy.save(t, {key: q})
+                    history = self.save_policy.save_step(history, t, {key: q}, user_data)
             else:                                                   # do_reject (dae.py:2198-2203): back to t_n, new step size
                 rejected += 1
                 t = t_n
@@ -321,9 +399,11 @@ class TimeSteppingManager:
         if ctrl["interrupt"]:                                       # dae.py:2245-2249
             q = np.full_like(q, np.nan)
         steps = accepted + rejected
-        return TimeSteppingManagerState({key: q}, settings, self.save_policy, steps, accepted, rejected, newton_its)
+        history = self.save_policy.finalize(history) if self.save_policy is not None else None
+        return TimeSteppingManagerState({key: q}, settings, history, steps, accepted, rejected, newton_its)
 
 
 __all__ = ["TimeSteppingManager", "TimeSteppingManagerState", "BackwardEuler", "BackwardDiffFormula", "AdamsMoulton",
            "DiagonallyImplicitRungeKutta", "RootIterationController",
-           "ConstantStepSizeController", "SaveAllPolicy"]
+           "ConstantStepSizeController", "SaveAllPolicy", "SaveNothingPolicy", "SaveEquidistantPolicy", "SavePolicy",
+           "HistoryState"]

@@ -400,6 +400,7 @@ def install():
         "array": _wrap_fn(np.array), "asarray": _wrap_fn(lambda x, dtype=None: _asarray(x, dtype)),
         "linalg": _NS("jax.numpy.linalg", np.linalg),
         "invert": _wrap_fn(np.invert),
+        "astype": _wrap_fn(lambda x, dtype, **k: np.asarray(x).astype(dtype)),     # jnp.astype accepts Python scalars
         "einsum": _wrap_fn(lambda sub, *ops, **k: np.einsum(sub.replace(" ", ""), *ops, **k)), "pi": np.pi, "inf": np.inf, "nan": np.nan, "newaxis": None,
     })
     class _Mod(types.ModuleType):

@@ -431,7 +431,35 @@ def case_dae_rules(out):
         out[pre + "order"] = np.array(int(integ.order))
 
 
-CASES = {"dae_rules": case_dae_rules, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
+DAE_SAVE_TIMES = [0.0, 0.2, 0.35, 0.5, 0.7, 0.9, 1.0]
+DAE_CTRL_SEQ = [(True, 2, 0.1), (True, 9, 0.2), (False, 4, 0.25), (True, 1, 0.29), (False, 3, 0.02), (False, 3, 0.011)]
+
+
+def case_dae_control(out):
+    """dae.SaveEquidistantPolicy / SaveAllPolicy (dae.py:1186-1311) fed with a sequence of accepted steps, and
+    dae.RootIterationController / ConstantStepSizeController (dae.py:1474-1573) fed with a sequence of
+    (converged, iterations, dt): the histories and controller states the reference's own classes produce."""
+    from autopdex import dae
+    q0 = np.arange(4.0)
+    for tag, pol, max_steps in (("equi3", dae.SaveEquidistantPolicy(num_points=3, tol=1e-6), 10),
+                                ("equi_default", dae.SaveEquidistantPolicy(), 5), ("all", dae.SaveAllPolicy(), 10),
+                                ("all_clipped", dae.SaveAllPolicy(), 4)):
+        st = pol.initialize({"a": jnp.asarray(q0)}, 1.0, max_steps, {"u": jnp.asarray(0.0)})
+        for t in DAE_SAVE_TIMES:
+            st = pol.save_step(st, t, {"a": jnp.asarray(q0 + t)}, {"u": jnp.asarray(2 * t)})
+        h = pol.finalize(st)
+        out["dae_save_%s_t" % tag], out["dae_save_%s_q" % tag], out["dae_save_%s_u" % tag] = A(h.t), A(h.q["a"]), A(h.user["u"])
+    for tag, ctrl in (("root", dae.RootIterationController(target_niters=6, gamma=0.5, max_step_size=0.3, min_step_size=0.01)),
+                      ("const", dae.ConstantStepSizeController())):
+        st, rows = ctrl.initialize(0.0), []
+        for conv, its, dt in DAE_CTRL_SEQ:
+            st = ctrl.compute_scaler(None, None, None, st, 1, conv, its, dt, -1)
+            st = ctrl.check_accept(st, conv, -1)
+            rows.append([float(st.step_scaler), float(getattr(st, "dt", 1.0)), float(st.accept), float(st.interrupt)])
+        out["dae_ctrl_%s" % tag] = np.array(rows)
+
+
+CASES = {"dae_rules": case_dae_rules, "dae_control": case_dae_control, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
          "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "elements_more": case_elements_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 

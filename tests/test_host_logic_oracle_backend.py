@@ -71,6 +71,10 @@ def test_root_iteration_controller_host(fake):
     dae_cases.test_root_iteration_controller_grows_and_rejects_like_the_reference()
 
 
+def test_save_policies_and_postprocessing_host(fake):
+    dae_cases.test_save_policies_and_postprocessing_mirror_the_reference()
+
+
 def test_time_stepping_manager_rejections_host(fake):
     dae_cases.test_time_stepping_manager_rejections()
 

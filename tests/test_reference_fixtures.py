@@ -338,3 +338,30 @@ def test_time_integrator_rules_against_reference_integrators(tag):
     q_n1, q_t_n1 = integ.update(stages, q_n, q_t_n, dt)
     assert np.abs(q_n1 - FIX[pre + "q_n1"]).max() < 1e-13 * max(1.0, np.abs(q_n1).max())
     assert np.abs(q_t_n1 - FIX[pre + "q_t_n1"].reshape(q_t_n1.shape)).max() < 1e-13 * scale
+
+
+def test_save_policies_and_step_size_controllers_against_reference_classes():
+    """autopdex_b200.dae save policies / step-size controllers against the reference's own classes (autopdex/dae.py:1186-1311,
+    1474-1573; fixture case `dae_control`, same input sequences as tests/golden/make_reference_fixtures.py)."""
+    from autopdex_b200 import dae
+    times = [0.0, 0.2, 0.35, 0.5, 0.7, 0.9, 1.0]
+    seq = [(True, 2, 0.1), (True, 9, 0.2), (False, 4, 0.25), (True, 1, 0.29), (False, 3, 0.02), (False, 3, 0.011)]
+    q0 = np.arange(4.0)
+    for tag, pol, max_steps in (("equi3", dae.SaveEquidistantPolicy(num_points=3, tol=1e-6), 10),
+                                ("equi_default", dae.SaveEquidistantPolicy(), 5), ("all", dae.SaveAllPolicy(), 10),
+                                ("all_clipped", dae.SaveAllPolicy(), 4)):
+        st = pol.initialize({"a": q0}, 1.0, max_steps, {"u": np.asarray(0.0)})
+        for t in times:
+            st = pol.save_step(st, t, {"a": q0 + t}, {"u": np.asarray(2 * t)})
+        h = pol.finalize(st)
+        for got, name in ((h.t, "t"), (h.q["a"], "q"), (h.user["u"], "u")):
+            ref = FIX["dae_save_%s_%s" % (tag, name)]
+            assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-15, atol=0, equal_nan=True), (tag, name)
+    for tag, ctrl in (("root", dae.RootIterationController(target_niters=6, gamma=0.5, max_step_size=0.3, min_step_size=0.01)),
+                      ("const", dae.ConstantStepSizeController())):
+        st, rows = ctrl.initialize(), []
+        for conv, its, dt in seq:
+            st = ctrl.compute_scaler(st, conv, its, dt)
+            st = ctrl.check_accept(st, conv, -1)
+            rows.append([st["step_scaler"], st["dt"], float(st["accept"]), float(st["interrupt"])])
+        assert np.allclose(np.array(rows), FIX["dae_ctrl_%s" % tag], rtol=1e-14, atol=0), tag

@@ -201,6 +201,38 @@ def test_root_iteration_controller_grows_and_rejects_like_the_reference():
     solver.clear_plan_cache()
 
 
+def test_save_policies_and_postprocessing_mirror_the_reference():
+    """dae.SaveAllPolicy / SaveEquidistantPolicy / SaveNothingPolicy (dae.py:1160-1311) and the user data of
+    `postprocessing_fun` (dae.py:2140, 2188): pre-allocated arrays of max_steps + 1 rows padded with NaN, equidistant
+    targets hit by the first accepted step at or after them."""
+    from autopdex_b200 import dae, solver
+    n, dt, n_steps = 4, 0.05, 4
+    coords, K, M, F, mask, values, res, settings = _settings(n)
+    static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": dae.BackwardEuler()},
+                       "solver backend": "b200", "solver": "cg", "type of preconditioner": "jacobi", "verbose": -1}
+    q0 = 0.3 * np.cos(coords[:, 1])
+    ref = _scipy_steps(K, M, F, mask, values, q0, [1.0, -1.0], dt, n_steps)
+    post = lambda q_fun, t, settings: {"mean": np.asarray(q_fun(t)["theta"]).mean(), "time": np.asarray(t)}
+    out = dae.TimeSteppingManager(static_settings, save_policy=dae.SaveAllPolicy(), postprocessing_fun=post, tol=1e-13).run(
+        {"theta": q0}, dt, dt * n_steps, 6, settings)
+    h = out.history
+    assert isinstance(h, dae.HistoryState) and h.t.shape == (7,) and h.q["theta"].shape == (7, coords.shape[0])
+    assert np.allclose(h.t[:5], dt * np.arange(5)) and np.isnan(h.t[5:]).all() and np.isnan(h.q["theta"][5:]).all()
+    assert np.array_equal(h.q["theta"][0], q0)
+    for k in range(n_steps):
+        assert np.linalg.norm(h.q["theta"][k + 1] - ref[k]) / np.linalg.norm(ref[k]) < 1e-9
+    assert np.allclose(h.user["mean"][:5], h.q["theta"][:5].mean(axis=1)) and np.allclose(h.user["time"][:5], h.t[:5])
+    # two equidistant intervals over four steps: rows at t = 0, 2 dt, 4 dt
+    out = dae.TimeSteppingManager(static_settings, save_policy=dae.SaveEquidistantPolicy(num_points=2), tol=1e-13).run(
+        {"theta": q0}, dt, dt * n_steps, 6, settings)
+    assert np.allclose(out.history.t, [0.0, 2 * dt, 4 * dt])
+    assert np.linalg.norm(out.history.q["theta"][1] - ref[1]) / np.linalg.norm(ref[1]) < 1e-9
+    assert np.linalg.norm(out.history.q["theta"][2] - ref[3]) / np.linalg.norm(ref[3]) < 1e-9
+    out = dae.TimeSteppingManager(static_settings, save_policy=dae.SaveNothingPolicy(), tol=1e-13).run({"theta": q0}, dt, dt, 6, settings)
+    assert out.history is None and out.num_accepted == 1
+    solver.clear_plan_cache()
+
+
 def test_time_stepping_manager_with_multigrid():
     from autopdex_b200 import dae, solver
     n, dt = 8, 0.1
