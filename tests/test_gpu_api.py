@@ -73,6 +73,44 @@ def test_cook_adaptive_load_stepping_golden():
     assert np.isclose(dofs.ravel() @ dofs.ravel(), 19390.35027108, rtol=1e-8, atol=0)   # reference golden value G2
 
 
+def test_cook_first_order_sensitivities_reproduce_the_reference_golden_values():
+    """SURVEY 8f N3 end to end on the reference's own numbers: tests/test_user_elem_impl_diff_and_adaptive_load_step.py
+    pins d(u.u)/dE = -216.0310416 and d(u.u)/dnu = -1859.43760286 (:152-164, jnp.allclose: rtol 1e-5) for the converged
+    Cook's membrane state, computed there by JAX AD through implicit_diff (forward: _root_jvp, implicit_diff.py:274-304;
+    reverse: _root_vjp, :139-183).  Here the linear solves those rules need run on the device (solver.tangent_solve) and the
+    parameter derivative of the residual, which JAX AD supplies in the reference, is a central difference of
+    assembler.assemble_residual:  forward  du/dp = -K^-1 dR/dp, dJ/dp = 2 u . du/dp;  reverse  dJ/dp = -(K^-T 2u) . dR/dp."""
+    from autopdex_b200 import assembler, solver
+    p, settings, static_settings = _cook_settings()
+    q0 = p["q0"]
+
+    def multiplier_settings(settings, multiplier):
+        settings["load multiplier"] = multiplier * q0
+        return settings
+
+    out = solver.adaptive_load_stepping(np.zeros(p["mask"].shape), settings, static_settings, multiplier_settings, False, None,
+                                        newton_tol=1e-10, tol=1e-13)
+    u, settings = out[0], dict(out[4])
+    assert np.isclose(out[1], 1.0) and np.isclose(u.ravel() @ u.ravel(), 19390.35027108, rtol=1e-8, atol=0)
+    free = ~p["mask"]
+
+    def dR_dp(key, h):
+        rp = assembler.assemble_residual(u, dict(settings, **{key: settings[key] + h}), static_settings)
+        rm = assembler.assemble_residual(u, dict(settings, **{key: settings[key] - h}), static_settings)
+        return np.where(free, (rp - rm) / (2 * h), 0.0)
+    lam = solver.tangent_solve(u, 2.0 * u, settings, static_settings, transpose=True, tol=1e-13)      # adjoint: one solve
+    for key, h, golden in (("youngs modulus", 1e-3, -216.0310416), ("poisson ratio", 1e-6, -1859.43760286)):
+        g = dR_dp(key, h)
+        du = -solver.tangent_solve(u, g, settings, static_settings, transpose=False, tol=1e-13)         # forward: one per parameter
+        forward = 2.0 * (u.ravel() @ du.ravel())
+        reverse = -(lam.ravel() @ g.ravel())
+        print("sensitivity %s: forward %.10f reverse %.10f reference golden %.10f" % (key, forward, reverse, golden))
+        assert np.isclose(forward, golden, rtol=2e-6, atol=0), (key, forward, golden)
+        assert np.isclose(reverse, golden, rtol=2e-6, atol=0), (key, reverse, golden)
+        assert np.isclose(forward, reverse, rtol=1e-9, atol=0)
+    solver.clear_plan_cache()
+
+
 def test_linear_solver_type_returns_mixed_vector():
     from autopdex_b200 import solver
     p, settings, static_settings = _cook_settings("bicgstab")
