@@ -73,9 +73,9 @@ def test_cook_adaptive_load_stepping_golden():
     assert np.isclose(dofs.ravel() @ dofs.ravel(), 19390.35027108, rtol=1e-8, atol=0)   # reference golden value G2
 
 
-def test_cook_first_order_sensitivities_reproduce_the_reference_golden_values():
+def test_cook_sensitivities_reproduce_the_reference_golden_values():
     """SURVEY 8f N3 end to end on the reference's own numbers: tests/test_user_elem_impl_diff_and_adaptive_load_step.py
-    pins d(u.u)/dE = -216.0310416 and d(u.u)/dnu = -1859.43760286 (:152-164, jnp.allclose: rtol 1e-5) for the converged
+    pins d(u.u)/dE = -216.0310416, d(u.u)/dnu = -1859.43760286 and the second derivatives (:152-164, jnp.allclose: rtol 1e-5) for the converged
     Cook's membrane state, computed there by JAX AD through implicit_diff (forward: _root_jvp, implicit_diff.py:274-304;
     reverse: _root_vjp, :139-183).  Here the linear solves those rules need run on the device (solver.tangent_solve) and the
     parameter derivative of the residual, which JAX AD supplies in the reference, is a central difference of
@@ -108,6 +108,29 @@ def test_cook_first_order_sensitivities_reproduce_the_reference_golden_values():
         assert np.isclose(forward, golden, rtol=2e-6, atol=0), (key, forward, golden)
         assert np.isclose(reverse, golden, rtol=2e-6, atol=0), (key, reverse, golden)
         assert np.isclose(forward, reverse, rtol=1e-9, atol=0)
+
+    # second order (the test's remaining golden values, :157-160: 4.17157824, -51.42695148 twice, -45854.7002203): central
+    # differences of the adjoint first-order sensitivities between re-converged neighbouring parameter values
+    steps = {"youngs modulus": 1e-3, "poisson ratio": 1e-6}
+
+    def gradient(st):
+        uu, info = solver.solver(u, st, static_settings, newton_tol=1e-11, tol=1e-14)
+        assert not info[2]
+        adj = solver.tangent_solve(uu, 2.0 * uu, st, static_settings, transpose=True, tol=1e-14)
+        g = {}
+        for key, h in steps.items():
+            rp = assembler.assemble_residual(uu, dict(st, **{key: st[key] + h}), static_settings)
+            rm = assembler.assemble_residual(uu, dict(st, **{key: st[key] - h}), static_settings)
+            g[key] = -(adj.ravel() @ np.where(free, (rp - rm) / (2 * h), 0.0).ravel())
+        return g
+    golden2 = {("youngs modulus", "youngs modulus"): 4.17157824, ("youngs modulus", "poisson ratio"): -51.42695148,
+               ("poisson ratio", "youngs modulus"): -51.42695148, ("poisson ratio", "poisson ratio"): -45854.7002203}
+    for key, h in (("youngs modulus", 0.05), ("poisson ratio", 1e-4)):
+        gp, gm = gradient(dict(settings, **{key: settings[key] + h})), gradient(dict(settings, **{key: settings[key] - h}))
+        for other in steps:
+            second = (gp[other] - gm[other]) / (2 * h)
+            print("second-order sensitivity d2/d(%s)d(%s): %.8f reference golden %.8f" % (key, other, second, golden2[key, other]))
+            assert np.isclose(second, golden2[key, other], rtol=5e-6, atol=0), (key, other, second)   # the reference: rtol 1e-5
     solver.clear_plan_cache()
 
 
