@@ -28,6 +28,7 @@ SLOW = [
     "tests/test_gpu_api.py::test_newton_maxiter_flags_divergence_like_reference",
     "tests/test_gpu_api.py::test_damped_newton_iteration_count_matches_oracle",
     "tests/test_gpu_api.py::test_tangent_solve_matches_reference_sensitivity_solve",
+    "tests/test_gpu_api.py::test_cook_sensitivities_reproduce_the_reference_golden_values",
     "tests/test_zz_gpu_multigrid.py::test_poisson_hex_multigrid_matches_oracle",
     "tests/test_zz_gpu_multigrid.py::test_neo_hooke_brick_multigrid_newton_counts",
     "tests/test_zz_gpu_r02_dae.py::test_verbose_prints_one_line_per_newton_iteration",
