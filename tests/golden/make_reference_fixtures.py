@@ -459,7 +459,40 @@ def case_dae_control(out):
         out["dae_ctrl_%s" % tag] = np.array(rows)
 
 
-CASES = {"dae_rules": case_dae_rules, "dae_control": case_dae_control, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
+LOAD_STEP_SCRIPTS = {
+    # (newton steps, diverged) per call of the Newton solver, repeated from the last entry on
+    "smooth": [(6, False)],
+    "halving": [(5, False), (30, True), (30, True), (4, False), (9, False), (30, True), (3, False)],
+    "stall": [(30, True)],                     # never converges: increments shrink below min_increment
+    "slow": [(12, False)],                     # more iterations than the target: increments shrink
+}
+
+
+def case_load_stepping(out):
+    """solver.adaptive_load_stepping (solver.py:155-457) driven by a scripted Newton solver: the sequence of load
+    multipliers it tries, the multipliers it accepts, and the final carry -- the rollback / halving / capping control flow
+    of :296-379 as the reference's own code executes it."""
+    from autopdex import solver as rsolver
+    real = rsolver.solver
+    for tag, script in LOAD_STEP_SCRIPTS.items():
+        calls = []
+
+        def fake_solver(dofs, settings, static_settings, newton_tol=1e-8, **kwargs):
+            steps, div = script[min(len(calls), len(script) - 1)]
+            calls.append(float(settings["load multiplier"]))
+            return dofs + 1.0, (jnp.asarray(steps), jnp.asarray(1e-12), jnp.asarray(div))
+        rsolver.solver = fake_solver
+        try:
+            st = flax.core.FrozenDict({"solver type": "newton", "verbose": -1})
+            carry = rsolver.adaptive_load_stepping(jnp.zeros(3), {"load multiplier": 0.0}, st, path_dependent=True,
+                                                   implicit_diff_mode=None, max_load_steps=1000)
+        finally:
+            rsolver.solver = real
+        out["loadstep_%s_tried" % tag] = np.array(calls)
+        out["loadstep_%s_final" % tag] = np.array([float(A(carry[0])[0]), float(carry[1]), float(carry[2])])
+
+
+CASES = {"dae_rules": case_dae_rules, "load_stepping": case_load_stepping, "dae_control": case_dae_control, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
          "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "elements_more": case_elements_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 

@@ -365,3 +365,29 @@ def test_save_policies_and_step_size_controllers_against_reference_classes():
             st = ctrl.check_accept(st, conv, -1)
             rows.append([st["step_scaler"], st["dt"], float(st["accept"]), float(st["interrupt"])])
         assert np.allclose(np.array(rows), FIX["dae_ctrl_%s" % tag], rtol=1e-14, atol=0), tag
+
+
+@pytest.mark.parametrize("tag", ["smooth", "halving", "stall", "slow"])
+def test_adaptive_load_stepping_control_flow_against_reference_run(tag, monkeypatch):
+    """solver.adaptive_load_stepping (rollback on divergence, halving, growth by the Newton count, capping at
+    max_multiplier / max_increment, stop below min_increment: solver.py:296-379) against the reference's own function
+    driven by the same scripted Newton solver (fixture case `load_stepping`): identical sequences of tried multipliers and
+    the same final carry."""
+    from autopdex_b200 import solver
+    script = {"smooth": [(6, False)],
+              "halving": [(5, False), (30, True), (30, True), (4, False), (9, False), (30, True), (3, False)],
+              "stall": [(30, True)], "slow": [(12, False)]}[tag]
+    calls = []
+
+    def fake_solver(dofs, settings, static_settings, newton_tol=1e-8, **kwargs):
+        steps, div = script[min(len(calls), len(script) - 1)]
+        calls.append(float(settings["load multiplier"]))
+        return dofs + 1.0, (steps, 1e-12, div)
+    monkeypatch.setattr(solver, "solver", fake_solver)
+    st = {"solver type": "newton", "solver backend": "b200", "solver": "cg", "verbose": -1, "assembling mode": ("user element",),
+          "model": (None,)}
+    monkeypatch.setattr(solver, "_Config", lambda s: type("C", (), {"solver_type": "newton", "verbose": -1})())
+    carry = solver.adaptive_load_stepping(np.zeros(3), {"load multiplier": 0.0}, st, path_dependent=True, implicit_diff_mode=None)
+    tried, final = FIX["loadstep_%s_tried" % tag], FIX["loadstep_%s_final" % tag]
+    assert len(calls) == len(tried) and np.allclose(calls, tried, rtol=1e-14, atol=0)
+    assert np.allclose([carry[0][0], carry[1], carry[2]], final, rtol=1e-13, atol=1e-300)
