@@ -151,7 +151,8 @@ class FakeCustomJVP:
         tagged = [i for i, a in enumerate(args) if isinstance(a, XPoint) and a.tangent is not None]
         if tagged:
             prim = tuple(np.asarray(a).view(JArray) if isinstance(a, np.ndarray) else a for a in args)
-            tang = tuple(J(np.asarray(args[i].tangent)) if i in tagged else (None if i > 0 else 0 * np.asarray(a))
+            tang = tuple(J(np.asarray(args[i].tangent)) if i in tagged else
+                         (J(np.zeros_like(np.asarray(a, dtype=float))) if (i == 0 or isinstance(a, np.ndarray)) else None)
                          for i, a in enumerate(args))
             tang = tuple(t if t is not None else None for t in tang)
             _, t_out = self.rule(prim, tang)
@@ -368,8 +369,25 @@ def _fori_loop(lo, hi, body, carry):
     return carry
 
 
-def _cond(pred, tf, ff, *ops):
+def _cond(pred, tf, ff, *ops, **kw):
+    if "operand" in kw:                       # the older keyword form jax.lax.cond(pred, tf, ff, operand=x)
+        ops = (kw["operand"],)
     return tf(*ops) if bool(pred) else ff(*ops)
+
+
+def _jvp(fun, primals, tangents):
+    """jax.jvp for one array argument by a central difference along the tangent (dae.newton_solver builds its dense
+    Jacobian column by column this way; exact to rounding for the linear test systems it is used on here)."""
+    (x,), (v,) = primals, tangents
+    x, v = np.asarray(x, dtype=float), np.asarray(v, dtype=float)
+    h = 1e-6 * max(1.0, float(np.abs(x).max()))
+    fp, fm = np.asarray(fun(J(x + h * v))), np.asarray(fun(J(x - h * v)))
+    return J(np.asarray(fun(J(x)))), J((fp - fm) / (2 * h))
+
+
+def _custom_root(f, initial_guess, solve, tangent_solve, has_aux=False):
+    """jax.lax.custom_root: the forward pass is solve(f, initial_guess); the implicit-differentiation rule is not needed."""
+    return solve(f, initial_guess)
 
 
 def _lax_map(f, xs, batch_size=None):
@@ -417,7 +435,7 @@ def install():
     jax.jacrev = jac
     jax.grad = jac
     jax.hessian = lambda f, **kw: jac(jac(f, **kw), **kw)
-    jax.jvp = None
+    jax.jvp = _jvp
     jax.vjp = None
     jax.linearize = None
     jax.custom_jvp = FakeCustomJVP
@@ -431,6 +449,7 @@ def install():
     lax = types.ModuleType("jax.lax")
     lax.while_loop, lax.fori_loop, lax.cond, lax.map = _while_loop, _fori_loop, _cond, _lax_map
     lax.stop_gradient = lambda x: x
+    lax.custom_root = _custom_root
     jax.lax = lax
     tree = types.ModuleType("jax.tree")
     tree.map = tree_map

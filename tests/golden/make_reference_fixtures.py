@@ -492,7 +492,38 @@ def case_load_stepping(out):
         out["loadstep_%s_final" % tag] = np.array([float(A(carry[0])[0]), float(carry[1]), float(carry[2])])
 
 
-CASES = {"dae_rules": case_dae_rules, "load_stepping": case_load_stepping, "dae_control": case_dae_control, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
+DAE_MANAGER_SCHEMES = ("backward_euler", "bdf2", "am2", "dirk2", "dirk3")
+
+
+def case_dae_manager(out):
+    """The reference's TimeSteppingManager.run (dae.py:2087-2268: stage loop, history roll, integrator updates,
+    constrained dofs in dae.newton_solver) EXECUTED on the semi-discrete heat conduction system M q_t + K q = F of
+    tests/test_zz_gpu_r02_dae._settings(2) (27 nodes, Dirichlet face x = 0 with non-zero values) given as a dense
+    'dae' callable: the trajectories the b200 backend must reproduce through its device solves."""
+    from autopdex import dae
+    from tests import test_zz_gpu_r02_dae as T
+    coords, K, M, F, mask, values, res, settings = T._settings(2)
+    Kd, Md = jnp.asarray(K.toarray()), jnp.asarray(M.toarray())
+    q0 = 0.3 * np.cos(coords[:, 1])
+    dt, n_steps = 0.05, 3
+
+    def dae_fun(q_fun, t, settings):
+        return Md @ jax.jacfwd(q_fun)(t)["theta"] + Kd @ q_fun(t)["theta"] - jnp.asarray(F)
+    tight = lambda *a, **k: dae.newton_solver(*a, **dict(k, atol=1e-12, max_iter=10))
+    for scheme in DAE_MANAGER_SCHEMES:
+        integ = (dae.BackwardEuler() if scheme == "backward_euler" else dae.BackwardDiffFormula(int(scheme[3:])) if scheme.startswith("bdf")
+                 else dae.AdamsMoulton(int(scheme[2:])) if scheme.startswith("am") else dae.DiagonallyImplicitRungeKutta(int(scheme[4:])))
+        st = flax.core.FrozenDict({"dae": dae_fun, "time integrators": {"theta": integ}, "verbose": -1, "implicit diff mode": None})
+        mgr = dae.TimeSteppingManager(st, root_solver=tight, save_policy=dae.SaveAllPolicy())
+        state = mgr.run({"theta": jnp.asarray(q0)}, dt, dt * n_steps, n_steps,
+                        {"current time": 0.0, "dirichlet dofs": {"theta": jnp.asarray(mask)},
+                         "dirichlet conditions": {"theta": jnp.asarray(values)}})
+        assert int(state.num_accepted) == n_steps
+        out["dae_manager_%s_q" % scheme] = A(state.history.q["theta"])[:n_steps + 1]
+        out["dae_manager_%s_t" % scheme] = A(state.history.t)[:n_steps + 1]
+
+
+CASES = {"dae_rules": case_dae_rules, "dae_manager": case_dae_manager, "load_stepping": case_load_stepping, "dae_control": case_dae_control, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
          "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "elements_more": case_elements_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 

@@ -71,6 +71,11 @@ def test_root_iteration_controller_host(fake):
     dae_cases.test_root_iteration_controller_grows_and_rejects_like_the_reference()
 
 
+@pytest.mark.parametrize("scheme", ["backward_euler", "bdf2", "am2", "dirk2", "dirk3"])
+def test_time_stepping_manager_against_reference_manager_host(fake, scheme):
+    dae_cases.test_time_stepping_manager_reproduces_trajectories_of_the_reference_manager(scheme)
+
+
 def test_save_policies_and_postprocessing_host(fake):
     dae_cases.test_save_policies_and_postprocessing_mirror_the_reference()
 

@@ -201,6 +201,28 @@ def test_root_iteration_controller_grows_and_rejects_like_the_reference():
     solver.clear_plan_cache()
 
 
+@pytest.mark.parametrize("scheme", ["backward_euler", "bdf2", "am2", "dirk2", "dirk3"])
+def test_time_stepping_manager_reproduces_trajectories_of_the_reference_manager(scheme):
+    """Against the REFERENCE'S OWN TimeSteppingManager.run (dae.py:2087-2268), executed by
+    tests/golden/make_reference_fixtures.py (case `dae_manager`) on the same semi-discrete system given as a dense 'dae'
+    callable: stage loop, history roll, integrator updates and the constrained dofs of dae.newton_solver are the
+    reference's code there, assembly + Newton + Krylov are the device's here."""
+    import os
+    from autopdex_b200 import dae, solver
+    fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_fixtures.npz"))
+    coords, K, M, F, mask, values, res, settings = _settings(2)
+    static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": _integrator(scheme)},
+                       "solver backend": "b200", "solver": "cg", "type of preconditioner": "jacobi", "verbose": -1}
+    q0 = 0.3 * np.cos(coords[:, 1])
+    save = dae.SaveAllPolicy()
+    out = dae.TimeSteppingManager(static_settings, save_policy=save, atol=1e-12, tol=1e-14).run({"theta": q0}, 0.05, 0.15, 3, settings)
+    ref_q, ref_t = fix["dae_manager_%s_q" % scheme], fix["dae_manager_%s_t" % scheme]
+    assert out.num_accepted == 3 and np.allclose(out.history.t[:4], ref_t, rtol=1e-14)
+    for k in range(4):
+        assert np.linalg.norm(out.history.q["theta"][k] - ref_q[k]) / np.linalg.norm(ref_q[k]) < 1e-9, (scheme, k)
+    solver.clear_plan_cache()
+
+
 def test_save_policies_and_postprocessing_mirror_the_reference():
     """dae.SaveAllPolicy / SaveEquidistantPolicy / SaveNothingPolicy (dae.py:1160-1311) and the user data of
     `postprocessing_fun` (dae.py:2140, 2188): pre-allocated arrays of max_steps + 1 rows padded with NaN, equidistant
