@@ -523,7 +523,29 @@ def case_dae_manager(out):
         out["dae_manager_%s_t" % scheme] = A(state.history.t)[:n_steps + 1]
 
 
-CASES = {"dae_rules": case_dae_rules, "dae_manager": case_dae_manager, "load_stepping": case_load_stepping, "dae_control": case_dae_control, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
+def utility_inputs():
+    rng = np.random.default_rng(21)
+    d = {"u": rng.normal(size=(5, 2)), "p": rng.normal(size=(5,)), "T": rng.normal(size=(3, 1))}
+    flat = rng.normal(size=5 * 2 + 5 + 3)
+    nodes = rng.random(6) < 0.5
+    return d, flat, nodes
+
+
+def case_utility(out):
+    """utility.dict_flatten / reshape_as / dict_zeros_like / dof_select (utility.py:82-199, 448-462) on a three-field dict
+    (insertion order u, p, T -- the order the reference concatenates in)."""
+    d, flat, nodes = utility_inputs()
+    dj = {k: jnp.asarray(v) for k, v in d.items()}
+    out["util_flat"] = A(utility.dict_flatten(dj))
+    back = utility.reshape_as(jnp.asarray(flat), dj)
+    for k in d:
+        out["util_reshape_" + k] = A(back[k])
+        out["util_zeros_" + k] = A(utility.dict_zeros_like(dj)[k])
+    out["util_dofsel_list"] = A(utility.dof_select(jnp.asarray(nodes), jnp.asarray([True, False, True])))
+    out["util_dofsel_bool"] = A(utility.dof_select(jnp.asarray(nodes), True))
+
+
+CASES = {"dae_rules": case_dae_rules, "utility": case_utility, "dae_manager": case_dae_manager, "load_stepping": case_load_stepping, "dae_control": case_dae_control, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
          "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "elements_more": case_elements_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 

@@ -391,3 +391,21 @@ def test_adaptive_load_stepping_control_flow_against_reference_run(tag, monkeypa
     tried, final = FIX["loadstep_%s_tried" % tag], FIX["loadstep_%s_final" % tag]
     assert len(calls) == len(tried) and np.allclose(calls, tried, rtol=1e-14, atol=0)
     assert np.allclose([carry[0][0], carry[1], carry[2]], final, rtol=1e-13, atol=1e-300)
+
+
+def test_dict_utilities_against_reference_run():
+    """autopdex_b200.utility.dict_flatten / reshape_as / dict_zeros_like / dof_select against the reference's functions
+    (utility.py:82-199, 448-462; fixture case `utility`): key order, shapes and values identical."""
+    from autopdex_b200 import utility
+    rng = np.random.default_rng(21)
+    d = {"u": rng.normal(size=(5, 2)), "p": rng.normal(size=(5,)), "T": rng.normal(size=(3, 1))}
+    flat = rng.normal(size=5 * 2 + 5 + 3)
+    nodes = rng.random(6) < 0.5
+    assert np.array_equal(utility.dict_flatten(d), FIX["util_flat"])
+    back, zeros = utility.reshape_as(flat, d), utility.dict_zeros_like(d)
+    assert list(back.keys()) == list(d.keys())
+    for k in d:
+        assert back[k].shape == FIX["util_reshape_" + k].shape and np.array_equal(back[k], FIX["util_reshape_" + k])
+        assert zeros[k].shape == FIX["util_zeros_" + k].shape and not zeros[k].any()
+    assert np.array_equal(utility.dof_select(nodes, [True, False, True]), FIX["util_dofsel_list"])
+    assert np.array_equal(utility.dof_select(nodes, True), FIX["util_dofsel_bool"])
