@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("APDX_LIB") or os.path.join(_HERE, "lib", "libapdx_b20
 APDX_PARAM = {"coefficient": 0, "source": 1, "youngs_modulus": 2, "poisson_ratio": 3, "body_load": 4, "traction": 5}
 APDX_MODEL = {"poisson_potential": 0, "poisson_weak": 1, "linear_elasticity": 2, "neo_hooke": 3, "neumann": 4,
               "capacity": 5, "pattern_only": 6}
-APDX_MODE = {None: 0, "plain strain": 1, "plain stress": 2, "3d": 3}
+APDX_MODE = {None: 0, "plain strain": 1, "plain stress": 2, "3d": 3, "lame": 4}
 APDX_KIND = {"domain": 0, "surface": 1, "intpoint": 2}
 APDX_LAYOUT = {"const": 0, "per_gp": 1, "per_row_gp": 2}
 APDX_KRYLOV = {"cg": 0, "bicgstab": 1}

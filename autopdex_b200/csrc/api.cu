@@ -306,7 +306,7 @@ static int validate_set(const apdx_set_desc &d, int dim, int nf, int idx) {
   if (scalar) APDX_REQUIRE(nf == 1, APDX_ERR_UNSUPPORTED, "set %d: scalar model needs one dof per node, got %d", idx, nf);
   if (vector) APDX_REQUIRE(nf == dim, APDX_ERR_UNSUPPORTED, "set %d: elasticity model needs nf == dim (%d), got %d", idx, dim, nf);
   if (vector) {
-    bool ok = (dim == 3 && d.mode == APDX_MODE_3D) ||
+    bool ok = (dim == 3 && d.mode == APDX_MODE_3D) || (d.mode == APDX_MODE_LAME && d.model == APDX_MODEL_LINEAR_ELASTICITY) ||
               (dim == 2 && (d.mode == APDX_MODE_PLAIN_STRAIN || (d.mode == APDX_MODE_PLAIN_STRESS && d.model == APDX_MODEL_LINEAR_ELASTICITY)));
     APDX_REQUIRE(ok, APDX_ERR_UNSUPPORTED, "set %d: elasticity mode %d not available for dim %d / this model", idx, d.mode, dim);
   }

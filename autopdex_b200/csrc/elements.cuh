@@ -69,7 +69,7 @@ __device__ __forceinline__ void lin_el_constants(int mode, double Em, double nu,
   } else if (mode == APDX_MODE_PLAIN_STRESS) {
     double co = Em / (1.0 - nu * nu);
     c11 = co; c12 = co * nu; c33 = co * (1.0 - nu) / 2.0;
-  } else {
+  } else {   // APDX_MODE_3D, APDX_MODE_LAME: c11 = lam + 2 mu, c12 = lam, c33 = mu
     double co = Em / (1.0 + nu);
     double c1 = 1.0 - 2.0 * nu;
     c11 = co * (1.0 - nu) / c1; c12 = co * nu / c1; c33 = co * 0.5;

@@ -72,11 +72,25 @@ def neo_hooke(F, param):
     raise RuntimeError("neo_hooke is evaluated on the device by the b200 backend")
 
 
+def linear_elastic_strain_energy(F, param):
+    """Small-strain energy psi = lam/2 tr(eps)^2 + mu eps:eps, eps = sym(F - 1) (models.py:1167-1185).  Token: inside
+    hyperelastic_steady_state_weak its first Piola-Kirchhoff stress is sigma = lam tr(eps) 1 + 2 mu eps, i.e. the linear
+    elasticity kernel with the isotropic tensor in the mesh's dimension ('plain strain': eps_33 = 0)."""
+    raise RuntimeError("linear_elastic_strain_energy is evaluated on the device by the b200 backend")
+
+
 def hyperelastic_steady_state_weak(strain_energy_fun, youngs_mod_fun, poisson_ratio_fun, mode, volume_load_fun=None):
-    if getattr(strain_energy_fun, "__name__", None) != "neo_hooke":
-        _unsupported("strain energy %r (only models.neo_hooke)" % (strain_energy_fun,))
+    energy = getattr(strain_energy_fun, "__name__", None)
+    if energy not in ("neo_hooke", "linear_elastic_strain_energy"):
+        _unsupported("strain energy %r (only models.neo_hooke and models.linear_elastic_strain_energy)" % (strain_energy_fun,))
     if mode not in ("plain strain", "3d"):
         raise AssertionError("Hyperelastic model supports only 'plain strain' and '3d' modes.")
+    if energy == "linear_elastic_strain_energy":
+        # device mode 'lame' (APDX_MODE_LAME) = the isotropic tensor lam 1x1 + 2 mu I_sym in the mesh's dimension; on a 2-D
+        # mesh that is the customary plane-strain matrix -- not the one of linear_elasticity_weak 'plain strain', whose
+        # shear entry the reference doubles (models.py:570-577)
+        return WeakForm("linear_elasticity", {"youngs_modulus": youngs_mod_fun, "poisson_ratio": poisson_ratio_fun,
+                                              "body_load": volume_load_fun}, "lame")
     return WeakForm("neo_hooke", {"youngs_modulus": youngs_mod_fun, "poisson_ratio": poisson_ratio_fun,
                                   "body_load": volume_load_fun}, mode)
 

@@ -62,7 +62,12 @@ enum {
                                        to 64, no shape tables, APDX_SET_DOMAIN. */
 };
 
-enum { APDX_MODE_NONE = 0, APDX_MODE_PLAIN_STRAIN = 1, APDX_MODE_PLAIN_STRESS = 2, APDX_MODE_3D = 3 };
+enum { APDX_MODE_NONE = 0, APDX_MODE_PLAIN_STRAIN = 1, APDX_MODE_PLAIN_STRESS = 2, APDX_MODE_3D = 3,
+       /* linear elasticity with the isotropic tensor lam 1x1 + 2 mu I_sym in the mesh's dimension: the first Piola-Kirchhoff
+        * stress of models.linear_elastic_strain_energy inside hyperelastic_steady_state_weak (models.py:917-1000, 1167-1185);
+        * in 2-D the customary plane-strain matrix, which differs from APDX_MODE_PLAIN_STRAIN = the matrix of
+        * linear_elasticity_weak with its doubled shear entry (models.py:570-577) */
+       APDX_MODE_LAME = 4 };
 
 /* run-time parameters of a set (values of the Python coefficient callables, evaluated by the host) */
 enum {

@@ -86,6 +86,12 @@ def elasticity_matrix(mode, Em, nu):
         c2, c3, c4 = co * (1 - nu) / c1, co * nu / c1, co * 0.5
         C = np.array([[c2, c3, c3, z, z, z], [c3, c2, c3, z, z, z], [c3, c3, c2, z, z, z],
                       [z, z, z, c4, z, z], [z, z, z, z, c4, z], [z, z, z, z, z, c4]])
+    elif mode == "lame 2d":
+        # P = d psi/dF of models.linear_elastic_strain_energy (models.py:1167-1185) inside hyperelastic_steady_state_weak
+        # 'plain strain' (models.py:917-1000): sigma = lam tr(eps) 1 + 2 mu eps with eps_33 = 0 -- the customary plane-strain
+        # matrix (shear mu on the engineering shear), NOT the matrix of linear_elasticity_weak above
+        lam, mu = Em * nu / ((1 + nu) * (1 - 2 * nu)), Em / (2 * (1 + nu))
+        C = np.array([[lam + 2 * mu, lam, z], [lam, lam + 2 * mu, z], [z, z, mu]])
     else:
         raise ValueError(mode)
     return np.moveaxis(C, (0, 1), (-2, -1))            # (..., nv, nv)
@@ -162,7 +168,9 @@ def point_contribution(model, N, G, s, u, g, settings, want_tangent=True):
     b = _par(model, "body_load", n, g, ncomp=nf) if model.get("body_load") is not None else None
     if name == "linear_elasticity":
         # sigma_voigt . deps_voigt - b . du   (models.py:605-633)
-        C = elasticity_matrix(model["mode"], Em, nu)
+        # mode 'lame': the isotropic tensor lam 1x1 + 2 mu I_sym in the mesh's dimension (3-D: identical to '3d')
+        mode = model["mode"] if model["mode"] != "lame" else ("3d" if dim == 3 else "lame 2d")
+        C = elasticity_matrix(mode, Em, nu)
         B = _bmatrix(G)
         K = s[:, None, None] * np.einsum("npi,npq,nqj->nij", B, C, B)
         R = np.einsum("nij,nj->ni", K, u.reshape(n, nen * nf))

@@ -545,7 +545,26 @@ def case_utility(out):
     out["util_dofsel_bool"] = A(utility.dof_select(jnp.asarray(nodes), True))
 
 
-CASES = {"dae_rules": case_dae_rules, "utility": case_utility, "dae_manager": case_dae_manager, "load_stepping": case_load_stepping, "dae_control": case_dae_control, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
+def case_hyper_linear(out):
+    """hyperelastic_steady_state_weak with models.linear_elastic_strain_energy (models.py:917-1000, 1167-1185) as user
+    elements: 'plain strain' on two Q1 quads, '3d' on one distorted hex8."""
+    E = lambda x, settings: settings["youngs modulus"]
+    nu = lambda x, settings: settings["poisson ratio"]
+    mat = {"youngs modulus": 100.0, "poisson ratio": 0.3}
+    cq, eq = mesher.structured_mesh((2, 1), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "quad")
+    # (no volume load: models.py:996-997 takes jnp.dot(b, virt_u) with virt_u the test FUNCTION -- the reference cannot
+    # evaluate a hyperelastic weak form with a volume load at all)
+    w2 = models.hyperelastic_steady_state_weak(models.linear_elastic_strain_energy, E, nu, "plain strain")
+    element_case(out, "hyperlin_plain_strain", A(cq), A(eq), 2, w2, spaces.fem_iso_line_quad_brick,
+                 seeder.gauss_legendre_nd(dimension=2, order=2), settings_extra=mat, dofs_scale=0.05)
+    cube2 = [[0, 0, 0], [1, 0, 0], [1.1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1.2], [1, 1, 1], [0, 1, 1]]
+    cb, eb = mesher.structured_mesh((1, 1, 2), cube2, "brick")
+    w3 = models.hyperelastic_steady_state_weak(models.linear_elastic_strain_energy, E, nu, "3d")
+    element_case(out, "hyperlin_3d", A(cb), A(eb)[:1], 3, w3, spaces.fem_iso_line_quad_brick,
+                 seeder.gauss_legendre_nd(dimension=3, order=2), settings_extra=mat, dofs_scale=0.05)
+
+
+CASES = {"dae_rules": case_dae_rules, "hyper_linear": case_hyper_linear, "utility": case_utility, "dae_manager": case_dae_manager, "load_stepping": case_load_stepping, "dae_control": case_dae_control, "tables": case_tables, "indices_dict": case_indices_dict, "two_fields": case_two_fields, "readme3": lambda o: readme_case(3, o, "readme3"),
          "readme5": lambda o: readme_case(5, o, "readme5"), "elements": case_elements, "potential3d": case_potential3d, "potential_more": case_potential_more, "elements_more": case_elements_more, "sparse": case_sparse_compiled, "simplex": case_simplex_direct,
          "newton": case_newton_semantics}
 

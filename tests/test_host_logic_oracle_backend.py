@@ -76,6 +76,13 @@ def test_time_stepping_manager_against_reference_manager_host(fake, scheme):
     dae_cases.test_time_stepping_manager_reproduces_trajectories_of_the_reference_manager(scheme)
 
 
+@pytest.mark.parametrize("tag", ["hyperlin_plain_strain", "hyperlin_3d"])
+def test_linear_elastic_strain_energy_route_host(fake, tag):
+    from tests import test_zz_gpu_r02_hyper_linear as hl
+    hl.test_linear_elastic_strain_energy_route_against_reference_run(tag)
+    hl.test_other_strain_energies_are_rejected()
+
+
 def test_save_policies_and_postprocessing_host(fake):
     dae_cases.test_save_policies_and_postprocessing_mirror_the_reference()
 

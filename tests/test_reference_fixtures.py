@@ -201,14 +201,23 @@ def _element_problem(tag):
         c, e = om.structured_mesh((2, 1), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "tri")
         return [dict(kind="domain", etype="tri3", conn=e, nf=2, gp=(FIX["tri_rule_2_x"], FIX["tri_rule_2_w"]),
                      model=dict(name="linear_elasticity", mode="plain stress", body_load=np.array([0.3, -1.0]), **mat))], c, 2
+    if tag in ("hyperlin_plain_strain", "hyperlin_3d"):      # generator: case_hyper_linear
+        if tag == "hyperlin_3d":
+            c, e = om.structured_mesh((1, 1, 2), cube2, "brick")
+            return [dict(kind="domain", etype="hex8", conn=e[:1], nf=3, gp=oq.gauss_legendre_nd(3, 2),
+                         model=dict(name="linear_elasticity", mode="lame", **mat))], c, 3
+        c, e = om.structured_mesh((2, 1), [[0, 0], [2, 0], [2.5, 1.5], [0, 1]], "quad")
+        return [dict(kind="domain", etype="quad4", conn=e, nf=2, gp=oq.gauss_legendre_nd(2, 2),
+                     model=dict(name="linear_elasticity", mode="lame", **mat))], c, 2
     raise KeyError(tag)
 
 
 ELEMENT_TAGS = ["cook_q9", "hex8_neo", "linel_plain_strain", "linel_plain_stress", "linel_3d", "tri6_neo"]
 ELEMENT_TAGS_MORE = ["quad4_neo_line2", "tet4_neo_tri3", "tri3_linel"]     # session 3: GPU half in test_zz_gpu_first_run.py
+ELEMENT_TAGS_HYPERLIN = ["hyperlin_plain_strain", "hyperlin_3d"]           # GPU half in test_zz_gpu_r02_hyper_linear.py
 
 
-@pytest.mark.parametrize("tag", ELEMENT_TAGS + ELEMENT_TAGS_MORE)
+@pytest.mark.parametrize("tag", ELEMENT_TAGS + ELEMENT_TAGS_MORE + ELEMENT_TAGS_HYPERLIN)
 def test_user_elements_against_reference_run(tag):
     if tag + "_R" not in FIX:
         pytest.skip("fixture %s not generated yet" % tag)
