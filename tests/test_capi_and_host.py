@@ -120,6 +120,19 @@ def test_reference_closures_are_recognised_by_qualname():
     cfg = solver.validate(_static(model=(ref_elem,), solver="bicgstab"))
     assert cfg.sets[0][1].weak.name == "neo_hooke"
 
+    def linear_elastic_strain_energy(F, param):        # the reference's small-strain energy (models.py:1167-1185)
+        raise AssertionError("must not be called")
+    lin = models.recognise(isoparametric_domain_element_galerkin(
+        hyperelastic_steady_state_weak(linear_elastic_strain_energy, E, nu, "plain strain"), fem_iso_line_quad_brick,
+        *seeder.gauss_legendre_nd(2, 2)))
+    assert lin.weak.name == "linear_elasticity" and lin.weak.mode == "lame"       # the isotropic tensor, not linear_elasticity_weak's
+
+    def isochoric_neo_hooke(F, mu):
+        raise AssertionError("must not be called")
+    with pytest.raises(ValueError, match="strain energy"):
+        models.recognise(isoparametric_domain_element_galerkin(hyperelastic_steady_state_weak(isochoric_neo_hooke, E, nu, "3d"),
+                                                               fem_iso_line_quad_brick, *seeder.gauss_legendre_nd(3, 2)))
+
 
 def test_callable_evaluation_reference_vs_physical_points():
     pts = np.random.default_rng(0).uniform(size=(100, 2))
