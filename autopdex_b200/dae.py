@@ -16,6 +16,10 @@ capacity kernels with `time increment` = -1/a and `dofs n` = -b/a: the capacity 
 -c/dt_eff N_i N_j (theta - theta_n,eff).  Assembly, the Newton loop (dae.newton_solver semantics: residual tolerance
 `atol`, at most `max_iter` updates) and the Krylov solve run on the device; the plan (pattern, index maps, multigrid
 hierarchy if asked for) is built once and reused by every stage of every step.
+One difference in the Newton loop: the device runs solver.damped_newton's loop (solver.py:837-948), which also declares a
+step diverged when the residual norm grows by more than 10x after the second iteration; dae.newton_solver (dae.py:1580-1708)
+has no such rule and would keep iterating up to max_iter.  Both report the step as not converged unless the residual
+norm falls below `atol`; the iteration counts of converging steps are equal (linear problems: 1).
 Step sizes: ConstantStepSizeController (dae.py:1474-1497) or RootIterationController (:1509-1573: proportional control on
 the Newton iteration count, failed steps rejected and repeated with half the step), with the accept / reject / interrupt
 logic of TimeSteppingManager.run (:2150-2249).
