@@ -330,7 +330,8 @@ class TimeSteppingManager:
                              "(models.mixed_reference_domain_residual_time)")
 
     def run(self, dofs, dt0, t_max, num_time_steps, settings=None):
-        """dae.TimeSteppingManager.run (dae.py:2087-2240) with a constant step size."""
+        """dae.TimeSteppingManager.run (dae.py:2087-2268): at most `num_time_steps` attempted steps (accepted + rejected) up to
+        t_max; returns the final state, the updated settings, the save policy's history and the step statistics."""
         settings = dict(settings if settings is not None else {"current time": 0.0})
         (key, integ), = self.integrators.items()
         if list(dofs.keys()) != [key]:
