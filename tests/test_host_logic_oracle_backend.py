@@ -81,6 +81,7 @@ def test_linear_elastic_strain_energy_route_host(fake, tag):
     from tests import test_zz_gpu_r02_hyper_linear as hl
     hl.test_linear_elastic_strain_energy_route_against_reference_run(tag)
     hl.test_other_strain_energies_are_rejected()
+    hl.test_newton_solve_with_the_lame_mode_matches_oracle("cg")
 
 
 def test_save_policies_and_postprocessing_host(fake):

@@ -43,3 +43,28 @@ def test_other_strain_energies_are_rejected():
         return 0.0
     with pytest.raises(ValueError, match="strain energy"):
         models.hyperelastic_steady_state_weak(isochoric_neo_hooke, lambda x: 1.0, lambda x: 0.3, "3d")
+
+
+@pytest.mark.parametrize("krylov", ["cg", "bicgstab"])
+def test_newton_solve_with_the_lame_mode_matches_oracle(krylov):
+    """The whole path (assembly, symmetric sliced-ELL matrix, Jacobi-Krylov, Newton) for the new material mode: a clamped
+    plane-strain membrane under a body load (an extension: the reference cannot evaluate a hyperelastic weak form with a
+    volume load, models.py:996-997), against the oracle's 'scipy' path -- one Newton step, solution to 1e-8."""
+    from autopdex_b200 import models, seeder, solver, spaces
+    from oracle import solve as osolve
+    from tests import problems
+    p = problems.elasticity_quad(6, mode="lame")
+    prob = osolve.Problem(p["sets"], p["coords"], p["mask"], p["values"])
+    ref, (rsteps, _, rdiv) = osolve.damped_newton(prob, np.zeros(p["mask"].shape))
+    weak = models.hyperelastic_steady_state_weak(models.linear_elastic_strain_energy, lambda x: 100.0, lambda x: 0.3, "plain strain",
+                                                 lambda x: np.asarray([0.0, -1.0]))
+    elem = models.isoparametric_domain_element_galerkin(weak, spaces.fem_iso_line_quad_brick, *seeder.gauss_legendre_nd(dimension=2, order=2))
+    static_settings = {"number of fields": (2,), "assembling mode": ("user element",), "solution structure": ("nodal imposition",),
+                       "model": (elem,), "solver type": "newton", "solver backend": "b200", "solver": krylov,
+                       "type of preconditioner": "jacobi", "verbose": -1}
+    settings = {"dirichlet dofs": p["mask"], "connectivity": (p["sets"][0]["conn"],), "node coordinates": p["coords"],
+                "dirichlet conditions": p["values"]}
+    sol, (steps, res, div) = solver.solver(np.zeros(p["mask"].shape), settings, static_settings, tol=1e-13)
+    assert steps == rsteps == 1 and not div and not rdiv
+    assert np.linalg.norm(np.asarray(sol).ravel() - ref.ravel()) / np.linalg.norm(ref) < 1e-8
+    solver.clear_plan_cache()
