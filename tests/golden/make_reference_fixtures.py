@@ -521,6 +521,19 @@ def case_dae_manager(out):
         assert int(state.num_accepted) == n_steps
         out["dae_manager_%s_q" % scheme] = A(state.history.q["theta"])[:n_steps + 1]
         out["dae_manager_%s_t" % scheme] = A(state.history.t)[:n_steps + 1]
+    # the Newton-iteration step-size controller inside the reference's loop (accepted steps grow by 1 + gamma (target - 1) / target
+    # for this linear system, capped at max_step_size, the last step cut at t_max)
+    st = flax.core.FrozenDict({"dae": dae_fun, "time integrators": {"theta": dae.BackwardEuler()}, "verbose": -1, "implicit diff mode": None})
+    # (default root solver, atol 1e-8: the stand-in's difference-quotient Jacobian is exact to ~1e-10 only, and a tighter
+    # tolerance would cost the reference a second Newton iteration that the exact tangent does not need)
+    mgr = dae.TimeSteppingManager(st, save_policy=dae.SaveAllPolicy(),
+                                  step_size_controller=dae.RootIterationController(target_niters=6, gamma=0.5, max_step_size=0.05))
+    state = mgr.run({"theta": jnp.asarray(q0)}, 0.02, 0.2, 12, {"current time": 0.0, "dirichlet dofs": {"theta": jnp.asarray(mask)},
+                                                                 "dirichlet conditions": {"theta": jnp.asarray(values)}})
+    na = int(state.num_accepted)
+    out["dae_manager_root_controller_t"] = A(state.history.t)[:na + 1]
+    out["dae_manager_root_controller_q"] = A(state.history.q["theta"])[:na + 1]
+    out["dae_manager_root_controller_counts"] = np.array([na, int(state.num_rejected)])
 
 
 def utility_inputs():

@@ -84,6 +84,10 @@ def test_linear_elastic_strain_energy_route_host(fake, tag):
     hl.test_newton_solve_with_the_lame_mode_matches_oracle("cg")
 
 
+def test_root_iteration_controller_against_reference_manager_host(fake):
+    dae_cases.test_root_iteration_controller_inside_the_loop_reproduces_the_reference_manager()
+
+
 def test_save_policies_and_postprocessing_host(fake):
     dae_cases.test_save_policies_and_postprocessing_mirror_the_reference()
 

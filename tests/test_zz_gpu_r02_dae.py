@@ -223,6 +223,29 @@ def test_time_stepping_manager_reproduces_trajectories_of_the_reference_manager(
     solver.clear_plan_cache()
 
 
+def test_root_iteration_controller_inside_the_loop_reproduces_the_reference_manager():
+    """The step-size controller inside the time loop, against the reference's own manager run (fixture case `dae_manager`,
+    RootIterationController(target 6, gamma 0.5, max step 0.05), dt0 = 0.02, t_max = 0.2): the same accepted times (growth
+    by 17/12 per step, capped, the last step cut at t_max) and the same states (the reference run carries the ~1e-10
+    error of the stand-in's difference-quotient Jacobian at its default tolerance)."""
+    import os
+    from autopdex_b200 import dae, solver
+    fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_fixtures.npz"))
+    coords, K, M, F, mask, values, res, settings = _settings(2)
+    static_settings = {"assembling mode": ("user residual",), "model": (res,), "time integrators": {"theta": dae.BackwardEuler()},
+                       "solver backend": "b200", "solver": "cg", "type of preconditioner": "jacobi", "verbose": -1}
+    ctrl = dae.RootIterationController(target_niters=6, gamma=0.5, max_step_size=0.05)
+    out = dae.TimeSteppingManager(static_settings, save_policy=dae.SaveAllPolicy(), step_size_controller=ctrl, tol=1e-14).run(
+        {"theta": 0.3 * np.cos(coords[:, 1])}, 0.02, 0.2, 12, settings)
+    ref_t, ref_q = fix["dae_manager_root_controller_t"], fix["dae_manager_root_controller_q"]
+    assert [out.num_accepted, out.num_rejected] == list(fix["dae_manager_root_controller_counts"])
+    n = out.num_accepted + 1
+    assert np.allclose(out.history.t[:n], ref_t, rtol=1e-13) and np.isnan(out.history.t[n:]).all()
+    for k in range(n):
+        assert np.linalg.norm(out.history.q["theta"][k] - ref_q[k]) / np.linalg.norm(ref_q[k]) < 1e-7, k
+    solver.clear_plan_cache()
+
+
 def test_save_policies_and_postprocessing_mirror_the_reference():
     """dae.SaveAllPolicy / SaveEquidistantPolicy / SaveNothingPolicy (dae.py:1160-1311) and the user data of
     `postprocessing_fun` (dae.py:2140, 2188): pre-allocated arrays of max_steps + 1 rows padded with NaN, equidistant
