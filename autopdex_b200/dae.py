@@ -295,6 +295,10 @@ class TimeSteppingManager:
             raise ValueError("autopdex_b200.dae handles 'solver backend': 'b200' only")
         if root_solver is not None:
             raise ValueError("b200 backend: the Newton iteration runs on the device; root_solver cannot be replaced")
+        if static_settings.get("dae", "call pde") != "call pde":
+            # the reference's ODE / DAE mode: a user-written residual function (dae.py:1975-1978) -- never routed to a host path
+            raise ValueError("b200 backend: static_settings['dae'] must be 'call pde' (the assembled PDE residual); a user-written "
+                             "'dae' function is not supported")
         if step_size_controller is None:
             step_size_controller = ConstantStepSizeController()
         if not isinstance(step_size_controller, ConstantStepSizeController):

@@ -300,6 +300,9 @@ def test_time_stepping_manager_rejections():
             "solver backend": "b200", "solver": "cg", "type of preconditioner": "jacobi"}
     with pytest.raises(ValueError):
         dae.TimeSteppingManager(dict(base, **{"time integrators": {"theta": object()}}))
+    dae.TimeSteppingManager(dict(base, dae="call pde"))                 # the reference's key for the PDE route is accepted
+    with pytest.raises(ValueError, match="call pde"):                   # its ODE mode (a user-written residual) is not
+        dae.TimeSteppingManager(dict(base, dae=lambda q_fun, t, settings: 0.0))
     with pytest.raises(ValueError):
         dae.TimeSteppingManager(dict(base, **{"solver backend": "scipy"}))
     with pytest.raises(ValueError):
